@@ -1,0 +1,178 @@
+/*
+ * tpgan_b200 — C ABI of the B200 (sm_100a) TP-GAN training-step hot path.
+ *
+ * This is the drop-in boundary.  The reference (PandaKenWei/TP-GAN) has no FFI: its hot path is a set of
+ * ATen calls made from ModificationLayer.py / D_and_G_model.py.  Each entry point below names the reference
+ * call site(s) it replaces.  All pointers are raw device pointers owned by the caller (PyTorch's allocator
+ * in the shipped host code); the library never allocates or frees device memory on the data path.
+ * All tensors are fp32, channels-last ("NHWC") views with unit channel stride.  Tensor-core math is TF32
+ * (tcgen05.mma kind::tf32, fp32 accumulation in TMEM).
+ *
+ * Every function returns 0 on success, a negative tpgan_status otherwise; tpgan_last_error() returns a
+ * thread-local message.  `stream` is a cudaStream_t passed as void*.  No call synchronises the device.
+ */
+#ifndef TPGAN_B200_H_
+#define TPGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPGAN_ABI_VERSION 1
+#define TPGAN_API __attribute__((visibility("default")))
+
+enum tpgan_status {
+  TPGAN_OK = 0,
+  TPGAN_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  TPGAN_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed (message has the CUDA error) */
+  TPGAN_ERR_NO_DEVICE = -3,   /* no sm_100 device */
+  TPGAN_ERR_KERNEL_ABORT = -4 /* a kernel's bounded barrier wait expired (see tpgan_kernel_status) */
+};
+
+/* NHWC view: element (n,y,x,c) is ptr[n*sn + y*sh + x*sw + c]; strides in elements. A view may be a channel
+ * slice of a wider buffer (that is how every torch.cat of D_and_G_model.py:100-104,293-324 is eliminated). */
+typedef struct tpgan_view {
+  float* ptr;
+  int64_t sn, sh, sw;
+  int32_t n, h, w, c;
+} tpgan_view;
+
+enum tpgan_conv_kind {
+  TPGAN_CONV_FWD = 0,     /* nn.Conv2d forward          ModificationLayer.py:101 */
+  TPGAN_CONV_DGRAD = 1,   /* its input gradient         (aten::convolution_backward, input half) */
+  TPGAN_DECONV_FWD = 2,   /* nn.ConvTranspose2d forward ModificationLayer.py:189 */
+  TPGAN_DECONV_DGRAD = 3  /* its input gradient */
+};
+
+enum tpgan_epilogue {
+  TPGAN_EPI_LINEAR = 0, /* y = v                                   (activation=None, ModificationLayer.py:154) */
+  TPGAN_EPI_LEAKY = 1,  /* y = v > 0 ? v : slope*v                 (LeakyReLU(0.01) / ReLU with slope 0)      */
+  TPGAN_EPI_MASK = 2    /* y = v * (mask > 0 ? 1 : slope[c])       (activation backward fused into dgrad)     */
+};
+
+/* One convolution-like problem, executed as a multi-tap implicit GEMM on tcgen05 tensor cores:
+ *   v[pixel, co] = sum_taps sum_ci A_tap[pixel, ci] * Wp[tap][co][ci]   (+ bias[co] + add1 + add2), then epilogue.
+ * `in` is the A operand (x for *_FWD, dY for *_DGRAD); `w_packed` must have been produced by
+ * tpgan_pack_weights for the same kind.  Supported: kh==kw in {1..8}, stride 1 or 2 for convs (H, W even when
+ * stride 2), stride 2 or 4 for deconvs with out = stride*in, width <= 128 of the tile space. */
+typedef struct tpgan_conv_args {
+  int32_t kind;
+  int32_t kh, kw, stride, pad;
+  tpgan_view in;
+  tpgan_view out;
+  const float* w_packed; /* [kh*kw + 1][w_rows_pad][w_k_pad], last tap all zero */
+  int32_t w_rows_pad, w_k_pad;
+  const float* bias;      /* [out.c] or NULL */
+  tpgan_view add1, add2;  /* optional addends with out's geometry; ptr NULL = unused */
+  tpgan_view mask;        /* TPGAN_EPI_MASK: tensor whose sign selects 1 or slope */
+  const float* slopes;    /* optional per-out-channel negative slopes (overrides `slope`) */
+  float slope;
+  int32_t epilogue;
+  int32_t round_tf32;     /* round the stored result to tf32 (round-to-nearest) */
+} tpgan_conv_args;
+
+/* Runs 1..4 independent problems in ONE persistent launch (the four local pathways of
+ * D_and_G_model.py:390-393 are one grouped launch per layer). */
+TPGAN_API int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream);
+
+/* Weight gradient, accumulated (+=, fp32 atomics) into the forward-packed layout:
+ *   conv   : dWp[tap][co][ci] += sum_{n,o} dy[n,o,co] * x[n, stride*o + tap - pad, ci]
+ *   deconv : dWp[tap][co][ci] += sum_{n,i} x[n,i,ci]  * dy[n, stride*i + tap - pad, co]
+ * (aten::convolution_backward, weight half). */
+typedef struct tpgan_wgrad_args {
+  int32_t kind; /* TPGAN_CONV_FWD or TPGAN_DECONV_FWD: which layer type the weights belong to */
+  int32_t kh, kw, stride, pad;
+  tpgan_view x;  /* layer input */
+  tpgan_view dy; /* gradient w.r.t. the layer's pre-activation output */
+  float* dw_packed;
+  int32_t w_rows_pad, w_k_pad;
+} tpgan_wgrad_args;
+TPGAN_API int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* stream);
+
+/* Weight (re)packing between the reference's parameter layout and the K-major tensor-core layout.
+ * ref element for (row r, k index k, tap t) is ref[row_map[r]*ref_row_stride + k_map[k]*ref_k_stride + t]
+ * (maps NULL = identity, entry -1 = zero padding).  packed is [taps+1][rows_pad][k_pad] with a zero last tap.
+ *   conv  weight (Cout,Cin,kh,kw), FWD  : rows=Cout (stride Cin*taps), k=Cin (stride taps)
+ *   conv  weight,                  DGRAD: rows=Cin  (stride taps),     k=Cout (stride Cin*taps)
+ *   deconv weight (Cin,Cout,kh,kw), FWD : rows=Cout (stride taps),     k=Cin (stride Cout*taps)
+ *   deconv weight,                 DGRAD: rows=Cin  (stride Cout*taps), k=Cout (stride taps)
+ * Values are rounded to tf32 (rna) when round_tf32 != 0. */
+TPGAN_API int tpgan_pack_weights(const float* ref, float* packed, int32_t taps, int32_t rows, int32_t k, int32_t rows_pad,
+                       int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
+                       const int32_t* k_map, int32_t round_tf32, void* stream);
+/* Inverse scatter of a packed gradient into the reference layout: ref (+)= packed.  accumulate=0 overwrites. */
+TPGAN_API int tpgan_unpack_weights(const float* packed, float* ref, int32_t taps, int32_t rows, int32_t k, int32_t rows_pad,
+                         int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
+                         const int32_t* k_map, int32_t accumulate, void* stream);
+
+/* ---- HBM-bound kernels of the path ------------------------------------------------------------------- */
+
+/* NCHW (reference tensor layout) <-> NHWC view conversion, optional tf32 rounding on the way in. */
+TPGAN_API int tpgan_nchw_to_nhwc(const float* src, tpgan_view dst, int32_t round_tf32, void* stream);
+TPGAN_API int tpgan_nhwc_to_nchw(tpgan_view src, float* dst, void* stream);
+
+/* dst = src * (mask > 0 ? 1 : slope[c])  (standalone activation backward; in place allowed). */
+TPGAN_API int tpgan_act_backward(tpgan_view src, tpgan_view mask, tpgan_view dst, const float* slopes, float slope,
+                       void* stream);
+/* dst (+)= src over a view (accumulate != 0 adds). */
+TPGAN_API int tpgan_view_copy(tpgan_view src, tpgan_view dst, int32_t accumulate, void* stream);
+/* bias gradient: db[c] (+)= sum over pixels of dy[...,c]. */
+TPGAN_API int tpgan_bias_grad(tpgan_view dy, float* db, int32_t accumulate, void* stream);
+
+/* nn.ReflectionPad2d((left,right,top,bottom)) forward / backward (ModificationLayer.py:93). */
+TPGAN_API int tpgan_reflect_pad(tpgan_view src, tpgan_view dst, int32_t left, int32_t top, void* stream);
+TPGAN_API int tpgan_reflect_pad_backward(tpgan_view dpad, tpgan_view dsrc, int32_t left, int32_t top, int32_t accumulate,
+                               void* stream);
+
+/* Landmark-centred patch crop, DataAndDataset.py:10-56 (process()).  img: (N,128,128,C) view, landmarks:
+ * device float[N][5][2] (x,y) as in process(); writes the four patches and the int32 crop boxes
+ * boxes[N][4][4] = (left, upper, right, lower) exactly as passed to PIL.Image.crop.  Out-of-image pixels take
+ * `fill` (PIL zero-fill is -1 after the dataset's *2-1 normalisation). */
+TPGAN_API int tpgan_patch_crop(tpgan_view img, const float* landmarks, tpgan_view left_eye, tpgan_view right_eye,
+                     tpgan_view nose, tpgan_view mouth, int32_t* boxes, float fill, void* stream);
+
+/* LocalFuser, D_and_G_model.py:132-159: out = max over the four zero-padded patches at the fixed offsets.
+ * argmax (optional, uint8 [N][128][128][C]) records the winning source 0..3 (first index wins ties, as
+ * torch.max over the stacked tensor), 4 = the zero padding only.  Backward routes the gradient to it. */
+TPGAN_API int tpgan_local_fuse(tpgan_view left_eye, tpgan_view right_eye, tpgan_view nose, tpgan_view mouth, tpgan_view out,
+                     uint8_t* argmax, void* stream);
+TPGAN_API int tpgan_local_fuse_backward(tpgan_view dout, const uint8_t* argmax, tpgan_view d_left_eye, tpgan_view d_right_eye,
+                              tpgan_view d_nose, tpgan_view d_mouth, int32_t accumulate, void* stream);
+
+/* Fused image losses of the oracle step (config.py:71-82 weights): in one pass over fake and the
+ * 128/64/32 targets (TrainDataset keys img_frontal/img64_frontal/img32_frontal, DataAndDataset.py:206-226)
+ * computes pixel-L1 at 128/64/32 (fake average-pooled), symmetry-L1 at the same three scales and total variation, and
+ * writes d(loss)/d(fake).  sums[8] (device) receives the un-normalised partial sums
+ *   {l1_128, l1_64, l1_32, sym_128, sym_64, sym_32, tv_y, tv_x}.
+ * w[8] are the final coefficients applied to each term's gradient (weight / element count, host-computed). */
+TPGAN_API int tpgan_image_losses(tpgan_view fake, tpgan_view target128, tpgan_view target64, tpgan_view target32,
+                       tpgan_view dfake, const float* w, float* sums, void* stream);
+/* Patch L1 (local pixel loss): sums[0] += sum|a-b| ; da = coeff*sign(a-b). */
+TPGAN_API int tpgan_l1_loss(tpgan_view a, tpgan_view b, tpgan_view da, float coeff, float* sum, void* stream);
+
+/* maxout of nn.MaxPool1d(2,2) over adjacent feature pairs (D_and_G_model.py:214,290) and its backward. */
+TPGAN_API int tpgan_maxout2(const float* x, float* y, int32_t rows, int32_t cols_out, void* stream);
+TPGAN_API int tpgan_maxout2_backward(const float* x, const float* dy, float* dx, int32_t rows, int32_t cols_out, void* stream);
+
+/* Fused Adam over a flat fp32 parameter bucket (torch.optim.Adam semantics incl. L2 weight_decay). */
+TPGAN_API int tpgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* Per-sample gradient-penalty helpers: norms[n] = ||g[n]||_2 ; u = coeff[n] * g. */
+TPGAN_API int tpgan_sample_sqnorm(tpgan_view g, float* sqnorm, void* stream);
+TPGAN_API int tpgan_sample_scale(tpgan_view g, const float* coeff, tpgan_view u, void* stream);
+
+/* ---- diagnostics --------------------------------------------------------------------------------------- */
+TPGAN_API const char* tpgan_last_error(void);
+TPGAN_API int tpgan_abi_version(void);
+/* Non-zero after a kernel aborted a barrier wait (code | cta<<8); reading clears it. */
+TPGAN_API int tpgan_kernel_status(void);
+/* Number of kernels launched by this library since load (monotonic; bench.py reports the delta). */
+TPGAN_API int64_t tpgan_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPGAN_B200_H_ */

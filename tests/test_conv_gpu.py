@@ -1,0 +1,239 @@
+"""GPU parity of the tcgen05 convolution kernels (through the C ABI) against ATen CPU fp32, which is the arithmetic the
+reference's conv()/deconv() factories lower to (ModificationLayer.py:101,189).
+
+Tolerance: TF32 inputs (10-bit mantissa, round-to-nearest) with fp32 accumulation -> norm-wise relative error
+||a-b||_2/||b||_2 <= 1e-3 per op (north-star tolerance for tf32)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _mk(n, c, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand((n, c, h, w), generator=g) * 2 - 1
+
+
+def _act(t, ops):
+    n, c, h, w = t.shape
+    return ops.Act.empty(n, h, w, c).from_nchw(t.cuda(), round_tf32=True)
+
+
+CONV_CASES = [
+    # n, cin, cout, h, w, k, stride, pad
+    (2, 32, 16, 8, 8, 1, 1, 0),
+    (2, 64, 64, 16, 16, 3, 1, 1),
+    (1, 8, 64, 128, 128, 3, 1, 1),
+    (2, 206, 206, 32, 32, 5, 1, 2),
+    (1, 3, 64, 128, 128, 7, 1, 3),
+    (2, 75, 75, 64, 64, 7, 1, 3),
+    (3, 64, 128, 32, 32, 3, 2, 1),
+    (2, 64, 64, 128, 128, 5, 2, 2),
+    (5, 3, 64, 40, 40, 3, 1, 1),
+    (5, 64, 128, 40, 40, 3, 2, 1),
+    (7, 256, 512, 10, 10, 3, 2, 1),
+    (7, 512, 512, 5, 5, 3, 1, 1),
+    (3, 128, 64, 32, 48, 3, 1, 1),
+    (4, 576, 576, 9, 9, 2, 1, 0),
+    (2, 416, 416, 32, 32, 3, 1, 1),
+    (4, 512, 1, 4, 4, 3, 1, 1),
+    (4, 64, 3, 40, 40, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd(case):
+    from tpgan_b200 import ops
+    n, cin, cout, h, w, k, s, p = case
+    x = _mk(n, cin, h, w, 1)
+    wt = _mk(cout, cin, k, k, 2) * (1.0 / (cin * k * k) ** 0.5)
+    b = _mk(1, cout, 1, 1, 3).flatten()
+    ref = F.leaky_relu(F.conv2d(x, wt, b, stride=s, padding=p), 0.01)
+    xa = _act(x, ops)
+    out = ops.Act.empty(n, ref.shape[2], ref.shape[3], cout)
+    pw = ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True)
+    ops.conv2d(ops.CONV_FWD, xa, out, pw, k, s, p, bias=b.cuda(), slope=0.01, epilogue=ops.EPI_LEAKY, round_tf32=True)
+    torch.cuda.synchronize()
+    from tpgan_b200 import _lib
+    assert _lib.kernel_status() == 0
+    err = rel(out.to_nchw(), ref)
+    assert err < TOL, err
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad(case):
+    from tpgan_b200 import ops
+    n, cin, cout, h, w, k, s, p = case
+    if s == 2 and (h % 2 or w % 2):
+        pytest.skip("stride-2 dgrad needs even input")
+    wt = _mk(cout, cin, k, k, 2) * (1.0 / (cout * k * k) ** 0.5)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    dy = _mk(n, cout, ho, wo, 5)
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt, dy, stride=s, padding=p)
+    dya = _act(dy, ops)
+    dx = ops.Act.empty(n, h, w, cin)
+    pw = ops.pack_weights(wt.cuda(), ops.CONV_DGRAD, round_tf32=True)
+    ops.conv2d(ops.CONV_DGRAD, dya, dx, pw, k, s, p, round_tf32=True)
+    torch.cuda.synchronize()
+    err = rel(dx.to_nchw(), ref)
+    assert err < TOL, err
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad(case):
+    from tpgan_b200 import ops
+    n, cin, cout, h, w, k, s, p = case
+    x = _mk(n, cin, h, w, 1)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    dy = _mk(n, cout, ho, wo, 5)
+    ref = torch.nn.grad.conv2d_weight(x, (cout, cin, k, k), dy, stride=s, padding=p)
+    xa, dya = _act(x, ops), _act(dy, ops)
+    dw = ops.alloc_packed(ops.CONV_FWD, (cout, cin, k, k))
+    ops.wgrad(ops.CONV_FWD, xa, dya, dw, k, s, p)
+    got = torch.zeros((cout, cin, k, k), device="cuda")
+    ops.unpack_weights(dw, got, ops.CONV_FWD)
+    torch.cuda.synchronize()
+    err = rel(got, ref)
+    assert err < TOL, err
+
+
+DECONV_CASES = [
+    # n, cin, cout, h, w, k, stride, pad, out_pad
+    (2, 512, 256, 5, 5, 3, 2, 1, 1),
+    (2, 128, 64, 20, 20, 3, 2, 1, 1),
+    (2, 208, 64, 64, 64, 3, 2, 1, 1),
+    (3, 64, 32, 8, 8, 3, 4, 0, 1),
+    (4, 320, 64, 1, 1, 8, 1, 0, 0),
+    (2, 16, 8, 64, 64, 3, 2, 1, 1),
+    (2, 256, 128, 8, 12, 3, 2, 1, 1),
+]
+
+
+def _deconv_as_args(case):
+    n, cin, cout, h, w, k, s, p, op = case
+    return n, cin, cout, h, w, k, s, p, op
+
+
+@pytest.mark.parametrize("case", DECONV_CASES)
+def test_deconv_fwd(case):
+    from tpgan_b200 import ops
+    n, cin, cout, h, w, k, s, p, op = case
+    x = _mk(n, cin, h, w, 1)
+    wt = _mk(cin, cout, k, k, 2) * (1.0 / (cin * k * k) ** 0.5)
+    b = _mk(1, cout, 1, 1, 3).flatten()
+    ref = F.relu(F.conv_transpose2d(x, wt, b, stride=s, padding=p, output_padding=op))
+    xa = _act(x, ops)
+    out = ops.Act.empty(n, ref.shape[2], ref.shape[3], cout)
+    if k == 8:  # deconv_8 (D_and_G_model.py:218): 1x1 input -> a GEMM with N = (r, s, co); run as a 1x1 conv
+        w_lin = wt.permute(2, 3, 1, 0).reshape(k * k * cout, cin, 1, 1).contiguous()
+        b_lin = b.repeat(k * k)
+        pw = ops.pack_weights(w_lin.cuda(), ops.CONV_FWD, round_tf32=True)
+        flat = ops.Act(out.buf.view(n, 1, 1, k * k * cout))
+        ops.conv2d(ops.CONV_FWD, xa, flat, pw, 1, 1, 0, bias=b_lin.cuda(), slope=0.0, epilogue=ops.EPI_LEAKY, round_tf32=True)
+    else:
+        pw = ops.pack_weights(wt.cuda(), ops.DECONV_FWD, round_tf32=True)
+        ops.conv2d(ops.DECONV_FWD, xa, out, pw, k, s, p, bias=b.cuda(), slope=0.0, epilogue=ops.EPI_LEAKY, round_tf32=True)
+    torch.cuda.synchronize()
+    err = rel(out.to_nchw(), ref)
+    assert err < TOL, err
+
+
+@pytest.mark.parametrize("case", [c for c in DECONV_CASES if c[5] != 8])
+def test_deconv_dgrad_wgrad(case):
+    from tpgan_b200 import ops
+    n, cin, cout, h, w, k, s, p, op = case
+    x = _mk(n, cin, h, w, 1).requires_grad_(True)
+    wt = (_mk(cin, cout, k, k, 2) * (1.0 / (cout * k * k) ** 0.5)).requires_grad_(True)
+    y = F.conv_transpose2d(x, wt, None, stride=s, padding=p, output_padding=op)
+    dy = _mk(*y.shape, 7)
+    y.backward(dy)
+    dya, xa = _act(dy, ops), _act(x.detach(), ops)
+    dx = ops.Act.empty(n, h, w, cin)
+    pw = ops.pack_weights(wt.detach().cuda(), ops.DECONV_DGRAD, round_tf32=True)
+    ops.conv2d(ops.DECONV_DGRAD, dya, dx, pw, k, s, p, round_tf32=True)
+    dw = ops.alloc_packed(ops.DECONV_FWD, (cin, cout, k, k))
+    ops.wgrad(ops.DECONV_FWD, xa, dya, dw, k, s, p)
+    got = torch.zeros((cin, cout, k, k), device="cuda")
+    ops.unpack_weights(dw, got, ops.DECONV_FWD)
+    torch.cuda.synchronize()
+    e1, e2 = rel(dx.to_nchw(), x.grad), rel(got, wt.grad)
+    assert e1 < TOL and e2 < TOL, (e1, e2)
+
+
+def test_epilogue_residual_and_mask():
+    """ResidualBlock tail (ModificationLayer.py:300-302): act(conv(h) + x), and the fused activation backward."""
+    from tpgan_b200 import ops
+    n, c, h, w, k = 2, 80, 64, 64, 5
+    hmid, x = _mk(n, c, h, w, 1), _mk(n, c, h, w, 2)
+    wt = _mk(c, c, k, k, 3) * (1.0 / (c * k * k) ** 0.5)
+    b = _mk(1, c, 1, 1, 4).flatten()
+    ref = F.leaky_relu(F.conv2d(hmid, wt, b, padding=2) + x, 0.01)
+    out = ops.Act.empty(n, h, w, c)
+    pw = ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True)
+    ops.conv2d(ops.CONV_FWD, _act(hmid, ops), out, pw, k, 1, 2, bias=b.cuda(), add1=_act(x, ops), slope=0.01,
+               epilogue=ops.EPI_LEAKY, round_tf32=True)
+    torch.cuda.synchronize()
+    assert rel(out.to_nchw(), ref) < TOL
+    # dgrad with two addends and a per-channel mask
+    dy, a1, a2, msrc = _mk(n, c, h, w, 5), _mk(n, c, h, w, 6), _mk(n, c, h, w, 7), _mk(n, c, h, w, 8)
+    slopes = torch.where(torch.arange(c) % 3 == 0, 0.0, 0.01)
+    slopes[5] = 1.0
+    g = torch.nn.grad.conv2d_input((n, c, h, w), wt, dy, padding=2) + a1 + a2
+    refm = torch.where(msrc > 0, g, g * slopes.view(1, c, 1, 1))
+    dx = ops.Act.empty(n, h, w, c)
+    pwd = ops.pack_weights(wt.cuda(), ops.CONV_DGRAD, round_tf32=True)
+    ops.conv2d(ops.CONV_DGRAD, _act(dy, ops), dx, pwd, k, 1, 2, add1=_act(a1, ops), add2=_act(a2, ops),
+               mask=_act(msrc, ops), slopes=slopes.cuda(), epilogue=ops.EPI_MASK, round_tf32=True)
+    torch.cuda.synchronize()
+    assert rel(dx.to_nchw(), refm) < TOL
+
+
+def test_concat_slice_io():
+    """Reads a channel slice of a wide buffer and writes into a slice of another (torch.cat elimination)."""
+    from tpgan_b200 import ops
+    n, h, w = 2, 32, 32
+    wide_in = ops.Act.empty(n, h, w, 160)
+    x = _mk(n, 128, h, w, 1)
+    wide_in.slice(32, 128).from_nchw(x.cuda())
+    wt = _mk(64, 128, 3, 3, 2) * 0.03
+    ref = F.conv2d(x, wt, None, padding=1)
+    wide_out = ops.Act.empty(n, h, w, 208)
+    pw = ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True)
+    ops.conv2d(ops.CONV_FWD, wide_in.slice(32, 128), wide_out.slice(140, 64), pw, 3, 1, 1, round_tf32=True)
+    torch.cuda.synchronize()
+    assert rel(wide_out.slice(140, 64).to_nchw(), ref) < TOL
+    assert float(wide_out.slice(0, 140).to_nchw().abs().max()) == 0.0
+    assert float(wide_out.slice(204, 4).to_nchw().abs().max()) == 0.0
+
+
+def test_grouped_local_pathway_shapes():
+    """Four problems with the local-pathway patch sizes in one launch (D_and_G_model.py:390-393)."""
+    from tpgan_b200 import ops
+    shapes = [(40, 40), (40, 40), (32, 40), (32, 48)]
+    n, cin, cout = 3, 64, 64
+    args, refs, outs = [], [], []
+    keep = []
+    for i, (h, w) in enumerate(shapes):
+        x = _mk(n, cin, h, w, 10 + i)
+        wt = _mk(cout, cin, 3, 3, 20 + i) * 0.04
+        b = _mk(1, cout, 1, 1, 30 + i).flatten()
+        refs.append(F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.01))
+        out = ops.Act.empty(n, h, w, cout)
+        pw = ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True)
+        xa, bc = _act(x, ops), b.cuda()
+        keep += [xa, pw, bc]
+        args.append(ops.conv_args(ops.CONV_FWD, xa, out, pw, 3, 1, 1, bias=bc, slope=0.01, epilogue=ops.EPI_LEAKY,
+                                  round_tf32=True))
+        outs.append(out)
+    ops.conv2d_grouped(args)
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert rel(o.to_nchw(), r) < TOL

@@ -1,0 +1,451 @@
+// C-ABI entry points for the tensor-core convolution kernels: host-side planning (tap lists, parity planes, tile
+// geometry, TMA descriptors) and launch.  See include/tpgan_b200.h for the contract of every function.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/tpgan_b200.h"
+#include "host_common.h"
+#include "kparams.h"
+
+namespace tpg {
+
+template <class Params>
+__global__ void tapgemm_kernel(const __grid_constant__ Params P, int* status);
+template <class Params>
+__global__ void wgrad_kernel(const __grid_constant__ Params P, int* status);
+
+// ------------------------------------------------------------------------------------------------ error state
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------------ device state
+struct DeviceState {
+  bool ready = false;
+  int sm_count = 0;
+  int max_smem = 0;
+  int* status_dev = nullptr;   // device alias of the mapped host status word
+  int* status_host = nullptr;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+static DeviceState g_dev;
+static std::mutex g_mu;
+
+static int ensure_device() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev.ready) return 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_NO_DEVICE, "cudaGetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_NO_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return set_error(TPGAN_ERR_NO_DEVICE, "tpgan_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
+  g_dev.sm_count = prop.multiProcessorCount;
+  g_dev.max_smem = (int)prop.sharedMemPerBlockOptin;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+    return set_error(TPGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+  g_dev.encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  e = cudaHostAlloc((void**)&g_dev.status_host, sizeof(int), cudaHostAllocMapped);
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e));
+  *g_dev.status_host = 0;
+  e = cudaHostGetDevicePointer((void**)&g_dev.status_dev, g_dev.status_host, 0);
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e));
+  g_dev.ready = true;
+  return 0;
+}
+
+int device_sm_count() { return g_dev.sm_count; }
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+// 4D NHWC plane: dims {C, W, H, N}; step = parity-plane subsampling factor along H and W.
+static int encode_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int N, long long sw, long long sh,
+                       long long sn, int bw, int bh, int bn, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    return set_error(TPGAN_ERR_INVALID, "TMA operand must be 16-byte aligned (ptr %p, strides %lld %lld %lld elements)",
+                     (const void*)base, sw, sh, sn);
+  if (bw > 256 || bh > 256 || bn > 256 || bw < 1 || bh < 1 || bn < 1)
+    return set_error(TPGAN_ERR_INVALID, "bad TMA box %d %d %d", bw, bh, bn);
+  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(TPGAN_ERR_CUDA, "cuTensorMapEncodeTiled(4D C=%d W=%d H=%d N=%d box %d,%d,%d) failed: %d", C, W, H, N,
+                     bw, bh, bn, (int)r);
+  return 0;
+}
+
+static int encode_weights(CUtensorMap* m, const float* base, int k_pad, int rows_pad, int taps, int block_n) {
+  cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)rows_pad, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)k_pad * 4, (cuuint64_t)k_pad * rows_pad * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)block_n, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((uintptr_t)base & 15) return set_error(TPGAN_ERR_INVALID, "packed weights must be 16-byte aligned");
+  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(TPGAN_ERR_CUDA, "cuTensorMapEncodeTiled(weights k=%d rows=%d taps=%d bn=%d) failed: %d", k_pad,
+                     rows_pad, taps, block_n, (int)r);
+  return 0;
+}
+
+static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int pos_mod(int a, int b) { return a - floor_div(a, b) * b; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static DevView to_dev(const tpgan_view& v) { return DevView{v.ptr, v.sn, v.sh, v.sw}; }
+static bool view_vec_ok(const tpgan_view& v) {
+  return v.ptr == nullptr || (((uintptr_t)v.ptr & 15) == 0 && v.sn % 4 == 0 && v.sh % 4 == 0 && v.sw % 4 == 0);
+}
+
+// Parity planes of `t` for sampling stride s: plane (a,b) holds pixels (s*i + a, s*j + b).
+static int encode_planes(CUtensorMap* maps, const tpgan_view& t, int s, int bw, int bh, int bn,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  for (int a = 0; a < s; ++a)
+    for (int b = 0; b < s; ++b) {
+      int Hp = (t.h - a + s - 1) / s, Wp = (t.w - b + s - 1) / s;
+      if (Hp <= 0 || Wp <= 0) return set_error(TPGAN_ERR_INVALID, "empty parity plane");
+      int rc = encode_nhwc(&maps[a * s + b], t.ptr + a * t.sh + b * t.sw, t.c, Wp, Hp, t.n, t.sw * s, t.sh * s, t.sn,
+                           bw, bh, bn, swz);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ conv planning
+static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G) {
+  memset(&G, 0, sizeof(G));
+  const int k = a.kh;
+  if (a.kh != a.kw || k < 1 || k > 8) return set_error(TPGAN_ERR_INVALID, "kernel %dx%d unsupported", a.kh, a.kw);
+  const int s = a.stride, p = a.pad;
+  if (s != 1 && s != 2 && s != 4) return set_error(TPGAN_ERR_INVALID, "stride %d unsupported", s);
+  if (a.in.n != a.out.n) return set_error(TPGAN_ERR_INVALID, "batch mismatch");
+  const bool gather = (a.kind == TPGAN_CONV_FWD || a.kind == TPGAN_DECONV_DGRAD);
+  const bool phased = (a.kind == TPGAN_CONV_DGRAD || a.kind == TPGAN_DECONV_FWD);
+  if (!gather && !phased) return set_error(TPGAN_ERR_INVALID, "bad kind %d", a.kind);
+  const int Kc = a.in.c;
+  const int taps = k * k;
+  if (a.w_k_pad % 32 || a.w_k_pad < Kc || a.w_rows_pad % 16 || a.w_rows_pad < a.out.c)
+    return set_error(TPGAN_ERR_INVALID, "packed weight dims (%d x %d) do not cover K=%d N=%d", a.w_rows_pad, a.w_k_pad, Kc,
+                     a.out.c);
+
+  G.Nimg = a.in.n;
+  int ntap = 0;
+  if (gather) {
+    // out[o] = sum_r in[s*o + r - p] * w[r]
+    const int Ho = (a.in.h + 2 * p - k) / s + 1, Wo = (a.in.w + 2 * p - k) / s + 1;
+    if (a.kind == TPGAN_CONV_FWD && (Ho != a.out.h || Wo != a.out.w))
+      return set_error(TPGAN_ERR_INVALID, "conv output %dx%d expected %dx%d", a.out.h, a.out.w, Ho, Wo);
+    G.Hm = a.out.h;
+    G.Wm = a.out.w;
+    G.out_sy = G.out_sx = 1;
+    G.n_phases = 1;
+    G.phase[0].tap_begin = 0;
+    G.phase[0].oy = G.phase[0].ox = 0;
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        int ey = r - p, ex = c - p;
+        TapDesc t;
+        t.plane = (int8_t)(pos_mod(ey, s) * s + pos_mod(ex, s));
+        t.dy = (int8_t)floor_div(ey, s);
+        t.dx = (int8_t)floor_div(ex, s);
+        t.wtap = (uint8_t)(r * k + c);
+        G.taps[ntap++] = t;
+      }
+    G.phase[0].tap_count = (short)ntap;
+  } else {
+    // out[s*m + a] = sum_{r : (a + p - r) % s == 0} in[m + (a + p - r)/s] * w[r]
+    if (a.out.h % s || a.out.w % s) return set_error(TPGAN_ERR_INVALID, "output %dx%d not a multiple of stride %d", a.out.h, a.out.w, s);
+    G.Hm = a.out.h / s;
+    G.Wm = a.out.w / s;
+    G.out_sy = G.out_sx = s;
+    G.n_phases = s * s;
+    for (int pa = 0; pa < s; ++pa)
+      for (int pb = 0; pb < s; ++pb) {
+        PhaseDesc& ph = G.phase[pa * s + pb];
+        ph.tap_begin = (short)ntap;
+        ph.oy = (short)pa;
+        ph.ox = (short)pb;
+        for (int r = 0; r < k; ++r) {
+          if (pos_mod(pa + p - r, s)) continue;
+          for (int c = 0; c < k; ++c) {
+            if (pos_mod(pb + p - c, s)) continue;
+            if (ntap >= kMaxTaps) return set_error(TPGAN_ERR_INVALID, "too many taps");
+            TapDesc t;
+            t.plane = 0;
+            t.dy = (int8_t)((pa + p - r) / s);
+            t.dx = (int8_t)((pb + p - c) / s);
+            t.wtap = (uint8_t)(r * k + c);
+            G.taps[ntap++] = t;
+          }
+        }
+        if (ntap == ph.tap_begin) {  // hole phase (stride > kernel): bias only, through the all-zero tap
+          TapDesc t;
+          t.plane = 0; t.dy = 0; t.dx = 0; t.wtap = (uint8_t)taps;
+          G.taps[ntap++] = t;
+        }
+        ph.tap_count = (short)(ntap - ph.tap_begin);
+      }
+  }
+  if (G.Wm > 128) return set_error(TPGAN_ERR_INVALID, "tile-space width %d > 128 unsupported", G.Wm);
+  G.bw = G.Wm;
+  G.bh = std::min(G.Hm, 128 / G.bw);
+  G.bn = (G.bh == G.Hm) ? std::max(1, std::min(G.Nimg, 128 / (G.bw * G.bh))) : 1;
+  G.tiles_h = ceil_div(G.Hm, G.bh);
+  G.m_tiles = G.tiles_h * ceil_div(G.Nimg, G.bn);
+  G.n_tiles = ceil_div(a.w_rows_pad, 256);
+  G.block_n = ceil_div(ceil_div(a.w_rows_pad, G.n_tiles), 16) * 16;
+  G.kchunks = ceil_div(Kc, 32);
+  G.last_mmas = ceil_div(Kc - 32 * (G.kchunks - 1), 8);
+  G.tile_count = G.n_phases * G.m_tiles * G.n_tiles;
+
+  int rc = gather ? encode_planes(G.amap, a.in, s, G.bw, G.bh, G.bn) : encode_planes(G.amap, a.in, 1, G.bw, G.bh, G.bn);
+  if (rc) return rc;
+  rc = encode_weights(&G.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, taps + 1, G.block_n);
+  if (rc) return rc;
+
+  G.out = to_dev(a.out);
+  G.add1 = to_dev(a.add1);
+  G.add2 = to_dev(a.add2);
+  G.mask = to_dev(a.mask);
+  G.bias = a.bias;
+  G.slopes = a.slopes;
+  G.Hout = a.out.h;
+  G.Wout = a.out.w;
+  G.cout_valid = a.out.c;
+  G.epilogue = a.epilogue;
+  G.slope = a.slope;
+  G.round_tf32 = a.round_tf32;
+  if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) return set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view");
+  G.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask);
+  return 0;
+}
+
+template <class Params>
+static int launch_tapgemm(Params& P, cudaStream_t st) {
+  int bmax = 0;
+  int tiles = 0;
+  for (int i = 0; i < P.ngroups; ++i) {
+    P.g[i].tile_begin = tiles;
+    tiles += P.g[i].tile_count;
+    bmax = std::max(bmax, P.g[i].block_n * 128);
+  }
+  P.total_tiles = tiles;
+  P.b_stage_bytes = bmax;
+  const int stage_bytes = 16384 + bmax;
+  const int budget = g_dev.max_smem - 1024 - 256;
+  P.stages = std::min(kMaxStages, budget / stage_bytes);
+  if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "not enough shared memory for 2 stages");
+  const int smem = P.stages * stage_bytes + 1024;
+  static std::once_flag once;
+  auto kern = tapgemm_kernel<Params>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int grid = std::min(tiles, g_dev.sm_count);
+  kern<<<grid, 256, smem, st>>>(P, g_dev.status_dev);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad planning
+static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G) {
+  memset(&G, 0, sizeof(G));
+  const int k = a.kh;
+  if (a.kh != a.kw || k < 1 || k > 8) return set_error(TPGAN_ERR_INVALID, "kernel %dx%d unsupported", a.kh, a.kw);
+  const int s = a.stride, p = a.pad;
+  if (s != 1 && s != 2 && s != 4) return set_error(TPGAN_ERR_INVALID, "stride %d unsupported", s);
+  if (a.x.n != a.dy.n) return set_error(TPGAN_ERR_INVALID, "batch mismatch");
+  // conv  : P = dy (Cout), Q = x planes  (Cin)  -> dw[tap][co][ci], m=co n=ci
+  // deconv: P = x  (Cin),  Q = dy planes (Cout) -> dw[tap][co][ci], m=ci n=co (transposed write)
+  const bool is_conv = (a.kind == TPGAN_CONV_FWD);
+  if (!is_conv && a.kind != TPGAN_DECONV_FWD) return set_error(TPGAN_ERR_INVALID, "bad wgrad kind %d", a.kind);
+  const tpgan_view& Pt = is_conv ? a.dy : a.x;
+  const tpgan_view& Qt = is_conv ? a.x : a.dy;
+  G.transpose_out = is_conv ? 0 : 1;
+  G.m_valid = Pt.c;
+  G.n_valid = Qt.c;
+  const int cout = a.dy.c, cin = a.x.c;
+  if (a.w_rows_pad < cout || a.w_k_pad < cin) return set_error(TPGAN_ERR_INVALID, "packed dw too small");
+  G.rows_pad = a.w_rows_pad;
+  G.k_pad = a.w_k_pad;
+  G.dw = a.dw_packed;
+  G.Hp = Pt.h;
+  G.Wp = Pt.w;
+  G.Nimg = Pt.n;
+  // pixel boxes of ~32 pixels
+  G.bw = (G.Wp <= 48) ? G.Wp : 32;
+  G.bh = std::max(1, std::min(G.Hp, 32 / G.bw));
+  G.bn = (G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, 32 / (G.bw * G.bh))) : 1;
+  G.kp = ceil_div(G.bw * G.bh * G.bn, 8) * 8;
+  G.tiles_w = ceil_div(G.Wp, G.bw);
+  G.tiles_h = ceil_div(G.Hp, G.bh);
+  G.chunks = G.tiles_w * G.tiles_h * ceil_div(G.Nimg, G.bn);
+  G.m_tiles = ceil_div(G.m_valid, 128);
+  const int nch_total = ceil_div(G.n_valid, 32);
+  G.n_tiles = ceil_div(nch_total, 8);
+  G.block_n = ceil_div(nch_total, G.n_tiles) * 32;
+  G.ntaps = k * k;
+  int nt = 0;
+  for (int r = 0; r < k; ++r)
+    for (int c = 0; c < k; ++c) {
+      int ey = r - p, ex = c - p;
+      TapDesc t;
+      t.plane = (int8_t)(pos_mod(ey, s) * s + pos_mod(ex, s));
+      t.dy = (int8_t)floor_div(ey, s);
+      t.dx = (int8_t)floor_div(ex, s);
+      t.wtap = (uint8_t)(r * k + c);
+      G.taps[nt++] = t;
+    }
+  // MN-major tf32 operands need the 32B-atom flavour of the 128B swizzle
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.bw, G.bh, G.bn, swz);
+  if (rc) return rc;
+  rc = encode_planes(G.qmap, Qt, s, G.bw, G.bh, G.bn, swz);
+  if (rc) return rc;
+  return 0;
+}
+
+template <class Params>
+static int launch_wgrad(Params& P, cudaStream_t st) {
+  int amax = 0, bmax = 0, base_units = 0;
+  for (int i = 0; i < P.ngroups; ++i) {
+    WgradGroup& G = P.g[i];
+    amax = std::max(amax, 4 * G.kp * 128);
+    bmax = std::max(bmax, (G.block_n / 32) * G.kp * 128);
+    base_units += G.ntaps * G.m_tiles * G.n_tiles;
+  }
+  // split the pixel reduction so that ~2 waves of units cover the SMs
+  int units = 0;
+  for (int i = 0; i < P.ngroups; ++i) {
+    WgradGroup& G = P.g[i];
+    int want = std::max(1, ceil_div(2 * g_dev.sm_count, std::max(1, base_units)));
+    int ks = std::min(want, G.chunks);
+    G.chunks_per_split = ceil_div(G.chunks, ks);
+    G.ksplits = ceil_div(G.chunks, G.chunks_per_split);
+    G.unit_begin = units;
+    G.unit_count = G.ntaps * G.m_tiles * G.n_tiles * G.ksplits;
+    units += G.unit_count;
+  }
+  P.total_units = units;
+  P.a_stage_bytes = amax;
+  P.b_stage_bytes = bmax;
+  const int stage_bytes = amax + bmax;
+  const int budget = g_dev.max_smem - 1024 - 256;
+  P.stages = std::min(kMaxStages, budget / stage_bytes);
+  if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "wgrad: not enough shared memory for 2 stages (%d B/stage)", stage_bytes);
+  const int smem = P.stages * stage_bytes + 1024;
+  auto kern = wgrad_kernel<Params>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int grid = std::min(units, g_dev.sm_count);
+  kern<<<grid, 256, smem, st>>>(P, g_dev.status_dev);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // namespace tpg
+
+using namespace tpg;
+
+extern "C" {
+
+int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
+  if (!groups || ngroups < 1 || ngroups > kMaxGroups) return set_error(TPGAN_ERR_INVALID, "ngroups must be 1..%d", kMaxGroups);
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ngroups == 1) {
+    static thread_local TapGemmParams1 P;
+    P.ngroups = 1;
+    rc = plan_group(groups[0], P.g[0]);
+    if (rc) return rc;
+    return launch_tapgemm(P, st);
+  }
+  static thread_local TapGemmParams P;
+  P.ngroups = ngroups;
+  for (int i = 0; i < ngroups; ++i) {
+    rc = plan_group(groups[i], P.g[i]);
+    if (rc) return rc;
+  }
+  return launch_tapgemm(P, st);
+}
+
+int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* stream) {
+  if (!groups || ngroups < 1 || ngroups > kMaxGroups) return set_error(TPGAN_ERR_INVALID, "ngroups must be 1..%d", kMaxGroups);
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ngroups == 1) {
+    static thread_local WgradParams1 P;
+    P.ngroups = 1;
+    rc = plan_wgrad(groups[0], P.g[0]);
+    if (rc) return rc;
+    return launch_wgrad(P, st);
+  }
+  static thread_local WgradParams P;
+  P.ngroups = ngroups;
+  bool uniform = true;
+  for (int i = 0; i < ngroups; ++i) {
+    rc = plan_wgrad(groups[i], P.g[i]);
+    if (rc) return rc;
+    const WgradGroup& G = P.g[i];
+    // the zero-padded K rows of the smem ring stay zero only if every box fills its rows or all boxes are alike
+    if ((G.bw * G.bh * G.bn) % 8) uniform = false;
+  }
+  if (!uniform) {
+    bool same = true;
+    for (int i = 1; i < ngroups; ++i)
+      same = same && P.g[i].bw == P.g[0].bw && P.g[i].bh == P.g[0].bh && P.g[i].bn == P.g[0].bn &&
+             P.g[i].block_n == P.g[0].block_n;
+    if (!same) {
+      for (int i = 0; i < ngroups; ++i) {
+        rc = tpgan_conv2d_wgrad(groups + i, 1, stream);
+        if (rc) return rc;
+      }
+      return 0;
+    }
+  }
+  return launch_wgrad(P, st);
+}
+
+const char* tpgan_last_error(void) { return g_err; }
+int tpgan_abi_version(void) { return TPGAN_ABI_VERSION; }
+int tpgan_kernel_status(void) {
+  if (!g_dev.status_host) return 0;
+  int v = *(volatile int*)g_dev.status_host;
+  if (v) *(volatile int*)g_dev.status_host = 0;
+  return v;
+}
+int64_t tpgan_launch_count(void) { return (int64_t)g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Kernel-parameter structures shared by the host planner (api.cu) and the tcgen05 kernels.
+// They are passed by value as __grid_constant__ kernel parameters, so the TMA descriptors they hold live in
+// the parameter bank and can be handed to cp.async.bulk.tensor directly.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace tpg {
+
+constexpr int kMaxTaps = 64;    // 7x7 conv = 49, 8x8 deconv-as-GEMM is a 1-tap problem
+constexpr int kMaxPhases = 16;  // stride-4 deconv: 4x4 output phases
+constexpr int kMaxPlanes = 16;  // stride-4 gather: 4x4 input parity planes
+constexpr int kMaxGroups = 4;   // the four local pathways
+constexpr int kMaxStages = 8;
+
+struct TapDesc {
+  int8_t plane;  // which A tensor map (parity plane)
+  int8_t dy, dx; // box origin offset in the plane
+  uint8_t wtap;  // weight tap slice in the packed tensor
+};
+
+struct DevView {
+  float* ptr;
+  long long sn, sh, sw;
+};
+
+struct PhaseDesc {
+  short tap_begin, tap_count;
+  short oy, ox;  // output pixel = (y*out_sy + oy, x*out_sx + ox)
+};
+
+// ---------------------------------------------------------------- forward-type multi-tap GEMM
+struct TapGemmGroup {
+  CUtensorMap amap[kMaxPlanes];  // 4D {C, W, H, N} fp32, box {32, bw, bh, bn}, 128B swizzle
+  CUtensorMap bmap;              // 3D {k_pad, rows_pad, taps+1}, box {32, block_n, 1}
+  int Hm, Wm, Nimg;              // tile space (pixels enumerated by the M dimension)
+  int bw, bh, bn;                // pixels of one 128-row tile = bw*bh*bn (<= 128)
+  int tiles_h, m_tiles;          // ceil(Hm/bh), tiles_h * ceil(Nimg/bn)
+  int n_tiles, block_n;
+  int kchunks, last_mmas;        // K = C of the A operand, in 32-float chunks; MMAs (K=8) in the last chunk
+  int n_phases;
+  int tile_begin, tile_count;    // this group's slice of the persistent tile list
+  PhaseDesc phase[kMaxPhases];
+  TapDesc taps[kMaxTaps];
+  // epilogue
+  DevView out, add1, add2, mask;
+  const float* bias;
+  const float* slopes;
+  int out_sy, out_sx, Hout, Wout;
+  int cout_valid;
+  int epilogue;
+  float slope;
+  int round_tf32;
+  int vec_ok;
+};
+
+struct TapGemmParams {
+  int ngroups;
+  int total_tiles;
+  int stages;
+  int b_stage_bytes;  // max over groups of block_n*128
+  TapGemmGroup g[kMaxGroups];
+};
+
+struct TapGemmParams1 {  // single-group variant (keeps the parameter block small for the common launch)
+  int ngroups;
+  int total_tiles;
+  int stages;
+  int b_stage_bytes;
+  TapGemmGroup g[1];
+};
+
+// ---------------------------------------------------------------- weight-gradient GEMM
+// D[m = channel of P][n = channel of Q] (per tap) = sum over pixels P[pix, m] * Qtap[pix, n]
+struct WgradGroup {
+  CUtensorMap pmap;              // unshifted tensor, 4D {C, W, H, N}, box {32, bw, bh, bn}
+  CUtensorMap qmap[kMaxPlanes];  // shifted tensor planes, same box
+  int Hp, Wp, Nimg;
+  int bw, bh, bn, kp;            // kp = K rows per stage (pixels rounded up to 8)
+  int tiles_w, tiles_h, chunks;  // pixel boxes: tiles_w * tiles_h * ceil(Nimg/bn)
+  int m_tiles, n_tiles, block_n; // M tile = 128 P-channels, N tile = block_n Q-channels
+  int ksplits, chunks_per_split;
+  int ntaps;
+  int unit_begin, unit_count;    // units = taps * m_tiles * n_tiles * ksplits
+  TapDesc taps[kMaxTaps];
+  float* dw;                     // [taps+1][rows_pad][k_pad]
+  int rows_pad, k_pad;
+  int transpose_out;             // 0: dw[tap][m][n]   1: dw[tap][n][m]
+  int m_valid, n_valid;          // bounds in the dw tensor (rows_pad/k_pad by orientation)
+};
+
+struct WgradParams {
+  int ngroups;
+  int total_units;
+  int stages;
+  int a_stage_bytes, b_stage_bytes;
+  WgradGroup g[kMaxGroups];
+};
+struct WgradParams1 {
+  int ngroups;
+  int total_units;
+  int stages;
+  int a_stage_bytes, b_stage_bytes;
+  WgradGroup g[1];
+};
+
+}  // namespace tpg

@@ -1,0 +1,691 @@
+// HBM-bound kernels of the TP-GAN hot path: weight (un)packing, layout conversion, activation backward, bias
+// gradient, reflection padding, landmark patch crop, LocalFuser max-stitch, fused losses, maxout, Adam.
+// All tensors are fp32 NHWC views (unit channel stride).  Grid-stride loops, grids sized from the SM count.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+#include <stdint.h>
+
+#include "../../include/tpgan_b200.h"
+#include "common.cuh"
+#include "host_common.h"
+
+namespace tpg {
+
+static inline int grid_for(long long n, int block, int per_sm = 8) {
+  long long want = (n + block - 1) / block;
+  long long cap = (long long)std::max(1, device_sm_count()) * per_sm;
+  if (device_sm_count() == 0) cap = 148 * per_sm;
+  return (int)std::max(1ll, std::min(want, cap));
+}
+
+struct V {  // device copy of tpgan_view
+  float* p;
+  long long sn, sh, sw;
+  int n, h, w, c;
+};
+static inline V dv(const tpgan_view& v) { return V{v.ptr, v.sn, v.sh, v.sw, v.n, v.h, v.w, v.c}; }
+__device__ __forceinline__ long long voff(const V& v, int n, int y, int x) {
+  return (long long)n * v.sn + (long long)y * v.sh + (long long)x * v.sw;
+}
+
+// ------------------------------------------------------------------------------------------------ pack / unpack
+__global__ void pack_kernel(const float* __restrict__ ref, float* __restrict__ packed, int taps, int rows, int k,
+                            int rows_pad, int k_pad, long long rs, long long ks, const int* __restrict__ row_map,
+                            const int* __restrict__ k_map, int round) {
+  const long long total = (long long)(taps + 1) * rows_pad * k_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int kk = (int)(i % k_pad);
+    long long r2 = i / k_pad;
+    int rr = (int)(r2 % rows_pad);
+    int t = (int)(r2 / rows_pad);
+    float v = 0.f;
+    if (t < taps && rr < rows && kk < k) {
+      int rref = row_map ? row_map[rr] : rr;
+      int kref = k_map ? k_map[kk] : kk;
+      if (rref >= 0 && kref >= 0) v = ref[rref * rs + kref * ks + t];
+    }
+    packed[i] = round ? round_tf32(v) : v;
+  }
+}
+
+__global__ void unpack_kernel(const float* __restrict__ packed, float* __restrict__ ref, int taps, int rows, int k,
+                              int rows_pad, int k_pad, long long rs, long long ks, const int* __restrict__ row_map,
+                              const int* __restrict__ k_map, int accumulate) {
+  const long long total = (long long)taps * rows * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int kk = (int)(i % k);
+    long long r2 = i / k;
+    int rr = (int)(r2 % rows);
+    int t = (int)(r2 / rows);
+    int rref = row_map ? row_map[rr] : rr;
+    int kref = k_map ? k_map[kk] : kk;
+    if (rref < 0 || kref < 0) continue;
+    float v = packed[((long long)t * rows_pad + rr) * k_pad + kk];
+    float* d = ref + rref * rs + kref * ks + t;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, V dst, int round) {
+  const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dst.c);
+    long long r = i / dst.c;
+    int x = (int)(r % dst.w);
+    r /= dst.w;
+    int y = (int)(r % dst.h);
+    int n = (int)(r / dst.h);
+    float v = src[(((long long)n * dst.c + c) * dst.h + y) * dst.w + x];
+    dst.p[voff(dst, n, y, x) + c] = round ? round_tf32(v) : v;
+  }
+}
+__global__ void nhwc_to_nchw_kernel(V src, float* __restrict__ dst) {
+  const long long total = (long long)src.n * src.h * src.w * src.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % src.w);
+    long long r = i / src.w;
+    int y = (int)(r % src.h);
+    r /= src.h;
+    int c = (int)(r % src.c);
+    int n = (int)(r / src.c);
+    dst[i] = src.p[voff(src, n, y, x) + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void act_backward_kernel(V src, V mask, V dst, const float* __restrict__ slopes, float slope) {
+  const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dst.c);
+    long long r = i / dst.c;
+    int x = (int)(r % dst.w);
+    r /= dst.w;
+    int y = (int)(r % dst.h);
+    int n = (int)(r / dst.h);
+    float g = src.p[voff(src, n, y, x) + c];
+    float m = mask.p[voff(mask, n, y, x) + c];
+    float s = slopes ? slopes[c] : slope;
+    dst.p[voff(dst, n, y, x) + c] = m > 0.f ? g : g * s;
+  }
+}
+__global__ void view_copy_kernel(V src, V dst, int accumulate) {
+  const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dst.c);
+    long long r = i / dst.c;
+    int x = (int)(r % dst.w);
+    r /= dst.w;
+    int y = (int)(r % dst.h);
+    int n = (int)(r / dst.h);
+    float v = src.p[voff(src, n, y, x) + c];
+    float* d = dst.p + voff(dst, n, y, x) + c;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+
+// db[c] (+)= sum_pixels dy[pix, c].  Block = 256 threads = 8 pixel lanes x 32 channel lanes; coalesced along c.
+__global__ void bias_grad_kernel(V dy, float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cl;
+  const long long npix = (long long)dy.n * dy.h * dy.w;
+  float acc = 0.f;
+  if (c < dy.c) {
+    for (long long pix = (long long)blockIdx.x * 8 + pl; pix < npix; pix += (long long)gridDim.x * 8) {
+      int x = (int)(pix % dy.w);
+      long long r = pix / dy.w;
+      int y = (int)(r % dy.h);
+      int n = (int)(r / dy.h);
+      acc += dy.p[voff(dy, n, y, x) + c];
+    }
+  }
+  red[pl][cl] = acc;
+  __syncthreads();
+  if (pl == 0 && c < dy.c) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][cl];
+    atomicAdd(db + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ reflection pad
+__device__ __forceinline__ int reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+__global__ void reflect_pad_kernel(V src, V dst, int left, int top) {
+  const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dst.c);
+    long long r = i / dst.c;
+    int x = (int)(r % dst.w);
+    r /= dst.w;
+    int y = (int)(r % dst.h);
+    int n = (int)(r / dst.h);
+    int sy = reflect(y - top, src.h), sx = reflect(x - left, src.w);
+    dst.p[voff(dst, n, y, x) + c] = src.p[voff(src, n, sy, sx) + c];
+  }
+}
+// gather form of the backward: each source pixel sums the padded pixels that mirror onto it
+__global__ void reflect_pad_backward_kernel(V dpad, V dsrc, int left, int top, int accumulate) {
+  const long long total = (long long)dsrc.n * dsrc.h * dsrc.w * dsrc.c;
+  const int right = dpad.w - dsrc.w - left, bottom = dpad.h - dsrc.h - top;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dsrc.c);
+    long long r = i / dsrc.c;
+    int x = (int)(r % dsrc.w);
+    r /= dsrc.w;
+    int y = (int)(r % dsrc.h);
+    int n = (int)(r / dsrc.h);
+    // candidate padded coordinates mapping to (y, x): direct, top/left mirror, bottom/right mirror
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = y + top;
+    if (y >= 1 && y <= top) ys[ny++] = top - y;
+    if (y <= dsrc.h - 2 && y >= dsrc.h - 1 - bottom) ys[ny++] = top + 2 * (dsrc.h - 1) - y;
+    xs[nx++] = x + left;
+    if (x >= 1 && x <= left) xs[nx++] = left - x;
+    if (x <= dsrc.w - 2 && x >= dsrc.w - 1 - right) xs[nx++] = left + 2 * (dsrc.w - 1) - x;
+    float s = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b) s += dpad.p[voff(dpad, n, ys[a], xs[b]) + c];
+    float* d = dsrc.p + voff(dsrc, n, y, x) + c;
+    *d = accumulate ? (*d + s) : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ patch crop
+struct CropOut {
+  V v[4];
+};
+// one warp per (image, part, patch row): lanes sweep (x, c) contiguously
+__global__ void patch_crop_kernel(V img, const float* __restrict__ lm, CropOut out, int* __restrict__ boxes, float fill) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pw[4] = {40, 40, 40, 48}, phh[4] = {40, 40, 32, 32};
+  int rows_total = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rows_total += phh[i];  // 144 rows per image
+  const long long total_rows = (long long)img.n * rows_total;
+  for (long long wr = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wr < total_rows;
+       wr += (long long)gridDim.x * warps_per_block) {
+    int n = (int)(wr / rows_total);
+    int rr = (int)(wr % rows_total);
+    int part = 0;
+    while (rr >= phh[part]) { rr -= phh[part]; ++part; }
+    const float* l = lm + (long long)n * 10;
+    float lx, ly;
+    if (part < 3) {
+      lx = l[part * 2];
+      ly = l[part * 2 + 1];
+    } else {  // mouth centre = mean of the two mouth corners (DataAndDataset.py:42-43), float32 arithmetic
+      lx = __fdiv_rn(__fadd_rn(l[6], l[8]), 2.0f);
+      ly = __fdiv_rn(__fadd_rn(l[7], l[9]), 2.0f);
+    }
+    const int cx = (int)floorf(lx), cy = (int)floorf(ly);
+    const int left = cx - pw[part] / 2 + 1, upper = cy - phh[part] / 2 + 1;
+    if (rr == 0 && lane < 4 && boxes) {
+      int vals[4] = {left, upper, cx + pw[part] / 2 + 1, cy + phh[part] / 2 + 1};
+      boxes[((long long)n * 4 + part) * 4 + lane] = vals[lane];
+    }
+    const V& o = out.v[part];
+    const int sy = upper + rr;
+    const int C = o.c;
+    for (int e = lane; e < pw[part] * C; e += 32) {
+      int x = e / C, c = e % C;
+      int sx = left + x;
+      float v = fill;
+      if (sy >= 0 && sy < img.h && sx >= 0 && sx < img.w) v = img.p[voff(img, n, sy, sx) + c];
+      o.p[voff(o, n, rr, x) + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LocalFuser
+// Fixed paste rectangles, D_and_G_model.py:148-157: (left, top, width, height) of LE, RE, nose, mouth.
+__constant__ int kFuseRect[4][4] = {{18, 19, 40, 40}, {65, 18, 40, 40}, {43, 47, 40, 32}, {40, 72, 48, 32}};
+
+struct FuseIn {
+  V v[4];
+};
+__global__ void local_fuse_kernel(FuseIn in, V out, uint8_t* __restrict__ argmax) {
+  const long long total = (long long)out.n * out.h * out.w * out.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % out.c);
+    long long r = i / out.c;
+    int x = (int)(r % out.w);
+    r /= out.w;
+    int y = (int)(r % out.h);
+    int n = (int)(r / out.h);
+    // torch.max over the stack [LE, RE, N, M] of zero-padded maps; first maximal index wins
+    float best = 0.f;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int px = x - kFuseRect[k][0], py = y - kFuseRect[k][1];
+      float v = 0.f;
+      if (px >= 0 && px < kFuseRect[k][2] && py >= 0 && py < kFuseRect[k][3]) v = in.v[k].p[voff(in.v[k], n, py, px) + c];
+      if (k == 0 || v > best) {
+        best = v;
+        arg = k;
+      }
+    }
+    out.p[voff(out, n, y, x) + c] = best;
+    if (argmax) argmax[i] = (uint8_t)arg;
+  }
+}
+__global__ void local_fuse_backward_kernel(V dout, const uint8_t* __restrict__ argmax, FuseIn din, int accumulate) {
+  long long sizes[4], total = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sizes[k] = (long long)din.v[k].n * din.v[k].h * din.v[k].w * din.v[k].c;
+    total += sizes[k];
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i;
+    int k = 0;
+    while (j >= sizes[k]) { j -= sizes[k]; ++k; }
+    const V& d = din.v[k];
+    int c = (int)(j % d.c);
+    long long r = j / d.c;
+    int px = (int)(r % d.w);
+    r /= d.w;
+    int py = (int)(r % d.h);
+    int n = (int)(r / d.h);
+    int x = px + kFuseRect[k][0], y = py + kFuseRect[k][1];
+    long long oi = (((long long)n * dout.h + y) * dout.w + x) * dout.c + c;
+    float g = (argmax[oi] == k) ? dout.p[voff(dout, n, y, x) + c] : 0.f;
+    float* dst = d.p + voff(d, n, py, px) + c;
+    *dst = accumulate ? (*dst + g) : g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ losses
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+__device__ __forceinline__ float block_mean(const V& f, int n, int y0, int x0, int s, int c) {
+  float a = 0.f;
+  for (int dy = 0; dy < s; ++dy)
+    for (int dx = 0; dx < s; ++dx) a += f.p[voff(f, n, y0 + dy, x0 + dx) + c];
+  return a / (float)(s * s);
+}
+
+// w: {l1_128, l1_64, l1_32, sym_128, sym_64, sym_32, tv_y, tv_x} coefficients (already divided by element counts)
+struct LossW {
+  float w[8];
+};
+__global__ void image_losses_kernel(V f, V g128, V g64, V g32, V df, LossW W, float* __restrict__ sums) {
+  float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int H = f.h, Wd = f.w;
+  const long long total = (long long)f.n * H * Wd * f.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % f.c);
+    long long r = i / f.c;
+    int x = (int)(r % Wd);
+    r /= Wd;
+    int y = (int)(r % H);
+    int n = (int)(r / H);
+    const int mx = Wd - 1 - x;
+    float grad = 0.f;
+    const float v = f.p[voff(f, n, y, x) + c];
+    // pixel L1 @128
+    float d = v - g128.p[voff(g128, n, y, x) + c];
+    part[0] += fabsf(d);
+    grad += W.w[0] * sgn(d);
+    // symmetry @128
+    float ds = v - f.p[voff(f, n, y, mx) + c];
+    part[3] += fabsf(ds);
+    grad += 2.f * W.w[3] * sgn(ds);
+    // scales 64 and 32
+#pragma unroll
+    for (int lv = 1; lv <= 2; ++lv) {
+      const int s = 1 << lv;
+      const V& gt = (lv == 1) ? g64 : g32;
+      const int by = y / s, bx = x / s;
+      const int mbx = (Wd / s) - 1 - bx;
+      const float m = block_mean(f, n, by * s, bx * s, s, c);
+      const float mm = block_mean(f, n, by * s, mbx * s, s, c);
+      const float dd = m - gt.p[voff(gt, n, by, bx) + c];
+      const float dsm = m - mm;
+      const bool owner = ((y % s) == 0) && ((x % s) == 0);
+      if (owner) {
+        part[lv] += fabsf(dd);
+        part[3 + lv] += fabsf(dsm);
+      }
+      const float inv = 1.f / (float)(s * s);
+      grad += W.w[lv] * inv * sgn(dd) + 2.f * W.w[3 + lv] * inv * sgn(dsm);
+    }
+    // total variation
+    if (y + 1 < H) {
+      float t = f.p[voff(f, n, y + 1, x) + c] - v;
+      part[6] += fabsf(t);
+      grad -= W.w[6] * sgn(t);
+    }
+    if (y > 0) grad += W.w[6] * sgn(v - f.p[voff(f, n, y - 1, x) + c]);
+    if (x + 1 < Wd) {
+      float t = f.p[voff(f, n, y, x + 1) + c] - v;
+      part[7] += fabsf(t);
+      grad -= W.w[7] * sgn(t);
+    }
+    if (x > 0) grad += W.w[7] * sgn(v - f.p[voff(f, n, y, x - 1) + c]);
+    df.p[voff(df, n, y, x) + c] = grad;
+  }
+  // block reduction of the 8 partial sums
+  __shared__ float red[8][8];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float s = part[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[k][wp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[threadIdx.x][i];
+    atomicAdd(sums + threadIdx.x, s);
+  }
+}
+
+__global__ void l1_loss_kernel(V a, V b, V da, float coeff, float* __restrict__ sum) {
+  float part = 0.f;
+  const long long total = (long long)a.n * a.h * a.w * a.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % a.c);
+    long long r = i / a.c;
+    int x = (int)(r % a.w);
+    r /= a.w;
+    int y = (int)(r % a.h);
+    int n = (int)(r / a.h);
+    float d = a.p[voff(a, n, y, x) + c] - b.p[voff(b, n, y, x) + c];
+    part += fabsf(d);
+    if (da.p) da.p[voff(da, n, y, x) + c] = coeff * sgn(d);
+  }
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) red[wp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(sum, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ maxout / Adam / GP
+__global__ void maxout2_kernel(const float* __restrict__ x, float* __restrict__ y, long long n_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
+    float a = x[2 * i], b = x[2 * i + 1];
+    y[i] = a >= b ? a : b;  // MaxPool1d keeps the first element on ties
+  }
+}
+__global__ void maxout2_backward_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                        long long n_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
+    float a = x[2 * i], b = x[2 * i + 1];
+    float g = dy[i];
+    dx[2 * i] = a >= b ? g : 0.f;
+    dx[2 * i + 1] = a >= b ? 0.f : g;
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    if (wd != 0.f) gi += wd * pi;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+// one block per sample
+__global__ void sample_sqnorm_kernel(V g, float* __restrict__ out) {
+  const int n = blockIdx.x;
+  const long long per = (long long)g.h * g.w * g.c;
+  float part = 0.f;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    int c = (int)(i % g.c);
+    long long r = i / g.c;
+    int x = (int)(r % g.w);
+    int y = (int)(r / g.w);
+    float v = g.p[voff(g, n, y, x) + c];
+    part += v * v;
+  }
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) red[wp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    out[n] = s;
+  }
+}
+__global__ void sample_scale_kernel(V g, const float* __restrict__ coeff, V u) {
+  const long long total = (long long)g.n * g.h * g.w * g.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % g.c);
+    long long r = i / g.c;
+    int x = (int)(r % g.w);
+    r /= g.w;
+    int y = (int)(r % g.h);
+    int n = (int)(r / g.h);
+    u.p[voff(u, n, y, x) + c] = coeff[n] * g.p[voff(g, n, y, x) + c];
+  }
+}
+
+static bool same_geom(const tpgan_view& a, const tpgan_view& b) {
+  return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
+}
+
+}  // namespace tpg
+
+using namespace tpg;
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+
+int tpgan_pack_weights(const float* ref, float* packed, int32_t taps, int32_t rows, int32_t k, int32_t rows_pad,
+                       int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
+                       const int32_t* k_map, int32_t round_tf32, void* stream) {
+  if (!ref || !packed || taps < 1 || rows > rows_pad || k > k_pad) return set_error(TPGAN_ERR_INVALID, "pack: bad args");
+  long long total = (long long)(taps + 1) * rows_pad * k_pad;
+  pack_kernel<<<grid_for(total, 256), 256, 0, ST>>>(ref, packed, taps, rows, k, rows_pad, k_pad, ref_row_stride,
+                                                    ref_k_stride, row_map, k_map, round_tf32);
+  TPG_CHECK_LAUNCH("pack_weights");
+  return 0;
+}
+int tpgan_unpack_weights(const float* packed, float* ref, int32_t taps, int32_t rows, int32_t k, int32_t rows_pad,
+                         int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
+                         const int32_t* k_map, int32_t accumulate, void* stream) {
+  if (!ref || !packed || taps < 1 || rows > rows_pad || k > k_pad) return set_error(TPGAN_ERR_INVALID, "unpack: bad args");
+  long long total = (long long)taps * rows * k;
+  unpack_kernel<<<grid_for(total, 256), 256, 0, ST>>>(packed, ref, taps, rows, k, rows_pad, k_pad, ref_row_stride,
+                                                      ref_k_stride, row_map, k_map, accumulate);
+  TPG_CHECK_LAUNCH("unpack_weights");
+  return 0;
+}
+
+int tpgan_nchw_to_nhwc(const float* src, tpgan_view dst, int32_t round_tf32, void* stream) {
+  long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  if (!src || !dst.ptr || total <= 0) return set_error(TPGAN_ERR_INVALID, "nchw_to_nhwc: bad args");
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, ST>>>(src, dv(dst), round_tf32);
+  TPG_CHECK_LAUNCH("nchw_to_nhwc");
+  return 0;
+}
+int tpgan_nhwc_to_nchw(tpgan_view src, float* dst, void* stream) {
+  long long total = (long long)src.n * src.h * src.w * src.c;
+  if (!dst || !src.ptr || total <= 0) return set_error(TPGAN_ERR_INVALID, "nhwc_to_nchw: bad args");
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(src), dst);
+  TPG_CHECK_LAUNCH("nhwc_to_nchw");
+  return 0;
+}
+
+int tpgan_act_backward(tpgan_view src, tpgan_view mask, tpgan_view dst, const float* slopes, float slope, void* stream) {
+  if (!same_geom(src, dst) || !same_geom(mask, dst)) return set_error(TPGAN_ERR_INVALID, "act_backward: geometry mismatch");
+  long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  act_backward_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(src), dv(mask), dv(dst), slopes, slope);
+  TPG_CHECK_LAUNCH("act_backward");
+  return 0;
+}
+int tpgan_view_copy(tpgan_view src, tpgan_view dst, int32_t accumulate, void* stream) {
+  if (!same_geom(src, dst)) return set_error(TPGAN_ERR_INVALID, "view_copy: geometry mismatch");
+  long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  view_copy_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(src), dv(dst), accumulate);
+  TPG_CHECK_LAUNCH("view_copy");
+  return 0;
+}
+int tpgan_bias_grad(tpgan_view dy, float* db, int32_t accumulate, void* stream) {
+  if (!dy.ptr || !db) return set_error(TPGAN_ERR_INVALID, "bias_grad: bad args");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * dy.c, ST);
+    if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  }
+  long long npix = (long long)dy.n * dy.h * dy.w;
+  dim3 grid((unsigned)std::max(1ll, std::min((npix + 63) / 64, 4ll * 148)), (unsigned)((dy.c + 31) / 32));
+  bias_grad_kernel<<<grid, 256, 0, ST>>>(dv(dy), db);
+  TPG_CHECK_LAUNCH("bias_grad");
+  return 0;
+}
+
+int tpgan_reflect_pad(tpgan_view src, tpgan_view dst, int32_t left, int32_t top, void* stream) {
+  if (src.n != dst.n || src.c != dst.c || dst.h < src.h + top || dst.w < src.w + left)
+    return set_error(TPGAN_ERR_INVALID, "reflect_pad: geometry mismatch");
+  long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  reflect_pad_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(src), dv(dst), left, top);
+  TPG_CHECK_LAUNCH("reflect_pad");
+  return 0;
+}
+int tpgan_reflect_pad_backward(tpgan_view dpad, tpgan_view dsrc, int32_t left, int32_t top, int32_t accumulate,
+                               void* stream) {
+  if (dsrc.n != dpad.n || dsrc.c != dpad.c || dpad.h < dsrc.h + top || dpad.w < dsrc.w + left)
+    return set_error(TPGAN_ERR_INVALID, "reflect_pad_backward: geometry mismatch");
+  long long total = (long long)dsrc.n * dsrc.h * dsrc.w * dsrc.c;
+  reflect_pad_backward_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(dpad), dv(dsrc), left, top, accumulate);
+  TPG_CHECK_LAUNCH("reflect_pad_backward");
+  return 0;
+}
+
+int tpgan_patch_crop(tpgan_view img, const float* landmarks, tpgan_view left_eye, tpgan_view right_eye, tpgan_view nose,
+                     tpgan_view mouth, int32_t* boxes, float fill, void* stream) {
+  const tpgan_view* o[4] = {&left_eye, &right_eye, &nose, &mouth};
+  const int pw[4] = {40, 40, 40, 48}, ph[4] = {40, 40, 32, 32};
+  CropOut co;
+  for (int i = 0; i < 4; ++i) {
+    if (o[i]->w != pw[i] || o[i]->h != ph[i] || o[i]->n != img.n || o[i]->c != img.c)
+      return set_error(TPGAN_ERR_INVALID, "patch_crop: patch %d must be (N,%d,%d,C)", i, ph[i], pw[i]);
+    co.v[i] = dv(*o[i]);
+  }
+  if (!landmarks) return set_error(TPGAN_ERR_INVALID, "patch_crop: landmarks NULL");
+  long long rows = (long long)img.n * 144;
+  int grid = (int)std::max(1ll, std::min((rows + 7) / 8, 8ll * 148));
+  patch_crop_kernel<<<grid, 256, 0, ST>>>(dv(img), landmarks, co, boxes, fill);
+  TPG_CHECK_LAUNCH("patch_crop");
+  return 0;
+}
+
+int tpgan_local_fuse(tpgan_view left_eye, tpgan_view right_eye, tpgan_view nose, tpgan_view mouth, tpgan_view out,
+                     uint8_t* argmax, void* stream) {
+  const tpgan_view* in[4] = {&left_eye, &right_eye, &nose, &mouth};
+  const int pw[4] = {40, 40, 40, 48}, ph[4] = {40, 40, 32, 32};
+  FuseIn fi;
+  for (int i = 0; i < 4; ++i) {
+    if (in[i]->w != pw[i] || in[i]->h != ph[i] || in[i]->n != out.n || in[i]->c != out.c)
+      return set_error(TPGAN_ERR_INVALID, "local_fuse: patch %d must be (N,%d,%d,C)", i, ph[i], pw[i]);
+    fi.v[i] = dv(*in[i]);
+  }
+  if (out.h != 128 || out.w != 128) return set_error(TPGAN_ERR_INVALID, "local_fuse: output must be 128x128");
+  long long total = (long long)out.n * out.h * out.w * out.c;
+  local_fuse_kernel<<<grid_for(total, 256), 256, 0, ST>>>(fi, dv(out), argmax);
+  TPG_CHECK_LAUNCH("local_fuse");
+  return 0;
+}
+int tpgan_local_fuse_backward(tpgan_view dout, const uint8_t* argmax, tpgan_view d_left_eye, tpgan_view d_right_eye,
+                              tpgan_view d_nose, tpgan_view d_mouth, int32_t accumulate, void* stream) {
+  const tpgan_view* in[4] = {&d_left_eye, &d_right_eye, &d_nose, &d_mouth};
+  const int pw[4] = {40, 40, 40, 48}, ph[4] = {40, 40, 32, 32};
+  FuseIn fi;
+  long long total = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (in[i]->w != pw[i] || in[i]->h != ph[i] || in[i]->n != dout.n || in[i]->c != dout.c)
+      return set_error(TPGAN_ERR_INVALID, "local_fuse_backward: patch %d must be (N,%d,%d,C)", i, ph[i], pw[i]);
+    fi.v[i] = dv(*in[i]);
+    total += (long long)in[i]->n * in[i]->h * in[i]->w * in[i]->c;
+  }
+  if (!argmax) return set_error(TPGAN_ERR_INVALID, "local_fuse_backward: argmax NULL");
+  local_fuse_backward_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(dout), argmax, fi, accumulate);
+  TPG_CHECK_LAUNCH("local_fuse_backward");
+  return 0;
+}
+
+int tpgan_image_losses(tpgan_view fake, tpgan_view t128, tpgan_view t64, tpgan_view t32, tpgan_view dfake, const float* w,
+                       float* sums, void* stream) {
+  if (!same_geom(fake, t128) || !same_geom(fake, dfake) || t64.h * 2 != fake.h || t32.h * 4 != fake.h || (fake.w % 4) ||
+      (fake.h % 4))
+    return set_error(TPGAN_ERR_INVALID, "image_losses: geometry mismatch");
+  LossW W;
+  for (int i = 0; i < 8; ++i) W.w[i] = w[i];
+  long long total = (long long)fake.n * fake.h * fake.w * fake.c;
+  image_losses_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(fake), dv(t128), dv(t64), dv(t32), dv(dfake), W, sums);
+  TPG_CHECK_LAUNCH("image_losses");
+  return 0;
+}
+int tpgan_l1_loss(tpgan_view a, tpgan_view b, tpgan_view da, float coeff, float* sum, void* stream) {
+  if (!same_geom(a, b)) return set_error(TPGAN_ERR_INVALID, "l1_loss: geometry mismatch");
+  long long total = (long long)a.n * a.h * a.w * a.c;
+  l1_loss_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(a), dv(b), dv(da), coeff, sum);
+  TPG_CHECK_LAUNCH("l1_loss");
+  return 0;
+}
+
+int tpgan_maxout2(const float* x, float* y, int32_t rows, int32_t cols_out, void* stream) {
+  long long n = (long long)rows * cols_out;
+  maxout2_kernel<<<grid_for(n, 256), 256, 0, ST>>>(x, y, n);
+  TPG_CHECK_LAUNCH("maxout2");
+  return 0;
+}
+int tpgan_maxout2_backward(const float* x, const float* dy, float* dx, int32_t rows, int32_t cols_out, void* stream) {
+  long long n = (long long)rows * cols_out;
+  maxout2_backward_kernel<<<grid_for(n, 256), 256, 0, ST>>>(x, dy, dx, n);
+  TPG_CHECK_LAUNCH("maxout2_backward");
+  return 0;
+}
+
+int tpgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int32_t step, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || step < 1) return set_error(TPGAN_ERR_INVALID, "adam_step: bad args");
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(n, 256, 16), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                   (float)sqrt(bc2), grad_scale);
+  TPG_CHECK_LAUNCH("adam_step");
+  return 0;
+}
+
+int tpgan_sample_sqnorm(tpgan_view g, float* sqnorm, void* stream) {
+  sample_sqnorm_kernel<<<g.n, 1024, 0, ST>>>(dv(g), sqnorm);
+  TPG_CHECK_LAUNCH("sample_sqnorm");
+  return 0;
+}
+int tpgan_sample_scale(tpgan_view g, const float* coeff, tpgan_view u, void* stream) {
+  if (!same_geom(g, u)) return set_error(TPGAN_ERR_INVALID, "sample_scale: geometry mismatch");
+  long long total = (long long)g.n * g.h * g.w * g.c;
+  sample_scale_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(g), coeff, dv(u));
+  TPG_CHECK_LAUNCH("sample_scale");
+  return 0;
+}
+
+}  // extern "C"

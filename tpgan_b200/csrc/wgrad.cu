@@ -1,0 +1,218 @@
+// Weight-gradient GEMM on Blackwell tensor cores (sm_100a).
+//
+//   dW[tap][m][n] += sum over pixels  P[pix, m] * Q_tap[pix, n]
+//
+// P is the un-shifted tensor (dY for a conv, x for a transposed conv), Q the tap-shifted one (x / dY), both NHWC.
+// The reduction (GEMM K) dimension is the pixel index, so both operands are "MN-major" in shared memory: a TMA box
+// {32 channels, bw, bh, bn} lands as [pixel][32ch] rows of 128 B, which is exactly the canonical MN-major tf32
+// layout (128B swizzle with 32B atoms: 4 K-rows x 128 B per atom, TMA mode SWIZZLE_128B_ATOM_32B).  TF32 UMMA accepts
+// MN-major A and B in that layout, so no transpose is ever materialised.
+// Zero padding and the conv stride are again TMA out-of-bounds fill and parity-plane tensor maps.
+//
+// Work unit = (tap, 128-channel M tile, N tile, K split); units are spread over one persistent CTA per SM and the
+// partial sums are combined with fp32 red.global.add into the forward-packed weight-gradient tensor.
+// Replaces the weight half of aten::convolution_backward for ModificationLayer.py:101,189.
+#include "common.cuh"
+#include "kparams.h"
+
+namespace tpg {
+
+constexpr int kWTmemCols = 512;
+constexpr int kWAccCols = 256;
+
+struct UnitCoord {
+  int gi, tap, mt, nt, ks;
+};
+
+template <class Params>
+__device__ __forceinline__ UnitCoord decode_unit(const Params& P, int unit) {
+  UnitCoord u;
+  int gi = 0;
+  constexpr int kG = (int)(sizeof(P.g) / sizeof(P.g[0]));
+#pragma unroll
+  for (int i = 1; i < kG; ++i)
+    if (i < P.ngroups && unit >= P.g[i].unit_begin) gi = i;
+  const WgradGroup& G = P.g[gi];
+  int local = unit - G.unit_begin;
+  u.gi = gi;
+  u.tap = local % G.ntaps;
+  local /= G.ntaps;
+  u.nt = local % G.n_tiles;
+  local /= G.n_tiles;
+  u.mt = local % G.m_tiles;
+  u.ks = local / G.m_tiles;
+  return u;
+}
+
+template <class Params>
+__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ Params P, int* status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_flag;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = P.stages;
+  const uint32_t stage_bytes = (uint32_t)(P.a_stage_bytes + P.b_stage_bytes);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  // Zero the whole ring once: K rows beyond a box (pixel count not a multiple of 8) and channel chunks that are
+  // never loaded must read as zero for the lifetime of the kernel.
+  {
+    uint4* p = reinterpret_cast<uint4*>(smem);
+    const int n16 = (int)((size_t)S * stage_bytes / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_s, kWTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  AbortCtl ac{&abort_flag, status};
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int unit = blockIdx.x; ok && unit < P.total_units; unit += gridDim.x) {
+        UnitCoord u = decode_unit(P, unit);
+        const WgradGroup& G = P.g[u.gi];
+        const TapDesc tap = G.taps[u.tap];
+        const CUtensorMap* qm = &G.qmap[tap.plane];
+        const int mch = min(4, (G.m_valid - u.mt * 128 + 31) / 32);
+        const int nch = min(G.block_n / 32, (G.n_valid - u.nt * G.block_n + 31) / 32);
+        const uint32_t box_bytes = (uint32_t)(G.bw * G.bh * G.bn) * 128u;
+        const uint32_t tx = box_bytes * (uint32_t)(mch + nch);
+        const uint32_t chunk_stride = (uint32_t)G.kp * 128u;
+        const int c_begin = u.ks * G.chunks_per_split;
+        const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
+        for (int c = c_begin; c < c_end; ++c) {
+          int wb = c % G.tiles_w;
+          int r = c / G.tiles_w;
+          int hb = r % G.tiles_h;
+          int nb = r / G.tiles_h;
+          const int x0 = wb * G.bw, y0 = hb * G.bh, n0 = nb * G.bn;
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1u, ac, 11)) { ok = false; break; }
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + P.a_stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          for (int i = 0; i < mch; ++i)
+            tma_load_4d(sa + (size_t)i * chunk_stride, &G.pmap, &full_bar[stage], u.mt * 128 + i * 32, x0, y0, n0);
+          for (int i = 0; i < nch; ++i)
+            tma_load_4d(sb + (size_t)i * chunk_stride, qm, &full_bar[stage], u.nt * G.block_n + i * 32, x0 + tap.dx,
+                        y0 + tap.dy, n0);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      bool ok = true;
+      for (int unit = blockIdx.x; ok && unit < P.total_units; unit += gridDim.x) {
+        UnitCoord u = decode_unit(P, unit);
+        const WgradGroup& G = P.g[u.gi];
+        if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 12)) break;
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_tf32(128, G.block_n, 1, 1);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kWAccCols);
+        const uint32_t chunk_stride = (uint32_t)G.kp * 128u;
+        const int kgroups = G.kp / 8;
+        const int c_begin = u.ks * G.chunks_per_split;
+        const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
+        uint32_t acc = 0;
+        for (int c = c_begin; c < c_end; ++c) {
+          if (!mbar_wait(&full_bar[stage], phase, ac, 13)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + (uint32_t)P.a_stage_bytes;
+          for (int k = 0; k < kgroups; ++k) {
+            mma_tf32_ss(d_tmem, make_smem_desc(a_addr + k * 1024, chunk_stride, 512, 1),
+                        make_smem_desc(b_addr + k * 1024, chunk_stride, 512, 1), idesc, acc);
+            acc = 1;
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        tc_commit(&tfull_bar[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> red.add into dW
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int unit = blockIdx.x; unit < P.total_units; unit += gridDim.x) {
+      UnitCoord u = decode_unit(P, unit);
+      const WgradGroup& G = P.g[u.gi];
+      if (!mbar_wait(&tfull_bar[as], aphase, ac, 14)) break;
+      tc_fence_after();
+      const int m = u.mt * 128 + row;
+      const bool mvalid = m < G.m_valid;
+      const TapDesc tap = G.taps[u.tap];
+      float* dw = G.dw + (size_t)tap.wtap * G.rows_pad * G.k_pad;
+      const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols) + ((uint32_t)(q * 32) << 16);
+      const int c_begin = u.ks * G.chunks_per_split;
+      const bool nonempty = c_begin < G.chunks;
+      for (int c0 = 0; c0 < G.block_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (mvalid && nonempty) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = u.nt * G.block_n + c0 + j;
+            if (n < G.n_valid) {
+              const size_t idx = G.transpose_out ? ((size_t)n * G.k_pad + m) : ((size_t)m * G.k_pad + n);
+              atomicAdd(dw + idx, __uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, kWTmemCols);
+}
+
+template __global__ void wgrad_kernel<WgradParams>(const __grid_constant__ WgradParams, int*);
+template __global__ void wgrad_kernel<WgradParams1>(const __grid_constant__ WgradParams1, int*);
+
+}  // namespace tpg

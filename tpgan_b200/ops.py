@@ -1,0 +1,256 @@
+"""Thin Python operators over the C ABI (include/tpgan_b200.h).
+
+PyTorch is used only for device memory and streams: every function here takes torch CUDA tensors (or `Act` channel
+views of NHWC buffers), turns them into raw pointers and calls libtpgan_b200.so.  Nothing computes in ATen.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (CONV_DGRAD, CONV_FWD, DECONV_DGRAD, DECONV_FWD, EPI_LEAKY, EPI_LINEAR, EPI_MASK, NULL_VIEW, ConvArgs,
+                   View, WgradArgs)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype in (torch.float32, torch.int32, torch.uint8), (t.device, t.dtype)
+    return t.data_ptr()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Act:
+    """Channel slice [c0, c0+c) of an NHWC fp32 buffer `buf` of shape (N, H, W, Cs)."""
+
+    __slots__ = ("buf", "c0", "c")
+
+    def __init__(self, buf: torch.Tensor, c0: int = 0, c: Optional[int] = None):
+        assert buf.dim() == 4 and buf.dtype == torch.float32 and buf.is_contiguous(), (buf.shape, buf.dtype)
+        self.buf = buf
+        self.c0 = c0
+        self.c = buf.shape[3] - c0 if c is None else c
+        assert 0 <= c0 and c0 + self.c <= buf.shape[3]
+
+    @staticmethod
+    def empty(n: int, h: int, w: int, c: int, device="cuda", zero: bool = True) -> "Act":
+        cs = round_up(c, 4)
+        buf = (torch.zeros if zero else torch.empty)((n, h, w, cs), dtype=torch.float32, device=device)
+        return Act(buf, 0, c)
+
+    @property
+    def n(self):
+        return self.buf.shape[0]
+
+    @property
+    def h(self):
+        return self.buf.shape[1]
+
+    @property
+    def w(self):
+        return self.buf.shape[2]
+
+    def slice(self, c0: int, c: int) -> "Act":
+        return Act(self.buf, self.c0 + c0, c)
+
+    def view(self) -> View:
+        n, h, w, cs = self.buf.shape
+        return View(self.buf.data_ptr() + 4 * self.c0, h * w * cs, w * cs, cs, n, h, w, self.c)
+
+    def like(self, zero: bool = True) -> "Act":
+        return Act.empty(self.n, self.h, self.w, self.c, self.buf.device, zero)
+
+    def to_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
+        _lib.check(_lib.load().tpgan_nhwc_to_nchw(self.view(), out.data_ptr(), _stream()), "nhwc_to_nchw")
+        return out
+
+    def from_nchw(self, t: torch.Tensor, round_tf32: bool = False) -> "Act":
+        t = t.contiguous()
+        assert tuple(t.shape) == (self.n, self.c, self.h, self.w), (t.shape, (self.n, self.c, self.h, self.w))
+        _lib.check(_lib.load().tpgan_nchw_to_nhwc(t.data_ptr(), self.view(), int(round_tf32), _stream()), "nchw_to_nhwc")
+        return self
+
+
+def _v(a: Optional[Act]) -> View:
+    return NULL_VIEW if a is None else a.view()
+
+
+@dataclass
+class Packed:
+    """Tensor-core weight layout [taps+1][rows_pad][k_pad] (see tpgan_pack_weights)."""
+    data: torch.Tensor
+    taps: int
+    rows: int
+    k: int
+    rows_pad: int
+    k_pad: int
+
+
+def pack_geometry(kind: int, w_shape: Sequence[int]):
+    """(rows, k, taps, row_stride, k_stride) of the reference weight for the GEMM of `kind`."""
+    d0, d1, kh, kw = w_shape
+    taps = kh * kw
+    if kind == CONV_FWD:      # weight (Cout, Cin, kh, kw): rows = Cout, k = Cin
+        return d0, d1, taps, d1 * taps, taps
+    if kind == CONV_DGRAD:    # rows = Cin, k = Cout
+        return d1, d0, taps, taps, d1 * taps
+    if kind == DECONV_FWD:    # weight (Cin, Cout, kh, kw): rows = Cout, k = Cin
+        return d1, d0, taps, taps, d1 * taps
+    if kind == DECONV_DGRAD:  # rows = Cin, k = Cout
+        return d0, d1, taps, d1 * taps, taps
+    raise ValueError(kind)
+
+
+def alloc_packed(kind: int, w_shape: Sequence[int], rows_int: Optional[int] = None, k_int: Optional[int] = None,
+                 device="cuda") -> Packed:
+    rows, k, taps, _, _ = pack_geometry(kind, w_shape)
+    rows = rows if rows_int is None else rows_int
+    k = k if k_int is None else k_int
+    rows_pad, k_pad = round_up(rows, 16), round_up(k, 32)
+    data = torch.zeros((taps + 1, rows_pad, k_pad), dtype=torch.float32, device=device)
+    return Packed(data, taps, rows, k, rows_pad, k_pad)
+
+
+def pack_weights(w: torch.Tensor, kind: int, out: Optional[Packed] = None, row_map: Optional[torch.Tensor] = None,
+                 k_map: Optional[torch.Tensor] = None, round_tf32: bool = True) -> Packed:
+    """Reference-layout weight -> tensor-core layout for the GEMM of `kind`.  row_map/k_map (int32, device) give for each
+    internal row / k index the reference channel (-1 = padding)."""
+    w = w.detach()
+    assert w.is_contiguous() and w.dtype == torch.float32
+    rows, k, taps, rs, ks = pack_geometry(kind, w.shape)
+    rows_int = rows if row_map is None else row_map.numel()
+    k_int = k if k_map is None else k_map.numel()
+    if out is None:
+        out = alloc_packed(kind, w.shape, rows_int, k_int, w.device)
+    _lib.check(_lib.load().tpgan_pack_weights(w.data_ptr(), out.data.data_ptr(), taps, rows_int, k_int, out.rows_pad,
+                                              out.k_pad, rs, ks, _ptr(row_map), _ptr(k_map), int(round_tf32), _stream()),
+               "pack_weights")
+    return out
+
+
+def unpack_weights(packed: Packed, w_grad: torch.Tensor, kind: int = CONV_FWD, row_map=None, k_map=None,
+                   accumulate: bool = False) -> None:
+    """Packed (forward-layout) weight gradient -> reference layout gradient tensor."""
+    assert w_grad.is_contiguous()
+    rows, k, taps, rs, ks = pack_geometry(kind, w_grad.shape)
+    rows_int = rows if row_map is None else row_map.numel()
+    k_int = k if k_map is None else k_map.numel()
+    _lib.check(_lib.load().tpgan_unpack_weights(packed.data.data_ptr(), w_grad.data_ptr(), taps, rows_int, k_int,
+                                                packed.rows_pad, packed.k_pad, rs, ks, _ptr(row_map), _ptr(k_map),
+                                                int(accumulate), _stream()), "unpack_weights")
+
+
+def conv_args(kind: int, x: Act, out: Act, w: Packed, k: int, stride: int, pad: int, bias: Optional[torch.Tensor] = None,
+              add1: Optional[Act] = None, add2: Optional[Act] = None, mask: Optional[Act] = None,
+              slopes: Optional[torch.Tensor] = None, slope: float = 0.0, epilogue: int = EPI_LINEAR,
+              round_tf32: bool = True) -> ConvArgs:
+    return ConvArgs(kind, k, k, stride, pad, x.view(), out.view(), w.data.data_ptr(), w.rows_pad, w.k_pad, _ptr(bias),
+                    _v(add1), _v(add2), _v(mask), _ptr(slopes), float(slope), epilogue, int(round_tf32))
+
+
+def conv2d_grouped(args: List[ConvArgs]) -> None:
+    arr = (ConvArgs * len(args))(*args)
+    _lib.check(_lib.load().tpgan_conv2d(arr, len(args), _stream()), "conv2d")
+
+
+def conv2d(*a, **kw) -> None:
+    conv2d_grouped([conv_args(*a, **kw)])
+
+
+def wgrad_args(kind: int, x: Act, dy: Act, dw: Packed, k: int, stride: int, pad: int) -> WgradArgs:
+    return WgradArgs(kind, k, k, stride, pad, x.view(), dy.view(), dw.data.data_ptr(), dw.rows_pad, dw.k_pad)
+
+
+def wgrad_grouped(args: List[WgradArgs]) -> None:
+    arr = (WgradArgs * len(args))(*args)
+    _lib.check(_lib.load().tpgan_conv2d_wgrad(arr, len(args), _stream()), "conv2d_wgrad")
+
+
+def wgrad(*a, **kw) -> None:
+    wgrad_grouped([wgrad_args(*a, **kw)])
+
+
+def act_backward(src: Act, mask: Act, dst: Act, slope: float = 0.0, slopes: Optional[torch.Tensor] = None) -> None:
+    _lib.check(_lib.load().tpgan_act_backward(src.view(), mask.view(), dst.view(), _ptr(slopes), float(slope), _stream()),
+               "act_backward")
+
+
+def view_copy(src: Act, dst: Act, accumulate: bool = False) -> None:
+    _lib.check(_lib.load().tpgan_view_copy(src.view(), dst.view(), int(accumulate), _stream()), "view_copy")
+
+
+def bias_grad(dy: Act, db: torch.Tensor, accumulate: bool = True) -> None:
+    _lib.check(_lib.load().tpgan_bias_grad(dy.view(), db.data_ptr(), int(accumulate), _stream()), "bias_grad")
+
+
+def reflect_pad(src: Act, dst: Act, left: int, top: int) -> None:
+    _lib.check(_lib.load().tpgan_reflect_pad(src.view(), dst.view(), left, top, _stream()), "reflect_pad")
+
+
+def reflect_pad_backward(dpad: Act, dsrc: Act, left: int, top: int, accumulate: bool = False) -> None:
+    _lib.check(_lib.load().tpgan_reflect_pad_backward(dpad.view(), dsrc.view(), left, top, int(accumulate), _stream()),
+               "reflect_pad_backward")
+
+
+def patch_crop(img: Act, landmarks: torch.Tensor, patches: Sequence[Act], boxes: Optional[torch.Tensor] = None,
+               fill: float = -1.0) -> None:
+    assert landmarks.dtype == torch.float32 and landmarks.is_contiguous() and tuple(landmarks.shape) == (img.n, 5, 2)
+    _lib.check(_lib.load().tpgan_patch_crop(img.view(), landmarks.data_ptr(), *[p.view() for p in patches], _ptr(boxes),
+                                            float(fill), _stream()), "patch_crop")
+
+
+def local_fuse(patches: Sequence[Act], out: Act, argmax: Optional[torch.Tensor] = None) -> None:
+    _lib.check(_lib.load().tpgan_local_fuse(*[p.view() for p in patches], out.view(), _ptr(argmax), _stream()),
+               "local_fuse")
+
+
+def local_fuse_backward(dout: Act, argmax: torch.Tensor, dpatches: Sequence[Act], accumulate: bool = False) -> None:
+    _lib.check(_lib.load().tpgan_local_fuse_backward(dout.view(), argmax.data_ptr(), *[p.view() for p in dpatches],
+                                                     int(accumulate), _stream()), "local_fuse_backward")
+
+
+def image_losses(fake: Act, t128: Act, t64: Act, t32: Act, dfake: Act, coeffs: Sequence[float],
+                 sums: torch.Tensor) -> None:
+    w = (C.c_float * 8)(*coeffs)
+    _lib.check(_lib.load().tpgan_image_losses(fake.view(), t128.view(), t64.view(), t32.view(), dfake.view(), w,
+                                              sums.data_ptr(), _stream()), "image_losses")
+
+
+def l1_loss(a: Act, b: Act, da: Optional[Act], coeff: float, total: torch.Tensor) -> None:
+    _lib.check(_lib.load().tpgan_l1_loss(a.view(), b.view(), _v(da), float(coeff), total.data_ptr(), _stream()), "l1_loss")
+
+
+def maxout2(x: torch.Tensor, y: torch.Tensor) -> None:
+    rows, cols = y.shape
+    _lib.check(_lib.load().tpgan_maxout2(x.data_ptr(), y.data_ptr(), rows, cols, _stream()), "maxout2")
+
+
+def maxout2_backward(x: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor) -> None:
+    rows, cols = dy.shape
+    _lib.check(_lib.load().tpgan_maxout2_backward(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), rows, cols, _stream()),
+               "maxout2_backward")
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+    _lib.check(_lib.load().tpgan_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1,
+                                           beta2, eps, weight_decay, step, grad_scale, _stream()), "adam_step")
+
+
+def sample_sqnorm(g: Act, out: torch.Tensor) -> None:
+    _lib.check(_lib.load().tpgan_sample_sqnorm(g.view(), out.data_ptr(), _stream()), "sample_sqnorm")
+
+
+def sample_scale(g: Act, coeff: torch.Tensor, u: Act) -> None:
+    _lib.check(_lib.load().tpgan_sample_scale(g.view(), coeff.data_ptr(), u.view(), _stream()), "sample_scale")
