@@ -1,0 +1,153 @@
+"""ORACLE (test infrastructure): fp32 PyTorch restatement ("port") of the reference Generator / Discriminator forward,
+driven by a reference-format state_dict.  It exists because /root/reference cannot travel to the GPU box; it is pinned
+against the live (shimmed) reference in tests/test_oracle_cpu.py and against committed golden vectors.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this file.
+
+Follows (file:line in /root/reference):
+  conv()/deconv()/ResidualBlock        ModificationLayer.py:54-123, 158-202, 233-302
+  LocalPathway                         D_and_G_model.py:18-110
+  LocalFuser                           D_and_G_model.py:112-159
+  GlobalPathway                        D_and_G_model.py:161-329   (with fix F3: dim128 includes I128's 3 channels)
+  FeaturePredict / Generator           D_and_G_model.py:331-407
+  Discriminator                        D_and_G_model.py:409-435
+Config defaults: use_batchnorm=False for G and D (config.py:63,68) - the only configuration restated.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+LEAKY = 0.01  # nn.LeakyReLU(1e-2) and nn.LeakyReLU() both have negative_slope 0.01
+
+
+def _conv(sd, key, x, stride=1, pad=0, slope=LEAKY):
+    """conv(): [ReflectionPad2d(4-list)] -> Conv2d(bias) -> activation (ModificationLayer.py:83-119)."""
+    if isinstance(pad, (list, tuple)):
+        x = F.pad(x, tuple(pad), mode="reflect")  # ReflectionPad2d((left, right, top, bottom)), :93
+        idx, p = 1, 0
+    else:
+        idx, p = 0, pad
+    y = F.conv2d(x, sd[f"{key}.{idx}.weight"], sd[f"{key}.{idx}.bias"], stride=stride, padding=p)
+    return y if slope is None else F.leaky_relu(y, slope)
+
+
+def _deconv(sd, key, x, stride, pad, out_pad):
+    """deconv(): ConvTranspose2d(bias) -> ReLU (ModificationLayer.py:189-198)."""
+    return F.relu(F.conv_transpose2d(x, sd[f"{key}.0.weight"], sd[f"{key}.0.bias"], stride=stride, padding=pad,
+                                     output_padding=out_pad))
+
+
+def _res(sd, key, x, k=3, pad=None):
+    """Non-bottleneck ResidualBlock with identity shortcut, scaling_factor 1.0 (ModificationLayer.py:292-302)."""
+    pad = (k - 1) // 2 if pad is None else pad
+    h = _conv(sd, f"{key}.layers.0", x, 1, pad, LEAKY)
+    y = _conv(sd, f"{key}.layers.1", h, 1, pad, None)
+    return F.leaky_relu(y + 1.0 * x, LEAKY)
+
+
+def _conv_res(sd, key, x, k, stride, pad):
+    """sequential(conv(...), ResidualBlock(...)) as used by every encoder stage."""
+    return _res(sd, f"{key}.1", _conv(sd, f"{key}.0", x, stride, pad), k if key.endswith(("conv0", "conv1")) else 3)
+
+
+def local_pathway(sd, pre, x):
+    """D_and_G_model.py:84-110.  Returns (local_img, deconv2)."""
+    c = lambda name, t, s: _res(sd, f"{pre}.{name}.1", _conv(sd, f"{pre}.{name}.0", t, s, 1), 3)
+    conv0 = c("conv0", x, 1)
+    conv1 = c("conv1", conv0, 2)
+    conv2 = c("conv2", conv1, 2)
+    conv3 = c("conv3", conv2, 2)
+    deconv0 = _deconv(sd, f"{pre}.deconv0", conv3, 2, 1, 1)
+    as0 = c("after_select0", torch.cat([deconv0, conv2], 1), 1)
+    deconv1 = _deconv(sd, f"{pre}.deconv1", as0, 2, 1, 1)
+    as1 = c("after_select1", torch.cat([deconv1, conv1], 1), 1)
+    deconv2 = _deconv(sd, f"{pre}.deconv2", as1, 2, 1, 1)
+    as2 = c("after_select2", torch.cat([deconv2, conv0], 1), 1)
+    local_img = _conv(sd, f"{pre}.local_img", as2, 1, 0, None)
+    return local_img, deconv2
+
+
+# (left, top, width, height) of the fixed paste rectangles, D_and_G_model.py:148-157
+FUSE_RECTS = ((39 - 20 - 1, 40 - 20 - 1, 40, 40), (86 - 20 - 1, 39 - 20 - 1, 40, 40), (64 - 20 - 1, 64 - 16 - 1, 40, 32),
+              (65 - 24 - 1, 89 - 16 - 1, 48, 32))
+
+
+def local_fuser(parts, return_index=False):
+    """max over the four zero-padded maps (D_and_G_model.py:154-159)."""
+    padded = []
+    for t, (left, top, w, h) in zip(parts, FUSE_RECTS):
+        assert t.shape[2] == h and t.shape[3] == w
+        padded.append(F.pad(t, (left, 128 - left - w, top, 128 - top - h)))
+    val, idx = torch.max(torch.stack(padded, 0), 0)
+    return (val, idx) if return_index else val
+
+
+def global_pathway(sd, pre, I128, local_fake, local_feat, z):
+    """D_and_G_model.py:281-329."""
+    p = lambda n: f"{pre}.{n}"
+    conv0 = _res(sd, p("conv0.1"), _conv(sd, p("conv0.0"), I128, 1, 3), 7)
+    conv1 = _res(sd, p("conv1.1"), _conv(sd, p("conv1.0"), conv0, 2, 2), 5)
+    conv2 = _res(sd, p("conv2.1"), _conv(sd, p("conv2.0"), conv1, 2, 1), 3)
+    conv3 = _res(sd, p("conv3.1"), _conv(sd, p("conv3.0"), conv2, 2, 1), 3)
+    conv4 = _conv(sd, p("conv4.0"), conv3, 2, 1)
+    for i in range(1, 5):
+        conv4 = _res(sd, p(f"conv4.{i}"), conv4, 3)
+    B = I128.shape[0]
+    fc1 = F.linear(conv4.reshape(B, -1), sd[p("fc1.weight")], sd[p("fc1.bias")])
+    fc2 = F.max_pool1d(fc1.view(B, -1, 2), 2, 2).view(B, -1)
+    deconv_8 = _deconv(sd, p("deconv_8"), torch.cat([fc2, z], 1).view(B, -1, 1, 1), 1, 0, 0)
+    deconv_32 = _deconv(sd, p("deconv_32"), deconv_8, 4, 0, 1)
+    deconv_64 = _deconv(sd, p("deconv_64"), deconv_32, 2, 1, 1)
+    deconv_128 = _deconv(sd, p("deconv_128"), deconv_64, 2, 1, 1)
+    rp = [1, 0, 1, 0]
+    f8 = _res(sd, p("add_conv_and_deconv_8"), torch.cat([deconv_8, conv4], 1), 2, rp)
+    f8 = _res(sd, p("enhance_features_8.1"), _res(sd, p("enhance_features_8.0"), f8, 2, rp), 2, rp)
+    up16 = _deconv(sd, p("upsample_16"), f8, 2, 1, 1)
+    a16 = _res(sd, p("add_conv_and_deconv_16"), conv3, 3)
+    f16 = torch.cat([up16, a16], 1)
+    f16 = _res(sd, p("enhance_features_16.1"), _res(sd, p("enhance_features_16.0"), f16, 3), 3)
+    up32 = _deconv(sd, p("upsample_32"), f16, 2, 1, 1)
+    a32 = _res(sd, p("add_conv_and_deconv_32"), torch.cat([deconv_32, conv2], 1), 3)
+    f32 = torch.cat([up32, a32], 1)
+    f32 = _res(sd, p("enhance_features_32.1"), _res(sd, p("enhance_features_32.0"), f32, 3), 3)
+    up64 = _deconv(sd, p("upsample_64"), f32, 2, 1, 1)
+    a64 = _res(sd, p("add_conv_and_deconv_64"), torch.cat([deconv_64, conv1], 1), 5)
+    f64 = torch.cat([up64, a64], 1)
+    f64 = _res(sd, p("enhance_features_64.1"), _res(sd, p("enhance_features_64.0"), f64, 3), 3)
+    up128 = _deconv(sd, p("upsample_128"), f64, 2, 1, 1)
+    a128 = _res(sd, p("add_conv_and_deconv_128"), torch.cat([deconv_128, conv0, I128], 1), 7)
+    f128 = _res(sd, p("enhance_features_128.0"), torch.cat([up128, a128, local_feat, local_fake], 1), 5)
+    conv5 = _res(sd, p("conv5.1"), _conv(sd, p("conv5.0"), f128, 1, 2), 3)
+    conv6 = _conv(sd, p("conv6"), conv5, 1, 1)
+    img = _conv(sd, p("decoded_img128"), conv6, 1, 1, None)
+    return img, fc2
+
+
+def generator(sd, I128, left_eye, right_eye, nose, mouth, z, dropout_mask=None):
+    """Generator.forward (D_and_G_model.py:374-407); returns the same 8-tuple.  dropout_mask (B,256), already scaled by
+    1/(1-p), replaces nn.Dropout(0.3) when use_dropout is wanted; None = use_dropout False."""
+    parts_in = (left_eye, right_eye, nose, mouth)
+    names = ("left_eye", "right_eye", "nose", "mouth")
+    imgs, feats = [], []
+    for n, t in zip(names, parts_in):
+        im, ft = local_pathway(sd, f"local_pathway_{n}", t)
+        imgs.append(im)
+        feats.append(ft)
+    fused_feat = local_fuser(feats)
+    fused_img = local_fuser(imgs)
+    fused_in = local_fuser(parts_in)
+    fake, enc = global_pathway(sd, "global_pathway", I128, fused_img, fused_feat, z)
+    e = enc if dropout_mask is None else enc * dropout_mask
+    logits = F.linear(e, sd["feature_predict.fc.weight"], sd["feature_predict.fc.bias"])
+    return fake, logits, fused_img, imgs[0], imgs[1], imgs[2], imgs[3], fused_in
+
+
+def discriminator(sd, x):
+    """Discriminator.forward (D_and_G_model.py:421-435): model.{0..3}=conv s2, .4=RB, .5=conv s2, .6=RB, .7=conv."""
+    for i in range(4):
+        x = _conv(sd, f"model.{i}", x, 2, 1)
+    x = _res(sd, "model.4", x, 3)
+    x = _conv(sd, "model.5", x, 2, 1)
+    x = _res(sd, "model.6", x, 3)
+    return _conv(sd, "model.7", x, 1, 1, None)
