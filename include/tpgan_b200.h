@@ -98,7 +98,7 @@ TPGAN_API int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups
  *   conv  weight,                  DGRAD: rows=Cin  (stride taps),     k=Cout (stride Cin*taps)
  *   deconv weight (Cin,Cout,kh,kw), FWD : rows=Cout (stride taps),     k=Cin (stride Cout*taps)
  *   deconv weight,                 DGRAD: rows=Cin  (stride Cout*taps), k=Cout (stride taps)
- * Values are rounded to tf32 (rna) when round_tf32 != 0. */
+ * round_tf32: 0 = keep fp32 bits, 1 = round to tf32 (rna), 2 = store the residual w - tf32(w). */
 TPGAN_API int tpgan_pack_weights(const float* ref, float* packed, int32_t taps, int32_t rows, int32_t k, int32_t rows_pad,
                        int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
                        const int32_t* k_map, int32_t round_tf32, void* stream);
@@ -135,7 +135,8 @@ TPGAN_API int tpgan_patch_crop(tpgan_view img, const float* landmarks, tpgan_vie
 
 /* LocalFuser, D_and_G_model.py:132-159: out = max over the four zero-padded patches at the fixed offsets.
  * argmax (optional, uint8 [N][128][128][C]) records the winning source 0..3 (first index wins ties, as
- * torch.max over the stacked tensor), 4 = the zero padding only.  Backward routes the gradient to it. */
+ * torch.max over the stacked tensor, so 0 where only zero padding covers the pixel).  Backward routes the
+ * gradient to it. */
 TPGAN_API int tpgan_local_fuse(tpgan_view left_eye, tpgan_view right_eye, tpgan_view nose, tpgan_view mouth, tpgan_view out,
                      uint8_t* argmax, void* stream);
 TPGAN_API int tpgan_local_fuse_backward(tpgan_view dout, const uint8_t* argmax, tpgan_view d_left_eye, tpgan_view d_right_eye,
@@ -163,6 +164,21 @@ TPGAN_API int tpgan_adam_step(float* p, const float* g, float* m, float* v, int6
 /* Per-sample gradient-penalty helpers: norms[n] = ||g[n]||_2 ; u = coeff[n] * g. */
 TPGAN_API int tpgan_sample_sqnorm(tpgan_view g, float* sqnorm, void* stream);
 TPGAN_API int tpgan_sample_scale(tpgan_view g, const float* coeff, tpgan_view u, void* stream);
+/* coeff[n] = scale * (sqrt(sqnorm[n]) - 1) / sqrt(sqnorm[n]) ; *gp_sum += sum_n (sqrt(sqnorm[n]) - 1)^2 (gp_sum may be NULL). */
+TPGAN_API int tpgan_gp_coeff(const float* sqnorm, float* coeff, int32_t n, float scale, float* gp_sum, void* stream);
+/* out[n] = alpha[n]*a[n] + (1-alpha[n])*b[n]: the WGAN-GP interpolate x_hat (oracle step, config.py:72). */
+TPGAN_API int tpgan_lerp(tpgan_view a, tpgan_view b, const float* alpha, tpgan_view out, void* stream);
+/* out = a * b elementwise (nn.Dropout mask of FeaturePredict, D_and_G_model.py:344-346, and its backward). */
+TPGAN_API int tpgan_mul(tpgan_view a, tpgan_view b, tpgan_view out, void* stream);
+/* hi = tf32(src) (round to nearest), lo = src - hi.  With tpgan_pack_weights(round_tf32 = 2) (which stores w - tf32(w))
+ * this gives the fp32-exact verification mode: conv(x, w) = conv(hi, wh) + conv(hi, wl) + conv(lo, wh) up to 2^-21. */
+TPGAN_API int tpgan_split_tf32(tpgan_view src, tpgan_view hi, tpgan_view lo, void* stream);
+/* out[...] = value. */
+TPGAN_API int tpgan_fill(tpgan_view out, float value, void* stream);
+/* Cross-entropy of FeaturePredict logits (config.py:82 weight_cross_entropy): *loss_sum += sum_n CE(logits[n], labels[n]);
+ * dlogits[n] = coeff * (softmax(logits[n]) - onehot(labels[n])) (dlogits may be NULL).  labels are int64. */
+TPGAN_API int tpgan_softmax_ce(const float* logits, int64_t row_stride, const int64_t* labels, float* dlogits,
+                               int64_t drow_stride, int32_t rows, int32_t cols, float coeff, float* loss_sum, void* stream);
 
 /* ---- diagnostics --------------------------------------------------------------------------------------- */
 TPGAN_API const char* tpgan_last_error(void);

@@ -20,6 +20,88 @@ import torch.nn.functional as F
 
 LEAKY = 0.01  # nn.LeakyReLU(1e-2) and nn.LeakyReLU() both have negative_slope 0.01
 
+# ---- optional TF32 operand emulation ---------------------------------------------------------------------------------
+# The CUDA path multiplies TF32 operands (10-bit mantissa, round-to-nearest-away = PTX cvt.rna.tf32.f32) and accumulates
+# in fp32.  With EMULATE_TF32 = True the port rounds exactly the same operands (weights, and every conv output where the
+# kernels round at store), so the only remaining difference to the device is fp32 summation order.  This separates
+# "arithmetic format" deviations from logic errors: LeakyReLU sign flips caused by TF32 noise otherwise dominate any
+# gradient comparison against pure fp32.  Default False = the reference's fp32 arithmetic.
+EMULATE_TF32 = False
+
+
+def tf32_rna(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32: keep 10 mantissa bits, round to nearest, ties away from zero."""
+    i = x.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF)
+    r = torch.where((i & 0x7F800000) == 0x7F800000, i, r)  # inf / nan unchanged
+    return r.view(torch.float32)
+
+
+class _RoundST(torch.autograd.Function):
+    """tf32 rounding in forward, and of the gradient in backward (the kernels round stored activations AND stored
+    activation gradients)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return tf32_rna(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return tf32_rna(g)
+
+
+def _q(x):
+    return _RoundST.apply(x) if EMULATE_TF32 else x
+
+
+class _RoundW(torch.autograd.Function):
+    """tf32 rounding of a weight in forward; its gradient passes through unchanged."""
+
+    @staticmethod
+    def forward(ctx, w):
+        return tf32_rna(w)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _qw(w):
+    return _RoundW.apply(w) if EMULATE_TF32 else w
+
+
+# ---- optional activation-mask injection ---------------------------------------------------------------------------------
+# (Leaky)ReLU makes gradients discontinuous in the forward values: an element whose pre-activation changes sign between
+# two implementations changes its gradient by ~100 %, so a forward deviation eps turns into a gradient deviation of order
+# sqrt(eps) that has nothing to do with the backward arithmetic being checked.  MASK_HOOK(name) may return the stored
+# output of the CUDA path for the activation site `name`; the port then evaluates the activation's *backward* with the
+# sign pattern of that tensor (forward values stay the port's own).  Gradient parity tests use it to verify dgrad / wgrad
+# / plumbing at the precision of the arithmetic format.  Default None = plain autograd.
+MASK_HOOK = None
+
+
+class _ActWithMask(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, mask_src, slope):
+        ctx.save_for_backward(mask_src > 0)
+        ctx.slope = slope
+        return F.leaky_relu(y, slope)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        return torch.where(pos, g, g * ctx.slope), None, None
+
+
+def _act(y, slope, name):
+    if slope is None:
+        return y
+    if MASK_HOOK is not None:
+        m = MASK_HOOK(name)
+        if m is not None:
+            return _ActWithMask.apply(y, m.reshape(y.shape), slope)
+    return F.leaky_relu(y, slope)
+
 
 def _conv(sd, key, x, stride=1, pad=0, slope=LEAKY):
     """conv(): [ReflectionPad2d(4-list)] -> Conv2d(bias) -> activation (ModificationLayer.py:83-119)."""
@@ -28,22 +110,26 @@ def _conv(sd, key, x, stride=1, pad=0, slope=LEAKY):
         idx, p = 1, 0
     else:
         idx, p = 0, pad
-    y = F.conv2d(x, sd[f"{key}.{idx}.weight"], sd[f"{key}.{idx}.bias"], stride=stride, padding=p)
-    return y if slope is None else F.leaky_relu(y, slope)
+    y = F.conv2d(x, _qw(sd[f"{key}.{idx}.weight"]), sd[f"{key}.{idx}.bias"], stride=stride, padding=p)
+    return _q(_act(y, slope, key))
 
 
 def _deconv(sd, key, x, stride, pad, out_pad):
     """deconv(): ConvTranspose2d(bias) -> ReLU (ModificationLayer.py:189-198)."""
-    return F.relu(F.conv_transpose2d(x, sd[f"{key}.0.weight"], sd[f"{key}.0.bias"], stride=stride, padding=pad,
-                                     output_padding=out_pad))
+    return _q(_act(F.conv_transpose2d(x, _qw(sd[f"{key}.0.weight"]), sd[f"{key}.0.bias"], stride=stride, padding=pad,
+                                      output_padding=out_pad), 0.0, key))
 
 
 def _res(sd, key, x, k=3, pad=None):
     """Non-bottleneck ResidualBlock with identity shortcut, scaling_factor 1.0 (ModificationLayer.py:292-302)."""
     pad = (k - 1) // 2 if pad is None else pad
     h = _conv(sd, f"{key}.layers.0", x, 1, pad, LEAKY)
-    y = _conv(sd, f"{key}.layers.1", h, 1, pad, None)
-    return F.leaky_relu(y + 1.0 * x, LEAKY)
+    if isinstance(pad, (list, tuple)):
+        hp, idx, p = F.pad(h, tuple(pad), mode="reflect"), 1, 0
+    else:
+        hp, idx, p = h, 0, pad
+    y = F.conv2d(hp, _qw(sd[f"{key}.layers.1.{idx}.weight"]), sd[f"{key}.layers.1.{idx}.bias"], padding=p)
+    return _q(_act(y + 1.0 * x, LEAKY, f"{key}.layers.1"))
 
 
 def _conv_res(sd, key, x, k, stride, pad):
@@ -94,7 +180,7 @@ def global_pathway(sd, pre, I128, local_fake, local_feat, z):
     for i in range(1, 5):
         conv4 = _res(sd, p(f"conv4.{i}"), conv4, 3)
     B = I128.shape[0]
-    fc1 = F.linear(conv4.reshape(B, -1), sd[p("fc1.weight")], sd[p("fc1.bias")])
+    fc1 = _q(F.linear(conv4.reshape(B, -1), _qw(sd[p("fc1.weight")]), sd[p("fc1.bias")]))
     fc2 = F.max_pool1d(fc1.view(B, -1, 2), 2, 2).view(B, -1)
     deconv_8 = _deconv(sd, p("deconv_8"), torch.cat([fc2, z], 1).view(B, -1, 1, 1), 1, 0, 0)
     deconv_32 = _deconv(sd, p("deconv_32"), deconv_8, 4, 0, 1)
@@ -127,6 +213,8 @@ def global_pathway(sd, pre, I128, local_fake, local_feat, z):
 def generator(sd, I128, left_eye, right_eye, nose, mouth, z, dropout_mask=None):
     """Generator.forward (D_and_G_model.py:374-407); returns the same 8-tuple.  dropout_mask (B,256), already scaled by
     1/(1-p), replaces nn.Dropout(0.3) when use_dropout is wanted; None = use_dropout False."""
+    if EMULATE_TF32:  # the kernels round the staged inputs too
+        I128, left_eye, right_eye, nose, mouth, z = (tf32_rna(t) for t in (I128, left_eye, right_eye, nose, mouth, z))
     parts_in = (left_eye, right_eye, nose, mouth)
     names = ("left_eye", "right_eye", "nose", "mouth")
     imgs, feats = [], []
@@ -139,12 +227,14 @@ def generator(sd, I128, left_eye, right_eye, nose, mouth, z, dropout_mask=None):
     fused_in = local_fuser(parts_in)
     fake, enc = global_pathway(sd, "global_pathway", I128, fused_img, fused_feat, z)
     e = enc if dropout_mask is None else enc * dropout_mask
-    logits = F.linear(e, sd["feature_predict.fc.weight"], sd["feature_predict.fc.bias"])
+    logits = _q(F.linear(e, _qw(sd["feature_predict.fc.weight"]), sd["feature_predict.fc.bias"]))
     return fake, logits, fused_img, imgs[0], imgs[1], imgs[2], imgs[3], fused_in
 
 
 def discriminator(sd, x):
     """Discriminator.forward (D_and_G_model.py:421-435): model.{0..3}=conv s2, .4=RB, .5=conv s2, .6=RB, .7=conv."""
+    if EMULATE_TF32:
+        x = _q(x)
     for i in range(4):
         x = _conv(sd, f"model.{i}", x, 2, 1)
     x = _res(sd, "model.4", x, 3)

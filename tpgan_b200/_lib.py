@@ -62,6 +62,12 @@ SYMBOLS = {
     "tpgan_adam_step": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _F, _I32, _F, _VP]),
     "tpgan_sample_sqnorm": (C.c_int, [View, _VP, _VP]),
     "tpgan_sample_scale": (C.c_int, [View, _VP, View, _VP]),
+    "tpgan_gp_coeff": (C.c_int, [_VP, _VP, _I32, _F, _VP, _VP]),
+    "tpgan_lerp": (C.c_int, [View, View, _VP, View, _VP]),
+    "tpgan_mul": (C.c_int, [View, View, View, _VP]),
+    "tpgan_fill": (C.c_int, [View, _F, _VP]),
+    "tpgan_split_tf32": (C.c_int, [View, View, View, _VP]),
+    "tpgan_softmax_ce": (C.c_int, [_VP, _I64, _VP, _VP, _I64, _I32, _I32, _F, _VP, _VP]),
     "tpgan_last_error": (C.c_char_p, []),
     "tpgan_abi_version": (C.c_int, []),
     "tpgan_kernel_status": (C.c_int, []),

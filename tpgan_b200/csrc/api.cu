@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -261,13 +262,16 @@ static int launch_tapgemm(Params& P, cudaStream_t st) {
   const int stage_bytes = 16384 + bmax;
   const int budget = g_dev.max_smem - 1024 - 256;
   P.stages = std::min(kMaxStages, budget / stage_bytes);
+  P.tap_rot = getenv("TPGAN_TAPROT") ? atoi(getenv("TPGAN_TAPROT")) : 0;
+  if (const char* ev = getenv("TPGAN_STAGES")) P.stages = std::min(P.stages, std::max(2, atoi(ev)));
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "not enough shared memory for 2 stages");
   const int smem = P.stages * stage_bytes + 1024;
   static std::once_flag once;
   auto kern = tapgemm_kernel<Params>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int grid = std::min(tiles, g_dev.sm_count);
+  int grid = std::min(tiles, g_dev.sm_count);
+  if (const char* ev = getenv("TPGAN_GRID")) grid = std::min(grid, std::max(1, atoi(ev)));
   kern<<<grid, 256, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));

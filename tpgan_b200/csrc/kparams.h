@@ -59,6 +59,7 @@ struct TapGemmParams {
   int total_tiles;
   int stages;
   int b_stage_bytes;  // max over groups of block_n*128
+  int tap_rot;
   TapGemmGroup g[kMaxGroups];
 };
 
@@ -67,6 +68,7 @@ struct TapGemmParams1 {  // single-group variant (keeps the parameter block smal
   int total_tiles;
   int stages;
   int b_stage_bytes;
+  int tap_rot;
   TapGemmGroup g[1];
 };
 

@@ -46,7 +46,7 @@ __global__ void pack_kernel(const float* __restrict__ ref, float* __restrict__ p
       int kref = k_map ? k_map[kk] : kk;
       if (rref >= 0 && kref >= 0) v = ref[rref * rs + kref * ks + t];
     }
-    packed[i] = round ? round_tf32(v) : v;
+    packed[i] = (round == 1) ? round_tf32(v) : ((round == 2) ? (v - round_tf32(v)) : v);
   }
 }
 
@@ -487,6 +487,111 @@ __global__ void sample_scale_kernel(V g, const float* __restrict__ coeff, V u) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ small elementwise ops
+// out = a * b (dropout mask application and its backward)
+__global__ void mul_kernel(V a, V b, V o) {
+  const long long total = (long long)a.n * a.h * a.w * a.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % a.c);
+    long long r = i / a.c;
+    int x = (int)(r % a.w);
+    r /= a.w;
+    int y = (int)(r % a.h);
+    int n = (int)(r / a.h);
+    o.p[voff(o, n, y, x) + c] = a.p[voff(a, n, y, x) + c] * b.p[voff(b, n, y, x) + c];
+  }
+}
+// out[n] = alpha[n] * a[n] + (1 - alpha[n]) * b[n]   (WGAN-GP interpolate)
+__global__ void lerp_kernel(V a, V b, const float* __restrict__ alpha, V o) {
+  const long long total = (long long)a.n * a.h * a.w * a.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % a.c);
+    long long r = i / a.c;
+    int x = (int)(r % a.w);
+    r /= a.w;
+    int y = (int)(r % a.h);
+    int n = (int)(r / a.h);
+    const float t = alpha[n];
+    o.p[voff(o, n, y, x) + c] = t * a.p[voff(a, n, y, x) + c] + (1.f - t) * b.p[voff(b, n, y, x) + c];
+  }
+}
+// gradient-penalty scalars: coeff[n] = scale * (||g_n|| - 1) / ||g_n|| ; gp_sum += sum_n (||g_n|| - 1)^2
+__global__ void gp_coeff_kernel(const float* __restrict__ sqnorm, float* __restrict__ coeff, int n, float scale,
+                                float* __restrict__ gp_sum) {
+  float part = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float nr = sqrtf(sqnorm[i]);
+    const float d = nr - 1.f;
+    coeff[i] = nr > 0.f ? scale * d / nr : 0.f;
+    part += d * d;
+  }
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) red[wp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    if (gp_sum) atomicAdd(gp_sum, s);
+  }
+}
+// fill every element of a view with a constant
+__global__ void fill_kernel(V o, float v) {
+  const long long total = (long long)o.n * o.h * o.w * o.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % o.c);
+    long long r = i / o.c;
+    int x = (int)(r % o.w);
+    r /= o.w;
+    int y = (int)(r % o.h);
+    int n = (int)(r / o.h);
+    o.p[voff(o, n, y, x) + c] = v;
+  }
+}
+// softmax cross-entropy over rows of logits (B, C): loss_sum += sum_n -log softmax(x_n)[label_n];
+// dlogits = coeff * (softmax - onehot).  One warp per row.
+__global__ void softmax_ce_kernel(const float* __restrict__ x, long long row_stride, const long long* __restrict__ label,
+                                  float* __restrict__ dx, long long drow_stride, int rows, int cols, float coeff,
+                                  float* __restrict__ loss_sum) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * row_stride;
+  float m = -INFINITY;
+  for (int j = lane; j < cols; j += 32) m = fmaxf(m, xr[j]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int j = lane; j < cols; j += 32) s += expf(xr[j] - m);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int lab = (int)label[row];
+  const float lse = m + logf(s);
+  if (lane == 0 && loss_sum) atomicAdd(loss_sum, lse - xr[lab]);
+  if (dx) {
+    float* dr = dx + row * drow_stride;
+    for (int j = lane; j < cols; j += 32) dr[j] = coeff * (expf(xr[j] - lse) - (j == lab ? 1.f : 0.f));
+  }
+}
+
+
+// hi = rna_tf32(src), lo = src - hi  (operand split of the fp32-exact verification mode: a*w ~ ah*wh + ah*wl + al*wh)
+__global__ void split_tf32_kernel(V s, V hi, V lo) {
+  const long long total = (long long)s.n * s.h * s.w * s.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % s.c);
+    long long r = i / s.c;
+    int x = (int)(r % s.w);
+    r /= s.w;
+    int y = (int)(r % s.h);
+    int n = (int)(r / s.h);
+    const float v = s.p[voff(s, n, y, x) + c];
+    const float h = round_tf32(v);
+    hi.p[voff(hi, n, y, x) + c] = h;
+    lo.p[voff(lo, n, y, x) + c] = v - h;
+  }
+}
+
 static bool same_geom(const tpgan_view& a, const tpgan_view& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
@@ -685,6 +790,52 @@ int tpgan_sample_scale(tpgan_view g, const float* coeff, tpgan_view u, void* str
   long long total = (long long)g.n * g.h * g.w * g.c;
   sample_scale_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(g), coeff, dv(u));
   TPG_CHECK_LAUNCH("sample_scale");
+  return 0;
+}
+
+int tpgan_mul(tpgan_view a, tpgan_view b, tpgan_view out, void* stream) {
+  if (!same_geom(a, b) || !same_geom(a, out)) return set_error(TPGAN_ERR_INVALID, "mul: geometry mismatch");
+  long long total = (long long)a.n * a.h * a.w * a.c;
+  mul_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(a), dv(b), dv(out));
+  TPG_CHECK_LAUNCH("mul");
+  return 0;
+}
+int tpgan_lerp(tpgan_view a, tpgan_view b, const float* alpha, tpgan_view out, void* stream) {
+  if (!same_geom(a, b) || !same_geom(a, out)) return set_error(TPGAN_ERR_INVALID, "lerp: geometry mismatch");
+  long long total = (long long)a.n * a.h * a.w * a.c;
+  lerp_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(a), dv(b), alpha, dv(out));
+  TPG_CHECK_LAUNCH("lerp");
+  return 0;
+}
+int tpgan_gp_coeff(const float* sqnorm, float* coeff, int32_t n, float scale, float* gp_sum, void* stream) {
+  if (n < 1) return set_error(TPGAN_ERR_INVALID, "gp_coeff: n < 1");
+  gp_coeff_kernel<<<1, 256, 0, ST>>>(sqnorm, coeff, n, scale, gp_sum);
+  TPG_CHECK_LAUNCH("gp_coeff");
+  return 0;
+}
+int tpgan_fill(tpgan_view out, float value, void* stream) {
+  long long total = (long long)out.n * out.h * out.w * out.c;
+  if (total <= 0) return 0;
+  fill_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(out), value);
+  TPG_CHECK_LAUNCH("fill");
+  return 0;
+}
+int tpgan_softmax_ce(const float* logits, int64_t row_stride, const int64_t* labels, float* dlogits, int64_t drow_stride,
+                     int32_t rows, int32_t cols, float coeff, float* loss_sum, void* stream) {
+  if (rows < 1 || cols < 1) return set_error(TPGAN_ERR_INVALID, "softmax_ce: empty");
+  const int wpb = 4;
+  softmax_ce_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, ST>>>(logits, row_stride, (const long long*)labels, dlogits,
+                                                                 drow_stride, rows, cols, coeff, loss_sum);
+  TPG_CHECK_LAUNCH("softmax_ce");
+  return 0;
+}
+
+int tpgan_split_tf32(tpgan_view src, tpgan_view hi, tpgan_view lo, void* stream) {
+  if (!same_geom(src, hi) || !same_geom(src, lo)) return set_error(TPGAN_ERR_INVALID, "split_tf32: geometry mismatch");
+  long long total = (long long)src.n * src.h * src.w * src.c;
+  if (total <= 0) return 0;
+  split_tf32_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(src), dv(hi), dv(lo));
+  TPG_CHECK_LAUNCH("split_tf32");
   return 0;
 }
 

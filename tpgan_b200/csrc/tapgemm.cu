@@ -97,15 +97,22 @@ __global__ void __launch_bounds__(256, 1) tapgemm_kernel(const __grid_constant__
         const TapGemmGroup& G = P.g[tc.gi];
         const uint32_t tx = (uint32_t)(G.bw * G.bh * G.bn + G.block_n) * 128u;
         const PhaseDesc ph = G.phase[tc.ph];
-        for (int t = 0; ok && t < ph.tap_count; ++t) {
+        const int rot = (P.tap_rot & 1) ? (int)(blockIdx.x % (unsigned)ph.tap_count) : 0;
+        for (int t0 = 0; ok && t0 < ph.tap_count; ++t0) {
+          int t = t0 + rot;
+          if (t >= ph.tap_count) t -= ph.tap_count;
           const TapDesc tap = G.taps[ph.tap_begin + t];
           const CUtensorMap* am = &G.amap[tap.plane];
           for (int c = 0; c < G.kchunks; ++c) {
             if (!mbar_wait(&empty_bar[stage], phase ^ 1u, ac, 1)) { ok = false; break; }
             uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], tx);
-            tma_load_4d(sa, am, &full_bar[stage], c * 32, tap.dx, tc.h0 + tap.dy, tc.n0);
-            tma_load_3d(sa + kAStageBytes, &G.bmap, &full_bar[stage], c * 32, tc.nt * G.block_n, tap.wtap);
+            const int dbg = P.tap_rot >> 4;
+            uint32_t txx = 0;
+            if (!(dbg & 1)) txx += (uint32_t)(G.bw * G.bh * G.bn) * 128u;
+            if (!(dbg & 2)) txx += (uint32_t)G.block_n * 128u;
+            if (txx) mbar_arrive_expect_tx(&full_bar[stage], txx); else mbar_arrive(&full_bar[stage]);
+            if (!(dbg & 1)) tma_load_4d(sa, am, &full_bar[stage], c * 32, tap.dx, tc.h0 + tap.dy, tc.n0);
+            if (!(dbg & 2)) tma_load_3d(sa + kAStageBytes, &G.bmap, &full_bar[stage], c * 32, tc.nt * G.block_n, tap.wtap);
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
@@ -136,6 +143,7 @@ __global__ void __launch_bounds__(256, 1) tapgemm_kernel(const __grid_constant__
             const uint32_t b_addr = a_addr + kAStageBytes;
             const int nm = (c == G.kchunks - 1) ? G.last_mmas : 4;
             for (int k = 0; k < nm; ++k) {
+              if ((P.tap_rot >> 4) & 4) break;
               mma_tf32_ss(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
                           idesc, acc);
               acc = 1;

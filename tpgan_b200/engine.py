@@ -35,6 +35,7 @@ class T:
         self.cmap: Optional[List[int]] = None    # internal channel -> reference channel (-1 = padding lane)
         self.ref_c: int = act.c                  # number of reference (logical) channels
         self.grad: Optional[Act] = None
+        self.flat = False                        # (B,1,1,C) tensor that the module API exposes as (B, C)
         # backward-trace state
         self.pending = 0
         self.grad_written = False
@@ -50,36 +51,45 @@ class T:
 
 
 class ConvLayer:
-    """One Conv2d / ConvTranspose2d of the reference model: reference-layout parameters + tensor-core packings."""
+    """One Conv2d / ConvTranspose2d / Linear of the reference model: reference-layout parameters + tensor-core packings.
+
+    `w_shape` lets a Linear be run as a convolution (fc1 = 8x8 valid conv over the 8x8x512 map, feature_predict.fc = 1x1)."""
 
     def __init__(self, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter], transposed: bool, k: int,
-                 stride: int, pad: int, name: str = ""):
+                 stride: int, pad: int, name: str = "", w_shape: Optional[Sequence[int]] = None):
         self.weight, self.bias = weight, bias
+        self.w_shape = tuple(weight.shape) if w_shape is None else tuple(w_shape)
         self.transposed = transposed
         self.k, self.stride, self.pad = k, stride, pad
         self.name = name
         self.kind_fwd = DECONV_FWD if transposed else CONV_FWD
         self.kind_dgrad = DECONV_DGRAD if transposed else CONV_DGRAD
-        self.cin = weight.shape[0] if transposed else weight.shape[1]
-        self.cout = weight.shape[1] if transposed else weight.shape[0]
+        self.cin = self.w_shape[0] if transposed else self.w_shape[1]
+        self.cout = self.w_shape[1] if transposed else self.w_shape[0]
+        self.bias_view = None
         self.ready = False
 
     def setup(self, in_cmap: Optional[List[int]], out_cmap: Optional[List[int]], in_c: int, out_c: int, device,
-              need_dgrad: bool = True):
+              need_dgrad: bool = True, exact: bool = False):
         """Allocate packings for the internal channel layouts seen at trace time (idempotent; layouts must not change)."""
         key = (tuple(in_cmap) if in_cmap else None, tuple(out_cmap) if out_cmap else None, in_c, out_c)
         if self.ready:
             assert key == self._key, f"{self.name}: channel layout changed between traces"
+            if exact and self.wf_lo is None:
+                self._alloc_lo()
+                self.repack()
             return
+        self.wf_lo = self.wd_lo = None
+        self._want_lo = exact
         self._key = key
         mk = lambda m: None if m is None else torch.tensor(m, dtype=torch.int32, device=device)
         self.in_map, self.out_map = mk(in_cmap), mk(out_cmap)
         self.in_c, self.out_c = in_c, out_c  # internal widths (incl. padding lanes when a map is given)
-        shp = tuple(self.weight.shape)
-        self.wf = ops.alloc_packed(self.kind_fwd, shp, rows_int=out_c, k_int=in_c, device=device)
-        self.wd = ops.alloc_packed(self.kind_dgrad, shp, rows_int=in_c, k_int=out_c, device=device) if need_dgrad else None
-        self.dw = ops.alloc_packed(self.kind_fwd, shp, rows_int=out_c, k_int=in_c, device=device)
-        self.bias_int = torch.zeros(round_up(out_c, 4), dtype=torch.float32, device=device) if self.bias is not None else None
+        self._alloc(device, need_dgrad)
+        if exact:
+            self._alloc_lo()
+        self.bias_int = torch.zeros(round_up(self.bias_len(), 4), dtype=torch.float32, device=device) \
+            if self.bias is not None else None
         self.db_int = torch.zeros_like(self.bias_int) if self.bias is not None else None
         if out_cmap is not None:
             oc = torch.tensor(out_cmap, dtype=torch.long, device=device)
@@ -88,20 +98,63 @@ class ConvLayer:
         self.ready = True
         self.repack()
 
+    def bias_len(self):
+        return self.out_c
+
+    def _alloc(self, device, need_dgrad):
+        shp = self.w_shape
+        self.wf = ops.alloc_packed(self.kind_fwd, shp, rows_int=self.out_c, k_int=self.in_c, device=device)
+        self.wd = ops.alloc_packed(self.kind_dgrad, shp, rows_int=self.in_c, k_int=self.out_c, device=device) \
+            if need_dgrad else None
+        self.dw = ops.alloc_packed(self.kind_fwd, shp, rows_int=self.out_c, k_int=self.in_c, device=device)
+
+    def _alloc_lo(self):
+        """Residual packings w - tf32(w) for the fp32-exact verification mode (Plan(exact=True))."""
+        cp = lambda pk: None if pk is None else ops.Packed(torch.zeros_like(pk.data), pk.taps, pk.rows, pk.k, pk.rows_pad,
+                                                          pk.k_pad)
+        self.wf_lo, self.wd_lo = cp(self.wf), cp(self.wd)
+
+    def _w(self):
+        return self.weight.data.view(self.w_shape)
+
     def repack(self):
         """Reference-layout fp32 master weights -> tf32-rounded K-major packings (after every optimizer step)."""
         if not self.ready:
             return
-        w = self.weight.data
+        w = self._w()
         ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map)
         if self.wd is not None:
             ops.pack_weights(w, self.kind_dgrad, self.wd, row_map=self.in_map, k_map=self.out_map)
+        if self.wf_lo is not None:
+            ops.pack_weights(w, self.kind_fwd, self.wf_lo, row_map=self.out_map, k_map=self.in_map, round_tf32=2)
+            if self.wd_lo is not None:
+                ops.pack_weights(w, self.kind_dgrad, self.wd_lo, row_map=self.in_map, k_map=self.out_map, round_tf32=2)
+        self._repack_bias()
+
+    def _repack_bias(self):
         if self.bias is not None:
             if self.out_map is None:
                 self.bias_int[: self.cout].copy_(self.bias.data)
             else:
                 self.bias_int.zero_()
                 self.bias_int[self._b_valid] = self.bias.data[self._b_ref]
+
+    def _versions(self):
+        return (self.weight._version, self.weight.data_ptr(), None if self.bias is None else self.bias._version)
+
+    def refresh(self):
+        """Repack if the reference-layout parameters changed since the last pack (optimizer.step, load_state_dict)."""
+        if self.ready and getattr(self, "_packed_ver", None) != self._versions():
+            self.repack()
+            self._packed_ver = self._versions()
+
+    def export_grad_autograd(self):
+        """Accumulate this layer's gradients into param.grad (autograd semantics), creating it when absent."""
+        for p in (self.weight, self.bias):
+            if p is not None and p.requires_grad and p.grad is None:
+                p.grad = torch.zeros_like(p)
+        if self.weight.requires_grad:
+            self.export_grad(accumulate=True)
 
     def zero_grad(self):
         if self.ready:
@@ -113,8 +166,11 @@ class ConvLayer:
         """Packed dW / internal db -> .grad of the reference-layout parameters."""
         if not self.ready or self.weight.grad is None:
             return
-        ops.unpack_weights(self.dw, self.weight.grad, self.kind_fwd, row_map=self.out_map, k_map=self.in_map,
-                           accumulate=accumulate)
+        ops.unpack_weights(self.dw, self.weight.grad.view(self.w_shape), self.kind_fwd, row_map=self.out_map,
+                           k_map=self.in_map, accumulate=accumulate)
+        self._export_bias(accumulate)
+
+    def _export_bias(self, accumulate):
         if self.bias is not None and self.bias.grad is not None:
             if self.out_map is None:
                 src = self.db_int[: self.cout]
@@ -127,11 +183,74 @@ class ConvLayer:
                 self.bias.grad.copy_(src)
 
 
+class DeconvAsLinear(ConvLayer):
+    """ConvTranspose2d(k, stride 1, pad 0) applied to a 1x1 map (deconv_8, D_and_G_model.py:218): a plain GEMM
+    (B, Cin) x (Cin, k*k*Cout) whose NHWC output (B, k, k, Cout) is the flat row (tap, co).  Runs as a 1x1 convolution
+    with N = k*k*Cout; the DECONV_FWD packing [tap][co][ci] *is* the [n = tap*Cout + co][ci] operand."""
+
+    def __init__(self, weight, bias, k: int, name: str = ""):
+        cin, cout = weight.shape[0], weight.shape[1]
+        super().__init__(weight, bias, False, 1, 1, 0, name, w_shape=(k * k * cout, cin, 1, 1))
+        self.ref_shape = tuple(weight.shape)
+        self.kk, self.co = k * k, cout
+        assert cout % 16 == 0
+        self.bias_view = (k, k, cout)
+
+    def bias_len(self):
+        return self.co
+
+    def _alloc(self, device, need_dgrad):
+        assert self.out_map is None and self.in_map is None and self.in_c % 32 == 0
+        n, kdim = self.kk * self.co, self.in_c
+        mk = lambda: torch.zeros((2, n, kdim), dtype=torch.float32, device=device)
+        self.wf = ops.Packed(mk(), 1, n, kdim, n, kdim)
+        self.dw = ops.Packed(mk(), 1, n, kdim, n, kdim)
+        # views of the same storage in the [taps+1][Cout][Cin] geometry the (un)pack kernels use
+        self._wf_taps = ops.Packed(self.wf.data, self.kk, self.co, kdim, self.co, kdim)
+        self._dw_taps = ops.Packed(self.dw.data, self.kk, self.co, kdim, self.co, kdim)
+        self.wd = ops.Packed(torch.zeros((2, round_up(kdim, 16), n), dtype=torch.float32, device=device), 1, kdim, n,
+                             round_up(kdim, 16), n)
+        kk, co = self.kk, self.co
+        idx = torch.arange(n, dtype=torch.int64)
+        self._kmap_d = ((idx % co) * kk + idx // co).to(torch.int32).to(device)  # (tap, co) -> co*kk + tap
+        self.bias_full = torch.zeros(n, dtype=torch.float32, device=device)
+
+    def _alloc_lo(self):
+        super()._alloc_lo()
+        self._wf_lo_taps = ops.Packed(self.wf_lo.data, self.kk, self.co, self.in_c, self.co, self.in_c)
+
+    def repack(self):
+        if not self.ready:
+            return
+        w = self.weight.data
+        ops.pack_weights(w, DECONV_FWD, self._wf_taps)
+        lib = ops._lib.load()
+        n = self.kk * self.co
+        ops._lib.check(lib.tpgan_pack_weights(w.data_ptr(), self.wd.data.data_ptr(), 1, self.in_c, n, self.wd.rows_pad, n,
+                                              n, 1, None, self._kmap_d.data_ptr(), 1, ops._stream()), "pack deconv_8 dgrad")
+        if self.wf_lo is not None:
+            ops.pack_weights(w, DECONV_FWD, self._wf_lo_taps, round_tf32=2)
+            ops._lib.check(lib.tpgan_pack_weights(w.data_ptr(), self.wd_lo.data.data_ptr(), 1, self.in_c, n,
+                                                  self.wd.rows_pad, n, n, 1, None, self._kmap_d.data_ptr(), 2,
+                                                  ops._stream()), "pack deconv_8 dgrad lo")
+        if self.bias is not None:
+            self.bias_full.view(self.kk, self.co).copy_(self.bias.data.view(1, self.co).expand(self.kk, self.co))
+
+    def export_grad(self, accumulate: bool = False):
+        if not self.ready or self.weight.grad is None:
+            return
+        ops.unpack_weights(self._dw_taps, self.weight.grad, DECONV_FWD, accumulate=accumulate)
+        if self.bias is not None and self.bias.grad is not None:
+            src = self.db_int[: self.co]
+            self.bias.grad.add_(src) if accumulate else self.bias.grad.copy_(src)
+
+
 class Plan:
     """Traced schedule for one network instance and batch size."""
 
-    def __init__(self, device, training: bool = True, need_wgrad: bool = True):
+    def __init__(self, device, training: bool = True, need_wgrad: bool = True, exact: bool = False):
         self.device = device
+        self.exact = exact  # fp32-exact verification mode: every tensor-core product is split hi/lo (3 launches)
         self.training = training
         self.need_wgrad = need_wgrad
         self.fwd: List[Callable[[], None]] = []
@@ -141,6 +260,8 @@ class Plan:
         self.keep: list = []  # keeps buffers / ctypes structs alive
         self.bytes = 0
         self.bwd_marks: Dict[str, int] = {}   # layer name -> index in self.bwd after which its dW is final
+        self.layers: List[ConvLayer] = []     # every conv layer this plan launches (for repack / grad export)
+        self.named: Dict[str, T] = {}         # layer name -> its output tensor (introspection / tests)
 
     # ------------------------------------------------------------------ buffers
     def new(self, n, h, w, c, slope=LINEAR, name="", requires_grad=True) -> T:
@@ -219,18 +340,80 @@ class Plan:
                 out_cmap = r.cmap
                 out.cmap, out.ref_c = r.cmap, r.ref_c
             out.slope = LINEAR if slope is None else slope
-            L.setup(x.cmap, out_cmap, x.act.c, out.act.c, self.device)
+            L.setup(x.cmap, out_cmap, x.act.c, out.act.c, self.device, exact=self.exact)
+            if L not in self.layers:
+                self.layers.append(L)
+            self.named[L.name] = out
             assert (x.ref_c == L.cin) and (out.ref_c == L.cout), (L.name, x.ref_c, L.cin, out.ref_c, L.cout)
-            args.append(ops.conv_args(L.kind_fwd, x.act, out.act, L.wf, L.k, L.stride, L.pad, bias=L.bias_int,
-                                      add1=None if r is None else r.act, slope=0.0 if slope is None else slope,
-                                      epilogue=EPI_LINEAR if slope is None else EPI_LEAKY))
+            args.append(dict(L=L, dgrad=False, x=x.act, out=out.act, bias=getattr(L, "bias_full", L.bias_int),
+                             add1=None if r is None else r.act, slope=0.0 if slope is None else slope,
+                             epilogue=EPI_LINEAR if slope is None else EPI_LEAKY))
             self.use(x)
             if r is not None:
                 self.use(r)
             outs_l.append(out)
-        self.fwd.append(self._conv_launch(args))
+        self._emit_conv(args, self.fwd)
         self.tape.append(lambda: self._bwd_conv(layers, list(xs), outs_l, res))
         return outs_l
+
+    def _emit_conv(self, specs, lst):
+        """specs: dicts {L, dgrad, x, out, bias, add1, add2, mask, slopes, slope, epilogue} of one grouped launch."""
+        def mk(sp, x, out, pack, **kw):
+            L = sp["L"]
+            return ops.conv_args(L.kind_dgrad if sp["dgrad"] else L.kind_fwd, x, out, pack, L.k, L.stride, L.pad,
+                                 round_tf32=not self.exact, **kw)
+        full = lambda sp: dict(bias=sp.get("bias"), add1=sp.get("add1"), add2=sp.get("add2"), mask=sp.get("mask"),
+                               slopes=sp.get("slopes"), slope=sp.get("slope", 0.0), epilogue=sp.get("epilogue", EPI_LINEAR))
+        if not self.exact:
+            lst.append(self._conv_launch([mk(sp, sp["x"], sp["out"], sp["L"].wd if sp["dgrad"] else sp["L"].wf, **full(sp))
+                                          for sp in specs]))
+            return
+        a1, a2, a3 = [], [], []
+        for sp in specs:
+            L, x, out = sp["L"], sp["x"], sp["out"]
+            hi_pack, lo_pack = (L.wd, L.wd_lo) if sp["dgrad"] else (L.wf, L.wf_lo)
+            xh, xl = Act.empty(x.n, x.h, x.w, x.c, self.device), Act.empty(x.n, x.h, x.w, x.c, self.device)
+            tmp = Act.empty(out.n, out.h, out.w, out.c, self.device)
+            self.keep.append((xh, xl, tmp))  # ConvArgs hold raw pointers only
+            lst.append(lambda x=x, xh=xh, xl=xl: ops.split_tf32(x, xh, xl))
+            a1.append(mk(sp, xh, tmp, lo_pack))
+            a2.append(mk(sp, xl, tmp, hi_pack, add1=tmp))
+            kw = full(sp)
+            if kw["add1"] is not None and kw["add2"] is not None:
+                extra = kw["add2"]
+                a2_post = (lambda e=extra, t=tmp: ops.view_copy(e, t, True))
+                kw["add2"] = tmp
+                a3.append((mk(sp, xh, out, hi_pack, **kw), a2_post))
+            else:
+                if kw["add1"] is None:
+                    kw["add1"] = tmp
+                else:
+                    kw["add2"] = tmp
+                a3.append((mk(sp, xh, out, hi_pack, **kw), None))
+        lst.append(self._conv_launch(a1))
+        lst.append(self._conv_launch(a2))
+        for _, post in a3:
+            if post is not None:
+                lst.append(post)
+        lst.append(self._conv_launch([a for a, _ in a3]))
+
+    def _emit_wgrad(self, specs, lst):
+        """specs: (L, x Act, dy Act) of one grouped weight-gradient launch."""
+        mk = lambda L, x, dy: ops.wgrad_args(L.kind_fwd, x, dy, L.dw, L.k, L.stride, L.pad)
+        if not self.exact:
+            lst.append(self._wgrad_launch([mk(L, x, dy) for L, x, dy in specs]))
+            return
+        g1, g2, g3 = [], [], []
+        for L, x, dy in specs:
+            e = lambda a: Act.empty(a.n, a.h, a.w, a.c, self.device)
+            xh, xl, dh, dl = e(x), e(x), e(dy), e(dy)
+            self.keep.append((xh, xl, dh, dl))
+            lst.append(lambda x=x, xh=xh, xl=xl, dy=dy, dh=dh, dl=dl: (ops.split_tf32(x, xh, xl), ops.split_tf32(dy, dh, dl)))
+            g1.append(mk(L, xh, dh))
+            g2.append(mk(L, xl, dh))
+            g3.append(mk(L, xh, dl))
+        for g in (g1, g2, g3):
+            lst.append(self._wgrad_launch(g))
 
     def _conv_launch(self, args):
         arr = (ops.ConvArgs * len(args))(*args)
@@ -300,6 +483,105 @@ class Plan:
             contribs = [(lambda fn, x=x: self._contribute(x, fn)) for x in inputs]
             bwd(contribs)
         self.tape.append(tape_fn)
+
+    def alias(self, src: T, h: int, w: int, c: int, name: str = "") -> T:
+        """Same storage seen with another (h, w, c) factorisation of the per-image row (e.g. deconv_8's (1,1,4096) GEMM row
+        = the (8,8,64) NHWC map).  `src` must have no other consumer; the alias has no activation of its own."""
+        buf = src.act.buf
+        n = buf.shape[0]
+        assert src.act.c0 == 0 and src.act.c == buf.shape[3] and buf.shape[1] * buf.shape[2] * buf.shape[3] == h * w * c
+        nbuf = buf.view(n, h, w, c)
+        out = T(Act(nbuf, 0, c), LINEAR, name or src.name + ".alias")
+        self.use(src)
+        self.keep.append(nbuf)
+
+        def bwd():
+            if not self._has_grad(out):
+                return self._null(src)
+            self._finalize(out)
+            assert not src.grad_written, "alias source must have a single consumer"
+            src.grad = Act(self.grad_act(out).buf.view(buf.shape), 0, src.act.c)
+            src.grad_written = True
+            src.pending -= 1
+        # the two T's must share one gradient buffer: allocate it through the alias and view it back
+        self.tape.append(bwd)
+        return out
+
+    def local_fuse(self, parts: Sequence[T], out: T, name: str = "fuse") -> T:
+        """LocalFuser (D_and_G_model.py:132-159): max over the four zero-padded patches at the fixed offsets."""
+        need_grad = any(p.requires_grad for p in parts)
+        n, c = out.act.n, out.act.c
+        argmax = torch.empty((n, 128, 128, c), dtype=torch.uint8, device=self.device) if need_grad else None
+        self.bytes += 0 if argmax is None else argmax.numel()
+        out.slope = LINEAR
+        acts = [p.act for p in parts]
+        for p in parts:
+            self.use(p)
+        self.fwd.append(lambda: ops.local_fuse(acts, out.act, argmax))
+        self.fuse_argmax = getattr(self, "fuse_argmax", {})
+        self.fuse_argmax[name] = argmax
+
+        def bwd():
+            if not need_grad or not self._has_grad(out):
+                for p in parts:
+                    self._null(p)
+                return
+            self._finalize(out)
+            g = self.grad_act(out)
+            written = [all(l.grad_written for l in p.leaves()) for p in parts]
+            acc = any(written)
+            if acc and not all(written):
+                for p in parts:
+                    self._zero_unwritten(p)
+            dsts = [self.grad_act(p) for p in parts]
+            self.bwd.append(lambda: ops.local_fuse_backward(g, argmax, dsts, acc))
+            for p in parts:
+                for l in p.leaves():
+                    l.grad_written = True
+                    l.pending -= 1
+        self.tape.append(bwd)
+        return out
+
+    def maxout2(self, x: T, name: str = "maxout") -> T:
+        """nn.MaxPool1d(2,2) over adjacent feature pairs of a (B,1,1,2C) row (D_and_G_model.py:214,290)."""
+        n, c2 = x.act.n, x.act.c
+        assert x.act.h == 1 and x.act.w == 1 and c2 % 8 == 0 and x.act.c0 == 0 and x.act.buf.shape[3] == c2
+        out = self.new(n, 1, 1, c2 // 2, name=name)
+        self.use(x)
+        xb, yb = x.act.buf.view(n, c2), out.act.buf.view(n, c2 // 2)
+        self.fwd.append(lambda: ops.maxout2(xb, yb))
+
+        def bwd():
+            if not self._has_grad(out):
+                return self._null(x)
+            self._finalize(out)
+            g = self.grad_act(out).buf.view(n, c2 // 2)
+
+            def emit(dst, acc):
+                assert not acc
+                ops.maxout2_backward(xb, g, dst.buf.view(n, c2))
+            self._contribute(x, emit)
+        self.tape.append(bwd)
+        return out
+
+    def mul_mask(self, x: T, mask: Act, name: str = "dropout") -> T:
+        """y = x * mask (nn.Dropout with an externally drawn, pre-scaled mask; D_and_G_model.py:344-346)."""
+        out = self.new(x.act.n, x.act.h, x.act.w, x.act.c, name=name)
+        self.use(x)
+        self.fwd.append(lambda: ops.mul(x.act, mask, out.act))
+
+        def bwd():
+            if not self._has_grad(out):
+                return self._null(x)
+            self._finalize(out)
+            g = self.grad_act(out)
+
+            def emit(dst, acc):
+                assert not acc
+                ops.mul(g, mask, dst)
+            self._contribute(x, emit)
+        self.tape.append(bwd)
+        return out
 
     # ------------------------------------------------------------------ backward tracing
     def seed_grad(self, t: T):
@@ -381,13 +663,13 @@ class Plan:
             self._finalize(outs[i])
         # weight / bias gradients
         if self.need_wgrad:
-            wargs = [ops.wgrad_args(layers[i].kind_fwd, xs[i].act, self.grad_act(outs[i]), layers[i].dw, layers[i].k,
-                                    layers[i].stride, layers[i].pad) for i in live]
-            self.bwd.append(self._wgrad_launch(wargs))
+            self._emit_wgrad([(layers[i], xs[i].act, self.grad_act(outs[i])) for i in live], self.bwd)
             for i in live:
                 L = layers[i]
                 if L.db_int is not None:
                     g = self.grad_act(outs[i])
+                    if L.bias_view is not None:
+                        g = Act(g.buf.view(g.n, *L.bias_view))
                     self.bwd.append(lambda g=g, L=L: ops.bias_grad(g, L.db_int, True))
             for i in live:
                 self.bwd_marks[layers[i].name] = len(self.bwd)
@@ -443,13 +725,13 @@ class Plan:
                         vec[o:o + p.act.c] = s
                     slope_vec = vec.to(self.device)
                     self.keep.append(slope_vec)
-            dargs.append(ops.conv_args(L.kind_dgrad, self.grad_act(outs[i]), dst, L.wd, L.k, L.stride, L.pad,
-                                       add1=adds[0] if len(adds) > 0 else None, add2=adds[1] if len(adds) > 1 else None,
-                                       mask=mask, slopes=slope_vec, slope=slope_val, epilogue=epi, round_tf32=True))
+            dargs.append(dict(L=L, dgrad=True, x=self.grad_act(outs[i]), out=dst,
+                              add1=adds[0] if len(adds) > 0 else None, add2=adds[1] if len(adds) > 1 else None,
+                              mask=mask, slopes=slope_vec, slope=slope_val, epilogue=epi))
             for p in leaves:
                 p.grad_written = True
         if dargs:
-            self.bwd.append(self._conv_launch(dargs))
+            self._emit_conv(dargs, self.bwd)
 
     # ------------------------------------------------------------------ replay
     def run_forward(self):

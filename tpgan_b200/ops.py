@@ -124,7 +124,7 @@ def alloc_packed(kind: int, w_shape: Sequence[int], rows_int: Optional[int] = No
 
 
 def pack_weights(w: torch.Tensor, kind: int, out: Optional[Packed] = None, row_map: Optional[torch.Tensor] = None,
-                 k_map: Optional[torch.Tensor] = None, round_tf32: bool = True) -> Packed:
+                 k_map: Optional[torch.Tensor] = None, round_tf32=True) -> Packed:
     """Reference-layout weight -> tensor-core layout for the GEMM of `kind`.  row_map/k_map (int32, device) give for each
     internal row / k index the reference channel (-1 = padding)."""
     w = w.detach()
@@ -254,3 +254,34 @@ def sample_sqnorm(g: Act, out: torch.Tensor) -> None:
 
 def sample_scale(g: Act, coeff: torch.Tensor, u: Act) -> None:
     _lib.check(_lib.load().tpgan_sample_scale(g.view(), coeff.data_ptr(), u.view(), _stream()), "sample_scale")
+
+
+def gp_coeff(sqnorm: torch.Tensor, coeff: torch.Tensor, scale: float, gp_sum: Optional[torch.Tensor]) -> None:
+    _lib.check(_lib.load().tpgan_gp_coeff(sqnorm.data_ptr(), coeff.data_ptr(), sqnorm.numel(), float(scale), _ptr(gp_sum),
+                                          _stream()), "gp_coeff")
+
+
+def lerp(a: Act, b: Act, alpha: torch.Tensor, out: Act) -> None:
+    assert alpha.dtype == torch.float32 and alpha.numel() == a.n
+    _lib.check(_lib.load().tpgan_lerp(a.view(), b.view(), alpha.data_ptr(), out.view(), _stream()), "lerp")
+
+
+def mul(a: Act, b: Act, out: Act) -> None:
+    _lib.check(_lib.load().tpgan_mul(a.view(), b.view(), out.view(), _stream()), "mul")
+
+
+def split_tf32(src: Act, hi: Act, lo: Act) -> None:
+    _lib.check(_lib.load().tpgan_split_tf32(src.view(), hi.view(), lo.view(), _stream()), "split_tf32")
+
+
+def fill(out: Act, value: float) -> None:
+    _lib.check(_lib.load().tpgan_fill(out.view(), float(value), _stream()), "fill")
+
+
+def softmax_ce(logits: Act, labels: torch.Tensor, dlogits: Optional[Act], coeff: float, loss_sum: torch.Tensor) -> None:
+    """logits: (B,1,1,C) Act; labels int64 (B,)."""
+    assert labels.dtype == torch.int64 and labels.is_cuda and logits.h == 1 and logits.w == 1
+    lv = logits.view()
+    dptr, dstride = (None, 0) if dlogits is None else (dlogits.view().ptr, dlogits.view().sn)
+    _lib.check(_lib.load().tpgan_softmax_ce(lv.ptr, lv.sn, labels.data_ptr(), dptr, dstride, logits.n, logits.c,
+                                            float(coeff), loss_sum.data_ptr(), _stream()), "softmax_ce")
