@@ -1,0 +1,448 @@
+"""The TP-GAN G+D training step on the C-ABI kernels.
+
+The reference ships no training loop and no loss code - only the loss weights (config.py:71-82), `train` hyper-parameters
+(config.py:50-57), set_requires_grad (UtilityMethods.py:43-56) and the TrainDataset batch keys (DataAndDataset.py:206-226).
+The step implemented here is the one oracle/step.py defines from those and is checked against it:
+
+  D phase : L_D = mean D(fake) - mean D(real) + 10 * mean_n (||grad_xhat sum D(xhat_n)||_2 - 1)^2     (WGAN-GP critic)
+  G phase : L_G = 1.0*pixel + 3.0*local + 0.3*symmetry + 1e-3*(-mean D(fake)) + 1e-3*tv + 10*CE
+  Adam(lr = train['learning_rate'] = 1e-4) on both networks.
+
+Everything on the device is a launch of libtpgan_b200.so:
+  * landmark crop of the 4 profile + 4 frontal patches (one kernel each),
+  * the generator forward/backward plan of tpgan_b200.D_and_G_model (tcgen05 convs, grouped local pathways, fused stitch),
+  * the critic: ONE batched forward over [fake; real; xhat], one batched dgrad chain, weight gradients on the fake/real
+    part, and the gradient penalty's double backward as a *tangent forward* - because D is piecewise linear
+    (conv + LeakyReLU, no BN), d GP / d W_l = wgrad(x = v_{l-1}, dy = e_l) where e_l are the masked deltas of the
+    backward pass seeded with ones and v_l = mask_l * (W_l v_{l-1}) is the forward pass of u = dGP/dg through the same
+    masks.  No autograd graph, no second-order kernels.
+  * fused image losses (pixel L1 at 3 scales + symmetry + TV in one pass, writing dL/dfake), patch L1, softmax-CE,
+  * flat-buffer Adam (one launch per network), weight re-packing into the tensor-core layout.
+Data parallelism (tpgan_b200.parallel) all-reduces the flat gradient buffers in buckets overlapped with backward.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from . import config as cfg
+from . import ops
+from .D_and_G_model import PART_NAMES, PATCH_HW, Discriminator, Generator, _layer, _unpack_conv_seq
+from .engine import LINEAR, ConvLayer, Plan, T
+from .ModificationLayer import ResidualBlock, _negative_slope
+from .ops import Act, EPI_LEAKY, EPI_LINEAR, EPI_MASK
+
+
+def _sl(a: Act, n0: int, n1: int) -> Act:
+    """Batch slice [n0, n1) of an activation (same channel window)."""
+    return Act(a.buf[n0:n1], a.c0, a.c)
+
+
+# ---------------------------------------------------------------------------------------------------------- flat buffers
+class FlatParams:
+    """All parameters of a module as views into ONE flat fp32 buffer (and their .grad into a second one), so the optimizer
+    is a single kernel launch and the gradient all-reduce works on contiguous buckets.  `order` = parameter names in the
+    order their gradients become final during backward (bucket order)."""
+
+    def __init__(self, module: torch.nn.Module, order: Optional[Sequence[str]] = None):
+        named = dict(module.named_parameters())
+        names = list(named.keys())
+        if order is not None:
+            seen = set()
+            names = [n for n in order if n in named and not (n in seen or seen.add(n))] + \
+                    [n for n in named if n not in set(order)]
+        self.names = names
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for n in names:
+            self.offsets[n] = off
+            off += ops.round_up(named[n].numel(), 4)
+        self.total = off
+        dev = named[names[0]].device
+        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.step = 0
+        for n in names:
+            p = named[n]
+            o, k = self.offsets[n], p.numel()
+            self.data[o:o + k].copy_(p.data.flatten())
+            p.data = self.data[o:o + k].view(p.shape)
+            p.grad = self.grad[o:o + k].view(p.shape)
+
+    def adam(self, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        self.step += 1
+        ops.adam_step(self.data, self.grad, self.m, self.v, lr, betas[0], betas[1], eps, weight_decay, self.step, grad_scale)
+
+
+# ---------------------------------------------------------------------------------------------------------- critic
+class CriticPlan:
+    """Static schedule of the discriminator (reference D_and_G_model.py:409-435) for a batch of M images, with the native
+    WGAN-GP machinery described in the module docstring."""
+
+    def __init__(self, D: Discriminator, M: int, B: int, device, exact: bool = False):
+        self.D, self.M, self.B, self.device, self.exact = D, M, B, device, exact
+        self.h = Plan(device, exact=exact)  # launch emitters / keep-alive only
+        new = lambda n, hw, c: Act.empty(n, hw, hw, c, device)
+        self.x0 = new(M, 128, 3)
+        self.ops_: List[dict] = []
+        cur, hw = self.x0, 128
+        self.layers: List[ConvLayer] = []
+        for i, m in enumerate(D.model):
+            if isinstance(m, ResidualBlock):
+                assert len(m.shortcut) == 0 and m.scaling_factor == 1.0
+                L1 = self._mk(m.layers[0], f"model.{i}.layers.0", cur.c)
+                L2 = self._mk(m.layers[1], f"model.{i}.layers.1", cur.c)
+                hmid, y = new(M, hw, L1.cout), new(M, hw, L2.cout)
+                s1 = _unpack_conv_seq(m.layers[0])[2]
+                self.ops_.append(dict(kind="res", L1=L1, L2=L2, x=cur, h=hmid, y=y, s1=s1, s2=_negative_slope(m.activation)))
+                cur = y
+            else:
+                _, cm, slope = _unpack_conv_seq(m)
+                L = self._mk(m, f"model.{i}", cur.c)
+                hw = (hw + 2 * L.pad - L.k) // L.stride + 1
+                y = new(M, hw, L.cout)
+                self.ops_.append(dict(kind="conv", L=L, x=cur, y=y, s=slope))
+                cur = y
+        self.logits = cur
+        # gradient (masked delta) buffers, one per activation, and tangent buffers (B images)
+        self.g: Dict[int, Act] = {}
+        self.v: Dict[int, Act] = {}
+        for op in self.ops_:
+            for a in ([op["x"], op["y"]] + ([op["h"]] if op["kind"] == "res" else [])):
+                if id(a.buf) not in self.g:
+                    self.g[id(a.buf)] = Act.empty(M, a.h, a.w, a.c, device)
+                    self.v[id(a.buf)] = Act.empty(B, a.h, a.w, a.c, device)
+        self.g_logits_g = Act.empty(B, self.logits.h, self.logits.w, 1, device)  # seed of the G phase
+        self.sq = torch.zeros(B, dtype=torch.float32, device=device)
+        self.coeff = torch.zeros(B, dtype=torch.float32, device=device)
+        self.gp_sum = torch.zeros(1, dtype=torch.float32, device=device)
+        self._slope_of: Dict[int, float] = {id(self.x0.buf): LINEAR}
+        for op in self.ops_:
+            if op["kind"] == "res":
+                self._slope_of[id(op["h"].buf)] = op["s1"]
+                self._slope_of[id(op["y"].buf)] = op["s2"]
+            else:
+                self._slope_of[id(op["y"].buf)] = LINEAR if op["s"] is None else op["s"]
+        self._build()
+
+    def _mk(self, seq, name, in_c) -> ConvLayer:
+        _, cm, _ = _unpack_conv_seq(seq)
+        L = _layer(cm, name)
+        L.setup(None, None, in_c, L.cout, self.device, exact=self.exact)
+        self.layers.append(L)
+        return L
+
+    def G_(self, a: Act) -> Act:
+        return self.g[id(a.buf)]
+
+    def V_(self, a: Act) -> Act:
+        return self.v[id(a.buf)]
+
+    # ---- schedule construction
+    def _fwd_list(self, n0, n1) -> List[Callable]:
+        lst: List[Callable] = []
+        e = self.h._emit_conv
+        for op in self.ops_:
+            if op["kind"] == "conv":
+                L, s = op["L"], op["s"]
+                e([dict(L=L, dgrad=False, x=_sl(op["x"], n0, n1), out=_sl(op["y"], n0, n1), bias=L.bias_int,
+                        slope=0.0 if s is None else s, epilogue=EPI_LINEAR if s is None else EPI_LEAKY)], lst)
+            else:
+                L1, L2 = op["L1"], op["L2"]
+                e([dict(L=L1, dgrad=False, x=_sl(op["x"], n0, n1), out=_sl(op["h"], n0, n1), bias=L1.bias_int,
+                        slope=op["s1"], epilogue=EPI_LEAKY)], lst)
+                e([dict(L=L2, dgrad=False, x=_sl(op["h"], n0, n1), out=_sl(op["y"], n0, n1), bias=L2.bias_int,
+                        add1=_sl(op["x"], n0, n1), slope=op["s2"], epilogue=EPI_LEAKY)], lst)
+        return lst
+
+    def _dgrad(self, lst, L, dy: Act, x_full: Act, n0: int, n1: int, add: Optional[Act]):
+        """G(x)[n0:n1] = mask_x * (W^T dy + add)."""
+        sx = self._slope_of[id(x_full.buf)]
+        kw = dict(L=L, dgrad=True, x=dy, out=_sl(self.G_(x_full), n0, n1), add1=add)
+        if sx != LINEAR:
+            kw.update(mask=_sl(x_full, n0, n1), slope=sx, epilogue=EPI_MASK)
+        self.h._emit_conv([kw], lst)
+
+    def _bwd_list(self, n0, n1, w0, w1, g_logits: Act, dx_out: Optional[Act], dx_acc: bool, x0r=None) -> List[Callable]:
+        """dgrad chain over images [n0,n1) seeded from g_logits; weight/bias gradients over [w0,w1) (w1<=w0: none);
+        the input gradient of images x0r=[a,b) goes to dx_out (accumulating when dx_acc) or is skipped when None."""
+        x0r = (n0, n1) if x0r is None else x0r
+        lst: List[Callable] = []
+        sl = lambda a: _sl(a, n0, n1)
+        gout = lambda a: g_logits if a is self.logits else sl(self.G_(a))
+
+        def wg(L, x, dy_full):
+            if w1 > w0:
+                self.h._emit_wgrad([(L, _sl(x, w0, w1), dy_full)], lst)
+                if L.db_int is not None:
+                    lst.append(lambda d=dy_full, L=L: ops.bias_grad(d, L.db_int, True))
+
+        def dyw(a):  # delta of activation `a` restricted to the weight-gradient images
+            if a is self.logits:
+                return _sl(g_logits, w0 - n0, w1 - n0)
+            return _sl(self.G_(a), w0, w1)
+
+        for op in reversed(self.ops_):
+            if op["kind"] == "conv":
+                L, x, y = op["L"], op["x"], op["y"]
+                wg(L, x, dyw(y) if w1 > w0 else None)
+                if x is self.x0:
+                    if dx_out is not None:
+                        dy0 = _sl(self.G_(y), x0r[0], x0r[1])
+                        self.h._emit_conv([dict(L=L, dgrad=True, x=dy0, out=dx_out, add1=dx_out if dx_acc else None)], lst)
+                else:
+                    self._dgrad(lst, L, gout(y), x, n0, n1, None)
+            else:
+                L1, L2, x, hm, y = op["L1"], op["L2"], op["x"], op["h"], op["y"]
+                wg(L2, hm, dyw(y) if w1 > w0 else None)
+                self._dgrad(lst, L2, gout(y), hm, n0, n1, None)
+                wg(L1, x, dyw(hm) if w1 > w0 else None)
+                self._dgrad(lst, L1, sl(self.G_(hm)), x, n0, n1, gout(y))
+        return lst
+
+    def _tangent_list(self, n0, n1) -> List[Callable]:
+        """v_l = mask_l * (W_l v_{l-1} [+ v_skip]) over the masks of images [n0,n1), then dW_l += wgrad(v_{l-1}, e_l)."""
+        lst: List[Callable] = []
+        e = self.h._emit_conv
+        sl = lambda a: _sl(a, n0, n1)
+
+        def tconv(L, vin, a_out, add=None, last=False):
+            self.h._emit_wgrad([(L, vin, sl(self.G_(a_out)))], lst)
+            if last:
+                return
+            s = self._slope_of[id(a_out.buf)]
+            kw = dict(L=L, dgrad=False, x=vin, out=self.V_(a_out), add1=add)
+            if s != LINEAR:
+                kw.update(mask=sl(a_out), slope=s, epilogue=EPI_MASK)
+            e([kw], lst)
+
+        n_ops = len(self.ops_)
+        for i, op in enumerate(self.ops_):
+            if op["kind"] == "conv":
+                tconv(op["L"], self.V_(op["x"]), op["y"], last=(i == n_ops - 1))
+            else:
+                tconv(op["L1"], self.V_(op["x"]), op["h"])
+                tconv(op["L2"], self.V_(op["h"]), op["y"], add=self.V_(op["x"]))
+        return lst
+
+    def _build(self):
+        B, M = self.B, self.M
+        self.fwd_all = self._fwd_list(0, M)
+        self.fwd_fake = self._fwd_list(0, B)
+        if M >= 3 * B:
+            gl = self.G_(self.logits)
+            # D phase: deltas for all 3B images; weight grads from fake+real; input gradient only for xhat
+            self.g_x = Act.empty(B, 128, 128, 3, self.device)   # d sum D(xhat) / d xhat
+            self.bwd_d = self._bwd_list(0, M, 0, 2 * B, gl, self.g_x, False, x0r=(2 * B, 3 * B))
+            self.tangent = self._tangent_list(2 * B, 3 * B)
+        self.dx_g: Optional[Act] = None
+
+    def build_g_phase(self, dfake: Act):
+        """G phase: dgrad-only chain over the fake images, input gradient accumulated into `dfake`."""
+        self.dx_g = dfake
+        self.bwd_g = self._bwd_list(0, self.B, 0, 0, self.g_logits_g, dfake, True)
+
+    # ---- execution
+    @staticmethod
+    def _run(lst):
+        for f in lst:
+            f()
+
+    def zero_grad(self):
+        for L in self.layers:
+            L.zero_grad()
+
+    def repack(self):
+        for L in self.layers:
+            L.repack()
+
+    def export_grads(self):
+        for L in self.layers:
+            L.export_grad(accumulate=False)
+
+    def d_phase(self, gp_weight: float):
+        """x0 must hold [fake; real; xhat].  Leaves dW/db of L_D in the layers' packed gradient buffers."""
+        B = self.B
+        gl = self.G_(self.logits)
+        c = 1.0 / (B * self.logits.h * self.logits.w)
+        ops.fill(_sl(gl, 0, B), c)
+        ops.fill(_sl(gl, B, 2 * B), -c)
+        ops.fill(_sl(gl, 2 * B, 3 * B), 1.0)
+        self.zero_grad()
+        self._run(self.fwd_all)
+        self._run(self.bwd_d)
+        gx = self.g_x
+        self.gp_sum.zero_()
+        ops.sample_sqnorm(gx, self.sq)
+        ops.gp_coeff(self.sq, self.coeff, gp_weight * 2.0 / B, self.gp_sum)
+        ops.sample_scale(gx, self.coeff, self.V_(self.x0))
+        self._run(self.tangent)
+
+    def g_phase(self, adv_weight: float):
+        """D(fake) with the current weights, then d(-adv_weight * mean D(fake))/d fake accumulated into dfake."""
+        B = self.B
+        ops.fill(self.g_logits_g, -adv_weight / (B * self.logits.h * self.logits.w))
+        self._run(self.fwd_fake)
+        self._run(self.bwd_g)
+
+
+# ---------------------------------------------------------------------------------------------------------- trainer
+class TPGANTrainer:
+    """One object = both networks, their plans for per-GPU batch `B`, flat parameter buffers and Adam state.
+
+    step(batch) consumes NCHW CUDA tensors with the TrainDataset conventions (DataAndDataset.py:206-226):
+      img, img_frontal (B,3,128,128) in [-1,1]; img64_frontal, img32_frontal; landmarks (B,5,2) float32 (x,y);
+      z (B,64); label (B,) int64; gp_alpha (B,) float32 (the WGAN-GP interpolation coefficients).
+    Patches are cropped on the device from img / img_frontal with the reference's process() arithmetic
+    (DataAndDataset.py:10-56)."""
+
+    def __init__(self, G: Generator, D: Discriminator, B: int, device="cuda", use_dropout: bool = False,
+                 exact: bool = False, grad_hook=None, world_size: int = 1):
+        self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
+        self.use_dropout, self.exact = use_dropout, exact
+        self.w = dict(cfg.loss)
+        self.lr = cfg.train["learning_rate"]
+        self.world_size = world_size
+        self.grad_hook = grad_hook
+        self._build_g()
+        self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact)
+        self.critic.build_g_phase(self.plan.grad_act(self.fake))
+        order = self._ready_order()
+        self.flat_g = FlatParams(G, order)
+        self.flat_d = FlatParams(D)
+        for L in self.plan.layers + self.critic.layers:
+            L.repack()
+        self.sums = torch.zeros(16, dtype=torch.float32, device=self.device)  # 0..7 image terms, 8..11 local parts, 12 ce
+        self._d_logits = None
+
+    # ---- generator plan
+    def _build_g(self):
+        G, B, dev = self.G, self.B, self.device
+        plan = Plan(dev, exact=self.exact)
+        self.plan = plan
+        gp = G.global_pathway
+        bufs = gp.alloc_concats(plan, B)
+        self.bufs = bufs
+        bufs["a128"].parts[2].requires_grad = False
+        bufs["zin"].parts[1].requires_grad = False
+        self.patches = [plan.new(B, h, w, 3, name=n, requires_grad=False) for n, (h, w) in zip(PART_NAMES, PATCH_HW)]
+        self.patches_gt = [Act.empty(B, h, w, 3, dev) for (h, w) in PATCH_HW]
+        self.frontal = Act.empty(B, 128, 128, 3, dev)
+        self.t64, self.t32 = Act.empty(B, 64, 64, 3, dev), Act.empty(B, 32, 32, 3, dev)
+        self.boxes = torch.zeros((B, 4, 4), dtype=torch.int32, device=dev)
+        self.mask = None
+        if self.use_dropout:
+            self.mask = Act.empty(B, 1, 1, 256, dev)
+        outs = G.trace_body(plan, bufs, self.patches, self.mask)
+        self.fake, self.logits = outs[0], outs[1]
+        self.local_imgs = list(outs[3:7])
+        for t in [self.fake, self.logits] + self.local_imgs:
+            plan.seed_grad(t)
+        plan.trace_backward()
+
+    def _ready_order(self) -> List[str]:
+        """Parameter names in the order the backward plan finalises their gradients."""
+        marks = self.plan.bwd_marks
+        layers = sorted([L for L in self.plan.layers if L.name in marks], key=lambda L: marks[L.name])
+        pname = {id(p): n for n, p in self.G.named_parameters()}
+        order = []
+        for L in layers:
+            for p in (L.weight, L.bias):
+                if p is not None and id(p) in pname:
+                    order.append(pname[id(p)])
+        return order
+
+    # ---- one training step
+    def stage_inputs(self, b: Dict[str, torch.Tensor]):
+        B = self.B
+        rt = not self.exact
+        img = self.bufs["a128"].parts[2].act
+        img.from_nchw(b["img"], round_tf32=rt)
+        self.frontal.from_nchw(b["img_frontal"], round_tf32=False)
+        self.t64.from_nchw(b["img64_frontal"])
+        self.t32.from_nchw(b["img32_frontal"])
+        self.bufs["zin"].parts[1].act.from_nchw(b["z"].reshape(B, -1, 1, 1), round_tf32=rt)
+        lm = b["landmarks"].contiguous()
+        ops.patch_crop(img, lm, [p.act for p in self.patches], self.boxes)
+        ops.patch_crop(self.frontal, lm, self.patches_gt, None)
+        if self.mask is not None:
+            m = self.G.feature_predict.draw_mask(B, self.device) if "dropout_mask" not in b else b["dropout_mask"]
+            self.mask.buf.copy_(m.reshape(self.mask.buf.shape))
+        self.labels = b["label"]
+        self.alpha = b["gp_alpha"].contiguous()
+
+    def step(self, b: Dict[str, torch.Tensor], optimize: bool = True, read_metrics: bool = True):
+        B, w, crit = self.B, self.w, self.critic
+        self.stage_inputs(b)
+        # ---------------- G forward
+        self.plan.run_forward()
+        fake = self.fake.act
+        # ---------------- D phase
+        x0 = crit.x0
+        ops.view_copy(fake, _sl(x0, 0, B))
+        ops.view_copy(self.frontal, _sl(x0, B, 2 * B))
+        ops.lerp(self.frontal, fake, self.alpha, _sl(x0, 2 * B, 3 * B))
+        crit.d_phase(float(w["weight_gradient_penalty"]))
+        crit.export_grads()
+        if read_metrics:
+            self._d_logits = torch.empty_like(crit.logits.buf[:2 * B])
+            ops.view_copy(_sl(crit.logits, 0, 2 * B), Act(self._d_logits, 0, 1))
+        if self.world_size > 1:
+            self._allreduce(self.flat_d.grad)
+        if optimize:
+            self.flat_d.adam(self.lr, 1.0 / self.world_size)
+            crit.repack()
+        # ---------------- G phase
+        self.sums.zero_()
+        n128, n64, n32 = B * 3 * 128 * 128, B * 3 * 64 * 64, B * 3 * 32 * 32
+        wp, ws, wt = w["weight_pixelwise"], w["weight_symmetry"], w["weight_total_varation"]
+        coeffs = [wp * w["weight_128"] / n128, wp * w["weight_64"] / n64, wp * w["weight_32"] / n32,
+                  ws * w["weight_128"] / n128, ws * w["weight_64"] / n64, ws * w["weight_32"] / n32,
+                  wt / (B * 3 * 127 * 128), wt / (B * 3 * 128 * 127)]
+        dfake = self.plan.grad_act(self.fake)
+        ops.image_losses(fake, self.frontal, self.t64, self.t32, dfake, coeffs, self.sums[0:8])
+        crit.g_phase(float(w["weight_adv_G"]))
+        for i, (t, gt, (h, wd)) in enumerate(zip(self.local_imgs, self.patches_gt, PATCH_HW)):
+            ops.l1_loss(t.act, gt, self.plan.grad_act(t), w["weight_pixelwise_local"] / (B * 3 * h * wd),
+                        self.sums[8 + i:9 + i])
+        ops.softmax_ce(self.logits.act, self.labels, self.plan.grad_act(self.logits), w["weight_cross_entropy"] / B,
+                       self.sums[12:13])
+        for L in self.plan.layers:
+            L.zero_grad()
+        self.plan.run_backward(self.grad_hook(self) if self.grad_hook else None)
+        if self.grad_hook is None:
+            for L in self.plan.layers:
+                L.export_grad(accumulate=False)
+            if self.world_size > 1:
+                self._allreduce(self.flat_g.grad)
+        if optimize:
+            self.flat_g.adam(self.lr, 1.0 / self.world_size)
+            for L in self.plan.layers:
+                L.repack()
+        return self.read_metrics() if read_metrics else None
+
+    def _allreduce(self, t: torch.Tensor):
+        import torch.distributed as dist
+        dist.all_reduce(t)
+
+    # ---- metrics (small device->host reads; all arithmetic on the host)
+    def read_metrics(self) -> Dict[str, float]:
+        B, w, crit = self.B, self.w, self.critic
+        s = self.sums.cpu().tolist()
+        n128, n64, n32 = B * 3 * 128 * 128, B * 3 * 64 * 64, B * 3 * 32 * 32
+        pixel = w["weight_128"] * s[0] / n128 + w["weight_64"] * s[1] / n64 + w["weight_32"] * s[2] / n32
+        sym = w["weight_128"] * s[3] / n128 + w["weight_64"] * s[4] / n64 + w["weight_32"] * s[5] / n32
+        tv = s[6] / (B * 3 * 127 * 128) + s[7] / (B * 3 * 128 * 127)
+        local = sum(s[8 + i] / (B * 3 * h * wd) for i, (h, wd) in enumerate(PATCH_HW))
+        ce = s[12] / B
+        dl = self._d_logits.cpu()[..., 0].reshape(2 * B, -1).mean(1).tolist()       # host arithmetic on 2B*16 floats
+        d_fake, d_real = sum(dl[:B]) / B, sum(dl[B:]) / B
+        gp = float(crit.gp_sum.cpu()[0]) / B
+        adv_g = -float(crit.logits.buf[:B].cpu()[..., 0].mean())
+        g_total = w["weight_pixelwise"] * pixel + w["weight_pixelwise_local"] * local + w["weight_symmetry"] * sym + \
+            w["weight_adv_G"] * adv_g + w["weight_total_varation"] * tv + w["weight_cross_entropy"] * ce
+        return dict(pixel=pixel, local=local, symmetry=sym, tv=tv, ce=ce, adv_g=adv_g, g_total=g_total, d_fake=d_fake,
+                    d_real=d_real, gp=gp, d_total=d_fake - d_real + w["weight_gradient_penalty"] * gp)
