@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py - TP-GAN G+D training-step throughput (images/sec) on N B200s, and the reference arm on the host CPU.
+
+Own arm (default):  one process per GPU; per-GPU batch 32 (BASELINE.json configs[1]: "full G+D training step batch 32 on
+1xB200 (tf32)"); synthetic 128x128 faces + landmark patches (oracle/step.py conventions); weights = seeded
+reference init.  A step = G forward, D phase (WGAN-GP critic incl. gradient penalty, Adam), G phase (all losses, backward,
+Adam, weight repack) - nothing is skipped.  `value` = images/s with the batch already resident in HBM; `e2e` = the same
+through the public step() call with HOST (pinned) inputs copied in and the metrics read back every step.
+Reference arm (--impl reference): the oracle's fp32 PyTorch restatement of the reference modules + step (the reference
+itself, /root/reference, does not travel to the GPU box and ships no training step), on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tpgan_g_d_train_step_images_per_sec"
+UNIT = "images/s"
+PER_GPU_BATCH = 32
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.index = index
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_step_time(batch: int, steps: int, warmup: int):
+    """Seconds per oracle-port training step (fp32 PyTorch, all host threads) at `batch` images."""
+    import torch
+    from oracle import model_port as mp, step as ostep
+    from tpgan_b200 import D_and_G_model as M, config
+    torch.manual_seed(0)
+    G = M.Generator(config.G["zdim"], config.G["num_classes"], config.G["use_batchnorm"], config.G["use_residual_block"])
+    D = M.Discriminator(config.D["use_batchnorm"])
+    pg = {k: v.clone().requires_grad_(True) for k, v in G.state_dict().items()}
+    pd = {k: v.clone().requires_grad_(True) for k, v in D.state_dict().items()}
+    del G, D
+    Gc, Dc = ostep.port_callables(pg, pd)
+    og = torch.optim.Adam(list(pg.values()), lr=ostep.LEARNING_RATE)
+    od = torch.optim.Adam(list(pd.values()), lr=ostep.LEARNING_RATE)
+    b = ostep.make_batch(batch)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ostep.train_step(Gc, Dc, list(pg.values()), list(pd.values()), og, od, b)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts), torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 2
+    sec, threads = cpu_port_step_time(batch, a.steps, a.warmup)
+    val = batch / sec
+    sample = f"oracle fp32 PyTorch port of the reference G+D + oracle step, batch {batch} per step, {a.steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TP-GAN G+D training step (WGAN-GP critic + all G losses + Adam), 128x128, "
+                                   f"bounded CPU sample batch {batch}", "per_step_batch": batch},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle import step as ostep  # synthetic batch generator only (inputs, not compute)
+    from tpgan_b200 import D_and_G_model as M, _lib, config
+    from tpgan_b200.train_step import TPGANTrainer
+    B = a.batch
+    torch.manual_seed(0)
+    G = M.Generator(config.G["zdim"], config.G["num_classes"], config.G["use_batchnorm"], config.G["use_residual_block"])
+    D = M.Discriminator(config.D["use_batchnorm"])
+    G.to(dev)
+    D.to(dev)
+    tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world)
+    host = ostep.make_batch(B, seed=1234 + rank)
+    keys = ("img", "img_frontal", "img64_frontal", "img32_frontal", "landmarks", "z", "label", "gp_alpha")
+    host = {k: host[k].contiguous().pin_memory() for k in keys}
+    devb = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    resident = lambda: tr.step(devb, read_metrics=False)
+    d2h_bytes = [0]
+
+    def e2e_step():
+        cb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        m = tr.step(cb, read_metrics=True)
+        d2h_bytes[0] = 16 * 4 + 3 * B * 16 * 4 * 4 + 4
+        return m
+
+    for _ in range(max(a.warmup, 3)):
+        resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(resident, a.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    assert _lib.kernel_status() == 0, "a kernel aborted a barrier wait"
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): per-launch CUDA events over one more step
+    roof = None
+    cpu = None
+    if rank == 0:
+        ev = []
+        torch.cuda.synchronize()
+
+        def instrument(lst):
+            for f in lst:
+                if getattr(f, "kind", None) in ("tapgemm", "wgrad"):
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    f()
+                    e.record()
+                    ev.append((f.kind, f.flops, s, e, f.label))
+                else:
+                    f()
+        tr.stage_inputs(devb)
+        instrument(tr.plan.fwd)
+        tr.plan.run_backward = tr.plan.run_backward  # (plan lists replayed below)
+        for L in tr.plan.layers:
+            L.zero_grad()
+        instrument(tr.plan.bwd)
+        torch.cuda.synchronize()
+        agg = {}
+        for kind, fl, s, e, label in ev:
+            t = s.elapsed_time(e)
+            g = agg.setdefault(kind, [0.0, 0.0, 0])
+            g[0] += fl
+            g[1] += t
+            g[2] += 1
+        peaks, which = _peaks()
+        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
+        fl, t, n = agg["tapgemm"]
+        ach = fl / (t * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "tapgemm_kernel (tcgen05 tf32 implicit-GEMM conv fwd/dgrad/deconv)",
+                "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                "peak_source": f"0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json ({which}); tf32 = half the bf16 rate",
+                "launches": n, "avg_launch_ms": t / n, "share_of_step": t / (ms / a.steps),
+                "wgrad_kernel": {"achieved": agg["wgrad"][0] / (agg["wgrad"][1] * 1e-3) / 1e12,
+                                 "launches": agg["wgrad"][2], "share_of_step": agg["wgrad"][1] / (ms / a.steps)}}
+        if not a.no_cpu:
+            sec, threads = cpu_port_step_time(2, 1, 0)
+            cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "one oracle-port G+D training step (fp32 PyTorch, CPU) at batch 2"}
+    if rank == 0:
+        gb = B * world
+        line = {"metric": METRIC, "value": gb * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "config": {"workload": f"TP-GAN G+D training step (WGAN-GP critic + all G losses + Adam), batch {B}/GPU, "
+                                       "128x128 synthetic faces + 4 landmark patches, dropout on",
+                           "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
+                           "l2": "activations per step (~8 GB) exceed the 126 MB L2; no explicit flush"},
+                "clocks": clocks,
+                "e2e": {"value": gb * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": ms_e2e / a.steps},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

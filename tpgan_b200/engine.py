@@ -356,8 +356,15 @@ class Plan:
         self.tape.append(lambda: self._bwd_conv(layers, list(xs), outs_l, res))
         return outs_l
 
+    @staticmethod
+    def _flops(L, x: Act, out: Act, dgrad: bool) -> float:
+        """Algorithmic FLOPs (2*MACs, unpadded reference channel counts) of one conv-like launch."""
+        pix_src = (out if L.transposed else x) if dgrad else (x if L.transposed else out)
+        return 2.0 * pix_src.n * pix_src.h * pix_src.w * L.cin * L.cout * L.k * L.k
+
     def _emit_conv(self, specs, lst):
         """specs: dicts {L, dgrad, x, out, bias, add1, add2, mask, slopes, slope, epilogue} of one grouped launch."""
+        fl = sum(self._flops(sp["L"], sp["x"], sp["out"], sp["dgrad"]) for sp in specs)
         def mk(sp, x, out, pack, **kw):
             L = sp["L"]
             return ops.conv_args(L.kind_dgrad if sp["dgrad"] else L.kind_fwd, x, out, pack, L.k, L.stride, L.pad,
@@ -366,7 +373,8 @@ class Plan:
                                slopes=sp.get("slopes"), slope=sp.get("slope", 0.0), epilogue=sp.get("epilogue", EPI_LINEAR))
         if not self.exact:
             lst.append(self._conv_launch([mk(sp, sp["x"], sp["out"], sp["L"].wd if sp["dgrad"] else sp["L"].wf, **full(sp))
-                                          for sp in specs]))
+                                          for sp in specs], fl, ",".join(sp["L"].name for sp in specs) +
+                                         (":dgrad" if specs[0]["dgrad"] else ":fwd")))
             return
         a1, a2, a3 = [], [], []
         for sp in specs:
@@ -401,7 +409,8 @@ class Plan:
         """specs: (L, x Act, dy Act) of one grouped weight-gradient launch."""
         mk = lambda L, x, dy: ops.wgrad_args(L.kind_fwd, x, dy, L.dw, L.k, L.stride, L.pad)
         if not self.exact:
-            lst.append(self._wgrad_launch([mk(L, x, dy) for L, x, dy in specs]))
+            fl = sum(self._flops(L, x, dy, False) for L, x, dy in specs)
+            lst.append(self._wgrad_launch([mk(L, x, dy) for L, x, dy in specs], fl, ",".join(L.name for L, _, _ in specs) + ":wgrad"))
             return
         g1, g2, g3 = [], [], []
         for L, x, dy in specs:
@@ -415,7 +424,7 @@ class Plan:
         for g in (g1, g2, g3):
             lst.append(self._wgrad_launch(g))
 
-    def _conv_launch(self, args):
+    def _conv_launch(self, args, flops: float = 0.0, label: str = ""):
         arr = (ops.ConvArgs * len(args))(*args)
         self.keep.append(arr)
         n = len(args)
@@ -423,9 +432,10 @@ class Plan:
 
         def run():
             ops._lib.check(lib.tpgan_conv2d(arr, n, ops._stream()), "conv2d")
+        run.kind, run.flops, run.label = "tapgemm", flops, label
         return run
 
-    def _wgrad_launch(self, args):
+    def _wgrad_launch(self, args, flops: float = 0.0, label: str = ""):
         arr = (ops.WgradArgs * len(args))(*args)
         self.keep.append(arr)
         n = len(args)
@@ -433,6 +443,7 @@ class Plan:
 
         def run():
             ops._lib.check(lib.tpgan_conv2d_wgrad(arr, n, ops._stream()), "wgrad")
+        run.kind, run.flops, run.label = "wgrad", flops, label
         return run
 
     def reflect_pad(self, x: T, left: int, top: int) -> T:

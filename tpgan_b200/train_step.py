@@ -300,13 +300,12 @@ class TPGANTrainer:
     (DataAndDataset.py:10-56)."""
 
     def __init__(self, G: Generator, D: Discriminator, B: int, device="cuda", use_dropout: bool = False,
-                 exact: bool = False, grad_hook=None, world_size: int = 1):
+                 exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0):
         self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
         self.use_dropout, self.exact = use_dropout, exact
         self.w = dict(cfg.loss)
         self.lr = cfg.train["learning_rate"]
-        self.world_size = world_size
-        self.grad_hook = grad_hook
+        self.world_size, self.group = world_size, group
         self._build_g()
         self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact)
         self.critic.build_g_phase(self.plan.grad_act(self.fake))
@@ -315,6 +314,10 @@ class TPGANTrainer:
         self.flat_d = FlatParams(D)
         for L in self.plan.layers + self.critic.layers:
             L.repack()
+        self.reducer = None
+        if world_size > 1:
+            from .parallel import BucketReducer
+            self.reducer = BucketReducer(self, bucket_mb, group)
         self.sums = torch.zeros(16, dtype=torch.float32, device=self.device)  # 0..7 image terms, 8..11 local parts, 12 ce
         self._d_logits = None
 
@@ -412,12 +415,13 @@ class TPGANTrainer:
                        self.sums[12:13])
         for L in self.plan.layers:
             L.zero_grad()
-        self.plan.run_backward(self.grad_hook(self) if self.grad_hook else None)
-        if self.grad_hook is None:
+        if self.reducer is not None:   # bucketed all-reduce overlapped with backward
+            self.plan.run_backward(self.reducer.hooks())
+            self.reducer.finish()
+        else:
+            self.plan.run_backward()
             for L in self.plan.layers:
                 L.export_grad(accumulate=False)
-            if self.world_size > 1:
-                self._allreduce(self.flat_g.grad)
         if optimize:
             self.flat_g.adam(self.lr, 1.0 / self.world_size)
             for L in self.plan.layers:
@@ -426,7 +430,7 @@ class TPGANTrainer:
 
     def _allreduce(self, t: torch.Tensor):
         import torch.distributed as dist
-        dist.all_reduce(t)
+        dist.all_reduce(t, group=self.group)
 
     # ---- metrics (small device->host reads; all arithmetic on the host)
     def read_metrics(self) -> Dict[str, float]:
