@@ -259,10 +259,12 @@ static int launch_tapgemm(Params& P, cudaStream_t st) {
   }
   P.total_tiles = tiles;
   P.b_stage_bytes = bmax;
-  const int stage_bytes = 16384 + bmax;
   const int budget = g_dev.max_smem - 1024 - 256;
+  // two 32-float K chunks per stage when at least 3 such stages fit (halves the per-stage barrier/issue overhead)
+  P.kst = (budget / (2 * (16384 + bmax)) >= 3) ? 2 : 1;
+  if (const char* ev = getenv("TPGAN_KST")) P.kst = std::max(1, std::min(2, atoi(ev)));
+  const int stage_bytes = P.kst * (16384 + bmax);
   P.stages = std::min(kMaxStages, budget / stage_bytes);
-  P.tap_rot = getenv("TPGAN_TAPROT") ? atoi(getenv("TPGAN_TAPROT")) : 0;
   if (const char* ev = getenv("TPGAN_STAGES")) P.stages = std::min(P.stages, std::max(2, atoi(ev)));
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "not enough shared memory for 2 stages");
   const int smem = P.stages * stage_bytes + 1024;

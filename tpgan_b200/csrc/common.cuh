@@ -12,6 +12,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp (ptxas recognises elect.sync and treats the guarded region as single-threaded, so
+// uniform-datapath instructions - UTMALDG, UTCHMMA, UTCBAR - are emitted without per-instruction election loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -66,6 +78,63 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, const 
     }
   }
   return true;
+}
+
+// ---- address-based variants: the hot loops compute shared addresses once and advance them arithmetically (taking
+// &bar[i] per use makes ptxas re-derive the shared-window address - S2UR CgaCtaId + ULEA - on every wait/arrive).
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+static __device__ __noinline__ bool mbar_wait_slow_a(uint32_t bar, uint32_t parity, volatile int* smem_flag, int* status, int code) {
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      if (*smem_flag) return false;
+      if (clock64() - t0 > (1ll << 31)) {
+        *smem_flag = 1;
+        if (status) {
+          atomicCAS(status, 0, code | (int(blockIdx.x) << 8));
+          __threadfence_system();
+        }
+        return false;
+      }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ bool mbar_wait_a(uint32_t bar, uint32_t parity, const AbortCtl& ac, int code) {
+  if (mbar_try_wait_a(bar, parity)) return true;
+  if (mbar_try_wait_a(bar, parity)) return true;
+  return mbar_wait_slow_a(bar, parity, ac.smem_flag, ac.status, code);
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- TMA (cp.async.bulk.tensor)
@@ -146,6 +215,16 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// Descriptor halves: hi word is constant per layout, lo word = (addr >> 4) | LBO field; advancing the operand by `bytes`
+// inside the tile is an add of bytes >> 4 on the lo word.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;

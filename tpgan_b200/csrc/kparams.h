@@ -59,7 +59,7 @@ struct TapGemmParams {
   int total_tiles;
   int stages;
   int b_stage_bytes;  // max over groups of block_n*128
-  int tap_rot;
+  int kst;            // 32-float K chunks per pipeline stage (1 or 2)
   TapGemmGroup g[kMaxGroups];
 };
 
@@ -68,7 +68,7 @@ struct TapGemmParams1 {  // single-group variant (keeps the parameter block smal
   int total_tiles;
   int stages;
   int b_stage_bytes;
-  int tap_rot;
+  int kst;
   TapGemmGroup g[1];
 };
 

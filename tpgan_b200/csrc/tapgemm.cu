@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(256, 1) tapgemm_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = P.stages;
-  const uint32_t stage_bytes = kAStageBytes + P.b_stage_bytes;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   if (threadIdx.x == 0) {
@@ -86,70 +85,106 @@ __global__ void __launch_bounds__(256, 1) tapgemm_kernel(const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
   AbortCtl ac{&abort_flag, status};
 
+  const int kst = P.kst;  // 32-float K chunks per pipeline stage (1 or 2)
+  const uint32_t a_region = (uint32_t)kst * kAStageBytes;
+  const uint32_t b_chunk = (uint32_t)P.b_stage_bytes;
+  const uint32_t stage_bytes = a_region + (uint32_t)kst * b_chunk;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t sa = smem_base, fb = full0, eb = empty0;
       bool ok = true;
       for (int tile = blockIdx.x; ok && tile < P.total_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(P, tile);
+        const TileCoord tc = decode_tile(P, tile);
         const TapGemmGroup& G = P.g[tc.gi];
-        const uint32_t tx = (uint32_t)(G.bw * G.bh * G.bn + G.block_n) * 128u;
+        const uint32_t chunk_tx = (uint32_t)(G.bw * G.bh * G.bn + G.block_n) * 128u;
         const PhaseDesc ph = G.phase[tc.ph];
-        const int rot = (P.tap_rot & 1) ? (int)(blockIdx.x % (unsigned)ph.tap_count) : 0;
-        for (int t0 = 0; ok && t0 < ph.tap_count; ++t0) {
-          int t = t0 + rot;
-          if (t >= ph.tap_count) t -= ph.tap_count;
-          const TapDesc tap = G.taps[ph.tap_begin + t];
+        const int kchunks = G.kchunks;
+        const int bn0 = tc.nt * G.block_n;
+        const TapDesc* taps = &G.taps[ph.tap_begin];
+        const CUtensorMap* bm = &G.bmap;
+        for (int t = 0; ok && t < ph.tap_count; ++t) {
+          const TapDesc tap = taps[t];
           const CUtensorMap* am = &G.amap[tap.plane];
-          for (int c = 0; c < G.kchunks; ++c) {
-            if (!mbar_wait(&empty_bar[stage], phase ^ 1u, ac, 1)) { ok = false; break; }
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            const int dbg = P.tap_rot >> 4;
-            uint32_t txx = 0;
-            if (!(dbg & 1)) txx += (uint32_t)(G.bw * G.bh * G.bn) * 128u;
-            if (!(dbg & 2)) txx += (uint32_t)G.block_n * 128u;
-            if (txx) mbar_arrive_expect_tx(&full_bar[stage], txx); else mbar_arrive(&full_bar[stage]);
-            if (!(dbg & 1)) tma_load_4d(sa, am, &full_bar[stage], c * 32, tap.dx, tc.h0 + tap.dy, tc.n0);
-            if (!(dbg & 2)) tma_load_3d(sa + kAStageBytes, &G.bmap, &full_bar[stage], c * 32, tc.nt * G.block_n, tap.wtap);
-            if (++stage == S) { stage = 0; phase ^= 1u; }
+          const int ax = tap.dx, ay = tc.h0 + tap.dy, wt = tap.wtap;
+          for (int c = 0; c < kchunks; c += kst) {
+            if (!mbar_wait_a(eb, phase ^ 1u, ac, 1)) { ok = false; break; }
+            const uint32_t sb = sa + a_region;
+            const bool two = (kst > 1) && (c + 1 < kchunks);
+            mbar_arrive_expect_tx_a(fb, two ? 2u * chunk_tx : chunk_tx);
+            tma_load_4d_a(sa, am, fb, c * 32, ax, ay, tc.n0);
+            tma_load_3d_a(sb, bm, fb, c * 32, bn0, wt);
+            if (two) {
+              tma_load_4d_a(sa + kAStageBytes, am, fb, c * 32 + 32, ax, ay, tc.n0);
+              tma_load_3d_a(sb + b_chunk, bm, fb, c * 32 + 32, bn0, wt);
+            }
+            sa += stage_bytes; fb += 8; eb += 8;
+            if (++stage == S) { stage = 0; phase ^= 1u; sa = smem_base; fb = full0; eb = empty0; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       bool ok = true;
+      const uint32_t dhi = desc_hi(1024, 2);
+      const uint32_t a_lo0 = desc_lo(smem_base, 16);
+      const uint32_t stage16 = stage_bytes >> 4, areg16 = a_region >> 4, b16 = b_chunk >> 4;
+      uint32_t a_lo = a_lo0, fb = full0, eb = empty0;
       for (int tile = blockIdx.x; ok && tile < P.total_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(P, tile);
+        const TileCoord tc = decode_tile(P, tile);
         const TapGemmGroup& G = P.g[tc.gi];
         if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 2)) break;
         tc_fence_after();
         const uint32_t idesc = make_idesc_tf32(128, G.block_n, 0, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccCols);
         const int ntap = G.phase[tc.ph].tap_count;
+        const int kchunks = G.kchunks;
+        // MMAs in the last stage of every tap: full chunks before the last one + the partial last chunk
+        const int last_c = ((kchunks - 1) / kst) * kst;
+        const int n_last = (kchunks - 1 - last_c) * 4 + G.last_mmas;
         uint32_t acc = 0;
         for (int t = 0; ok && t < ntap; ++t) {
-          for (int c = 0; c < G.kchunks; ++c) {
-            if (!mbar_wait(&full_bar[stage], phase, ac, 3)) { ok = false; break; }
+          for (int c = 0; c < kchunks; c += kst) {
+            if (!mbar_wait_a(fb, phase, ac, 3)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t b_addr = a_addr + kAStageBytes;
-            const int nm = (c == G.kchunks - 1) ? G.last_mmas : 4;
-            for (int k = 0; k < nm; ++k) {
-              if ((P.tap_rot >> 4) & 4) break;
-              mma_tf32_ss(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
-                          idesc, acc);
-              acc = 1;
+            const uint32_t b_lo = a_lo + areg16;
+            if (c < last_c) {  // a full stage: kst * 4 MMAs
+              mma_tf32_ss(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
+              mma_tf32_ss(d_tmem, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
+              mma_tf32_ss(d_tmem, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
+              mma_tf32_ss(d_tmem, desc_join(a_lo + 6, dhi), desc_join(b_lo + 6, dhi), idesc, 1);
+              if (kst > 1) {
+                const uint32_t a2 = a_lo + (kAStageBytes >> 4), b2 = b_lo + b16;
+                mma_tf32_ss(d_tmem, desc_join(a2, dhi), desc_join(b2, dhi), idesc, 1);
+                mma_tf32_ss(d_tmem, desc_join(a2 + 2, dhi), desc_join(b2 + 2, dhi), idesc, 1);
+                mma_tf32_ss(d_tmem, desc_join(a2 + 4, dhi), desc_join(b2 + 4, dhi), idesc, 1);
+                mma_tf32_ss(d_tmem, desc_join(a2 + 6, dhi), desc_join(b2 + 6, dhi), idesc, 1);
+              }
+            } else {
+#pragma unroll
+              for (int m = 0; m < 8; ++m) {
+                if (m < n_last) {
+                  const uint32_t off = (uint32_t)(m & 3) * 2u;
+                  const uint32_t aj = a_lo + off + ((m >> 2) ? (kAStageBytes >> 4) : 0u);
+                  const uint32_t bj = b_lo + off + ((m >> 2) ? b16 : 0u);
+                  mma_tf32_ss(d_tmem, desc_join(aj, dhi), desc_join(bj, dhi), idesc, m ? 1u : acc);
+                }
+              }
             }
-            tc_commit(&empty_bar[stage]);
-            if (++stage == S) { stage = 0; phase ^= 1u; }
+            acc = 1;
+            tc_commit_a(eb);
+            a_lo += stage16; fb += 8; eb += 8;
+            if (++stage == S) { stage = 0; phase ^= 1u; a_lo = a_lo0; fb = full0; eb = empty0; }
           }
         }
         if (!ok) break;

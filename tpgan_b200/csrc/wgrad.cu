@@ -90,75 +90,87 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
   const uint32_t tmem_base = tmem_base_s;
   AbortCtl ac{&abort_flag, status};
 
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t sa = smem_base, fb = full0, eb = empty0;
       bool ok = true;
       for (int unit = blockIdx.x; ok && unit < P.total_units; unit += gridDim.x) {
-        UnitCoord u = decode_unit(P, unit);
+        const UnitCoord u = decode_unit(P, unit);
         const WgradGroup& G = P.g[u.gi];
         const TapDesc tap = G.taps[u.tap];
         const CUtensorMap* qm = &G.qmap[tap.plane];
+        const CUtensorMap* pm = &G.pmap;
         const int mch = min(4, (G.m_valid - u.mt * 128 + 31) / 32);
         const int nch = min(G.block_n / 32, (G.n_valid - u.nt * G.block_n + 31) / 32);
-        const uint32_t box_bytes = (uint32_t)(G.bw * G.bh * G.bn) * 128u;
-        const uint32_t tx = box_bytes * (uint32_t)(mch + nch);
+        const uint32_t tx = (uint32_t)(G.bw * G.bh * G.bn) * 128u * (uint32_t)(mch + nch);
         const uint32_t chunk_stride = (uint32_t)G.kp * 128u;
         const int c_begin = u.ks * G.chunks_per_split;
         const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
+        const int tiles_w = G.tiles_w, tiles_h = G.tiles_h, bw = G.bw, bh = G.bh, bn = G.bn;
+        const int pc0 = u.mt * 128, qc0 = u.nt * G.block_n, tdx = tap.dx, tdy = tap.dy;
+        // running pixel-box coordinates (wb fastest, then hb, then nb)
+        int wb = c_begin % tiles_w, r = c_begin / tiles_w;
+        int hb = r % tiles_h, nb = r / tiles_h;
         for (int c = c_begin; c < c_end; ++c) {
-          int wb = c % G.tiles_w;
-          int r = c / G.tiles_w;
-          int hb = r % G.tiles_h;
-          int nb = r / G.tiles_h;
-          const int x0 = wb * G.bw, y0 = hb * G.bh, n0 = nb * G.bn;
-          if (!mbar_wait(&empty_bar[stage], phase ^ 1u, ac, 11)) { ok = false; break; }
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + P.a_stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], tx);
-          for (int i = 0; i < mch; ++i)
-            tma_load_4d(sa + (size_t)i * chunk_stride, &G.pmap, &full_bar[stage], u.mt * 128 + i * 32, x0, y0, n0);
+          const int x0 = wb * bw, y0 = hb * bh, n0 = nb * bn;
+          if (!mbar_wait_a(eb, phase ^ 1u, ac, 11)) { ok = false; break; }
+          const uint32_t sb = sa + (uint32_t)P.a_stage_bytes;
+          mbar_arrive_expect_tx_a(fb, tx);
+          for (int i = 0; i < mch; ++i) tma_load_4d_a(sa + (uint32_t)i * chunk_stride, pm, fb, pc0 + i * 32, x0, y0, n0);
           for (int i = 0; i < nch; ++i)
-            tma_load_4d(sb + (size_t)i * chunk_stride, qm, &full_bar[stage], u.nt * G.block_n + i * 32, x0 + tap.dx,
-                        y0 + tap.dy, n0);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+            tma_load_4d_a(sb + (uint32_t)i * chunk_stride, qm, fb, qc0 + i * 32, x0 + tdx, y0 + tdy, n0);
+          sa += stage_bytes; fb += 8; eb += 8;
+          if (++stage == S) { stage = 0; phase ^= 1u; sa = smem_base; fb = full0; eb = empty0; }
+          if (++wb == tiles_w) { wb = 0; if (++hb == tiles_h) { hb = 0; ++nb; } }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       bool ok = true;
+      const uint32_t dhi = desc_hi(512, 1);
+      const uint32_t stage16 = stage_bytes >> 4, areg16 = (uint32_t)P.a_stage_bytes >> 4;
+      uint32_t fb = full0, eb = empty0, sbase16 = (smem_base & 0x3FFFFu) >> 4;
+      const uint32_t sbase16_0 = sbase16;
       for (int unit = blockIdx.x; ok && unit < P.total_units; unit += gridDim.x) {
-        UnitCoord u = decode_unit(P, unit);
+        const UnitCoord u = decode_unit(P, unit);
         const WgradGroup& G = P.g[u.gi];
         if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 12)) break;
         tc_fence_after();
         const uint32_t idesc = make_idesc_tf32(128, G.block_n, 1, 1);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kWAccCols);
-        const uint32_t chunk_stride = (uint32_t)G.kp * 128u;
+        const uint32_t lbo_field = ((((uint32_t)G.kp * 128u) >> 4) & 0x3FFFu) << 16;
         const int kgroups = G.kp / 8;
         const int c_begin = u.ks * G.chunks_per_split;
         const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
         uint32_t acc = 0;
         for (int c = c_begin; c < c_end; ++c) {
-          if (!mbar_wait(&full_bar[stage], phase, ac, 13)) { ok = false; break; }
+          if (!mbar_wait_a(fb, phase, ac, 13)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + (uint32_t)P.a_stage_bytes;
-          for (int k = 0; k < kgroups; ++k) {
-            mma_tf32_ss(d_tmem, make_smem_desc(a_addr + k * 1024, chunk_stride, 512, 1),
-                        make_smem_desc(b_addr + k * 1024, chunk_stride, 512, 1), idesc, acc);
-            acc = 1;
+          const uint32_t a_lo = sbase16 | lbo_field, b_lo = (sbase16 + areg16) | lbo_field;
+          if (kgroups == 4) {
+            mma_tf32_ss(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
+            mma_tf32_ss(d_tmem, desc_join(a_lo + 64, dhi), desc_join(b_lo + 64, dhi), idesc, 1);
+            mma_tf32_ss(d_tmem, desc_join(a_lo + 128, dhi), desc_join(b_lo + 128, dhi), idesc, 1);
+            mma_tf32_ss(d_tmem, desc_join(a_lo + 192, dhi), desc_join(b_lo + 192, dhi), idesc, 1);
+          } else {
+            for (int k = 0; k < kgroups; ++k)
+              mma_tf32_ss(d_tmem, desc_join(a_lo + 64 * k, dhi), desc_join(b_lo + 64 * k, dhi), idesc, k ? 1u : acc);
           }
-          tc_commit(&empty_bar[stage]);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          acc = 1;
+          tc_commit_a(eb);
+          sbase16 += stage16; fb += 8; eb += 8;
+          if (++stage == S) { stage = 0; phase ^= 1u; sbase16 = sbase16_0; fb = full0; eb = empty0; }
         }
         if (!ok) break;
         tc_commit(&tfull_bar[as]);
