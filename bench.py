@@ -147,7 +147,7 @@ def run_b200(a):
     D = M.Discriminator(config.D["use_batchnorm"])
     G.to(dev)
     D.to(dev)
-    tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world)
+    tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world, use_graphs=not a.no_graphs)
     host = ostep.make_batch(B, seed=1234 + rank)
     keys = ("img", "img_frontal", "img64_frontal", "img32_frontal", "landmarks", "z", "label", "gp_alpha")
     host = {k: host[k].contiguous().pin_memory() for k in keys}
@@ -178,8 +178,7 @@ def run_b200(a):
     d2h_bytes = [0]
 
     def e2e_step():
-        cb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        m = tr.step(cb, read_metrics=True)
+        m = tr.step(host, read_metrics=True)   # pinned host tensors: H2D copies + metric read-back inside the call
         d2h_bytes[0] = 16 * 4 + 3 * B * 16 * 4 * 4 + 4
         return m
 
@@ -191,6 +190,9 @@ def run_b200(a):
     l0 = _lib.launch_count()
     ms = timed(resident, a.steps)
     launches = _lib.launch_count() - l0
+    if not a.no_graphs:   # replayed graphs do not go through the library's host entry points: count the captured kernels
+        runner = list(tr._sched.values())[0]
+        launches = a.steps * runner.kernels_per_run
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         e2e_step()
@@ -216,9 +218,6 @@ def run_b200(a):
                     f()
         tr.stage_inputs(devb)
         instrument(tr.plan.fwd)
-        tr.plan.run_backward = tr.plan.run_backward  # (plan lists replayed below)
-        for L in tr.plan.layers:
-            L.zero_grad()
         instrument(tr.plan.bwd)
         torch.cuda.synchronize()
         agg = {}
@@ -228,6 +227,12 @@ def run_b200(a):
             g[0] += fl
             g[1] += t
             g[2] += 1
+        if a.per_layer:
+            rows = sorted(((s.elapsed_time(e), kind, fl, label) for kind, fl, s, e, label in ev), reverse=True)
+            with open(a.per_layer, "w") as f:
+                for t, kind, fl, label in rows:
+                    f.write(json.dumps({"ms": round(t, 4), "kind": kind, "tflops": round(fl / (t * 1e-3) / 1e12, 1),
+                                        "gflop": round(fl / 1e9, 2), "label": label}) + "\n")
         peaks, which = _peaks()
         tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
         fl, t, n = agg["tapgemm"]
@@ -250,7 +255,8 @@ def run_b200(a):
                 "config": {"workload": f"TP-GAN G+D training step (WGAN-GP critic + all G losses + Adam), batch {B}/GPU, "
                                        "128x128 synthetic faces + 4 landmark patches, dropout on",
                            "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
-                           "l2": "activations per step (~8 GB) exceed the 126 MB L2; no explicit flush"},
+                           "l2": "activations per step (~8 GB) exceed the 126 MB L2; no explicit flush",
+                           "cuda_graphs": not a.no_graphs},
                 "clocks": clocks,
                 "e2e": {"value": gb * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": ms_e2e / a.steps},
@@ -268,6 +274,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--per-layer", default="", help="write the per-launch conv/wgrad timing table (JSON lines) here")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -88,6 +88,8 @@ typedef struct tpgan_wgrad_args {
   tpgan_view dy; /* gradient w.r.t. the layer's pre-activation output */
   float* dw_packed;
   int32_t w_rows_pad, w_k_pad;
+  int32_t accumulate; /* 1: dW += (atomics); 0: the caller guarantees this is the only launch writing dW since it was
+                         cleared, so tiles whose reduction is not split are written with plain vector stores */
 } tpgan_wgrad_args;
 TPGAN_API int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* stream);
 
@@ -160,6 +162,11 @@ TPGAN_API int tpgan_maxout2_backward(const float* x, const float* dy, float* dx,
 /* Fused Adam over a flat fp32 parameter bucket (torch.optim.Adam semantics incl. L2 weight_decay). */
 TPGAN_API int tpgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* Same update with the step count kept in device memory (*step_dev is incremented first, then used for the bias
+ * corrections), so the launch can be captured in a CUDA graph and replayed. */
+TPGAN_API int tpgan_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int32_t* step_dev, float grad_scale, void* stream);
 
 /* Per-sample gradient-penalty helpers: norms[n] = ||g[n]||_2 ; u = coeff[n] * g. */
 TPGAN_API int tpgan_sample_sqnorm(tpgan_view g, float* sqnorm, void* stream);

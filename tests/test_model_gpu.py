@@ -226,3 +226,31 @@ def test_full_size_batch32_properties():
     tr2 = TPGANTrainer(G2, D2, 2)
     tr2.step({k: v[:2].contiguous() for k, v in b.items()}, optimize=False)
     assert rel(tr2.fake.act.to_nchw().cpu(), fake32) < 1e-5
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The step captured into CUDA graphs (eager warm-up, capture, replays) reproduces the eagerly launched step: same
+    losses and gradients for a fixed-weights step, and an optimizer trajectory that stays within the run-to-run spread of
+    two eager runs (fp32 atomic-add order in wgrad/bias sums makes any two runs differ slightly; Adam's first updates are
+    sign-like and amplify that)."""
+    from oracle import step as ostep
+    from tpgan_b200.train_step import TPGANTrainer
+    B = 2
+    b = {k: v.cuda() for k, v in ostep.make_batch(B).items()}
+    fixed, traj = [], []
+    for graphs in (False, False, True):
+        G, D, _, _ = _models(False)
+        tr = TPGANTrainer(G, D, B, use_graphs=graphs)
+        ms = [tr.step(b, optimize=False) for _ in range(4)]      # warm-up, capture, two replays
+        fixed.append((ms[-1], tr.flat_g.grad.clone(), tr.flat_d.grad.clone()))
+        mt = [tr.step(b, optimize=True) for _ in range(4)]
+        torch.cuda.synchronize()
+        traj.append((mt[-1], tr.flat_g.data.clone()))
+    for k in fixed[0][0]:
+        assert abs(fixed[0][0][k] - fixed[2][0][k]) <= 1e-5 * abs(fixed[0][0][k]) + 1e-7, (k, fixed[0][0][k], fixed[2][0][k])
+    assert rel(fixed[2][1], fixed[0][1]) < 1e-5 and rel(fixed[2][2], fixed[0][2]) < 1e-5
+    spread = rel(traj[1][1], traj[0][1])
+    assert rel(traj[2][1], traj[0][1]) <= 3 * spread + 1e-6, (rel(traj[2][1], traj[0][1]), spread)
+    for k in traj[0][0]:
+        noise = abs(traj[0][0][k] - traj[1][0][k])
+        assert abs(traj[0][0][k] - traj[2][0][k]) <= 5 * noise + 2e-3 * abs(traj[0][0][k]) + 1e-5, (k, traj[0][0][k], traj[2][0][k])

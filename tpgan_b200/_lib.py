@@ -31,7 +31,8 @@ class ConvArgs(C.Structure):
 
 class WgradArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
-                ("x", View), ("dy", View), ("dw_packed", C.c_void_p), ("w_rows_pad", C.c_int32), ("w_k_pad", C.c_int32)]
+                ("x", View), ("dy", View), ("dw_packed", C.c_void_p), ("w_rows_pad", C.c_int32), ("w_k_pad", C.c_int32),
+                ("accumulate", C.c_int32)]
 
 
 NULL_VIEW = View(None, 0, 0, 0, 0, 0, 0, 0)
@@ -60,6 +61,7 @@ SYMBOLS = {
     "tpgan_maxout2": (C.c_int, [_VP, _VP, _I32, _I32, _VP]),
     "tpgan_maxout2_backward": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
     "tpgan_adam_step": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _F, _I32, _F, _VP]),
+    "tpgan_adam_step_dev": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _F, _VP, _F, _VP]),
     "tpgan_sample_sqnorm": (C.c_int, [View, _VP, _VP]),
     "tpgan_sample_scale": (C.c_int, [View, _VP, View, _VP]),
     "tpgan_gp_coeff": (C.c_int, [_VP, _VP, _I32, _F, _VP, _VP]),

@@ -303,6 +303,7 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G) {
   G.rows_pad = a.w_rows_pad;
   G.k_pad = a.w_k_pad;
   G.dw = a.dw_packed;
+  G.accumulate = a.accumulate;
   G.Hp = Pt.h;
   G.Wp = Pt.w;
   G.Nimg = Pt.n;

@@ -89,6 +89,7 @@ struct WgradGroup {
   int rows_pad, k_pad;
   int transpose_out;             // 0: dw[tap][m][n]   1: dw[tap][n][m]
   int m_valid, n_valid;          // bounds in the dw tensor (rows_pad/k_pad by orientation)
+  int accumulate;                // 1: dW += (always atomics); 0: dW = (plain stores when the K range is not split)
 };
 
 struct WgradParams {

@@ -126,7 +126,8 @@ __global__ void view_copy_kernel(V src, V dst, int accumulate) {
   }
 }
 
-// db[c] (+)= sum_pixels dy[pix, c].  Block = 256 threads = 8 pixel lanes x 32 channel lanes; coalesced along c.
+// db[c] (+)= sum_pixels dy[pix, c].  Pixel-dense views (sh == w*sw, sn == h*sh: every slice of an NHWC buffer) take the
+// vectorised path: a warp reads 32 x float4 = 128 consecutive channels of a pixel, 4 pixels in flight per thread.
 __global__ void bias_grad_kernel(V dy, float* __restrict__ db) {
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
@@ -149,6 +150,43 @@ __global__ void bias_grad_kernel(V dy, float* __restrict__ db) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][cl];
     atomicAdd(db + c, s);
+  }
+}
+__global__ void __launch_bounds__(256) bias_grad_dense_kernel(const float* __restrict__ p, long long npix, long long sw, int C,
+                                                              float* __restrict__ db) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const float* base = p + c;
+    const long long stride = (long long)gridDim.x * 8;
+    long long pix = (long long)blockIdx.x * 8 + wp;
+    for (; pix + 3 * stride < npix; pix += 4 * stride) {
+      const float4 v0 = *reinterpret_cast<const float4*>(base + pix * sw);
+      const float4 v1 = *reinterpret_cast<const float4*>(base + (pix + stride) * sw);
+      const float4 v2 = *reinterpret_cast<const float4*>(base + (pix + 2 * stride) * sw);
+      const float4 v3 = *reinterpret_cast<const float4*>(base + (pix + 3 * stride) * sw);
+      a.x += (v0.x + v1.x) + (v2.x + v3.x);
+      a.y += (v0.y + v1.y) + (v2.y + v3.y);
+      a.z += (v0.z + v1.z) + (v2.z + v3.z);
+      a.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; pix < npix; pix += stride) {
+      const float4 v = *reinterpret_cast<const float4*>(base + pix * sw);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  red[wp][lane] = a;
+  __syncthreads();
+  if (wp == 0 && c < C) {
+    float4 s = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s.x += red[i][lane].x; s.y += red[i][lane].y; s.z += red[i][lane].z; s.w += red[i][lane].w; }
+    atomicAdd(db + c, s.x);
+    if (c + 1 < C) atomicAdd(db + c + 1, s.y);
+    if (c + 2 < C) atomicAdd(db + c + 2, s.z);
+    if (c + 3 < C) atomicAdd(db + c + 3, s.w);
   }
 }
 
@@ -450,6 +488,28 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Graph-capturable Adam: the step count lives on the device (incremented by counter_inc_kernel before the launch).
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, float lr, float b1, float b2, float eps, float wd, const int* __restrict__ step,
+                                float gscale) {
+  const float t = (float)(*step);
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float lr1 = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    if (wd != 0.f) gi += wd * pi;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - lr1 * (mi / denom);
+  }
+}
+__global__ void counter_inc_kernel(int* c) { *c += 1; }
+
 // one block per sample
 __global__ void sample_sqnorm_kernel(V g, float* __restrict__ out) {
   const int n = blockIdx.x;
@@ -660,6 +720,15 @@ int tpgan_bias_grad(tpgan_view dy, float* db, int32_t accumulate, void* stream) 
     if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   }
   long long npix = (long long)dy.n * dy.h * dy.w;
+  const bool dense = dy.sh == (int64_t)dy.w * dy.sw && dy.sn == (int64_t)dy.h * dy.sh && (dy.sw % 4 == 0) &&
+                     (((uintptr_t)dy.ptr & 15) == 0);
+  if (dense) {
+    // channels beyond dy.c inside the last float4 are padding lanes of the same buffer (always readable)
+    dim3 grid((unsigned)std::max(1ll, std::min((npix + 31) / 32, 8ll * 148)), (unsigned)((dy.c + 127) / 128));
+    bias_grad_dense_kernel<<<grid, 256, 0, ST>>>(dy.ptr, npix, dy.sw, dy.c, db);
+    TPG_CHECK_LAUNCH("bias_grad");
+    return 0;
+  }
   dim3 grid((unsigned)std::max(1ll, std::min((npix + 63) / 64, 4ll * 148)), (unsigned)((dy.c + 31) / 32));
   bias_grad_kernel<<<grid, 256, 0, ST>>>(dv(dy), db);
   TPG_CHECK_LAUNCH("bias_grad");
@@ -836,6 +905,17 @@ int tpgan_split_tf32(tpgan_view src, tpgan_view hi, tpgan_view lo, void* stream)
   if (total <= 0) return 0;
   split_tf32_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(src), dv(hi), dv(lo));
   TPG_CHECK_LAUNCH("split_tf32");
+  return 0;
+}
+
+int tpgan_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int32_t* step_dev, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || !step_dev || n <= 0) return set_error(TPGAN_ERR_INVALID, "adam_step_dev: bad args");
+  counter_inc_kernel<<<1, 1, 0, ST>>>(step_dev);
+  TPG_CHECK_LAUNCH("counter_inc");
+  adam_dev_kernel<<<grid_for(n, 256, 16), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev,
+                                                        grad_scale);
+  TPG_CHECK_LAUNCH("adam_step_dev");
   return 0;
 }
 

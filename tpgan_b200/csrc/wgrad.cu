@@ -196,17 +196,42 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
       const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols) + ((uint32_t)(q * 32) << 16);
       const int c_begin = u.ks * G.chunks_per_split;
       const bool nonempty = c_begin < G.chunks;
+      const bool single = (G.ksplits == 1) && (G.accumulate == 0);  // sole writer of this dW tile: plain stores
       for (int c0 = 0; c0 < G.block_n; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
         if (mvalid && nonempty) {
+          const int n0 = u.nt * G.block_n + c0;
+          if (G.transpose_out) {   // dw[n][m]: lanes hold consecutive m -> every red is a coalesced 128 B row segment
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = u.nt * G.block_n + c0 + j;
-            if (n < G.n_valid) {
-              const size_t idx = G.transpose_out ? ((size_t)n * G.k_pad + m) : ((size_t)m * G.k_pad + n);
-              atomicAdd(dw + idx, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + j;
+              if (n < G.n_valid) {
+                float* d = dw + (size_t)n * G.k_pad + m;
+                if (single) *d = __uint_as_float(r[j]); else atomicAdd(d, __uint_as_float(r[j]));
+              }
+            }
+          } else {                 // dw[m][n]: each lane owns 16 consecutive floats of its row -> 16-byte vector ops
+            float* d = dw + (size_t)m * G.k_pad + n0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (n0 + j + 3 < G.n_valid) {
+                if (single) {
+                  *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(__uint_as_float(r[j])),
+                               "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                               : "memory");
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (n0 + j + i < G.n_valid) {
+                    if (single) d[j + i] = __uint_as_float(r[j + i]); else atomicAdd(d + j + i, __uint_as_float(r[j + i]));
+                  }
+              }
             }
           }
         }

@@ -50,6 +50,41 @@ class T:
         return (self.act.n, self.act.h, self.act.w, self.act.c)
 
 
+class GradArena:
+    """Bump allocator for the packed weight-gradient / bias-gradient accumulators of all layers on one device, so a step
+    clears them with one memset per 256 MB chunk instead of two launches per layer."""
+
+    _per_device: Dict[str, "GradArena"] = {}
+
+    def __init__(self, device, chunk_elems: int = 1 << 26):
+        self.device, self.chunk_elems = device, chunk_elems
+        self.chunks: List[torch.Tensor] = []
+        self.used: List[int] = []
+
+    @classmethod
+    def get(cls, device) -> "GradArena":
+        key = str(torch.device(device))
+        if key not in cls._per_device:
+            cls._per_device[key] = GradArena(torch.device(device))
+        return cls._per_device[key]
+
+    def alloc(self, shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n4 = round_up(max(n, 1), 64)  # 256-byte granularity keeps every allocation TMA/vector aligned
+        if not self.chunks or self.used[-1] + n4 > self.chunks[-1].numel():
+            self.chunks.append(torch.zeros(max(self.chunk_elems, n4), dtype=torch.float32, device=self.device))
+            self.used.append(0)
+        o = self.used[-1]
+        self.used[-1] = o + n4
+        return self.chunks[-1][o:o + n].view(*shape)
+
+    def zero(self):
+        for c, u in zip(self.chunks, self.used):
+            c[:u].zero_()
+
+
 class ConvLayer:
     """One Conv2d / ConvTranspose2d / Linear of the reference model: reference-layout parameters + tensor-core packings.
 
@@ -90,7 +125,7 @@ class ConvLayer:
             self._alloc_lo()
         self.bias_int = torch.zeros(round_up(self.bias_len(), 4), dtype=torch.float32, device=device) \
             if self.bias is not None else None
-        self.db_int = torch.zeros_like(self.bias_int) if self.bias is not None else None
+        self.db_int = GradArena.get(device).alloc((self.bias_int.numel(),)) if self.bias is not None else None
         if out_cmap is not None:
             oc = torch.tensor(out_cmap, dtype=torch.long, device=device)
             self._b_valid = (oc >= 0).nonzero().flatten()
@@ -106,7 +141,8 @@ class ConvLayer:
         self.wf = ops.alloc_packed(self.kind_fwd, shp, rows_int=self.out_c, k_int=self.in_c, device=device)
         self.wd = ops.alloc_packed(self.kind_dgrad, shp, rows_int=self.in_c, k_int=self.out_c, device=device) \
             if need_dgrad else None
-        self.dw = ops.alloc_packed(self.kind_fwd, shp, rows_int=self.out_c, k_int=self.in_c, device=device)
+        self.dw = ops.Packed(GradArena.get(device).alloc(tuple(self.wf.data.shape)), self.wf.taps, self.wf.rows, self.wf.k,
+                             self.wf.rows_pad, self.wf.k_pad)
 
     def _alloc_lo(self):
         """Residual packings w - tf32(w) for the fp32-exact verification mode (Plan(exact=True))."""
@@ -204,7 +240,7 @@ class DeconvAsLinear(ConvLayer):
         n, kdim = self.kk * self.co, self.in_c
         mk = lambda: torch.zeros((2, n, kdim), dtype=torch.float32, device=device)
         self.wf = ops.Packed(mk(), 1, n, kdim, n, kdim)
-        self.dw = ops.Packed(mk(), 1, n, kdim, n, kdim)
+        self.dw = ops.Packed(GradArena.get(device).alloc((2, n, kdim)), 1, n, kdim, n, kdim)
         # views of the same storage in the [taps+1][Cout][Cin] geometry the (un)pack kernels use
         self._wf_taps = ops.Packed(self.wf.data, self.kk, self.co, kdim, self.co, kdim)
         self._dw_taps = ops.Packed(self.dw.data, self.kk, self.co, kdim, self.co, kdim)
@@ -405,9 +441,11 @@ class Plan:
                 lst.append(post)
         lst.append(self._conv_launch([a for a, _ in a3]))
 
-    def _emit_wgrad(self, specs, lst):
-        """specs: (L, x Act, dy Act) of one grouped weight-gradient launch."""
-        mk = lambda L, x, dy: ops.wgrad_args(L.kind_fwd, x, dy, L.dw, L.k, L.stride, L.pad)
+    def _emit_wgrad(self, specs, lst, accumulate: bool = True):
+        """specs: (L, x Act, dy Act) of one grouped weight-gradient launch.  accumulate=False: the launch is the only
+        writer of each layer's (cleared) dW this step."""
+        acc = accumulate or self.exact
+        mk = lambda L, x, dy: ops.wgrad_args(L.kind_fwd, x, dy, L.dw, L.k, L.stride, L.pad, acc)
         if not self.exact:
             fl = sum(self._flops(L, x, dy, False) for L, x, dy in specs)
             lst.append(self._wgrad_launch([mk(L, x, dy) for L, x, dy in specs], fl, ",".join(L.name for L, _, _ in specs) + ":wgrad"))
@@ -674,7 +712,7 @@ class Plan:
             self._finalize(outs[i])
         # weight / bias gradients
         if self.need_wgrad:
-            self._emit_wgrad([(layers[i], xs[i].act, self.grad_act(outs[i])) for i in live], self.bwd)
+            self._emit_wgrad([(layers[i], xs[i].act, self.grad_act(outs[i])) for i in live], self.bwd, accumulate=False)
             for i in live:
                 L = layers[i]
                 if L.db_int is not None:

@@ -169,8 +169,9 @@ def conv2d(*a, **kw) -> None:
     conv2d_grouped([conv_args(*a, **kw)])
 
 
-def wgrad_args(kind: int, x: Act, dy: Act, dw: Packed, k: int, stride: int, pad: int) -> WgradArgs:
-    return WgradArgs(kind, k, k, stride, pad, x.view(), dy.view(), dw.data.data_ptr(), dw.rows_pad, dw.k_pad)
+def wgrad_args(kind: int, x: Act, dy: Act, dw: Packed, k: int, stride: int, pad: int, accumulate: bool = True) -> WgradArgs:
+    return WgradArgs(kind, k, k, stride, pad, x.view(), dy.view(), dw.data.data_ptr(), dw.rows_pad, dw.k_pad,
+                     int(accumulate))
 
 
 def wgrad_grouped(args: List[WgradArgs]) -> None:
@@ -246,6 +247,13 @@ def maxout2_backward(x: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor) -> Non
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
     _lib.check(_lib.load().tpgan_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1,
                                            beta2, eps, weight_decay, step, grad_scale, _stream()), "adam_step")
+
+
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev: torch.Tensor, grad_scale=1.0) -> None:
+    assert step_dev.dtype == torch.int32 and step_dev.is_cuda
+    _lib.check(_lib.load().tpgan_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1,
+                                               beta2, eps, weight_decay, step_dev.data_ptr(), grad_scale, _stream()),
+               "adam_step_dev")
 
 
 def sample_sqnorm(g: Act, out: torch.Tensor) -> None:

@@ -29,7 +29,7 @@ import torch
 from . import config as cfg
 from . import ops
 from .D_and_G_model import PART_NAMES, PATCH_HW, Discriminator, Generator, _layer, _unpack_conv_seq
-from .engine import LINEAR, ConvLayer, Plan, T
+from .engine import LINEAR, ConvLayer, GradArena, Plan, T
 from .ModificationLayer import ResidualBlock, _negative_slope
 from .ops import Act, EPI_LEAKY, EPI_LINEAR, EPI_MASK
 
@@ -65,6 +65,7 @@ class FlatParams:
         self.m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.v = torch.zeros(off, dtype=torch.float32, device=dev)
         self.step = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         for n in names:
             p = named[n]
             o, k = self.offsets[n], p.numel()
@@ -73,8 +74,84 @@ class FlatParams:
             p.grad = self.grad[o:o + k].view(p.shape)
 
     def adam(self, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        """torch.optim.Adam update of the whole flat buffer; the step count is device-resident (graph-capturable)."""
         self.step += 1
-        ops.adam_step(self.data, self.grad, self.m, self.v, lr, betas[0], betas[1], eps, weight_decay, self.step, grad_scale)
+        ops.adam_step_dev(self.data, self.grad, self.m, self.v, lr, betas[0], betas[1], eps, weight_decay, self.step_dev,
+                          grad_scale)
+
+
+# ---------------------------------------------------------------------------------------------------------- CUDA graphs
+class Eager:
+    """Marks a schedule entry that must run eagerly (collectives, host-visible side effects)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self):
+        self.fn()
+
+
+class GraphRunner:
+    """Replays a schedule (list of callables) as CUDA graphs: every maximal run of capturable entries becomes one graph,
+    `Eager` entries run between them.  All device pointers in a schedule are static (pre-allocated plans)."""
+
+    def __init__(self, schedule: Sequence[Callable]):
+        self.segments: list = []
+        run: List[Callable] = []
+        for f in schedule:
+            if isinstance(f, Eager):
+                if run:
+                    self.segments.append(run)
+                    run = []
+                self.segments.append(f)
+            else:
+                run.append(f)
+        if run:
+            self.segments.append(run)
+        self.graphs: Optional[list] = None
+        self.warm = False
+        self.kernels_per_run = 0
+
+    def run_eager(self):
+        for seg in self.segments:
+            if isinstance(seg, Eager):
+                seg()
+            else:
+                for f in seg:
+                    f()
+
+    def capture(self):
+        from . import _lib
+        torch.cuda.synchronize()
+        self.graphs = []
+        l0 = _lib.launch_count()
+        for seg in self.segments:
+            if isinstance(seg, Eager):
+                seg()
+                self.graphs.append(seg)
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for f in seg:
+                    f()
+            g.replay()          # capture does not execute: run the segment once so later segments see its results
+            self.graphs.append(g)
+        self.kernels_per_run = _lib.launch_count() - l0   # kernels of this library recorded into the graphs
+        torch.cuda.synchronize()
+
+    def run(self):
+        if not self.warm:       # first call: plain launches (CUDA lazily loads kernels on first use, which capture forbids)
+            self.run_eager()
+            self.warm = True
+            return
+        if self.graphs is None:
+            self.capture()      # the capturing call also executes the schedule once
+            return
+        for g in self.graphs:
+            if isinstance(g, Eager):
+                g()
+            else:
+                g.replay()
 
 
 # ---------------------------------------------------------------------------------------------------------- critic
@@ -252,8 +329,7 @@ class CriticPlan:
             f()
 
     def zero_grad(self):
-        for L in self.layers:
-            L.zero_grad()
+        GradArena.get(self.device).zero()   # clears every layer's packed gradient accumulators (G's are stale here)
 
     def repack(self):
         for L in self.layers:
@@ -263,30 +339,30 @@ class CriticPlan:
         for L in self.layers:
             L.export_grad(accumulate=False)
 
-    def d_phase(self, gp_weight: float):
+    def d_phase_list(self, gp_weight: float) -> List[Callable]:
         """x0 must hold [fake; real; xhat].  Leaves dW/db of L_D in the layers' packed gradient buffers."""
         B = self.B
         gl = self.G_(self.logits)
         c = 1.0 / (B * self.logits.h * self.logits.w)
-        ops.fill(_sl(gl, 0, B), c)
-        ops.fill(_sl(gl, B, 2 * B), -c)
-        ops.fill(_sl(gl, 2 * B, 3 * B), 1.0)
-        self.zero_grad()
-        self._run(self.fwd_all)
-        self._run(self.bwd_d)
         gx = self.g_x
-        self.gp_sum.zero_()
-        ops.sample_sqnorm(gx, self.sq)
-        ops.gp_coeff(self.sq, self.coeff, gp_weight * 2.0 / B, self.gp_sum)
-        ops.sample_scale(gx, self.coeff, self.V_(self.x0))
-        self._run(self.tangent)
+        pre = [lambda: ops.fill(_sl(gl, 0, B), c), lambda: ops.fill(_sl(gl, B, 2 * B), -c),
+               lambda: ops.fill(_sl(gl, 2 * B, 3 * B), 1.0), self.zero_grad]
+        mid = [lambda: self.gp_sum.zero_(), lambda: ops.sample_sqnorm(gx, self.sq),
+               lambda: ops.gp_coeff(self.sq, self.coeff, gp_weight * 2.0 / B, self.gp_sum),
+               lambda: ops.sample_scale(gx, self.coeff, self.V_(self.x0))]
+        return pre + self.fwd_all + self.bwd_d + mid + self.tangent
 
-    def g_phase(self, adv_weight: float):
+    def g_phase_list(self, adv_weight: float) -> List[Callable]:
         """D(fake) with the current weights, then d(-adv_weight * mean D(fake))/d fake accumulated into dfake."""
         B = self.B
-        ops.fill(self.g_logits_g, -adv_weight / (B * self.logits.h * self.logits.w))
-        self._run(self.fwd_fake)
-        self._run(self.bwd_g)
+        seed = -adv_weight / (B * self.logits.h * self.logits.w)
+        return [lambda: ops.fill(self.g_logits_g, seed)] + self.fwd_fake + self.bwd_g
+
+    def d_phase(self, gp_weight: float):
+        self._run(self.d_phase_list(gp_weight))
+
+    def g_phase(self, adv_weight: float):
+        self._run(self.g_phase_list(adv_weight))
 
 
 # ---------------------------------------------------------------------------------------------------------- trainer
@@ -300,12 +376,13 @@ class TPGANTrainer:
     (DataAndDataset.py:10-56)."""
 
     def __init__(self, G: Generator, D: Discriminator, B: int, device="cuda", use_dropout: bool = False,
-                 exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0):
+                 exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0, use_graphs: bool = False):
         self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
         self.use_dropout, self.exact = use_dropout, exact
         self.w = dict(cfg.loss)
         self.lr = cfg.train["learning_rate"]
         self.world_size, self.group = world_size, group
+        self.use_graphs = use_graphs
         self._build_g()
         self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact)
         self.critic.build_g_phase(self.plan.grad_act(self.fake))
@@ -319,7 +396,13 @@ class TPGANTrainer:
             from .parallel import BucketReducer
             self.reducer = BucketReducer(self, bucket_mb, group)
         self.sums = torch.zeros(16, dtype=torch.float32, device=self.device)  # 0..7 image terms, 8..11 local parts, 12 ce
-        self._d_logits = None
+        self._d_logits = torch.zeros_like(self.critic.logits.buf[:2 * B])
+        self.inp: Optional[Dict[str, torch.Tensor]] = None
+        self.inp_has_mask = self.fixed_mask = False
+        self._sched: Dict[tuple, object] = {}
+        if self.mask is not None:
+            self._rand = torch.empty_like(self.mask.buf)
+            self._keep = torch.empty_like(self.mask.buf, dtype=torch.bool)
 
     # ---- generator plan
     def _build_g(self):
@@ -359,8 +442,24 @@ class TPGANTrainer:
         return order
 
     # ---- one training step
-    def stage_inputs(self, b: Dict[str, torch.Tensor]):
-        B = self.B
+    # ---- inputs: copied into static device buffers so that every pointer of the schedule is fixed
+    INPUT_KEYS = ("img", "img_frontal", "img64_frontal", "img32_frontal", "landmarks", "z", "label", "gp_alpha")
+
+    def load_inputs(self, b: Dict[str, torch.Tensor]):
+        if self.inp is None:
+            self.inp = {k: torch.empty_like(b[k], device=self.device).contiguous() for k in self.INPUT_KEYS}
+            if self.mask is not None:
+                self.inp["dropout_mask"] = torch.ones_like(self.mask.buf)
+        for k in self.INPUT_KEYS:
+            if b[k] is not self.inp[k]:
+                self.inp[k].copy_(b[k], non_blocking=True)
+        self.inp_has_mask = "dropout_mask" in b
+        if self.inp_has_mask:
+            self.inp["dropout_mask"].copy_(b["dropout_mask"].reshape(self.mask.buf.shape))
+
+    def _stage(self):
+        """Static input buffers -> NHWC staging + landmark crops (all kernel launches, no host dependence)."""
+        B, b = self.B, self.inp
         rt = not self.exact
         img = self.bufs["a128"].parts[2].act
         img.from_nchw(b["img"], round_tf32=rt)
@@ -368,64 +467,87 @@ class TPGANTrainer:
         self.t64.from_nchw(b["img64_frontal"])
         self.t32.from_nchw(b["img32_frontal"])
         self.bufs["zin"].parts[1].act.from_nchw(b["z"].reshape(B, -1, 1, 1), round_tf32=rt)
-        lm = b["landmarks"].contiguous()
-        ops.patch_crop(img, lm, [p.act for p in self.patches], self.boxes)
-        ops.patch_crop(self.frontal, lm, self.patches_gt, None)
+        ops.patch_crop(img, b["landmarks"], [p.act for p in self.patches], self.boxes)
+        ops.patch_crop(self.frontal, b["landmarks"], self.patches_gt, None)
         if self.mask is not None:
-            m = self.G.feature_predict.draw_mask(B, self.device) if "dropout_mask" not in b else b["dropout_mask"]
-            self.mask.buf.copy_(m.reshape(self.mask.buf.shape))
-        self.labels = b["label"]
-        self.alpha = b["gp_alpha"].contiguous()
+            if self.fixed_mask:
+                self.mask.buf.copy_(b["dropout_mask"])
+            else:
+                p = self.G.feature_predict.dropout.p
+                torch.rand(self.mask.buf.shape, out=self._rand)
+                torch.ge(self._rand, p, out=self._keep)
+                self.mask.buf.copy_(self._keep)
+                self.mask.buf.mul_(1.0 / (1.0 - p))     # nn.Dropout's keep mask scaled by 1/(1-p); RNG = torch's philox
 
-    def step(self, b: Dict[str, torch.Tensor], optimize: bool = True, read_metrics: bool = True):
+    def stage_inputs(self, b: Dict[str, torch.Tensor]):
+        self.load_inputs(b)
+        self.fixed_mask = self.inp_has_mask
+        self._stage()
+
+    def _schedule(self, optimize: bool) -> List[Callable]:
+        """The whole step as a flat list of launches (Eager entries = collectives)."""
         B, w, crit = self.B, self.w, self.critic
-        self.stage_inputs(b)
-        # ---------------- G forward
-        self.plan.run_forward()
         fake = self.fake.act
-        # ---------------- D phase
         x0 = crit.x0
-        ops.view_copy(fake, _sl(x0, 0, B))
-        ops.view_copy(self.frontal, _sl(x0, B, 2 * B))
-        ops.lerp(self.frontal, fake, self.alpha, _sl(x0, 2 * B, 3 * B))
-        crit.d_phase(float(w["weight_gradient_penalty"]))
-        crit.export_grads()
-        if read_metrics:
-            self._d_logits = torch.empty_like(crit.logits.buf[:2 * B])
-            ops.view_copy(_sl(crit.logits, 0, 2 * B), Act(self._d_logits, 0, 1))
+        sch: List[Callable] = [self._stage]
+        sch += self.plan.fwd
+        # ---------------- D phase
+        sch += [lambda: ops.view_copy(fake, _sl(x0, 0, B)), lambda: ops.view_copy(self.frontal, _sl(x0, B, 2 * B)),
+                lambda: ops.lerp(self.frontal, fake, self.inp["gp_alpha"], _sl(x0, 2 * B, 3 * B))]
+        sch += crit.d_phase_list(float(w["weight_gradient_penalty"]))
+        sch.append(crit.export_grads)
+        d_logits = self._d_logits
+        sch.append(lambda: ops.view_copy(_sl(crit.logits, 0, 2 * B), Act(d_logits, 0, 1)))
         if self.world_size > 1:
-            self._allreduce(self.flat_d.grad)
+            sch.append(Eager(lambda: self._allreduce(self.flat_d.grad)))
         if optimize:
-            self.flat_d.adam(self.lr, 1.0 / self.world_size)
-            crit.repack()
+            sch.append(lambda: self.flat_d.adam(self.lr, 1.0 / self.world_size))
+            sch.append(crit.repack)
         # ---------------- G phase
-        self.sums.zero_()
         n128, n64, n32 = B * 3 * 128 * 128, B * 3 * 64 * 64, B * 3 * 32 * 32
         wp, ws, wt = w["weight_pixelwise"], w["weight_symmetry"], w["weight_total_varation"]
         coeffs = [wp * w["weight_128"] / n128, wp * w["weight_64"] / n64, wp * w["weight_32"] / n32,
                   ws * w["weight_128"] / n128, ws * w["weight_64"] / n64, ws * w["weight_32"] / n32,
                   wt / (B * 3 * 127 * 128), wt / (B * 3 * 128 * 127)]
         dfake = self.plan.grad_act(self.fake)
-        ops.image_losses(fake, self.frontal, self.t64, self.t32, dfake, coeffs, self.sums[0:8])
-        crit.g_phase(float(w["weight_adv_G"]))
+        sch.append(lambda: self.sums.zero_())
+        sch.append(lambda: ops.image_losses(fake, self.frontal, self.t64, self.t32, dfake, coeffs, self.sums[0:8]))
+        sch += crit.g_phase_list(float(w["weight_adv_G"]))
         for i, (t, gt, (h, wd)) in enumerate(zip(self.local_imgs, self.patches_gt, PATCH_HW)):
-            ops.l1_loss(t.act, gt, self.plan.grad_act(t), w["weight_pixelwise_local"] / (B * 3 * h * wd),
-                        self.sums[8 + i:9 + i])
-        ops.softmax_ce(self.logits.act, self.labels, self.plan.grad_act(self.logits), w["weight_cross_entropy"] / B,
-                       self.sums[12:13])
-        for L in self.plan.layers:
-            L.zero_grad()
+            sch.append(lambda t=t, gt=gt, i=i, c=w["weight_pixelwise_local"] / (B * 3 * h * wd):
+                       ops.l1_loss(t.act, gt, self.plan.grad_act(t), c, self.sums[8 + i:9 + i]))
+        sch.append(lambda: ops.softmax_ce(self.logits.act, self.inp["label"], self.plan.grad_act(self.logits),
+                                          w["weight_cross_entropy"] / B, self.sums[12:13]))
+        sch.append(GradArena.get(self.device).zero)   # D's gradients were exported above
         if self.reducer is not None:   # bucketed all-reduce overlapped with backward
-            self.plan.run_backward(self.reducer.hooks())
-            self.reducer.finish()
+            hooks = self.reducer.hooks()
+            for i, f in enumerate(self.plan.bwd):
+                sch.append(f)
+                if (i + 1) in hooks:
+                    sch.append(Eager(hooks[i + 1]))
+            sch.append(Eager(self.reducer.finish))
         else:
-            self.plan.run_backward()
-            for L in self.plan.layers:
-                L.export_grad(accumulate=False)
+            sch += self.plan.bwd
+            sch.append(lambda: [L.export_grad(accumulate=False) for L in self.plan.layers])
         if optimize:
-            self.flat_g.adam(self.lr, 1.0 / self.world_size)
-            for L in self.plan.layers:
-                L.repack()
+            sch.append(lambda: self.flat_g.adam(self.lr, 1.0 / self.world_size))
+            sch.append(lambda: [L.repack() for L in self.plan.layers])
+        return sch
+
+    def step(self, b: Dict[str, torch.Tensor], optimize: bool = True, read_metrics: bool = True):
+        """One G+D training step.  With use_graphs the schedule is captured into CUDA graphs on first use and replayed."""
+        self.load_inputs(b)
+        self.fixed_mask = self.inp_has_mask
+        key = (optimize, self.fixed_mask)
+        if key not in self._sched:
+            sch = self._schedule(optimize)
+            self._sched[key] = GraphRunner(sch) if self.use_graphs else sch
+        sch = self._sched[key]
+        if self.use_graphs:
+            sch.run()
+        else:
+            for f in sch:
+                f()
         return self.read_metrics() if read_metrics else None
 
     def _allreduce(self, t: torch.Tensor):
