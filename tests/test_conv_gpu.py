@@ -46,6 +46,13 @@ CONV_CASES = [
     (2, 416, 416, 32, 32, 3, 1, 1),
     (4, 512, 1, 4, 4, 3, 1, 1),
     (4, 64, 3, 40, 40, 1, 1, 0),
+    # full-width (W = 128) stride-1 layers: served by the row-tile kernel (rowconv.cu); H need not divide the row tile
+    (2, 206, 206, 12, 128, 5, 1, 2),
+    (2, 75, 75, 7, 128, 7, 1, 3),
+    (3, 64, 64, 9, 128, 7, 1, 3),
+    (2, 206, 64, 10, 128, 5, 1, 2),
+    (2, 64, 32, 6, 128, 3, 1, 1),
+    (1, 32, 3, 5, 128, 3, 1, 1),
 ]
 
 

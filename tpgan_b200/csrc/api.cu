@@ -24,6 +24,7 @@ template <class Params>
 __global__ void tapgemm_kernel(const __grid_constant__ Params P, int* status);
 template <class Params>
 __global__ void wgrad_kernel(const __grid_constant__ Params P, int* status);
+__global__ void rowconv_kernel(const __grid_constant__ RowConvParams P, int* status);
 
 // ------------------------------------------------------------------------------------------------ error state
 static thread_local char g_err[512] = "";
@@ -281,6 +282,72 @@ static int launch_tapgemm(Params& P, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ row-tile conv
+// Eligible: Conv2d forward / input gradient, stride 1, "same" padding (2p == k-1), width exactly 128 (one GEMM tile = one
+// image row), i.e. every full-resolution layer of the global pathway.  Returns 1 when launched, 0 when not eligible.
+static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
+  *rc_out = 0;
+  static const bool disabled = getenv("TPGAN_NO_ROWCONV") != nullptr;
+  if (disabled) return 0;
+  if (a.kind != TPGAN_CONV_FWD && a.kind != TPGAN_CONV_DGRAD) return 0;
+  const int k = a.kh, p = a.pad;
+  if (a.kh != a.kw || a.stride != 1 || 2 * p != k - 1 || k < 3 || k * k > kMaxTaps) return 0;
+  if (a.in.w != 128 || a.out.w != 128 || a.in.h != a.out.h || a.in.n != a.out.n) return 0;
+  if (a.w_rows_pad > 256) return 0;
+  static thread_local RowConvParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = a.out.h; P.W = 128; P.Nimg = a.in.n; P.k = k;
+  P.n_tiles = 1;
+  P.block_n = ceil_div(a.w_rows_pad, 16) * 16;
+  // T output rows share every weight tile; accumulators stay double-buffered (T * block_n <= 256 columns per buffer) -
+  // measured: a single-buffered wider tile loses more to the epilogue bubble than it gains in weight reuse
+  int T = std::max(1, std::min(4, 256 / P.block_n));
+  T = std::max(1, std::min(T, P.H));
+  if (const char* ev = getenv("TPGAN_ROWCONV_T")) T = std::max(1, std::min(atoi(ev), 512 / P.block_n));
+  P.T = T;
+  P.double_buf = (P.block_n * T <= 256) ? 1 : 0;
+  P.row_tiles = ceil_div(P.H, T);
+  P.total_tiles = P.Nimg * P.row_tiles * P.n_tiles;
+  P.kchunks = ceil_div(a.in.c, 32);
+  P.last_mmas = ceil_div(a.in.c - 32 * (P.kchunks - 1), 8);
+  const bool fwd = a.kind == TPGAN_CONV_FWD;
+  P.dy0 = fwd ? -p : p - k + 1;
+  P.dx0 = P.dy0;
+  for (int r = 0; r < k; ++r)
+    for (int j = 0; j < k; ++j) {
+      P.wtap[r * k + j] = (unsigned char)(fwd ? (r * k + j) : ((k - 1 - r) * k + (k - 1 - j)));
+      P.dxoff[r * k + j] = (unsigned char)j;
+    }
+  P.slab_bytes = ceil_div((128 + k - 1) * 128, 1024) * 1024;
+  P.b_bytes = P.block_n * 128;
+  const int budget = g_dev.max_smem - 1024 - 1024;   // alignment slack + this kernel's static shared memory
+  P.a_slots = std::min(16, T + 2);
+  P.b_slots = std::min(16, (budget - P.a_slots * P.slab_bytes) / P.b_bytes);
+  if (P.b_slots < 3) {
+    P.a_slots = T + 1;
+    P.b_slots = std::min(16, (budget - P.a_slots * P.slab_bytes) / P.b_bytes);
+    if (P.b_slots < 2) return 0;
+  }
+  int rc = encode_nhwc(&P.amap, a.in.ptr, a.in.c, a.in.w, a.in.h, a.in.n, a.in.sw, a.in.sh, a.in.sn, 128 + k - 1, 1, 1);
+  if (rc) { *rc_out = rc; return 1; }
+  rc = encode_weights(&P.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, k * k + 1, P.block_n);
+  if (rc) { *rc_out = rc; return 1; }
+  P.out = to_dev(a.out); P.add1 = to_dev(a.add1); P.add2 = to_dev(a.add2); P.mask = to_dev(a.mask);
+  P.bias = a.bias; P.slopes = a.slopes;
+  P.cout_valid = a.out.c; P.epilogue = a.epilogue; P.slope = a.slope; P.round_tf32 = a.round_tf32;
+  if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) { *rc_out = set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view"); return 1; }
+  P.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask);
+  const int smem = P.a_slots * P.slab_bytes + P.b_slots * P.b_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(rowconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
+  if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+  const int grid = std::min(P.total_tiles, g_dev.sm_count);
+  rowconv_kernel<<<grid, 256, smem, st>>>(P, g_dev.status_dev);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowconv launch: %s", cudaGetErrorString(e)); return 1; }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 1;
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad planning
 static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G) {
   memset(&G, 0, sizeof(G));
@@ -392,6 +459,8 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (ngroups == 1) {
+    int rrc = 0;
+    if (try_rowconv(groups[0], st, &rrc)) return rrc;
     static thread_local TapGemmParams1 P;
     P.ngroups = 1;
     rc = plan_group(groups[0], P.g[0]);

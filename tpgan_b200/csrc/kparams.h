@@ -72,6 +72,24 @@ struct TapGemmParams1 {  // single-group variant (keeps the parameter block smal
   TapGemmGroup g[1];
 };
 
+// ---------------------------------------------------------------- row-tile convolution (W = 128, stride 1)
+struct RowConvParams {
+  CUtensorMap amap;        // 4D {C, W, H, N} fp32, box {32, W + k - 1, 1, 1}, 128B swizzle (an input-row slab)
+  CUtensorMap bmap;        // 3D {k_pad, rows_pad, taps+1}, box {32, block_n, 1}
+  int H, W, Nimg, T, k;    // T output rows per tile; k x k tap grid
+  int dy0, dx0;            // input pixel of grid tap (0,0) relative to the output pixel
+  int kchunks, last_mmas;
+  int n_tiles, block_n, row_tiles, total_tiles;
+  int a_slots, b_slots, slab_bytes, b_bytes, double_buf;
+  unsigned char wtap[kMaxTaps];   // weight tap slice for grid position r*k + j
+  unsigned char dxoff[kMaxTaps];  // slab pixel-row offset (j) for grid position r*k + j
+  DevView out, add1, add2, mask;
+  const float* bias;
+  const float* slopes;
+  int cout_valid, epilogue, round_tf32, vec_ok;
+  float slope;
+};
+
 // ---------------------------------------------------------------- weight-gradient GEMM
 // D[m = channel of P][n = channel of Q] (per tap) = sum over pixels P[pix, m] * Qtap[pix, n]
 struct WgradGroup {
