@@ -109,6 +109,11 @@ TPGAN_API int tpgan_unpack_weights(const float* packed, float* ref, int32_t taps
                          int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
                          const int32_t* k_map, int32_t accumulate, void* stream);
 
+/* Per-tap transpose between two packings of the same layer: dst[t][kk][r] = src[t][r][kk] for r < rows, kk < k
+ * (forward packing [tap][Cout][Cin] <-> input-gradient packing [tap][Cin][Cout]); padding of dst is left untouched. */
+TPGAN_API int tpgan_transpose_packed(const float* src, float* dst, int32_t taps, int32_t rows, int32_t k, int32_t rows_src_pad,
+                           int32_t k_src_pad, int32_t rows_dst_pad, int32_t k_dst_pad, void* stream);
+
 /* ---- HBM-bound kernels of the path ------------------------------------------------------------------- */
 
 /* NCHW (reference tensor layout) <-> NHWC view conversion, optional tf32 rounding on the way in. */

@@ -46,6 +46,7 @@ SYMBOLS = {
     "tpgan_conv2d_wgrad": (C.c_int, [C.POINTER(WgradArgs), _I32, _VP]),
     "tpgan_pack_weights": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _VP, _VP, _I32, _VP]),
     "tpgan_unpack_weights": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _VP, _VP, _I32, _VP]),
+    "tpgan_transpose_packed": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "tpgan_nchw_to_nhwc": (C.c_int, [_VP, View, _I32, _VP]),
     "tpgan_nhwc_to_nchw": (C.c_int, [View, _VP, _VP]),
     "tpgan_act_backward": (C.c_int, [View, View, View, _VP, _F, _VP]),

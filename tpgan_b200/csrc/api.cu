@@ -349,7 +349,7 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad planning
-static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G) {
+static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   memset(&G, 0, sizeof(G));
   const int k = a.kh;
   if (a.kh != a.kw || k < 1 || k > 8) return set_error(TPGAN_ERR_INVALID, "kernel %dx%d unsupported", a.kh, a.kw);
@@ -375,9 +375,9 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G) {
   G.Wp = Pt.w;
   G.Nimg = Pt.n;
   // pixel boxes of ~32 pixels
-  G.bw = (G.Wp <= 48) ? G.Wp : 32;
-  G.bh = std::max(1, std::min(G.Hp, 32 / G.bw));
-  G.bn = (G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, 32 / (G.bw * G.bh))) : 1;
+  G.bw = (G.Wp <= box_px + box_px / 2) ? G.Wp : box_px;
+  G.bh = std::max(1, std::min(G.Hp, box_px / G.bw));
+  G.bn = (G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, box_px / (G.bw * G.bh))) : 1;
   G.kp = ceil_div(G.bw * G.bh * G.bn, 8) * 8;
   G.tiles_w = ceil_div(G.Wp, G.bw);
   G.tiles_h = ceil_div(G.Hp, G.bh);
@@ -405,6 +405,25 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G) {
   rc = encode_planes(G.qmap, Qt, s, G.bw, G.bh, G.bn, swz);
   if (rc) return rc;
   return 0;
+}
+
+// Pixels per pipeline stage: the largest of {128, 64, 32} that still leaves >= 4 stages in shared memory for every group
+// (few, large TMA boxes and 8-16 MMAs per barrier round trip; measured 1.8x on the 64-channel 128x128 layers).
+static int choose_wgrad_px(const tpgan_wgrad_args* groups, int ngroups) {
+  if (const char* ev = getenv("TPGAN_WGRAD_PX")) return std::max(8, std::min(128, atoi(ev)));
+  const int budget = g_dev.max_smem - 1024 - 256;
+  int chunks = 0;
+  for (int i = 0; i < ngroups; ++i) {
+    const bool is_conv = groups[i].kind == TPGAN_CONV_FWD;
+    const int pc = is_conv ? groups[i].dy.c : groups[i].x.c, qc = is_conv ? groups[i].x.c : groups[i].dy.c;
+    const int mch = std::min(4, ceil_div(pc, 32));
+    const int nch_total = ceil_div(qc, 32);
+    const int nch = ceil_div(nch_total, ceil_div(nch_total, 8));
+    chunks = std::max(chunks, mch + nch);
+  }
+  for (int px : {128, 64})
+    if (budget / (chunks * px * 128) >= 4) return px;
+  return 32;
 }
 
 template <class Params>
@@ -484,15 +503,16 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
   if (ngroups == 1) {
     static thread_local WgradParams1 P;
     P.ngroups = 1;
-    rc = plan_wgrad(groups[0], P.g[0]);
+    rc = plan_wgrad(groups[0], P.g[0], choose_wgrad_px(groups, 1));
     if (rc) return rc;
     return launch_wgrad(P, st);
   }
   static thread_local WgradParams P;
   P.ngroups = ngroups;
   bool uniform = true;
+  const int px = choose_wgrad_px(groups, ngroups);
   for (int i = 0; i < ngroups; ++i) {
-    rc = plan_wgrad(groups[i], P.g[i]);
+    rc = plan_wgrad(groups[i], P.g[i], px);
     if (rc) return rc;
     const WgradGroup& G = P.g[i];
     // the zero-padded K rows of the smem ring stay zero only if every box fills its rows or all boxes are alike

@@ -68,6 +68,72 @@ __global__ void unpack_kernel(const float* __restrict__ packed, float* __restric
   }
 }
 
+
+// ---- fast (un)packing for the row-contiguous case (ref_k_stride == taps): one block per packed row, the reference row
+// (k_ref x taps contiguous floats) staged through shared memory so that both the global read and the global write are
+// coalesced.  Used after every optimizer step (pack) and after every backward (unpack) for all 172 conv layers.
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ ref, float* __restrict__ packed, int taps,
+                                                        int rows, int k, int rows_pad, int k_pad, long long rs, int row_len,
+                                                        const int* __restrict__ row_map, const int* __restrict__ k_map,
+                                                        int round) {
+  extern __shared__ float srow[];
+  const int r = blockIdx.x;
+  const int rref = (r < rows) ? (row_map ? row_map[r] : r) : -1;
+  if (rref >= 0) {
+    const float* src = ref + (long long)rref * rs;
+    for (int i = threadIdx.x; i < row_len; i += blockDim.x) srow[i] = src[i];
+  }
+  __syncthreads();
+  for (int t = 0; t <= taps; ++t) {
+    float* dst = packed + ((long long)t * rows_pad + r) * k_pad;
+    for (int kk = threadIdx.x; kk < k_pad; kk += blockDim.x) {
+      float v = 0.f;
+      if (t < taps && rref >= 0 && kk < k) {
+        const int kref = k_map ? k_map[kk] : kk;
+        if (kref >= 0) v = srow[kref * taps + t];
+      }
+      dst[kk] = (round == 1) ? round_tf32(v) : ((round == 2) ? (v - round_tf32(v)) : v);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) unpack_rows_kernel(const float* __restrict__ packed, float* __restrict__ ref, int taps,
+                                                          int rows, int k, int rows_pad, int k_pad, long long rs, int row_len,
+                                                          const int* __restrict__ row_map, const int* __restrict__ k_map,
+                                                          int accumulate) {
+  extern __shared__ float srow[];
+  const int r = blockIdx.x;
+  const int rref = row_map ? row_map[r] : r;
+  if (rref < 0) return;
+  for (int t = 0; t < taps; ++t) {
+    const float* src = packed + ((long long)t * rows_pad + r) * k_pad;
+    for (int kk = threadIdx.x; kk < k; kk += blockDim.x) {
+      const int kref = k_map ? k_map[kk] : kk;
+      if (kref >= 0) srow[kref * taps + t] = src[kk];
+    }
+  }
+  __syncthreads();
+  float* dst = ref + (long long)rref * rs;
+  for (int i = threadIdx.x; i < row_len; i += blockDim.x) dst[i] = accumulate ? (dst[i] + srow[i]) : srow[i];
+}
+// dst[t][kk][r] = src[t][r][kk] for r < rows, kk < k (per-tap transpose between the forward and the dgrad packing)
+__global__ void transpose_packed_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int k,
+                                        int rows_src_pad, int k_src_pad, int rows_dst_pad, int k_dst_pad) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const float* s = src + (long long)t * rows_src_pad * k_src_pad;
+  float* d = dst + (long long)t * rows_dst_pad * k_dst_pad;
+  const int k0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, kk = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && kk < k) ? s[(long long)r * k_src_pad + kk] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int kk = k0 + i, r = r0 + threadIdx.x;
+    if (kk < k && r < rows) d[(long long)kk * k_dst_pad + r] = tile[threadIdx.x][i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ layout
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, V dst, int round) {
   const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
@@ -667,6 +733,19 @@ int tpgan_pack_weights(const float* ref, float* packed, int32_t taps, int32_t ro
                        int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
                        const int32_t* k_map, int32_t round_tf32, void* stream) {
   if (!ref || !packed || taps < 1 || rows > rows_pad || k > k_pad) return set_error(TPGAN_ERR_INVALID, "pack: bad args");
+  if (ref_k_stride == taps && ref_row_stride % taps == 0 && ref_row_stride * 4 <= 192 * 1024) {
+    const int row_len = (int)ref_row_stride;   // k_ref * taps contiguous floats per reference row
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+      cudaFuncSetAttribute(unpack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+      attr_set = true;
+    }
+    pack_rows_kernel<<<rows_pad, 256, (size_t)row_len * 4, ST>>>(ref, packed, taps, rows, k, rows_pad, k_pad, ref_row_stride,
+                                                                row_len, row_map, k_map, round_tf32);
+    TPG_CHECK_LAUNCH("pack_weights");
+    return 0;
+  }
   long long total = (long long)(taps + 1) * rows_pad * k_pad;
   pack_kernel<<<grid_for(total, 256), 256, 0, ST>>>(ref, packed, taps, rows, k, rows_pad, k_pad, ref_row_stride,
                                                     ref_k_stride, row_map, k_map, round_tf32);
@@ -677,6 +756,19 @@ int tpgan_unpack_weights(const float* packed, float* ref, int32_t taps, int32_t 
                          int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
                          const int32_t* k_map, int32_t accumulate, void* stream) {
   if (!ref || !packed || taps < 1 || rows > rows_pad || k > k_pad) return set_error(TPGAN_ERR_INVALID, "unpack: bad args");
+  if (ref_k_stride == taps && ref_row_stride % taps == 0 && ref_row_stride * 4 <= 192 * 1024) {
+    const int row_len = (int)ref_row_stride;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+      cudaFuncSetAttribute(unpack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+      attr_set = true;
+    }
+    unpack_rows_kernel<<<rows, 256, (size_t)row_len * 4, ST>>>(packed, ref, taps, rows, k, rows_pad, k_pad, ref_row_stride,
+                                                              row_len, row_map, k_map, accumulate);
+    TPG_CHECK_LAUNCH("unpack_weights");
+    return 0;
+  }
   long long total = (long long)taps * rows * k;
   unpack_kernel<<<grid_for(total, 256), 256, 0, ST>>>(packed, ref, taps, rows, k, rows_pad, k_pad, ref_row_stride,
                                                       ref_k_stride, row_map, k_map, accumulate);
@@ -916,6 +1008,17 @@ int tpgan_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n,
   adam_dev_kernel<<<grid_for(n, 256, 16), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev,
                                                         grad_scale);
   TPG_CHECK_LAUNCH("adam_step_dev");
+  return 0;
+}
+
+int tpgan_transpose_packed(const float* src, float* dst, int32_t taps, int32_t rows, int32_t k, int32_t rows_src_pad,
+                           int32_t k_src_pad, int32_t rows_dst_pad, int32_t k_dst_pad, void* stream) {
+  if (!src || !dst || taps < 1 || rows < 1 || k < 1 || rows > rows_src_pad || k > k_src_pad || k > rows_dst_pad ||
+      rows > k_dst_pad)
+    return set_error(TPGAN_ERR_INVALID, "transpose_packed: bad args");
+  dim3 grid((unsigned)((k + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)taps), block(32, 8);
+  transpose_packed_kernel<<<grid, block, 0, ST>>>(src, dst, rows, k, rows_src_pad, k_src_pad, rows_dst_pad, k_dst_pad);
+  TPG_CHECK_LAUNCH("transpose_packed");
   return 0;
 }
 

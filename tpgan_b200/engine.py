@@ -158,9 +158,17 @@ class ConvLayer:
         if not self.ready:
             return
         w = self._w()
-        ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map)
-        if self.wd is not None:
+        # the packing whose rows follow the reference's leading dimension is a row-contiguous (fast) pack; the other one
+        # is its per-tap transpose
+        if not self.transposed:
+            ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map)
+            if self.wd is not None:
+                ops.transpose_packed(self.wf, self.wd)
+        elif self.wd is not None:
             ops.pack_weights(w, self.kind_dgrad, self.wd, row_map=self.in_map, k_map=self.out_map)
+            ops.transpose_packed(self.wd, self.wf)
+        else:
+            ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map)
         if self.wf_lo is not None:
             ops.pack_weights(w, self.kind_fwd, self.wf_lo, row_map=self.out_map, k_map=self.in_map, round_tf32=2)
             if self.wd_lo is not None:
@@ -202,8 +210,17 @@ class ConvLayer:
         """Packed dW / internal db -> .grad of the reference-layout parameters."""
         if not self.ready or self.weight.grad is None:
             return
-        ops.unpack_weights(self.dw, self.weight.grad.view(self.w_shape), self.kind_fwd, row_map=self.out_map,
-                           k_map=self.in_map, accumulate=accumulate)
+        if self.transposed and self.wd is not None:
+            # deconv: transpose the [tap][Cout][Cin] gradient into the row-contiguous [tap][Cin][Cout] geometry first
+            if getattr(self, "_dw_t", None) is None:
+                self._dw_t = ops.Packed(torch.zeros_like(self.wd.data), self.wd.taps, self.wd.rows, self.wd.k,
+                                        self.wd.rows_pad, self.wd.k_pad)
+            ops.transpose_packed(self.dw, self._dw_t)
+            ops.unpack_weights(self._dw_t, self.weight.grad.view(self.w_shape), self.kind_dgrad, row_map=self.in_map,
+                               k_map=self.out_map, accumulate=accumulate)
+        else:
+            ops.unpack_weights(self.dw, self.weight.grad.view(self.w_shape), self.kind_fwd, row_map=self.out_map,
+                               k_map=self.in_map, accumulate=accumulate)
         self._export_bias(accumulate)
 
     def _export_bias(self, accumulate):

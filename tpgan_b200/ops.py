@@ -152,6 +152,14 @@ def unpack_weights(packed: Packed, w_grad: torch.Tensor, kind: int = CONV_FWD, r
                                                 int(accumulate), _stream()), "unpack_weights")
 
 
+def transpose_packed(src: Packed, dst: Packed) -> None:
+    """dst[t][kk][r] = src[t][r][kk] over the valid region (forward packing <-> input-gradient packing)."""
+    assert src.taps == dst.taps and src.rows == dst.k and src.k == dst.rows
+    _lib.check(_lib.load().tpgan_transpose_packed(src.data.data_ptr(), dst.data.data_ptr(), src.taps, src.rows, src.k,
+                                                  src.rows_pad, src.k_pad, dst.rows_pad, dst.k_pad, _stream()),
+               "transpose_packed")
+
+
 def conv_args(kind: int, x: Act, out: Act, w: Packed, k: int, stride: int, pad: int, bias: Optional[torch.Tensor] = None,
               add1: Optional[Act] = None, add2: Optional[Act] = None, mask: Optional[Act] = None,
               slopes: Optional[torch.Tensor] = None, slope: float = 0.0, epilogue: int = EPI_LINEAR,
