@@ -114,6 +114,33 @@ TPGAN_API int tpgan_unpack_weights(const float* packed, float* ref, int32_t taps
 TPGAN_API int tpgan_transpose_packed(const float* src, float* dst, int32_t taps, int32_t rows, int32_t k, int32_t rows_src_pad,
                            int32_t k_src_pad, int32_t rows_dst_pad, int32_t k_dst_pad, void* stream);
 
+/* ---- multi-tensor variants: ONE launch over a device-resident job table (one job per layer) ------------------------
+ * block_begin = first block of the job in the launch; jobs sorted by block_begin; total_blocks = sum over jobs. */
+typedef struct tpgan_bias_job {   /* db[c] += sum over npix pixels of dy[pix*sw + c]; blocks = pix_blocks * cgroups */
+  const float* dy;
+  float* db;
+  int64_t npix, sw;
+  int32_t c, block_begin, pix_blocks, cgroups; /* cgroups = ceil(c / 128) */
+} tpgan_bias_job;
+typedef struct tpgan_pack_job {   /* row-contiguous (un)pack, see tpgan_pack_weights; blocks = rows_pad (pack) / rows */
+  const float* ref_c;             /* reference tensor (read when packing)  */
+  float* ref;                     /* same tensor (written when unpacking)  */
+  float* packed;
+  const int32_t* row_map;
+  const int32_t* k_map;
+  int64_t rs;                     /* reference row stride = row_len */
+  int32_t taps, rows, k, rows_pad, k_pad, row_len, flag /* pack: round mode 0/1/2; unpack: accumulate */, block_begin;
+} tpgan_pack_job;
+typedef struct tpgan_transpose_job { /* see tpgan_transpose_packed; blocks = taps * tiles_r * tiles_k */
+  const float* src;
+  float* dst;
+  int32_t taps, rows, k, rows_src_pad, k_src_pad, rows_dst_pad, k_dst_pad, block_begin, tiles_k, tiles_r;
+} tpgan_transpose_job;
+TPGAN_API int tpgan_bias_grad_multi(const tpgan_bias_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream);
+TPGAN_API int tpgan_pack_multi(const tpgan_pack_job* jobs_dev, int32_t njobs, int32_t total_blocks, int32_t max_row_len,
+                     int32_t unpack, void* stream);
+TPGAN_API int tpgan_transpose_multi(const tpgan_transpose_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream);
+
 /* ---- HBM-bound kernels of the path ------------------------------------------------------------------- */
 
 /* NCHW (reference tensor layout) <-> NHWC view conversion, optional tf32 rounding on the way in. */

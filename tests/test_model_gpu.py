@@ -253,4 +253,5 @@ def test_cuda_graph_replay_matches_eager():
     assert rel(traj[2][1], traj[0][1]) <= 3 * spread + 1e-6, (rel(traj[2][1], traj[0][1]), spread)
     for k in traj[0][0]:
         noise = abs(traj[0][0][k] - traj[1][0][k])
-        assert abs(traj[0][0][k] - traj[2][0][k]) <= 5 * noise + 2e-3 * abs(traj[0][0][k]) + 1e-5, (k, traj[0][0][k], traj[2][0][k])
+        # (||grad||-1)^2 and the critic means are differences of nearly equal numbers: allow an absolute slack as well
+        assert abs(traj[0][0][k] - traj[2][0][k]) <= 5 * noise + 2e-3 * abs(traj[0][0][k]) + 1e-3, (k, traj[0][0][k], traj[2][0][k])

@@ -35,6 +35,24 @@ class WgradArgs(C.Structure):
                 ("accumulate", C.c_int32)]
 
 
+class BiasJob(C.Structure):
+    _fields_ = [("dy", C.c_void_p), ("db", C.c_void_p), ("npix", C.c_int64), ("sw", C.c_int64), ("c", C.c_int32),
+                ("block_begin", C.c_int32), ("pix_blocks", C.c_int32), ("cgroups", C.c_int32)]
+
+
+class PackJob(C.Structure):
+    _fields_ = [("ref_c", C.c_void_p), ("ref", C.c_void_p), ("packed", C.c_void_p), ("row_map", C.c_void_p),
+                ("k_map", C.c_void_p), ("rs", C.c_int64), ("taps", C.c_int32), ("rows", C.c_int32), ("k", C.c_int32),
+                ("rows_pad", C.c_int32), ("k_pad", C.c_int32), ("row_len", C.c_int32), ("flag", C.c_int32),
+                ("block_begin", C.c_int32)]
+
+
+class TransposeJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("taps", C.c_int32), ("rows", C.c_int32), ("k", C.c_int32),
+                ("rows_src_pad", C.c_int32), ("k_src_pad", C.c_int32), ("rows_dst_pad", C.c_int32),
+                ("k_dst_pad", C.c_int32), ("block_begin", C.c_int32), ("tiles_k", C.c_int32), ("tiles_r", C.c_int32)]
+
+
 NULL_VIEW = View(None, 0, 0, 0, 0, 0, 0, 0)
 
 _lib: Optional[C.CDLL] = None
@@ -47,6 +65,9 @@ SYMBOLS = {
     "tpgan_pack_weights": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _VP, _VP, _I32, _VP]),
     "tpgan_unpack_weights": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _VP, _VP, _I32, _VP]),
     "tpgan_transpose_packed": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "tpgan_bias_grad_multi": (C.c_int, [_VP, _I32, _I32, _VP]),
+    "tpgan_pack_multi": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _VP]),
+    "tpgan_transpose_multi": (C.c_int, [_VP, _I32, _I32, _VP]),
     "tpgan_nchw_to_nhwc": (C.c_int, [_VP, View, _I32, _VP]),
     "tpgan_nhwc_to_nchw": (C.c_int, [View, _VP, _VP]),
     "tpgan_act_backward": (C.c_int, [View, View, View, _VP, _F, _VP]),

@@ -718,6 +718,126 @@ __global__ void split_tf32_kernel(V s, V hi, V lo) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ multi-tensor launches
+// One launch over a device-resident job table instead of one tiny launch per layer (172 conv layers): bias gradients,
+// weight packing (+ per-tap transposes) after the optimizer step, gradient unpacking after backward.
+template <class Job>
+__device__ __forceinline__ int find_job(const Job* jobs, int njobs, int block) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_begin <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) bias_grad_multi_kernel(const tpgan_bias_job* __restrict__ jobs, int njobs) {
+  __shared__ float4 red[8][32];
+  const int ji = find_job(jobs, njobs, (int)blockIdx.x);
+  const tpgan_bias_job J = jobs[ji];
+  const int local = (int)blockIdx.x - J.block_begin;
+  const int cg = local % J.cgroups, pb = local / J.cgroups;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c = (cg * 32 + lane) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < J.c) {
+    const float* base = J.dy + c;
+    const long long stride = (long long)J.pix_blocks * 8;
+    long long pix = (long long)pb * 8 + wp;
+    for (; pix + 3 * stride < J.npix; pix += 4 * stride) {
+      const float4 v0 = *reinterpret_cast<const float4*>(base + pix * J.sw);
+      const float4 v1 = *reinterpret_cast<const float4*>(base + (pix + stride) * J.sw);
+      const float4 v2 = *reinterpret_cast<const float4*>(base + (pix + 2 * stride) * J.sw);
+      const float4 v3 = *reinterpret_cast<const float4*>(base + (pix + 3 * stride) * J.sw);
+      a.x += (v0.x + v1.x) + (v2.x + v3.x);
+      a.y += (v0.y + v1.y) + (v2.y + v3.y);
+      a.z += (v0.z + v1.z) + (v2.z + v3.z);
+      a.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; pix < J.npix; pix += stride) {
+      const float4 v = *reinterpret_cast<const float4*>(base + pix * J.sw);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  red[wp][lane] = a;
+  __syncthreads();
+  if (wp == 0 && c < J.c) {
+    float4 s = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s.x += red[i][lane].x; s.y += red[i][lane].y; s.z += red[i][lane].z; s.w += red[i][lane].w; }
+    atomicAdd(J.db + c, s.x);
+    if (c + 1 < J.c) atomicAdd(J.db + c + 1, s.y);
+    if (c + 2 < J.c) atomicAdd(J.db + c + 2, s.z);
+    if (c + 3 < J.c) atomicAdd(J.db + c + 3, s.w);
+  }
+}
+
+// mode 0: pack rows (ref -> packed), mode 1: unpack rows (packed -> ref, accumulate per job flag)
+__global__ void __launch_bounds__(256) pack_multi_kernel(const tpgan_pack_job* __restrict__ jobs, int njobs, int mode) {
+  extern __shared__ float srow[];
+  const int ji = find_job(jobs, njobs, (int)blockIdx.x);
+  const tpgan_pack_job J = jobs[ji];
+  const int r = (int)blockIdx.x - J.block_begin;
+  const int taps = J.taps;
+  if (mode == 0) {
+    const int rref = (r < J.rows) ? (J.row_map ? J.row_map[r] : r) : -1;
+    if (rref >= 0) {
+      const float* src = J.ref_c + (long long)rref * J.rs;
+      for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) srow[i] = src[i];
+    }
+    __syncthreads();
+    for (int t = 0; t <= taps; ++t) {
+      float* dst = J.packed + ((long long)t * J.rows_pad + r) * J.k_pad;
+      for (int kk = threadIdx.x; kk < J.k_pad; kk += blockDim.x) {
+        float v = 0.f;
+        if (t < taps && rref >= 0 && kk < J.k) {
+          const int kref = J.k_map ? J.k_map[kk] : kk;
+          if (kref >= 0) v = srow[kref * taps + t];
+        }
+        dst[kk] = (J.flag == 1) ? round_tf32(v) : ((J.flag == 2) ? (v - round_tf32(v)) : v);
+      }
+    }
+  } else {
+    if (r >= J.rows) return;
+    const int rref = J.row_map ? J.row_map[r] : r;
+    if (rref < 0) return;
+    for (int t = 0; t < taps; ++t) {
+      const float* src = J.packed + ((long long)t * J.rows_pad + r) * J.k_pad;
+      for (int kk = threadIdx.x; kk < J.k; kk += blockDim.x) {
+        const int kref = J.k_map ? J.k_map[kk] : kk;
+        if (kref >= 0) srow[kref * taps + t] = src[kk];
+      }
+    }
+    __syncthreads();
+    float* dst = J.ref + (long long)rref * J.rs;
+    for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) dst[i] = J.flag ? (dst[i] + srow[i]) : srow[i];
+  }
+}
+
+__global__ void transpose_multi_kernel(const tpgan_transpose_job* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][33];
+  const int ji = find_job(jobs, njobs, (int)blockIdx.x);
+  const tpgan_transpose_job J = jobs[ji];
+  int local = (int)blockIdx.x - J.block_begin;
+  const int tk = local % J.tiles_k;
+  local /= J.tiles_k;
+  const int tr = local % J.tiles_r;
+  const int t = local / J.tiles_r;
+  const float* s = J.src + (long long)t * J.rows_src_pad * J.k_src_pad;
+  float* d = J.dst + (long long)t * J.rows_dst_pad * J.k_dst_pad;
+  const int k0 = tk * 32, r0 = tr * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, kk = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < J.rows && kk < J.k) ? s[(long long)r * J.k_src_pad + kk] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int kk = k0 + i, r = r0 + threadIdx.x;
+    if (kk < J.k && r < J.rows) d[(long long)kk * J.k_dst_pad + r] = tile[threadIdx.x][i];
+  }
+}
+
 static bool same_geom(const tpgan_view& a, const tpgan_view& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
@@ -1019,6 +1139,32 @@ int tpgan_transpose_packed(const float* src, float* dst, int32_t taps, int32_t r
   dim3 grid((unsigned)((k + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)taps), block(32, 8);
   transpose_packed_kernel<<<grid, block, 0, ST>>>(src, dst, rows, k, rows_src_pad, k_src_pad, rows_dst_pad, k_dst_pad);
   TPG_CHECK_LAUNCH("transpose_packed");
+  return 0;
+}
+
+int tpgan_bias_grad_multi(const tpgan_bias_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream) {
+  if (!jobs_dev || njobs < 1 || total_blocks < 1) return set_error(TPGAN_ERR_INVALID, "bias_grad_multi: bad args");
+  bias_grad_multi_kernel<<<total_blocks, 256, 0, ST>>>(jobs_dev, njobs);
+  TPG_CHECK_LAUNCH("bias_grad_multi");
+  return 0;
+}
+int tpgan_pack_multi(const tpgan_pack_job* jobs_dev, int32_t njobs, int32_t total_blocks, int32_t max_row_len, int32_t unpack,
+                     void* stream) {
+  if (!jobs_dev || njobs < 1 || total_blocks < 1 || max_row_len < 1 || max_row_len > 48 * 1024)
+    return set_error(TPGAN_ERR_INVALID, "pack_multi: bad args");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(pack_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+    attr_set = true;
+  }
+  pack_multi_kernel<<<total_blocks, 256, (size_t)max_row_len * 4, ST>>>(jobs_dev, njobs, unpack ? 1 : 0);
+  TPG_CHECK_LAUNCH("pack_multi");
+  return 0;
+}
+int tpgan_transpose_multi(const tpgan_transpose_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream) {
+  if (!jobs_dev || njobs < 1 || total_blocks < 1) return set_error(TPGAN_ERR_INVALID, "transpose_multi: bad args");
+  transpose_multi_kernel<<<total_blocks, dim3(32, 8), 0, ST>>>(jobs_dev, njobs);
+  TPG_CHECK_LAUNCH("transpose_multi");
   return 0;
 }
 

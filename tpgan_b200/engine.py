@@ -123,9 +123,10 @@ class ConvLayer:
         self._alloc(device, need_dgrad)
         if exact:
             self._alloc_lo()
-        self.bias_int = torch.zeros(round_up(self.bias_len(), 4), dtype=torch.float32, device=device) \
-            if self.bias is not None else None
-        self.db_int = GradArena.get(device).alloc((self.bias_int.numel(),)) if self.bias is not None else None
+        nb = round_up(self.bias_len(), 4)
+        self._bias_buf = torch.zeros(2 * nb, dtype=torch.float32, device=device) if self.bias is not None else None
+        self.bias_int = self._bias_buf[:nb] if self.bias is not None else None
+        self.db_int = GradArena.get(device).alloc((nb,)) if self.bias is not None else None
         if out_cmap is not None:
             oc = torch.tensor(out_cmap, dtype=torch.long, device=device)
             self._b_valid = (oc >= 0).nonzero().flatten()
@@ -182,6 +183,52 @@ class ConvLayer:
             else:
                 self.bias_int.zero_()
                 self.bias_int[self._b_valid] = self.bias.data[self._b_ref]
+
+    # ---- job descriptors for the multi-tensor launches (None = this layer needs its own calls)
+    MAX_MULTI_ROW = 12288   # floats of shared memory per block in the multi-tensor pack kernel
+
+    def _row_geometry(self):
+        """(pack target, transpose target, rows map, k map, reference row length) of the row-contiguous packing."""
+        taps = self.k * self.k
+        if not self.transposed:
+            return self.wf, self.wd, self.out_map, self.in_map, self.w_shape[1] * taps
+        return self.wd, self.wf, self.in_map, self.out_map, self.w_shape[1] * taps
+
+    def multi_ok(self) -> bool:
+        if type(self) is not ConvLayer or not self.ready or self.wf_lo is not None:
+            return False
+        if self.transposed and self.wd is None:
+            return False
+        return self._row_geometry()[4] <= self.MAX_MULTI_ROW
+
+    def pack_jobs(self):
+        """([pack jobs], [transpose jobs]) re-creating wf / wd / bias_int from the reference-layout parameters."""
+        tgt, other, rmap, kmap, row_len = self._row_geometry()
+        packs = [ops.pack_job(self.weight.data, tgt, self.k * self.k, row_len, rmap, kmap, 1)]
+        if self.bias is not None:
+            nb = self.bias_int.numel()
+            bp = ops.Packed(self._bias_buf, 1, 1, self.out_c, 1, nb)
+            packs.append(ops.pack_job(self.bias.data, bp, 1, self.bias.numel(), None, self.out_map, 0))
+        trans = [ops.transpose_job(tgt, other)] if other is not None else []
+        return packs, trans
+
+    def unpack_jobs(self, accumulate: bool = False):
+        """([transpose jobs], [unpack jobs]) writing weight.grad / bias.grad from the packed accumulators."""
+        tgt, other, rmap, kmap, row_len = self._row_geometry()
+        trans = []
+        src = self.dw
+        if self.transposed:
+            if getattr(self, "_dw_t", None) is None:
+                self._dw_t = ops.Packed(torch.zeros_like(self.wd.data), self.wd.taps, self.wd.rows, self.wd.k,
+                                        self.wd.rows_pad, self.wd.k_pad)
+            trans.append(ops.transpose_job(self.dw, self._dw_t))
+            src = self._dw_t
+        unp = [ops.pack_job(self.weight.grad, src, self.k * self.k, row_len, rmap, kmap, int(accumulate))]
+        if self.bias is not None:
+            nb = self.bias_int.numel()
+            bp = ops.Packed(self.db_int, 1, 1, self.out_c, 1, nb)
+            unp.append(ops.pack_job(self.bias.grad, bp, 1, self.bias.numel(), None, self.out_map, int(accumulate)))
+        return trans, unp
 
     def _versions(self):
         return (self.weight._version, self.weight.data_ptr(), None if self.bias is None else self.bias._version)
@@ -301,8 +348,11 @@ class DeconvAsLinear(ConvLayer):
 class Plan:
     """Traced schedule for one network instance and batch size."""
 
-    def __init__(self, device, training: bool = True, need_wgrad: bool = True, exact: bool = False):
+    def __init__(self, device, training: bool = True, need_wgrad: bool = True, exact: bool = False,
+                 defer_bias: bool = False):
         self.device = device
+        self.defer_bias = defer_bias  # record (layer, dY, ready index) instead of launching one bias-grad kernel per layer
+        self.bias_jobs: list = []
         self.exact = exact  # fp32-exact verification mode: every tensor-core product is split hi/lo (3 launches)
         self.training = training
         self.need_wgrad = need_wgrad
@@ -736,7 +786,10 @@ class Plan:
                     g = self.grad_act(outs[i])
                     if L.bias_view is not None:
                         g = Act(g.buf.view(g.n, *L.bias_view))
-                    self.bwd.append(lambda g=g, L=L: ops.bias_grad(g, L.db_int, True))
+                    if self.defer_bias:
+                        self.bias_jobs.append((L, g))
+                    else:
+                        self.bwd.append(lambda g=g, L=L: ops.bias_grad(g, L.db_int, True))
             for i in live:
                 self.bwd_marks[layers[i].name] = len(self.bwd)
         # residual branch: its gradient is d_pre itself; defer it as an addend of the next conv contribution

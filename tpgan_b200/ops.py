@@ -301,3 +301,56 @@ def softmax_ce(logits: Act, labels: torch.Tensor, dlogits: Optional[Act], coeff:
     dptr, dstride = (None, 0) if dlogits is None else (dlogits.view().ptr, dlogits.view().sn)
     _lib.check(_lib.load().tpgan_softmax_ce(lv.ptr, lv.sn, labels.data_ptr(), dptr, dstride, logits.n, logits.c,
                                             float(coeff), loss_sum.data_ptr(), _stream()), "softmax_ce")
+
+
+# ---------------------------------------------------------------------------------------------------- multi-tensor launches
+class JobTable:
+    """A device-resident array of job structs + the launch that consumes it (one launch for all layers)."""
+
+    def __init__(self, kind: str, jobs: list, device, unpack: bool = False):
+        self.kind, self.n, self.unpack = kind, len(jobs), unpack
+        self.blocks, self.max_row = 0, 1
+        if not jobs:
+            return
+        for j in jobs:
+            j.block_begin = self.blocks
+            if kind == "bias":
+                self.blocks += j.pix_blocks * j.cgroups
+            elif kind == "pack":
+                self.blocks += j.rows if unpack else j.rows_pad
+                self.max_row = max(self.max_row, j.row_len)
+            else:
+                self.blocks += j.taps * j.tiles_r * j.tiles_k
+        arr = (type(jobs[0]) * len(jobs))(*jobs)
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+    def run(self):
+        if self.n == 0:
+            return
+        lib = _lib.load()
+        if self.kind == "bias":
+            _lib.check(lib.tpgan_bias_grad_multi(self.table.data_ptr(), self.n, self.blocks, _stream()), "bias_grad_multi")
+        elif self.kind == "pack":
+            _lib.check(lib.tpgan_pack_multi(self.table.data_ptr(), self.n, self.blocks, self.max_row, int(self.unpack),
+                                            _stream()), "pack_multi")
+        else:
+            _lib.check(lib.tpgan_transpose_multi(self.table.data_ptr(), self.n, self.blocks, _stream()), "transpose_multi")
+
+
+def bias_job(g: Act, db: torch.Tensor) -> "_lib.BiasJob":
+    v = g.view()
+    assert v.sh == v.w * v.sw and v.sn == v.h * v.sh and v.sw % 4 == 0 and v.ptr % 16 == 0, "bias job needs a dense view"
+    npix = v.n * v.h * v.w
+    return _lib.BiasJob(v.ptr, db.data_ptr(), npix, v.sw, v.c, 0, max(1, min((npix + 31) // 32, 1184)), (v.c + 127) // 128)
+
+
+def pack_job(ref: torch.Tensor, packed: Packed, taps: int, row_len: int, row_map, k_map, flag: int) -> "_lib.PackJob":
+    p = ref.data_ptr()
+    return _lib.PackJob(p, p, packed.data.data_ptr(), _ptr(row_map), _ptr(k_map), row_len, taps, packed.rows, packed.k,
+                        packed.rows_pad, packed.k_pad, row_len, flag, 0)
+
+
+def transpose_job(src: Packed, dst: Packed) -> "_lib.TransposeJob":
+    assert src.taps == dst.taps and src.rows == dst.k and src.k == dst.rows
+    return _lib.TransposeJob(src.data.data_ptr(), dst.data.data_ptr(), src.taps, src.rows, src.k, src.rows_pad, src.k_pad,
+                             dst.rows_pad, dst.k_pad, 0, (src.k + 31) // 32, (src.rows + 31) // 32)

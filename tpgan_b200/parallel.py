@@ -65,6 +65,9 @@ class BucketReducer:
             acc += s
         self.layers = layers
         self.buckets = plan_buckets(sizes, ready, int(bucket_mb * 1024 * 1024 / 4))
+        from .train_step import LayerSet
+        # per bucket: the deferred bias gradients of its layers + the multi-tensor gradient export
+        self.sets = [LayerSet(layers[i0:i1], trainer.device, plan.bias_jobs) for (i0, i1, _, _) in self.buckets]
         self.ready = ready
         self.tail = (acc, flat.total - acc)  # parameters outside the traced layers (none for G): reduced with the last bucket
         self.comm = torch.cuda.Stream()
@@ -78,9 +81,8 @@ class BucketReducer:
             if last:
                 cnt = flat.total - off
 
-            def fn(i0=i0, i1=i1, off=off, cnt=cnt):
-                for L in self.layers[i0:i1]:
-                    L.export_grad(accumulate=False)
+            def fn(bi=bi, off=off, cnt=cnt):
+                self.sets[bi].export()
                 ev = torch.cuda.Event()
                 ev.record()
                 self.comm.wait_event(ev)

@@ -80,6 +80,43 @@ class FlatParams:
                           grad_scale)
 
 
+class LayerSet:
+    """Re-packing (after the optimizer) and gradient export (after backward) of a set of layers as multi-tensor launches:
+    one pack, one transpose and one unpack launch for all eligible layers, individual calls for the few special ones
+    (fc1's 128 KB rows, the deconv-as-GEMM layer)."""
+
+    def __init__(self, layers: Sequence[ConvLayer], device, bias_jobs: Sequence = ()):
+        self.multi = [L for L in layers if L.multi_ok()]
+        self.single = [L for L in layers if not L.multi_ok()]
+        packs, ptr, utr, unp = [], [], [], []
+        for L in self.multi:
+            a, b = L.pack_jobs()
+            packs += a
+            ptr += b
+            c, d = L.unpack_jobs(False)
+            utr += c
+            unp += d
+        self.pack_tab = ops.JobTable("pack", packs, device)
+        self.ptrans_tab = ops.JobTable("transpose", ptr, device)
+        self.utrans_tab = ops.JobTable("transpose", utr, device)
+        self.unpack_tab = ops.JobTable("pack", unp, device, unpack=True)
+        ids = {id(L) for L in layers}
+        self.bias_tab = ops.JobTable("bias", [ops.bias_job(g, L.db_int) for L, g in bias_jobs if id(L) in ids], device)
+
+    def repack(self):
+        self.pack_tab.run()
+        self.ptrans_tab.run()
+        for L in self.single:
+            L.repack()
+
+    def export(self):
+        self.bias_tab.run()
+        self.utrans_tab.run()
+        self.unpack_tab.run()
+        for L in self.single:
+            L.export_grad(accumulate=False)
+
+
 # ---------------------------------------------------------------------------------------------------------- CUDA graphs
 class Eager:
     """Marks a schedule entry that must run eagerly (collectives, host-visible side effects)."""
@@ -389,8 +426,10 @@ class TPGANTrainer:
         order = self._ready_order()
         self.flat_g = FlatParams(G, order)
         self.flat_d = FlatParams(D)
-        for L in self.plan.layers + self.critic.layers:
-            L.repack()
+        self.g_set = LayerSet(self.plan.layers, self.device, self.plan.bias_jobs)
+        self.d_set = LayerSet(self.critic.layers, self.device)
+        self.g_set.repack()
+        self.d_set.repack()
         self.reducer = None
         if world_size > 1:
             from .parallel import BucketReducer
@@ -407,7 +446,7 @@ class TPGANTrainer:
     # ---- generator plan
     def _build_g(self):
         G, B, dev = self.G, self.B, self.device
-        plan = Plan(dev, exact=self.exact)
+        plan = Plan(dev, exact=self.exact, defer_bias=True)
         self.plan = plan
         gp = G.global_pathway
         bufs = gp.alloc_concats(plan, B)
@@ -495,14 +534,14 @@ class TPGANTrainer:
         sch += [lambda: ops.view_copy(fake, _sl(x0, 0, B)), lambda: ops.view_copy(self.frontal, _sl(x0, B, 2 * B)),
                 lambda: ops.lerp(self.frontal, fake, self.inp["gp_alpha"], _sl(x0, 2 * B, 3 * B))]
         sch += crit.d_phase_list(float(w["weight_gradient_penalty"]))
-        sch.append(crit.export_grads)
+        sch.append(self.d_set.export)
         d_logits = self._d_logits
         sch.append(lambda: ops.view_copy(_sl(crit.logits, 0, 2 * B), Act(d_logits, 0, 1)))
         if self.world_size > 1:
             sch.append(Eager(lambda: self._allreduce(self.flat_d.grad)))
         if optimize:
             sch.append(lambda: self.flat_d.adam(self.lr, 1.0 / self.world_size))
-            sch.append(crit.repack)
+            sch.append(self.d_set.repack)
         # ---------------- G phase
         n128, n64, n32 = B * 3 * 128 * 128, B * 3 * 64 * 64, B * 3 * 32 * 32
         wp, ws, wt = w["weight_pixelwise"], w["weight_symmetry"], w["weight_total_varation"]
@@ -528,10 +567,10 @@ class TPGANTrainer:
             sch.append(Eager(self.reducer.finish))
         else:
             sch += self.plan.bwd
-            sch.append(lambda: [L.export_grad(accumulate=False) for L in self.plan.layers])
+            sch.append(self.g_set.export)
         if optimize:
             sch.append(lambda: self.flat_g.adam(self.lr, 1.0 / self.world_size))
-            sch.append(lambda: [L.repack() for L in self.plan.layers])
+            sch.append(self.g_set.repack)
         return sch
 
     def step(self, b: Dict[str, torch.Tensor], optimize: bool = True, read_metrics: bool = True):
