@@ -23,6 +23,7 @@ SHAPES = [
     ("enh64_208x208_k3", 208, 208, 3, 1, 1, 64, False),
     ("enh16_768x768_k3", 768, 768, 3, 1, 1, 16, False),
     ("conv5_206x64_k5", 206, 64, 5, 1, 2, 128, False),
+    ("conv00_3x64_k7", 3, 64, 7, 1, 3, 128, False),
     ("conv4rb_512x512_k3", 512, 512, 3, 1, 1, 8, False),
     ("add64_80x80_k5", 80, 80, 5, 1, 2, 64, False),
     ("conv5rb_64x64_k3", 64, 64, 3, 1, 1, 128, False),

@@ -384,9 +384,30 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   G.chunks = G.tiles_w * G.tiles_h * ceil_div(G.Nimg, G.bn);
   G.m_tiles = ceil_div(G.m_valid, 128);
   const int nch_total = ceil_div(G.n_valid, 32);
-  G.n_tiles = ceil_div(nch_total, 8);
-  G.block_n = ceil_div(nch_total, G.n_tiles) * 32;
   G.ntaps = k * k;
+  static const bool no_pack = getenv("TPGAN_WGRAD_NOPACK") != nullptr;
+  static const int tap_pack_max = getenv("TPGAN_WGRAD_TAPPACK") ? atoi(getenv("TPGAN_WGRAD_TAPPACK")) : 1;
+  if (nch_total <= tap_pack_max && G.ntaps > 1 && !no_pack) {
+    // narrow shifted tensor (one 32-channel chunk: the 3-channel image layers): several taps side by side in N, all
+    // sharing the loads of P (measured: pays only for a single chunk; wider tensors become L2-bound)
+    G.ncpt = nch_total;
+    G.tpu = std::min(G.ntaps, 8 / nch_total);
+    G.n_tiles = 1;
+    G.block_n = G.tpu * G.ncpt * 32;
+    G.mpu = 1;
+  } else {
+    G.tpu = 1;
+    G.n_tiles = ceil_div(nch_total, 8);
+    G.block_n = ceil_div(nch_total, G.n_tiles) * 32;
+    G.ncpt = G.block_n / 32;
+    // several M tiles per unit (one accumulator each), all sharing the loads of Q - when the reduction is long enough
+    // (>= 4096 pixels per image batch) to amortise the then single-buffered epilogue
+    const long long npix = (long long)G.Hp * G.Wp * G.Nimg;
+    G.mpu = (no_pack || npix < 32768) ? 1 : std::max(1, std::min(G.m_tiles, 512 / G.block_n));
+  }
+  G.tap_groups = ceil_div(G.ntaps, G.tpu);
+  G.mt_groups = ceil_div(G.m_tiles, G.mpu);
+  G.nbuf = (G.mpu * G.block_n <= 256) ? 2 : 1;
   int nt = 0;
   for (int r = 0; r < k; ++r)
     for (int c = 0; c < k; ++c) {
@@ -413,17 +434,31 @@ static int choose_wgrad_px(const tpgan_wgrad_args* groups, int ngroups) {
   if (const char* ev = getenv("TPGAN_WGRAD_PX")) return std::max(8, std::min(128, atoi(ev)));
   const int budget = g_dev.max_smem - 1024 - 256;
   int chunks = 0;
+  static const bool no_pack = getenv("TPGAN_WGRAD_NOPACK") != nullptr;
   for (int i = 0; i < ngroups; ++i) {
     const bool is_conv = groups[i].kind == TPGAN_CONV_FWD;
     const int pc = is_conv ? groups[i].dy.c : groups[i].x.c, qc = is_conv ? groups[i].x.c : groups[i].dy.c;
-    const int mch = std::min(4, ceil_div(pc, 32));
+    const int ntaps = groups[i].kh * groups[i].kw;
+    const int m_tiles = ceil_div(pc, 128);
     const int nch_total = ceil_div(qc, 32);
-    const int nch = ceil_div(nch_total, ceil_div(nch_total, 8));
-    chunks = std::max(chunks, mch + nch);
+    int a_ch, b_ch;
+    static const int tap_pack_max = getenv("TPGAN_WGRAD_TAPPACK") ? atoi(getenv("TPGAN_WGRAD_TAPPACK")) : 1;
+    const tpgan_view& Pt = is_conv ? groups[i].dy : groups[i].x;
+    const long long npix = (long long)Pt.h * Pt.w * Pt.n;
+    if (nch_total <= tap_pack_max && ntaps > 1 && !no_pack) {
+      a_ch = std::min(4, ceil_div(pc, 32));
+      b_ch = std::min(ntaps, 8 / nch_total) * nch_total;
+    } else {
+      b_ch = ceil_div(nch_total, ceil_div(nch_total, 8));
+      const int mpu = (no_pack || npix < 32768) ? 1 : std::max(1, std::min(m_tiles, 512 / (b_ch * 32)));
+      a_ch = std::min(4 * mpu, ceil_div(pc, 32));
+    }
+    chunks = std::max(chunks, a_ch + b_ch);
   }
   for (int px : {128, 64})
     if (budget / (chunks * px * 128) >= 4) return px;
-  return 32;
+  if (budget / (chunks * 32 * 128) >= 3) return 32;
+  return 16;
 }
 
 template <class Params>
@@ -431,9 +466,9 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
   int amax = 0, bmax = 0, base_units = 0;
   for (int i = 0; i < P.ngroups; ++i) {
     WgradGroup& G = P.g[i];
-    amax = std::max(amax, 4 * G.kp * 128);
+    amax = std::max(amax, 4 * G.mpu * G.kp * 128);
     bmax = std::max(bmax, (G.block_n / 32) * G.kp * 128);
-    base_units += G.ntaps * G.m_tiles * G.n_tiles;
+    base_units += G.tap_groups * G.mt_groups * G.n_tiles;
   }
   // split the pixel reduction so that ~2 waves of units cover the SMs
   int units = 0;
@@ -444,10 +479,12 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
     G.chunks_per_split = ceil_div(G.chunks, ks);
     G.ksplits = ceil_div(G.chunks, G.chunks_per_split);
     G.unit_begin = units;
-    G.unit_count = G.ntaps * G.m_tiles * G.n_tiles * G.ksplits;
+    G.unit_count = G.tap_groups * G.mt_groups * G.n_tiles * G.ksplits;
     units += G.unit_count;
   }
   P.total_units = units;
+  P.nbuf = 2;
+  for (int i = 0; i < P.ngroups; ++i) P.nbuf = std::min(P.nbuf, P.g[i].nbuf);
   P.a_stage_bytes = amax;
   P.b_stage_bytes = bmax;
   const int stage_bytes = amax + bmax;
@@ -522,7 +559,7 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
     bool same = true;
     for (int i = 1; i < ngroups; ++i)
       same = same && P.g[i].bw == P.g[0].bw && P.g[i].bh == P.g[0].bh && P.g[i].bn == P.g[0].bn &&
-             P.g[i].block_n == P.g[0].block_n;
+             P.g[i].block_n == P.g[0].block_n && P.g[i].mpu == P.g[0].mpu && P.g[i].tpu == P.g[0].tpu;
     if (!same) {
       for (int i = 0; i < ngroups; ++i) {
         rc = tpgan_conv2d_wgrad(groups + i, 1, stream);

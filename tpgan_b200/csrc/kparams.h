@@ -98,10 +98,15 @@ struct WgradGroup {
   int Hp, Wp, Nimg;
   int bw, bh, bn, kp;            // kp = K rows per stage (pixels rounded up to 8)
   int tiles_w, tiles_h, chunks;  // pixel boxes: tiles_w * tiles_h * ceil(Nimg/bn)
-  int m_tiles, n_tiles, block_n; // M tile = 128 P-channels, N tile = block_n Q-channels
+  int m_tiles, n_tiles, block_n; // M tile = 128 P-channels, N tile = block_n columns
+  // A unit covers `mpu` consecutive M tiles (one accumulator each; they share every Q load) and `tpu` consecutive taps
+  // (their Q chunks sit side by side in the N dimension; they share every P load).  mpu > 1 and tpu > 1 are exclusive.
+  int mpu, mt_groups;            // M tiles per unit, ceil(m_tiles / mpu)
+  int tpu, tap_groups, ncpt;     // taps per unit, ceil(ntaps / tpu), 32-channel Q chunks per tap (tpu > 1: block_n = tpu*ncpt*32)
+  int nbuf;                      // TMEM accumulator buffers (2 when mpu * block_n <= 256)
   int ksplits, chunks_per_split;
   int ntaps;
-  int unit_begin, unit_count;    // units = taps * m_tiles * n_tiles * ksplits
+  int unit_begin, unit_count;    // units = tap_groups * mt_groups * n_tiles * ksplits
   TapDesc taps[kMaxTaps];
   float* dw;                     // [taps+1][rows_pad][k_pad]
   int rows_pad, k_pad;
@@ -115,6 +120,7 @@ struct WgradParams {
   int total_units;
   int stages;
   int a_stage_bytes, b_stage_bytes;
+  int nbuf;
   WgradGroup g[kMaxGroups];
 };
 struct WgradParams1 {
@@ -122,6 +128,7 @@ struct WgradParams1 {
   int total_units;
   int stages;
   int a_stage_bytes, b_stage_bytes;
+  int nbuf;
   WgradGroup g[1];
 };
 

@@ -21,7 +21,7 @@ constexpr int kWTmemCols = 512;
 constexpr int kWAccCols = 256;
 
 struct UnitCoord {
-  int gi, tap, mt, nt, ks;
+  int gi, tg, mg, nt, ks;
 };
 
 template <class Params>
@@ -35,12 +35,12 @@ __device__ __forceinline__ UnitCoord decode_unit(const Params& P, int unit) {
   const WgradGroup& G = P.g[gi];
   int local = unit - G.unit_begin;
   u.gi = gi;
-  u.tap = local % G.ntaps;
-  local /= G.ntaps;
+  u.tg = local % G.tap_groups;
+  local /= G.tap_groups;
   u.nt = local % G.n_tiles;
   local /= G.n_tiles;
-  u.mt = local % G.m_tiles;
-  u.ks = local / G.m_tiles;
+  u.mg = local % G.mt_groups;
+  u.ks = local / G.mt_groups;
   return u;
 }
 
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   // Zero the whole ring once: K rows beyond a box (pixel count not a multiple of 8) and channel chunks that are
-  // never loaded must read as zero for the lifetime of the kernel.
+  // never loaded must read as finite values for the lifetime of the kernel.
   {
     uint4* p = reinterpret_cast<uint4*>(smem);
     const int n16 = (int)((size_t)S * stage_bytes / 16);
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   AbortCtl ac{&abort_flag, status};
+  const int nbuf = P.nbuf;   // accumulator buffers (uniform over the groups of a launch)
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
@@ -102,28 +103,46 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
       for (int unit = blockIdx.x; ok && unit < P.total_units; unit += gridDim.x) {
         const UnitCoord u = decode_unit(P, unit);
         const WgradGroup& G = P.g[u.gi];
-        const TapDesc tap = G.taps[u.tap];
-        const CUtensorMap* qm = &G.qmap[tap.plane];
         const CUtensorMap* pm = &G.pmap;
-        const int mch = min(4, (G.m_valid - u.mt * 128 + 31) / 32);
-        const int nch = min(G.block_n / 32, (G.n_valid - u.nt * G.block_n + 31) / 32);
-        const uint32_t tx = (uint32_t)(G.bw * G.bh * G.bn) * 128u * (uint32_t)(mch + nch);
+        const int mt0 = u.mg * G.mpu;
+        const int pc0 = mt0 * 128;
+        const int mch = min(4 * G.mpu, (G.m_valid - pc0 + 31) / 32);        // P chunks of this unit (all its M tiles)
+        const int tap0 = u.tg * G.tpu;
+        const int ntap = min(G.tpu, G.ntaps - tap0);
+        const int qc0 = (G.tpu > 1) ? 0 : u.nt * G.block_n;
+        const int ncpt = (G.tpu > 1) ? G.ncpt : min(G.block_n / 32, (G.n_valid - qc0 + 31) / 32);
+        const uint32_t box_bytes = (uint32_t)(G.bw * G.bh * G.bn) * 128u;
+        const uint32_t tx = box_bytes * (uint32_t)(mch + ntap * ncpt);
         const uint32_t chunk_stride = (uint32_t)G.kp * 128u;
         const int c_begin = u.ks * G.chunks_per_split;
         const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
         const int tiles_w = G.tiles_w, tiles_h = G.tiles_h, bw = G.bw, bh = G.bh, bn = G.bn;
-        const int pc0 = u.mt * 128, qc0 = u.nt * G.block_n, tdx = tap.dx, tdy = tap.dy;
-        // running pixel-box coordinates (wb fastest, then hb, then nb)
+        const TapDesc* taps = &G.taps[tap0];
+        const bool single_tap = (G.tpu == 1);
+        const TapDesc tapA = taps[0];
+        const CUtensorMap* qm0 = &G.qmap[tapA.plane];
+        const int tdx0 = tapA.dx, tdy0 = tapA.dy;
         int wb = c_begin % tiles_w, r = c_begin / tiles_w;
         int hb = r % tiles_h, nb = r / tiles_h;
         for (int c = c_begin; c < c_end; ++c) {
           const int x0 = wb * bw, y0 = hb * bh, n0 = nb * bn;
           if (!mbar_wait_a(eb, phase ^ 1u, ac, 11)) { ok = false; break; }
-          const uint32_t sb = sa + (uint32_t)P.a_stage_bytes;
+          uint32_t sb = sa + (uint32_t)P.a_stage_bytes;
           mbar_arrive_expect_tx_a(fb, tx);
           for (int i = 0; i < mch; ++i) tma_load_4d_a(sa + (uint32_t)i * chunk_stride, pm, fb, pc0 + i * 32, x0, y0, n0);
-          for (int i = 0; i < nch; ++i)
-            tma_load_4d_a(sb + (uint32_t)i * chunk_stride, qm, fb, qc0 + i * 32, x0 + tdx, y0 + tdy, n0);
+          if (single_tap) {
+            for (int i = 0; i < ncpt; ++i)
+              tma_load_4d_a(sb + (uint32_t)i * chunk_stride, qm0, fb, qc0 + i * 32, x0 + tdx0, y0 + tdy0, n0);
+          } else {
+            for (int t = 0; t < ntap; ++t) {
+              const TapDesc tap = taps[t];
+              const CUtensorMap* qm = &G.qmap[tap.plane];
+              for (int i = 0; i < ncpt; ++i) {
+                tma_load_4d_a(sb, qm, fb, qc0 + i * 32, x0 + tap.dx, y0 + tap.dy, n0);
+                sb += chunk_stride;
+              }
+            }
+          }
           sa += stage_bytes; fb += 8; eb += 8;
           if (++stage == S) { stage = 0; phase ^= 1u; sa = smem_base; fb = full0; eb = empty0; }
           if (++wb == tiles_w) { wb = 0; if (++hb == tiles_h) { hb = 0; ++nb; } }
@@ -149,23 +168,36 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
         tc_fence_after();
         const uint32_t idesc = make_idesc_tf32(128, G.block_n, 1, 1);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kWAccCols);
-        const uint32_t lbo_field = ((((uint32_t)G.kp * 128u) >> 4) & 0x3FFFu) << 16;
+        const uint32_t chunk16 = ((uint32_t)G.kp * 128u) >> 4;
+        const uint32_t lbo_field = (chunk16 & 0x3FFFu) << 16;
         const int kgroups = G.kp / 8;
+        const int nm = min(G.mpu, G.m_tiles - u.mg * G.mpu);   // M tiles (accumulators) of this unit
         const int c_begin = u.ks * G.chunks_per_split;
         const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
         uint32_t acc = 0;
         for (int c = c_begin; c < c_end; ++c) {
           if (!mbar_wait_a(fb, phase, ac, 13)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t a_lo = sbase16 | lbo_field, b_lo = (sbase16 + areg16) | lbo_field;
-          if (kgroups == 4) {
+          const uint32_t b_lo = (sbase16 + areg16) | lbo_field;
+          if (nm == 1 && kgroups == 8) {
+            const uint32_t a_lo = sbase16 | lbo_field;
             mma_tf32_ss(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
-            mma_tf32_ss(d_tmem, desc_join(a_lo + 64, dhi), desc_join(b_lo + 64, dhi), idesc, 1);
-            mma_tf32_ss(d_tmem, desc_join(a_lo + 128, dhi), desc_join(b_lo + 128, dhi), idesc, 1);
-            mma_tf32_ss(d_tmem, desc_join(a_lo + 192, dhi), desc_join(b_lo + 192, dhi), idesc, 1);
-          } else {
-            for (int k = 0; k < kgroups; ++k)
-              mma_tf32_ss(d_tmem, desc_join(a_lo + 64 * k, dhi), desc_join(b_lo + 64 * k, dhi), idesc, k ? 1u : acc);
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+              mma_tf32_ss(d_tmem, desc_join(a_lo + 64 * k, dhi), desc_join(b_lo + 64 * k, dhi), idesc, 1);
+          } else
+          for (int mi = 0; mi < nm; ++mi) {
+            const uint32_t a_lo = (sbase16 + (uint32_t)mi * 4u * chunk16) | lbo_field;
+            const uint32_t d = d_tmem + (uint32_t)(mi * G.block_n);
+            if (kgroups == 4) {
+              mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
+              mma_tf32_ss(d, desc_join(a_lo + 64, dhi), desc_join(b_lo + 64, dhi), idesc, 1);
+              mma_tf32_ss(d, desc_join(a_lo + 128, dhi), desc_join(b_lo + 128, dhi), idesc, 1);
+              mma_tf32_ss(d, desc_join(a_lo + 192, dhi), desc_join(b_lo + 192, dhi), idesc, 1);
+            } else {
+              for (int k = 0; k < kgroups; ++k)
+                mma_tf32_ss(d, desc_join(a_lo + 64 * k, dhi), desc_join(b_lo + 64 * k, dhi), idesc, k ? 1u : acc);
+            }
           }
           acc = 1;
           tc_commit_a(eb);
@@ -174,12 +206,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
         }
         if (!ok) break;
         tc_commit(&tfull_bar[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
+        if (++as == nbuf) { as = 0; aphase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: TMEM -> red.add into dW
+    // ------------------------------------------------------------------ epilogue: TMEM -> dW (stores or vector reds)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int as = 0;
@@ -189,20 +220,25 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
       const WgradGroup& G = P.g[u.gi];
       if (!mbar_wait(&tfull_bar[as], aphase, ac, 14)) break;
       tc_fence_after();
-      const int m = u.mt * 128 + row;
-      const bool mvalid = m < G.m_valid;
-      const TapDesc tap = G.taps[u.tap];
-      float* dw = G.dw + (size_t)tap.wtap * G.rows_pad * G.k_pad;
-      const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols) + ((uint32_t)(q * 32) << 16);
       const int c_begin = u.ks * G.chunks_per_split;
       const bool nonempty = c_begin < G.chunks;
       const bool single = (G.ksplits == 1) && (G.accumulate == 0);  // sole writer of this dW tile: plain stores
-      for (int c0 = 0; c0 < G.block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (mvalid && nonempty) {
-          const int n0 = u.nt * G.block_n + c0;
+      const int nm = min(G.mpu, G.m_tiles - u.mg * G.mpu);
+      const int tap0 = u.tg * G.tpu;
+      const int cols_per_tap = (G.tpu > 1) ? G.ncpt * 32 : G.block_n;
+      for (int mi = 0; mi < nm; ++mi) {
+        const int m = (u.mg * G.mpu + mi) * 128 + row;
+        const bool mvalid = m < G.m_valid;
+        const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + mi * G.block_n) + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < G.block_n; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const int ti = c0 / cols_per_tap;                 // cols_per_tap is a multiple of 32 (or block_n itself)
+          if (!(mvalid && nonempty) || tap0 + ti >= G.ntaps) continue;
+          const TapDesc tap = G.taps[tap0 + ti];
+          float* dw = G.dw + (size_t)tap.wtap * G.rows_pad * G.k_pad;
+          const int n0 = ((G.tpu > 1) ? 0 : u.nt * G.block_n) + (c0 - ti * cols_per_tap);
           if (G.transpose_out) {   // dw[n][m]: lanes hold consecutive m -> every red is a coalesced 128 B row segment
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -238,8 +274,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
+      if (++as == nbuf) { as = 0; aphase ^= 1u; }
     }
   }
 
