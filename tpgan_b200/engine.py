@@ -475,9 +475,15 @@ class Plan:
         full = lambda sp: dict(bias=sp.get("bias"), add1=sp.get("add1"), add2=sp.get("add2"), mask=sp.get("mask"),
                                slopes=sp.get("slopes"), slope=sp.get("slope", 0.0), epilogue=sp.get("epilogue", EPI_LINEAR))
         if not self.exact:
-            lst.append(self._conv_launch([mk(sp, sp["x"], sp["out"], sp["L"].wd if sp["dgrad"] else sp["L"].wf, **full(sp))
-                                          for sp in specs], fl, ",".join(sp["L"].name for sp in specs) +
-                                         (":dgrad" if specs[0]["dgrad"] else ":fwd")))
+            run = self._conv_launch([mk(sp, sp["x"], sp["out"], sp["L"].wd if sp["dgrad"] else sp["L"].wf, **full(sp))
+                                     for sp in specs], fl, ",".join(sp["L"].name for sp in specs) +
+                                    (":dgrad" if specs[0]["dgrad"] else ":fwd"))
+            sp0, L0 = specs[0], specs[0]["L"]
+            pk = L0.wd if sp0["dgrad"] else L0.wf
+            if (len(specs) == 1 and not L0.transposed and L0.stride == 1 and 2 * L0.pad == L0.k - 1 and L0.k >= 3
+                    and sp0["x"].w == 128 and sp0["out"].w == 128 and pk.rows_pad <= 256):
+                run.kind = "rowconv"   # the library routes these to rowconv_kernel (api.cu: try_rowconv)
+            lst.append(run)
             return
         a1, a2, a3 = [], [], []
         for sp in specs:
