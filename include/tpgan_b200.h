@@ -176,6 +176,13 @@ TPGAN_API int tpgan_local_fuse(tpgan_view left_eye, tpgan_view right_eye, tpgan_
 TPGAN_API int tpgan_local_fuse_backward(tpgan_view dout, const uint8_t* argmax, tpgan_view d_left_eye, tpgan_view d_right_eye,
                               tpgan_view d_nose, tpgan_view d_mouth, int32_t accumulate, void* stream);
 
+/* Identity network (restated ResNet18-128, ResNet.py:28-55): nn.MaxPool2d(3,2,1) (:33) with the window position of the
+ * first maximum recorded in argmax (uint8 [N][Ho][Wo][C]) and its backward; nn.AdaptiveAvgPool2d((1,1)) (:45). */
+TPGAN_API int tpgan_maxpool3s2(tpgan_view x, tpgan_view y, uint8_t* argmax, void* stream);
+TPGAN_API int tpgan_maxpool3s2_backward(tpgan_view dy, const uint8_t* argmax, tpgan_view dx, int32_t accumulate, void* stream);
+TPGAN_API int tpgan_avgpool(tpgan_view x, tpgan_view y, void* stream);
+TPGAN_API int tpgan_avgpool_backward(tpgan_view dy, tpgan_view dx, int32_t accumulate, void* stream);
+
 /* Fused image losses of the oracle step (config.py:71-82 weights): in one pass over fake and the
  * 128/64/32 targets (TrainDataset keys img_frontal/img64_frontal/img32_frontal, DataAndDataset.py:206-226)
  * computes pixel-L1 at 128/64/32 (fake average-pooled), symmetry-L1 at the same three scales and total variation, and

@@ -1,0 +1,155 @@
+"""Identity / feature network: a ResNet18 for 128x128 inputs with the interface the reference INTENDS
+(ResNet.py:5-119: conv1 7x7 s2 p3 -> 64 + BN + ReLU (:30-31), MaxPool2d(3,2,1) (:33), stages [64,128,256,512] x [2,2,2,2]
+residual blocks (:28-29,38-42), AdaptiveAvgPool2d((1,1)) (:45), optional FC0 512 -> feature_layer_dim_before_FC (+BN1d)
+(:48-49), Dropout (:52), FC -> classes (:55), forward(x, use_dropout) -> (out, out_FC0) (:80-119)).
+
+The reference's own class cannot be constructed (conv() has no `bias` kwarg, the block factory is called
+with stride in the kernel_size slot, only 3 of 4 stages are built and all with stride 1, `resnet18()` is mis-indented), so
+this is a RESTATEMENT, not a drop-in for a working class: the canonical ResNet18 wiring (stage strides 1,2,2,2, projection
+shortcut where shape changes) with the reference's constructor/forward signatures.  Parity for it is oracle-defined
+(oracle/identity_port.py), stated in DESIGN.md.
+
+Execution: in eval mode (the only mode the TP-GAN step uses it in: a FROZEN identity network) BatchNorm is folded into the
+preceding conv / linear and the whole forward (and the input gradient) runs as a traced plan on the tcgen05 kernels.
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import ConvLayer, Plan, T
+from .ModificationLayer import conv, linear
+
+
+class BasicBlock(nn.Module):
+    """act( BN(conv3x3(act(BN(conv3x3_s(x))))) + shortcut(x) ); shortcut = 1x1 stride-s conv + BN where the shape changes."""
+
+    def __init__(self, in_channels, out_channels, stride=1, activation=nn.ReLU(inplace=True), use_batchnorm=True):
+        super().__init__()
+        self.out_channels = out_channels
+        self.conv_a = conv(in_channels, out_channels, 3, stride, 1, "kaiming", activation, use_batchnorm)
+        self.conv_b = conv(out_channels, out_channels, 3, 1, 1, "kaiming", None, use_batchnorm)
+        self.shortcut = conv(in_channels, out_channels, 1, stride, 0, "kaiming", None, use_batchnorm) \
+            if (stride != 1 or in_channels != out_channels) else nn.Sequential()
+        self.activation = activation
+
+    def forward(self, x):
+        return self.activation(self.conv_b(self.conv_a(x)) + self.shortcut(x))
+
+
+def _fold(seq: nn.Sequential):
+    """conv()/linear() stack [Conv2d|Linear, BatchNorm?, act?] -> (weight, bias, has_relu) with eval-mode BN folded in."""
+    lin, bn, relu = None, None, False
+    for m in seq:
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            lin = m
+        elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+            bn = m
+        elif isinstance(m, nn.ReLU):
+            relu = True
+        else:
+            raise NotImplementedError(type(m).__name__)
+    w = lin.weight.detach().float()
+    b = lin.bias.detach().float() if lin.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+        w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+        b = (b - bn.running_mean) * scale + bn.bias.detach()
+    return lin, w.contiguous(), b.contiguous(), relu
+
+
+class ResNet18(nn.Module):
+    def __init__(self, residualBlock=BasicBlock, num_of_output_classes=1000, use_batchnorm=True,
+                 feature_layer_dim_before_FC=None, activation=nn.ReLU(inplace=True), dropout_rate=0.0):
+        super().__init__()
+        self.use_batchnorm = use_batchnorm
+        self.activation = activation
+        self.feature_layer_dim_before_FC = feature_layer_dim_before_FC
+        num_features, num_sections, strides = [64, 128, 256, 512], [2, 2, 2, 2], [1, 2, 2, 2]
+        self.conv1 = conv(3, num_features[0], 7, 2, 3, "kaiming", activation, use_batchnorm)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        sections, cin = [], num_features[0]
+        for cout, nblk, st in zip(num_features, num_sections, strides):
+            sections.append(self._build_blocks(residualBlock, cin, cout, st, nblk))
+            cin = cout
+        self.sections = nn.Sequential(*sections)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        if feature_layer_dim_before_FC is not None:
+            self.FC0 = linear(num_features[-1], feature_layer_dim_before_FC, use_batchnorm=use_batchnorm)
+        self.dropout = nn.Dropout(dropout_rate)
+        fc_in = feature_layer_dim_before_FC if feature_layer_dim_before_FC is not None else num_features[-1]
+        self.FC = linear(fc_in, num_of_output_classes, use_batchnorm=False)
+
+    def _build_blocks(self, residualBlock, in_channels, out_channels, stride, num_of_residual_block):
+        layers = []
+        for i in range(num_of_residual_block):
+            layers.append(residualBlock(in_channels if i == 0 else out_channels, out_channels, stride if i == 0 else 1,
+                                        activation=copy.deepcopy(self.activation), use_batchnorm=self.use_batchnorm))
+        return nn.Sequential(*layers)
+
+    # ---- traced execution (eval mode, BN folded)
+    def _folded_layers(self, device):
+        """Builds (once per call - weights are frozen) the ConvLayers of the folded network."""
+        L = {}
+
+        def mk(name, seq, k, s, p, w_shape=None):
+            lin, w, b, relu = _fold(seq)
+            w4 = w if w.dim() == 4 else w.view(w.shape[0], w.shape[1], 1, 1)
+            L[name] = (ConvLayer(w4.to(device), b.to(device), False, k, s, p, name), relu)
+        mk("conv1", self.conv1, 7, 2, 3)
+        for si, sec in enumerate(self.sections):
+            for bi, blk in enumerate(sec):
+                st = blk.conv_a[0].stride[0]
+                mk(f"sections.{si}.{bi}.conv_a", blk.conv_a, 3, st, 1)
+                mk(f"sections.{si}.{bi}.conv_b", blk.conv_b, 3, 1, 1)
+                if len(blk.shortcut):
+                    mk(f"sections.{si}.{bi}.shortcut", blk.shortcut, 1, st, 0)
+        if hasattr(self, "FC0"):
+            mk("FC0", self.FC0, 1, 1, 0)
+        mk("FC", self.FC, 1, 1, 0)
+        return L
+
+    def trace(self, plan: Plan, x: T, with_logits: bool = True):
+        """x: (N,128,128,3) NHWC -> (pooled 512 feature T, FC0 feature T or None, logits T or None)."""
+        assert not self.training, "the traced identity network is eval-only (BatchNorm folded with running statistics)"
+        L = self._folded_layers(x.act.buf.device)
+        self._traced_layers = L   # keeps the folded parameters alive
+
+        def cv(name, t, residual=None, relu=None):
+            layer, r = L[name]
+            r = r if relu is None else relu
+            return plan.conv([layer], [t], 0.0 if r else None, residuals=None if residual is None else [residual])[0]
+        h = cv("conv1", x)
+        h = plan.maxpool3s2(h)
+        for si, sec in enumerate(self.sections):
+            for bi, blk in enumerate(sec):
+                pre = f"sections.{si}.{bi}"
+                a = cv(pre + ".conv_a", h)
+                sc = cv(pre + ".shortcut", h) if len(blk.shortcut) else h
+                h = cv(pre + ".conv_b", a, residual=sc, relu=True)
+        pooled = plan.avgpool(h)
+        fc0 = cv("FC0", pooled) if hasattr(self, "FC0") else None
+        logits = cv("FC", fc0 if fc0 is not None else pooled) if with_logits else None
+        return pooled, fc0, logits
+
+    def forward(self, x, use_dropout=False):
+        if not x.is_cuda:
+            raise RuntimeError("tpgan_b200 modules run on CUDA tensors only (there is no CPU fallback)")
+        if self.training:
+            raise NotImplementedError("ResNet18 runs as a frozen (eval-mode) identity network on the TP-GAN hot path; "
+                                      "training it (batch-statistics BatchNorm) is outside the path (SURVEY.md 8)")
+        if use_dropout and self.dropout.p > 0:
+            raise NotImplementedError("dropout is a training-time option")
+        n = x.shape[0]
+        plan = Plan(x.device, training=False, need_wgrad=False)
+        t = plan.new(n, x.shape[2], x.shape[3], 3, name="in", requires_grad=False)
+        pooled, fc0, logits = self.trace(plan, t)
+        t.act.from_nchw(x.detach().float(), round_tf32=True)
+        plan.run_forward()
+        out = logits.act.to_nchw().reshape(n, -1)
+        out_fc0 = fc0.act.to_nchw().reshape(n, -1) if fc0 is not None else None
+        return out, out_fc0

@@ -78,6 +78,10 @@ SYMBOLS = {
     "tpgan_patch_crop": (C.c_int, [View, _VP, View, View, View, View, _VP, _F, _VP]),
     "tpgan_local_fuse": (C.c_int, [View, View, View, View, View, _VP, _VP]),
     "tpgan_local_fuse_backward": (C.c_int, [View, _VP, View, View, View, View, _I32, _VP]),
+    "tpgan_maxpool3s2": (C.c_int, [View, View, _VP, _VP]),
+    "tpgan_maxpool3s2_backward": (C.c_int, [View, _VP, View, _I32, _VP]),
+    "tpgan_avgpool": (C.c_int, [View, View, _VP]),
+    "tpgan_avgpool_backward": (C.c_int, [View, View, _I32, _VP]),
     "tpgan_image_losses": (C.c_int, [View, View, View, View, View, _VP, _VP, _VP]),
     "tpgan_l1_loss": (C.c_int, [View, View, View, _F, _VP, _VP]),
     "tpgan_maxout2": (C.c_int, [_VP, _VP, _I32, _I32, _VP]),

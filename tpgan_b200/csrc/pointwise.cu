@@ -838,6 +838,89 @@ __global__ void transpose_multi_kernel(const tpgan_transpose_job* __restrict__ j
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ pooling (identity net)
+// nn.MaxPool2d(3, 2, 1) (ResNet.py:33): out[oy][ox] = max over the 3x3 window at (2*oy-1, 2*ox-1); the window position of
+// the first maximum (row-major scan, strict >, as ATen) is kept in `arg` for the backward pass.
+__global__ void maxpool3s2_kernel(V x, V y, uint8_t* __restrict__ arg) {
+  const long long total = (long long)y.n * y.h * y.w * y.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % y.c);
+    long long r = i / y.c;
+    int ox = (int)(r % y.w);
+    r /= y.w;
+    int oy = (int)(r % y.h);
+    int n = (int)(r / y.h);
+    float best = -INFINITY;
+    int bi = 0;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int iy = 2 * oy - 1 + dy, ix = 2 * ox - 1 + dx;
+        if (iy >= 0 && iy < x.h && ix >= 0 && ix < x.w) {
+          const float v = x.p[voff(x, n, iy, ix) + c];
+          if (bi == 0 || v > best) { best = v; bi = dy * 3 + dx + 1; }
+        }
+      }
+    y.p[voff(y, n, oy, ox) + c] = best;
+    if (arg) arg[i] = (uint8_t)(bi - 1);
+  }
+}
+// gather form: input pixel (iy, ix) collects dy of the (at most 2x2) windows whose recorded maximum is this pixel
+__global__ void maxpool3s2_backward_kernel(V dy, const uint8_t* __restrict__ arg, V dx, int accumulate) {
+  const long long total = (long long)dx.n * dx.h * dx.w * dx.c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dx.c);
+    long long r = i / dx.c;
+    int ix = (int)(r % dx.w);
+    r /= dx.w;
+    int iy = (int)(r % dx.h);
+    int n = (int)(r / dx.h);
+    float g = 0.f;
+    // windows covering iy: oy with 2*oy-1 <= iy <= 2*oy+1  <=>  oy in [ceil((iy-1)/2), floor((iy+1)/2)]
+    for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= dy.h) continue;
+      const int wy = iy - (2 * oy - 1);
+      if (wy < 0 || wy > 2) continue;
+      for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= dy.w) continue;
+        const int wx = ix - (2 * ox - 1);
+        if (wx < 0 || wx > 2) continue;
+        const long long oi = (((long long)n * dy.h + oy) * dy.w + ox) * dy.c + c;
+        if (arg[oi] == wy * 3 + wx) g += dy.p[voff(dy, n, oy, ox) + c];
+      }
+    }
+    float* d = dx.p + voff(dx, n, iy, ix) + c;
+    *d = accumulate ? (*d + g) : g;
+  }
+}
+// nn.AdaptiveAvgPool2d((1,1)) (ResNet.py:45): one warp per (n, 32-channel group)
+__global__ void avgpool_kernel(V x, V y) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= x.c) return;
+  float s = 0.f;
+  for (int iy = 0; iy < x.h; ++iy)
+    for (int ix = 0; ix < x.w; ++ix) s += x.p[voff(x, n, iy, ix) + c];
+  y.p[voff(y, n, 0, 0) + c] = s / (float)(x.h * x.w);
+}
+__global__ void avgpool_backward_kernel(V dy, V dx, int accumulate) {
+  const long long total = (long long)dx.n * dx.h * dx.w * dx.c;
+  const float inv = 1.f / (float)(dx.h * dx.w);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dx.c);
+    long long r = i / dx.c;
+    int ix = (int)(r % dx.w);
+    r /= dx.w;
+    int iy = (int)(r % dx.h);
+    int n = (int)(r / dx.h);
+    const float g = dy.p[voff(dy, n, 0, 0) + c] * inv;
+    float* d = dx.p + voff(dx, n, iy, ix) + c;
+    *d = accumulate ? (*d + g) : g;
+  }
+}
+
 static bool same_geom(const tpgan_view& a, const tpgan_view& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
@@ -1165,6 +1248,35 @@ int tpgan_transpose_multi(const tpgan_transpose_job* jobs_dev, int32_t njobs, in
   if (!jobs_dev || njobs < 1 || total_blocks < 1) return set_error(TPGAN_ERR_INVALID, "transpose_multi: bad args");
   transpose_multi_kernel<<<total_blocks, dim3(32, 8), 0, ST>>>(jobs_dev, njobs);
   TPG_CHECK_LAUNCH("transpose_multi");
+  return 0;
+}
+
+int tpgan_maxpool3s2(tpgan_view x, tpgan_view y, uint8_t* argmax, void* stream) {
+  if (x.n != y.n || x.c != y.c || y.h != (x.h + 2 - 3) / 2 + 1 || y.w != (x.w + 2 - 3) / 2 + 1)
+    return set_error(TPGAN_ERR_INVALID, "maxpool3s2: geometry mismatch");
+  long long total = (long long)y.n * y.h * y.w * y.c;
+  maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(x), dv(y), argmax);
+  TPG_CHECK_LAUNCH("maxpool3s2");
+  return 0;
+}
+int tpgan_maxpool3s2_backward(tpgan_view dy, const uint8_t* argmax, tpgan_view dx, int32_t accumulate, void* stream) {
+  if (!argmax || dx.n != dy.n || dx.c != dy.c) return set_error(TPGAN_ERR_INVALID, "maxpool3s2_backward: bad args");
+  long long total = (long long)dx.n * dx.h * dx.w * dx.c;
+  maxpool3s2_backward_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(dy), argmax, dv(dx), accumulate);
+  TPG_CHECK_LAUNCH("maxpool3s2_backward");
+  return 0;
+}
+int tpgan_avgpool(tpgan_view x, tpgan_view y, void* stream) {
+  if (x.n != y.n || x.c != y.c || y.h != 1 || y.w != 1) return set_error(TPGAN_ERR_INVALID, "avgpool: geometry mismatch");
+  avgpool_kernel<<<dim3((unsigned)((x.c + 63) / 64), (unsigned)x.n), 64, 0, ST>>>(dv(x), dv(y));
+  TPG_CHECK_LAUNCH("avgpool");
+  return 0;
+}
+int tpgan_avgpool_backward(tpgan_view dy, tpgan_view dx, int32_t accumulate, void* stream) {
+  if (dx.n != dy.n || dx.c != dy.c || dy.h != 1 || dy.w != 1) return set_error(TPGAN_ERR_INVALID, "avgpool_backward: bad args");
+  long long total = (long long)dx.n * dx.h * dx.w * dx.c;
+  avgpool_backward_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(dy), dv(dx), accumulate);
+  TPG_CHECK_LAUNCH("avgpool_backward");
   return 0;
 }
 

@@ -705,6 +705,40 @@ class Plan:
         self.tape.append(bwd)
         return out
 
+    def maxpool3s2(self, x: T, name: str = "maxpool") -> T:
+        """nn.MaxPool2d(3, 2, 1) (identity network, ResNet.py:33)."""
+        n, h, w, c = x.act.n, x.act.h, x.act.w, x.act.c
+        ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        out = self.new(n, ho, wo, c, name=name)
+        need = x.requires_grad and self.training
+        arg = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=self.device) if need else None
+        self.use(x)
+        self.fwd.append(lambda: ops.maxpool3s2(x.act, out.act, arg))
+
+        def bwd():
+            if not need or not self._has_grad(out):
+                return self._null(x)
+            self._finalize(out)
+            g = self.grad_act(out)
+            self._contribute(x, lambda dst, acc: ops.maxpool3s2_backward(g, arg, dst, acc))
+        self.tape.append(bwd)
+        return out
+
+    def avgpool(self, x: T, name: str = "avgpool") -> T:
+        """nn.AdaptiveAvgPool2d((1, 1)) (ResNet.py:45)."""
+        out = self.new(x.act.n, 1, 1, x.act.c, name=name)
+        self.use(x)
+        self.fwd.append(lambda: ops.avgpool(x.act, out.act))
+
+        def bwd():
+            if not self._has_grad(out):
+                return self._null(x)
+            self._finalize(out)
+            g = self.grad_act(out)
+            self._contribute(x, lambda dst, acc: ops.avgpool_backward(g, dst, acc))
+        self.tape.append(bwd)
+        return out
+
     # ------------------------------------------------------------------ backward tracing
     def seed_grad(self, t: T):
         """Declare that an external kernel (a loss) writes t's gradient before the backward replay."""

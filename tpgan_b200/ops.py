@@ -230,6 +230,23 @@ def local_fuse_backward(dout: Act, argmax: torch.Tensor, dpatches: Sequence[Act]
                                                      int(accumulate), _stream()), "local_fuse_backward")
 
 
+def maxpool3s2(x: Act, y: Act, argmax: Optional[torch.Tensor]) -> None:
+    _lib.check(_lib.load().tpgan_maxpool3s2(x.view(), y.view(), _ptr(argmax), _stream()), "maxpool3s2")
+
+
+def maxpool3s2_backward(dy: Act, argmax: torch.Tensor, dx: Act, accumulate: bool = False) -> None:
+    _lib.check(_lib.load().tpgan_maxpool3s2_backward(dy.view(), argmax.data_ptr(), dx.view(), int(accumulate), _stream()),
+               "maxpool3s2_backward")
+
+
+def avgpool(x: Act, y: Act) -> None:
+    _lib.check(_lib.load().tpgan_avgpool(x.view(), y.view(), _stream()), "avgpool")
+
+
+def avgpool_backward(dy: Act, dx: Act, accumulate: bool = False) -> None:
+    _lib.check(_lib.load().tpgan_avgpool_backward(dy.view(), dx.view(), int(accumulate), _stream()), "avgpool_backward")
+
+
 def image_losses(fake: Act, t128: Act, t64: Act, t32: Act, dfake: Act, coeffs: Sequence[float],
                  sums: torch.Tensor) -> None:
     w = (C.c_float * 8)(*coeffs)
