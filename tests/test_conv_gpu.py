@@ -53,10 +53,17 @@ CONV_CASES = [
     (2, 206, 64, 10, 128, 5, 1, 2),
     (2, 64, 32, 6, 128, 3, 1, 1),
     (1, 32, 3, 5, 128, 3, 1, 1),
+    # slab-mode weight gradients: partial last pixel box (W = 200), even kernel, wide-P / narrow-Q (operand swap)
+    (1, 64, 64, 4, 200, 3, 1, 1),
+    (2, 40, 24, 6, 36, 4, 1, 2),
+    (2, 160, 32, 5, 64, 5, 1, 2),
 ]
 
 
-@pytest.mark.parametrize("case", CONV_CASES)
+FWD_CASES = [c for c in CONV_CASES if c[4] <= 128]   # the forward/dgrad kernels tile widths up to 128
+
+
+@pytest.mark.parametrize("case", FWD_CASES)
 def test_conv_fwd(case):
     from tpgan_b200 import ops
     n, cin, cout, h, w, k, s, p = case
@@ -75,7 +82,7 @@ def test_conv_fwd(case):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("case", FWD_CASES)
 def test_conv_dgrad(case):
     from tpgan_b200 import ops
     n, cin, cout, h, w, k, s, p = case
@@ -121,6 +128,7 @@ DECONV_CASES = [
     (4, 320, 64, 1, 1, 8, 1, 0, 0),
     (2, 16, 8, 64, 64, 3, 2, 1, 1),
     (2, 256, 128, 8, 12, 3, 2, 1, 1),
+    (2, 32, 16, 8, 40, 3, 1, 1, 0),
 ]
 
 

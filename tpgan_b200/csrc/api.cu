@@ -1,5 +1,6 @@
 // C-ABI entry points for the tensor-core convolution kernels: host-side planning (tap lists, parity planes, tile
 // geometry, TMA descriptors) and launch.  See include/tpgan_b200.h for the contract of every function.
+#include <cmath>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
@@ -349,6 +350,101 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad planning
+// How one weight-gradient problem is mapped onto the kernel (see WgradGroup in kparams.h).
+struct WgradChoice {
+  bool swap;      // stride-1 conv only: P = x (M = Cin), Q = dy shifted by -tap (N = Cout), dw written transposed
+  bool slab;      // taps of one kernel row share one Q slab (N = taps * 32 per MMA)
+  int pc, qc;     // channels of P and Q
+  int m_tiles, nch_total, n_tiles, block_n, ncpt, mpu, tpu;
+  int a_ch;       // 32-channel P chunks per stage
+  int b_ch;       // 32-channel Q chunks per stage (non-slab)
+  double cost;    // modelled tensor-pipe cycles per 8-pixel K step over all taps / tiles
+};
+
+static const double kL2BytesPerClk = 45.0;   // sustained L2->SM bytes/clk/SM with every SM streaming (measured 35-50)
+
+static WgradChoice wgrad_option(const tpgan_wgrad_args& a, bool swap, bool slab) {
+  WgradChoice c{};
+  static const bool no_pack = getenv("TPGAN_WGRAD_NOPACK") != nullptr;
+  static const int tap_pack_max = getenv("TPGAN_WGRAD_TAPPACK") ? atoi(getenv("TPGAN_WGRAD_TAPPACK")) : 1;
+  const bool is_conv = (a.kind == TPGAN_CONV_FWD);
+  const bool p_is_dy = is_conv && !swap;
+  const tpgan_view& Pt = p_is_dy ? a.dy : a.x;
+  const tpgan_view& Qt = p_is_dy ? a.x : a.dy;
+  const int k = a.kh, ntaps = k * k;
+  c.swap = swap;
+  c.slab = slab;
+  c.pc = Pt.c;
+  c.qc = Qt.c;
+  c.m_tiles = ceil_div(c.pc, 128);
+  c.nch_total = ceil_div(c.qc, 32);
+  const long long npix = (long long)Pt.h * Pt.w * Pt.n;
+  if (slab) {
+    c.ncpt = c.nch_total;
+    c.n_tiles = 1;
+    c.mpu = (c.m_tiles * c.ncpt * 2 <= 16) ? c.m_tiles : 1;   // (acc_chunks below may still shrink tpu)
+    static const int acc_chunks = getenv("TPGAN_WGRAD_SLAB_COLS") ? atoi(getenv("TPGAN_WGRAD_SLAB_COLS")) / 32 : 16;
+    const int tmax = std::min(std::min(k, 8), acc_chunks / std::max(1, c.mpu * c.ncpt));
+    if (c.ncpt > 8 || tmax < 2) { c.cost = 1e30; return c; }
+    const int ngrp = ceil_div(k, tmax);
+    c.tpu = ceil_div(k, ngrp);
+    if (k * ngrp * c.tpu > kMaxTaps) { c.cost = 1e30; return c; }
+    c.block_n = c.tpu * 32;
+    c.a_ch = std::min(4 * c.mpu, ceil_div(c.pc, 32));
+    c.b_ch = c.ncpt;
+    double row = 0;   // MMA cycles per K step for the taps of one kernel row, one M tile, one Q chunk
+    for (int g = 0, left = k; g < ngrp; ++g) {
+      const int nt = std::min(c.tpu, left);
+      left -= nt;
+      const double mma = std::max(16.0 * nt, 32.0 + 8.0 * nt) * c.mpu * c.ncpt;
+      const double l2 = (c.a_ch + c.ncpt) * 1024.0 / kL2BytesPerClk;
+      row += std::max(mma, l2) * ceil_div(c.m_tiles, c.mpu);
+    }
+    c.cost = row * k;
+    return c;
+  }
+  if (c.nch_total <= tap_pack_max && ntaps > 1 && !no_pack) {
+    // narrow shifted tensor (one 32-channel chunk: the 3-channel image layers): several taps side by side in N, all
+    // sharing the loads of P
+    c.ncpt = c.nch_total;
+    c.tpu = std::min(ntaps, 8 / c.nch_total);
+    c.n_tiles = 1;
+    c.block_n = c.tpu * c.ncpt * 32;
+    c.mpu = 1;
+    c.a_ch = std::min(4, ceil_div(c.pc, 32));
+    c.b_ch = c.tpu * c.ncpt;
+  } else {
+    c.tpu = 1;
+    c.n_tiles = ceil_div(c.nch_total, 8);
+    c.block_n = ceil_div(c.nch_total, c.n_tiles) * 32;
+    c.ncpt = c.block_n / 32;
+    // several M tiles per unit (one accumulator each), all sharing the loads of Q - when the reduction is long enough
+    // (>= 32768 pixels) to amortise the then single-buffered epilogue
+    c.mpu = (no_pack || npix < 32768) ? 1 : std::max(1, std::min(c.m_tiles, 512 / c.block_n));
+    c.a_ch = std::min(4 * c.mpu, ceil_div(c.pc, 32));
+    c.b_ch = c.ncpt;
+  }
+  const double mma = std::max(c.block_n / 2.0, 32.0 + c.block_n / 4.0) * c.mpu;
+  const double l2 = (c.a_ch + c.b_ch) * 1024.0 / kL2BytesPerClk;
+  c.cost = std::max(mma, l2) * ceil_div(ntaps, c.tpu) * ceil_div(c.m_tiles, c.mpu) * c.n_tiles;
+  return c;
+}
+
+static WgradChoice choose_wgrad(const tpgan_wgrad_args& a) {
+  static const int slab_mode = getenv("TPGAN_WGRAD_SLAB") ? atoi(getenv("TPGAN_WGRAD_SLAB")) : 1;
+  WgradChoice best = wgrad_option(a, false, false);
+  const bool is_conv = (a.kind == TPGAN_CONV_FWD);
+  const tpgan_view& Pt = is_conv ? a.dy : a.x;
+  // slab mode needs unit-stride taps along W and row-segment boxes worth a pipeline stage
+  if (slab_mode && a.stride == 1 && a.kh >= 2 && Pt.w >= 32) {
+    for (int sw = 0; sw < (is_conv ? 2 : 1); ++sw) {
+      WgradChoice c = wgrad_option(a, sw != 0, true);
+      if (c.cost < best.cost * 0.95) best = c;
+    }
+  }
+  return best;
+}
+
 static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   memset(&G, 0, sizeof(G));
   const int k = a.kh;
@@ -357,12 +453,15 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   if (s != 1 && s != 2 && s != 4) return set_error(TPGAN_ERR_INVALID, "stride %d unsupported", s);
   if (a.x.n != a.dy.n) return set_error(TPGAN_ERR_INVALID, "batch mismatch");
   // conv  : P = dy (Cout), Q = x planes  (Cin)  -> dw[tap][co][ci], m=co n=ci
+  // conv, swapped (stride 1): P = x (Cin), Q = dy shifted by -tap (Cout) -> m=ci n=co (transposed write)
   // deconv: P = x  (Cin),  Q = dy planes (Cout) -> dw[tap][co][ci], m=ci n=co (transposed write)
   const bool is_conv = (a.kind == TPGAN_CONV_FWD);
   if (!is_conv && a.kind != TPGAN_DECONV_FWD) return set_error(TPGAN_ERR_INVALID, "bad wgrad kind %d", a.kind);
-  const tpgan_view& Pt = is_conv ? a.dy : a.x;
-  const tpgan_view& Qt = is_conv ? a.x : a.dy;
-  G.transpose_out = is_conv ? 0 : 1;
+  const WgradChoice ch = choose_wgrad(a);
+  const bool p_is_dy = is_conv && !ch.swap;
+  const tpgan_view& Pt = p_is_dy ? a.dy : a.x;
+  const tpgan_view& Qt = p_is_dy ? a.x : a.dy;
+  G.transpose_out = p_is_dy ? 0 : 1;
   G.m_valid = Pt.c;
   G.n_valid = Qt.c;
   const int cout = a.dy.c, cin = a.x.c;
@@ -374,40 +473,60 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   G.Hp = Pt.h;
   G.Wp = Pt.w;
   G.Nimg = Pt.n;
-  // pixel boxes of ~32 pixels
+  // pixel boxes of ~box_px pixels (slab mode: one row segment)
   G.bw = (G.Wp <= box_px + box_px / 2) ? G.Wp : box_px;
-  G.bh = std::max(1, std::min(G.Hp, box_px / G.bw));
-  G.bn = (G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, box_px / (G.bw * G.bh))) : 1;
+  G.bh = ch.slab ? 1 : std::max(1, std::min(G.Hp, box_px / G.bw));
+  G.bn = (!ch.slab && G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, box_px / (G.bw * G.bh))) : 1;
   G.kp = ceil_div(G.bw * G.bh * G.bn, 8) * 8;
   G.tiles_w = ceil_div(G.Wp, G.bw);
   G.tiles_h = ceil_div(G.Hp, G.bh);
   G.chunks = G.tiles_w * G.tiles_h * ceil_div(G.Nimg, G.bn);
-  G.m_tiles = ceil_div(G.m_valid, 128);
-  const int nch_total = ceil_div(G.n_valid, 32);
-  G.ntaps = k * k;
-  static const bool no_pack = getenv("TPGAN_WGRAD_NOPACK") != nullptr;
-  static const int tap_pack_max = getenv("TPGAN_WGRAD_TAPPACK") ? atoi(getenv("TPGAN_WGRAD_TAPPACK")) : 1;
-  if (nch_total <= tap_pack_max && G.ntaps > 1 && !no_pack) {
-    // narrow shifted tensor (one 32-channel chunk: the 3-channel image layers): several taps side by side in N, all
-    // sharing the loads of P (measured: pays only for a single chunk; wider tensors become L2-bound)
-    G.ncpt = nch_total;
-    G.tpu = std::min(G.ntaps, 8 / nch_total);
-    G.n_tiles = 1;
-    G.block_n = G.tpu * G.ncpt * 32;
-    G.mpu = 1;
-  } else {
-    G.tpu = 1;
-    G.n_tiles = ceil_div(nch_total, 8);
-    G.block_n = ceil_div(nch_total, G.n_tiles) * 32;
-    G.ncpt = G.block_n / 32;
-    // several M tiles per unit (one accumulator each), all sharing the loads of Q - when the reduction is long enough
-    // (>= 4096 pixels per image batch) to amortise the then single-buffered epilogue
-    const long long npix = (long long)G.Hp * G.Wp * G.Nimg;
-    G.mpu = (no_pack || npix < 32768) ? 1 : std::max(1, std::min(G.m_tiles, 512 / G.block_n));
-  }
-  G.tap_groups = ceil_div(G.ntaps, G.tpu);
+  G.m_tiles = ch.m_tiles;
+  G.ncpt = ch.ncpt;
+  G.tpu = ch.tpu;
+  G.n_tiles = ch.n_tiles;
+  G.block_n = ch.block_n;
+  G.mpu = ch.mpu;
+  G.slab = ch.slab ? 1 : 0;
   G.mt_groups = ceil_div(G.m_tiles, G.mpu);
+  // MN-major tf32 operands need the 32B-atom flavour of the 128B swizzle
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.bw, G.bh, G.bn, swz);
+  if (rc) return rc;
+  if (ch.slab) {
+    // taps: per kernel row, groups of tpu slots (unused slots: wtap 255), horizontal offset increasing inside a group
+    const int ngrp = ceil_div(k, G.tpu);
+    int nt = 0;
+    for (int r = 0; r < k; ++r)
+      for (int g = 0; g < ngrp; ++g)
+        for (int t = 0; t < G.tpu; ++t) {
+          const int j = g * G.tpu + t;          // position along the row in order of increasing offset
+          TapDesc td;
+          td.plane = 0;
+          if (j < k) {
+            const int c = ch.swap ? (k - 1 - j) : j;   // swapped: the shifted tensor is dy at offset -(tap - p)
+            const int ey = r - p, ex = c - p;
+            td.dy = (int8_t)(ch.swap ? -ey : ey);
+            td.dx = (int8_t)(ch.swap ? -ex : ex);
+            td.wtap = (uint8_t)(r * k + c);
+          } else {
+            td.dy = td.dx = 0;
+            td.wtap = 255;
+          }
+          G.taps[nt++] = td;
+        }
+    G.ntaps = nt;
+    G.tap_groups = k * ngrp;
+    G.nbuf = (G.mpu * G.ncpt * G.tpu * 32 <= 256) ? 2 : 1;
+    G.q_chunk_bytes = ceil_div(G.kp + G.tpu - 1, 8) * 8 * 128;
+    rc = encode_nhwc(&G.qslab, Qt.ptr, Qt.c, Qt.w, Qt.h, Qt.n, Qt.sw, Qt.sh, Qt.sn, G.bw + G.tpu - 1, 1, 1, swz);
+    if (rc) return rc;
+    return 0;
+  }
+  G.ntaps = k * k;
+  G.tap_groups = ceil_div(G.ntaps, G.tpu);
   G.nbuf = (G.mpu * G.block_n <= 256) ? 2 : 1;
+  G.q_chunk_bytes = G.kp * 128;
   int nt = 0;
   for (int r = 0; r < k; ++r)
     for (int c = 0; c < k; ++c) {
@@ -419,10 +538,6 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
       t.wtap = (uint8_t)(r * k + c);
       G.taps[nt++] = t;
     }
-  // MN-major tf32 operands need the 32B-atom flavour of the 128B swizzle
-  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.bw, G.bh, G.bn, swz);
-  if (rc) return rc;
   rc = encode_planes(G.qmap, Qt, s, G.bw, G.bh, G.bn, swz);
   if (rc) return rc;
   return 0;
@@ -433,69 +548,65 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
 static int choose_wgrad_px(const tpgan_wgrad_args* groups, int ngroups) {
   if (const char* ev = getenv("TPGAN_WGRAD_PX")) return std::max(8, std::min(128, atoi(ev)));
   const int budget = g_dev.max_smem - 1024 - 256;
-  int chunks = 0;
-  static const bool no_pack = getenv("TPGAN_WGRAD_NOPACK") != nullptr;
-  for (int i = 0; i < ngroups; ++i) {
-    const bool is_conv = groups[i].kind == TPGAN_CONV_FWD;
-    const int pc = is_conv ? groups[i].dy.c : groups[i].x.c, qc = is_conv ? groups[i].x.c : groups[i].dy.c;
-    const int ntaps = groups[i].kh * groups[i].kw;
-    const int m_tiles = ceil_div(pc, 128);
-    const int nch_total = ceil_div(qc, 32);
-    int a_ch, b_ch;
-    static const int tap_pack_max = getenv("TPGAN_WGRAD_TAPPACK") ? atoi(getenv("TPGAN_WGRAD_TAPPACK")) : 1;
-    const tpgan_view& Pt = is_conv ? groups[i].dy : groups[i].x;
-    const long long npix = (long long)Pt.h * Pt.w * Pt.n;
-    if (nch_total <= tap_pack_max && ntaps > 1 && !no_pack) {
-      a_ch = std::min(4, ceil_div(pc, 32));
-      b_ch = std::min(ntaps, 8 / nch_total) * nch_total;
-    } else {
-      b_ch = ceil_div(nch_total, ceil_div(nch_total, 8));
-      const int mpu = (no_pack || npix < 32768) ? 1 : std::max(1, std::min(m_tiles, 512 / (b_ch * 32)));
-      a_ch = std::min(4 * mpu, ceil_div(pc, 32));
+  auto stage_bytes = [&](int px) {
+    int worst = 0;
+    for (int i = 0; i < ngroups; ++i) {
+      const WgradChoice c = choose_wgrad(groups[i]);
+      const int q_rows = c.slab ? ceil_div(px + c.tpu - 1, 8) * 8 : px;
+      worst = std::max(worst, c.a_ch * px * 128 + c.b_ch * q_rows * 128);
     }
-    chunks = std::max(chunks, a_ch + b_ch);
-  }
+    return worst;
+  };
   for (int px : {128, 64})
-    if (budget / (chunks * px * 128) >= 4) return px;
-  if (budget / (chunks * 32 * 128) >= 3) return 32;
+    if (budget / stage_bytes(px) >= 4) return px;
+  if (budget / stage_bytes(32) >= 3) return 32;
   return 16;
 }
 
 template <class Params>
 static int launch_wgrad(Params& P, cudaStream_t st) {
-  int amax = 0, bmax = 0, base_units = 0;
+  int amax = 0, bmax = 0;
+  long long work = 0;
   for (int i = 0; i < P.ngroups; ++i) {
     WgradGroup& G = P.g[i];
-    amax = std::max(amax, 4 * G.mpu * G.kp * 128);
-    bmax = std::max(bmax, (G.block_n / 32) * G.kp * 128);
-    base_units += G.tap_groups * G.mt_groups * G.n_tiles;
+    amax = std::max(amax, std::min(4 * G.mpu, ceil_div(G.m_valid, 32)) * G.kp * 128);
+    bmax = std::max(bmax, (G.slab ? G.ncpt : G.block_n / 32) * G.q_chunk_bytes);
+    G.tiles = G.tap_groups * G.mt_groups * G.n_tiles;
+    // K blocks: pixel ranges whose activations (P and Q) fit a slice of L2; every CTA works through block after block
+    {
+      static const double mb_plain = getenv("TPGAN_WGRAD_KB_MB") ? atof(getenv("TPGAN_WGRAD_KB_MB")) : 64.0;
+      static const double mb_slab = getenv("TPGAN_WGRAD_KB_MB_SLAB") ? atof(getenv("TPGAN_WGRAD_KB_MB_SLAB")) : 1e6;   // slab units stream little from L2 and pay for every extra epilogue
+      const double bytes = (double)G.Hp * G.Wp * G.Nimg * 4.0 * (ceil_div(G.m_valid, 4) * 4 + ceil_div(G.n_valid, 4) * 4);
+      int nkb = (int)std::ceil(bytes / ((G.slab ? mb_slab : mb_plain) * 1048576.0));
+      nkb = std::max(1, std::min(nkb, G.chunks));
+      G.kb_chunks = ceil_div(G.chunks, nkb);
+      G.nkb = ceil_div(G.chunks, G.kb_chunks);
+    }
+    G.work_begin = (int)work;
+    work += (long long)G.tiles * G.chunks;
   }
-  // split the pixel reduction so that ~2 waves of units cover the SMs
-  int units = 0;
-  for (int i = 0; i < P.ngroups; ++i) {
-    WgradGroup& G = P.g[i];
-    int want = std::max(1, ceil_div(2 * g_dev.sm_count, std::max(1, base_units)));
-    int ks = std::min(want, G.chunks);
-    G.chunks_per_split = ceil_div(G.chunks, ks);
-    G.ksplits = ceil_div(G.chunks, G.chunks_per_split);
-    G.unit_begin = units;
-    G.unit_count = G.tap_groups * G.mt_groups * G.n_tiles * G.ksplits;
-    units += G.unit_count;
-  }
-  P.total_units = units;
+  if (work <= 0 || work > 0x7fffffffll) return set_error(TPGAN_ERR_INVALID, "wgrad: work list of %lld chunks unsupported", work);
+  P.total_work = (int)work;
   P.nbuf = 2;
   for (int i = 0; i < P.ngroups; ++i) P.nbuf = std::min(P.nbuf, P.g[i].nbuf);
   P.a_stage_bytes = amax;
   P.b_stage_bytes = bmax;
   const int stage_bytes = amax + bmax;
-  const int budget = g_dev.max_smem - 1024 - 256;
+  // an M = 128 MMA always reads four 32-channel P chunks; when fewer are loaded (P narrower than 128 channels) the read
+  // runs into the following bytes (rows that are never stored), so the ring is followed by that much slack
+  int slack = 0;
+  for (int i = 0; i < P.ngroups; ++i) slack = std::max(slack, 4 * P.g[i].mpu * P.g[i].kp * 128 - stage_bytes);
+  slack = std::max(0, slack);
+  const int budget = g_dev.max_smem - 1024 - 256 - slack;
   P.stages = std::min(kMaxStages, budget / stage_bytes);
+  P.ring_bytes = P.stages * stage_bytes + slack;
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "wgrad: not enough shared memory for 2 stages (%d B/stage)", stage_bytes);
-  const int smem = P.stages * stage_bytes + 1024;
+  const int smem = P.ring_bytes + 1024;
   auto kern = wgrad_kernel<Params>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int grid = std::min(units, g_dev.sm_count);
+  // balanced schedule: every CTA gets total_work / grid (+-1) chunks (see SegmentWalk in wgrad.cu)
+  const int grid = (int)std::min<long long>(work, g_dev.sm_count);
   kern<<<grid, 256, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
@@ -559,7 +670,8 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
     bool same = true;
     for (int i = 1; i < ngroups; ++i)
       same = same && P.g[i].bw == P.g[0].bw && P.g[i].bh == P.g[0].bh && P.g[i].bn == P.g[0].bn &&
-             P.g[i].block_n == P.g[0].block_n && P.g[i].mpu == P.g[0].mpu && P.g[i].tpu == P.g[0].tpu;
+             P.g[i].block_n == P.g[0].block_n && P.g[i].mpu == P.g[0].mpu && P.g[i].tpu == P.g[0].tpu &&
+             P.g[i].slab == P.g[0].slab;
     if (!same) {
       for (int i = 0; i < ngroups; ++i) {
         rc = tpgan_conv2d_wgrad(groups + i, 1, stream);

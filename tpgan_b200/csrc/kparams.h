@@ -95,6 +95,7 @@ struct RowConvParams {
 struct WgradGroup {
   CUtensorMap pmap;              // unshifted tensor, 4D {C, W, H, N}, box {32, bw, bh, bn}
   CUtensorMap qmap[kMaxPlanes];  // shifted tensor planes, same box
+  CUtensorMap qslab;             // slab mode: box {32, bw + tpu - 1, 1, 1} of the shifted tensor (one row segment + halo)
   int Hp, Wp, Nimg;
   int bw, bh, bn, kp;            // kp = K rows per stage (pixels rounded up to 8)
   int tiles_w, tiles_h, chunks;  // pixel boxes: tiles_w * tiles_h * ceil(Nimg/bn)
@@ -103,10 +104,15 @@ struct WgradGroup {
   // (their Q chunks sit side by side in the N dimension; they share every P load).  mpu > 1 and tpu > 1 are exclusive.
   int mpu, mt_groups;            // M tiles per unit, ceil(m_tiles / mpu)
   int tpu, tap_groups, ncpt;     // taps per unit, ceil(ntaps / tpu), 32-channel Q chunks per tap (tpu > 1: block_n = tpu*ncpt*32)
-  int nbuf;                      // TMEM accumulator buffers (2 when mpu * block_n <= 256)
-  int ksplits, chunks_per_split;
+  int nbuf;                      // TMEM accumulator buffers (2 when the unit's accumulators fit 256 columns)
+  // Slab mode (stride 1, row-segment boxes): the taps of a unit are `tpu` horizontally consecutive taps of ONE kernel row;
+  // Q is loaded once per chunk as a slab of bw + tpu - 1 pixels and tap t reads it shifted by t pixel rows (128 B), all
+  // taps in one MMA per 32-channel chunk (N = taps * 32, leading byte offset 128).  Accumulator columns:
+  // ((mi * ncpt + chunk) * tpu + tap) * 32 + channel.
+  int slab, q_chunk_bytes;
   int ntaps;
-  int unit_begin, unit_count;    // units = tap_groups * mt_groups * n_tiles * ksplits
+  int work_begin, tiles;         // tiles = tap_groups * mt_groups * n_tiles; work = tiles * chunks, prefix over groups
+  int kb_chunks, nkb;            // the work list is ordered (K block of kb_chunks chunks, tile, chunk); nkb = ceil(chunks / kb_chunks)
   TapDesc taps[kMaxTaps];
   float* dw;                     // [taps+1][rows_pad][k_pad]
   int rows_pad, k_pad;
@@ -117,17 +123,19 @@ struct WgradGroup {
 
 struct WgradParams {
   int ngroups;
-  int total_units;
+  int total_work;                // sum over groups of tiles * chunks
   int stages;
   int a_stage_bytes, b_stage_bytes;
+  int ring_bytes;                // stages * (a + b) + slack read (never written) by M = 128 MMAs over narrow P tensors
   int nbuf;
   WgradGroup g[kMaxGroups];
 };
 struct WgradParams1 {
   int ngroups;
-  int total_units;
+  int total_work;
   int stages;
   int a_stage_bytes, b_stage_bytes;
+  int ring_bytes;
   int nbuf;
   WgradGroup g[1];
 };

@@ -9,8 +9,9 @@
 // MN-major A and B in that layout, so no transpose is ever materialised.
 // Zero padding and the conv stride are again TMA out-of-bounds fill and parity-plane tensor maps.
 //
-// Work unit = (tap, 128-channel M tile, N tile, K split); units are spread over one persistent CTA per SM and the
-// partial sums are combined with fp32 red.global.add into the forward-packed weight-gradient tensor.
+// Output tile = (tap group, 128-channel M tile group, N tile); the (tile, pixel chunk) work list is cut into equal
+// contiguous slices, one per persistent CTA (one CTA per SM), and the partial sums of tiles that straddle CTAs are
+// combined with fp32 red.global.add into the forward-packed weight-gradient tensor.
 // Replaces the weight half of aten::convolution_backward for ModificationLayer.py:101,189.
 #include "common.cuh"
 #include "kparams.h"
@@ -20,28 +21,56 @@ namespace tpg {
 constexpr int kWTmemCols = 512;
 constexpr int kWAccCols = 256;
 
-struct UnitCoord {
-  int gi, tg, mg, nt, ks;
+// Balanced ("stream-K") schedule.  The reduction of every group is cut into K blocks (pixel ranges sized so that the
+// activations of one block stay in L2); the work of one K block is the list of (output tile, pixel chunk) pairs,
+// tile-major, and CTA b owns the contiguous slice [b*S/grid, (b+1)*S/grid) of EVERY block's list.  All CTAs therefore
+// stream the same pixel range at the same time (each activation byte comes from HBM once) and every CTA gets the same
+// number of chunks (+-1) per block whatever the tile count - no partial last wave.  A slice is walked as segments (one
+// output tile, a chunk range); a segment that covers its tile's whole reduction is written with plain stores, every
+// other one is added with vector reds.
+struct Segment {
+  int gi, tg, mg, nt;
+  int c_begin, c_end;
 };
 
 template <class Params>
-__device__ __forceinline__ UnitCoord decode_unit(const Params& P, int unit) {
-  UnitCoord u;
-  int gi = 0;
-  constexpr int kG = (int)(sizeof(P.g) / sizeof(P.g[0]));
-#pragma unroll
-  for (int i = 1; i < kG; ++i)
-    if (i < P.ngroups && unit >= P.g[i].unit_begin) gi = i;
-  const WgradGroup& G = P.g[gi];
-  int local = unit - G.unit_begin;
-  u.gi = gi;
-  u.tg = local % G.tap_groups;
-  local /= G.tap_groups;
-  u.nt = local % G.n_tiles;
-  local /= G.n_tiles;
-  u.mg = local % G.mt_groups;
-  u.ks = local / G.mt_groups;
-  return u;
+struct SegmentWalk {
+  const Params& P;
+  int gi, kb, pos, end, base, len;
+  __device__ __forceinline__ SegmentWalk(const Params& P_) : P(P_), gi(0), kb(-1), pos(0), end(0), base(0), len(1) {}
+  __device__ __forceinline__ bool next(Segment& s) {
+    while (pos >= end) {
+      if (gi >= P.ngroups) return false;
+      if (++kb >= P.g[gi].nkb) {
+        kb = 0;
+        if (++gi >= P.ngroups) return false;
+      }
+      const WgradGroup& G = P.g[gi];
+      base = kb * G.kb_chunks;
+      len = min(G.kb_chunks, G.chunks - base);
+      const long long S = (long long)G.tiles * len;
+      pos = (int)((S * blockIdx.x) / gridDim.x);
+      end = (int)((S * (blockIdx.x + 1)) / gridDim.x);
+    }
+    const WgradGroup& G = P.g[gi];
+    int tile = pos / len;
+    s.gi = gi;
+    s.c_begin = base + (pos - tile * len);
+    s.c_end = min(base + len, s.c_begin + (end - pos));
+    s.tg = tile % G.tap_groups;
+    tile /= G.tap_groups;
+    s.nt = tile % G.n_tiles;
+    s.mg = tile / G.n_tiles;
+    pos += s.c_end - s.c_begin;
+    return true;
+  }
+};
+
+// Slab mode pads every tap group to tpu slots; unused slots carry wtap == 255.
+__device__ __forceinline__ int slab_group_ntap(const WgradGroup& G, int tap0) {
+  int n = G.tpu;
+  while (n > 1 && G.taps[tap0 + n - 1].wtap == 255) --n;
+  return n;
 }
 
 template <class Params>
@@ -64,7 +93,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
   // never loaded must read as finite values for the lifetime of the kernel.
   {
     uint4* p = reinterpret_cast<uint4*>(smem);
-    const int n16 = (int)((size_t)S * stage_bytes / 16);
+    const int n16 = P.ring_bytes / 16;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
@@ -100,8 +129,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
       uint32_t phase = 0;
       uint32_t sa = smem_base, fb = full0, eb = empty0;
       bool ok = true;
-      for (int unit = blockIdx.x; ok && unit < P.total_units; unit += gridDim.x) {
-        const UnitCoord u = decode_unit(P, unit);
+      SegmentWalk<Params> walk(P);
+      Segment u;
+      while (ok && walk.next(u)) {
         const WgradGroup& G = P.g[u.gi];
         const CUtensorMap* pm = &G.pmap;
         const int mt0 = u.mg * G.mpu;
@@ -109,13 +139,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
         const int mch = min(4 * G.mpu, (G.m_valid - pc0 + 31) / 32);        // P chunks of this unit (all its M tiles)
         const int tap0 = u.tg * G.tpu;
         const int ntap = min(G.tpu, G.ntaps - tap0);
-        const int qc0 = (G.tpu > 1) ? 0 : u.nt * G.block_n;
-        const int ncpt = (G.tpu > 1) ? G.ncpt : min(G.block_n / 32, (G.n_valid - qc0 + 31) / 32);
+        const int qc0 = (G.tpu > 1 || G.slab) ? 0 : u.nt * G.block_n;
+        const int ncpt = (G.tpu > 1 || G.slab) ? G.ncpt : min(G.block_n / 32, (G.n_valid - qc0 + 31) / 32);
         const uint32_t box_bytes = (uint32_t)(G.bw * G.bh * G.bn) * 128u;
-        const uint32_t tx = box_bytes * (uint32_t)(mch + ntap * ncpt);
+        const bool slab = G.slab != 0;
+        const uint32_t q_stride = (uint32_t)G.q_chunk_bytes;
+        const uint32_t tx = slab ? box_bytes * (uint32_t)mch + (uint32_t)(G.bw + G.tpu - 1) * 128u * (uint32_t)G.ncpt
+                                 : box_bytes * (uint32_t)(mch + ntap * ncpt);
         const uint32_t chunk_stride = (uint32_t)G.kp * 128u;
-        const int c_begin = u.ks * G.chunks_per_split;
-        const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
+        const int c_begin = u.c_begin, c_end = u.c_end;
         const int tiles_w = G.tiles_w, tiles_h = G.tiles_h, bw = G.bw, bh = G.bh, bn = G.bn;
         const TapDesc* taps = &G.taps[tap0];
         const bool single_tap = (G.tpu == 1);
@@ -130,7 +162,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
           uint32_t sb = sa + (uint32_t)P.a_stage_bytes;
           mbar_arrive_expect_tx_a(fb, tx);
           for (int i = 0; i < mch; ++i) tma_load_4d_a(sa + (uint32_t)i * chunk_stride, pm, fb, pc0 + i * 32, x0, y0, n0);
-          if (single_tap) {
+          if (slab) {
+            for (int i = 0; i < ncpt; ++i)
+              tma_load_4d_a(sb + (uint32_t)i * q_stride, &G.qslab, fb, i * 32, x0 + tdx0, y0 + tdy0, n0);
+          } else if (single_tap) {
             for (int i = 0; i < ncpt; ++i)
               tma_load_4d_a(sb + (uint32_t)i * chunk_stride, qm0, fb, qc0 + i * 32, x0 + tdx0, y0 + tdy0, n0);
           } else {
@@ -161,8 +196,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
       const uint32_t stage16 = stage_bytes >> 4, areg16 = (uint32_t)P.a_stage_bytes >> 4;
       uint32_t fb = full0, eb = empty0, sbase16 = (smem_base & 0x3FFFFu) >> 4;
       const uint32_t sbase16_0 = sbase16;
-      for (int unit = blockIdx.x; ok && unit < P.total_units; unit += gridDim.x) {
-        const UnitCoord u = decode_unit(P, unit);
+      SegmentWalk<Params> walk(P);
+      Segment u;
+      while (ok && walk.next(u)) {
         const WgradGroup& G = P.g[u.gi];
         if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 12)) break;
         tc_fence_after();
@@ -172,14 +208,29 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
         const uint32_t lbo_field = (chunk16 & 0x3FFFu) << 16;
         const int kgroups = G.kp / 8;
         const int nm = min(G.mpu, G.m_tiles - u.mg * G.mpu);   // M tiles (accumulators) of this unit
-        const int c_begin = u.ks * G.chunks_per_split;
-        const int c_end = min(G.chunks, c_begin + G.chunks_per_split);
+        const int c_begin = u.c_begin, c_end = u.c_end;
         uint32_t acc = 0;
         for (int c = c_begin; c < c_end; ++c) {
           if (!mbar_wait_a(fb, phase, ac, 13)) { ok = false; break; }
           tc_fence_after();
           const uint32_t b_lo = (sbase16 + areg16) | lbo_field;
-          if (nm == 1 && kgroups == 8) {
+          if (G.slab) {
+            // one MMA per 32-channel Q chunk covers all taps of the group: the N dimension walks the taps with a leading
+            // byte offset of ONE pixel row (128 B) through the same slab (im2col by descriptor), D columns = [tap][32 ch]
+            const int ntap = slab_group_ntap(G, u.tg * G.tpu);
+            const uint32_t idesc_s = make_idesc_tf32(128, ntap * 32, 1, 1);
+            const uint32_t qchunk16 = (uint32_t)G.q_chunk_bytes >> 4;
+            const uint32_t bs_lo = (sbase16 + areg16) | (8u << 16);
+            for (int mi = 0; mi < nm; ++mi) {
+              const uint32_t a_lo = (sbase16 + (uint32_t)mi * 4u * chunk16) | lbo_field;
+              for (int i = 0; i < G.ncpt; ++i) {
+                const uint32_t d = d_tmem + (uint32_t)(((mi * G.ncpt + i) * G.tpu) * 32);
+                const uint32_t bi_lo = bs_lo + (uint32_t)i * qchunk16;
+                for (int k = 0; k < kgroups; ++k)
+                  mma_tf32_ss(d, desc_join(a_lo + 64 * k, dhi), desc_join(bi_lo + 64 * k, dhi), idesc_s, k ? 1u : acc);
+              }
+            }
+          } else if (nm == 1 && kgroups == 8) {
             const uint32_t a_lo = sbase16 | lbo_field;
             mma_tf32_ss(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
 #pragma unroll
@@ -215,17 +266,73 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
     const int row = q * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    for (int unit = blockIdx.x; unit < P.total_units; unit += gridDim.x) {
-      UnitCoord u = decode_unit(P, unit);
+    SegmentWalk<Params> walk(P);
+    Segment u;
+    while (walk.next(u)) {
       const WgradGroup& G = P.g[u.gi];
       if (!mbar_wait(&tfull_bar[as], aphase, ac, 14)) break;
       tc_fence_after();
-      const int c_begin = u.ks * G.chunks_per_split;
-      const bool nonempty = c_begin < G.chunks;
-      const bool single = (G.ksplits == 1) && (G.accumulate == 0);  // sole writer of this dW tile: plain stores
+      const bool nonempty = true;
+      // sole writer of this dW tile (whole reduction in this segment, nothing to add to): plain stores
+      const bool single = (u.c_begin == 0) && (u.c_end == G.chunks) && (G.accumulate == 0);
       const int nm = min(G.mpu, G.m_tiles - u.mg * G.mpu);
       const int tap0 = u.tg * G.tpu;
       const int cols_per_tap = (G.tpu > 1) ? G.ncpt * 32 : G.block_n;
+      // 16 accumulator columns of row m -> dw (columns n0 .. n0+15 of tap `tap`)
+      auto store16 = [&](const uint32_t (&r)[16], const TapDesc tap, int m, int n0) {
+        float* dw = G.dw + (size_t)tap.wtap * G.rows_pad * G.k_pad;
+        if (G.transpose_out) {   // dw[n][m]: lanes hold consecutive m -> every red is a coalesced 128 B row segment
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j;
+            if (n < G.n_valid) {
+              float* d = dw + (size_t)n * G.k_pad + m;
+              if (single) *d = __uint_as_float(r[j]); else atomicAdd(d, __uint_as_float(r[j]));
+            }
+          }
+        } else {                 // dw[m][n]: each lane owns 16 consecutive floats of its row -> 16-byte vector ops
+          float* d = dw + (size_t)m * G.k_pad + n0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (n0 + j + 3 < G.n_valid) {
+              if (single) {
+                *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(__uint_as_float(r[j])),
+                             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                             : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (n0 + j + i < G.n_valid) {
+                  if (single) d[j + i] = __uint_as_float(r[j + i]); else atomicAdd(d + j + i, __uint_as_float(r[j + i]));
+                }
+            }
+          }
+        }
+      };
+      if (G.slab) {
+        const int ntap = slab_group_ntap(G, tap0);
+        for (int mi = 0; mi < nm; ++mi) {
+          const int m = (u.mg * G.mpu + mi) * 128 + row;
+          const bool mvalid = m < G.m_valid;
+          for (int i = 0; i < G.ncpt; ++i)
+            for (int t = 0; t < ntap; ++t) {
+              const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + ((mi * G.ncpt + i) * G.tpu + t) * 32) +
+                                      ((uint32_t)(q * 32) << 16);
+              const TapDesc tap = G.taps[tap0 + t];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t r[16];
+                tmem_ld16(t_addr + (uint32_t)(h * 16), r);
+                tmem_ld_wait();
+                if (mvalid && i * 32 + h * 16 < G.n_valid) store16(r, tap, m, i * 32 + h * 16);
+              }
+            }
+        }
+      } else
       for (int mi = 0; mi < nm; ++mi) {
         const int m = (u.mg * G.mpu + mi) * 128 + row;
         const bool mvalid = m < G.m_valid;
@@ -236,40 +343,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
           tmem_ld_wait();
           const int ti = c0 / cols_per_tap;                 // cols_per_tap is a multiple of 32 (or block_n itself)
           if (!(mvalid && nonempty) || tap0 + ti >= G.ntaps) continue;
-          const TapDesc tap = G.taps[tap0 + ti];
-          float* dw = G.dw + (size_t)tap.wtap * G.rows_pad * G.k_pad;
           const int n0 = ((G.tpu > 1) ? 0 : u.nt * G.block_n) + (c0 - ti * cols_per_tap);
-          if (G.transpose_out) {   // dw[n][m]: lanes hold consecutive m -> every red is a coalesced 128 B row segment
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = n0 + j;
-              if (n < G.n_valid) {
-                float* d = dw + (size_t)n * G.k_pad + m;
-                if (single) *d = __uint_as_float(r[j]); else atomicAdd(d, __uint_as_float(r[j]));
-              }
-            }
-          } else {                 // dw[m][n]: each lane owns 16 consecutive floats of its row -> 16-byte vector ops
-            float* d = dw + (size_t)m * G.k_pad + n0;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (n0 + j + 3 < G.n_valid) {
-                if (single) {
-                  *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                } else {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(__uint_as_float(r[j])),
-                               "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
-                               : "memory");
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (n0 + j + i < G.n_valid) {
-                    if (single) d[j + i] = __uint_as_float(r[j + i]); else atomicAdd(d + j + i, __uint_as_float(r[j + i]));
-                  }
-              }
-            }
-          }
+          store16(r, G.taps[tap0 + ti], m, n0);
         }
       }
       tc_fence_before();
