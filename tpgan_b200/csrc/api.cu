@@ -142,7 +142,7 @@ static int encode_planes(CUtensorMap* maps, const tpgan_view& t, int s, int bw, 
 }
 
 // ------------------------------------------------------------------------------------------------ conv planning
-static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G) {
+static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1) {
   memset(&G, 0, sizeof(G));
   const int k = a.kh;
   if (a.kh != a.kw || k < 1 || k > 8) return set_error(TPGAN_ERR_INVALID, "kernel %dx%d unsupported", a.kh, a.kw);
@@ -222,8 +222,9 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G) {
   G.bn = (G.bh == G.Hm) ? std::max(1, std::min(G.Nimg, 128 / (G.bw * G.bh))) : 1;
   G.tiles_h = ceil_div(G.Hm, G.bh);
   G.m_tiles = G.tiles_h * ceil_div(G.Nimg, G.bn);
-  G.n_tiles = ceil_div(a.w_rows_pad, 256);
+  G.n_tiles = ceil_div(a.w_rows_pad, 256) * n_split;
   G.block_n = ceil_div(ceil_div(a.w_rows_pad, G.n_tiles), 16) * 16;
+  G.n_tiles = ceil_div(a.w_rows_pad, G.block_n);
   G.kchunks = ceil_div(Kc, 32);
   G.last_mmas = ceil_div(Kc - 32 * (G.kchunks - 1), 8);
   G.tile_count = G.n_phases * G.m_tiles * G.n_tiles;
@@ -248,6 +249,37 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G) {
   if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) return set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view");
   G.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask);
   return 0;
+}
+
+// Narrower N tiles for launches that cannot fill the SMs (small feature maps): modelled makespan = waves of tiles x
+// (K steps x cycles of one M=128 MMA at that N + a fixed per-tile cost).  Returns the factor by which to multiply n_tiles.
+template <class Params>
+static int choose_n_split(const Params& P, const tpgan_conv_args* groups) {
+  static const bool off = getenv("TPGAN_NO_NSPLIT") != nullptr;
+  if (off) return 1;
+  double best_cost = 0;
+  int best = 1;
+  for (int f : {1, 2, 4, 8}) {
+    double tiles = 0, worst_tile = 0;
+    bool ok = true;
+    for (int i = 0; i < P.ngroups; ++i) {
+      const TapGemmGroup& G = P.g[i];
+      const int base_tiles = ceil_div(groups[i].w_rows_pad, 256);
+      const int bn = ceil_div(ceil_div(groups[i].w_rows_pad, base_tiles * f), 16) * 16;
+      if (f > 1 && bn < 32) { ok = false; break; }
+      const int nt = ceil_div(groups[i].w_rows_pad, bn);
+      int taps = 0;
+      for (int ph = 0; ph < G.n_phases; ++ph) taps += G.phase[ph].tap_count;
+      const double ksteps = (double)taps / G.n_phases * G.kchunks * 4;
+      const double per_tile = ksteps * std::max(bn / 2.0, 32.0 + bn / 4.0) + 4000.0;
+      tiles += (double)G.n_phases * G.m_tiles * nt;
+      worst_tile = std::max(worst_tile, per_tile);
+    }
+    if (!ok) break;
+    const double cost = std::ceil(tiles / g_dev.sm_count) * worst_tile;
+    if (f == 1 || cost < best_cost * 0.9) { best_cost = cost; best = f; }
+  }
+  return best;
 }
 
 template <class Params>
@@ -276,7 +308,7 @@ static int launch_tapgemm(Params& P, cudaStream_t st) {
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int grid = std::min(tiles, g_dev.sm_count);
   if (const char* ev = getenv("TPGAN_GRID")) grid = std::min(grid, std::max(1, atoi(ev)));
-  kern<<<grid, 256, smem, st>>>(P, g_dev.status_dev);
+  kern<<<grid, 384, smem, st>>>(P, g_dev.status_dev);   // kTapGemmThreads (tapgemm.cu)
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -632,6 +664,11 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     P.ngroups = 1;
     rc = plan_group(groups[0], P.g[0]);
     if (rc) return rc;
+    const int f = choose_n_split(P, groups);
+    if (f > 1) {
+      rc = plan_group(groups[0], P.g[0], f);
+      if (rc) return rc;
+    }
     return launch_tapgemm(P, st);
   }
   static thread_local TapGemmParams P;
@@ -640,6 +677,12 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     rc = plan_group(groups[i], P.g[i]);
     if (rc) return rc;
   }
+  const int f = choose_n_split(P, groups);
+  if (f > 1)
+    for (int i = 0; i < ngroups; ++i) {
+      rc = plan_group(groups[i], P.g[i], f);
+      if (rc) return rc;
+    }
   return launch_tapgemm(P, st);
 }
 

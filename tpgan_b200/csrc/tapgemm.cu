@@ -21,6 +21,9 @@ namespace tpg {
 constexpr int kAStageBytes = 128 * 128;  // 128 rows x 32 fp32
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
+// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue (two warps per TMEM lane quarter, each
+// taking every other 16-column group - the epilogue is latency-bound on its addend/mask loads, not on TMEM reads)
+constexpr int kTapGemmThreads = 384;
 
 struct TileCoord {
   int gi, ph, h0, n0, nt;
@@ -49,7 +52,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
 }
 
 template <class Params>
-__global__ void __launch_bounds__(256, 1) tapgemm_kernel(const __grid_constant__ Params P, int* status) {
+__global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __grid_constant__ Params P, int* status) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256, 1) tapgemm_kernel(const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kTapGemmThreads - 128);
     }
     abort_flag = 0;
     fence_barrier_init();
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) tapgemm_kernel(const __grid_constant__
       const float* pm = G.mask.ptr ? G.mask.ptr + (long long)n * G.mask.sn + (long long)yo * G.mask.sh + (long long)xo * G.mask.sw : nullptr;
       const uint32_t t_addr = tmem_base + (uint32_t)(as * kAccCols) + ((uint32_t)(q * 32) << 16);
       const int col_base = tc.nt * G.block_n;
-      for (int c0 = 0; c0 < G.block_n; c0 += 16) {
+      for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 32) {
         uint32_t r[16];
         tmem_ld16(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
