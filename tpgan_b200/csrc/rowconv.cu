@@ -21,8 +21,9 @@
 namespace tpg {
 
 constexpr int kRcMaxSlots = 16;
+constexpr int kRowConvThreads = 384;   // warps 4..11 are the epilogue (two per TMEM lane quarter, alternating 16-column groups)
 
-__global__ void __launch_bounds__(256, 1) rowconv_kernel(const __grid_constant__ RowConvParams P, int* status) {
+__global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __grid_constant__ RowConvParams P, int* status) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kRcMaxSlots];
   __shared__ __align__(8) uint64_t a_empty[kRcMaxSlots];
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256, 1) rowconv_kernel(const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kRowConvThreads - 128);
     }
     abort_flag = 0;
     fence_barrier_init();
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256, 1) rowconv_kernel(const __grid_constant__
         const float* p2 = P.add2.ptr ? P.add2.ptr + (long long)n * P.add2.sn + (long long)y * P.add2.sh + (long long)x * P.add2.sw : nullptr;
         const float* pm = P.mask.ptr ? P.mask.ptr + (long long)n * P.mask.sn + (long long)y * P.mask.sh + (long long)x * P.mask.sw : nullptr;
         const uint32_t t_addr = tmem_base + (uint32_t)(buf * 256 + t * P.block_n) + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < P.block_n; c0 += 16) {
+        for (int c0 = ((warp - 4) >> 2) * 16; c0 < P.block_n; c0 += 32) {
           uint32_t r[16];
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();

@@ -20,6 +20,7 @@ namespace tpg {
 
 constexpr int kWTmemCols = 512;
 constexpr int kWAccCols = 256;
+constexpr int kWgradThreads = 384;   // warps 4..11 are the epilogue (two per TMEM lane quarter, alternating 16-column groups)
 
 // Balanced ("stream-K") schedule.  The reduction of every group is cut into K blocks (pixel ranges sized so that the
 // activations of one block stay in L2); the work of one K block is the list of (output tile, pixel chunk) pairs,
@@ -74,7 +75,7 @@ __device__ __forceinline__ int slab_group_ntap(const WgradGroup& G, int tap0) {
 }
 
 template <class Params>
-__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ Params P, int* status) {
+__global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_constant__ Params P, int* status) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kWgradThreads - 128);
     }
     abort_flag = 0;
     fence_barrier_init();
@@ -323,8 +324,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
               const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + ((mi * G.ncpt + i) * G.tpu + t) * 32) +
                                       ((uint32_t)(q * 32) << 16);
               const TapDesc tap = G.taps[tap0 + t];
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
+              {
+                const int h = (warp - 4) >> 2;
                 uint32_t r[16];
                 tmem_ld16(t_addr + (uint32_t)(h * 16), r);
                 tmem_ld_wait();
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
         const int m = (u.mg * G.mpu + mi) * 128 + row;
         const bool mvalid = m < G.m_valid;
         const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + mi * G.block_n) + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < G.block_n; c0 += 16) {
+        for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 32) {
           uint32_t r[16];
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
