@@ -102,8 +102,9 @@ def image_terms(fake, b):
     return pixel, sym, tv
 
 
-def g_loss(g_out, d_fake, b):
-    """g_out = the Generator 8-tuple; d_fake = D(fake) patch logits."""
+def g_loss(g_out, d_fake, b, identity_sd=None):
+    """g_out = the Generator 8-tuple; d_fake = D(fake) patch logits; identity_sd = state_dict of the frozen identity
+    network (oracle/identity_port.py) or None (the reference's own FeatureExtract/ResNet cannot be built: SURVEY 2.3)."""
     w = LOSS_W
     fake, logits, _, le, re, nose, mouth, _ = g_out
     pixel, sym, tv = image_terms(fake, b)
@@ -113,7 +114,14 @@ def g_loss(g_out, d_fake, b):
     ce = F.cross_entropy(logits, b["label"])
     total = w["weight_pixelwise"] * pixel + w["weight_pixelwise_local"] * local + w["weight_symmetry"] * sym + \
         w["weight_adv_G"] * adv + w["weight_total_varation"] * tv + w["weight_cross_entropy"] * ce
-    return total, dict(pixel=pixel, local=local, symmetry=sym, adv_g=adv, tv=tv, ce=ce, g_total=total)
+    m = dict(pixel=pixel, local=local, symmetry=sym, adv_g=adv, tv=tv, ce=ce)
+    if identity_sd is not None:
+        from . import identity_port
+        ip = identity_port.identity_loss(identity_sd, fake, b["img_frontal"])
+        total = total + w["weight_identity_preserving"] * ip
+        m["ip"] = ip
+    m["g_total"] = total
+    return total, m
 
 
 def d_loss(D: Callable, fake, b):
@@ -127,7 +135,7 @@ def d_loss(D: Callable, fake, b):
     return total, dict(d_fake=d_fake, d_real=d_real, gp=gp, d_total=total)
 
 
-def train_step(G: Callable, D: Callable, g_params, d_params, opt_g, opt_d, b, step_optim: bool = True):
+def train_step(G: Callable, D: Callable, g_params, d_params, opt_g, opt_d, b, step_optim: bool = True, identity_sd=None):
     """One oracle step.  G(b) -> 8-tuple, D(x) -> logits.  Returns python-float metrics."""
     g_out = G(b)
     fake = g_out[0]
@@ -143,7 +151,7 @@ def train_step(G: Callable, D: Callable, g_params, d_params, opt_g, opt_d, b, st
     for p in d_params:
         p.requires_grad_(False)
     opt_g.zero_grad(set_to_none=True)
-    lg, mg = g_loss(g_out, D(fake), b)
+    lg, mg = g_loss(g_out, D(fake), b, identity_sd)
     lg.backward()
     if step_optim:
         opt_g.step()

@@ -1,0 +1,151 @@
+"""GPU parity of the frozen identity network (restated ResNet18-128 / FeatureExtractModel) and of the identity-preserving
+loss against oracle/identity_port.py (fp32 PyTorch on the CPU).
+
+Parity here is ORACLE-DEFINED ("unpinned"): the reference's ResNet.py / FeatureExtract.py cannot be constructed
+(SURVEY.md 2.3), so there is no reference output to record; the oracle restates what those files describe.
+
+Tolerances (||a-b||_2/||b||_2): features of the production TF32 path <= 3e-3 (21 stacked convolutions with folded
+BatchNorm); the input gradient is compared WITHOUT activation-mask injection, so ReLU sign flips caused by the forward
+deviation (17 ReLUs and a max-pool arg-max between the features and the image) show up as a sqrt(eps)-sized deviation
+(see tests/test_model_gpu.py): measured 8e-2 for TF32 (asserted 1.2e-1), <= 2e-2 in the fp32-exact verification mode,
+which is the check that pins the backward plumbing; pooling kernels are compared bit-exactly / at fp32 round-off."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _net(seed=0, fdim=256, classes=347):
+    from tpgan_b200.FeatureExtract import FeatureExtractModel
+    from tpgan_b200.ResNet import BasicBlock
+    torch.manual_seed(seed)
+    net = FeatureExtractModel("resnet", classes, residualBlock=BasicBlock, feature_layer_dim_before_FC=fdim)
+    g = torch.Generator().manual_seed(seed + 1)
+    for m in net.modules():          # non-trivial BatchNorm statistics / affine parameters (a "pretrained" state)
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    net.eval()
+    sd = {k: v.clone() for k, v in net.base_model.state_dict().items()}
+    return net, sd
+
+
+def test_pooling_kernels():
+    from tpgan_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(3, 20, 33, 31)
+    x[0, :, 4:7, 4:7] = 1.5          # ties inside windows: the first maximum in row-major order wins (ATen rule)
+    xa = ops.Act.empty(3, 33, 31, 20).from_nchw(x.cuda())
+    y = ops.Act.empty(3, 17, 16, 20)
+    arg = torch.empty((3, 17, 16, 20), dtype=torch.uint8, device="cuda")
+    ops.maxpool3s2(xa, y, arg)
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(y.to_nchw().cpu(), ref.detach())
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    dya = ops.Act.empty(3, 17, 16, 20).from_nchw(dy.cuda())
+    dx = ops.Act.empty(3, 33, 31, 20)
+    ops.maxpool3s2_backward(dya, arg, dx)
+    assert rel(dx.to_nchw(), xr.grad) < 1e-6
+    p = ops.Act.empty(3, 1, 1, 20)
+    ops.avgpool(xa, p)
+    assert rel(p.to_nchw().flatten(1), x.mean((2, 3))) < 1e-6
+    g = torch.randn(3, 20)
+    ga = ops.Act.empty(3, 1, 1, 20).from_nchw(g.view(3, 20, 1, 1).cuda())
+    ops.avgpool_backward(ga, dx)
+    assert rel(dx.to_nchw(), (g / (33 * 31)).view(3, 20, 1, 1).expand(3, 20, 33, 31)) < 1e-6
+
+
+def test_identity_network_forward():
+    from oracle import identity_port as ip
+    net, sd = _net()
+    x = torch.rand(4, 3, 128, 128, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    out, fc0 = net.cuda()(x.cuda())
+    ref_out, ref_fc0, _ = ip.resnet18_128(sd, x)
+    assert out.shape == (4, 347) and fc0.shape == (4, 256)
+    assert rel(fc0, ref_fc0) < 3e-3, rel(fc0, ref_fc0)
+    assert rel(out, ref_out) < 3e-3, rel(out, ref_out)
+    with pytest.raises(RuntimeError):
+        net(x)                       # CPU tensors: no fallback
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(x.cuda())
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_identity_loss_and_input_gradient(exact):
+    """Loss value against the oracle; the backward chain (FC0 -> pool -> 8 residual blocks -> max-pool -> stem, input
+    gradient ACCUMULATED into d fake) is checked with fixed feature cotangents instead of the L1 sign pattern, which a
+    forward deviation of 1e-3 flips for every feature whose fake/gt difference is that small."""
+    from oracle import identity_port as ip
+    from tpgan_b200 import ops
+    from tpgan_b200.train_step import IdentityPlan
+    net, sd = _net(seed=3)
+    net.cuda()
+    B = 3
+    g = torch.Generator().manual_seed(9)
+    fake = (torch.rand(B, 3, 128, 128, generator=g) * 2 - 1).requires_grad_(True)
+    gt = torch.rand(B, 3, 128, 128, generator=g) * 2 - 1
+    c_pool, c_fc0 = torch.randn(B, 512, generator=g), torch.randn(B, 256, generator=g)
+    ref = ip.identity_loss(sd, fake, gt)
+    _, f0, p0 = ip.resnet18_128(sd, fake)
+    ((p0 * c_pool).sum() + (f0 * c_fc0).sum()).backward()
+    fa = ops.Act.empty(B, 128, 128, 3).from_nchw(fake.detach().cuda(), round_tf32=not exact)
+    ga = ops.Act.empty(B, 128, 128, 3).from_nchw(gt.cuda(), round_tf32=not exact)
+    dfa = ops.Act.empty(B, 128, 128, 3)
+    base = torch.full((B, 3, 128, 128), 0.25)
+    sums = torch.zeros(2, device="cuda")
+    plan = IdentityPlan(net, B, fa, dfa, ga, 1.0, sums, torch.device("cuda"), exact=exact)
+    # (1) the loss as scheduled
+    dfa.from_nchw(base.cuda())
+    for f in plan.schedule():
+        f()
+    torch.cuda.synchronize()
+    got = plan.value(sums.cpu().tolist())
+    assert abs(got - float(ref.detach())) <= (3e-4 if exact else 5e-3) * abs(float(ref.detach())), (got, float(ref.detach()))
+    assert float((dfa.to_nchw().cpu() - base).abs().max()) > 0
+    # (2) fixed cotangents through the same backward launches
+    dfa.from_nchw(base.cuda())
+    seeds = [plan.pf.grad_act(t) for t in plan.feats]
+    for f in plan.pg.fwd + plan.pf.fwd:
+        f()
+    seeds[0].from_nchw(c_pool.view(B, 512, 1, 1).cuda())
+    seeds[1].from_nchw(c_fc0.view(B, 256, 1, 1).cuda())
+    for f in plan.pf.bwd:
+        f()
+    torch.cuda.synchronize()
+    e = rel(dfa.to_nchw().cpu() - base, fake.grad)
+    assert e < (2e-2 if exact else 1.2e-1), e
+
+
+def test_step_with_identity_loss():
+    """The fused G+D step with the identity term: every metric against the oracle step (same weights, same batch)."""
+    from oracle import step as ostep
+    from tpgan_b200 import D_and_G_model as M, config
+    from tpgan_b200.train_step import TPGANTrainer
+    M.EXACT_MODE = False
+    torch.manual_seed(0)
+    G = M.Generator(config.G["zdim"], config.G["num_classes"], config.G["use_batchnorm"], config.G["use_residual_block"])
+    D = M.Discriminator(config.D["use_batchnorm"])
+    pg = {k: v.clone().requires_grad_(True) for k, v in G.state_dict().items()}
+    pd = {k: v.clone().requires_grad_(True) for k, v in D.state_dict().items()}
+    net, sd = _net(seed=7)
+    B = 2
+    b = ostep.make_batch(B)
+    tr = TPGANTrainer(G.cuda(), D.cuda(), B, identity_net=net.cuda())
+    m = tr.step({k: v.cuda() for k, v in b.items()}, optimize=False)
+    Gc, Dc = ostep.port_callables(pg, pd)
+    og = torch.optim.Adam(list(pg.values()), lr=ostep.LEARNING_RATE)
+    od = torch.optim.Adam(list(pd.values()), lr=ostep.LEARNING_RATE)
+    ref = ostep.train_step(Gc, Dc, list(pg.values()), list(pd.values()), og, od, b, step_optim=False, identity_sd=sd)
+    for k in ("pixel", "local", "symmetry", "tv", "ce", "ip", "g_total"):
+        assert abs(m[k] - ref[k]) <= 1e-2 * abs(ref[k]) + 1e-4, (k, m[k], ref[k])

@@ -139,3 +139,63 @@ def test_flops_table_matches_survey():
     from oracle import layer_table
     f = layer_table.flops()
     assert abs(f["G"] / 1e9 - 176.56) < 0.02 and abs(f["D"] / 1e9 - 1.298) < 0.002, f
+
+
+def test_identity_port_is_the_canonical_resnet18():
+    """oracle/identity_port.py restates the ResNet18 the reference's ResNet.py describes but cannot build.
+    Its wiring is pinned against torchvision's resnet18 (the canonical network the reference file follows: 7x7/2 stem,
+    MaxPool(3,2,1), [2,2,2,2] basic blocks, stage strides 1,2,2,2, 1x1 projection shortcuts, global average pool, FC):
+    same weights -> same logits on a 128x128 input."""
+    tv = pytest.importorskip("torchvision")
+    from oracle import identity_port as ip
+    torch.manual_seed(0)
+    ref = tv.models.resnet18(num_classes=37).eval()
+    g = torch.Generator().manual_seed(1)
+    for m in ref.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    src = ref.state_dict()
+    sd = {}
+
+    def bn(dst, s):
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            sd[f"{dst}.{k}"] = src[f"{s}.{k}"]
+    sd["conv1.0.weight"] = src["conv1.weight"]
+    bn("conv1.1", "bn1")
+    for s in range(4):
+        for b in range(2):
+            a, d = f"layer{s + 1}.{b}", f"sections.{s}.{b}"
+            sd[d + ".conv_a.0.weight"] = src[a + ".conv1.weight"]
+            bn(d + ".conv_a.1", a + ".bn1")
+            sd[d + ".conv_b.0.weight"] = src[a + ".conv2.weight"]
+            bn(d + ".conv_b.1", a + ".bn2")
+            if a + ".downsample.0.weight" in src:
+                sd[d + ".shortcut.0.weight"] = src[a + ".downsample.0.weight"]
+                bn(d + ".shortcut.1", a + ".downsample.1")
+    sd["FC.0.weight"], sd["FC.0.bias"] = src["fc.weight"], src["fc.bias"]
+    x = torch.rand(2, 3, 128, 128, generator=g) * 2 - 1
+    with torch.no_grad():
+        want = ref(x)
+        got, fc0, pooled = ip.resnet18_128(sd, x)
+    assert fc0 is None and pooled.shape == (2, 512)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), float((got - want).abs().max())
+
+
+def test_identity_modules_mirror_reference_interface():
+    """tpgan_b200.ResNet / FeatureExtract keep the reference's constructor and forward signatures (ResNet.py:6-7,80;
+    FeatureExtract.py:6,40) and the state_dict key structure of its layer factories."""
+    from tpgan_b200.FeatureExtract import FeatureExtractModel
+    from tpgan_b200.ResNet import BasicBlock, ResNet18
+    net = FeatureExtractModel("resnet", 347, residualBlock=BasicBlock, feature_layer_dim_before_FC=256)
+    keys = set(net.state_dict())
+    assert "base_model.conv1.0.weight" in keys and "base_model.conv1.1.running_mean" in keys
+    assert "base_model.FC0.0.weight" in keys and "base_model.FC.0.weight" in keys
+    assert net.base_model.FC[0].out_features == 347 and net.base_model.FC[0].in_features == 256
+    assert sum(p.numel() for p in ResNet18(BasicBlock, 1000).parameters()) == 11689512   # canonical ResNet18
+    with pytest.raises(ValueError):
+        FeatureExtractModel("vgg")
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.zeros(1, 3, 128, 128))   # CPU tensor: the product path has no CPU fallback

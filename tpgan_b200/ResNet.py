@@ -116,8 +116,11 @@ class ResNet18(nn.Module):
     def trace(self, plan: Plan, x: T, with_logits: bool = True):
         """x: (N,128,128,3) NHWC -> (pooled 512 feature T, FC0 feature T or None, logits T or None)."""
         assert not self.training, "the traced identity network is eval-only (BatchNorm folded with running statistics)"
-        L = self._folded_layers(x.act.buf.device)
-        self._traced_layers = L   # keeps the folded parameters alive
+        # one set of folded tensor-core layers per module: several plans (fake / gt batches) share the packed weights
+        L = getattr(self, "_traced_layers", None)
+        if L is None:
+            L = self._folded_layers(x.act.buf.device)
+            self._traced_layers = L
 
         def cv(name, t, residual=None, relu=None):
             layer, r = L[name]

@@ -402,6 +402,49 @@ class CriticPlan:
         self._run(self.g_phase_list(adv_weight))
 
 
+# ---------------------------------------------------------------------------------------------------------- identity
+class IdentityPlan:
+    """Identity-preserving loss (config.py:79 weight_identity_preserving; TP-GAN eq. 5) through a FROZEN feature network
+    (FeatureExtract.py:5-41 / ResNet.py:5-119, restated - see tpgan_b200/ResNet.py): features of the frontal ground
+    truth (no gradient) and of the fake image, L1 on the two last feature layers (pooled 512 and FC0), input gradient
+    of the fake branch accumulated into d fake.  No weight gradients: the network is frozen."""
+
+    def __init__(self, net, B: int, fake: Act, dfake: Act, frontal: Act, weight: float, sums: torch.Tensor, device,
+                 exact: bool = False):
+        from .FeatureExtract import FeatureExtractModel
+        base = net.base_model if isinstance(net, FeatureExtractModel) else net
+        assert not base.training, "the identity network must be in eval() mode (frozen, BatchNorm folded)"
+        self.base = base
+        # fake branch: forward + input gradient
+        pf = Plan(device, training=True, need_wgrad=False, exact=exact)
+        xin = pf.wrap(fake, name="fake", requires_grad=True)
+        xin.grad = dfake
+        xin.grad_written = True           # image / adversarial terms are already in d fake: accumulate
+        pooled, fc0, _ = base.trace(pf, xin, with_logits=False)
+        # gt branch: forward only
+        pg = Plan(device, training=False, need_wgrad=False, exact=exact)
+        gin = pg.wrap(frontal, name="frontal", requires_grad=False)
+        pooled_gt, fc0_gt, _ = base.trace(pg, gin, with_logits=False)
+        feats = [(pooled, pooled_gt)] + ([(fc0, fc0_gt)] if fc0 is not None else [])
+        self.feats = [a for a, _ in feats]
+        self.loss: List[Callable] = []
+        self.denoms: List[float] = []
+        for i, (a, b) in enumerate(feats):
+            pf.seed_grad(a)
+            n = float(B * a.act.c)
+            self.denoms.append(n)
+            self.loss.append(lambda a=a, b=b, i=i, n=n: ops.l1_loss(a.act, b.act, pf.grad_act(a), weight / n, sums[i:i + 1]))
+        pf.trace_backward()
+        self.pf, self.pg = pf, pg
+        self.sums = sums
+
+    def schedule(self) -> List[Callable]:
+        return self.pg.fwd + self.pf.fwd + self.loss + self.pf.bwd
+
+    def value(self, s: Sequence[float]) -> float:
+        return sum(v / n for v, n in zip(s, self.denoms))
+
+
 # ---------------------------------------------------------------------------------------------------------- trainer
 class TPGANTrainer:
     """One object = both networks, their plans for per-GPU batch `B`, flat parameter buffers and Adam state.
@@ -413,7 +456,10 @@ class TPGANTrainer:
     (DataAndDataset.py:10-56)."""
 
     def __init__(self, G: Generator, D: Discriminator, B: int, device="cuda", use_dropout: bool = False,
-                 exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0, use_graphs: bool = False):
+                 exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0, use_graphs: bool = False,
+                 identity_net=None):
+        """identity_net: optional frozen FeatureExtractModel / ResNet18 in eval() mode; adds the identity-preserving
+        term weight_identity_preserving * L_ip to the generator loss."""
         self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
         self.use_dropout, self.exact = use_dropout, exact
         self.w = dict(cfg.loss)
@@ -434,7 +480,11 @@ class TPGANTrainer:
         if world_size > 1:
             from .parallel import BucketReducer
             self.reducer = BucketReducer(self, bucket_mb, group)
-        self.sums = torch.zeros(16, dtype=torch.float32, device=self.device)  # 0..7 image terms, 8..11 local parts, 12 ce
+        self.sums = torch.zeros(16, dtype=torch.float32, device=self.device)  # 0..7 image terms, 8..11 local parts, 12 ce, 13..14 identity
+        self.identity = None
+        if identity_net is not None:
+            self.identity = IdentityPlan(identity_net, B, self.fake.act, self.plan.grad_act(self.fake), self.frontal,
+                                         float(self.w["weight_identity_preserving"]), self.sums[13:15], self.device, exact=exact)
         self._d_logits = torch.zeros_like(self.critic.logits.buf[:2 * B])
         self.inp: Optional[Dict[str, torch.Tensor]] = None
         self.inp_has_mask = self.fixed_mask = False
@@ -552,6 +602,8 @@ class TPGANTrainer:
         sch.append(lambda: self.sums.zero_())
         sch.append(lambda: ops.image_losses(fake, self.frontal, self.t64, self.t32, dfake, coeffs, self.sums[0:8]))
         sch += crit.g_phase_list(float(w["weight_adv_G"]))
+        if self.identity is not None:
+            sch += self.identity.schedule()
         for i, (t, gt, (h, wd)) in enumerate(zip(self.local_imgs, self.patches_gt, PATCH_HW)):
             sch.append(lambda t=t, gt=gt, i=i, c=w["weight_pixelwise_local"] / (B * 3 * h * wd):
                        ops.l1_loss(t.act, gt, self.plan.grad_act(t), c, self.sums[8 + i:9 + i]))
@@ -609,5 +661,9 @@ class TPGANTrainer:
         adv_g = -float(crit.logits.buf[:B].cpu()[..., 0].mean())
         g_total = w["weight_pixelwise"] * pixel + w["weight_pixelwise_local"] * local + w["weight_symmetry"] * sym + \
             w["weight_adv_G"] * adv_g + w["weight_total_varation"] * tv + w["weight_cross_entropy"] * ce
-        return dict(pixel=pixel, local=local, symmetry=sym, tv=tv, ce=ce, adv_g=adv_g, g_total=g_total, d_fake=d_fake,
-                    d_real=d_real, gp=gp, d_total=d_fake - d_real + w["weight_gradient_penalty"] * gp)
+        out = dict(pixel=pixel, local=local, symmetry=sym, tv=tv, ce=ce, adv_g=adv_g, g_total=g_total, d_fake=d_fake,
+                   d_real=d_real, gp=gp, d_total=d_fake - d_real + w["weight_gradient_penalty"] * gp)
+        if self.identity is not None:
+            out["ip"] = self.identity.value(s[13:15])
+            out["g_total"] = g_total + w["weight_identity_preserving"] * out["ip"]
+        return out
