@@ -308,7 +308,7 @@ static int launch_tapgemm(Params& P, cudaStream_t st) {
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int grid = std::min(tiles, g_dev.sm_count);
   if (const char* ev = getenv("TPGAN_GRID")) grid = std::min(grid, std::max(1, atoi(ev)));
-  kern<<<grid, 384, smem, st>>>(P, g_dev.status_dev);   // kTapGemmThreads (tapgemm.cu)
+  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -374,7 +374,7 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
   cudaError_t e = cudaFuncSetAttribute(rowconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
   const int grid = std::min(P.total_tiles, g_dev.sm_count);
-  rowconv_kernel<<<grid, 384, smem, st>>>(P, g_dev.status_dev);   // kRowConvThreads (rowconv.cu)
+  rowconv_kernel<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowconv launch: %s", cudaGetErrorString(e)); return 1; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -639,7 +639,7 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   // balanced schedule: every CTA gets total_work / grid (+-1) chunks (see SegmentWalk in wgrad.cu)
   const int grid = (int)std::min<long long>(work, g_dev.sm_count);
-  kern<<<grid, 384, smem, st>>>(P, g_dev.status_dev);   // kWgradThreads (wgrad.cu)
+  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);

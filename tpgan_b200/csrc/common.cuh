@@ -232,4 +232,93 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+
+// ---------------------------------------------------------------- fused conv epilogue (shared by tapgemm / rowconv)
+// One 16-column group of one accumulator row: + bias, + up to two addends, (Leaky)ReLU or activation-backward mask with
+// a scalar or per-channel slope, optional tf32 rounding, store.  All global loads of the group are issued before the first
+// store (an addend may legitimately alias the output - in-place accumulation - so the pointers are not __restrict__; with
+// loads interleaved between stores they serialise and the epilogue becomes a chain of ~8 dependent memory round trips).
+struct EpiArgs {
+  const float* bias;
+  const float* slopes;
+  int cout_valid, epilogue, round_tf32, vec_ok;
+  float slope;
+};
+__device__ __forceinline__ void epilogue_store16(const uint32_t (&r)[16], const EpiArgs& E, int col0, float* po,
+                                                 const float* p1, const float* p2, const float* pm) {
+  const int nv16 = E.cout_valid - col0;
+  if (nv16 <= 0) return;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (E.vec_ok && nv16 >= 16) {
+    float4 a1[4], a2[4], mk[4];
+    if (p1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a1[j] = *reinterpret_cast<const float4*>(p1 + col0 + 4 * j);
+    }
+    if (p2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a2[j] = *reinterpret_cast<const float4*>(p2 + col0 + 4 * j);
+    }
+    if (E.epilogue == 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mk[j] = *reinterpret_cast<const float4*>(pm + col0 + 4 * j);
+    }
+    if (E.bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __ldg(E.bias + col0 + j);
+    }
+    if (p1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[4 * j] += a1[j].x; v[4 * j + 1] += a1[j].y; v[4 * j + 2] += a1[j].z; v[4 * j + 3] += a1[j].w; }
+    }
+    if (p2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[4 * j] += a2[j].x; v[4 * j + 1] += a2[j].y; v[4 * j + 2] += a2[j].z; v[4 * j + 3] += a2[j].w; }
+    }
+    if (E.epilogue == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * E.slope;
+    } else if (E.epilogue == 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float m4[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float s = E.slopes ? __ldg(E.slopes + col0 + 4 * j + i) : E.slope;
+          v[4 * j + i] = m4[i] > 0.f ? v[4 * j + i] : v[4 * j + i] * s;
+        }
+      }
+    }
+    if (E.round_tf32) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(po + col0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    return;
+  }
+  // ragged tail / unaligned views: element-wise
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < nv16) {
+      float x = v[j];
+      const int col = col0 + j;
+      if (E.bias) x += __ldg(E.bias + col);
+      if (p1) x += p1[col];
+      if (p2) x += p2[col];
+      if (E.epilogue == 1) {
+        x = x > 0.f ? x : x * E.slope;
+      } else if (E.epilogue == 2) {
+        const float s = E.slopes ? __ldg(E.slopes + col) : E.slope;
+        x = pm[col] > 0.f ? x : x * s;
+      }
+      if (E.round_tf32) x = round_tf32(x);
+      po[col] = x;
+    }
+  }
+}
+
 }  // namespace tpg

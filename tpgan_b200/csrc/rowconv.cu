@@ -21,7 +21,7 @@
 namespace tpg {
 
 constexpr int kRcMaxSlots = 16;
-constexpr int kRowConvThreads = 384;   // warps 4..11 are the epilogue (two per TMEM lane quarter, alternating 16-column groups)
+constexpr int kRowConvThreads = kConvThreads;   // warps 4..11 are the epilogue (two per TMEM lane quarter, alternating 16-column groups)
 
 __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __grid_constant__ RowConvParams P, int* status) {
   extern __shared__ uint8_t smem_raw[];
@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
       if (!mbar_wait(&tfull_bar[buf], tph, ac, 26)) break;
       tc_fence_after();
       const int col_base = nt * P.block_n;
+      const EpiArgs E{P.bias, P.slopes, P.cout_valid, P.epilogue, P.round_tf32, P.vec_ok, P.slope};
       for (int t = 0; t < T; ++t) {
         const int y = rt * T + t;
         const bool valid = (y < P.H) && (x < P.W);
@@ -199,77 +200,11 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
         const float* p2 = P.add2.ptr ? P.add2.ptr + (long long)n * P.add2.sn + (long long)y * P.add2.sh + (long long)x * P.add2.sw : nullptr;
         const float* pm = P.mask.ptr ? P.mask.ptr + (long long)n * P.mask.sn + (long long)y * P.mask.sh + (long long)x * P.mask.sw : nullptr;
         const uint32_t t_addr = tmem_base + (uint32_t)(buf * 256 + t * P.block_n) + ((uint32_t)(q * 32) << 16);
-        for (int c0 = ((warp - 4) >> 2) * 16; c0 < P.block_n; c0 += 32) {
+        for (int c0 = ((warp - 4) >> 2) * 16; c0 < P.block_n; c0 += 16 * kEpiPerQuarter) {
           uint32_t r[16];
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const int col = col_base + c0 + j;
-              const int nv = P.cout_valid - col;
-              if (nv <= 0) break;
-              float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                            __uint_as_float(r[j + 3])};
-              const bool vec = P.vec_ok && nv >= 4;
-              if (P.bias) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (i < nv) v[i] += __ldg(P.bias + col + i);
-              }
-              if (p1) {
-                if (vec) {
-                  float4 a = *reinterpret_cast<const float4*>(p1 + col);
-                  v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (i < nv) v[i] += p1[col + i];
-                }
-              }
-              if (p2) {
-                if (vec) {
-                  float4 a = *reinterpret_cast<const float4*>(p2 + col);
-                  v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (i < nv) v[i] += p2[col + i];
-                }
-              }
-              if (P.epilogue == 1) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * P.slope;
-              } else if (P.epilogue == 2) {
-                float m[4] = {1.f, 1.f, 1.f, 1.f};
-                if (vec) {
-                  float4 a = *reinterpret_cast<const float4*>(pm + col);
-                  m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (i < nv) m[i] = pm[col + i];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float s = P.slope;
-                  if (P.slopes && i < nv) s = __ldg(P.slopes + col + i);
-                  v[i] = m[i] > 0.f ? v[i] : v[i] * s;
-                }
-              }
-              if (P.round_tf32) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = round_tf32(v[i]);
-              }
-              if (vec) {
-                *reinterpret_cast<float4*>(po + col) = make_float4(v[0], v[1], v[2], v[3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (i < nv) po[col + i] = v[i];
-              }
-            }
-          }
+          if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm);
         }
       }
       tc_fence_before();

@@ -23,7 +23,7 @@ constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
 // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue (two warps per TMEM lane quarter, each
 // taking every other 16-column group - the epilogue is latency-bound on its addend/mask loads, not on TMEM reads)
-constexpr int kTapGemmThreads = 384;
+constexpr int kTapGemmThreads = kConvThreads;
 
 struct TileCoord {
   int gi, ph, h0, n0, nt;
@@ -222,77 +222,12 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
       const float* pm = G.mask.ptr ? G.mask.ptr + (long long)n * G.mask.sn + (long long)yo * G.mask.sh + (long long)xo * G.mask.sw : nullptr;
       const uint32_t t_addr = tmem_base + (uint32_t)(as * kAccCols) + ((uint32_t)(q * 32) << 16);
       const int col_base = tc.nt * G.block_n;
-      for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 32) {
+      const EpiArgs E{G.bias, G.slopes, G.cout_valid, G.epilogue, G.round_tf32, G.vec_ok, G.slope};
+      for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 16 * kEpiPerQuarter) {
         uint32_t r[16];
         tmem_ld16(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const int col = col_base + c0 + j;
-            const int nv = G.cout_valid - col;
-            if (nv <= 0) break;
-            float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                          __uint_as_float(r[j + 3])};
-            const bool vec = G.vec_ok && nv >= 4;
-            if (G.bias) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i < nv) v[i] += __ldg(G.bias + col + i);
-            }
-            if (p1) {
-              if (vec) {
-                float4 a = *reinterpret_cast<const float4*>(p1 + col);
-                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (i < nv) v[i] += p1[col + i];
-              }
-            }
-            if (p2) {
-              if (vec) {
-                float4 a = *reinterpret_cast<const float4*>(p2 + col);
-                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (i < nv) v[i] += p2[col + i];
-              }
-            }
-            if (G.epilogue == 1) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * G.slope;
-            } else if (G.epilogue == 2) {
-              float m[4] = {1.f, 1.f, 1.f, 1.f};
-              if (vec) {
-                float4 a = *reinterpret_cast<const float4*>(pm + col);
-                m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (i < nv) m[i] = pm[col + i];
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float s = G.slope;
-                if (G.slopes && i < nv) s = __ldg(G.slopes + col + i);
-                v[i] = m[i] > 0.f ? v[i] : v[i] * s;
-              }
-            }
-            if (G.round_tf32) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) v[i] = round_tf32(v[i]);
-            }
-            if (vec) {
-              *reinterpret_cast<float4*>(po + col) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i < nv) po[col + i] = v[i];
-            }
-          }
-        }
+        if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm);
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);

@@ -20,7 +20,7 @@ namespace tpg {
 
 constexpr int kWTmemCols = 512;
 constexpr int kWAccCols = 256;
-constexpr int kWgradThreads = 384;   // warps 4..11 are the epilogue (two per TMEM lane quarter, alternating 16-column groups)
+constexpr int kWgradThreads = kConvThreads;   // warps 4..11 are the epilogue (two per TMEM lane quarter, alternating 16-column groups)
 
 // Balanced ("stream-K") schedule.  The reduction of every group is cut into K blocks (pixel ranges sized so that the
 // activations of one block stay in L2); the work of one K block is the list of (output tile, pixel chunk) pairs,
@@ -319,26 +319,26 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
         for (int mi = 0; mi < nm; ++mi) {
           const int m = (u.mg * G.mpu + mi) * 128 + row;
           const bool mvalid = m < G.m_valid;
-          for (int i = 0; i < G.ncpt; ++i)
-            for (int t = 0; t < ntap; ++t) {
-              const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + ((mi * G.ncpt + i) * G.tpu + t) * 32) +
-                                      ((uint32_t)(q * 32) << 16);
-              const TapDesc tap = G.taps[tap0 + t];
-              {
-                const int h = (warp - 4) >> 2;
-                uint32_t r[16];
-                tmem_ld16(t_addr + (uint32_t)(h * 16), r);
-                tmem_ld_wait();
-                if (mvalid && i * 32 + h * 16 < G.n_valid) store16(r, tap, m, i * 32 + h * 16);
-              }
-            }
+          // 16-column blocks (chunk i, tap t, half h) of this M tile, round-robin over the warps of the quarter
+          const int nblk = G.ncpt * ntap * 2;
+          for (int blk = (warp - 4) >> 2; blk < nblk; blk += kEpiPerQuarter) {
+            const int h = blk & 1;
+            const int t = (blk >> 1) % ntap;
+            const int i = (blk >> 1) / ntap;
+            const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + ((mi * G.ncpt + i) * G.tpu + t) * 32 + h * 16) +
+                                    ((uint32_t)(q * 32) << 16);
+            uint32_t r[16];
+            tmem_ld16(t_addr, r);
+            tmem_ld_wait();
+            if (mvalid && i * 32 + h * 16 < G.n_valid) store16(r, G.taps[tap0 + t], m, i * 32 + h * 16);
+          }
         }
       } else
       for (int mi = 0; mi < nm; ++mi) {
         const int m = (u.mg * G.mpu + mi) * 128 + row;
         const bool mvalid = m < G.m_valid;
         const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + mi * G.block_n) + ((uint32_t)(q * 32) << 16);
-        for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 32) {
+        for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 16 * kEpiPerQuarter) {
           uint32_t r[16];
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
