@@ -26,6 +26,7 @@ __global__ void tapgemm_kernel(const __grid_constant__ Params P, int* status);
 template <class Params>
 __global__ void wgrad_kernel(const __grid_constant__ Params P, int* status);
 __global__ void rowconv_kernel(const __grid_constant__ RowConvParams P, int* status);
+__global__ void rowstack_kernel(const __grid_constant__ RowStackParams P, int* status);
 
 // ------------------------------------------------------------------------------------------------ error state
 static thread_local char g_err[512] = "";
@@ -84,10 +85,11 @@ int device_sm_count() { return g_dev.sm_count; }
 // ------------------------------------------------------------------------------------------------ TMA descriptors
 // 4D NHWC plane: dims {C, W, H, N}; step = parity-plane subsampling factor along H and W.
 static int encode_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int N, long long sw, long long sh,
-                       long long sn, int bw, int bh, int bn, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                       long long sn, int bw, int bh, int bn, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+                       int bc = 32) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
     return set_error(TPGAN_ERR_INVALID, "TMA operand must be 16-byte aligned (ptr %p, strides %lld %lld %lld elements)",
@@ -103,14 +105,15 @@ static int encode_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, i
   return 0;
 }
 
-static int encode_weights(CUtensorMap* m, const float* base, int k_pad, int rows_pad, int taps, int block_n) {
+static int encode_weights(CUtensorMap* m, const float* base, int k_pad, int rows_pad, int taps, int block_n,
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int bc = 32) {
   cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)rows_pad, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)k_pad * 4, (cuuint64_t)k_pad * rows_pad * 4};
-  cuuint32_t box[3] = {32, (cuuint32_t)block_n, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bc, (cuuint32_t)block_n, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   if ((uintptr_t)base & 15) return set_error(TPGAN_ERR_INVALID, "packed weights must be 16-byte aligned");
   CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(TPGAN_ERR_CUDA, "cuTensorMapEncodeTiled(weights k=%d rows=%d taps=%d bn=%d) failed: %d", k_pad,
@@ -377,6 +380,78 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
   rowconv_kernel<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowconv launch: %s", cudaGetErrorString(e)); return 1; }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ N-stacked row-tile conv
+// Eligible: as try_rowconv, with at most 128 (padded) output channels so that at least two output rows share an MMA.
+static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
+  *rc_out = 0;
+  static const bool disabled = getenv("TPGAN_NO_ROWSTACK") != nullptr;
+  if (disabled) return 0;
+  if (a.kind != TPGAN_CONV_FWD && a.kind != TPGAN_CONV_DGRAD) return 0;
+  const int k = a.kh, p = a.pad;
+  if (a.kh != a.kw || a.stride != 1 || 2 * p != k - 1 || k < 3 || k * k > kMaxTaps) return 0;
+  if (a.in.w != 128 || a.out.w != 128 || a.in.h != a.out.h || a.in.n != a.out.n) return 0;
+  if (a.w_rows_pad > 128) return 0;
+  static thread_local RowStackParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = a.out.h; P.W = 128; P.Nimg = a.in.n; P.k = k;
+  P.block_n = ceil_div(a.w_rows_pad, 16) * 16;
+  int T = std::max(1, std::min(4, 256 / P.block_n));
+  T = std::max(1, std::min(T, P.H));
+  if (const char* ev = getenv("TPGAN_ROWSTACK_T")) T = std::max(1, std::min(atoi(ev), 256 / P.block_n));
+  if (T < 2) return 0;
+  P.T = T;
+  P.row_tiles = ceil_div(P.H, T);
+  P.total_tiles = P.Nimg * P.row_tiles;
+  P.kchunks = ceil_div(a.in.c, 16);
+  P.last_mmas = ceil_div(a.in.c - 16 * (P.kchunks - 1), 8);
+  const bool fwd = a.kind == TPGAN_CONV_FWD;
+  P.dy0 = fwd ? -p : p - k + 1;
+  P.dx0 = P.dy0;
+  for (int r = 0; r < k; ++r)
+    for (int j = 0; j < k; ++j)
+      P.wtap[r * k + j] = (unsigned char)(fwd ? (r * k + j) : ((k - 1 - r) * k + (k - 1 - j)));
+  for (int s = 0; s < T + k - 1; ++s) {
+    const int t_lo = std::max(0, s - k + 1), t_hi = std::min(T - 1, s);
+    const int nn = (t_hi - t_lo + 1) * P.block_n;
+    // kind::tf32 instruction descriptor, M = 128, N = nn, K-major A and B (make_idesc_tf32 in common.cuh)
+    P.s_idesc[s] = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    P.s_boff[s] = (uint32_t)(k - 1 - (s - t_lo)) * (uint32_t)P.block_n * 4u;
+    P.s_doff[s] = (uint32_t)(t_lo * P.block_n);
+  }
+  P.slab_bytes = ceil_div((128 + k - 1) * 64, 1024) * 1024;
+  P.wb_bytes = k * P.block_n * 64;
+  const int budget = g_dev.max_smem - 1024 - 1024;   // alignment slack + this kernel's static shared memory
+  const int nslab = T + k - 1;
+  P.b_slots = 3;
+  P.a_slots = std::min(16, (budget - P.b_slots * P.wb_bytes) / P.slab_bytes);
+  if (P.a_slots < nslab + 1) {
+    P.b_slots = 2;
+    P.a_slots = std::min(16, (budget - P.b_slots * P.wb_bytes) / P.slab_bytes);
+    if (P.a_slots < nslab) return 0;
+  }
+  P.a_slots = std::min(P.a_slots, nslab + 4);
+  if (nslab > 16) return 0;
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_64B;
+  int rc = encode_nhwc(&P.amap, a.in.ptr, a.in.c, a.in.w, a.in.h, a.in.n, a.in.sw, a.in.sh, a.in.sn, 128 + k - 1, 1, 1, swz, 16);
+  if (rc) { *rc_out = rc; return 1; }
+  rc = encode_weights(&P.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, k * k + 1, P.block_n, swz, 16);
+  if (rc) { *rc_out = rc; return 1; }
+  P.out = to_dev(a.out); P.add1 = to_dev(a.add1); P.add2 = to_dev(a.add2); P.mask = to_dev(a.mask);
+  P.bias = a.bias; P.slopes = a.slopes;
+  P.cout_valid = a.out.c; P.epilogue = a.epilogue; P.slope = a.slope; P.round_tf32 = a.round_tf32;
+  if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) { *rc_out = set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view"); return 1; }
+  P.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask);
+  const int smem = P.a_slots * P.slab_bytes + P.b_slots * P.wb_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(rowstack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
+  if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+  const int grid = std::min(P.total_tiles, g_dev.sm_count);
+  rowstack_kernel<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowstack launch: %s", cudaGetErrorString(e)); return 1; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 1;
 }
@@ -659,6 +734,7 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ngroups == 1) {
     int rrc = 0;
+    if (try_rowstack(groups[0], st, &rrc)) return rrc;
     if (try_rowconv(groups[0], st, &rrc)) return rrc;
     static thread_local TapGemmParams1 P;
     P.ngroups = 1;

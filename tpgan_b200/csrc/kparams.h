@@ -98,6 +98,27 @@ struct RowConvParams {
   float slope;
 };
 
+// ---------------------------------------------------------------- row-tile convolution, N-stacked vertical taps (N <= 128)
+struct RowStackParams {
+  CUtensorMap amap;        // 4D {C, W, H, N} fp32, box {16, W + k - 1, 1, 1}, 64B swizzle (an input-row slab, 16 channels)
+  CUtensorMap bmap;        // 3D {k_pad, rows_pad, taps+1}, box {16, block_n, 1}, 64B swizzle
+  int H, W, Nimg, T, k;    // T output rows per tile (T * block_n <= 256 TMEM columns, double-buffered)
+  int dy0, dx0;            // input pixel of grid tap (0,0) relative to the output pixel
+  int kchunks, last_mmas;  // 16-channel K chunks; K = 8 MMAs in the last one (1 or 2)
+  int block_n, row_tiles, total_tiles;
+  int a_slots, b_slots, slab_bytes, wb_bytes;
+  unsigned char wtap[kMaxTaps];   // weight tap slice for grid position r*k + j
+  // per input-row slab s of a tile (it feeds output rows t_lo(s) .. t_hi(s)): instruction descriptor with
+  // N' = (t_hi - t_lo + 1) * block_n, offset of vertical tap r = s - t_lo inside the weight stack (16 B units), first
+  // accumulator column t_lo * block_n
+  uint32_t s_idesc[16], s_boff[16], s_doff[16];
+  DevView out, add1, add2, mask;
+  const float* bias;
+  const float* slopes;
+  int cout_valid, epilogue, round_tf32, vec_ok;
+  float slope;
+};
+
 // ---------------------------------------------------------------- weight-gradient GEMM
 // D[m = channel of P][n = channel of Q] (per tap) = sum over pixels P[pix, m] * Qtap[pix, n]
 struct WgradGroup {

@@ -210,25 +210,32 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
         const int kgroups = G.kp / 8;
         const int nm = min(G.mpu, G.m_tiles - u.mg * G.mpu);   // M tiles (accumulators) of this unit
         const int c_begin = u.c_begin, c_end = u.c_end;
+        // slab mode constants of this segment (hoisted: the issuing thread is the critical resource)
+        const int s_ntap = G.slab ? slab_group_ntap(G, u.tg * G.tpu) : 0;
+        const uint32_t idesc_s = make_idesc_tf32(128, s_ntap * 32, 1, 1);
+        const uint32_t qchunk16 = (uint32_t)G.q_chunk_bytes >> 4;
+        const int s_ncpt = G.ncpt;
+        const uint32_t s_dstep = (uint32_t)(G.tpu * 32);
+        const bool is_slab = G.slab != 0;
         uint32_t acc = 0;
         for (int c = c_begin; c < c_end; ++c) {
           if (!mbar_wait_a(fb, phase, ac, 13)) { ok = false; break; }
           tc_fence_after();
           const uint32_t b_lo = (sbase16 + areg16) | lbo_field;
-          if (G.slab) {
+          if (is_slab) {
             // one MMA per 32-channel Q chunk covers all taps of the group: the N dimension walks the taps with a leading
             // byte offset of ONE pixel row (128 B) through the same slab (im2col by descriptor), D columns = [tap][32 ch]
-            const int ntap = slab_group_ntap(G, u.tg * G.tpu);
-            const uint32_t idesc_s = make_idesc_tf32(128, ntap * 32, 1, 1);
-            const uint32_t qchunk16 = (uint32_t)G.q_chunk_bytes >> 4;
             const uint32_t bs_lo = (sbase16 + areg16) | (8u << 16);
+            uint32_t d = d_tmem;
             for (int mi = 0; mi < nm; ++mi) {
               const uint32_t a_lo = (sbase16 + (uint32_t)mi * 4u * chunk16) | lbo_field;
-              for (int i = 0; i < G.ncpt; ++i) {
-                const uint32_t d = d_tmem + (uint32_t)(((mi * G.ncpt + i) * G.tpu) * 32);
-                const uint32_t bi_lo = bs_lo + (uint32_t)i * qchunk16;
-                for (int k = 0; k < kgroups; ++k)
-                  mma_tf32_ss(d, desc_join(a_lo + 64 * k, dhi), desc_join(bi_lo + 64 * k, dhi), idesc_s, k ? 1u : acc);
+              uint32_t bi_lo = bs_lo;
+              for (int i = 0; i < s_ncpt; ++i) {
+                mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(bi_lo, dhi), idesc_s, acc);
+                for (int k = 1; k < kgroups; ++k)
+                  mma_tf32_ss(d, desc_join(a_lo + 64 * k, dhi), desc_join(bi_lo + 64 * k, dhi), idesc_s, 1);
+                d += s_dstep;
+                bi_lo += qchunk16;
               }
             }
           } else if (nm == 1 && kgroups == 8) {
