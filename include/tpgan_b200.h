@@ -120,7 +120,10 @@ typedef struct tpgan_bias_job {   /* db[c] += sum over npix pixels of dy[pix*sw 
   const float* dy;
   float* db;
   int64_t npix, sw;
-  int32_t c, block_begin, pix_blocks, cgroups; /* cgroups = ceil(c / 128) */
+  int32_t c, block_begin, pix_blocks, cgroups; /* cgroups = ceil(c / (4 * lanes)) */
+  int32_t lanes;                  /* lanes of a warp that share one pixel (power of two <= 32, 4 channels each); the
+                                     other 32 / lanes sub-groups of the warp take further pixels */
+  int32_t pad_;
 } tpgan_bias_job;
 typedef struct tpgan_pack_job {   /* row-contiguous (un)pack, see tpgan_pack_weights; blocks = rows_pad (pack) / rows */
   const float* ref_c;             /* reference tensor (read when packing)  */

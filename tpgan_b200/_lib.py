@@ -37,7 +37,8 @@ class WgradArgs(C.Structure):
 
 class BiasJob(C.Structure):
     _fields_ = [("dy", C.c_void_p), ("db", C.c_void_p), ("npix", C.c_int64), ("sw", C.c_int64), ("c", C.c_int32),
-                ("block_begin", C.c_int32), ("pix_blocks", C.c_int32), ("cgroups", C.c_int32)]
+                ("block_begin", C.c_int32), ("pix_blocks", C.c_int32), ("cgroups", C.c_int32), ("lanes", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 class PackJob(C.Structure):

@@ -739,30 +739,37 @@ __global__ void __launch_bounds__(256) bias_grad_multi_kernel(const tpgan_bias_j
   const int local = (int)blockIdx.x - J.block_begin;
   const int cg = local % J.cgroups, pb = local / J.cgroups;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int c = (cg * 32 + lane) * 4;
+  // `lanes` lanes cover the (up to 4 * lanes) channels of one pixel; the 32 / lanes sub-groups of a warp take different
+  // pixels, so narrow tensors (64, 3 channels) keep every lane loading 16 B
+  const int lpp = J.lanes, ppw = 32 / lpp;
+  const int sub = lane / lpp, cl = lane - sub * lpp;
+  const int c = (cg * lpp + cl) * 4;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < J.c) {
     const float* base = J.dy + c;
-    const long long stride = (long long)J.pix_blocks * 8;
-    long long pix = (long long)pb * 8 + wp;
-    for (; pix + 3 * stride < J.npix; pix += 4 * stride) {
-      const float4 v0 = *reinterpret_cast<const float4*>(base + pix * J.sw);
-      const float4 v1 = *reinterpret_cast<const float4*>(base + (pix + stride) * J.sw);
-      const float4 v2 = *reinterpret_cast<const float4*>(base + (pix + 2 * stride) * J.sw);
-      const float4 v3 = *reinterpret_cast<const float4*>(base + (pix + 3 * stride) * J.sw);
-      a.x += (v0.x + v1.x) + (v2.x + v3.x);
-      a.y += (v0.y + v1.y) + (v2.y + v3.y);
-      a.z += (v0.z + v1.z) + (v2.z + v3.z);
-      a.w += (v0.w + v1.w) + (v2.w + v3.w);
+    const long long stride = (long long)J.pix_blocks * 8 * ppw;
+    long long pix = ((long long)pb * 8 + wp) * ppw + sub;
+    for (; pix + 7 * stride < J.npix; pix += 8 * stride) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(base + (pix + i * stride) * J.sw);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w; }
     }
     for (; pix < J.npix; pix += stride) {
       const float4 v = *reinterpret_cast<const float4*>(base + pix * J.sw);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
   }
+  for (int o = lpp; o < 32; o <<= 1) {   // fold the pixel sub-groups of the warp
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+    a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+    a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+  }
   red[wp][lane] = a;
   __syncthreads();
-  if (wp == 0 && c < J.c) {
+  if (wp == 0 && lane < lpp && c < J.c) {
     float4 s = red[0][lane];
 #pragma unroll
     for (int i = 1; i < 8; ++i) { s.x += red[i][lane].x; s.y += red[i][lane].y; s.z += red[i][lane].z; s.w += red[i][lane].w; }

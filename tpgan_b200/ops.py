@@ -358,7 +358,13 @@ def bias_job(g: Act, db: torch.Tensor) -> "_lib.BiasJob":
     v = g.view()
     assert v.sh == v.w * v.sw and v.sn == v.h * v.sh and v.sw % 4 == 0 and v.ptr % 16 == 0, "bias job needs a dense view"
     npix = v.n * v.h * v.w
-    return _lib.BiasJob(v.ptr, db.data_ptr(), npix, v.sw, v.c, 0, max(1, min((npix + 31) // 32, 1184)), (v.c + 127) // 128)
+    lanes = 1
+    while lanes < 32 and lanes * 4 < v.c:
+        lanes *= 2
+    ppb = 8 * (32 // lanes)                      # pixels one 8-warp block takes per sweep
+    # ~64 sweeps per block (8 loads of 16 B in flight per lane), at most two waves of blocks per tensor
+    pix_blocks = max(1, min((npix + 64 * ppb - 1) // (64 * ppb), 296))
+    return _lib.BiasJob(v.ptr, db.data_ptr(), npix, v.sw, v.c, 0, pix_blocks, (v.c + 4 * lanes - 1) // (4 * lanes), lanes, 0)
 
 
 def pack_job(ref: torch.Tensor, packed: Packed, taps: int, row_len: int, row_map, k_map, flag: int) -> "_lib.PackJob":
