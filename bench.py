@@ -213,7 +213,9 @@ def run_b200(a):
                     s.record()
                     f()
                     e.record()
-                    ev.append((f.kind, f.flops, s, e, f.label))
+                    # conv launches: ask the library which kernel it actually routed the call to
+                    kind = f.kind if f.kind == "wgrad" else _lib.last_conv_kernel()
+                    ev.append((kind, f.flops, s, e, f.label))
                 else:
                     f()
         tr.stage_inputs(devb)
@@ -236,7 +238,8 @@ def run_b200(a):
         peaks, which = _peaks()
         tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
         names = {"tapgemm": "tapgemm_kernel (tcgen05 tf32 multi-tap implicit-GEMM conv fwd/dgrad/deconv/linear)",
-                 "rowconv": "rowconv_kernel (tcgen05 tf32 row-tile conv for the 128x128 stride-1 layers, fwd/dgrad)",
+                 "rowconv": "rowconv_kernel (tcgen05 tf32 row-tile conv for the wide 128x128 stride-1 layers, fwd/dgrad)",
+                 "rowstack": "rowstack_kernel (tcgen05 tf32 N-stacked row-tile conv for the narrow 128x128 layers, fwd/dgrad)",
                  "wgrad": "wgrad_kernel (tcgen05 tf32 weight-gradient GEMM over pixels)"}
         step_ms = ms / a.steps
 

@@ -236,6 +236,9 @@ TPGAN_API int tpgan_abi_version(void);
 TPGAN_API int tpgan_kernel_status(void);
 /* Number of kernels launched by this library since load (monotonic; bench.py reports the delta). */
 TPGAN_API int64_t tpgan_launch_count(void);
+/* Which tensor-core kernel the calling thread's most recent tpgan_conv2d launched (profiling / bench attribution):
+ * 0 = tapgemm_kernel, 1 = rowconv_kernel, 2 = rowstack_kernel. */
+TPGAN_API int tpgan_last_conv_kernel(void);
 
 #ifdef __cplusplus
 }

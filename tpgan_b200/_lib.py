@@ -101,6 +101,7 @@ SYMBOLS = {
     "tpgan_abi_version": (C.c_int, []),
     "tpgan_kernel_status": (C.c_int, []),
     "tpgan_launch_count": (C.c_int64, []),
+    "tpgan_last_conv_kernel": (C.c_int, []),
 }
 
 
@@ -130,6 +131,11 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(load().tpgan_launch_count())
+
+
+def last_conv_kernel() -> str:
+    """Which kernel the most recent conv2d call of this thread launched."""
+    return ("tapgemm", "rowconv", "rowstack")[int(load().tpgan_last_conv_kernel())]
 
 
 def kernel_status() -> int:

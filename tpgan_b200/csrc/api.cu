@@ -725,6 +725,8 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
 
 using namespace tpg;
 
+static thread_local int g_last_conv_kernel = 0;
+
 extern "C" {
 
 int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
@@ -734,8 +736,11 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ngroups == 1) {
     int rrc = 0;
+    g_last_conv_kernel = 2;
     if (try_rowstack(groups[0], st, &rrc)) return rrc;
+    g_last_conv_kernel = 1;
     if (try_rowconv(groups[0], st, &rrc)) return rrc;
+    g_last_conv_kernel = 0;
     static thread_local TapGemmParams1 P;
     P.ngroups = 1;
     rc = plan_group(groups[0], P.g[0]);
@@ -747,6 +752,7 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     }
     return launch_tapgemm(P, st);
   }
+  g_last_conv_kernel = 0;
   static thread_local TapGemmParams P;
   P.ngroups = ngroups;
   for (int i = 0; i < ngroups; ++i) {
@@ -811,5 +817,6 @@ int tpgan_kernel_status(void) {
   return v;
 }
 int64_t tpgan_launch_count(void) { return (int64_t)g_launches.load(); }
+int tpgan_last_conv_kernel(void) { return g_last_conv_kernel; }
 
 }  // extern "C"
