@@ -527,7 +527,8 @@ static WgradChoice wgrad_option(const tpgan_wgrad_args& a, bool swap, bool slab)
     c.ncpt = c.block_n / 32;
     // several M tiles per unit (one accumulator each), all sharing the loads of Q - when the reduction is long enough
     // (>= 32768 pixels) to amortise the then single-buffered epilogue
-    c.mpu = (no_pack || npix < 32768) ? 1 : std::max(1, std::min(c.m_tiles, 512 / c.block_n));
+    static const long long mpu_min_pix = getenv("TPGAN_WGRAD_MPU_MINPIX") ? atoll(getenv("TPGAN_WGRAD_MPU_MINPIX")) : 32768;
+    c.mpu = (no_pack || npix < mpu_min_pix) ? 1 : std::max(1, std::min(c.m_tiles, 512 / c.block_n));
     c.a_ch = std::min(4 * c.mpu, ceil_div(c.pc, 32));
     c.b_ch = c.ncpt;
   }
@@ -707,6 +708,9 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
   const int budget = g_dev.max_smem - 1024 - 256 - slack;
   P.stages = std::min(kMaxStages, budget / stage_bytes);
   P.ring_bytes = P.stages * stage_bytes + slack;
+  P.need_zero = 0;
+  for (int i = 0; i < P.ngroups; ++i)
+    if ((P.g[i].bw * P.g[i].bh * P.g[i].bn) % 8) P.need_zero = 1;
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "wgrad: not enough shared memory for 2 stages (%d B/stage)", stage_bytes);
   const int smem = P.ring_bytes + 1024;
   auto kern = wgrad_kernel<Params>;

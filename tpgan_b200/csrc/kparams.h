@@ -156,6 +156,7 @@ struct WgradParams {
   int stages;
   int a_stage_bytes, b_stage_bytes;
   int ring_bytes;                // stages * (a + b) + slack read (never written) by M = 128 MMAs over narrow P tensors
+  int need_zero;                 // some group's pixel box leaves K rows unwritten: zero the ring first
   int nbuf;
   WgradGroup g[kMaxGroups];
 };
@@ -165,6 +166,7 @@ struct WgradParams1 {
   int stages;
   int a_stage_bytes, b_stage_bytes;
   int ring_bytes;
+  int need_zero;
   int nbuf;
   WgradGroup g[1];
 };

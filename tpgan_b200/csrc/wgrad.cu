@@ -90,9 +90,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
   const uint32_t stage_bytes = (uint32_t)(P.a_stage_bytes + P.b_stage_bytes);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  // Zero the whole ring once: K rows beyond a box (pixel count not a multiple of 8) and channel chunks that are
-  // never loaded must read as finite values for the lifetime of the kernel.
-  {
+  // Zero the whole ring once when some box does not fill its K rows (pixel count not a multiple of 8): those rows must
+  // read as zeros for the lifetime of the kernel.  (M rows / N columns beyond the loaded channel chunks may hold anything:
+  // they only reach accumulator rows / columns that are never stored.)
+  if (P.need_zero) {
     uint4* p = reinterpret_cast<uint4*>(smem);
     const int n16 = P.ring_bytes / 16;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
