@@ -257,3 +257,27 @@ def test_cuda_graph_replay_matches_eager():
         # (a wrong device-side Adam step count or a stale packed weight would show as O(1) deviations; the slack only has to
         # absorb the chaotic amplification of summation-order noise over four sign-like Adam steps)
         assert abs(traj[0][0][k] - traj[2][0][k]) <= 10 * noise + 1e-2 * abs(traj[0][0][k]) + 5e-3, (k, traj[0][0][k], traj[2][0][k])
+
+
+def test_prefetched_inputs_match_direct_copies():
+    """step(b, prefetch_next=b2) stages b2's host->device copies on a side stream; the next step(b2) must see exactly the
+    same inputs as a plain step(b2) (same losses, fixed weights), also when batches alternate."""
+    from oracle import step as ostep
+    from tpgan_b200.train_step import TPGANTrainer
+    B = 2
+    keys = TPGANTrainer.INPUT_KEYS
+    b1 = {k: v.contiguous().pin_memory() for k, v in ostep.make_batch(B, seed=11).items() if k in keys}
+    b2 = {k: v.contiguous().pin_memory() for k, v in ostep.make_batch(B, seed=12).items() if k in keys}
+    G, D, _, _ = _models(False)
+    tr = TPGANTrainer(G, D, B, use_graphs=True)
+    ref1 = [tr.step(b1, optimize=False) for _ in range(3)][-1]      # warm-up, capture, replay
+    ref2 = tr.step(b2, optimize=False)
+    tr.prefetch(b1)
+    m1 = tr.step(b1, optimize=False, prefetch_next=b2)
+    m2 = tr.step(b2, optimize=False, prefetch_next=b1)
+    m1b = tr.step(b1, optimize=False)
+    for k in ref1:
+        assert abs(m1[k] - ref1[k]) <= 1e-5 * abs(ref1[k]) + 1e-7, (k, m1[k], ref1[k])
+        assert abs(m2[k] - ref2[k]) <= 1e-5 * abs(ref2[k]) + 1e-7, (k, m2[k], ref2[k])
+        assert abs(m1b[k] - ref1[k]) <= 1e-5 * abs(ref1[k]) + 1e-7, (k, m1b[k], ref1[k])
+    assert abs(ref1["pixel"] - ref2["pixel"]) > 1e-4   # the two batches really differ

@@ -487,6 +487,7 @@ class TPGANTrainer:
                                          float(self.w["weight_identity_preserving"]), self.sums[13:15], self.device, exact=exact)
         self._d_logits = torch.zeros_like(self.critic.logits.buf[:2 * B])
         self.inp: Optional[Dict[str, torch.Tensor]] = None
+        self._pf_stream = self._pf_event = self._pf_bufs = self._pf_batch = self._pf_picked = None
         self.inp_has_mask = self.fixed_mask = False
         self._sched: Dict[tuple, object] = {}
         if self.mask is not None:
@@ -534,14 +535,38 @@ class TPGANTrainer:
     # ---- inputs: copied into static device buffers so that every pointer of the schedule is fixed
     INPUT_KEYS = ("img", "img_frontal", "img64_frontal", "img32_frontal", "landmarks", "z", "label", "gp_alpha")
 
+    def prefetch(self, b: Dict[str, torch.Tensor]):
+        """Start the host->device copies of a FUTURE batch on a side stream (pinned host tensors), so they overlap the step
+        that is running; a later step(b) with the same dict object picks the staged copies up with device-to-device copies."""
+        if self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream(device=self.device)
+            self._pf_event = torch.cuda.Event()
+            self._pf_bufs = {k: torch.empty_like(b[k], device=self.device).contiguous() for k in self.INPUT_KEYS}
+        if self._pf_picked is not None:
+            self._pf_stream.wait_event(self._pf_picked)   # the staging buffers are free once the last pick-up has run
+        with torch.cuda.stream(self._pf_stream):
+            for k in self.INPUT_KEYS:
+                self._pf_bufs[k].copy_(b[k], non_blocking=True)
+            self._pf_event.record(self._pf_stream)
+        self._pf_batch = b
+
     def load_inputs(self, b: Dict[str, torch.Tensor]):
         if self.inp is None:
             self.inp = {k: torch.empty_like(b[k], device=self.device).contiguous() for k in self.INPUT_KEYS}
             if self.mask is not None:
                 self.inp["dropout_mask"] = torch.ones_like(self.mask.buf)
-        for k in self.INPUT_KEYS:
-            if b[k] is not self.inp[k]:
-                self.inp[k].copy_(b[k], non_blocking=True)
+        if b is self._pf_batch:     # staged by prefetch(): wait for the side stream, then device-to-device
+            torch.cuda.current_stream(self.device).wait_event(self._pf_event)
+            for k in self.INPUT_KEYS:
+                self.inp[k].copy_(self._pf_bufs[k], non_blocking=True)
+            if self._pf_picked is None:
+                self._pf_picked = torch.cuda.Event()
+            self._pf_picked.record(torch.cuda.current_stream(self.device))
+            self._pf_batch = None
+        else:
+            for k in self.INPUT_KEYS:
+                if b[k] is not self.inp[k]:
+                    self.inp[k].copy_(b[k], non_blocking=True)
         self.inp_has_mask = "dropout_mask" in b
         if self.inp_has_mask:
             self.inp["dropout_mask"].copy_(b["dropout_mask"].reshape(self.mask.buf.shape))
@@ -625,8 +650,11 @@ class TPGANTrainer:
             sch.append(self.g_set.repack)
         return sch
 
-    def step(self, b: Dict[str, torch.Tensor], optimize: bool = True, read_metrics: bool = True):
-        """One G+D training step.  With use_graphs the schedule is captured into CUDA graphs on first use and replayed."""
+    def step(self, b: Dict[str, torch.Tensor], optimize: bool = True, read_metrics: bool = True,
+             prefetch_next: Optional[Dict[str, torch.Tensor]] = None):
+        """One G+D training step.  With use_graphs the schedule is captured into CUDA graphs on first use and replayed.
+        prefetch_next: the batch of the NEXT step (pinned host tensors); its host->device copies are started on a side
+        stream as soon as this step's launches are enqueued (see prefetch())."""
         self.load_inputs(b)
         self.fixed_mask = self.inp_has_mask
         key = (optimize, self.fixed_mask)
@@ -639,6 +667,8 @@ class TPGANTrainer:
         else:
             for f in sch:
                 f()
+        if prefetch_next is not None:
+            self.prefetch(prefetch_next)
         return self.read_metrics() if read_metrics else None
 
     def _allreduce(self, t: torch.Tensor):
