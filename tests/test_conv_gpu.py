@@ -252,3 +252,64 @@ def test_grouped_local_pathway_shapes():
     torch.cuda.synchronize()
     for o, r in zip(outs, refs):
         assert rel(o.to_nchw(), r) < TOL
+
+
+# ---- full-size (BASELINE config 1, batch 32) size-independent property: the three kernels of a layer are adjoint.
+#   <conv(x, w), dy> = <x, dgrad(dy, w)> = <w, wgrad(x, dy)>
+# With tf32-representable x, w, dy every product is exact in the tensor cores, so the three inner products differ only
+# by fp32 accumulation order and by the tf32 rounding of the stored conv / dgrad outputs (relative 2^-11 per element,
+# averaging out over the sum): 1e-3 relative to the norm bound ||y||*||dy|| is generous and still catches a single
+# mis-routed tap, tile, channel chunk or K block.  Shapes: SURVEY.md T1 (rowconv / rowstack / tapgemm / wgrad plain,
+# slab and swapped modes at their production sizes).
+ADJOINT_CASES = [
+    # cin, cout, k, stride, pad, H=W
+    (206, 206, 5, 1, 2, 128),
+    (75, 75, 7, 1, 3, 128),
+    (64, 64, 7, 1, 3, 128),
+    (206, 64, 5, 1, 2, 128),
+    (3, 64, 7, 1, 3, 128),
+    (64, 3, 3, 1, 1, 128),
+    (64, 64, 5, 2, 2, 128),
+    (208, 208, 3, 1, 1, 64),
+    (416, 416, 3, 1, 1, 32),
+    (768, 768, 3, 1, 1, 16),
+    (512, 512, 3, 1, 1, 8),
+]
+
+
+@pytest.mark.parametrize("case", ADJOINT_CASES)
+def test_full_size_adjoint_identities(case):
+    from oracle.model_port import tf32_rna
+    from tpgan_b200 import ops
+    cin, cout, k, s, p, H = case
+    B = 32
+    Ho = (H + 2 * p - k) // s + 1
+    g = torch.Generator(device="cuda").manual_seed(123)
+
+    def rnd(*shape, scale=1.0):
+        return tf32_rna((torch.rand(*shape, device="cuda", generator=g) * 2 - 1) * scale)
+    x = ops.Act.empty(B, H, H, cin)
+    x.buf.copy_(rnd(*x.buf.shape))
+    dy = ops.Act.empty(B, Ho, Ho, cout)
+    dy.buf.copy_(rnd(*dy.buf.shape))
+    if cin % 4:
+        x.buf[..., cin:] = 0
+    if cout % 4:
+        dy.buf[..., cout:] = 0
+    w = rnd(cout, cin, k, k, scale=0.05)
+    y, dx = ops.Act.empty(B, Ho, Ho, cout), ops.Act.empty(B, H, H, cin)
+    wf, wd = ops.pack_weights(w, ops.CONV_FWD), ops.pack_weights(w, ops.CONV_DGRAD)
+    dw = ops.alloc_packed(ops.CONV_FWD, tuple(w.shape))
+    ops.conv2d(ops.CONV_FWD, x, y, wf, k, s, p, round_tf32=False)
+    ops.conv2d(ops.CONV_DGRAD, dy, dx, wd, k, s, p, round_tf32=False)
+    ops.wgrad(ops.CONV_FWD, x, dy, dw, k, s, p, accumulate=False)
+    dwr = torch.zeros_like(w)
+    ops.unpack_weights(dw, dwr, ops.CONV_FWD)
+    torch.cuda.synchronize()
+    dot = lambda a, b: float((a.double() * b.double()).sum())
+    a1 = dot(y.buf[..., :cout], dy.buf[..., :cout])
+    a2 = dot(x.buf[..., :cin], dx.buf[..., :cin])
+    a3 = dot(w, dwr)
+    bound = float(y.buf[..., :cout].double().norm() * dy.buf[..., :cout].double().norm())
+    assert abs(a1 - a2) <= 1e-3 * bound and abs(a1 - a3) <= 1e-3 * bound, (a1, a2, a3, bound)
+    assert abs(a1) > 0 and bound > 0
