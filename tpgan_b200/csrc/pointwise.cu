@@ -382,6 +382,69 @@ __global__ void local_fuse_kernel(FuseIn in, V out, uint8_t* __restrict__ argmax
     if (argmax) argmax[i] = (uint8_t)arg;
   }
 }
+// Vectorised variants (C % 4 == 0, 16-byte aligned views - the 64-channel feature stitch): one thread = one pixel x four
+// channels; float4 loads / stores, uchar4 arg-max, index math by shifts (the output is always 128 x 128).
+__global__ void local_fuse_vec4_kernel(FuseIn in, V out, uint8_t* __restrict__ argmax) {
+  const int c4n = out.c >> 2;
+  const long long total = (long long)out.n * 16384 * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    const long long pix = i / c4n;
+    const int x = (int)(pix & 127), y = (int)((pix >> 7) & 127), n = (int)(pix >> 14);
+    float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 arg = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = x - kFuseRect[k][0], py = y - kFuseRect[k][1];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (px >= 0 && px < kFuseRect[k][2] && py >= 0 && py < kFuseRect[k][3])
+        v = *reinterpret_cast<const float4*>(in.v[k].p + voff(in.v[k], n, py, px) + c);
+      if (k == 0) {
+        best = v;
+      } else {   // strict > : the first maximal index of the stack [LE, RE, N, M] wins, as torch.max
+        if (v.x > best.x) { best.x = v.x; arg.x = (unsigned char)k; }
+        if (v.y > best.y) { best.y = v.y; arg.y = (unsigned char)k; }
+        if (v.z > best.z) { best.z = v.z; arg.z = (unsigned char)k; }
+        if (v.w > best.w) { best.w = v.w; arg.w = (unsigned char)k; }
+      }
+    }
+    *reinterpret_cast<float4*>(out.p + voff(out, n, y, x) + c) = best;
+    if (argmax) *reinterpret_cast<uchar4*>(argmax + pix * out.c + c) = arg;
+  }
+}
+__global__ void local_fuse_backward_vec4_kernel(V dout, const uint8_t* __restrict__ argmax, FuseIn din, int accumulate) {
+  const int c4n = dout.c >> 2;
+  long long sizes[4], total = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sizes[k] = (long long)din.v[k].n * din.v[k].h * din.v[k].w * c4n;
+    total += sizes[k];
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i;
+    int k = 0;
+    while (j >= sizes[k]) { j -= sizes[k]; ++k; }
+    const V& d = din.v[k];
+    const int c = (int)(j % c4n) * 4;
+    long long r = j / c4n;
+    const int px = (int)(r % d.w);
+    r /= d.w;
+    const int py = (int)(r % d.h);
+    const int n = (int)(r / d.h);
+    const int x = px + kFuseRect[k][0], y = py + kFuseRect[k][1];
+    const long long oi = ((((long long)n << 14) + (y << 7) + x)) * dout.c + c;
+    const uchar4 a = *reinterpret_cast<const uchar4*>(argmax + oi);
+    const float4 go = *reinterpret_cast<const float4*>(dout.p + voff(dout, n, y, x) + c);
+    float4 g = make_float4(a.x == k ? go.x : 0.f, a.y == k ? go.y : 0.f, a.z == k ? go.z : 0.f, a.w == k ? go.w : 0.f);
+    float4* dst = reinterpret_cast<float4*>(d.p + voff(d, n, py, px) + c);
+    if (accumulate) {
+      const float4 o = *dst;
+      g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+    }
+    *dst = g;
+  }
+}
+
 __global__ void local_fuse_backward_kernel(V dout, const uint8_t* __restrict__ argmax, FuseIn din, int accumulate) {
   long long sizes[4], total = 0;
 #pragma unroll
@@ -572,6 +635,36 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
     v[i] = vi;
     float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = pi - lr1 * (mi / denom);
+  }
+}
+// float4 variant (all four arrays 16-byte aligned, n % 4 == 0: the flat parameter buffers): 112 B per thread iteration
+__global__ void adam_dev_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                     float4* __restrict__ v, long long n4, float lr, float b1, float b2, float eps, float wd,
+                                     const int* __restrict__ step, float gscale) {
+  const float t = (float)(*step);
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float lr1 = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = g[i];
+    float4 p4 = p[i], m4 = m[i], v4 = v[i];
+    float* pp = reinterpret_cast<float*>(&p4);
+    float* mm = reinterpret_cast<float*>(&m4);
+    float* vv = reinterpret_cast<float*>(&v4);
+    const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gi = gg[j] * gscale;
+      if (wd != 0.f) gi += wd * pp[j];
+      const float mi = b1 * mm[j] + (1.f - b1) * gi;
+      const float vi = b2 * vv[j] + (1.f - b2) * gi * gi;
+      mm[j] = mi;
+      vv[j] = vi;
+      pp[j] = pp[j] - lr1 * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+    p[i] = p4;
+    m[i] = m4;
+    v[i] = v4;
   }
 }
 __global__ void counter_inc_kernel(int* c) { *c += 1; }
@@ -928,6 +1021,9 @@ __global__ void avgpool_backward_kernel(V dy, V dx, int accumulate) {
   }
 }
 
+static bool view_vec4_ok(const tpgan_view& v) {
+  return (((uintptr_t)v.ptr & 15) == 0) && v.sn % 4 == 0 && v.sh % 4 == 0 && v.sw % 4 == 0;
+}
 static bool same_geom(const tpgan_view& a, const tpgan_view& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
@@ -1085,7 +1181,12 @@ int tpgan_local_fuse(tpgan_view left_eye, tpgan_view right_eye, tpgan_view nose,
   }
   if (out.h != 128 || out.w != 128) return set_error(TPGAN_ERR_INVALID, "local_fuse: output must be 128x128");
   long long total = (long long)out.n * out.h * out.w * out.c;
-  local_fuse_kernel<<<grid_for(total, 256), 256, 0, ST>>>(fi, dv(out), argmax);
+  bool vec = (out.c % 4 == 0) && view_vec4_ok(out) && (((uintptr_t)argmax & 3) == 0);
+  for (int i = 0; i < 4; ++i) vec = vec && view_vec4_ok(*in[i]);
+  if (vec)
+    local_fuse_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, ST>>>(fi, dv(out), argmax);
+  else
+    local_fuse_kernel<<<grid_for(total, 256), 256, 0, ST>>>(fi, dv(out), argmax);
   TPG_CHECK_LAUNCH("local_fuse");
   return 0;
 }
@@ -1102,7 +1203,12 @@ int tpgan_local_fuse_backward(tpgan_view dout, const uint8_t* argmax, tpgan_view
     total += (long long)in[i]->n * in[i]->h * in[i]->w * in[i]->c;
   }
   if (!argmax) return set_error(TPGAN_ERR_INVALID, "local_fuse_backward: argmax NULL");
-  local_fuse_backward_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(dout), argmax, fi, accumulate);
+  bool vec = (dout.c % 4 == 0) && view_vec4_ok(dout) && (((uintptr_t)argmax & 3) == 0) && dout.h == 128 && dout.w == 128;
+  for (int i = 0; i < 4; ++i) vec = vec && view_vec4_ok(*in[i]);
+  if (vec)
+    local_fuse_backward_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, ST>>>(dv(dout), argmax, fi, accumulate);
+  else
+    local_fuse_backward_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(dout), argmax, fi, accumulate);
   TPG_CHECK_LAUNCH("local_fuse_backward");
   return 0;
 }
@@ -1215,8 +1321,14 @@ int tpgan_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n,
   if (!p || !g || !m || !v || !step_dev || n <= 0) return set_error(TPGAN_ERR_INVALID, "adam_step_dev: bad args");
   counter_inc_kernel<<<1, 1, 0, ST>>>(step_dev);
   TPG_CHECK_LAUNCH("counter_inc");
-  adam_dev_kernel<<<grid_for(n, 256, 16), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev,
-                                                        grad_scale);
+  const bool vec = (n % 4 == 0) && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  if (vec)
+    adam_dev_vec4_kernel<<<grid_for(n / 4, 256, 16), 256, 0, ST>>>(
+        reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+        reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale);
+  else
+    adam_dev_kernel<<<grid_for(n, 256, 16), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev,
+                                                          grad_scale);
   TPG_CHECK_LAUNCH("adam_step_dev");
   return 0;
 }
