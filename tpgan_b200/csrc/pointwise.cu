@@ -72,48 +72,84 @@ __global__ void unpack_kernel(const float* __restrict__ packed, float* __restric
 // ---- fast (un)packing for the row-contiguous case (ref_k_stride == taps): one block per packed row, the reference row
 // (k_ref x taps contiguous floats) staged through shared memory so that both the global read and the global write are
 // coalesced.  Used after every optimizer step (pack) and after every backward (unpack) for all 172 conv layers.
-__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ ref, float* __restrict__ packed, int taps,
-                                                        int rows, int k, int rows_pad, int k_pad, long long rs, int row_len,
-                                                        const int* __restrict__ row_map, const int* __restrict__ k_map,
-                                                        int round) {
+// Row staging in shared memory is indexed [k][tap]; the pack / unpack phases read it with consecutive k per thread, i.e.
+// with a stride of `taps` floats - a 32-way bank conflict for taps = 64 (fc1's 8x8 window), 4-way for taps = 4.  An odd
+// stride (taps | 1) makes it conflict-free; the linear phase maps i -> (i / taps) * stride + i % taps.
+__device__ __forceinline__ int srow_index(int i, int taps, int tstride) {
+  if (tstride == taps) return i;
+  const int q = i / taps;
+  return q * tstride + (i - q * taps);
+}
+
+__global__ void __launch_bounds__(1024) pack_rows_kernel(const float* __restrict__ ref, float* __restrict__ packed, int taps,
+                                                         int rows, int k, int rows_pad, int k_pad, long long rs, int row_len,
+                                                         const int* __restrict__ row_map, const int* __restrict__ k_map,
+                                                         int round) {
   extern __shared__ float srow[];
   const int r = blockIdx.x;
+  const int tstride = taps | 1;
   const int rref = (r < rows) ? (row_map ? row_map[r] : r) : -1;
   if (rref >= 0) {
     const float* src = ref + (long long)rref * rs;
-    for (int i = threadIdx.x; i < row_len; i += blockDim.x) srow[i] = src[i];
-  }
-  __syncthreads();
-  for (int t = 0; t <= taps; ++t) {
-    float* dst = packed + ((long long)t * rows_pad + r) * k_pad;
-    for (int kk = threadIdx.x; kk < k_pad; kk += blockDim.x) {
-      float v = 0.f;
-      if (t < taps && rref >= 0 && kk < k) {
-        const int kref = k_map ? k_map[kk] : kk;
-        if (kref >= 0) v = srow[kref * taps + t];
+    if ((row_len & 3) == 0 && (rs & 3) == 0 && (((uintptr_t)ref) & 15) == 0) {   // 16-byte loads of the reference row
+      for (int i = threadIdx.x * 4; i < row_len; i += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        srow[srow_index(i, taps, tstride)] = v.x;
+        srow[srow_index(i + 1, taps, tstride)] = v.y;
+        srow[srow_index(i + 2, taps, tstride)] = v.z;
+        srow[srow_index(i + 3, taps, tstride)] = v.w;
       }
-      dst[kk] = (round == 1) ? round_tf32(v) : ((round == 2) ? (v - round_tf32(v)) : v);
+    } else {
+      for (int i = threadIdx.x; i < row_len; i += blockDim.x) srow[srow_index(i, taps, tstride)] = src[i];
     }
   }
+  __syncthreads();
+  auto cvt = [&](float v) { return (round == 1) ? round_tf32(v) : ((round == 2) ? (v - round_tf32(v)) : v); };
+  // (tap, 4 consecutive k) per thread iteration: one 16-byte store
+  const int kq = k_pad >> 2;
+  for (int idx = threadIdx.x; idx < (taps + 1) * kq; idx += blockDim.x) {
+    const int t = idx / kq, kk = (idx - t * kq) * 4;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t < taps && rref >= 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kk + j < k) {
+          const int kref = k_map ? k_map[kk + j] : kk + j;
+          if (kref >= 0) o[j] = srow[kref * tstride + t];
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(packed + ((long long)t * rows_pad + r) * k_pad + kk) = make_float4(cvt(o[0]), cvt(o[1]), cvt(o[2]), cvt(o[3]));
+  }
 }
-__global__ void __launch_bounds__(256) unpack_rows_kernel(const float* __restrict__ packed, float* __restrict__ ref, int taps,
-                                                          int rows, int k, int rows_pad, int k_pad, long long rs, int row_len,
-                                                          const int* __restrict__ row_map, const int* __restrict__ k_map,
-                                                          int accumulate) {
+__global__ void __launch_bounds__(1024) unpack_rows_kernel(const float* __restrict__ packed, float* __restrict__ ref, int taps,
+                                                           int rows, int k, int rows_pad, int k_pad, long long rs, int row_len,
+                                                           const int* __restrict__ row_map, const int* __restrict__ k_map,
+                                                           int accumulate) {
   extern __shared__ float srow[];
   const int r = blockIdx.x;
+  const int tstride = taps | 1;
   const int rref = row_map ? row_map[r] : r;
   if (rref < 0) return;
-  for (int t = 0; t < taps; ++t) {
-    const float* src = packed + ((long long)t * rows_pad + r) * k_pad;
-    for (int kk = threadIdx.x; kk < k; kk += blockDim.x) {
-      const int kref = k_map ? k_map[kk] : kk;
-      if (kref >= 0) srow[kref * taps + t] = src[kk];
+  const int kq = k_pad >> 2;
+  for (int idx = threadIdx.x; idx < taps * kq; idx += blockDim.x) {
+    const int t = idx / kq, kk = (idx - t * kq) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(packed + ((long long)t * rows_pad + r) * k_pad + kk);
+    const float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (kk + j < k) {
+        const int kref = k_map ? k_map[kk + j] : kk + j;
+        if (kref >= 0) srow[kref * tstride + t] = o[j];
+      }
     }
   }
   __syncthreads();
   float* dst = ref + (long long)rref * rs;
-  for (int i = threadIdx.x; i < row_len; i += blockDim.x) dst[i] = accumulate ? (dst[i] + srow[i]) : srow[i];
+  for (int i = threadIdx.x; i < row_len; i += blockDim.x) {
+    const float v = srow[srow_index(i, taps, tstride)];
+    dst[i] = accumulate ? (dst[i] + v) : v;
+  }
 }
 // dst[t][kk][r] = src[t][r][kk] for r < rows, kk < k (per-tap transpose between the forward and the dgrad packing)
 __global__ void transpose_packed_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int k,
@@ -880,11 +916,12 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tpgan_pack_job* _
   const tpgan_pack_job J = jobs[ji];
   const int r = (int)blockIdx.x - J.block_begin;
   const int taps = J.taps;
+  const int tstride = taps | 1;
   if (mode == 0) {
     const int rref = (r < J.rows) ? (J.row_map ? J.row_map[r] : r) : -1;
     if (rref >= 0) {
       const float* src = J.ref_c + (long long)rref * J.rs;
-      for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) srow[i] = src[i];
+      for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) srow[srow_index(i, taps, tstride)] = src[i];
     }
     __syncthreads();
     for (int t = 0; t <= taps; ++t) {
@@ -893,7 +930,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tpgan_pack_job* _
         float v = 0.f;
         if (t < taps && rref >= 0 && kk < J.k) {
           const int kref = J.k_map ? J.k_map[kk] : kk;
-          if (kref >= 0) v = srow[kref * taps + t];
+          if (kref >= 0) v = srow[kref * tstride + t];
         }
         dst[kk] = (J.flag == 1) ? round_tf32(v) : ((J.flag == 2) ? (v - round_tf32(v)) : v);
       }
@@ -906,12 +943,15 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const tpgan_pack_job* _
       const float* src = J.packed + ((long long)t * J.rows_pad + r) * J.k_pad;
       for (int kk = threadIdx.x; kk < J.k; kk += blockDim.x) {
         const int kref = J.k_map ? J.k_map[kk] : kk;
-        if (kref >= 0) srow[kref * taps + t] = src[kk];
+        if (kref >= 0) srow[kref * tstride + t] = src[kk];
       }
     }
     __syncthreads();
     float* dst = J.ref + (long long)rref * J.rs;
-    for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) dst[i] = J.flag ? (dst[i] + srow[i]) : srow[i];
+    for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) {
+      const float v = srow[srow_index(i, taps, tstride)];
+      dst[i] = J.flag ? (dst[i] + v) : v;
+    }
   }
 }
 
@@ -1039,7 +1079,7 @@ int tpgan_pack_weights(const float* ref, float* packed, int32_t taps, int32_t ro
                        int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
                        const int32_t* k_map, int32_t round_tf32, void* stream) {
   if (!ref || !packed || taps < 1 || rows > rows_pad || k > k_pad) return set_error(TPGAN_ERR_INVALID, "pack: bad args");
-  if (ref_k_stride == taps && ref_row_stride % taps == 0 && ref_row_stride * 4 <= 192 * 1024) {
+  if (ref_k_stride == taps && ref_row_stride % taps == 0 && (ref_row_stride / taps) * (taps | 1) * 4 <= 192 * 1024) {
     const int row_len = (int)ref_row_stride;   // k_ref * taps contiguous floats per reference row
     static bool attr_set = false;
     if (!attr_set) {
@@ -1047,7 +1087,7 @@ int tpgan_pack_weights(const float* ref, float* packed, int32_t taps, int32_t ro
       cudaFuncSetAttribute(unpack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
       attr_set = true;
     }
-    pack_rows_kernel<<<rows_pad, 256, (size_t)row_len * 4, ST>>>(ref, packed, taps, rows, k, rows_pad, k_pad, ref_row_stride,
+    pack_rows_kernel<<<rows_pad, 1024, (size_t)((row_len / taps) * (taps | 1) + row_len % taps) * 4, ST>>>(ref, packed, taps, rows, k, rows_pad, k_pad, ref_row_stride,
                                                                 row_len, row_map, k_map, round_tf32);
     TPG_CHECK_LAUNCH("pack_weights");
     return 0;
@@ -1062,7 +1102,7 @@ int tpgan_unpack_weights(const float* packed, float* ref, int32_t taps, int32_t 
                          int32_t k_pad, int64_t ref_row_stride, int64_t ref_k_stride, const int32_t* row_map,
                          const int32_t* k_map, int32_t accumulate, void* stream) {
   if (!ref || !packed || taps < 1 || rows > rows_pad || k > k_pad) return set_error(TPGAN_ERR_INVALID, "unpack: bad args");
-  if (ref_k_stride == taps && ref_row_stride % taps == 0 && ref_row_stride * 4 <= 192 * 1024) {
+  if (ref_k_stride == taps && ref_row_stride % taps == 0 && (ref_row_stride / taps) * (taps | 1) * 4 <= 192 * 1024) {
     const int row_len = (int)ref_row_stride;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1070,7 +1110,7 @@ int tpgan_unpack_weights(const float* packed, float* ref, int32_t taps, int32_t 
       cudaFuncSetAttribute(unpack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
       attr_set = true;
     }
-    unpack_rows_kernel<<<rows, 256, (size_t)row_len * 4, ST>>>(packed, ref, taps, rows, k, rows_pad, k_pad, ref_row_stride,
+    unpack_rows_kernel<<<rows, 1024, (size_t)((row_len / taps) * (taps | 1) + row_len % taps) * 4, ST>>>(packed, ref, taps, rows, k, rows_pad, k_pad, ref_row_stride,
                                                               row_len, row_map, k_map, accumulate);
     TPG_CHECK_LAUNCH("unpack_weights");
     return 0;

@@ -335,7 +335,8 @@ class JobTable:
                 self.blocks += j.pix_blocks * j.cgroups
             elif kind == "pack":
                 self.blocks += j.rows if unpack else j.rows_pad
-                self.max_row = max(self.max_row, j.row_len)
+                # shared-memory floats of one staged row: [k][tap] with an odd tap stride (pack_multi_kernel)
+                self.max_row = max(self.max_row, j.row_len // j.taps * (j.taps | 1) + j.row_len % j.taps)
             else:
                 self.blocks += j.taps * j.tiles_r * j.tiles_k
         arr = (type(jobs[0]) * len(jobs))(*jobs)
