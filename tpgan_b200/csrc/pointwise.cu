@@ -910,47 +910,79 @@ __global__ void __launch_bounds__(256) bias_grad_multi_kernel(const tpgan_bias_j
 }
 
 // mode 0: pack rows (ref -> packed), mode 1: unpack rows (packed -> ref, accumulate per job flag)
-__global__ void __launch_bounds__(256) pack_multi_kernel(const tpgan_pack_job* __restrict__ jobs, int njobs, int mode) {
+__global__ void __launch_bounds__(512) pack_multi_kernel(const tpgan_pack_job* __restrict__ jobs, int njobs, int mode) {
   extern __shared__ float srow[];
   const int ji = find_job(jobs, njobs, (int)blockIdx.x);
   const tpgan_pack_job J = jobs[ji];
   const int r = (int)blockIdx.x - J.block_begin;
   const int taps = J.taps;
   const int tstride = taps | 1;
+  const int kq = J.k_pad >> 2;          // k_pad is a multiple of 32: (tap, 4 consecutive k) per thread = 16-byte accesses
   if (mode == 0) {
     const int rref = (r < J.rows) ? (J.row_map ? J.row_map[r] : r) : -1;
     if (rref >= 0) {
       const float* src = J.ref_c + (long long)rref * J.rs;
-      for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) srow[srow_index(i, taps, tstride)] = src[i];
+      if ((J.row_len & 3) == 0 && (J.rs & 3) == 0 && (((uintptr_t)J.ref_c) & 15) == 0) {
+        for (int i = threadIdx.x * 4; i < J.row_len; i += blockDim.x * 4) {
+          const float4 v = *reinterpret_cast<const float4*>(src + i);
+          srow[srow_index(i, taps, tstride)] = v.x;
+          srow[srow_index(i + 1, taps, tstride)] = v.y;
+          srow[srow_index(i + 2, taps, tstride)] = v.z;
+          srow[srow_index(i + 3, taps, tstride)] = v.w;
+        }
+      } else {
+        for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) srow[srow_index(i, taps, tstride)] = src[i];
+      }
     }
     __syncthreads();
-    for (int t = 0; t <= taps; ++t) {
-      float* dst = J.packed + ((long long)t * J.rows_pad + r) * J.k_pad;
-      for (int kk = threadIdx.x; kk < J.k_pad; kk += blockDim.x) {
-        float v = 0.f;
-        if (t < taps && rref >= 0 && kk < J.k) {
-          const int kref = J.k_map ? J.k_map[kk] : kk;
-          if (kref >= 0) v = srow[kref * tstride + t];
+    auto cvt = [&](float v) { return (J.flag == 1) ? round_tf32(v) : ((J.flag == 2) ? (v - round_tf32(v)) : v); };
+    for (int idx = threadIdx.x; idx < (taps + 1) * kq; idx += blockDim.x) {
+      const int t = idx / kq, kk = (idx - t * kq) * 4;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (t < taps && rref >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (kk + j < J.k) {
+            const int kref = J.k_map ? J.k_map[kk + j] : kk + j;
+            if (kref >= 0) o[j] = srow[kref * tstride + t];
+          }
         }
-        dst[kk] = (J.flag == 1) ? round_tf32(v) : ((J.flag == 2) ? (v - round_tf32(v)) : v);
       }
+      *reinterpret_cast<float4*>(J.packed + ((long long)t * J.rows_pad + r) * J.k_pad + kk) =
+          make_float4(cvt(o[0]), cvt(o[1]), cvt(o[2]), cvt(o[3]));
     }
   } else {
     if (r >= J.rows) return;
     const int rref = J.row_map ? J.row_map[r] : r;
     if (rref < 0) return;
-    for (int t = 0; t < taps; ++t) {
-      const float* src = J.packed + ((long long)t * J.rows_pad + r) * J.k_pad;
-      for (int kk = threadIdx.x; kk < J.k; kk += blockDim.x) {
-        const int kref = J.k_map ? J.k_map[kk] : kk;
-        if (kref >= 0) srow[kref * tstride + t] = src[kk];
+    for (int idx = threadIdx.x; idx < taps * kq; idx += blockDim.x) {
+      const int t = idx / kq, kk = (idx - t * kq) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(J.packed + ((long long)t * J.rows_pad + r) * J.k_pad + kk);
+      const float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kk + j < J.k) {
+          const int kref = J.k_map ? J.k_map[kk + j] : kk + j;
+          if (kref >= 0) srow[kref * tstride + t] = o[j];
+        }
       }
     }
     __syncthreads();
     float* dst = J.ref + (long long)rref * J.rs;
-    for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) {
-      const float v = srow[srow_index(i, taps, tstride)];
-      dst[i] = J.flag ? (dst[i] + v) : v;
+    if ((J.row_len & 3) == 0 && (J.rs & 3) == 0 && (((uintptr_t)J.ref) & 15) == 0 && tstride == taps) {
+      for (int i = threadIdx.x * 4; i < J.row_len; i += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(srow + i);
+        if (J.flag) {
+          const float4 d = *reinterpret_cast<const float4*>(dst + i);
+          v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+        }
+        *reinterpret_cast<float4*>(dst + i) = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < J.row_len; i += blockDim.x) {
+        const float v = srow[srow_index(i, taps, tstride)];
+        dst[i] = J.flag ? (dst[i] + v) : v;
+      }
     }
   }
 }
@@ -1399,7 +1431,7 @@ int tpgan_pack_multi(const tpgan_pack_job* jobs_dev, int32_t njobs, int32_t tota
     cudaFuncSetAttribute(pack_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
     attr_set = true;
   }
-  pack_multi_kernel<<<total_blocks, 256, (size_t)max_row_len * 4, ST>>>(jobs_dev, njobs, unpack ? 1 : 0);
+  pack_multi_kernel<<<total_blocks, 512, (size_t)max_row_len * 4, ST>>>(jobs_dev, njobs, unpack ? 1 : 0);
   TPG_CHECK_LAUNCH("pack_multi");
   return 0;
 }
