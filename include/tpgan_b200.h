@@ -229,6 +229,54 @@ TPGAN_API int tpgan_fill(tpgan_view out, float value, void* stream);
 TPGAN_API int tpgan_softmax_ce(const float* logits, int64_t row_stride, const int64_t* labels, float* dlogits,
                                int64_t drow_stride, int32_t rows, int32_t cols, float coeff, float* loss_sum, void* stream);
 
+
+/* ---- Pretrain path: MobileNetV2 + SSDHead + MultiTaskLoss, MobileNetV2.py:10-534 --------------------- */
+
+/* nn.Conv2d(C, C, 3, stride, 1, groups=C, bias=False) - the depthwise layer of InvertedResidual (MobileNetV2.py:110) -
+ * forward, input gradient and weight gradient.  w / dw are the reference tensors (C,1,3,3) themselves (no packing);
+ * dw is accumulated with atomics (clear it per step).  C % 4 == 0, stride 1 or 2. */
+TPGAN_API int tpgan_dwconv3x3(tpgan_view x, tpgan_view y, const float* w, int32_t stride, void* stream);
+TPGAN_API int tpgan_dwconv3x3_dgrad(tpgan_view dy, tpgan_view dx, const float* w, int32_t stride, int32_t accumulate,
+                                    void* stream);
+TPGAN_API int tpgan_dwconv3x3_wgrad(tpgan_view x, tpgan_view dy, float* dw, int32_t stride, void* stream);
+
+/* nn.BatchNorm2d (+ nn.ReLU6, + the residual add of InvertedResidual.forward, MobileNetV2.py:107-120,150-170) over a
+ * pixel-dense NHWC view.  training != 0: batch statistics (sums = caller-owned double[2*C] scratch that must stay intact
+ * until the matching backward), running_mean / running_var updated in place with `momentum` and the unbiased variance;
+ * training == 0: running statistics.  coef = caller-owned float[4*C] (scale, shift, mean, invstd) consumed by the backward.
+ * y = x*scale + shift (+ res) -> ReLU6 if relu6 -> tf32 rounding if round_tf32 (operand of a tensor-core conv). */
+TPGAN_API int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps, int32_t training,
+                               int32_t relu6, int32_t round_tf32, double* sums, float* coef, void* stream);
+/* dz = dy * [0 < y < 6] (if relu6); training: dx (+)= scale*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum dz*xhat,
+ * dbeta = sum dz (overwritten; may be NULL); eval: dx (+)= scale*dz.  dsums = double[2*C] scratch. */
+TPGAN_API int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* coef, int32_t training, int32_t relu6,
+                                int32_t accumulate, int32_t round_tf32, double* dsums, float* dgamma, float* dbeta,
+                                void* stream);
+
+/* SSDHead.forward (MobileNetV2.py:62-76): the NHWC head output (N,h,w,A*K) already is permute(0,2,3,1); view(N,-1,K) and
+ * torch.cat(dim=1) are a copy of each image's h*w*A*K floats to `offset` of its concatenated row (row_stride floats).
+ * reverse != 0 copies the other way (backward of the cat). */
+TPGAN_API int tpgan_rows_gather(tpgan_view v, float* flat, int64_t row_stride, int64_t offset, int32_t reverse, void* stream);
+
+/* MultiTaskLoss (MobileNetV2.py:342-534), batched: per sample, distances of the n predicted points to the 4 ground-truth
+ * points, per-label threshold = k_near-th smallest distance, positives = dist <= threshold, label = nearest such ground
+ * truth (first wins), location MSE on clamp(./[W,H],0,1) per label, cross-entropy per label + background (class 4) with
+ * at most ratio_non_background * positives background points (the ones with the smallest keys u - the explicit form of
+ * the reference's torch.multinomial draw); sample loss = alpha*loc + beta*cls; sums[0..2] += coeff*(total, loc, cls);
+ * loc_stride / cls_stride = floats between consecutive samples of loc, dloc / cls, dcls (>= 2n / 5n);
+ * dloc / dcls = coeff * d(sample loss)/d(.) ; labels[B][n] = assignment (-1 background) for the bit-exact check. */
+TPGAN_API int tpgan_multitask_loss(const float* loc, const float* cls, const float* truth, const float* u, int32_t batch,
+                                   int32_t n, int64_t loc_stride, int64_t cls_stride, int32_t num_classes, int32_t k_near, float img_w, float img_h, float alpha,
+                                   float beta, float ratio_non_background, float coeff, float* dloc, float* dcls,
+                                   int32_t* labels, float* sums, void* stream);
+
+/* torch.optim.SGD(momentum, weight_decay, nesterov) over a flat fp32 bucket (getOptimizer 'SGD', UtilityMethods.py:30,
+ * config.py:31-35); buf must start zeroed; the learning rate is read from device memory (MultiStepLR, Pretrain.py:117-121,
+ * without re-capturing a CUDA graph). */
+TPGAN_API int tpgan_sgd_step(float* p, const float* g, float* buf, int64_t n, const float* lr_dev, float momentum,
+                             float weight_decay, int32_t nesterov, float grad_scale, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------------- */
 TPGAN_API const char* tpgan_last_error(void);
 TPGAN_API int tpgan_abi_version(void);

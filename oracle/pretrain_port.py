@@ -1,0 +1,246 @@
+"""ORACLE (test infrastructure, never shipped on the product path): the Pretrain path.
+
+CPU / plain-PyTorch fp32 restatement of
+  * `MobileNetV2` + `SSDHead` + `InvertedResidual`          (MobileNetV2.py:10-250),
+  * `MultiTaskLoss`                                         (MobileNetV2.py:342-534),
+  * the Pretrain optimisation step                          (Pretrain.py:159-181, UtilityMethods.py:14-41,
+                                                             config.py:29-35: SGD lr 5e-4, momentum 0.9, nesterov,
+                                                             weight decay 5e-4).
+It can travel to the GPU box (the reference tree cannot).  PINNED:
+  * the network is bit-exact against the live reference with a shared state_dict
+    (tests/test_pretrain_cpu.py::test_port_matches_live_reference) and against golden vectors recorded from it
+    (tools/make_golden_pretrain.py -> tests/golden/pretrain_golden.pt),
+  * the loss reproduces the reference's only known answer, Temp.py:8-29 -> 0.8939134478569031
+    (test_multitask_loss_known_answer) and the live `MultiTaskLoss` on random inputs
+    (test_multitask_loss_matches_live_reference).
+
+Two things are ORACLE-DEFINED because the reference leaves them open (stated in DESIGN.md):
+  1. batch > 1.  The reference loss is written for batch_size = 1 (config.py:12; `[0]` indexing at MobileNetV2.py:407,
+     465,498).  The batched loss here is the reference's per-sample loss averaged over the batch.
+  2. background sub-sampling.  The reference draws `torch.multinomial(background.float(), m)` (MobileNetV2.py:505):
+     m background points, uniformly, without replacement.  Here the draw is an explicit input: per-point uniform keys
+     `u` (B, n); the m background points with the smallest keys are kept (ties -> lower index).  For i.i.d. keys that is
+     the same distribution, and it makes the step reproducible across implementations.
+
+Distances: `torch.cdist` switches to a matmul formula above 25 points (ATen `_euclidean_dist`), whose rounding depends on
+the BLAS in use.  The port computes sqrt(fl(fl(dx*dx) + fl(dy*dy))) in fp32 for every n - identical to ATen's direct
+path (n <= 25, e.g. the Temp.py known answer) and within 2 ulp of the matmul path; an assignment can only differ from
+the live reference at an exact near-tie of two distances (the live-reference test draws seeds where none occurs).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+# MobileNetV2.py:138-147 (t, c, n, s)
+SETTING = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2], [6, 320, 1, 1]]
+HEAD_IN = [96, 1280, 512, 256, 256, 128]      # MobileNetV2.py:28-44
+HEAD_ANCHORS = [4, 6, 6, 6, 6, 6]
+NUM_CLASSES = 5                                # 4 landmarks + background (MobileNetV2.py:177)
+ALPHA, BETA, RATIO, RATIO_NON_BACKGROUND = 30.0, 0.1, 0.1, 5.0   # config.py:25-27, MobileNetV2.py:343
+SGD = dict(lr=5e-4, momentum=0.9, nesterov=True, weight_decay=5e-4)  # config.py:31-35
+
+
+class InvertedResidualPort(nn.Module):
+    """MobileNetV2.py:81-120."""
+
+    def __init__(self, inp, oup, stride, expand_ratio):
+        super().__init__()
+        self.use_res_connect = stride == 1 and inp == oup
+        hid = inp * expand_ratio
+        self.conv = nn.Sequential(
+            nn.Conv2d(inp, hid, 1, 1, 0, bias=False), nn.BatchNorm2d(hid), nn.ReLU6(inplace=True),
+            nn.Conv2d(hid, hid, 3, stride, 1, groups=hid, bias=False), nn.BatchNorm2d(hid), nn.ReLU6(inplace=True),
+            nn.Conv2d(hid, oup, 1, 1, 0, bias=False), nn.BatchNorm2d(oup))
+
+    def forward(self, x):
+        return x + self.conv(x) if self.use_res_connect else self.conv(x)
+
+
+class SSDHeadPort(nn.Module):
+    """MobileNetV2.py:10-79."""
+
+    def __init__(self, num_classes=NUM_CLASSES):
+        super().__init__()
+        self.num_of_out_classes, self.num_of_out_location = num_classes, 2
+        self.location_layer = nn.ModuleList(nn.Conv2d(c, a * 2, 3, padding=1) for c, a in zip(HEAD_IN, HEAD_ANCHORS))
+        self.classification_layer = nn.ModuleList(nn.Conv2d(c, a * num_classes, 3, padding=1)
+                                                  for c, a in zip(HEAD_IN, HEAD_ANCHORS))
+
+    def forward(self, features):
+        locs, clss = [], []
+        for i, x in enumerate(features):
+            l = self.location_layer[i](x).permute(0, 2, 3, 1).contiguous()
+            locs.append(torch.relu(l.view(l.size(0), -1, 2)))                      # :63-67
+            c = self.classification_layer[i](x).permute(0, 2, 3, 1).contiguous()
+            clss.append(c.view(c.size(0), -1, self.num_of_out_classes))            # :70-72
+        return torch.cat(locs, 1), torch.cat(clss, 1)
+
+
+class MobileNetV2Port(nn.Module):
+    """MobileNetV2.py:122-250; same attribute names => same state_dict keys as the reference class."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv2d(3, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU6(inplace=True))
+        cin = 32
+        self.bottlenecks = nn.ModuleList()
+        for t, c, n, s in SETTING:
+            for i in range(n):
+                self.bottlenecks.append(InvertedResidualPort(cin, c, s if i == 0 else 1, t))
+                cin = c
+        self.conv2 = nn.Sequential(nn.Conv2d(320, 1280, 1, 1, 0, bias=False), nn.BatchNorm2d(1280), nn.ReLU6(inplace=True))
+        self.avgpool = nn.AdaptiveAvgPool2d(1)   # constructed, never used by forward (MobileNetV2.py:174)
+        self.ssd_head = SSDHeadPort(NUM_CLASSES)
+        self.extra_layers = nn.ModuleList([
+            nn.Conv2d(1280, 512, 1), nn.Conv2d(512, 512, 3, 2, 1), nn.Conv2d(512, 256, 1), nn.Conv2d(256, 256, 3, 2, 1),
+            nn.Conv2d(256, 256, 3, 2, 1), nn.Conv2d(256, 128, 1), nn.Conv2d(128, 128, 3, 2, 1)])
+        self._initialize_weights()
+
+    def _initialize_weights(self):
+        """MobileNetV2.py:219-250, same module order => same RNG consumption as the reference."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def forward(self, x, use_dropout=False):
+        feats = []
+        x = self.conv1(x)
+        for i, b in enumerate(self.bottlenecks):
+            x = b(x)
+            if i == 12:
+                feats.append(x)
+        x = self.conv2(x)
+        feats.append(x)
+        for i, l in enumerate(self.extra_layers):
+            x = l(x)
+            if i in (1, 3, 4, 6):
+                feats.append(x)
+        return self.ssd_head(feats)
+
+
+# ------------------------------------------------------------------------------------------------------ MultiTaskLoss
+def point_distances(loc: torch.Tensor, true4: torch.Tensor) -> torch.Tensor:
+    """(n,2),(4,2) -> (n,4) Euclidean distances, fp32, operation order fixed (see the module docstring)."""
+    dx = loc[:, None, 0] - true4[None, :, 0]
+    dy = loc[:, None, 1] - true4[None, :, 1]
+    return torch.sqrt(dx * dx + dy * dy)
+
+
+def assign_labels(dist: torch.Tensor, ratio: float = RATIO) -> torch.Tensor:
+    """MobileNetV2.py:393-430 on one sample.  dist (n,4) -> int32 labels (n,), -1 = background.
+
+    Per label: threshold = k-th smallest distance (k = int(ratio*n), :399-401), positives = dist <= threshold (:404); a
+    point positive for several labels takes the one with the strictly smallest distance, first label on ties (:420-430)."""
+    n = dist.shape[0]
+    k = int(ratio * n)
+    thr = dist.topk(k, dim=0, largest=False)[0].max(dim=0)[0]          # (4,)
+    pos = dist <= thr[None, :]
+    d = torch.where(pos, dist, torch.full_like(dist, float("inf")))
+    best, lab = d.min(dim=1)    # torch.min returns the first index among equal minima == the reference's strict `<` scan
+    # torch.min's tie rule on CPU is "first occurrence"; make it explicit so that it does not depend on the backend
+    first = (d == best[:, None]).to(torch.int32).argmax(dim=1)
+    return torch.where(torch.isinf(best), torch.full_like(first, -1), first).to(torch.int32)
+
+
+def select_background(labels: torch.Tensor, u: Optional[torch.Tensor], ratio_nb: float = RATIO_NON_BACKGROUND) -> torch.Tensor:
+    """MobileNetV2.py:494-507: bool mask of the background points that enter the loss.  `u` = per-point keys (see the
+    module docstring); None is allowed only when no sub-sampling is needed."""
+    bg = labels < 0
+    n_pos = int((~bg).sum())
+    m = int(n_pos * ratio_nb)
+    if int(bg.sum()) <= m:
+        return bg
+    assert u is not None, "background sub-sampling needs the per-point keys u"
+    key = torch.where(bg, u.to(torch.float32), torch.full_like(u, float("inf"), dtype=torch.float32))
+    order = torch.sort(key, stable=True)[1][:m]
+    sel = torch.zeros_like(bg)
+    sel[order] = True
+    return sel
+
+
+def multitask_loss_sample(loc, cls, true8, image_size, u=None, alpha=ALPHA, beta=BETA, ratio=RATIO, labels_out=None):
+    """MultiTaskLoss.forward (MobileNetV2.py:432-534) for ONE sample: loc (n,2), cls (n,5), true8 (8,), image_size (H, W)."""
+    true4 = true8.view(4, 2)
+    with torch.no_grad():
+        labels = assign_labels(point_distances(loc.detach(), true4), ratio)
+        bg_sel = select_background(labels, u)
+    if labels_out is not None:
+        labels_out.append(labels)
+    h, w = image_size
+    size = torch.tensor([w, h], dtype=loc.dtype, device=loc.device)       # :457 (width, height)
+    lp = torch.clamp(loc / size, 0, 1)
+    lt = torch.clamp(true4 / size, 0, 1)
+    loc_loss = loc.new_zeros(())
+    cls_loss = loc.new_zeros(())
+    if bool(bg_sel.any()):                                                # :510-516
+        idx = bg_sel.nonzero().flatten()
+        cls_loss = cls_loss + F.cross_entropy(cls[idx], torch.full((idx.numel(),), 4, dtype=torch.long, device=cls.device))
+    for j in range(4):
+        idx = (labels == j).nonzero().flatten()
+        if idx.numel():
+            loc_loss = loc_loss + F.mse_loss(lp[idx], lt[j].expand(idx.numel(), 2))          # :471-481
+            cls_loss = cls_loss + F.cross_entropy(cls[idx], torch.full((idx.numel(),), j, dtype=torch.long,
+                                                                      device=cls.device))  # :519-528
+    return alpha * loc_loss + beta * cls_loss, loc_loss, cls_loss
+
+
+def multitask_loss(loc, cls, true, image_size, u=None, labels_out=None, **kw):
+    """Batched loss = mean over the batch of the reference's per-sample loss (oracle-defined, see module docstring)."""
+    B = loc.shape[0]
+    tot = loc.new_zeros(())
+    for b in range(B):
+        t, _, _ = multitask_loss_sample(loc[b], cls[b], true[b].reshape(8), image_size, None if u is None else u[b],
+                                        labels_out=labels_out, **kw)
+        tot = tot + t
+    return tot / B
+
+
+# ------------------------------------------------------------------------------------------------------ training step
+def sgd_nesterov_step(params: List[torch.Tensor], grads: List[torch.Tensor], bufs: List[Optional[torch.Tensor]],
+                      lr=SGD["lr"], momentum=SGD["momentum"], weight_decay=SGD["weight_decay"]):
+    """torch.optim.SGD(nesterov=True) update (UtilityMethods.py:30), written out: first step buf = g."""
+    for i, (p, g) in enumerate(zip(params, grads)):
+        g = g + weight_decay * p
+        if bufs[i] is None:
+            bufs[i] = g.clone()
+        else:
+            bufs[i].mul_(momentum).add_(g)
+        p.sub_(lr * (g + momentum * bufs[i]))
+
+
+def pretrain_step(model: nn.Module, images, true, u, optimizer: Optional[torch.optim.Optimizer] = None):
+    """One Pretrain.py:159-181 iteration (model.train(): batch-statistics BatchNorm, running stats updated).  Returns
+    (loss, labels list); gradients are left in .grad; steps `optimizer` if given."""
+    model.train()
+    loc, cls = model(images, use_dropout=True)
+    labels: list = []
+    loss = multitask_loss(loc, cls, true, (images.shape[2], images.shape[3]), u, labels_out=labels)
+    for p in model.parameters():
+        p.grad = None
+    loss.backward()
+    if optimizer is not None:
+        optimizer.step()
+    return loss.detach(), labels, loc.detach(), cls.detach()
+
+
+def make_batch(B: int, seed: int = 1234, device="cpu"):
+    """Synthetic Pretrain batch: faces ~ U(-1,1) (B,3,128,128); 4 ground-truth points = canonical landmark
+    means (D_and_G_model.py:120-128: eyes, nose, mouth centre) + U(-3,3) px
+    jitter; u = background sub-sampling keys."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.rand((B, 3, 128, 128), generator=g) * 2 - 1
+    means = torch.tensor([[39.4799, 40.2799], [85.9613, 38.7062], [63.6415, 63.6473], [64.7803, 89.3250]])
+    true = (means[None] + (torch.rand((B, 4, 2), generator=g) * 6 - 3)).reshape(B, 8)
+    u = torch.rand((B, 394), generator=g)
+    return images.to(device), true.to(device), u.to(device)

@@ -1,0 +1,183 @@
+"""CPU tests of the Pretrain path: the oracle (oracle/pretrain_port.py) is pinned against the live
+reference when /root/reference is present and against the golden vectors recorded from it (tools/make_golden_pretrain.py ->
+tests/golden/pretrain_golden.pt); the drop-in module mirrors the reference's interface and state_dict."""
+import contextlib
+import io
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import pretrain_port as P
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "pretrain_golden.pt")
+REF = os.environ.get("TPGAN_REFERENCE_DIR", "/root/reference")
+needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "MobileNetV2.py")), reason="reference tree absent")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, weights_only=False)
+
+
+def _ref():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import MobileNetV2 as R
+    return R
+
+
+def _temp_py_inputs():
+    loc = torch.tensor([[[1.0, 1.0], [420.0, 360.0], [370.0, 150.0], [180.0, 220.0], [330.0, 270.0], [290.0, 135.0],
+                         [500.0, 380.0], [190.0, 400.0], [210.0, 420.0], [510.0, 70.0], [178.0, 321.0], [420.0, 110.0]]])
+    true = torch.tensor([[0.0, 0.0, 150.0, 400.0, 350.0, 250.0, 300.0, 150.0]])
+    cls = torch.tensor([[[2.0, 1.0, 0.1, 0.5, 1.4], [1.0, 2.0, 0.1, 0.3, 1.1], [0.1, 2.0, 1.0, 0.4, 0.5],
+                         [2.0, 0.1, 1.0, 0.7, 0.5], [1.0, 0.1, 1.4, 0.8, 2.0], [0.1, 1.0, 2.0, 0.6, 0.7],
+                         [2.0, 1.0, 0.1, 0.9, 1.5], [1.0, 0.8, 0.1, 1.1, 2.0], [0.1, 1.2, 1.0, 2.0, 0.5],
+                         [2.0, 0.1, 1.0, 1.3, 0.6], [1.0, 0.1, 2.0, 1.4, 1.6], [0.1, 1.0, 1.3, 1.5, 2.0]]])
+    return loc, cls, true
+
+
+def _loss_case(seed, n=394):     # the generator of tools/make_golden_pretrain.py
+    g = torch.Generator().manual_seed(seed)
+    loc = (torch.rand((1, n, 2), generator=g) * 140 - 6).clamp_min(0)
+    cls = torch.randn((1, n, 5), generator=g)
+    true = torch.tensor([[39.48, 40.28, 85.96, 38.7, 63.64, 63.65, 64.78, 89.32]]) + torch.rand((1, 8), generator=g) * 6 - 3
+    u = torch.rand((1, n), generator=g)
+    return loc, cls, true, u
+
+
+def test_multitask_loss_known_answer(gold):
+    """Temp.py:8-29, the reference's only known answer."""
+    loc, cls, true = _temp_py_inputs()
+    got = float(P.multitask_loss(loc, cls, true, (600, 800)))
+    assert got == pytest.approx(0.8939134478569031, abs=1e-7)
+    assert gold["temp_py_total_loss"] == 0.8939134478569031
+
+
+def test_port_matches_golden(gold):
+    torch.manual_seed(0)
+    net = P.MobileNetV2Port()
+    sums = {k: float(v.double().sum()) for k, v in net.state_dict().items() if v.dtype.is_floating_point}
+    assert sums == gold["param_sums"]                       # same initialisation order / RNG consumption
+    x, _, _ = P.make_batch(2, seed=11)
+    net.train()
+    with torch.no_grad():
+        loc, cls = net(x)
+    assert torch.equal(loc, gold["train_loc"]) and torch.equal(cls, gold["train_cls"])
+    sd = net.state_dict()
+    assert all(torch.equal(sd[k], v) for k, v in gold["running"].items())
+    net.eval()
+    with torch.no_grad():
+        loc, cls = net(x)
+    assert torch.equal(loc, gold["eval_loc"]) and torch.equal(cls, gold["eval_cls"])
+
+
+def test_loss_matches_golden(gold):
+    for case in gold["loss_cases"]:
+        loc, cls, true, u = _loss_case(case["seed"])
+        loc.requires_grad_(True), cls.requires_grad_(True)
+        labs = []
+        val = P.multitask_loss(loc, cls, true, (128, 128), u, labels_out=labs)
+        gl, gc = torch.autograd.grad(val, [loc, cls])
+        assert torch.equal(labs[0], case["labels"])
+        assert float(val) == pytest.approx(case["loss"], rel=1e-6)
+        assert torch.allclose(gl, case["dloc"], rtol=1e-5, atol=1e-9) and torch.allclose(gc, case["dcls"], rtol=1e-5, atol=1e-9)
+
+
+def test_assignment_rules():
+    # threshold = k-th smallest distance with ties included; a point positive for two labels takes the nearer, first on ties
+    d = torch.tensor([[1.0, 9.0, 9.0, 9.0], [2.0, 2.0, 9.0, 9.0], [2.0, 1.0, 9.0, 9.0], [5.0, 5.0, 1.0, 1.0]] +
+                     [[7.0 + 0.1 * i] * 4 for i in range(16)])
+    lab = P.assign_labels(d, ratio=0.1)            # n = 20, k = 2: thresholds 2, 2, 7, 7
+    # point 1 ties label 0 / 1 at distance 2 -> first label; points 3 and 4 tie label 2 / 3 -> label 2
+    assert lab[:5].tolist() == [0, 0, 1, 2, 2] and (lab[5:] == -1).all()
+    # background sub-sampling keeps the m smallest keys, lower index on ties
+    labels = torch.tensor([0, -1, -1, -1, -1, -1, -1, -1], dtype=torch.int32)
+    u = torch.tensor([0.0, 0.9, 0.1, 0.5, 0.1, 0.7, 0.2, 0.3])
+    sel = P.select_background(labels, u, ratio_nb=3.0)   # 1 positive -> 3 background points
+    assert sel.nonzero().flatten().tolist() == [2, 4, 6]
+
+
+@needs_ref
+def test_port_matches_live_reference():
+    R = _ref()
+    torch.manual_seed(0)
+    ref = R.MobileNetV2()
+    torch.manual_seed(0)
+    port = P.MobileNetV2Port()
+    sr, sp = ref.state_dict(), port.state_dict()
+    assert list(sr.keys()) == list(sp.keys()) and all(torch.equal(sr[k], sp[k]) for k in sr)
+    x, _, _ = P.make_batch(2, seed=3)
+    ref.train(), port.train()
+    a, b = ref(x), port(x)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    (a[0].sum() + a[1].square().sum()).backward()
+    (b[0].sum() + b[1].square().sum()).backward()
+    pr = dict(ref.named_parameters())
+    assert all(torch.equal(p.grad, pr[k].grad) for k, p in port.named_parameters())
+
+
+@needs_ref
+def test_multitask_loss_matches_live_reference():
+    R = _ref()
+    for seed in (10, 11, 12):
+        loc, cls, true, u = _loss_case(seed)
+        labs = []
+        want_port = P.multitask_loss(loc, cls, true, (128, 128), u, labels_out=labs)
+        orig = torch.multinomial
+
+        def keyed(w, m, replacement=False, u=u):
+            key = torch.where(w > 0, u[0], torch.full_like(u[0], float("inf")))
+            return torch.sort(key, stable=True)[1][:m]
+        torch.multinomial = keyed
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                L = R.MultiTaskLoss()
+                want = L(loc, cls, true, (128, 128))
+                _, labels = L.get_positive_samples_and_classification_tensor(loc, true)
+        finally:
+            torch.multinomial = orig
+        assert torch.equal(labels, labs[0])
+        assert float(want) == pytest.approx(float(want_port), rel=1e-6)
+
+
+def test_dropin_module_mirrors_reference_interface():
+    import inspect
+
+    from tpgan_b200.MobileNetV2 import InvertedResidual, MobileNetV2, MultiTaskLoss, SSDHead
+    torch.manual_seed(0)
+    net = MobileNetV2()
+    torch.manual_seed(0)
+    port = P.MobileNetV2Port()
+    sa, sb = net.state_dict(), port.state_dict()
+    assert list(sa.keys()) == list(sb.keys()) and len(sa) == 356
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)        # bit-identical seeded initialisation
+    assert sum(p.numel() for p in net.parameters()) == 7_676_334
+    assert MobileNetV2.num_points(128, 128) == 394
+    assert list(inspect.signature(MobileNetV2.forward).parameters) == ["self", "x", "use_dropout"]
+    assert list(inspect.signature(InvertedResidual.__init__).parameters) == ["self", "inp", "oup", "stride", "expand_ratio"]
+    assert list(inspect.signature(SSDHead.__init__).parameters) == ["self", "num_of_out_classes"]
+    assert list(inspect.signature(MultiTaskLoss.forward).parameters)[:5] == ["self", "locations_pred", "classifications_pred",
+                                                                            "locations_true", "image_size"]
+    L = MultiTaskLoss()
+    assert (L.alpha, L.beta, L.distance_threshold_ratio, L.ratio_non_background) == (30.0, 0.1, 0.1, 5.0)  # config.py:25-27
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 128, 128))                    # no CPU fallback
+
+
+def test_sgd_port_equals_torch_sgd():
+    torch.manual_seed(1)
+    p0 = [torch.randn(17), torch.randn(5, 3)]
+    ref = [torch.nn.Parameter(t.clone()) for t in p0]
+    opt = torch.optim.SGD(ref, **P.SGD)
+    mine, bufs = [t.clone() for t in p0], [None, None]
+    for _ in range(3):
+        gs = [torch.randn_like(t) for t in p0]
+        for r, g in zip(ref, gs):
+            r.grad = g.clone()
+        opt.step()
+        P.sgd_nesterov_step(mine, gs, bufs)
+    assert all(torch.allclose(a, b.data, rtol=1e-6, atol=1e-8) for a, b in zip(mine, ref))

@@ -125,7 +125,7 @@ class _EngineFn(torch.autograd.Function):
         for t, x in zip(traced.ins, inputs):
             x4 = x.detach().float()
             t.act.from_nchw(x4.reshape(t.act.n, t.act.c, t.act.h, t.act.w), round_tf32=not plan.exact)
-        for L in plan.layers:
+        for L in plan.layers + plan.aux:
             L.refresh()
         plan.run_forward()
         outs = []
@@ -148,10 +148,10 @@ class _EngineFn(torch.autograd.Function):
                 ops.fill(ga, 0.0)
             else:
                 ga.from_nchw(g.detach().float().reshape(ga.n, ga.c, ga.h, ga.w))
-        for L in plan.layers:
+        for L in plan.layers + plan.aux:
             L.zero_grad()
         plan.run_backward()
-        for L in plan.layers:
+        for L in plan.layers + plan.aux:
             L.export_grad_autograd()
         gin = []
         for t in traced.ins:

@@ -97,6 +97,15 @@ SYMBOLS = {
     "tpgan_fill": (C.c_int, [View, _F, _VP]),
     "tpgan_split_tf32": (C.c_int, [View, View, View, _VP]),
     "tpgan_softmax_ce": (C.c_int, [_VP, _I64, _VP, _VP, _I64, _I32, _I32, _F, _VP, _VP]),
+    "tpgan_dwconv3x3": (C.c_int, [View, View, _VP, _I32, _VP]),
+    "tpgan_dwconv3x3_dgrad": (C.c_int, [View, View, _VP, _I32, _I32, _VP]),
+    "tpgan_dwconv3x3_wgrad": (C.c_int, [View, View, _VP, _I32, _VP]),
+    "tpgan_bn_forward": (C.c_int, [View, View, View, _VP, _VP, _VP, _VP, _F, _F, _I32, _I32, _I32, _VP, _VP, _VP]),
+    "tpgan_bn_backward": (C.c_int, [View, View, View, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "tpgan_rows_gather": (C.c_int, [View, _VP, _I64, _I64, _I32, _VP]),
+    "tpgan_multitask_loss": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I64, _I64, _I32, _I32, _F, _F, _F, _F, _F, _F, _VP, _VP, _VP,
+                                       _VP, _VP]),
+    "tpgan_sgd_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _F, _F, _I32, _F, _VP]),
     "tpgan_last_error": (C.c_char_p, []),
     "tpgan_abi_version": (C.c_int, []),
     "tpgan_kernel_status": (C.c_int, []),

@@ -365,6 +365,8 @@ class Plan:
         self.bwd_marks: Dict[str, int] = {}   # layer name -> index in self.bwd after which its dW is final
         self.layers: List[ConvLayer] = []     # every conv layer this plan launches (for repack / grad export)
         self.named: Dict[str, T] = {}         # layer name -> its output tensor (introspection / tests)
+        self.aux: list = []                   # non-tensor-core parameter holders (BatchNorm, depthwise conv) of this plan
+        self.direct_grads = False             # aux layers write straight into param.grad (flat buffers of a trainer)
 
     # ------------------------------------------------------------------ buffers
     def new(self, n, h, w, c, slope=LINEAR, name="", requires_grad=True) -> T:
@@ -737,6 +739,105 @@ class Plan:
             g = self.grad_act(out)
             self._contribute(x, lambda dst, acc: ops.avgpool_backward(g, dst, acc))
         self.tape.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------ Pretrain path (MobileNetV2.py) ops
+    def batchnorm(self, bn, x: T, res: Optional[T] = None, relu6: bool = False, round_out: bool = True,
+                  round_dx: bool = True, name: str = "") -> T:
+        """nn.BatchNorm2d (+nn.ReLU6, + the residual add of InvertedResidual.forward, MobileNetV2.py:107-120).  `bn` is a
+        BNLayer (tpgan_b200/MobileNetV2.py).  Training plans use batch statistics and update the running ones."""
+        n, h, w, c = x.shape
+        assert c % 4 == 0 and x.act.c0 == 0 and x.act.buf.shape[3] == c, "BatchNorm needs a whole pixel-dense buffer"
+        out = self.new(n, h, w, c, name=name or bn.name)
+        st = bn.state(self, c)
+        if bn not in self.aux:
+            self.aux.append(bn)
+        training = self.training
+        rt = round_out and not self.exact
+        self.use(x)
+        if res is not None:
+            self.use(res)
+        m = bn.module
+        eps = float(m.eps)
+        mom = 0.1 if m.momentum is None else float(m.momentum)
+        self.fwd.append(lambda: ops.bn_forward(x.act, None if res is None else res.act, out.act, m.weight.data, m.bias.data,
+                                               m.running_mean, m.running_var, mom, eps, training, relu6, rt, st.sums,
+                                               st.coef))
+        self.named[name or bn.name] = out
+
+        def tape_fn():
+            if not self._has_grad(out):
+                self._null(x)
+                if res is not None:
+                    self._null(res)
+                return
+            self._finalize(out)
+            g = self.grad_act(out)
+            need_param = training and self.need_wgrad
+            dg, db = (bn.grad_targets(self) if need_param else (None, None))
+            rdx = round_dx and not self.exact
+            if res is not None:
+                self._contribute(res, lambda dst, acc: ops.view_copy(g, dst, acc))
+            if x.requires_grad:
+                self._contribute(x, lambda dst, acc: ops.bn_backward(g, x.act, dst, st.coef, training, relu6, acc, rdx,
+                                                                     st.dsums, dg, db))
+        self.tape.append(tape_fn)
+        return out
+
+    def dwconv(self, layer, x: T, name: str = "") -> T:
+        """Depthwise 3x3 conv, pad 1, stride 1|2 (MobileNetV2.py:110).  `layer` is a DepthwiseLayer."""
+        n, h, w, c = x.shape
+        s = layer.stride
+        ho, wo = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+        out = self.new(n, ho, wo, c, name=name or layer.name)
+        if layer not in self.aux:
+            self.aux.append(layer)
+        wt = layer.weight
+        self.use(x)
+        self.fwd.append(lambda: ops.dwconv3x3(x.act, out.act, wt.data, s))
+        self.named[name or layer.name] = out
+
+        def tape_fn():
+            if not self._has_grad(out):
+                return self._null(x)
+            self._finalize(out)
+            g = self.grad_act(out)
+            if self.need_wgrad:
+                dw = layer.grad_target(self)
+                self.bwd.append(lambda: ops.dwconv3x3_wgrad(x.act, g, dw, s))
+            if x.requires_grad:
+                self._contribute(x, lambda dst, acc: ops.dwconv3x3_dgrad(g, dst, wt.data, s, acc))
+        self.tape.append(tape_fn)
+        return out
+
+    def gather_rows(self, parts: Sequence[T], name: str = "rows") -> T:
+        """SSDHead.forward's view(N,-1,K) + torch.cat(dim=1) (MobileNetV2.py:62-76): the NHWC head outputs laid end to end
+        per image.  Returns a flat (N,1,1,total) tensor."""
+        n = parts[0].act.n
+        sizes = [p.act.h * p.act.w * p.act.c for p in parts]
+        total = sum(sizes)
+        out = self.new(n, 1, 1, total, name=name)
+        out.flat = True
+        stride = out.act.buf.shape[3]
+        offs = [sum(sizes[:i]) for i in range(len(sizes))]
+        for p in parts:
+            self.use(p)
+        acts = [p.act for p in parts]
+        self.fwd.append(lambda: [ops.rows_gather(a, out.act.buf, stride, o) for a, o in zip(acts, offs)])
+
+        def tape_fn():
+            if not self._has_grad(out):
+                for p in parts:
+                    self._null(p)
+                return
+            self._finalize(out)
+            g = self.grad_act(out).buf
+            for p, o in zip(parts, offs):
+                def emit(dst, acc, o=o):
+                    assert not acc, "a head output has a single consumer"
+                    ops.rows_gather(dst, g, stride, o, reverse=True)
+                self._contribute(p, emit)
+        self.tape.append(tape_fn)
         return out
 
     # ------------------------------------------------------------------ backward tracing

@@ -378,3 +378,62 @@ def transpose_job(src: Packed, dst: Packed) -> "_lib.TransposeJob":
     assert src.taps == dst.taps and src.rows == dst.k and src.k == dst.rows
     return _lib.TransposeJob(src.data.data_ptr(), dst.data.data_ptr(), src.taps, src.rows, src.k, src.rows_pad, src.k_pad,
                              dst.rows_pad, dst.k_pad, 0, (src.k + 31) // 32, (src.rows + 31) // 32)
+
+
+# ---------------------------------------------------------------------------------------------------------- Pretrain path
+def dwconv3x3(x: Act, y: Act, w: torch.Tensor, stride: int) -> None:
+    """Depthwise 3x3 conv, pad 1 (MobileNetV2.py:110); w = the reference (C,1,3,3) tensor."""
+    _lib.check(_lib.load().tpgan_dwconv3x3(x.view(), y.view(), _ptr(w), stride, _stream()), "dwconv3x3")
+
+
+def dwconv3x3_dgrad(dy: Act, dx: Act, w: torch.Tensor, stride: int, accumulate: bool = False) -> None:
+    _lib.check(_lib.load().tpgan_dwconv3x3_dgrad(dy.view(), dx.view(), _ptr(w), stride, int(accumulate), _stream()),
+               "dwconv3x3_dgrad")
+
+
+def dwconv3x3_wgrad(x: Act, dy: Act, dw: torch.Tensor, stride: int) -> None:
+    """dw (C,1,3,3) += ... (atomics)."""
+    _lib.check(_lib.load().tpgan_dwconv3x3_wgrad(x.view(), dy.view(), _ptr(dw), stride, _stream()), "dwconv3x3_wgrad")
+
+
+def bn_forward(x: Act, res: Optional[Act], y: Act, gamma, beta, running_mean, running_var, momentum: float, eps: float,
+               training: bool, relu6: bool, round_tf32: bool, sums: torch.Tensor, coef: torch.Tensor) -> None:
+    """nn.BatchNorm2d (+ReLU6 / + residual) forward; sums = float64[2C] scratch, coef = float32[4C] (kept for backward)."""
+    assert sums.dtype == torch.float64 and coef.dtype == torch.float32
+    _lib.check(_lib.load().tpgan_bn_forward(x.view(), _v(res), y.view(), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                            _ptr(running_var), momentum, eps, int(training), int(relu6), int(round_tf32),
+                                            sums.data_ptr(), _ptr(coef), _stream()), "bn_forward")
+
+
+def bn_backward(dy: Act, x: Act, dx: Act, coef: torch.Tensor, training: bool, relu6: bool, accumulate: bool,
+                round_tf32: bool, dsums: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor]) -> None:
+    assert dsums.dtype == torch.float64
+    _lib.check(_lib.load().tpgan_bn_backward(dy.view(), x.view(), dx.view(), _ptr(coef), int(training), int(relu6),
+                                             int(accumulate), int(round_tf32), dsums.data_ptr(), _ptr(dgamma), _ptr(dbeta),
+                                             _stream()), "bn_backward")
+
+
+def rows_gather(v: Act, flat: torch.Tensor, row_stride: int, offset: int, reverse: bool = False) -> None:
+    """SSDHead view(N,-1,K) + cat(dim=1) (MobileNetV2.py:62-76): v's per-image floats <-> flat[n, offset:offset+h*w*c]."""
+    _lib.check(_lib.load().tpgan_rows_gather(v.view(), _ptr(flat), row_stride, offset, int(reverse), _stream()),
+               "rows_gather")
+
+
+def multitask_loss(loc: torch.Tensor, cls: torch.Tensor, truth: torch.Tensor, u: Optional[torch.Tensor], n: int,
+                   loc_stride: int, cls_stride: int, k_near: int, img_w: float, img_h: float, alpha: float, beta: float,
+                   ratio_nb: float, coeff: float, dloc: Optional[torch.Tensor], dcls: Optional[torch.Tensor],
+                   labels: Optional[torch.Tensor], sums: torch.Tensor) -> None:
+    """Batched MultiTaskLoss (MobileNetV2.py:342-534); see include/tpgan_b200.h."""
+    B = truth.shape[0]
+    assert truth.is_contiguous() and truth.numel() == B * 8 and (u is None or (u.is_contiguous() and u.numel() == B * n))
+    assert labels is None or (labels.dtype == torch.int32 and labels.numel() == B * n)
+    _lib.check(_lib.load().tpgan_multitask_loss(_ptr(loc), _ptr(cls), _ptr(truth), _ptr(u), B, n, loc_stride, cls_stride, 5,
+                                                k_near, img_w, img_h, alpha, beta, ratio_nb, coeff, _ptr(dloc), _ptr(dcls),
+                                                _ptr(labels), _ptr(sums), _stream()), "multitask_loss")
+
+
+def sgd_step(p: torch.Tensor, g: torch.Tensor, buf: torch.Tensor, lr_dev: torch.Tensor, momentum: float,
+             weight_decay: float, nesterov: bool, grad_scale: float = 1.0) -> None:
+    """torch.optim.SGD (UtilityMethods.py:30) over flat buffers; lr read from device memory."""
+    _lib.check(_lib.load().tpgan_sgd_step(_ptr(p), _ptr(g), _ptr(buf), p.numel(), _ptr(lr_dev), momentum, weight_decay,
+                                          int(nesterov), grad_scale, _stream()), "sgd_step")

@@ -1,0 +1,140 @@
+"""Pretrain.py's training iteration (Pretrain.py:159-181) for MobileNetV2 as ONE flat launch schedule on the device:
+
+    stage images (NCHW -> NHWC, tf32) -> MobileNetV2 forward (training-mode BatchNorm) -> batched MultiTaskLoss (loss value,
+    assignment, dL/dlocations, dL/dclassifications in one launch) -> backward -> gradient export into the flat .grad buffer
+    -> [NCCL all-reduce] -> SGD-Nesterov (UtilityMethods.py:30, config.py:31-35) -> weight re-pack
+
+with no host synchronisation inside (the reference syncs per predicted point: `.item()` at MobileNetV2.py:411-430), captured
+into a CUDA graph on request.  Data parallelism: full replica per rank, batch sharded by rank, one all-reduce
+of the 30 MB flat gradient; BatchNorm statistics stay rank-local, exactly as nn.BatchNorm2d under DistributedDataParallel
+without SyncBN (the reference has none) - an N-GPU run equals a 1-GPU run only at equal per-GPU batch.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+from .engine import GradArena, Plan
+from .MobileNetV2 import MobileNetV2
+from .train_step import Eager, FlatParams, GraphRunner, LayerSet
+
+# config.py:25-35 (pretrain['loss'], optimizer_param); the reference module itself is not imported by the product
+LOSS = dict(alpha=30.0, beta=0.1, ratio_non_background=5.0, distance_threshold_ratio=0.1)
+OPTIM = dict(learning_rate=5e-4, momentum=0.9, nesterov=True, weight_decay=5e-4)
+LR_MILESTONES, LR_GAMMA = (10, 20, 30), 0.1     # config.py:16-18, Pretrain.py:117-121 (MultiStepLR)
+
+
+class PretrainTrainer:
+    """step(images (B,3,H,W) in [-1,1], labels (B,8) = 4 ground-truth points (x,y), u (B,n) optional sub-sampling keys)."""
+
+    def __init__(self, model: MobileNetV2, B: int, image_hw=(128, 128), device="cuda", exact: bool = False,
+                 world_size: int = 1, group=None, use_graphs: bool = False):
+        self.model, self.B, self.device = model, B, torch.device(device)
+        self.hw = tuple(image_hw)
+        self.world_size, self.group, self.use_graphs = world_size, group, use_graphs
+        model.train()
+        self.flat = FlatParams(model)                      # params + .grad as views of flat buffers (m = momentum buffer)
+        self.lr_dev = torch.full((1,), OPTIM["learning_rate"], dtype=torch.float32, device=self.device)
+        self.epoch = 0
+        plan = Plan(self.device, training=True, need_wgrad=True, exact=exact, defer_bias=True)
+        plan.direct_grads = True
+        self.plan = plan
+        H, W = self.hw
+        self.x = plan.new(B, H, W, 3, name="images", requires_grad=False)
+        self.loc, self.cls = model.trace(plan, self.x)
+        plan.seed_grad(self.loc)
+        plan.seed_grad(self.cls)
+        plan.trace_backward()
+        self.n = self.loc.act.c // 2
+        assert self.cls.act.c == 5 * self.n
+        self.set = LayerSet(plan.layers, self.device, plan.bias_jobs)
+        self.set.repack()
+        self.sums = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.labels = torch.zeros((B, self.n), dtype=torch.int32, device=self.device)
+        self.inp: Optional[Dict[str, torch.Tensor]] = None
+        self._sched: Dict[bool, object] = {}
+        self.steps = 0
+
+    # ---- inputs live in static device buffers so that every pointer of the schedule is fixed
+    def load_inputs(self, images: torch.Tensor, labels: torch.Tensor, u: Optional[torch.Tensor]):
+        if self.inp is None:
+            self.inp = dict(images=torch.empty((self.B, 3) + self.hw, dtype=torch.float32, device=self.device),
+                            labels=torch.empty((self.B, 8), dtype=torch.float32, device=self.device),
+                            u=torch.empty((self.B, self.n), dtype=torch.float32, device=self.device))
+        self.inp["images"].copy_(images, non_blocking=True)
+        self.inp["labels"].copy_(labels.reshape(self.B, 8), non_blocking=True)
+        if u is not None:
+            self.inp["u"].copy_(u, non_blocking=True)
+        self._draw_u = u is None
+
+    def _stage(self):
+        self.x.act.from_nchw(self.inp["images"], round_tf32=not self.plan.exact)
+        if self._draw_u:
+            self.inp["u"].uniform_()        # the torch.multinomial draw of MobileNetV2.py:505 as per-point keys (philox)
+
+    def _loss(self):
+        a = LOSS
+        H, W = self.hw
+        dloc, dcls = self.plan.grad_act(self.loc).buf, self.plan.grad_act(self.cls).buf
+        ops.multitask_loss(self.loc.act.buf, self.cls.act.buf, self.inp["labels"], self.inp["u"], self.n,
+                           self.loc.act.buf.shape[3], self.cls.act.buf.shape[3],
+                           int(a["distance_threshold_ratio"] * self.n), float(W), float(H), a["alpha"], a["beta"],
+                           a["ratio_non_background"], 1.0 / self.B, dloc, dcls, self.labels, self.sums)
+
+    def _schedule(self, optimize: bool) -> List[Callable]:
+        sch: List[Callable] = [self._stage]
+        sch += self.plan.fwd
+        sch += [lambda: self.sums.zero_(), self._loss, GradArena.get(self.device).zero, lambda: self.flat.grad.zero_()]
+        sch += self.plan.bwd
+        sch.append(self.set.export)
+        if self.world_size > 1:
+            sch.append(Eager(self._allreduce))
+        if optimize:
+            o = OPTIM
+            sch.append(lambda: ops.sgd_step(self.flat.data, self.flat.grad, self.flat.m, self.lr_dev, o["momentum"],
+                                            o["weight_decay"], o["nesterov"], 1.0 / self.world_size))
+            sch.append(self.set.repack)
+        return sch
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.flat.grad, group=self.group)
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor, u: Optional[torch.Tensor] = None, optimize: bool = True,
+             read_metrics: bool = True):
+        self.load_inputs(images, labels, u)
+        if optimize not in self._sched:
+            sch = self._schedule(optimize)
+            self._sched[optimize] = GraphRunner(sch) if self.use_graphs else sch
+        sch = self._sched[optimize]
+        if self.use_graphs:
+            sch.run()
+        else:
+            for f in sch:
+                f()
+        self.steps += 1
+        return self.read_metrics() if read_metrics else None
+
+    def read_metrics(self) -> Dict[str, float]:
+        s = self.sums.cpu().tolist()
+        return dict(loss=s[0], location=s[1], classification=s[2])
+
+    def outputs(self):
+        """(locations (B,n,2), classifications (B,n,5)) of the last step (copies)."""
+        n = self.n
+        return (self.loc.act.buf.view(self.B, -1)[:, :2 * n].reshape(self.B, n, 2).clone(),
+                self.cls.act.buf.view(self.B, -1)[:, :5 * n].reshape(self.B, n, 5).clone())
+
+    def end_epoch(self):
+        """learning_rate_scheduler.step() (Pretrain.py:296): MultiStepLR(milestones, gamma)."""
+        self.epoch += 1
+        k = sum(1 for m in LR_MILESTONES if self.epoch >= m)
+        self.lr_dev.fill_(OPTIM["learning_rate"] * (LR_GAMMA ** k))
+
+    def sync_buffers(self):
+        """num_batches_tracked of every BatchNorm2d (state_dict parity with nn.BatchNorm2d in train mode)."""
+        for m in self.model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
+                m.num_batches_tracked.fill_(self.steps)
