@@ -244,3 +244,46 @@ def make_batch(B: int, seed: int = 1234, device="cpu"):
     true = (means[None] + (torch.rand((B, 4, 2), generator=g) * 6 - 3)).reshape(B, 8)
     u = torch.rand((B, 394), generator=g)
     return images.to(device), true.to(device), u.to(device)
+
+
+# ------------------------------------------------------------------------------------------------------ TF32 emulation
+def forward_tf32_emulated(model: MobileNetV2Port, x: torch.Tensor):
+    """Forward of the port with the PRODUCTION path's rounding points restated (tpgan_b200/MobileNetV2.py): operands of
+    every dense (tensor-core) convolution - stored activations feeding one, and its weights - are rounded to tf32
+    (cvt.rna), products are accumulated in fp32; depthwise convolutions, BatchNorm, ReLU6 and the residual add are fp32.
+    Lets the TF32 path be checked sharply although the network itself amplifies any perturbation ~100x from the stem
+    to the heads at random initialisation (measured in tests/test_pretrain_gpu.py).  Forward only."""
+    from .model_port import tf32_rna as q
+
+    def dense(conv, h):          # h is already rounded where the product rounds it
+        return F.conv2d(h, q(conv.weight), conv.bias, conv.stride, conv.padding)
+
+    def bn(m, h):
+        return F.batch_norm(h, m.running_mean, m.running_var, m.weight, m.bias, m.training, m.momentum, m.eps)
+
+    with torch.no_grad():
+        h = q(x)
+        h = q(F.relu6(bn(model.conv1[1], dense(model.conv1[0], h))))
+        feats = []
+        for i, b in enumerate(model.bottlenecks):
+            c = b.conv
+            t = F.relu6(bn(c[1], dense(c[0], h)))                      # feeds the depthwise conv: not rounded
+            t = F.conv2d(t, c[3].weight, None, c[3].stride, c[3].padding, 1, c[3].groups)
+            t = q(F.relu6(bn(c[4], t)))
+            t = bn(c[7], dense(c[6], t))
+            h = q(t + h) if b.use_res_connect else q(t)
+            if i == 12:
+                feats.append(h)
+        h = q(F.relu6(bn(model.conv2[1], dense(model.conv2[0], h))))
+        feats.append(h)
+        for i, l in enumerate(model.extra_layers):
+            h = q(dense(l, h))
+            if i in (1, 3, 4, 6):
+                feats.append(h)
+        locs, clss = [], []
+        for i, f in enumerate(feats):
+            l = dense(model.ssd_head.location_layer[i], f).permute(0, 2, 3, 1).contiguous()
+            locs.append(torch.relu(l.view(l.size(0), -1, 2)))
+            c = dense(model.ssd_head.classification_layer[i], f).permute(0, 2, 3, 1).contiguous()
+            clss.append(c.view(c.size(0), -1, NUM_CLASSES))
+        return torch.cat(locs, 1), torch.cat(clss, 1)

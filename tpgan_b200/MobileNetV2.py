@@ -162,8 +162,10 @@ class SSDHead(nn.Module):
         locs, clss = [], []
         for i, f in enumerate(features):
             # ReLU on the locations (MobileNetV2.py:67) fused into the conv epilogue
-            locs.append(plan.conv([_layer(self.location_layer[i], f"{pre}.location_layer.{i}")], [f], 0.0)[0])
-            clss.append(plan.conv([_layer(self.classification_layer[i], f"{pre}.classification_layer.{i}")], [f], None)[0])
+            locs.append(plan.conv([_layer(self.location_layer[i], f"{pre}.location_layer.{i}")], [f], 0.0,
+                                  round_out=False)[0])
+            clss.append(plan.conv([_layer(self.classification_layer[i], f"{pre}.classification_layer.{i}")], [f], None,
+                                  round_out=False)[0])
         return plan.gather_rows(locs, "locations"), plan.gather_rows(clss, "classifications")
 
     def forward(self, features):
@@ -185,11 +187,11 @@ class InvertedResidual(nn.Module):
 
     def trace(self, plan: Plan, x: T, pre: str) -> T:
         c = self.conv
-        h = plan.conv([_layer(c[0], f"{pre}.conv.0")], [x], None)[0]
+        h = plan.conv([_layer(c[0], f"{pre}.conv.0")], [x], None, round_out=False)[0]       # BatchNorm reads full fp32
         h = plan.batchnorm(_aux(c[1], BNLayer, f"{pre}.conv.1"), h, relu6=True, round_out=False)      # feeds the depthwise
         h = plan.dwconv(_aux(c[3], DepthwiseLayer, f"{pre}.conv.3"), h)
         h = plan.batchnorm(_aux(c[4], BNLayer, f"{pre}.conv.4"), h, relu6=True, round_dx=False)
-        h = plan.conv([_layer(c[6], f"{pre}.conv.6")], [h], None)[0]
+        h = plan.conv([_layer(c[6], f"{pre}.conv.6")], [h], None, round_out=False)[0]
         return plan.batchnorm(_aux(c[7], BNLayer, f"{pre}.conv.7"), h, res=x if self.use_res_connect else None)
 
     def forward(self, x):
@@ -239,13 +241,13 @@ class MobileNetV2(TracedModule):
     def trace(self, plan: Plan, x: T):
         """x: (N,H,W,3) NHWC -> (locations flat T (N,1,1,n*2), classifications flat T (N,1,1,n*5))."""
         feats = []
-        h = plan.conv([_layer(self.conv1[0], "conv1.0")], [x], None)[0]
+        h = plan.conv([_layer(self.conv1[0], "conv1.0")], [x], None, round_out=False)[0]
         h = plan.batchnorm(_aux(self.conv1[1], BNLayer, "conv1.1"), h, relu6=True)
         for idx, b in enumerate(self.bottlenecks):
             h = b.trace(plan, h, f"bottlenecks.{idx}")
             if idx == 12:                                   # MobileNetV2.py:192-193
                 feats.append(h)
-        h = plan.conv([_layer(self.conv2[0], "conv2.0")], [h], None)[0]
+        h = plan.conv([_layer(self.conv2[0], "conv2.0")], [h], None, round_out=False)[0]
         h = plan.batchnorm(_aux(self.conv2[1], BNLayer, "conv2.1"), h, relu6=True)
         feats.append(h)
         for idx, l in enumerate(self.extra_layers):          # plain convs with bias, no activation (:202-206)

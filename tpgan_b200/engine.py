@@ -419,8 +419,9 @@ class Plan:
                 p.pending += 1
 
     def conv(self, layers: Sequence[ConvLayer], xs: Sequence[T], slope: Optional[float], outs: Optional[Sequence[T]] = None,
-             residuals: Optional[Sequence[Optional[T]]] = None, name: str = "") -> List[T]:
-        """Grouped conv/deconv forward (+bias, +residual, +activation).  slope None = no activation."""
+             residuals: Optional[Sequence[Optional[T]]] = None, name: str = "", round_out: bool = True) -> List[T]:
+        """Grouped conv/deconv forward (+bias, +residual, +activation).  slope None = no activation.  round_out=False
+        keeps the stored result in full fp32 (consumers that are not tensor-core operands: BatchNorm, losses)."""
         G = len(layers)
         res = list(residuals) if residuals is not None else [None] * G
         outs_l: List[T] = []
@@ -452,7 +453,7 @@ class Plan:
             assert (x.ref_c == L.cin) and (out.ref_c == L.cout), (L.name, x.ref_c, L.cin, out.ref_c, L.cout)
             args.append(dict(L=L, dgrad=False, x=x.act, out=out.act, bias=getattr(L, "bias_full", L.bias_int),
                              add1=None if r is None else r.act, slope=0.0 if slope is None else slope,
-                             epilogue=EPI_LINEAR if slope is None else EPI_LEAKY))
+                             epilogue=EPI_LINEAR if slope is None else EPI_LEAKY, round=round_out))
             self.use(x)
             if r is not None:
                 self.use(r)
@@ -473,7 +474,7 @@ class Plan:
         def mk(sp, x, out, pack, **kw):
             L = sp["L"]
             return ops.conv_args(L.kind_dgrad if sp["dgrad"] else L.kind_fwd, x, out, pack, L.k, L.stride, L.pad,
-                                 round_tf32=not self.exact, **kw)
+                                 round_tf32=(not self.exact) and sp.get("round", True), **kw)
         full = lambda sp: dict(bias=sp.get("bias"), add1=sp.get("add1"), add2=sp.get("add2"), mask=sp.get("mask"),
                                slopes=sp.get("slopes"), slope=sp.get("slope", 0.0), epilogue=sp.get("epilogue", EPI_LINEAR))
         if not self.exact:
