@@ -282,6 +282,182 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ Pretrain workload
+PRETRAIN_METRIC = "mobilenetv2_pretrain_step_images_per_sec"
+
+
+def cpu_pretrain_step_time(batch: int, steps: int, warmup: int):
+    """Seconds per oracle-port Pretrain step (MobileNetV2 + MultiTaskLoss + SGD-Nesterov, fp32 PyTorch, all host threads)."""
+    import torch
+    from oracle import pretrain_port as P
+    torch.manual_seed(0)
+    net = P.MobileNetV2Port()
+    opt = torch.optim.SGD(net.parameters(), **P.SGD)
+    x, true, u = P.make_batch(batch)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        P.pretrain_step(net, x, true, u, opt)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts), torch.get_num_threads()
+
+
+def run_pretrain_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    batch = a.batch
+    sec, threads = cpu_pretrain_step_time(batch, a.steps, max(a.warmup, 1))
+    val = batch / sec
+    sample = f"oracle fp32 PyTorch port of MobileNetV2 + MultiTaskLoss + SGD step, batch {batch} per step, {a.steps} steps"
+    line = {"impl": "reference", "metric": PRETRAIN_METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": max(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Pretrain.py step: MobileNetV2-SSD + MultiTaskLoss + SGD-Nesterov, batch {batch}, 128x128",
+                       "per_step_batch": batch},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_pretrain(a):
+    """BASELINE.json configs[4]: Pretrain.py feature-extractor pre-training, MobileNetV2, global batch 256 at 8 GPUs
+    (32 per GPU, weak scaling), synthetic 128x128 faces."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle import pretrain_port as P   # synthetic batch generator only (inputs, not compute)
+    from tpgan_b200 import _lib
+    from tpgan_b200.MobileNetV2 import MobileNetV2
+    from tpgan_b200.pretrain_step import PretrainTrainer
+    B = a.batch
+    torch.manual_seed(0)
+    net = MobileNetV2().to(dev)
+    tr = PretrainTrainer(net, B, device=dev, world_size=world, use_graphs=not a.no_graphs)
+    x, true, u = P.make_batch(B, seed=1234 + rank)
+    host = [t.contiguous().pin_memory() for t in (x, true, u)]
+    devb = [t.to(dev) for t in host]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    resident = lambda: tr.step(*devb, read_metrics=False)
+    e2e_step = lambda: tr.step(*host, read_metrics=True)     # pinned host batch in, loss read back, every step
+    for _ in range(max(a.warmup, 3)):
+        resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(resident, a.steps)
+    launches = _lib.launch_count() - l0
+    if not a.no_graphs:
+        launches = a.steps * list(tr._sched.values())[0].kernels_per_run
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    assert _lib.kernel_status() == 0, "a kernel aborted a barrier wait"
+    roof = cpu = None
+    if rank == 0:
+        ev = []
+        tr.load_inputs(*devb)
+        tr._stage()
+        torch.cuda.synchronize()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2: each timed launch starts cold
+        for lst in (tr.plan.fwd, tr.plan.bwd):
+            for f in lst:
+                kind = getattr(f, "kind", None)
+                if kind is None:
+                    f()
+                    continue
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                f()
+                e.record()
+                ev.append((kind, getattr(f, "bytes", 0.0), getattr(f, "flops", 0.0), s, e))
+        torch.cuda.synchronize()
+        agg = {}
+        for kind, by, fl, s, e in ev:
+            g = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
+            g[0] += by
+            g[1] += fl
+            g[2] += s.elapsed_time(e)
+            g[3] += 1
+        peaks, which = _peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
+        total_t = sum(v[2] for v in agg.values())
+
+        def entry(kind):
+            by, fl, t, n = agg[kind]
+            d = {"launches": n, "avg_launch_ms": t / n, "share_of_timed_launches": t / total_t}
+            if by > 0:
+                d.update(achieved=by / (t * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s", frac=by / (t * 1e-3) / 1e9 / hbm_peak,
+                         algorithmic_mb_per_step=by / 1e6)
+            else:
+                d.update(achieved=fl / (t * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s", frac=fl / (t * 1e-3) / 1e12 / tf32_peak,
+                         algorithmic_gflop_per_step=fl / 1e9)
+            return d
+        dom = max(agg, key=lambda k: agg[k][2])
+        names = {"bn_fwd": "bn_stats/bn_finalize/bn_apply_kernel (training BatchNorm + ReLU6 / residual forward)",
+                 "bn_bwd": "bn_bwd_reduce/bn_bwd_apply_kernel (BatchNorm + ReLU6 backward)",
+                 "dw_fwd": "dw3x3_fwd_kernel", "dw_dgrad": "dw3x3_dgrad_kernel", "dw_wgrad": "dw3x3_wgrad_kernel",
+                 "tapgemm": "tapgemm_kernel (tcgen05 tf32: 1x1 / 3x3 dense convs fwd + dgrad)",
+                 "wgrad": "wgrad_kernel (tcgen05 tf32 weight gradients)"}
+        roof = {"bound": "hbm" if agg[dom][0] > 0 else "tensor", "kernel": names.get(dom, dom), **entry(dom), "traffic": None,
+                "timing": "per-launch CUDA events in eager mode with an L2 flush (256 MB memset) before each launch",
+                "peak_source": f"MEASURED_PEAKS.json ({which})",
+                "other_kernels": {names.get(k, k): entry(k) for k in agg if k != dom}}
+        if not a.no_cpu:
+            sec, threads = cpu_pretrain_step_time(B, 2, 1)
+            cpu = {"value": B / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"two oracle-port Pretrain steps (fp32 PyTorch, CPU) at batch {B} after one warm-up"}
+        gb = B * world
+        line = {"metric": PRETRAIN_METRIC, "value": gb * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "config": {"workload": f"Pretrain.py step: MobileNetV2-SSD forward/backward (training BatchNorm) + batched "
+                                       f"MultiTaskLoss + SGD-Nesterov, batch {B}/GPU, 128x128 synthetic faces",
+                           "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
+                           "l2": "the step's working set (~1.2 GB at batch 32) exceeds the 126 MB L2; no flush between steps",
+                           "cuda_graphs": not a.no_graphs},
+                "clocks": clocks,
+                "e2e": {"value": gb * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / a.steps},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,11 +465,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    ap.add_argument("--workload", default="gan", choices=["gan", "pretrain"],
+                    help="gan = G+D training step (BASELINE configs[1], the headline); pretrain = Pretrain.py MobileNetV2 "
+                         "step (configs[4])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-layer", default="", help="write the per-launch conv/wgrad timing table (JSON lines) here")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
-    if a.impl == "reference":
+    if a.workload == "pretrain":
+        (run_pretrain_reference if a.impl == "reference" else run_pretrain)(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -181,3 +181,44 @@ def test_sgd_port_equals_torch_sgd():
         opt.step()
         P.sgd_nesterov_step(mine, gs, bufs)
     assert all(torch.allclose(a, b.data, rtol=1e-6, atol=1e-8) for a, b in zip(mine, ref))
+
+
+# ---------------------------------------------------------------------------------------------- data parallel (gloo, world 2)
+def _dp_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tpgan_b200.parallel import allreduce_sum
+    torch.set_num_threads(2)
+    torch.manual_seed(0)
+    net = P.MobileNetV2Port()
+
+    def shard_grad(r):
+        x, true, u = P.make_batch(2, seed=1234 + r)          # bench.py's per-rank seeding
+        P.pretrain_step(net, x, true, u, None)
+        return torch.cat([p.grad.flatten() for p in net.parameters()])
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    flat = shard_grad(rank)
+    allreduce_sum(flat).wait()
+    flat *= 1.0 / world                                      # PretrainTrainer's grad_scale of the SGD kernel
+    if rank == 0:
+        want = torch.zeros_like(flat)
+        for r in range(world):                               # "replicas with local BatchNorm statistics" 
+            net.load_state_dict(sd)
+            want += shard_grad(r) / world
+        ret["err"] = float((flat - want).norm() / want.norm())
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_pretrain_gradient_is_the_mean_of_the_replicas():
+    import socket
+
+    import torch.multiprocessing as tmp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = tmp.Manager()
+    ret = mgr.dict()
+    tmp.spawn(_dp_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["err"] < 1e-6, ret["err"]

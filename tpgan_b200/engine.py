@@ -22,6 +22,12 @@ from .ops import Act, CONV_DGRAD, CONV_FWD, DECONV_DGRAD, DECONV_FWD, EPI_LEAKY,
 LINEAR = 1.0  # "slope" of a tensor with no activation (nothing to mask in backward)
 
 
+def _tag(fn, kind: str, nbytes: float, label: str = ""):
+    """Attach (kind, algorithmic HBM bytes, label) to a recorded launch; bench.py groups per-launch timings by kind."""
+    fn.kind, fn.bytes, fn.label = kind, nbytes, label
+    return fn
+
+
 class T:
     """A traced activation: forward view + static gradient bookkeeping."""
 
@@ -761,9 +767,11 @@ class Plan:
         m = bn.module
         eps = float(m.eps)
         mom = 0.1 if m.momentum is None else float(m.momentum)
-        self.fwd.append(lambda: ops.bn_forward(x.act, None if res is None else res.act, out.act, m.weight.data, m.bias.data,
-                                               m.running_mean, m.running_var, mom, eps, training, relu6, rt, st.sums,
-                                               st.coef))
+        elems = n * h * w * c
+        self.fwd.append(_tag(lambda: ops.bn_forward(x.act, None if res is None else res.act, out.act, m.weight.data,
+                                                    m.bias.data, m.running_mean, m.running_var, mom, eps, training, relu6,
+                                                    rt, st.sums, st.coef),
+                             "bn_fwd", 4.0 * elems * ((3 if training else 2) + (res is not None)), name or bn.name))
         self.named[name or bn.name] = out
 
         def tape_fn():
@@ -780,8 +788,9 @@ class Plan:
             if res is not None:
                 self._contribute(res, lambda dst, acc: ops.view_copy(g, dst, acc))
             if x.requires_grad:
-                self._contribute(x, lambda dst, acc: ops.bn_backward(g, x.act, dst, st.coef, training, relu6, acc, rdx,
-                                                                     st.dsums, dg, db))
+                self._contribute(x, _tag(lambda dst, acc: ops.bn_backward(g, x.act, dst, st.coef, training, relu6, acc, rdx,
+                                                                          st.dsums, dg, db),
+                                         "bn_bwd", 4.0 * elems * (5 if training else 3), name or bn.name))
         self.tape.append(tape_fn)
         return out
 
@@ -795,7 +804,8 @@ class Plan:
             self.aux.append(layer)
         wt = layer.weight
         self.use(x)
-        self.fwd.append(lambda: ops.dwconv3x3(x.act, out.act, wt.data, s))
+        ein, eout = n * h * w * c, n * ho * wo * c
+        self.fwd.append(_tag(lambda: ops.dwconv3x3(x.act, out.act, wt.data, s), "dw_fwd", 4.0 * (ein + eout), layer.name))
         self.named[name or layer.name] = out
 
         def tape_fn():
@@ -805,9 +815,10 @@ class Plan:
             g = self.grad_act(out)
             if self.need_wgrad:
                 dw = layer.grad_target(self)
-                self.bwd.append(lambda: ops.dwconv3x3_wgrad(x.act, g, dw, s))
+                self.bwd.append(_tag(lambda: ops.dwconv3x3_wgrad(x.act, g, dw, s), "dw_wgrad", 4.0 * (ein + eout), layer.name))
             if x.requires_grad:
-                self._contribute(x, lambda dst, acc: ops.dwconv3x3_dgrad(g, dst, wt.data, s, acc))
+                self._contribute(x, _tag(lambda dst, acc: ops.dwconv3x3_dgrad(g, dst, wt.data, s, acc), "dw_dgrad",
+                                         4.0 * (ein + eout), layer.name))
         self.tape.append(tape_fn)
         return out
 
@@ -902,7 +913,10 @@ class Plan:
             self._zero_unwritten(x)
         acc = any(written)
         dst = self.grad_act(x)
-        self.bwd.append(lambda: emit(dst, acc))
+        run = lambda: emit(dst, acc)
+        if hasattr(emit, "kind"):   # tagged launches (kind, algorithmic HBM bytes) keep their tag for bench.py
+            _tag(run, emit.kind, emit.bytes + (4.0 * dst.n * dst.h * dst.w * dst.c if acc else 0.0), emit.label)
+        self.bwd.append(run)
         for p in leaves:
             p.grad_written = True
             p.pending -= 1
