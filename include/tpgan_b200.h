@@ -241,15 +241,17 @@ TPGAN_API int tpgan_dwconv3x3_dgrad(tpgan_view dy, tpgan_view dx, const float* w
 TPGAN_API int tpgan_dwconv3x3_wgrad(tpgan_view x, tpgan_view dy, float* dw, int32_t stride, void* stream);
 
 /* nn.BatchNorm2d (+ nn.ReLU6, + the residual add of InvertedResidual.forward, MobileNetV2.py:107-120,150-170) over a
- * pixel-dense NHWC view.  training != 0: batch statistics (sums = caller-owned double[2*C] scratch that must stay intact
- * until the matching backward), running_mean / running_var updated in place with `momentum` and the unbiased variance;
+ * pixel-dense NHWC view.  training != 0: batch statistics; sums = caller-owned scratch of 2*C + 1 doubles, ZEROED ONCE by
+ * the caller and left zeroed by every call (the last word is a block ticket: the last block of the statistics kernel
+ * finalises and clears), running_mean / running_var updated in place with `momentum` and the unbiased variance;
  * training == 0: running statistics.  coef = caller-owned float[4*C] (scale, shift, mean, invstd) consumed by the backward.
  * y = x*scale + shift (+ res) -> ReLU6 if relu6 -> tf32 rounding if round_tf32 (operand of a tensor-core conv). */
 TPGAN_API int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, int32_t training,
                                int32_t relu6, int32_t round_tf32, double* sums, float* coef, void* stream);
 /* dz = dy * [0 < y < 6] (if relu6); training: dx (+)= scale*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum dz*xhat,
- * dbeta = sum dz (overwritten; may be NULL); eval: dx (+)= scale*dz.  dsums = double[2*C] scratch. */
+ * dbeta = sum dz (overwritten; may be NULL); eval: dx (+)= scale*dz.  dsums = scratch of 2*C + 1 doubles, zeroed once by the
+ * caller and left zeroed by every call. */
 TPGAN_API int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* coef, int32_t training, int32_t relu6,
                                 int32_t accumulate, int32_t round_tf32, double* dsums, float* dgamma, float* dbeta,
                                 void* stream);

@@ -97,7 +97,7 @@ def test_batchnorm_kernels(C, M, relu6, residual):
         o.backward(dy)
         g, b = bn.weight.data.cuda(), bn.bias.data.cuda()
         rm, rv = rm0.cuda(), rv0.cuda()
-        sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+        sums = torch.zeros(2 * C + 1, dtype=torch.float64, device="cuda")
         dsums = torch.zeros_like(sums)
         coef = torch.zeros(4 * C, device="cuda")
         xa, y = _act(x), ops.Act.empty(n, h, w, C)
@@ -112,6 +112,7 @@ def test_batchnorm_kernels(C, M, relu6, residual):
         assert rel(dx.to_nchw(), xr.grad) < tol, training
         if training:
             assert rel(dg, bn.weight.grad) < tol and rel(db, bn.bias.grad) < tol
+        assert float(sums.abs().sum()) == 0.0 and float(dsums.abs().sum()) == 0.0     # scratch left zeroed (incl. the ticket)
 
 
 def test_rows_gather_round_trip():

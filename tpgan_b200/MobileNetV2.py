@@ -38,8 +38,8 @@ from .ops import Act
 # ---------------------------------------------------------------------------------------------------- parameter holders
 class _BNState:
     def __init__(self, c: int, device):
-        self.sums = torch.zeros(2 * c, dtype=torch.float64, device=device)
-        self.dsums = torch.zeros(2 * c, dtype=torch.float64, device=device)
+        self.sums = torch.zeros(2 * c + 1, dtype=torch.float64, device=device)     # + block ticket; kernels leave it zeroed
+        self.dsums = torch.zeros(2 * c + 1, dtype=torch.float64, device=device)
         self.coef = torch.zeros(4 * c, dtype=torch.float32, device=device)
 
 

@@ -45,78 +45,112 @@ __device__ __forceinline__ float4 rnd4(float4 v) {
 }
 
 // ------------------------------------------------------------------------------------------- depthwise 3x3 convolution
-// nn.Conv2d(C, C, 3, stride, 1, groups=C, bias=False) (MobileNetV2.py:110).  w is the reference tensor (C,1,3,3) = [C][9];
-// it is staged transposed ([9][C]) in shared memory so that a thread's four channels are one 16-byte read per tap.
-__global__ void __launch_bounds__(256) dw3x3_fwd_kernel(PV x, PV y, const float* __restrict__ w, int stride) {
-  extern __shared__ float ws[];
-  const int C = x.c;
-  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) ws[(i % 9) * C + i / 9] = w[i];
-  __syncthreads();
-  const int cqn = C >> 2;
-  const long long total = (long long)y.n * y.h * y.w * cqn;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % cqn);
-    long long r = i / cqn;
-    const int ox = (int)(r % y.w);
-    r /= y.w;
+// nn.Conv2d(C, C, 3, stride, 1, groups=C, bias=False) (MobileNetV2.py:110).  w is the reference tensor (C,1,3,3) = [C][9].
+// Thread mapping shared by all Pretrain streaming kernels: a block of 256 threads is QB channel quads x RG pixel groups
+// (QB = all C/4 quads when they fit, else an even split over gridDim.y); a thread keeps ONE quad for its whole life, so
+// its 36 weights (4 channels x 9 taps = 144 contiguous bytes of w) sit in registers, and walks pixels p = blockIdx.x*RG
+// + rg, += gridDim.x*RG.  Consecutive threads read consecutive 16-byte quads of a pixel and then the next pixel: fully
+// coalesced for pixel-dense buffers whatever C is (96 channels = 24 quads no longer idle a quarter of each warp).
+struct QMap {
+  int qb, rg, ny;   // quads per block, pixel groups per block, blocks along the channel axis
+};
+static inline QMap qmap(int C) {
+  const int cqn = C / 4;
+  QMap m;
+  m.ny = (cqn + 255) / 256;
+  m.qb = (cqn + m.ny - 1) / m.ny;
+  m.rg = 256 / m.qb;
+  return m;
+}
+
+__device__ __forceinline__ void load_w36(const float* __restrict__ w, int q, float (&k)[36]) {
+  const float4* src = reinterpret_cast<const float4*>(w + (long long)q * 36);   // channels 4q..4q+3, 9 taps each
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float4 v = __ldg(src + i);
+    k[4 * i] = v.x, k[4 * i + 1] = v.y, k[4 * i + 2] = v.z, k[4 * i + 3] = v.w;
+  }
+}
+// weight of channel j (0..3 within the quad), tap t: k[j*9 + t]
+#define DWK(j, t) k[(j) * 9 + (t)]
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256) dw3x3_fwd_kernel(PV x, PV y, const float* __restrict__ w, int qb, int rg) {
+  const int ql = threadIdx.x % qb, g = threadIdx.x / qb;
+  const int q = blockIdx.y * qb + ql;
+  if (g >= rg || q * 4 >= x.c) return;
+  float k[36];
+  load_w36(w, q, k);
+  const long long npix = (long long)y.n * y.h * y.w;
+  for (long long p = (long long)blockIdx.x * rg + g; p < npix; p += (long long)gridDim.x * rg) {
+    const int ox = (int)(p % y.w);
+    const long long r = p / y.w;
     const int oy = (int)(r % y.h);
     const int n = (int)(r / y.h);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // all nine 16-byte loads are issued unconditionally from clamped coordinates and zero-selected afterwards, so they
+    // are in flight together (a branch per tap serialises them)
+    float4 v[9];
 #pragma unroll
     for (int kr = 0; kr < 3; ++kr) {
-      const int iy = oy * stride - 1 + kr;
-      if (iy < 0 || iy >= x.h) continue;
+      const int iy = oy * STRIDE - 1 + kr;
+      const int cy = min(max(iy, 0), x.h - 1);
 #pragma unroll
       for (int ks = 0; ks < 3; ++ks) {
-        const int ix = ox * stride - 1 + ks;
-        if (ix < 0 || ix >= x.w) continue;
-        const float4 v = ld4(x.p + poff(x, n, iy, ix) + q * 4);
-        const float4 k = ld4(ws + (kr * 3 + ks) * C + q * 4);
-        acc.x = fmaf(v.x, k.x, acc.x);
-        acc.y = fmaf(v.y, k.y, acc.y);
-        acc.z = fmaf(v.z, k.z, acc.z);
-        acc.w = fmaf(v.w, k.w, acc.w);
+        const int ix = ox * STRIDE - 1 + ks;
+        const int cx = min(max(ix, 0), x.w - 1);
+        v[kr * 3 + ks] = ld4(x.p + poff(x, n, cy, cx) + q * 4);
+        if (iy != cy || ix != cx) v[kr * 3 + ks] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      acc.x = fmaf(v[t].x, DWK(0, t), acc.x);
+      acc.y = fmaf(v[t].y, DWK(1, t), acc.y);
+      acc.z = fmaf(v[t].z, DWK(2, t), acc.z);
+      acc.w = fmaf(v[t].w, DWK(3, t), acc.w);
     }
     st4(y.p + poff(y, n, oy, ox) + q * 4, acc);
   }
 }
 
 // dx[n,iy,ix,c] (+)= sum_{kr,ks : (iy+1-kr) % s == 0, (ix+1-ks) % s == 0} dy[n,(iy+1-kr)/s,(ix+1-ks)/s,c] * w[c,kr,ks]
-__global__ void __launch_bounds__(256) dw3x3_dgrad_kernel(PV dy, PV dx, const float* __restrict__ w, int stride, int accumulate) {
-  extern __shared__ float ws[];
-  const int C = dx.c;
-  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) ws[(i % 9) * C + i / 9] = w[i];
-  __syncthreads();
-  const int cqn = C >> 2;
-  const long long total = (long long)dx.n * dx.h * dx.w * cqn;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % cqn);
-    long long r = i / cqn;
-    const int ix = (int)(r % dx.w);
-    r /= dx.w;
+template <int STRIDE>
+__global__ void __launch_bounds__(256) dw3x3_dgrad_kernel(PV dy, PV dx, const float* __restrict__ w, int accumulate, int qb,
+                                                         int rg) {
+  const int ql = threadIdx.x % qb, g = threadIdx.x / qb;
+  const int q = blockIdx.y * qb + ql;
+  if (g >= rg || q * 4 >= dx.c) return;
+  float k[36];
+  load_w36(w, q, k);
+  const long long npix = (long long)dx.n * dx.h * dx.w;
+  for (long long p = (long long)blockIdx.x * rg + g; p < npix; p += (long long)gridDim.x * rg) {
+    const int ix = (int)(p % dx.w);
+    const long long r = p / dx.w;
     const int iy = (int)(r % dx.h);
     const int n = (int)(r / dx.h);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[9];
 #pragma unroll
     for (int kr = 0; kr < 3; ++kr) {
       const int ty = iy + 1 - kr;
-      if (ty < 0 || (ty % stride) != 0) continue;
-      const int oy = ty / stride;
-      if (oy >= dy.h) continue;
+      const bool oky = ty >= 0 && (ty % STRIDE) == 0 && ty / STRIDE < dy.h;
+      const int oy = oky ? ty / STRIDE : 0;
 #pragma unroll
       for (int ks = 0; ks < 3; ++ks) {
         const int tx = ix + 1 - ks;
-        if (tx < 0 || (tx % stride) != 0) continue;
-        const int ox = tx / stride;
-        if (ox >= dy.w) continue;
-        const float4 g = ld4(dy.p + poff(dy, n, oy, ox) + q * 4);
-        const float4 k = ld4(ws + (kr * 3 + ks) * C + q * 4);
-        acc.x = fmaf(g.x, k.x, acc.x);
-        acc.y = fmaf(g.y, k.y, acc.y);
-        acc.z = fmaf(g.z, k.z, acc.z);
-        acc.w = fmaf(g.w, k.w, acc.w);
+        const bool okx = tx >= 0 && (tx % STRIDE) == 0 && tx / STRIDE < dy.w;
+        const int ox = okx ? tx / STRIDE : 0;
+        v[kr * 3 + ks] = ld4(dy.p + poff(dy, n, oy, ox) + q * 4);
+        if (!(oky && okx)) v[kr * 3 + ks] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      acc.x = fmaf(v[t].x, DWK(0, t), acc.x);
+      acc.y = fmaf(v[t].y, DWK(1, t), acc.y);
+      acc.z = fmaf(v[t].z, DWK(2, t), acc.z);
+      acc.w = fmaf(v[t].w, DWK(3, t), acc.w);
     }
     float* d = dx.p + poff(dx, n, iy, ix) + q * 4;
     if (accumulate) {
@@ -128,102 +162,71 @@ __global__ void __launch_bounds__(256) dw3x3_dgrad_kernel(PV dy, PV dx, const fl
 }
 
 // dw[c][kr*3+ks] += sum_{n,oy,ox} dy[n,oy,ox,c] * x[n, oy*s-1+kr, ox*s-1+ks, c]   (atomics into the reference layout).
-// block (32, 8): lane = channel quad (a warp reads 512 contiguous bytes of a pixel), ty = pixel sub-group.
-__global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(PV x, PV dy, float* __restrict__ dw, int stride) {
-  __shared__ float sacc[36][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int i = ty * 32 + tx; i < 36 * 33; i += 256) (&sacc[0][0])[i] = 0.f;
+// 36 accumulators per thread; the RG pixel groups of a block are folded through shared memory before ONE global atomic
+// per (channel, tap) and block.
+template <int STRIDE>
+__global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(PV x, PV dy, float* __restrict__ dw, int qb, int rg) {
+  extern __shared__ float sacc[];   // [qb][36]
+  for (int i = threadIdx.x; i < qb * 36; i += 256) sacc[i] = 0.f;
   __syncthreads();
-  const int cqn = x.c >> 2;
-  const int q = blockIdx.y * 32 + tx;
-  if (q < cqn) {
-    float4 acc[9];
+  const int ql = threadIdx.x % qb, g = threadIdx.x / qb;
+  const int q = blockIdx.y * qb + ql;
+  if (g < rg && q * 4 < x.c) {
+    float a[36];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 36; ++i) a[i] = 0.f;
     const long long npix = (long long)dy.n * dy.h * dy.w;
-    for (long long p = (long long)blockIdx.x * 8 + ty; p < npix; p += (long long)gridDim.x * 8) {
+    for (long long p = (long long)blockIdx.x * rg + g; p < npix; p += (long long)gridDim.x * rg) {
       const int ox = (int)(p % dy.w);
-      long long r = p / dy.w;
+      const long long r = p / dy.w;
       const int oy = (int)(r % dy.h);
       const int n = (int)(r / dy.h);
-      const float4 g = ld4(dy.p + poff(dy, n, oy, ox) + q * 4);
+      const float4 gv = ld4(dy.p + poff(dy, n, oy, ox) + q * 4);
+      float4 v[9];
 #pragma unroll
       for (int kr = 0; kr < 3; ++kr) {
-        const int iy = oy * stride - 1 + kr;
-        if (iy < 0 || iy >= x.h) continue;
+        const int iy = oy * STRIDE - 1 + kr;
+        const int cy = min(max(iy, 0), x.h - 1);
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks) {
-          const int ix = ox * stride - 1 + ks;
-          if (ix < 0 || ix >= x.w) continue;
-          const float4 v = ld4(x.p + poff(x, n, iy, ix) + q * 4);
-          float4& a = acc[kr * 3 + ks];
-          a.x = fmaf(g.x, v.x, a.x);
-          a.y = fmaf(g.y, v.y, a.y);
-          a.z = fmaf(g.z, v.z, a.z);
-          a.w = fmaf(g.w, v.w, a.w);
+          const int ix = ox * STRIDE - 1 + ks;
+          const int cx = min(max(ix, 0), x.w - 1);
+          v[kr * 3 + ks] = ld4(x.p + poff(x, n, cy, cx) + q * 4);
+          if (iy != cy || ix != cx) v[kr * 3 + ks] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        a[t] = fmaf(gv.x, v[t].x, a[t]);
+        a[9 + t] = fmaf(gv.y, v[t].y, a[9 + t]);
+        a[18 + t] = fmaf(gv.z, v[t].z, a[18 + t]);
+        a[27 + t] = fmaf(gv.w, v[t].w, a[27 + t]);
       }
     }
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      atomicAdd(&sacc[t * 4 + 0][tx], acc[t].x);
-      atomicAdd(&sacc[t * 4 + 1][tx], acc[t].y);
-      atomicAdd(&sacc[t * 4 + 2][tx], acc[t].z);
-      atomicAdd(&sacc[t * 4 + 3][tx], acc[t].w);
-    }
+    for (int i = 0; i < 36; ++i) atomicAdd(&sacc[ql * 36 + i], a[i]);   // a[j*9 + t] -> dw[(4q + j)*9 + t]: same order
   }
   __syncthreads();
-  for (int i = ty * 32 + tx; i < 36 * 32; i += 256) {
-    const int lane = i & 31, e = i >> 5;       // e = tap*4 + channel-in-quad
-    const int t = e >> 2, j = e & 3;
-    const int c = (blockIdx.y * 32 + lane) * 4 + j;
-    if (c < x.c) atomicAdd(dw + (long long)c * 9 + t, sacc[e][lane]);
-  }
+  const int qn = min(qb, x.c / 4 - blockIdx.y * qb);
+  float* dst = dw + (long long)blockIdx.y * qb * 36;
+  for (int i = threadIdx.x; i < qn * 36; i += 256) atomicAdd(dst + i, sacc[i]);
 }
 
 // ------------------------------------------------------------------------------------------- BatchNorm (training mode)
 // nn.BatchNorm2d (MobileNetV2.py:107,111,115,152,168) over a pixel-dense [M][ld] matrix.
-//   stats    : sums[0][c] += sum_p x, sums[1][c] += sum_p x^2   (fp32 per-thread partials of <= ~32 elements, then fp64)
-//   finalize : coef[0..3][c] = scale, shift, mean, invstd ; running statistics updated (momentum, unbiased variance)
+//   stats    : sums[0][c] += sum_p x, sums[1][c] += sum_p x^2   (fp32 per-thread partials of <= ~32 elements, then fp64);
+//              the last block to finish writes coef[0..3][c] = scale, shift, mean, invstd, updates the running statistics
+//              (momentum, unbiased variance) and re-zeroes the scratch: no separate finalize / memset launches
 //   apply    : y = x*scale + shift (+ residual) -> optional ReLU6 -> optional tf32 rounding
 //   backward : dz = dy * [0 < y < 6] ; dsums = (sum dz, sum dz*xhat) ; dx = scale * (dz - mean(dz) - xhat * mean(dz*xhat))
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, long long M, long long ld, int C,
-                                                      double* __restrict__ sums) {
-  __shared__ double red[8][32][8];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int q = blockIdx.y * 32 + tx;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
-  if (q * 4 < C) {
-    for (long long r = (long long)blockIdx.x * 8 + ty; r < M; r += (long long)gridDim.x * 8) {
-      const float4 v = ld4(x + r * ld + q * 4);
-      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
-      ss.x = fmaf(v.x, v.x, ss.x), ss.y = fmaf(v.y, v.y, ss.y), ss.z = fmaf(v.z, v.z, ss.z), ss.w = fmaf(v.w, v.w, ss.w);
-    }
-  }
-  double* d = red[ty][tx];
-  d[0] = s.x, d[1] = s.y, d[2] = s.z, d[3] = s.w, d[4] = ss.x, d[5] = ss.y, d[6] = ss.z, d[7] = ss.w;
-  __syncthreads();
-  // 256 threads finish the 32 x 8 outputs of the block: thread -> (lane = tid & 31, component = tid >> 5)
-  const int tid = ty * 32 + tx, lane = tid & 31, e = tid >> 5;
-  const int c = (blockIdx.y * 32 + lane) * 4 + (e & 3);
-  if (c < C) {
-    double a = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a += red[k][lane][e];
-    atomicAdd(sums + (e >> 2) * C + c, a);
-  }
-}
-
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum, float eps, int training,
-                                   float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__device__ __forceinline__ void bn_finalize_channel(int c, double sum, double sumsq, long long M, int C,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                    float momentum, float eps, int training, float* __restrict__ coef) {
   double mean, var;
   if (training) {
-    mean = sums[c] / (double)M;
-    var = sums[C + c] / (double)M - mean * mean;
+    mean = sum / (double)M;
+    var = sumsq / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
     if (running_mean) {
       const double unb = (M > 1) ? var * (double)M / (double)(M - 1) : var;
@@ -240,6 +243,86 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M,
   coef[C + c] = beta[c] - (float)mean * scale;
   coef[2 * C + c] = (float)mean;
   coef[3 * C + c] = invstd;
+}
+
+// Shared tail of the two reduction kernels: fold the RG pixel groups of the block (fp64), one atomic per (channel,
+// component) and block.  part[8] = the thread's 2 x 4 partial sums (component-major: s0.xyzw, s1.xyzw).
+__device__ __forceinline__ void bn_block_reduce(const float (&part)[8], int ql, int g, int qb, int rg, bool active, int C,
+                                                int q0, double* __restrict__ sums, double* red /* [rg][qb][8] */) {
+  if (active) {
+    double* d = red + ((long long)g * qb + ql) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = (double)part[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < qb * 8; i += 256) {
+    const int lq = i >> 3, e = i & 7;
+    const int c = (q0 + lq) * 4 + (e & 3);
+    if (c >= C) continue;
+    double a = 0.0;
+    for (int k = 0; k < rg; ++k) a += red[((long long)k * qb + lq) * 8 + e];
+    atomicAdd(sums + (e >> 2) * C + c, a);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, long long M, long long ld, int C,
+                                                      double* __restrict__ sums, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                      float* __restrict__ running_var, float momentum, float eps,
+                                                      float* __restrict__ coef, int qb, int rg) {
+  extern __shared__ double red[];
+  __shared__ int is_last;
+  const int ql = threadIdx.x % qb, g = threadIdx.x / qb;
+  const int q = blockIdx.y * qb + ql;
+  const bool active = g < rg && q * 4 < C;
+  float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const long long step = (long long)gridDim.x * rg;
+    const float* px = x + q * 4;
+    long long r = (long long)blockIdx.x * rg + g;
+    for (; r + 3 * step < M; r += 4 * step) {      // four independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld4(px + (r + u * step) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        part[0] += v[u].x, part[1] += v[u].y, part[2] += v[u].z, part[3] += v[u].w;
+        part[4] = fmaf(v[u].x, v[u].x, part[4]), part[5] = fmaf(v[u].y, v[u].y, part[5]);
+        part[6] = fmaf(v[u].z, v[u].z, part[6]), part[7] = fmaf(v[u].w, v[u].w, part[7]);
+      }
+    }
+    for (; r < M; r += step) {
+      const float4 v = ld4(px + r * ld);
+      part[0] += v.x, part[1] += v.y, part[2] += v.z, part[3] += v.w;
+      part[4] = fmaf(v.x, v.x, part[4]), part[5] = fmaf(v.y, v.y, part[5]);
+      part[6] = fmaf(v.z, v.z, part[6]), part[7] = fmaf(v.w, v.w, part[7]);
+    }
+  }
+  bn_block_reduce(part, ql, g, qb, rg, active, C, blockIdx.y * qb, sums, red);
+  // the last block to arrive folds the statistics into (scale, shift, mean, invstd), updates the running statistics and
+  // leaves the scratch zeroed for the next launch (threadfence-reduction pattern; the ticket lives behind the sums)
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 2 * C);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int ch = threadIdx.x; ch < C; ch += 256) {
+    const double su = __ldcg(sums + ch), sq = __ldcg(sums + C + ch);
+    bn_finalize_channel(ch, su, sq, M, C, gamma, beta, running_mean, running_var, momentum, eps, 1, coef);
+    sums[ch] = 0.0;
+    sums[C + ch] = 0.0;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// eval mode only (running statistics); in training mode the last block of bn_stats_kernel finalises
+__global__ void bn_finalize_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float eps,
+                                   float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) bn_finalize_channel(c, 0.0, 0.0, 1, C, gamma, beta, running_mean, running_var, 0.f, eps, 0, coef);
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, long long M, long long ldx, int C,
@@ -279,35 +362,39 @@ __device__ __forceinline__ float relu6_gate(float x, float scale, float shift, f
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, long long ldd,
                                                            const float* __restrict__ x, long long ldx, long long M, int C,
                                                            const float* __restrict__ coef, int relu6,
-                                                           double* __restrict__ dsums) {
-  __shared__ double red[8][32][8];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int q = blockIdx.y * 32 + tx;
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  if (q * 4 < C) {
+                                                           double* __restrict__ dsums, int qb, int rg) {
+  extern __shared__ double red[];
+  const int ql = threadIdx.x % qb, g = threadIdx.x / qb;
+  const int q = blockIdx.y * qb + ql;
+  const bool active = g < rg && q * 4 < C;
+  float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
     const float4 a = ld4(coef + q * 4), b = ld4(coef + C + q * 4), mu = ld4(coef + 2 * C + q * 4),
                  is = ld4(coef + 3 * C + q * 4);
-    for (long long r = (long long)blockIdx.x * 8 + ty; r < M; r += (long long)gridDim.x * 8) {
-      const float4 v = ld4(x + r * ldx + q * 4);
-      const float4 g = ld4(dy + r * ldd + q * 4);
-      const float gx = relu6_gate(v.x, a.x, b.x, g.x, relu6), gy = relu6_gate(v.y, a.y, b.y, g.y, relu6),
-                  gz = relu6_gate(v.z, a.z, b.z, g.z, relu6), gw = relu6_gate(v.w, a.w, b.w, g.w, relu6);
-      s1.x += gx, s1.y += gy, s1.z += gz, s1.w += gw;
-      s2.x = fmaf(gx, (v.x - mu.x) * is.x, s2.x), s2.y = fmaf(gy, (v.y - mu.y) * is.y, s2.y);
-      s2.z = fmaf(gz, (v.z - mu.z) * is.z, s2.z), s2.w = fmaf(gw, (v.w - mu.w) * is.w, s2.w);
-    }
-  }
-  double* d = red[ty][tx];
-  d[0] = s1.x, d[1] = s1.y, d[2] = s1.z, d[3] = s1.w, d[4] = s2.x, d[5] = s2.y, d[6] = s2.z, d[7] = s2.w;
-  __syncthreads();
-  const int tid = ty * 32 + tx, lane = tid & 31, e = tid >> 5;
-  const int c = (blockIdx.y * 32 + lane) * 4 + (e & 3);
-  if (c < C) {
-    double acc = 0.0;
+    const long long step = (long long)gridDim.x * rg;
+    const float* px = x + q * 4;
+    const float* pg = dy + q * 4;
+    auto add = [&](const float4& v, const float4& gr) {
+      const float gx = relu6_gate(v.x, a.x, b.x, gr.x, relu6), gy = relu6_gate(v.y, a.y, b.y, gr.y, relu6),
+                  gz = relu6_gate(v.z, a.z, b.z, gr.z, relu6), gw = relu6_gate(v.w, a.w, b.w, gr.w, relu6);
+      part[0] += gx, part[1] += gy, part[2] += gz, part[3] += gw;
+      part[4] = fmaf(gx, (v.x - mu.x) * is.x, part[4]), part[5] = fmaf(gy, (v.y - mu.y) * is.y, part[5]);
+      part[6] = fmaf(gz, (v.z - mu.z) * is.z, part[6]), part[7] = fmaf(gw, (v.w - mu.w) * is.w, part[7]);
+    };
+    long long r = (long long)blockIdx.x * rg + g;
+    for (; r + 3 * step < M; r += 4 * step) {      // eight independent 16-byte loads in flight per thread
+      float4 v[4], gr[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += red[k][lane][e];
-    atomicAdd(dsums + (e >> 2) * C + c, acc);
+      for (int u = 0; u < 4; ++u) {
+        v[u] = ld4(px + (r + u * step) * ldx);
+        gr[u] = ld4(pg + (r + u * step) * ldd);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) add(v[u], gr[u]);
+    }
+    for (; r < M; r += step) add(ld4(px + r * ldx), ld4(pg + r * ldd));
   }
+  bn_block_reduce(part, ql, g, qb, rg, active, C, blockIdx.y * qb, dsums, red);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, long long ldd,
@@ -317,10 +404,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                           int accumulate, int round, float* __restrict__ dgamma,
                                                           float* __restrict__ dbeta) {
   extern __shared__ float sm[];  // c1[C] = mean(dz), c2[C] = mean(dz*xhat)
+  __shared__ int is_last;
   float* c1 = sm;
   float* c2 = sm + C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double a = training ? dsums[c] : 0.0, b = training ? dsums[C + c] : 0.0;
+    const double a = training ? __ldcg(dsums + c) : 0.0, b = training ? __ldcg(dsums + C + c) : 0.0;
     c1[c] = (float)(a / (double)M);
     c2[c] = (float)(b / (double)M);
     if (training && blockIdx.x == 0) {
@@ -329,6 +417,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     }
   }
   __syncthreads();
+  if (training) {   // every block has consumed dsums once it takes a ticket: the last one leaves the scratch zeroed
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(const_cast<double*>(dsums) + 2 * C);
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+      double* z = const_cast<double*>(dsums);
+      for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) z[c] = 0.0;
+      if (threadIdx.x == 0) *ticket = 0u;
+    }
+  }
   const int cqn = C >> 2;
   const long long total = M * cqn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -560,21 +658,30 @@ extern "C" {
 
 int tpgan_dwconv3x3(tpgan_view x, tpgan_view y, const float* w, int32_t stride, void* stream) {
   if (!vec_view(x) || !vec_view(y) || !w || x.c != y.c || x.n != y.n || (stride != 1 && stride != 2) ||
-      y.h != (x.h + 2 - 3) / stride + 1 || y.w != (x.w + 2 - 3) / stride + 1 || x.c * 36 > 48 * 1024)
-    return set_error(TPGAN_ERR_INVALID, "dwconv3x3: bad geometry (C %% 4 == 0, C <= 1365, stride 1|2, pad 1)");
-  const long long total = (long long)y.n * y.h * y.w * (y.c / 4);
-  dw3x3_fwd_kernel<<<grid_cap((total + 255) / 256, 8), 256, (size_t)x.c * 36, ST>>>(pv(x), pv(y), w, stride);
+      y.h != (x.h + 2 - 3) / stride + 1 || y.w != (x.w + 2 - 3) / stride + 1)
+    return set_error(TPGAN_ERR_INVALID, "dwconv3x3: bad geometry (C %% 4 == 0, stride 1|2, pad 1)");
+  const QMap m = qmap(x.c);
+  const long long npix = (long long)y.n * y.h * y.w;
+  dim3 grid((unsigned)grid_cap((npix + m.rg * 2 - 1) / (m.rg * 2), 8), (unsigned)m.ny);
+  if (stride == 1)
+    dw3x3_fwd_kernel<1><<<grid, 256, 0, ST>>>(pv(x), pv(y), w, m.qb, m.rg);
+  else
+    dw3x3_fwd_kernel<2><<<grid, 256, 0, ST>>>(pv(x), pv(y), w, m.qb, m.rg);
   TPG_CHECK_LAUNCH("dwconv3x3");
   return 0;
 }
 
 int tpgan_dwconv3x3_dgrad(tpgan_view dy, tpgan_view dx, const float* w, int32_t stride, int32_t accumulate, void* stream) {
   if (!vec_view(dx) || !vec_view(dy) || !w || dx.c != dy.c || dx.n != dy.n || (stride != 1 && stride != 2) ||
-      dy.h != (dx.h + 2 - 3) / stride + 1 || dy.w != (dx.w + 2 - 3) / stride + 1 || dx.c * 36 > 48 * 1024)
+      dy.h != (dx.h + 2 - 3) / stride + 1 || dy.w != (dx.w + 2 - 3) / stride + 1)
     return set_error(TPGAN_ERR_INVALID, "dwconv3x3_dgrad: bad geometry");
-  const long long total = (long long)dx.n * dx.h * dx.w * (dx.c / 4);
-  dw3x3_dgrad_kernel<<<grid_cap((total + 255) / 256, 8), 256, (size_t)dx.c * 36, ST>>>(pv(dy), pv(dx), w, stride,
-                                                                                     accumulate);
+  const QMap m = qmap(dx.c);
+  const long long npix = (long long)dx.n * dx.h * dx.w;
+  dim3 grid((unsigned)grid_cap((npix + m.rg * 2 - 1) / (m.rg * 2), 8), (unsigned)m.ny);
+  if (stride == 1)
+    dw3x3_dgrad_kernel<1><<<grid, 256, 0, ST>>>(pv(dy), pv(dx), w, accumulate, m.qb, m.rg);
+  else
+    dw3x3_dgrad_kernel<2><<<grid, 256, 0, ST>>>(pv(dy), pv(dx), w, accumulate, m.qb, m.rg);
   TPG_CHECK_LAUNCH("dwconv3x3_dgrad");
   return 0;
 }
@@ -583,9 +690,14 @@ int tpgan_dwconv3x3_wgrad(tpgan_view x, tpgan_view dy, float* dw, int32_t stride
   if (!vec_view(x) || !vec_view(dy) || !dw || x.c != dy.c || x.n != dy.n || (stride != 1 && stride != 2) ||
       dy.h != (x.h + 2 - 3) / stride + 1 || dy.w != (x.w + 2 - 3) / stride + 1)
     return set_error(TPGAN_ERR_INVALID, "dwconv3x3_wgrad: bad geometry");
+  const QMap m = qmap(x.c);
   const long long npix = (long long)dy.n * dy.h * dy.w;
-  dim3 grid((unsigned)grid_cap((npix + 63) / 64, 2), (unsigned)((x.c / 4 + 31) / 32));
-  dw3x3_wgrad_kernel<<<grid, dim3(32, 8), 0, ST>>>(pv(x), pv(dy), dw, stride);
+  dim3 grid((unsigned)grid_cap((npix + m.rg * 8 - 1) / (m.rg * 8), 4), (unsigned)m.ny);   // >= 8 pixels per thread
+  const size_t smem = (size_t)m.qb * 36 * 4;
+  if (stride == 1)
+    dw3x3_wgrad_kernel<1><<<grid, 256, smem, ST>>>(pv(x), pv(dy), dw, m.qb, m.rg);
+  else
+    dw3x3_wgrad_kernel<2><<<grid, 256, smem, ST>>>(pv(x), pv(dy), dw, m.qb, m.rg);
   TPG_CHECK_LAUNCH("dwconv3x3_wgrad");
   return 0;
 }
@@ -601,15 +713,15 @@ int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* ga
   const long long M = (long long)x.n * x.h * x.w;
   const int C = x.c;
   if (training) {
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, ST);
-    if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
-    dim3 grid((unsigned)grid_cap((M + 255) / 256, 4), (unsigned)((C / 4 + 31) / 32));
-    bn_stats_kernel<<<grid, dim3(32, 8), 0, ST>>>(x.ptr, M, x.sw, C, sums);
+    const QMap m = qmap(C);
+    dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), 6), (unsigned)m.ny);   // >= 8 rows per thread
+    bn_stats_kernel<<<grid, 256, (size_t)m.rg * m.qb * 64, ST>>>(x.ptr, M, x.sw, C, sums, gamma, beta, running_mean,
+                                                                  running_var, momentum, eps, coef, m.qb, m.rg);
     TPG_CHECK_LAUNCH("bn_stats");
+  } else {
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(C, gamma, beta, running_mean, running_var, eps, coef);
+    TPG_CHECK_LAUNCH("bn_finalize");
   }
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sums, M, C, gamma, beta, running_mean, running_var, momentum, eps,
-                                                     training, coef);
-  TPG_CHECK_LAUNCH("bn_finalize");
   const long long total = M * (C / 4);
   bn_apply_kernel<<<grid_cap((total + 255) / 256, 8), 256, (size_t)C * 8, ST>>>(x.ptr, M, x.sw, C, coef, res.ptr, res.sw,
                                                                                y.ptr, y.sw, relu6, round_tf32);
@@ -625,10 +737,10 @@ int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* c
   const long long M = (long long)x.n * x.h * x.w;
   const int C = x.c;
   if (training) {
-    cudaError_t e = cudaMemsetAsync(dsums, 0, sizeof(double) * 2 * C, ST);
-    if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
-    dim3 grid((unsigned)grid_cap((M + 255) / 256, 4), (unsigned)((C / 4 + 31) / 32));
-    bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, ST>>>(dy.ptr, dy.sw, x.ptr, x.sw, M, C, coef, relu6, dsums);
+    const QMap m = qmap(C);
+    dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), 6), (unsigned)m.ny);
+    bn_bwd_reduce_kernel<<<grid, 256, (size_t)m.rg * m.qb * 64, ST>>>(dy.ptr, dy.sw, x.ptr, x.sw, M, C, coef, relu6, dsums,
+                                                                       m.qb, m.rg);
     TPG_CHECK_LAUNCH("bn_bwd_reduce");
   }
   const long long total = M * (C / 4);
