@@ -222,3 +222,19 @@ def test_gloo_world2_pretrain_gradient_is_the_mean_of_the_replicas():
     ret = mgr.dict()
     tmp.spawn(_dp_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret["err"] < 1e-6, ret["err"]
+
+
+def test_save_model_writes_a_reference_loadable_checkpoint(tmp_path):
+    """save_model (UtilityMethods.py:58-76) on the drop-in module -> the file loads into the reference-layout network."""
+    from tpgan_b200.MobileNetV2 import MobileNetV2
+    from tpgan_b200.UtilityMethods import save_model
+    torch.manual_seed(3)
+    net = MobileNetV2()
+    path = save_model(net, str(tmp_path / "ckpt"), 4)
+    assert path.endswith("model_epoch_4.pth")
+    port = P.MobileNetV2Port()
+    port.load_state_dict(torch.load(path), strict=True)
+    assert all(torch.equal(a, b) for a, b in zip(port.state_dict().values(), net.state_dict().values()))
+    if os.path.isfile(os.path.join(REF, "MobileNetV2.py")):
+        ref = _ref().MobileNetV2()
+        ref.load_state_dict(torch.load(path), strict=True)

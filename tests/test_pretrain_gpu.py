@@ -371,3 +371,42 @@ def test_full_size_step_properties():
     for _ in range(10):
         last = tr.step(xs, ts, us)["loss"]
     assert last < first, (first, last)
+
+
+def test_checkpoint_helpers_round_trip(tmp_path):
+    """save_model / save_optimizer (UtilityMethods.py:58-103) on the trainer's model and fused optimizer state: the files
+    load into the oracle network and a stock torch.optim.SGD, and back into a fresh trainer."""
+    from oracle import pretrain_port as P
+    from tpgan_b200.MobileNetV2 import MobileNetV2
+    from tpgan_b200.pretrain_step import PretrainTrainer
+    from tpgan_b200.UtilityMethods import save_model, save_optimizer
+    port, net = _nets(seed=6)
+    tr = PretrainTrainer(net, 2)
+    x, true, u = P.make_batch(2, seed=50)
+    for _ in range(2):
+        tr.step(x.cuda(), true.cuda(), u.cuda())
+    tr.sync_buffers()
+    mpath = save_model(net, str(tmp_path / "run"), 3)
+    opath = save_optimizer(tr.optimizer, net, str(tmp_path / "run"), 3)
+    assert mpath.endswith("model_epoch_3.pth") and opath.endswith("optimizer_epoch_3.pth")
+    sd = torch.load(mpath, map_location="cpu")
+    port.load_state_dict(sd, strict=True)                       # reference-layout keys and shapes
+    ck = torch.load(opath, map_location="cpu")
+    assert set(ck) == {"optimizer", "model", "epoch"} and ck["epoch"] == 3
+    opt = torch.optim.SGD(port.parameters(), **P.SGD)
+    opt.load_state_dict(ck["optimizer"])                        # a stock optimizer accepts the fused state
+    bufs = [opt.state[p]["momentum_buffer"] for p in port.parameters()]
+    assert len(bufs) == 197 and all(float(b.abs().sum()) > 0 for b in bufs[:5])
+    g = opt.param_groups[0]
+    assert (g["lr"], g["momentum"], g["weight_decay"], g["nesterov"]) == (5e-4, 0.9, 5e-4, True)
+    # and back: a fresh trainer resumes with identical parameters and momentum
+    torch.manual_seed(123)
+    net2 = MobileNetV2().cuda()
+    net2.load_state_dict(torch.load(mpath))
+    tr2 = PretrainTrainer(net2, 2)
+    tr2.optimizer.load_state_dict(torch.load(opath)["optimizer"])
+    assert torch.equal(tr2.flat.m, tr.flat.m) and torch.equal(tr2.flat.data, tr.flat.data)
+    a = tr.step(x.cuda(), true.cuda(), u.cuda())
+    b = tr2.step(x.cuda(), true.cuda(), u.cuda())
+    assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(a["loss"])
+    assert rel(tr2.flat.data, tr.flat.data) < 1e-6

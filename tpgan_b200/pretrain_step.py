@@ -18,7 +18,7 @@ import torch
 from . import ops
 from .engine import GradArena, Plan
 from .MobileNetV2 import MobileNetV2
-from .train_step import Eager, FlatParams, GraphRunner, LayerSet
+from .train_step import Eager, FlatOptimizer, FlatParams, GraphRunner, LayerSet
 
 # config.py:25-35 (pretrain['loss'], optimizer_param); the reference module itself is not imported by the product
 LOSS = dict(alpha=30.0, beta=0.1, ratio_non_background=5.0, distance_threshold_ratio=0.1)
@@ -37,6 +37,10 @@ class PretrainTrainer:
         model.train()
         self.flat = FlatParams(model)                      # params + .grad as views of flat buffers (m = momentum buffer)
         self.lr_dev = torch.full((1,), OPTIM["learning_rate"], dtype=torch.float32, device=self.device)
+        # what getOptimizer(model.parameters(), 'SGD')() would hold; save_optimizer(tr.optimizer, model, dir, epoch) works
+        self.optimizer = FlatOptimizer(self.flat, model, "sgd", dict(lr=OPTIM["learning_rate"], momentum=OPTIM["momentum"],
+                                                                     weight_decay=OPTIM["weight_decay"],
+                                                                     nesterov=OPTIM["nesterov"]))
         self.epoch = 0
         plan = Plan(self.device, training=True, need_wgrad=True, exact=exact, defer_bias=True)
         plan.direct_grads = True

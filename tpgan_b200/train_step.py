@@ -80,6 +80,60 @@ class FlatParams:
                           grad_scale)
 
 
+class FlatOptimizer:
+    """torch.optim-compatible view of the fused optimizer state kept in a FlatParams (momentum / Adam moments as flat
+    buffers, step count on the device), so that the reference's checkpoint helpers work unchanged:
+    `save_optimizer(trainer.optimizer, model, dir, epoch)` (UtilityMethods.py:78-103) writes the same
+    {'optimizer', 'model', 'epoch'} file a torch.optim.SGD / Adam over `module.parameters()` would, and a file written
+    by the reference's loop loads back with load_state_dict()."""
+
+    def __init__(self, flat: "FlatParams", module: torch.nn.Module, kind: str, hyper: Dict[str, float]):
+        assert kind in ("sgd", "adam")
+        self.flat, self.module, self.kind, self.hyper = flat, module, kind, dict(hyper)
+
+    def _template_group(self) -> dict:
+        p = [torch.nn.Parameter(torch.zeros(1))]
+        opt = torch.optim.SGD(p, **self.hyper) if self.kind == "sgd" else torch.optim.Adam(p, **self.hyper)
+        return dict(opt.state_dict()["param_groups"][0])
+
+    def _slices(self):
+        for i, (name, p) in enumerate(self.module.named_parameters()):
+            o = self.flat.offsets[name]
+            yield i, p, slice(o, o + p.numel())
+
+    def state_dict(self) -> dict:
+        state = {}
+        steps = int(self.flat.step_dev.item()) if self.kind == "adam" else 0
+        for i, p, sl in self._slices():
+            if self.kind == "sgd":
+                state[i] = {"momentum_buffer": self.flat.m[sl].view(p.shape).clone()}
+            else:
+                state[i] = {"step": torch.tensor(float(steps)), "exp_avg": self.flat.m[sl].view(p.shape).clone(),
+                            "exp_avg_sq": self.flat.v[sl].view(p.shape).clone()}
+        group = self._template_group()
+        group["params"] = list(range(len(state)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict):
+        n = sum(1 for _ in self.module.parameters())
+        ids = sd["param_groups"][0]["params"]
+        if len(sd["param_groups"]) != 1 or len(ids) != n:
+            raise ValueError("optimizer state does not match the module's parameter list")
+        for i, p, sl in self._slices():
+            st = sd["state"].get(ids[i], sd["state"].get(str(ids[i])))
+            if st is None:                       # torch omits parameters that never received a gradient
+                self.flat.m[sl].zero_()
+                self.flat.v[sl].zero_()
+                continue
+            if self.kind == "sgd":
+                self.flat.m[sl].copy_(st["momentum_buffer"].flatten())
+            else:
+                self.flat.m[sl].copy_(st["exp_avg"].flatten())
+                self.flat.v[sl].copy_(st["exp_avg_sq"].flatten())
+                self.flat.step_dev.fill_(int(st["step"]))
+                self.flat.step = int(st["step"])
+
+
 class LayerSet:
     """Re-packing (after the optimizer) and gradient export (after backward) of a set of layers as multi-tensor launches:
     one pack, one transpose and one unpack launch for all eligible layers, individual calls for the few special ones
@@ -472,6 +526,8 @@ class TPGANTrainer:
         order = self._ready_order()
         self.flat_g = FlatParams(G, order)
         self.flat_d = FlatParams(D)
+        adam = dict(lr=self.lr)      # torch.optim.Adam defaults otherwise, as FlatParams.adam
+        self.optimizer_g, self.optimizer_d = FlatOptimizer(self.flat_g, G, "adam", adam), FlatOptimizer(self.flat_d, D, "adam", adam)
         self.g_set = LayerSet(self.plan.layers, self.device, self.plan.bias_jobs)
         self.d_set = LayerSet(self.critic.layers, self.device)
         self.g_set.repack()
