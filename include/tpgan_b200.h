@@ -273,6 +273,16 @@ TPGAN_API int tpgan_multitask_loss(const float* loc, const float* cls, const flo
                                    float beta, float ratio_non_background, float coeff, float* dloc, float* dcls,
                                    int32_t* labels, float* sums, void* stream);
 
+/* MultiTaskDecoder.forward (MobileNetV2.py:536-649) for the whole batch: per class, candidates = softmax score >
+ * confidence_threshold; greedy distance-NMS in descending score order (a kept point removes the remaining ones within
+ * nms_distance); the first top_k kept points are the detections.  Fixed-shape outputs: count[B][K], score[B][K][top_k],
+ * point[B][K][top_k][2] (unused slots zero).  accuracy[B] (optional, with truth[B][8]) = _calculate_accuracy
+ * (Pretrain.py:17-64) on the top-1 point of the four landmark classes; a class without detection contributes 0. */
+TPGAN_API int tpgan_ssd_decode(const float* loc, const float* cls, int32_t batch, int32_t n, int64_t loc_stride,
+                               int64_t cls_stride, int32_t num_classes, int32_t top_k, float confidence_threshold,
+                               float nms_distance, int32_t* count, float* score, float* point, const float* truth,
+                               float* accuracy, void* stream);
+
 /* torch.optim.SGD(momentum, weight_decay, nesterov) over a flat fp32 bucket (getOptimizer 'SGD', UtilityMethods.py:30,
  * config.py:31-35); buf must start zeroed; the learning rate is read from device memory (MultiStepLR, Pretrain.py:117-121,
  * without re-capturing a CUDA graph). */

@@ -287,3 +287,47 @@ def forward_tf32_emulated(model: MobileNetV2Port, x: torch.Tensor):
             c = dense(model.ssd_head.classification_layer[i], f).permute(0, 2, 3, 1).contiguous()
             clss.append(c.view(c.size(0), -1, NUM_CLASSES))
         return torch.cat(locs, 1), torch.cat(clss, 1)
+
+
+# ------------------------------------------------------------------------------------------------------ decoder / accuracy
+def decode_sample(loc: torch.Tensor, cls: torch.Tensor, confidence_threshold=0.5, top_k=1, nms_distance_threshold=20.0):
+    """MultiTaskDecoder.forward + nms (MobileNetV2.py:552-649) for one sample, as fixed-shape tensors:
+    count (K,), score (K, top_k), point (K, top_k, 2).  Greedy distance-NMS in descending score order followed by top_k
+    == top_k rounds of { arg-max among live candidates; drop everything within the distance threshold }."""
+    K = cls.shape[1]
+    scores = torch.softmax(cls, dim=-1)
+    count = torch.zeros(K, dtype=torch.int32)
+    score = torch.zeros(K, top_k)
+    point = torch.zeros(K, top_k, 2)
+    for c in range(K):
+        s = torch.where(scores[:, c] > confidence_threshold, scores[:, c], torch.full_like(scores[:, c], -1.0))
+        for t in range(top_k):
+            best = s.max()
+            if float(best) <= 0:
+                break
+            bi = int((s == best).nonzero()[0])            # lowest index among equal scores
+            score[c, t], point[c, t] = best, loc[bi]
+            count[c] += 1
+            d = torch.norm(loc - loc[bi], dim=1)
+            s = torch.where(d > nms_distance_threshold, s, torch.full_like(s, -1.0))
+            s[bi] = -1.0
+    return count, score, point
+
+
+def accuracy_sample(count, point, true8) -> float:
+    """_calculate_accuracy (Pretrain.py:17-64) on the top-1 detections of the four landmark classes.  The reference indexes
+    `predicts[:-1]` and therefore only works when every class (incl. background) has exactly one detection; for that case
+    this is the same number.  ORACLE-DEFINED otherwise: a landmark class without detection contributes 0."""
+    thresholds, weights = [5, 10, 18, 30, 45], [1.0, 0.9, 0.65, 0.35, 0.1]
+    gt = true8.view(4, 2)
+    acc = 0.0
+    for c in range(4):
+        if int(count[c]) == 0:
+            continue
+        d = float(torch.sqrt(((point[c, 0] - gt[c]) ** 2).sum()))
+        prev = 0
+        for th, w in zip(thresholds, weights):
+            if prev < d <= th:
+                acc += w
+            prev = th
+    return acc / 4.0

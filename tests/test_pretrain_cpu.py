@@ -238,3 +238,37 @@ def test_save_model_writes_a_reference_loadable_checkpoint(tmp_path):
     if os.path.isfile(os.path.join(REF, "MobileNetV2.py")):
         ref = _ref().MobileNetV2()
         ref.load_state_dict(torch.load(path), strict=True)
+
+
+# ---------------------------------------------------------------------------------------------- decoder / accuracy (row f4)
+def test_decoder_known_answer():
+    """Temp.py:7-29,55-61 with nms_distance_threshold=30: one detection, class 1, confidence 0.5148, point (370, 150)."""
+    loc, cls, _ = _temp_py_inputs()
+    count, score, point = P.decode_sample(loc[0], cls[0], 0.5, 1, 30.0)
+    assert count.tolist() == [0, 1, 0, 0, 0]
+    assert float(score[1, 0]) == pytest.approx(0.5148, abs=5e-5) and point[1, 0].tolist() == [370.0, 150.0]
+
+
+@needs_ref
+def test_decoder_and_accuracy_match_live_reference():
+    R = _ref()
+    import Pretrain as PT     # has a __main__ guard; importing defines _calculate_accuracy only
+    for seed in range(4):
+        g = torch.Generator().manual_seed(seed)
+        loc = torch.rand((1, 394, 2), generator=g) * 128
+        cls = torch.randn((1, 394, 5), generator=g) * 3
+        for top_k, thr, nms in ((1, 0.5, 20), (3, 0.6, 15), (8, 0.3, 40)):
+            live = R.MultiTaskDecoder(thr, top_k, nms)(loc, cls)[0]
+            count, score, point = P.decode_sample(loc[0], cls[0], thr, top_k, float(nms))
+            mine = [(c, float(score[c, t]), point[c, t].tolist()) for c in range(5) for t in range(int(count[c]))]
+            assert len(mine) == len(live)
+            for (c, s, p), (lc, ls, lp) in zip(mine, live):
+                assert c == lc and abs(s - float(ls)) < 1e-7 and p == lp.tolist()
+    g = torch.Generator().manual_seed(3)          # a case where every class has exactly one detection (the reference's
+    loc = torch.rand((1, 50, 2), generator=g) * 128    # accuracy only works then)
+    cls = torch.randn((1, 50, 5), generator=g) * 6
+    true = torch.rand((1, 8), generator=g) * 128
+    live = R.MultiTaskDecoder(0.5, 1, 20)(loc, cls)[0]
+    assert [c for c, _, _ in live] == [0, 1, 2, 3, 4]
+    count, _, point = P.decode_sample(loc[0], cls[0], 0.5, 1, 20.0)
+    assert P.accuracy_sample(count, point, true[0]) == pytest.approx(PT._calculate_accuracy(live, true), abs=1e-6)

@@ -410,3 +410,44 @@ def test_checkpoint_helpers_round_trip(tmp_path):
     b = tr2.step(x.cuda(), true.cuda(), u.cuda())
     assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(a["loss"])
     assert rel(tr2.flat.data, tr.flat.data) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ decoder (row f4)
+@pytest.mark.parametrize("top_k,thr,nms", [(1, 0.5, 20.0), (3, 0.6, 15.0), (8, 0.3, 40.0)])
+def test_decoder_matches_oracle(top_k, thr, nms):
+    from oracle import pretrain_port as P
+    from tpgan_b200.MobileNetV2 import MultiTaskDecoder
+    g = torch.Generator().manual_seed(int(nms))
+    B, n = 6, 394
+    loc = torch.rand((B, n, 2), generator=g) * 128
+    cls = torch.randn((B, n, 5), generator=g) * 3
+    loc[:, 7] = loc[:, 3]                                  # duplicate points (distance 0 <= threshold: suppressed)
+    true = torch.rand((B, 8), generator=g) * 128
+    true[0, 0:2] = loc[0, 0]
+    dec = MultiTaskDecoder(thr, top_k, nms)
+    count, score, point, acc = dec.decode(loc.cuda(), cls.cuda(), true.cuda())
+    for b in range(B):
+        c_w, s_w, p_w = P.decode_sample(loc[b], cls[b], thr, top_k, nms)
+        assert torch.equal(count[b].cpu(), c_w), b
+        assert torch.equal(point[b].cpu(), p_w), b                      # selected points: bit-exact
+        assert torch.allclose(score[b].cpu(), s_w, rtol=0, atol=2e-6), b
+        assert abs(float(acc[b]) - P.accuracy_sample(c_w, p_w, true[b])) < 1e-6, b
+    out = dec(loc.cuda(), cls.cuda())                                   # the reference's list-of-tuples structure
+    assert len(out) == B and sum(len(o) for o in out) == int(count.sum())
+    c0, s0, p0 = out[0][0]
+    assert isinstance(c0, int) and s0.shape == () and p0.shape == (2,)
+
+
+def test_decoder_known_answer():
+    """Temp.py:7-29,55-61: one detection - class 1, confidence 0.5148, point (370, 150)."""
+    from tpgan_b200.MobileNetV2 import MultiTaskDecoder
+    loc = torch.tensor([[[1.0, 1.0], [420.0, 360.0], [370.0, 150.0], [180.0, 220.0], [330.0, 270.0], [290.0, 135.0],
+                         [500.0, 380.0], [190.0, 400.0], [210.0, 420.0], [510.0, 70.0], [178.0, 321.0], [420.0, 110.0]]])
+    cls = torch.tensor([[[2.0, 1.0, 0.1, 0.5, 1.4], [1.0, 2.0, 0.1, 0.3, 1.1], [0.1, 2.0, 1.0, 0.4, 0.5],
+                         [2.0, 0.1, 1.0, 0.7, 0.5], [1.0, 0.1, 1.4, 0.8, 2.0], [0.1, 1.0, 2.0, 0.6, 0.7],
+                         [2.0, 1.0, 0.1, 0.9, 1.5], [1.0, 0.8, 0.1, 1.1, 2.0], [0.1, 1.2, 1.0, 2.0, 0.5],
+                         [2.0, 0.1, 1.0, 1.3, 0.6], [1.0, 0.1, 2.0, 1.4, 1.6], [0.1, 1.0, 1.3, 1.5, 2.0]]])
+    out = MultiTaskDecoder(nms_distance_threshold=30)(loc.cuda(), cls.cuda())[0]
+    assert len(out) == 1
+    c, s, p = out[0]
+    assert c == 1 and abs(float(s) - 0.5148) < 5e-5 and p.tolist() == [370.0, 150.0]

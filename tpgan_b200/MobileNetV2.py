@@ -319,3 +319,50 @@ class MultiTaskLoss(nn.Module):
         return _MTLFn.apply(locations_pred, classifications_pred, locations_true, u.float().contiguous(), tuple(image_size),
                             float(self.alpha), float(self.beta), float(self.distance_threshold_ratio),
                             float(self.ratio_non_background), self)
+
+
+# ---------------------------------------------------------------------------------------------------- decoder
+class MultiTaskDecoder(nn.Module):
+    """MobileNetV2.py:536-649 on the device: ONE launch decodes the whole batch (softmax, confidence filter, greedy
+    distance-NMS, top-k per class) instead of a Python loop with a sort and a host sync per kept point.
+
+    forward(locations, classifications) returns the reference's structure - per sample a list of
+    (class_idx, score tensor, point tensor (2,)) in class order, best first - built from the fixed-shape device outputs with a
+    single device-to-host read.  decode(...) returns those device tensors without synchronising:
+    count (B,K) int32, score (B,K,top_k), point (B,K,top_k,2) and, given the ground truth (B,8), accuracy (B,) =
+    `_calculate_accuracy` of Pretrain.py:17-64 on the top-1 landmark detections."""
+
+    def __init__(self, confidence_threshold=0.5, top_k=1, nms_distance_threshold=20):
+        super().__init__()
+        self.confidence_threshold = confidence_threshold
+        self.top_k = top_k
+        self.nms_distance_threshold = nms_distance_threshold
+
+    def decode(self, locations, classifications, locations_true: Optional[torch.Tensor] = None):
+        if not locations.is_cuda:
+            raise RuntimeError("tpgan_b200.MultiTaskDecoder runs on CUDA tensors only (there is no CPU fallback)")
+        B, n, K = classifications.shape
+        loc, cls = locations.detach().float().contiguous(), classifications.detach().float().contiguous()
+        dev = loc.device
+        count = torch.zeros((B, K), dtype=torch.int32, device=dev)
+        score = torch.empty((B, K, self.top_k), dtype=torch.float32, device=dev)
+        point = torch.empty((B, K, self.top_k, 2), dtype=torch.float32, device=dev)
+        truth = acc = None
+        if locations_true is not None:
+            truth = locations_true.detach().float().contiguous().view(B, 8)
+            acc = torch.empty(B, dtype=torch.float32, device=dev)
+        ops.ssd_decode(loc, cls, n, 2 * n, K * n, K, int(self.top_k), float(self.confidence_threshold),
+                       float(self.nms_distance_threshold), count, score, point, truth, acc)
+        return count, score, point, acc
+
+    def forward(self, locations, classifications):
+        count, score, point, _ = self.decode(locations, classifications)
+        cnt = count.cpu()                                   # the one host read
+        out = []
+        for b in range(cnt.shape[0]):
+            res = []
+            for c in range(cnt.shape[1]):
+                for t in range(int(cnt[b, c])):
+                    res.append((c, score[b, c, t], point[b, c, t]))
+            out.append(res)
+        return out

@@ -105,6 +105,7 @@ SYMBOLS = {
     "tpgan_rows_gather": (C.c_int, [View, _VP, _I64, _I64, _I32, _VP]),
     "tpgan_multitask_loss": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I64, _I64, _I32, _I32, _F, _F, _F, _F, _F, _F, _VP, _VP, _VP,
                                        _VP, _VP]),
+    "tpgan_ssd_decode": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I64, _I32, _I32, _F, _F, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tpgan_sgd_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _F, _F, _I32, _F, _VP]),
     "tpgan_last_error": (C.c_char_p, []),
     "tpgan_abi_version": (C.c_int, []),

@@ -624,6 +624,92 @@ __global__ void __launch_bounds__(256) multitask_loss_kernel(MtlArgs A) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------- MultiTaskDecoder
+// MobileNetV2.py:536-649 + _calculate_accuracy (Pretrain.py:17-64), one CTA per sample.  Per class: candidates = points
+// whose softmax score exceeds the confidence threshold; greedy distance-NMS in descending score order keeps a point and
+// drops every remaining one within nms_dist of it; the first top_k kept points are the detections.  Equivalent
+// formulation without a sort: repeat top_k times { arg-max score among live candidates (lowest index on ties); record;
+// kill candidates with distance <= nms_dist }.  Outputs are fixed-shape: count[B][K], score[B][K][top_k],
+// point[B][K][top_k][2] (unused slots zero).  accuracy[B] (optional, needs truth[B][8]): mean over the four landmark
+// classes of the distance-bucket weight of the class's top-1 point (no detection = 0).
+__global__ void __launch_bounds__(256) ssd_decode_kernel(const float* __restrict__ loc, const float* __restrict__ cls,
+                                                        long long loc_stride, long long cls_stride, int n, int K, int top_k,
+                                                        float conf_thr, float nms_dist, int* __restrict__ count,
+                                                        float* __restrict__ score, float* __restrict__ point,
+                                                        const float* __restrict__ truth, float* __restrict__ accuracy) {
+  extern __shared__ float smd[];
+  float* px = smd;          // [n]
+  float* py = px + n;       // [n]
+  float* sc = py + n;       // [n] score of the current class, -1 = not a candidate / suppressed
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  __shared__ float best_x, best_y, acc_sum;
+  __shared__ int best_i;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) acc_sum = 0.f;
+  for (int i = tid; i < n; i += blockDim.x) {
+    px[i] = loc[b * loc_stride + 2 * i];
+    py[i] = loc[b * loc_stride + 2 * i + 1];
+  }
+  __syncthreads();
+  for (int c = 0; c < K; ++c) {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const float* z = cls + b * cls_stride + (long long)i * K;
+      float mx = z[0];
+      for (int k = 1; k < K; ++k) mx = fmaxf(mx, z[k]);
+      float sum = 0.f;
+      for (int k = 0; k < K; ++k) sum += expf(z[k] - mx);
+      const float p = expf(z[c] - mx) / sum;
+      sc[i] = p > conf_thr ? p : -1.f;
+    }
+    __syncthreads();
+    int found = 0;
+    for (int t = 0; t < top_k; ++t) {
+      float bv = -1.f;
+      int bi = 0x7fffffff;
+      for (int i = tid; i < n; i += blockDim.x)
+        if (sc[i] > bv) bv = sc[i], bi = i;          // ascending i: the lowest index wins ties within a thread
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+      }
+      if ((tid & 31) == 0) red_v[tid >> 5] = bv, red_i[tid >> 5] = bi;
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) bv = red_v[w], bi = red_i[w];
+        best_i = bv > 0.f ? bi : -1;
+        if (bv > 0.f) {
+          best_x = px[bi], best_y = py[bi];
+          const long long o = ((long long)b * K + c) * top_k + t;
+          score[o] = bv;
+          point[2 * o] = best_x, point[2 * o + 1] = best_y;
+        }
+      }
+      __syncthreads();
+      if (best_i < 0) break;
+      ++found;
+      if (c < 4 && t == 0 && truth && tid == 0) {     // Pretrain.py:33-58: bucket weights of the top-1 distance
+        const float dx = best_x - truth[b * 8 + 2 * c], dy = best_y - truth[b * 8 + 2 * c + 1];
+        const float d = sqrtf(dx * dx + dy * dy);
+        const float w = (d > 0.f && d <= 5.f) ? 1.0f : (d <= 10.f && d > 5.f) ? 0.9f : (d <= 18.f && d > 10.f) ? 0.65f
+                        : (d <= 30.f && d > 18.f) ? 0.35f : (d <= 45.f && d > 30.f) ? 0.1f : 0.f;
+        acc_sum += w;
+      }
+      for (int i = tid; i < n; i += blockDim.x) {
+        const float dx = px[i] - best_x, dy = py[i] - best_y;
+        if (i == best_i || !(sqrtf(dx * dx + dy * dy) > nms_dist)) sc[i] = -1.f;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) count[b * K + c] = found;
+    __syncthreads();
+  }
+  if (tid == 0 && accuracy) accuracy[b] = acc_sum * 0.25f;
+}
+
 // ------------------------------------------------------------------------------------------------- SGD (Nesterov)
 // torch.optim.SGD(lr, momentum, weight_decay, nesterov=True), UtilityMethods.py:30 / config.py:31-35, dampening 0:
 //   g = grad_scale*g + wd*p ; buf = momentum*buf + g (a zero-initialised buf reproduces torch's first step buf = g) ;
@@ -770,6 +856,23 @@ int tpgan_multitask_loss(const float* loc, const float* cls, const float* truth,
             ratio_non_background, coeff};
   multitask_loss_kernel<<<batch, 256, (size_t)n * 9 * 4, ST>>>(A);
   TPG_CHECK_LAUNCH("multitask_loss");
+  return 0;
+}
+
+int tpgan_ssd_decode(const float* loc, const float* cls, int32_t batch, int32_t n, int64_t loc_stride, int64_t cls_stride,
+                     int32_t num_classes, int32_t top_k, float confidence_threshold, float nms_distance, int32_t* count,
+                     float* score, float* point, const float* truth, float* accuracy, void* stream) {
+  if (!loc || !cls || !count || !score || !point || batch < 1 || n < 1 || n > 4096 || num_classes < 1 || num_classes > 8 ||
+      top_k < 1 || top_k > 64 || loc_stride < 2ll * n || cls_stride < (long long)num_classes * n || (accuracy && !truth))
+    return set_error(TPGAN_ERR_INVALID, "ssd_decode: bad arguments (n <= 4096, classes <= 8, top_k <= 64)");
+  const size_t bytes = (size_t)batch * num_classes * top_k * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(score, 0, bytes, ST);
+  if (e == cudaSuccess) e = cudaMemsetAsync(point, 0, 2 * bytes, ST);
+  if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  ssd_decode_kernel<<<batch, 256, (size_t)n * 12, ST>>>(loc, cls, loc_stride, cls_stride, n, num_classes, top_k,
+                                                       confidence_threshold, nms_distance, count, score, point, truth,
+                                                       accuracy);
+  TPG_CHECK_LAUNCH("ssd_decode");
   return 0;
 }
 

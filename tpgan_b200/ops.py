@@ -437,3 +437,15 @@ def sgd_step(p: torch.Tensor, g: torch.Tensor, buf: torch.Tensor, lr_dev: torch.
     """torch.optim.SGD (UtilityMethods.py:30) over flat buffers; lr read from device memory."""
     _lib.check(_lib.load().tpgan_sgd_step(_ptr(p), _ptr(g), _ptr(buf), p.numel(), _ptr(lr_dev), momentum, weight_decay,
                                           int(nesterov), grad_scale, _stream()), "sgd_step")
+
+
+def ssd_decode(loc: torch.Tensor, cls: torch.Tensor, n: int, loc_stride: int, cls_stride: int, num_classes: int, top_k: int,
+               confidence_threshold: float, nms_distance: float, count: torch.Tensor, score: torch.Tensor,
+               point: torch.Tensor, truth: Optional[torch.Tensor] = None, accuracy: Optional[torch.Tensor] = None) -> None:
+    """Batched MultiTaskDecoder (+ _calculate_accuracy); see include/tpgan_b200.h."""
+    B = count.shape[0]
+    assert count.dtype == torch.int32 and count.numel() == B * num_classes
+    assert score.numel() == B * num_classes * top_k and point.numel() == 2 * score.numel()
+    _lib.check(_lib.load().tpgan_ssd_decode(_ptr(loc), _ptr(cls), B, n, loc_stride, cls_stride, num_classes, top_k,
+                                            confidence_threshold, nms_distance, _ptr(count), _ptr(score), _ptr(point),
+                                            _ptr(truth), _ptr(accuracy), _stream()), "ssd_decode")
