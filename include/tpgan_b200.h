@@ -289,6 +289,19 @@ TPGAN_API int tpgan_ssd_decode(const float* loc, const float* cls, int32_t batch
 TPGAN_API int tpgan_sgd_step(float* p, const float* g, float* buf, int64_t n, const float* lr_dev, float momentum,
                              float weight_decay, int32_t nesterov, float grad_scale, void* stream);
 
+/* ---- device-side input pipeline (DataAndDataset.py:179-256, UtilityMethods.py:146-164) ---------------- */
+
+/* transforms.ToTensor() then *2.0 - 1.0 (DataAndDataset.py:214-220,251-255): uint8 HWC bytes [N][H][W][C] -> fp32 NHWC view
+ * in [-1, 1], bit-identical to torch's three fp32 operations ((b / 255) * 2 - 1); optional tf32 rounding. */
+TPGAN_API int tpgan_u8_to_nhwc(const uint8_t* src, tpgan_view dst, int32_t round_tf32, void* stream);
+/* get_5_landmarks_pixal_position (UtilityMethods.py:146-164): out[n][j] = mean of points[n][lo_j..hi_j] (inclusive index
+ * ranges, ranges_dev = device int32[nranges][2]; a range outside the list gives NaN, as np.mean of an empty slice does),
+ * x scaled by scale_x and y by scale_y (the 128/width, 128/height rescale of TestDataset, DataAndDataset.py:242-245). */
+TPGAN_API int tpgan_landmarks_reduce(const float* points, int32_t batch, int32_t npoints, const int32_t* ranges_dev,
+                                     int32_t nranges, float scale_x, float scale_y, float* out, void* stream);
+/* half = 2x2 and quarter = 4x4 average pool of src in one pass (the 64x64 / 32x32 targets of the oracle step). */
+TPGAN_API int tpgan_pyramid(tpgan_view src, tpgan_view half, tpgan_view quarter, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------------- */
 TPGAN_API const char* tpgan_last_error(void);
 TPGAN_API int tpgan_abi_version(void);

@@ -107,6 +107,9 @@ SYMBOLS = {
                                        _VP, _VP]),
     "tpgan_ssd_decode": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _I64, _I32, _I32, _F, _F, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tpgan_sgd_step": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _F, _F, _I32, _F, _VP]),
+    "tpgan_u8_to_nhwc": (C.c_int, [_VP, View, _I32, _VP]),
+    "tpgan_landmarks_reduce": (C.c_int, [_VP, _I32, _I32, _VP, _I32, _F, _F, _VP, _VP]),
+    "tpgan_pyramid": (C.c_int, [View, View, View, _VP]),
     "tpgan_last_error": (C.c_char_p, []),
     "tpgan_abi_version": (C.c_int, []),
     "tpgan_kernel_status": (C.c_int, []),

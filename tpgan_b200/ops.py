@@ -449,3 +449,26 @@ def ssd_decode(loc: torch.Tensor, cls: torch.Tensor, n: int, loc_stride: int, cl
     _lib.check(_lib.load().tpgan_ssd_decode(_ptr(loc), _ptr(cls), B, n, loc_stride, cls_stride, num_classes, top_k,
                                             confidence_threshold, nms_distance, _ptr(count), _ptr(score), _ptr(point),
                                             _ptr(truth), _ptr(accuracy), _stream()), "ssd_decode")
+
+
+# ---------------------------------------------------------------------------------------------------------- input pipeline
+def u8_to_nhwc(src: torch.Tensor, dst: Act, round_tf32: bool = False) -> None:
+    """uint8 (N,H,W,C) -> fp32 NHWC in [-1,1]: ToTensor()*2-1 (DataAndDataset.py:214-220)."""
+    assert src.dtype == torch.uint8 and src.is_contiguous() and tuple(src.shape) == (dst.n, dst.h, dst.w, dst.c)
+    _lib.check(_lib.load().tpgan_u8_to_nhwc(_ptr(src), dst.view(), int(round_tf32), _stream()), "u8_to_nhwc")
+
+
+def landmarks_reduce(points: torch.Tensor, ranges: torch.Tensor, out: torch.Tensor, scale_x: float = 1.0,
+                     scale_y: float = 1.0) -> None:
+    """(N,P,2) landmark lists -> (N,R,2) means over inclusive index ranges (UtilityMethods.py:146-164)."""
+    assert points.dtype == torch.float32 and points.is_contiguous() and ranges.dtype == torch.int32
+    N, P = points.shape[0], points.shape[1]
+    R = ranges.shape[0]
+    assert tuple(out.shape) == (N, R, 2) and out.is_contiguous()
+    _lib.check(_lib.load().tpgan_landmarks_reduce(_ptr(points), N, P, _ptr(ranges), R, scale_x, scale_y, _ptr(out), _stream()),
+               "landmarks_reduce")
+
+
+def pyramid(src: Act, half: Act, quarter: Act) -> None:
+    """2x2 and 4x4 average pools of src in one pass."""
+    _lib.check(_lib.load().tpgan_pyramid(src.view(), half.view(), quarter.view(), _stream()), "pyramid")
