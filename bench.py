@@ -147,7 +147,14 @@ def run_b200(a):
     D = M.Discriminator(config.D["use_batchnorm"])
     G.to(dev)
     D.to(dev)
-    tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world, use_graphs=not a.no_graphs)
+    ident = None
+    if a.identity:   # BASELINE configs[2]: frozen FeatureExtract (ResNet18-128) identity-preserving loss (tf32 here; bf16 is not built)
+        from tpgan_b200.FeatureExtract import FeatureExtractModel
+        from tpgan_b200.ResNet import BasicBlock
+        ident = FeatureExtractModel("resnet", config.G["num_classes"], residualBlock=BasicBlock,
+                                    feature_layer_dim_before_FC=256).to(dev).eval()
+    tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world, use_graphs=not a.no_graphs,
+                      identity_net=ident)
     host = ostep.make_batch(B, seed=1234 + rank)
     keys = ("img", "img_frontal", "img64_frontal", "img32_frontal", "landmarks", "z", "label", "gp_alpha")
     host = {k: host[k].contiguous().pin_memory() for k in keys}
@@ -269,7 +276,8 @@ def run_b200(a):
                 "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
                 "config": {"workload": f"TP-GAN G+D training step (WGAN-GP critic + all G losses + Adam), batch {B}/GPU, "
-                                       "128x128 synthetic faces + 4 landmark patches, dropout on",
+                                       "128x128 synthetic faces + 4 landmark patches, dropout on" +
+                                       (", + frozen ResNet18 identity-preserving loss" if a.identity else ""),
                            "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
                            "l2": "activations per step (~8 GB) exceed the 126 MB L2; no explicit flush",
                            "cuda_graphs": not a.no_graphs},
@@ -470,6 +478,7 @@ def main():
                          "step (configs[4])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-layer", default="", help="write the per-launch conv/wgrad timing table (JSON lines) here")
+    ap.add_argument("--identity", action="store_true", help="gan workload: add the frozen identity network's loss (configs[2], tf32)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     if a.workload == "pretrain":

@@ -59,6 +59,24 @@ CONV_CASES = [
     (2, 160, 32, 5, 64, 5, 1, 2),
 ]
 
+# every distinct dense-conv shape of MobileNetV2-SSD at 128x128 (Pretrain path, MobileNetV2.py:28-44,103-171): the stem,
+# the 1x1 expand / project convs of the 17 bottlenecks, conv2, the extra layers (3x3 stride 2 down to 1x1 maps - a 3x3
+# stride-2 pad-1 conv on a 1x1 map is run as stride 1, see tpgan_b200/MobileNetV2.py::_layer_at) and the 12 SSD heads
+MOBILENET_CASES = [
+    (4, 3, 32, 128, 128, 3, 2, 1),
+    (4, 32, 32, 64, 64, 1, 1, 0), (4, 32, 16, 64, 64, 1, 1, 0), (4, 16, 96, 64, 64, 1, 1, 0), (4, 96, 24, 32, 32, 1, 1, 0),
+    (4, 24, 144, 32, 32, 1, 1, 0), (4, 144, 24, 32, 32, 1, 1, 0), (4, 144, 32, 16, 16, 1, 1, 0), (4, 32, 192, 16, 16, 1, 1, 0),
+    (4, 192, 32, 16, 16, 1, 1, 0), (4, 192, 64, 8, 8, 1, 1, 0), (4, 64, 384, 8, 8, 1, 1, 0), (4, 384, 64, 8, 8, 1, 1, 0),
+    (4, 384, 96, 8, 8, 1, 1, 0), (4, 96, 576, 8, 8, 1, 1, 0), (4, 576, 96, 8, 8, 1, 1, 0), (4, 576, 160, 4, 4, 1, 1, 0),
+    (4, 160, 960, 4, 4, 1, 1, 0), (4, 960, 160, 4, 4, 1, 1, 0), (4, 960, 320, 4, 4, 1, 1, 0), (4, 320, 1280, 4, 4, 1, 1, 0),
+    (4, 1280, 512, 4, 4, 1, 1, 0), (4, 512, 512, 4, 4, 3, 2, 1), (4, 512, 256, 2, 2, 1, 1, 0), (4, 256, 256, 2, 2, 3, 2, 1),
+    (4, 256, 256, 1, 1, 3, 1, 1), (4, 256, 128, 1, 1, 1, 1, 0), (4, 128, 128, 1, 1, 3, 1, 1),
+    (4, 96, 8, 8, 8, 3, 1, 1), (4, 96, 20, 8, 8, 3, 1, 1), (4, 1280, 12, 4, 4, 3, 1, 1), (4, 1280, 30, 4, 4, 3, 1, 1),
+    (4, 512, 12, 2, 2, 3, 1, 1), (4, 512, 30, 2, 2, 3, 1, 1), (4, 256, 12, 1, 1, 3, 1, 1), (4, 256, 30, 1, 1, 3, 1, 1),
+    (4, 128, 12, 1, 1, 3, 1, 1), (4, 128, 30, 1, 1, 3, 1, 1),
+]
+CONV_CASES = CONV_CASES + MOBILENET_CASES
+
 
 FWD_CASES = [c for c in CONV_CASES if c[4] <= 128]   # the forward/dgrad kernels tile widths up to 128
 

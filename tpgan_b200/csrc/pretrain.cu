@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/tpgan_b200.h"
 #include "common.cuh"
@@ -16,6 +17,10 @@
 
 namespace tpg {
 
+static inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 static inline int grid_cap(long long want, int per_sm) {
   long long cap = (long long)std::max(1, device_sm_count() ? device_sm_count() : 148) * per_sm;
   return (int)std::max(1ll, std::min(want, cap));
@@ -800,7 +805,8 @@ int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* ga
   const int C = x.c;
   if (training) {
     const QMap m = qmap(C);
-    dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), 6), (unsigned)m.ny);   // >= 8 rows per thread
+    static const int per_sm = env_int("TPGAN_BN_PER_SM", 4);
+    dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), per_sm), (unsigned)m.ny);   // >= 8 rows per thread
     bn_stats_kernel<<<grid, 256, (size_t)m.rg * m.qb * 64, ST>>>(x.ptr, M, x.sw, C, sums, gamma, beta, running_mean,
                                                                   running_var, momentum, eps, coef, m.qb, m.rg);
     TPG_CHECK_LAUNCH("bn_stats");
@@ -824,7 +830,8 @@ int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* c
   const int C = x.c;
   if (training) {
     const QMap m = qmap(C);
-    dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), 6), (unsigned)m.ny);
+    static const int per_sm = env_int("TPGAN_BN_PER_SM", 4);
+    dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), per_sm), (unsigned)m.ny);
     bn_bwd_reduce_kernel<<<grid, 256, (size_t)m.rg * m.qb * 64, ST>>>(dy.ptr, dy.sw, x.ptr, x.sw, M, C, coef, relu6, dsums,
                                                                        m.qb, m.rg);
     TPG_CHECK_LAUNCH("bn_bwd_reduce");
