@@ -217,6 +217,175 @@ __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(PV x, PV dy, float* __
   for (int i = threadIdx.x; i < qn * 36; i += 256) atomicAdd(dst + i, sacc[i]);
 }
 
+
+// ---- column-strip variants (the production kernels for stride-1 forward / input gradient and all weight gradients).
+// A block is QB channel quads x RG adjacent output columns of ONE image and walks down a strip of output rows keeping the
+// 3x3 input window in registers: per output pixel a thread issues 3 (stride 1) or 6 (stride 2) new 16-byte loads instead
+// of 9, its horizontal neighbours' loads hit L1, and every input row is fetched from L2 once per block (the per-pixel
+// kernels above re-fetch each input ~3.7x from L2; ncu: DRAM traffic was already algorithmic, L1/L2 -> SM was the bound).
+struct Row3 {
+  float4 a, b, c;   // columns x-1, x, x+1 (stride 1) or 2x-1, 2x, 2x+1 (stride 2)
+};
+template <int STRIDE>
+__device__ __forceinline__ Row3 load_row3(const PV& x, int n, int iy, int ox, int q) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  Row3 r{z, z, z};
+  if (iy < 0 || iy >= x.h) return r;
+  const int xc = ox * STRIDE;
+  const float* base = x.p + poff(x, n, iy, 0) + q * 4;
+  const int xl = xc - 1, xr = xc + 1;
+  r.b = ld4(base + (long long)xc * x.sw);
+  r.a = ld4(base + (long long)max(xl, 0) * x.sw);
+  r.c = ld4(base + (long long)min(xr, x.w - 1) * x.sw);
+  if (xl < 0) r.a = z;
+  if (xr >= x.w) r.c = z;
+  return r;
+}
+__device__ __forceinline__ void fma_row(float4& acc, const Row3& r, const float (&k)[36], int t0) {
+  acc.x = fmaf(r.a.x, k[t0], acc.x), acc.x = fmaf(r.b.x, k[t0 + 1], acc.x), acc.x = fmaf(r.c.x, k[t0 + 2], acc.x);
+  acc.y = fmaf(r.a.y, k[9 + t0], acc.y), acc.y = fmaf(r.b.y, k[9 + t0 + 1], acc.y), acc.y = fmaf(r.c.y, k[9 + t0 + 2], acc.y);
+  acc.z = fmaf(r.a.z, k[18 + t0], acc.z), acc.z = fmaf(r.b.z, k[18 + t0 + 1], acc.z), acc.z = fmaf(r.c.z, k[18 + t0 + 2], acc.z);
+  acc.w = fmaf(r.a.w, k[27 + t0], acc.w), acc.w = fmaf(r.b.w, k[27 + t0 + 1], acc.w), acc.w = fmaf(r.c.w, k[27 + t0 + 2], acc.w);
+}
+
+struct StripGeom {
+  int qb, rg, ncg, nst, rows;   // column groups per row, strips per image, output rows per strip
+};
+
+// y[n,oy,ox,c] (+)= sum_{kr,ks} x[n, oy*S-1+kr, ox*S-1+ks, c] * w[c, kr, ks]   (FLIP: w[c, 2-kr, 2-ks] - the stride-1
+// input gradient is the same correlation with the flipped kernel)
+template <int STRIDE, bool FLIP>
+__global__ void __launch_bounds__(256) dw3x3_strip_kernel(PV x, PV y, const float* __restrict__ w, StripGeom G,
+                                                         int accumulate) {
+  const int ql = threadIdx.x % G.qb, g = threadIdx.x / G.qb;
+  const int q = blockIdx.y * G.qb + ql;
+  int b = blockIdx.x;
+  const int cg = b % G.ncg;
+  b /= G.ncg;
+  const int st = b % G.nst, n = b / G.nst;
+  const int ox = cg * G.rg + g;
+  if (g >= G.rg || ox >= y.w || q * 4 >= x.c) return;
+  float k[36];
+  load_w36(w, q, k);
+  if (FLIP) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float tmp = k[j * 9 + t];
+        k[j * 9 + t] = k[j * 9 + 8 - t];
+        k[j * 9 + 8 - t] = tmp;
+      }
+  }
+  const int oy0 = st * G.rows, oy1 = min(oy0 + G.rows, y.h);
+  // the input rows of the NEXT output row are requested before the current one is computed (per-thread memory-level
+  // parallelism: this kernel runs at ~25 % occupancy, 96+ registers)
+  Row3 r0 = load_row3<STRIDE>(x, n, oy0 * STRIDE - 1, ox, q), r1, r2, p1, p2;
+  if (STRIDE == 1) {
+    r1 = load_row3<STRIDE>(x, n, oy0, ox, q);
+    r2 = load_row3<STRIDE>(x, n, oy0 + 1, ox, q);
+  } else {
+    r1 = load_row3<STRIDE>(x, n, oy0 * 2, ox, q);
+    r2 = load_row3<STRIDE>(x, n, oy0 * 2 + 1, ox, q);
+  }
+  for (int oy = oy0; oy < oy1; ++oy) {
+    const bool more = oy + 1 < oy1;
+    if (STRIDE == 1) {
+      if (more) p2 = load_row3<STRIDE>(x, n, oy + 2, ox, q);
+    } else if (more) {
+      p1 = load_row3<STRIDE>(x, n, oy * 2 + 2, ox, q);
+      p2 = load_row3<STRIDE>(x, n, oy * 2 + 3, ox, q);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    fma_row(acc, r0, k, 0);
+    fma_row(acc, r1, k, 3);
+    fma_row(acc, r2, k, 6);
+    float* d = y.p + poff(y, n, oy, ox) + q * 4;
+    if (accumulate) {
+      const float4 o = ld4(d);
+      acc.x += o.x, acc.y += o.y, acc.z += o.z, acc.w += o.w;
+    }
+    st4(d, acc);
+    if (STRIDE == 1) {
+      r0 = r1;
+      r1 = r2;
+      r2 = p2;
+    } else {
+      r0 = r2;
+      r1 = p1;
+      r2 = p2;
+    }
+  }
+}
+
+__device__ __forceinline__ void wg_row(float (&a)[36], const float4& g, const Row3& r, int t0) {
+  a[t0] = fmaf(g.x, r.a.x, a[t0]), a[t0 + 1] = fmaf(g.x, r.b.x, a[t0 + 1]), a[t0 + 2] = fmaf(g.x, r.c.x, a[t0 + 2]);
+  a[9 + t0] = fmaf(g.y, r.a.y, a[9 + t0]), a[9 + t0 + 1] = fmaf(g.y, r.b.y, a[9 + t0 + 1]), a[9 + t0 + 2] = fmaf(g.y, r.c.y, a[9 + t0 + 2]);
+  a[18 + t0] = fmaf(g.z, r.a.z, a[18 + t0]), a[18 + t0 + 1] = fmaf(g.z, r.b.z, a[18 + t0 + 1]), a[18 + t0 + 2] = fmaf(g.z, r.c.z, a[18 + t0 + 2]);
+  a[27 + t0] = fmaf(g.w, r.a.w, a[27 + t0]), a[27 + t0 + 1] = fmaf(g.w, r.b.w, a[27 + t0 + 1]), a[27 + t0 + 2] = fmaf(g.w, r.c.w, a[27 + t0 + 2]);
+}
+
+// dw[c][kr*3+ks] += sum over the block's strip of dy[n,oy,ox,c] * x[n, oy*S-1+kr, ox*S-1+ks, c]
+template <int STRIDE>
+__global__ void __launch_bounds__(256) dw3x3_strip_wgrad_kernel(PV x, PV dy, float* __restrict__ dw, StripGeom G) {
+  extern __shared__ float sacc[];   // [qb][36]
+  for (int i = threadIdx.x; i < G.qb * 36; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int ql = threadIdx.x % G.qb, g = threadIdx.x / G.qb;
+  const int q = blockIdx.y * G.qb + ql;
+  int b = blockIdx.x;
+  const int cg = b % G.ncg;
+  b /= G.ncg;
+  const int st = b % G.nst, n = b / G.nst;
+  const int ox = cg * G.rg + g;
+  if (g < G.rg && ox < dy.w && q * 4 < x.c) {
+    float a[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) a[i] = 0.f;
+    const int oy0 = st * G.rows, oy1 = min(oy0 + G.rows, dy.h);
+    Row3 r0 = load_row3<STRIDE>(x, n, oy0 * STRIDE - 1, ox, q), r1, r2, p1, p2;
+    if (STRIDE == 1) {
+      r1 = load_row3<STRIDE>(x, n, oy0, ox, q);
+      r2 = load_row3<STRIDE>(x, n, oy0 + 1, ox, q);
+    } else {
+      r1 = load_row3<STRIDE>(x, n, oy0 * 2, ox, q);
+      r2 = load_row3<STRIDE>(x, n, oy0 * 2 + 1, ox, q);
+    }
+    float4 gv = ld4(dy.p + poff(dy, n, oy0, ox) + q * 4), gn = gv;
+    for (int oy = oy0; oy < oy1; ++oy) {
+      const bool more = oy + 1 < oy1;
+      if (more) {
+        gn = ld4(dy.p + poff(dy, n, oy + 1, ox) + q * 4);
+        if (STRIDE == 1) {
+          p2 = load_row3<STRIDE>(x, n, oy + 2, ox, q);
+        } else {
+          p1 = load_row3<STRIDE>(x, n, oy * 2 + 2, ox, q);
+          p2 = load_row3<STRIDE>(x, n, oy * 2 + 3, ox, q);
+        }
+      }
+      wg_row(a, gv, r0, 0);
+      wg_row(a, gv, r1, 3);
+      wg_row(a, gv, r2, 6);
+      gv = gn;
+      if (STRIDE == 1) {
+        r0 = r1;
+        r1 = r2;
+        r2 = p2;
+      } else {
+        r0 = r2;
+        r1 = p1;
+        r2 = p2;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 36; ++i) atomicAdd(&sacc[ql * 36 + i], a[i]);
+  }
+  __syncthreads();
+  const int qn = min(G.qb, x.c / 4 - blockIdx.y * G.qb);
+  float* dst = dw + (long long)blockIdx.y * G.qb * 36;
+  for (int i = threadIdx.x; i < qn * 36; i += 256) atomicAdd(dst + i, sacc[i]);
+}
+
 // ------------------------------------------------------------------------------------------- BatchNorm (training mode)
 // nn.BatchNorm2d (MobileNetV2.py:107,111,115,152,168) over a pixel-dense [M][ld] matrix.
 //   stats    : sums[0][c] += sum_p x, sums[1][c] += sum_p x^2   (fp32 per-thread partials of <= ~32 elements, then fp64);
@@ -270,7 +439,7 @@ __device__ __forceinline__ void bn_block_reduce(const float (&part)[8], int ql, 
   }
 }
 
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, long long M, long long ld, int C,
+__global__ void __launch_bounds__(256, 6) bn_stats_kernel(const float* __restrict__ x, long long M, long long ld, int C,
                                                       double* __restrict__ sums, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float* __restrict__ running_mean,
                                                       float* __restrict__ running_var, float momentum, float eps,
@@ -282,10 +451,13 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   const bool active = g < rg && q * 4 < C;
   float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (active) {
-    const long long step = (long long)gridDim.x * rg;
+    // a block streams ONE contiguous chunk of rows (sequential DRAM pages), its RG row groups interleaved inside it
+    const long long step = rg;
+    const long long chunk = (M + gridDim.x - 1) / gridDim.x;
+    const long long Mend = min(M, (long long)(blockIdx.x + 1) * chunk);
     const float* px = x + q * 4;
-    long long r = (long long)blockIdx.x * rg + g;
-    for (; r + 3 * step < M; r += 4 * step) {      // four independent 16-byte loads in flight per thread
+    long long r = (long long)blockIdx.x * chunk + g;
+    for (; r + 3 * step < Mend; r += 4 * step) {      // four independent 16-byte loads in flight per thread
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = ld4(px + (r + u * step) * ld);
@@ -296,7 +468,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
         part[6] = fmaf(v[u].z, v[u].z, part[6]), part[7] = fmaf(v[u].w, v[u].w, part[7]);
       }
     }
-    for (; r < M; r += step) {
+    for (; r < Mend; r += step) {
       const float4 v = ld4(px + r * ld);
       part[0] += v.x, part[1] += v.y, part[2] += v.z, part[3] += v.w;
       part[4] = fmaf(v.x, v.x, part[4]), part[5] = fmaf(v.y, v.y, part[5]);
@@ -376,7 +548,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
   if (active) {
     const float4 a = ld4(coef + q * 4), b = ld4(coef + C + q * 4), mu = ld4(coef + 2 * C + q * 4),
                  is = ld4(coef + 3 * C + q * 4);
-    const long long step = (long long)gridDim.x * rg;
+    const long long step = rg;
+    const long long chunk = (M + gridDim.x - 1) / gridDim.x;
+    const long long Mend = min(M, (long long)(blockIdx.x + 1) * chunk);
     const float* px = x + q * 4;
     const float* pg = dy + q * 4;
     auto add = [&](const float4& v, const float4& gr) {
@@ -386,8 +560,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
       part[4] = fmaf(gx, (v.x - mu.x) * is.x, part[4]), part[5] = fmaf(gy, (v.y - mu.y) * is.y, part[5]);
       part[6] = fmaf(gz, (v.z - mu.z) * is.z, part[6]), part[7] = fmaf(gw, (v.w - mu.w) * is.w, part[7]);
     };
-    long long r = (long long)blockIdx.x * rg + g;
-    for (; r + 3 * step < M; r += 4 * step) {      // eight independent 16-byte loads in flight per thread
+    long long r = (long long)blockIdx.x * chunk + g;
+    for (; r + 3 * step < Mend; r += 4 * step) {      // eight independent 16-byte loads in flight per thread
       float4 v[4], gr[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -397,7 +571,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 #pragma unroll
       for (int u = 0; u < 4; ++u) add(v[u], gr[u]);
     }
-    for (; r < M; r += step) add(ld4(px + r * ldx), ld4(pg + r * ldd));
+    for (; r < Mend; r += step) add(ld4(px + r * ldx), ld4(pg + r * ldd));
   }
   bn_block_reduce(part, ql, g, qb, rg, active, C, blockIdx.y * qb, dsums, red);
 }
@@ -745,19 +919,47 @@ __global__ void sgd_kernel(float4* __restrict__ p, const float4* __restrict__ g,
 using namespace tpg;
 #define ST ((cudaStream_t)stream)
 
+// strips: enough blocks to fill the machine (~4 per SM) but at least 4 output rows each so the window reuse pays
+static StripGeom strip_geom(int C, int n, int out_h, int out_w, unsigned* blocks_x, unsigned* blocks_y) {
+  const QMap m = qmap(C);
+  StripGeom G;
+  G.qb = m.qb;
+  G.rg = std::min(m.rg, out_w);
+  G.ncg = (out_w + G.rg - 1) / G.rg;
+  const long long base = (long long)G.ncg * n * m.ny;
+  const int want = (int)std::max(1ll, (592 + base - 1) / base);
+  const int max_strips = std::max(1, out_h / 4);
+  const int strips = std::min(want, max_strips);
+  G.rows = (out_h + strips - 1) / strips;
+  G.nst = (out_h + G.rows - 1) / G.rows;
+  *blocks_x = (unsigned)(G.ncg * G.nst * n);
+  *blocks_y = (unsigned)m.ny;
+  return G;
+}
+
 extern "C" {
 
 int tpgan_dwconv3x3(tpgan_view x, tpgan_view y, const float* w, int32_t stride, void* stream) {
   if (!vec_view(x) || !vec_view(y) || !w || x.c != y.c || x.n != y.n || (stride != 1 && stride != 2) ||
       y.h != (x.h + 2 - 3) / stride + 1 || y.w != (x.w + 2 - 3) / stride + 1)
     return set_error(TPGAN_ERR_INVALID, "dwconv3x3: bad geometry (C %% 4 == 0, stride 1|2, pad 1)");
-  const QMap m = qmap(x.c);
-  const long long npix = (long long)y.n * y.h * y.w;
-  dim3 grid((unsigned)grid_cap((npix + m.rg * 2 - 1) / (m.rg * 2), 8), (unsigned)m.ny);
-  if (stride == 1)
-    dw3x3_fwd_kernel<1><<<grid, 256, 0, ST>>>(pv(x), pv(y), w, m.qb, m.rg);
-  else
-    dw3x3_fwd_kernel<2><<<grid, 256, 0, ST>>>(pv(x), pv(y), w, m.qb, m.rg);
+  static const bool per_pixel = getenv("TPGAN_DW_PER_PIXEL") != nullptr;   // the previous per-pixel kernels (A/B timing)
+  if (per_pixel) {
+    const QMap m = qmap(x.c);
+    const long long npix = (long long)y.n * y.h * y.w;
+    dim3 grid((unsigned)grid_cap((npix + m.rg * 2 - 1) / (m.rg * 2), 8), (unsigned)m.ny);
+    if (stride == 1)
+      dw3x3_fwd_kernel<1><<<grid, 256, 0, ST>>>(pv(x), pv(y), w, m.qb, m.rg);
+    else
+      dw3x3_fwd_kernel<2><<<grid, 256, 0, ST>>>(pv(x), pv(y), w, m.qb, m.rg);
+  } else {
+    unsigned bx, by;
+    const StripGeom G = strip_geom(x.c, y.n, y.h, y.w, &bx, &by);
+    if (stride == 1)
+      dw3x3_strip_kernel<1, false><<<dim3(bx, by), 256, 0, ST>>>(pv(x), pv(y), w, G, 0);
+    else
+      dw3x3_strip_kernel<2, false><<<dim3(bx, by), 256, 0, ST>>>(pv(x), pv(y), w, G, 0);
+  }
   TPG_CHECK_LAUNCH("dwconv3x3");
   return 0;
 }
@@ -766,13 +968,20 @@ int tpgan_dwconv3x3_dgrad(tpgan_view dy, tpgan_view dx, const float* w, int32_t 
   if (!vec_view(dx) || !vec_view(dy) || !w || dx.c != dy.c || dx.n != dy.n || (stride != 1 && stride != 2) ||
       dy.h != (dx.h + 2 - 3) / stride + 1 || dy.w != (dx.w + 2 - 3) / stride + 1)
     return set_error(TPGAN_ERR_INVALID, "dwconv3x3_dgrad: bad geometry");
-  const QMap m = qmap(dx.c);
-  const long long npix = (long long)dx.n * dx.h * dx.w;
-  dim3 grid((unsigned)grid_cap((npix + m.rg * 2 - 1) / (m.rg * 2), 8), (unsigned)m.ny);
-  if (stride == 1)
-    dw3x3_dgrad_kernel<1><<<grid, 256, 0, ST>>>(pv(dy), pv(dx), w, accumulate, m.qb, m.rg);
-  else
-    dw3x3_dgrad_kernel<2><<<grid, 256, 0, ST>>>(pv(dy), pv(dx), w, accumulate, m.qb, m.rg);
+  static const bool per_pixel = getenv("TPGAN_DW_PER_PIXEL") != nullptr;
+  if (stride == 1 && !per_pixel) {   // stride-1 input gradient = the same correlation with the flipped kernel
+    unsigned bx, by;
+    const StripGeom G = strip_geom(dx.c, dx.n, dx.h, dx.w, &bx, &by);
+    dw3x3_strip_kernel<1, true><<<dim3(bx, by), 256, 0, ST>>>(pv(dy), pv(dx), w, G, accumulate);
+  } else {
+    const QMap m = qmap(dx.c);
+    const long long npix = (long long)dx.n * dx.h * dx.w;
+    dim3 grid((unsigned)grid_cap((npix + m.rg * 2 - 1) / (m.rg * 2), 8), (unsigned)m.ny);
+    if (stride == 1)
+      dw3x3_dgrad_kernel<1><<<grid, 256, 0, ST>>>(pv(dy), pv(dx), w, accumulate, m.qb, m.rg);
+    else
+      dw3x3_dgrad_kernel<2><<<grid, 256, 0, ST>>>(pv(dy), pv(dx), w, accumulate, m.qb, m.rg);
+  }
   TPG_CHECK_LAUNCH("dwconv3x3_dgrad");
   return 0;
 }
@@ -781,14 +990,24 @@ int tpgan_dwconv3x3_wgrad(tpgan_view x, tpgan_view dy, float* dw, int32_t stride
   if (!vec_view(x) || !vec_view(dy) || !dw || x.c != dy.c || x.n != dy.n || (stride != 1 && stride != 2) ||
       dy.h != (x.h + 2 - 3) / stride + 1 || dy.w != (x.w + 2 - 3) / stride + 1)
     return set_error(TPGAN_ERR_INVALID, "dwconv3x3_wgrad: bad geometry");
+  static const bool per_pixel = getenv("TPGAN_DW_PER_PIXEL") != nullptr;
   const QMap m = qmap(x.c);
-  const long long npix = (long long)dy.n * dy.h * dy.w;
-  dim3 grid((unsigned)grid_cap((npix + m.rg * 8 - 1) / (m.rg * 8), 4), (unsigned)m.ny);   // >= 8 pixels per thread
   const size_t smem = (size_t)m.qb * 36 * 4;
-  if (stride == 1)
-    dw3x3_wgrad_kernel<1><<<grid, 256, smem, ST>>>(pv(x), pv(dy), dw, m.qb, m.rg);
-  else
-    dw3x3_wgrad_kernel<2><<<grid, 256, smem, ST>>>(pv(x), pv(dy), dw, m.qb, m.rg);
+  if (per_pixel) {
+    const long long npix = (long long)dy.n * dy.h * dy.w;
+    dim3 grid((unsigned)grid_cap((npix + m.rg * 8 - 1) / (m.rg * 8), 4), (unsigned)m.ny);   // >= 8 pixels per thread
+    if (stride == 1)
+      dw3x3_wgrad_kernel<1><<<grid, 256, smem, ST>>>(pv(x), pv(dy), dw, m.qb, m.rg);
+    else
+      dw3x3_wgrad_kernel<2><<<grid, 256, smem, ST>>>(pv(x), pv(dy), dw, m.qb, m.rg);
+  } else {
+    unsigned bx, by;
+    const StripGeom G = strip_geom(x.c, dy.n, dy.h, dy.w, &bx, &by);
+    if (stride == 1)
+      dw3x3_strip_wgrad_kernel<1><<<dim3(bx, by), 256, smem, ST>>>(pv(x), pv(dy), dw, G);
+    else
+      dw3x3_strip_wgrad_kernel<2><<<dim3(bx, by), 256, smem, ST>>>(pv(x), pv(dy), dw, G);
+  }
   TPG_CHECK_LAUNCH("dwconv3x3_wgrad");
   return 0;
 }
@@ -805,7 +1024,7 @@ int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* ga
   const int C = x.c;
   if (training) {
     const QMap m = qmap(C);
-    static const int per_sm = env_int("TPGAN_BN_PER_SM", 4);
+    static const int per_sm = env_int("TPGAN_BN_PER_SM", 6);
     dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), per_sm), (unsigned)m.ny);   // >= 8 rows per thread
     bn_stats_kernel<<<grid, 256, (size_t)m.rg * m.qb * 64, ST>>>(x.ptr, M, x.sw, C, sums, gamma, beta, running_mean,
                                                                   running_var, momentum, eps, coef, m.qb, m.rg);
@@ -830,7 +1049,7 @@ int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* c
   const int C = x.c;
   if (training) {
     const QMap m = qmap(C);
-    static const int per_sm = env_int("TPGAN_BN_PER_SM", 4);
+    static const int per_sm = env_int("TPGAN_BN_PER_SM", 5);
     dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), per_sm), (unsigned)m.ny);
     bn_bwd_reduce_kernel<<<grid, 256, (size_t)m.rg * m.qb * 64, ST>>>(dy.ptr, dy.sw, x.ptr, x.sw, M, C, coef, relu6, dsums,
                                                                        m.qb, m.rg);
