@@ -451,3 +451,16 @@ def test_decoder_known_answer():
     assert len(out) == 1
     c, s, p = out[0]
     assert c == 1 and abs(float(s) - 0.5148) < 5e-5 and p.tolist() == [370.0, 150.0]
+
+
+def test_pretrain_loop_runs_and_checkpoints(tmp_path):
+    """tpgan_b200.Pretrain.main: the reference's loop shape (train step, decode + accuracy, validation in eval mode,
+    MultiStepLR, save_model / save_optimizer per epoch) on synthetic batches."""
+    from tpgan_b200 import Pretrain as PT
+    hist = PT.main(["--epochs", "2", "--steps-per-epoch", "3", "--batch", "4", "--log-every", "2", "--val-steps", "1",
+                    "--log-dir", str(tmp_path / "log")])
+    assert len(hist) == 6 and all(math.isfinite(l) and 0.0 <= a <= 1.0 for l, a in hist)
+    for e in (0, 1):
+        assert (tmp_path / "log" / f"model_epoch_{e}.pth").exists() and (tmp_path / "log" / f"optimizer_epoch_{e}.pth").exists()
+    sd = torch.load(tmp_path / "log" / "model_epoch_1.pth", map_location="cpu")
+    assert int(sd["conv1.1.num_batches_tracked"]) == 6
