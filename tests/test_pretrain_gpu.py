@@ -464,3 +464,19 @@ def test_pretrain_loop_runs_and_checkpoints(tmp_path):
         assert (tmp_path / "log" / f"model_epoch_{e}.pth").exists() and (tmp_path / "log" / f"optimizer_epoch_{e}.pth").exists()
     sd = torch.load(tmp_path / "log" / "model_epoch_1.pth", map_location="cpu")
     assert int(sd["conv1.1.num_batches_tracked"]) == 6
+
+
+def test_full_size_forward_tf32_vs_emulated_oracle():
+    """B = 32 (BASELINE config 5's per-GPU batch): the production TF32 forward against the oracle with the same rounding
+    points - eval mode <= 1e-3, training mode (batch statistics over 512+ samples per channel) <= 3e-2."""
+    from oracle.pretrain_port import forward_tf32_emulated, make_batch
+    port, net = _nets(seed=8)
+    x, _, _ = make_batch(32, seed=60)
+    for train, tol in ((False, 1e-3), (True, 3e-2)):
+        port.train(train), net.train(train)
+        sd = {k: v.clone() for k, v in port.state_dict().items()}
+        le, ce = forward_tf32_emulated(port, x)
+        port.load_state_dict(sd)          # the emulated training forward updated the running statistics
+        with torch.no_grad():
+            lg, cg = net(x.cuda())
+        assert rel(lg, le) < tol and rel(cg, ce) < tol, (train, rel(lg, le), rel(cg, ce))
