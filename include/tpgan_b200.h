@@ -245,11 +245,14 @@ TPGAN_API int tpgan_dwconv3x3_wgrad(tpgan_view x, tpgan_view dy, float* dw, int3
  * the caller and left zeroed by every call (the last word is a block ticket: the last block of the statistics kernel
  * finalises and clears), running_mean / running_var updated in place with `momentum` and the unbiased variance;
  * training == 0: running statistics.  coef = caller-owned float[4*C] (scale, shift, mean, invstd) consumed by the backward.
- * y = x*scale + shift (+ res) -> ReLU6 if relu6 -> tf32 rounding if round_tf32 (operand of a tensor-core conv). */
+ * y = x*scale + shift (+ res) -> act -> tf32 rounding if round_tf32 (operand of a tensor-core conv).  act: 0 none, 1 ReLU6
+ * (MobileNetV2; not combinable with res), 2 (Leaky)ReLU with `slope` (ResNet.py:30-31,104-112: BatchNorm -> ReLU, the block's
+ * final ReLU after the shortcut add; slope 0 = ReLU). */
 TPGAN_API int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, int32_t training,
-                               int32_t relu6, int32_t round_tf32, double* sums, float* coef, void* stream);
-/* dz = dy * [0 < y < 6] (if relu6); training: dx (+)= scale*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum dz*xhat,
+                               int32_t act, float slope, int32_t round_tf32, double* sums, float* coef, void* stream);
+/* dz = dy * [0 < y < 6] (if relu6; for act 2 the caller masks dy by the sign of y first - tpgan_act_backward or the conv
+ * dgrad epilogue); training: dx (+)= scale*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum dz*xhat,
  * dbeta = sum dz (overwritten; may be NULL); eval: dx (+)= scale*dz.  dsums = scratch of 2*C + 1 doubles, zeroed once by the
  * caller and left zeroed by every call. */
 TPGAN_API int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* coef, int32_t training, int32_t relu6,

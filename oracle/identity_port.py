@@ -32,40 +32,43 @@ import torch.nn.functional as F
 EPS = 1e-5  # nn.BatchNorm default
 
 
-def _bn(sd: Dict[str, torch.Tensor], key: str, x: torch.Tensor) -> torch.Tensor:
-    """Eval-mode BatchNorm (running statistics) if the layer has one."""
+def _bn(sd: Dict[str, torch.Tensor], key: str, x: torch.Tensor, training: bool = False) -> torch.Tensor:
+    """BatchNorm if the layer has one: running statistics (eval) or batch statistics with the running ones updated in
+    place in `sd` (training, momentum 0.1 - nn.BatchNorm's defaults)."""
     if key + ".weight" not in sd:
         return x
     return F.batch_norm(x, sd[key + ".running_mean"], sd[key + ".running_var"], sd[key + ".weight"], sd[key + ".bias"],
-                        training=False, eps=EPS)
+                        training=training, momentum=0.1, eps=EPS)
 
 
-def _cbr(sd, key, x, stride, pad, relu):
+def _cbr(sd, key, x, stride, pad, relu, training=False):
     y = F.conv2d(x, sd[key + ".0.weight"], sd.get(key + ".0.bias"), stride=stride, padding=pad)
-    y = _bn(sd, key + ".1", y)
+    y = _bn(sd, key + ".1", y, training)
     return F.relu(y) if relu else y
 
 
-def _block(sd, key, x, stride):
-    a = _cbr(sd, key + ".conv_a", x, stride, 1, True)
-    b = _cbr(sd, key + ".conv_b", a, 1, 1, False)
-    sc = _cbr(sd, key + ".shortcut", x, stride, 0, False) if (key + ".shortcut.0.weight") in sd else x
+def _block(sd, key, x, stride, training=False):
+    a = _cbr(sd, key + ".conv_a", x, stride, 1, True, training)
+    b = _cbr(sd, key + ".conv_b", a, 1, 1, False, training)
+    sc = _cbr(sd, key + ".shortcut", x, stride, 0, False, training) if (key + ".shortcut.0.weight") in sd else x
     return F.relu(b + sc)
 
 
-def resnet18_128(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
-    """x (B,3,128,128) -> (logits, FC0 feature or None, pooled 512 feature)."""
-    h = _cbr(sd, "conv1", x, 2, 3, True)
+def resnet18_128(sd: Dict[str, torch.Tensor], x: torch.Tensor,
+                 training: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """x (B,3,128,128) -> (logits, FC0 feature or None, pooled 512 feature).  training=True: the pre-training forward
+    (batch-statistics BatchNorm; `sd`'s running statistics are updated in place)."""
+    h = _cbr(sd, "conv1", x, 2, 3, True, training)
     h = F.max_pool2d(h, 3, 2, 1)
     for s, stride in enumerate((1, 2, 2, 2)):
         for b in range(2):
-            h = _block(sd, f"sections.{s}.{b}", h, stride if b == 0 else 1)
+            h = _block(sd, f"sections.{s}.{b}", h, stride if b == 0 else 1, training)
     pooled = F.adaptive_avg_pool2d(h, 1).flatten(1)
     fc0 = None
     f = pooled
     if "FC0.0.weight" in sd:
         f = F.linear(pooled, sd["FC0.0.weight"], sd.get("FC0.0.bias"))
-        f = _bn(sd, "FC0.1", f)
+        f = _bn(sd, "FC0.1", f, training)
         fc0 = f
     logits = F.linear(f, sd["FC.0.weight"], sd.get("FC.0.bias"))
     return logits, fc0, pooled

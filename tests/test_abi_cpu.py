@@ -82,9 +82,9 @@ def test_invalid_arguments_are_rejected_before_any_launch():
                                                  fake, 1, None),                                                # C % 4 != 0
         "dwconv3x3_stride": lambda: lib.tpgan_dwconv3x3(V(fake, 512, 64, 8, 1, 8, 8, 8), V(fake, 512, 64, 8, 1, 8, 8, 8), fake, 3, None),
         "bn_forward": lambda: lib.tpgan_bn_forward(V(fake, 512, 64, 8, 1, 8, 8, 8), null, V(fake, 512, 64, 8, 1, 8, 8, 8), None, fake,
-                                                   None, None, 0.1, 1e-5, 1, 1, 0, fake, fake, None),           # gamma missing
+                                                   None, None, 0.1, 1e-5, 1, 1, 0.0, 0, fake, fake, None),      # gamma missing
         "bn_forward_res_relu6": lambda: lib.tpgan_bn_forward(V(fake, 512, 64, 8, 1, 8, 8, 8), V(fake, 512, 64, 8, 1, 8, 8, 8),
-                                                             V(fake, 512, 64, 8, 1, 8, 8, 8), fake, fake, fake, fake, 0.1, 1e-5, 1, 1, 0,
+                                                             V(fake, 512, 64, 8, 1, 8, 8, 8), fake, fake, fake, fake, 0.1, 1e-5, 1, 1, 0.0, 0,
                                                              fake, fake, None),                                 # residual + ReLU6
         "rows_gather": lambda: lib.tpgan_rows_gather(V(fake, 512, 64, 8, 1, 8, 8, 8), fake, 100, 0, 0, None),   # row too short
         "pyramid": lambda: lib.tpgan_pyramid(V(fake, 1, 1, 1, 1, 6, 6, 3), V(fake, 1, 1, 1, 1, 3, 3, 3), V(fake, 1, 1, 1, 1, 1, 1, 3), None),

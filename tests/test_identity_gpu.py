@@ -76,9 +76,9 @@ def test_identity_network_forward():
     assert rel(out, ref_out) < 3e-3, rel(out, ref_out)
     with pytest.raises(RuntimeError):
         net(x)                       # CPU tensors: no fallback
-    net.train()
-    with pytest.raises(NotImplementedError):
-        net(x.cuda())
+    net.train()                      # training mode is the unfolded batch-statistics path (test_resnet_training_mode_vs_oracle)
+    out_t, fc0_t = net(x.cuda())
+    assert out_t.shape == (4, 347) and fc0_t.shape == (4, 256) and out_t.requires_grad
 
 
 @pytest.mark.parametrize("exact", [False, True])
@@ -149,3 +149,58 @@ def test_step_with_identity_loss():
     ref = ostep.train_step(Gc, Dc, list(pg.values()), list(pd.values()), og, od, b, step_optim=False, identity_sd=sd)
     for k in ("pixel", "local", "symmetry", "tv", "ce", "ip", "g_total"):
         assert abs(m[k] - ref[k]) <= 1e-2 * abs(ref[k]) + 1e-4, (k, m[k], ref[k])
+
+
+@pytest.mark.parametrize("exact,use_bn", [(True, True), (False, True), (True, False)])
+def test_resnet_training_mode_vs_oracle(exact, use_bn):
+    """Pre-training mode of the feature extractor (BASELINE config 5, "ResNet backbones"): unfolded conv -> batch-statistics
+    BatchNorm (+ReLU, + shortcut add) forward and backward through the autograd bridge, against the oracle port in training
+    mode.  fp32-exact mode: outputs <= 2e-4, running statistics <= 1e-4, parameter gradients <= 2e-2 overall (ReLU / max-pool
+    gate flips, no mask injection); TF32: outputs <= 1e-2, gradients sanity-bounded (0.3)."""
+    import math
+
+    import tpgan_b200.D_and_G_model as M
+    from oracle import identity_port as ip
+    from tpgan_b200.ResNet import BasicBlock, ResNet18
+    M.EXACT_MODE = exact
+    try:
+        torch.manual_seed(3)
+        net = ResNet18(BasicBlock, 347, use_bn, 256)
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        params = {k: sd[k].requires_grad_(True) for k, _ in net.named_parameters()}
+        g = torch.Generator().manual_seed(4)
+        x = torch.rand((6, 3, 128, 128), generator=g) * 2 - 1
+        labels = torch.randint(0, 347, (6,), generator=g)
+        lo, f0, _ = ip.resnet18_128(sd, x, training=True)
+        loss = F.cross_entropy(lo, labels) + 0.1 * f0.square().mean()
+        loss.backward()
+        net.cuda().train()
+        lg, fg = net(x.cuda())
+        tol = 2e-4 if exact else 1e-2
+        assert rel(lg, lo) < tol and rel(fg, f0) < tol, (rel(lg, lo), rel(fg, f0))
+        lossg = F.cross_entropy(lg, labels.cuda()) + 0.1 * fg.square().mean()
+        lossg.backward()
+        if use_bn:
+            sg = net.state_dict()
+            for k in sd:
+                if "running_" in k:
+                    assert rel(sg[k], sd[k]) < (1e-4 if exact else 5e-3), k
+            assert int(sg["conv1.1.num_batches_tracked"]) == 1
+        num = den = 0.0
+        worst = (0.0, "")
+        for k, p in net.named_parameters():
+            a, b = p.grad.double().cpu(), params[k].grad.double()
+            num += float((a - b).pow(2).sum())
+            den += float(b.pow(2).sum())
+            r = float((a - b).norm() / (b.norm() + 1e-30))
+            worst = max(worst, (r, k))
+        overall = math.sqrt(num / den)
+        assert overall < (2e-2 if exact else 0.3), (overall, worst)
+        # back to eval: the folded copies are rebuilt from the trained weights / updated statistics
+        net.eval()
+        with torch.no_grad():
+            le, fe = net(x.cuda())
+        want_l, want_f, _ = ip.resnet18_128({k: v.detach() for k, v in sd.items()}, x, training=False)
+        assert rel(le, want_l) < (1e-3 if exact else 1e-2) and rel(fe, want_f) < (1e-3 if exact else 1e-2)
+    finally:
+        M.EXACT_MODE = False

@@ -9,8 +9,11 @@ this is a RESTATEMENT, not a drop-in for a working class: the canonical ResNet18
 shortcut where shape changes) with the reference's constructor/forward signatures.  Parity for it is oracle-defined
 (oracle/identity_port.py), stated in DESIGN.md.
 
-Execution: in eval mode (the only mode the TP-GAN step uses it in: a FROZEN identity network) BatchNorm is folded into the
+Execution: in eval mode (the mode the TP-GAN step uses it in: a FROZEN identity network) BatchNorm is folded into the
 preceding conv / linear and the whole forward (and the input gradient) runs as a traced plan on the tcgen05 kernels.
+In training mode (pre-training the feature extractor, BASELINE config 5 "ResNet backbones") the same layers run unfolded:
+conv -> training-mode BatchNorm (+ReLU, + the block's shortcut add) with the kernels of csrc/pretrain.cu, forward and
+backward through the autograd bridge of TracedModule, parameter gradients in the reference layout.
 """
 from __future__ import annotations
 
@@ -21,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .D_and_G_model import TracedModule, _layer
 from .engine import ConvLayer, Plan, T
 from .ModificationLayer import conv, linear
 
@@ -62,7 +66,7 @@ def _fold(seq: nn.Sequential):
     return lin, w.contiguous(), b.contiguous(), relu
 
 
-class ResNet18(nn.Module):
+class ResNet18(TracedModule):
     def __init__(self, residualBlock=BasicBlock, num_of_output_classes=1000, use_batchnorm=True,
                  feature_layer_dim_before_FC=None, activation=nn.ReLU(inplace=True), dropout_rate=0.0):
         super().__init__()
@@ -139,12 +143,79 @@ class ResNet18(nn.Module):
         logits = cv("FC", fc0 if fc0 is not None else pooled) if with_logits else None
         return pooled, fc0, logits
 
+    # ---- traced execution (training mode: batch-statistics BatchNorm, weight gradients)
+    @staticmethod
+    def _parts(seq: nn.Sequential):
+        lin = bn = None
+        relu = False
+        for m in seq:
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                lin = m
+            elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                bn = m
+            elif isinstance(m, nn.ReLU):
+                relu = True
+            else:
+                raise NotImplementedError(type(m).__name__)
+        return lin, bn, relu
+
+    @staticmethod
+    def _dense_layer(lin, name: str) -> ConvLayer:
+        if isinstance(lin, nn.Conv2d):
+            return _layer(lin, name)
+        L = lin.__dict__.get("_tc_layer")
+        if L is None:   # nn.Linear as a 1x1 convolution over the (B,1,1,C) row
+            L = ConvLayer(lin.weight, lin.bias, False, 1, 1, 0, name, w_shape=(lin.out_features, lin.in_features, 1, 1))
+            object.__setattr__(lin, "_tc_layer", L)
+        return L
+
+    def trace_train(self, plan: Plan, x: T):
+        """x: (N,128,128,3) NHWC -> (logits T, FC0 feature T or None, pooled T), BatchNorm on batch statistics."""
+        from .MobileNetV2 import BNLayer, _aux
+
+        def cbr(name, seq, t, res=None, relu=None, feeds_conv=True):
+            lin, bn, has_relu = self._parts(seq)
+            act = has_relu if relu is None else relu
+            L = self._dense_layer(lin, name + ".0")
+            if bn is None:      # use_batchnorm=False: bias (+ residual) (+ ReLU) in the conv epilogue
+                return plan.conv([L], [t], 0.0 if act else None, residuals=None if res is None else [res],
+                                 round_out=feeds_conv)[0]
+            h = plan.conv([L], [t], None, round_out=False)[0]
+            return plan.batchnorm(_aux(bn, BNLayer, name + ".1"), h, res=res, slope=0.0 if act else None,
+                                  round_out=feeds_conv)
+        h = cbr("conv1", self.conv1, x)
+        h = plan.maxpool3s2(h)
+        for si, sec in enumerate(self.sections):
+            for bi, blk in enumerate(sec):
+                pre = f"sections.{si}.{bi}"
+                a = cbr(pre + ".conv_a", blk.conv_a, h)
+                sc = cbr(pre + ".shortcut", blk.shortcut, h, feeds_conv=False) if len(blk.shortcut) else h
+                h = cbr(pre + ".conv_b", blk.conv_b, a, res=sc, relu=True)
+        pooled = plan.avgpool(h)
+        fc0 = cbr("FC0", self.FC0, pooled) if hasattr(self, "FC0") else None
+        logits = cbr("FC", self.FC, fc0 if fc0 is not None else pooled, feeds_conv=False)
+        return logits, fc0, pooled
+
+    def _trace(self, plan, x, static=()):
+        plan.training = True
+        logits, fc0, _ = self.trace_train(plan, x)
+        logits.flat = True
+        if fc0 is not None:
+            fc0.flat = True
+        return [logits] if fc0 is None else [logits, fc0]
+
     def forward(self, x, use_dropout=False):
         if not x.is_cuda:
             raise RuntimeError("tpgan_b200 modules run on CUDA tensors only (there is no CPU fallback)")
         if self.training:
-            raise NotImplementedError("ResNet18 runs as a frozen (eval-mode) identity network on the TP-GAN hot path; "
-                                      "training it (batch-statistics BatchNorm) is outside the path (SURVEY.md 8)")
+            if use_dropout and self.dropout.p > 0:
+                raise NotImplementedError("dropout > 0 between FC0 and FC is not built (ResNet.py:52 default 0.0)")
+            for m in self.modules():
+                if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)) and m.num_batches_tracked is not None:
+                    m.num_batches_tracked += 1
+            self._traced_layers = None      # the folded eval-mode copies are stale once the weights train
+            outs = self._traced_call([x], static=("train",))
+            return (outs[0], outs[1]) if len(outs) > 1 else (outs[0], None)
         if use_dropout and self.dropout.p > 0:
             raise NotImplementedError("dropout is a training-time option")
         n = x.shape[0]

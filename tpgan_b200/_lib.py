@@ -100,7 +100,7 @@ SYMBOLS = {
     "tpgan_dwconv3x3": (C.c_int, [View, View, _VP, _I32, _VP]),
     "tpgan_dwconv3x3_dgrad": (C.c_int, [View, View, _VP, _I32, _I32, _VP]),
     "tpgan_dwconv3x3_wgrad": (C.c_int, [View, View, _VP, _I32, _VP]),
-    "tpgan_bn_forward": (C.c_int, [View, View, View, _VP, _VP, _VP, _VP, _F, _F, _I32, _I32, _I32, _VP, _VP, _VP]),
+    "tpgan_bn_forward": (C.c_int, [View, View, View, _VP, _VP, _VP, _VP, _F, _F, _I32, _I32, _F, _I32, _VP, _VP, _VP]),
     "tpgan_bn_backward": (C.c_int, [View, View, View, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP]),
     "tpgan_rows_gather": (C.c_int, [View, _VP, _I64, _I64, _I32, _VP]),
     "tpgan_multitask_loss": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I64, _I64, _I32, _I32, _F, _F, _F, _F, _F, _F, _VP, _VP, _VP,

@@ -504,8 +504,8 @@ __global__ void bn_finalize_kernel(int C, const float* __restrict__ gamma, const
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, long long M, long long ldx, int C,
                                                       const float* __restrict__ coef, const float* __restrict__ res,
-                                                      long long ldr, float* __restrict__ y, long long ldy, int relu6,
-                                                      int round) {
+                                                      long long ldr, float* __restrict__ y, long long ldy, int act,
+                                                      float slope, int round) {
   extern __shared__ float sc[];  // scale[C], shift[C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sc[i] = coef[i];
   __syncthreads();
@@ -521,9 +521,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
       const float4 e = ld4(res + r * ldr + q * 4);
       o.x += e.x, o.y += e.y, o.z += e.z, o.w += e.w;
     }
-    if (relu6) {
+    if (act == 1) {
       o.x = fminf(fmaxf(o.x, 0.f), 6.f), o.y = fminf(fmaxf(o.y, 0.f), 6.f);
       o.z = fminf(fmaxf(o.z, 0.f), 6.f), o.w = fminf(fmaxf(o.w, 0.f), 6.f);
+    } else if (act == 2) {
+      o.x = o.x > 0.f ? o.x : o.x * slope, o.y = o.y > 0.f ? o.y : o.y * slope;
+      o.z = o.z > 0.f ? o.z : o.z * slope, o.w = o.w > 0.f ? o.w : o.w * slope;
     }
     if (round) o = rnd4(o);
     st4(y + r * ldy + q * 4, o);
@@ -1013,8 +1016,10 @@ int tpgan_dwconv3x3_wgrad(tpgan_view x, tpgan_view dy, float* dw, int32_t stride
 }
 
 int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* gamma, const float* beta, float* running_mean,
-                     float* running_var, float momentum, float eps, int32_t training, int32_t relu6, int32_t round_tf32,
-                     double* sums, float* coef, void* stream) {
+                     float* running_var, float momentum, float eps, int32_t training, int32_t act, float slope,
+                     int32_t round_tf32, double* sums, float* coef, void* stream) {
+  const int relu6 = act == 1;
+  if (act < 0 || act > 2) return set_error(TPGAN_ERR_INVALID, "bn_forward: act must be 0 (none), 1 (ReLU6) or 2 (leaky)");
   if (!dense(x) || !dense(y) || x.c != y.c || x.n != y.n || x.h != y.h || x.w != y.w || !gamma || !beta || !coef ||
       (training && !sums) || (!training && (!running_mean || !running_var)) || x.c * 8 > 48 * 1024)
     return set_error(TPGAN_ERR_INVALID, "bn_forward: bad arguments (pixel-dense views, C %% 4 == 0)");
@@ -1035,7 +1040,7 @@ int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* ga
   }
   const long long total = M * (C / 4);
   bn_apply_kernel<<<grid_cap((total + 255) / 256, 8), 256, (size_t)C * 8, ST>>>(x.ptr, M, x.sw, C, coef, res.ptr, res.sw,
-                                                                               y.ptr, y.sw, relu6, round_tf32);
+                                                                               y.ptr, y.sw, act, slope, round_tf32);
   TPG_CHECK_LAUNCH("bn_apply");
   return 0;
 }

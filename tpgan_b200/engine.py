@@ -750,12 +750,15 @@ class Plan:
 
     # ------------------------------------------------------------------ Pretrain path (MobileNetV2.py) ops
     def batchnorm(self, bn, x: T, res: Optional[T] = None, relu6: bool = False, round_out: bool = True,
-                  round_dx: bool = True, name: str = "") -> T:
+                  round_dx: bool = True, name: str = "", slope: Optional[float] = None) -> T:
         """nn.BatchNorm2d (+nn.ReLU6, + the residual add of InvertedResidual.forward, MobileNetV2.py:107-120).  `bn` is a
         BNLayer (tpgan_b200/MobileNetV2.py).  Training plans use batch statistics and update the running ones."""
         n, h, w, c = x.shape
         assert c % 4 == 0 and x.act.c0 == 0 and x.act.buf.shape[3] == c, "BatchNorm needs a whole pixel-dense buffer"
         out = self.new(n, h, w, c, name=name or bn.name)
+        if slope is not None:      # (Leaky)ReLU after the BatchNorm (+ residual): forward in the kernel, backward through
+            assert not relu6       # the engine's activation-mask machinery (sign of the stored output)
+            out.slope = slope
         st = bn.state(self, c)
         if bn not in self.aux:
             self.aux.append(bn)
@@ -770,7 +773,7 @@ class Plan:
         elems = n * h * w * c
         self.fwd.append(_tag(lambda: ops.bn_forward(x.act, None if res is None else res.act, out.act, m.weight.data,
                                                     m.bias.data, m.running_mean, m.running_var, mom, eps, training, relu6,
-                                                    rt, st.sums, st.coef),
+                                                    rt, st.sums, st.coef, slope),
                              "bn_fwd", 4.0 * elems * ((3 if training else 2) + (res is not None)), name or bn.name))
         self.named[name or bn.name] = out
 

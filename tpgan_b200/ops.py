@@ -397,12 +397,16 @@ def dwconv3x3_wgrad(x: Act, dy: Act, dw: torch.Tensor, stride: int) -> None:
 
 
 def bn_forward(x: Act, res: Optional[Act], y: Act, gamma, beta, running_mean, running_var, momentum: float, eps: float,
-               training: bool, relu6: bool, round_tf32: bool, sums: torch.Tensor, coef: torch.Tensor) -> None:
-    """nn.BatchNorm2d (+ReLU6 / + residual) forward; sums = float64[2C] scratch, coef = float32[4C] (kept for backward)."""
-    assert sums.dtype == torch.float64 and coef.dtype == torch.float32
+               training: bool, relu6: bool, round_tf32: bool, sums: torch.Tensor, coef: torch.Tensor,
+               slope: Optional[float] = None) -> None:
+    """nn.BatchNorm2d (+ReLU6 | + (Leaky)ReLU(slope), + residual) forward; sums = float64[2C+1] scratch, coef =
+    float32[4C] (kept for backward)."""
+    assert sums.dtype == torch.float64 and coef.dtype == torch.float32 and not (relu6 and slope is not None)
+    act = 1 if relu6 else (2 if slope is not None else 0)
     _lib.check(_lib.load().tpgan_bn_forward(x.view(), _v(res), y.view(), _ptr(gamma), _ptr(beta), _ptr(running_mean),
-                                            _ptr(running_var), momentum, eps, int(training), int(relu6), int(round_tf32),
-                                            sums.data_ptr(), _ptr(coef), _stream()), "bn_forward")
+                                            _ptr(running_var), momentum, eps, int(training), act,
+                                            0.0 if slope is None else float(slope), int(round_tf32), sums.data_ptr(),
+                                            _ptr(coef), _stream()), "bn_forward")
 
 
 def bn_backward(dy: Act, x: Act, dx: Act, coef: torch.Tensor, training: bool, relu6: bool, accumulate: bool,
