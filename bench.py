@@ -292,6 +292,7 @@ def run_b200(a):
 
 # ------------------------------------------------------------------------------------------------ Pretrain workload
 PRETRAIN_METRIC = "mobilenetv2_pretrain_step_images_per_sec"
+PRETRAIN_METRIC_RESNET = "resnet18_pretrain_step_images_per_sec"
 
 
 def cpu_pretrain_step_time(batch: int, steps: int, warmup: int):
@@ -311,19 +312,51 @@ def cpu_pretrain_step_time(batch: int, steps: int, warmup: int):
     return sum(ts) / len(ts), torch.get_num_threads()
 
 
+def cpu_classifier_step_time(batch: int, steps: int, warmup: int):
+    """Seconds per oracle-port ResNet18-128 classifier pre-training step (fp32 PyTorch, all host threads)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import identity_port as ip
+    from tpgan_b200.ResNet import BasicBlock, ResNet18
+    torch.manual_seed(0)
+    net = ResNet18(BasicBlock, 347, True, 256)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    names = [k for k, _ in net.named_parameters()]
+    params = [sd[k].requires_grad_(True) for k in names]
+    from oracle.pretrain_port import SGD
+    opt = torch.optim.SGD(params, **SGD)
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.rand((batch, 3, 128, 128), generator=g) * 2 - 1, torch.randint(0, 347, (batch,), generator=g)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        F.cross_entropy(ip.resnet18_128(sd, x, training=True)[0], y).backward()
+        opt.step()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts), torch.get_num_threads()
+
+
 def run_pretrain_reference(a):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     batch = a.batch
-    sec, threads = cpu_pretrain_step_time(batch, a.steps, max(a.warmup, 1))
+    resnet = a.backbone == "resnet"
+    sec, threads = (cpu_classifier_step_time if resnet else cpu_pretrain_step_time)(batch, a.steps, max(a.warmup, 1))
     val = batch / sec
-    sample = f"oracle fp32 PyTorch port of MobileNetV2 + MultiTaskLoss + SGD step, batch {batch} per step, {a.steps} steps"
-    line = {"impl": "reference", "metric": PRETRAIN_METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    sample = (f"oracle fp32 PyTorch port of ResNet18-128 + cross-entropy + SGD step, batch {batch} per step, {a.steps} steps"
+              if resnet else
+              f"oracle fp32 PyTorch port of MobileNetV2 + MultiTaskLoss + SGD step, batch {batch} per step, {a.steps} steps")
+    line = {"impl": "reference", "metric": PRETRAIN_METRIC_RESNET if resnet else PRETRAIN_METRIC, "value": val, "unit": UNIT,
+            "n_gpus": a.gpus, "steps": a.steps,
             "warmup": max(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Pretrain.py step: MobileNetV2-SSD + MultiTaskLoss + SGD-Nesterov, batch {batch}, 128x128",
+            "config": {"workload": (f"feature-extractor pre-training step: ResNet18-128 + cross-entropy + SGD-Nesterov, batch {batch}"
+                                    if resnet else
+                                    f"Pretrain.py step: MobileNetV2-SSD + MultiTaskLoss + SGD-Nesterov, batch {batch}, 128x128"),
                        "per_step_batch": batch},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -345,13 +378,21 @@ def run_pretrain(a):
     from oracle import pretrain_port as P   # synthetic batch generator only (inputs, not compute)
     from tpgan_b200 import _lib
     from tpgan_b200.MobileNetV2 import MobileNetV2
-    from tpgan_b200.pretrain_step import PretrainTrainer
+    from tpgan_b200.pretrain_step import ClassifierTrainer, PretrainTrainer
     B = a.batch
+    resnet = a.backbone == "resnet"
     torch.manual_seed(0)
-    net = MobileNetV2().to(dev)
-    tr = PretrainTrainer(net, B, device=dev, world_size=world, use_graphs=not a.no_graphs)
     x, true, u = P.make_batch(B, seed=1234 + rank)
-    host = [t.contiguous().pin_memory() for t in (x, true, u)]
+    if resnet:
+        from tpgan_b200.FeatureExtract import FeatureExtractModel
+        from tpgan_b200.ResNet import BasicBlock
+        net = FeatureExtractModel("resnet", 347, residualBlock=BasicBlock, feature_layer_dim_before_FC=256).to(dev)
+        tr = ClassifierTrainer(net, B, device=dev, world_size=world, use_graphs=not a.no_graphs)
+        host = [x.contiguous().pin_memory(), torch.randint(0, 347, (B,), generator=torch.Generator().manual_seed(rank)).pin_memory()]
+    else:
+        net = MobileNetV2().to(dev)
+        tr = PretrainTrainer(net, B, device=dev, world_size=world, use_graphs=not a.no_graphs)
+        host = [t.contiguous().pin_memory() for t in (x, true, u)]
     devb = [t.to(dev) for t in host]
     h2d = sum(t.numel() * t.element_size() for t in host)
 
@@ -445,15 +486,18 @@ def run_pretrain(a):
                 "peak_source": f"MEASURED_PEAKS.json ({which})",
                 "other_kernels": {names.get(k, k): entry(k) for k in agg if k != dom}}
         if not a.no_cpu:
-            sec, threads = cpu_pretrain_step_time(B, 2, 1)
+            sec, threads = (cpu_classifier_step_time if resnet else cpu_pretrain_step_time)(B, 2, 1)
             cpu = {"value": B / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"two oracle-port Pretrain steps (fp32 PyTorch, CPU) at batch {B} after one warm-up"}
+                   "sample": f"two oracle-port {'ResNet18 classifier' if resnet else 'Pretrain'} steps (fp32 PyTorch, CPU) at batch {B} after one warm-up"}
         gb = B * world
-        line = {"metric": PRETRAIN_METRIC, "value": gb * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        line = {"metric": PRETRAIN_METRIC_RESNET if resnet else PRETRAIN_METRIC, "value": gb * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-                "config": {"workload": f"Pretrain.py step: MobileNetV2-SSD forward/backward (training BatchNorm) + batched "
-                                       f"MultiTaskLoss + SGD-Nesterov, batch {B}/GPU, 128x128 synthetic faces",
+                "config": {"workload": (f"feature-extractor pre-training step: ResNet18-128 forward/backward (training BatchNorm) + "
+                                        f"softmax cross-entropy (347 identities) + SGD-Nesterov, batch {B}/GPU, 128x128 synthetic faces"
+                                        if resnet else
+                                        f"Pretrain.py step: MobileNetV2-SSD forward/backward (training BatchNorm) + batched "
+                                        f"MultiTaskLoss + SGD-Nesterov, batch {B}/GPU, 128x128 synthetic faces"),
                            "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
                            "l2": "the step's working set (~1.2 GB at batch 32) exceeds the 126 MB L2; no flush between steps",
                            "cuda_graphs": not a.no_graphs},
@@ -478,6 +522,8 @@ def main():
                          "step (configs[4])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-layer", default="", help="write the per-launch conv/wgrad timing table (JSON lines) here")
+    ap.add_argument("--backbone", default="mobilenetv2", choices=["mobilenetv2", "resnet"],
+                    help="pretrain workload: MobileNetV2-SSD landmark pre-training (Pretrain.py) or ResNet18 identity classifier")
     ap.add_argument("--identity", action="store_true", help="gan workload: add the frozen identity network's loss (configs[2], tf32)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()

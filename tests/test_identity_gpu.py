@@ -204,3 +204,48 @@ def test_resnet_training_mode_vs_oracle(exact, use_bn):
         assert rel(le, want_l) < (1e-3 if exact else 1e-2) and rel(fe, want_f) < (1e-3 if exact else 1e-2)
     finally:
         M.EXACT_MODE = False
+
+
+def test_classifier_trainer_step_vs_oracle():
+    """The fused pre-training step of the ResNet backbone (ClassifierTrainer, fp32-exact mode, CUDA-graph replay from the
+    second call): loss and SGD-Nesterov update against the oracle port driven by torch.optim.SGD, re-synchronised per step."""
+    import math
+
+    from oracle import identity_port as ip
+    from oracle.pretrain_port import SGD
+    from tpgan_b200.FeatureExtract import FeatureExtractModel
+    from tpgan_b200.pretrain_step import ClassifierTrainer
+    from tpgan_b200.ResNet import BasicBlock
+    torch.manual_seed(5)
+    model = FeatureExtractModel("resnet", 347, residualBlock=BasicBlock, feature_layer_dim_before_FC=256)
+    net = model.base_model
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    names = [k for k, _ in net.named_parameters()]
+    params = [sd[k].requires_grad_(True) for k in names]
+    opt = torch.optim.SGD(params, **SGD)
+    model.cuda()
+    B = 6
+    tr = ClassifierTrainer(model, B, exact=True, use_graphs=True)
+    pg = dict(net.named_parameters())
+    for it in range(3):
+        g = torch.Generator().manual_seed(30 + it)
+        x, y = torch.rand((B, 3, 128, 128), generator=g) * 2 - 1, torch.randint(0, 347, (B,), generator=g)
+        before = {k: sd[k].detach().clone() for k in names}
+        opt.zero_grad()
+        want = F.cross_entropy(ip.resnet18_128(sd, x, training=True)[0], y)
+        want.backward()
+        opt.step()
+        m = tr.step(x.cuda(), y.cuda())
+        assert abs(m["loss"] - float(want)) <= 1e-3 * abs(float(want)), (it, m, float(want))
+        num = den = 0.0
+        for k in names:
+            d_g, d_w = (pg[k].detach().cpu() - before[k]).double(), (sd[k].detach() - before[k]).double()
+            num += float((d_g - d_w).pow(2).sum())
+            den += float(d_w.pow(2).sum())
+        assert math.sqrt(num / den) < 5e-2, (it, math.sqrt(num / den))
+        for k, p in zip(names, params):          # re-synchronise parameters + momentum, re-pack the tensor-core copies
+            pg[k].data.copy_(p.detach())
+            o = tr.flat.offsets["base_model." + k]
+            tr.flat.m[o:o + p.numel()].copy_(opt.state[p]["momentum_buffer"].flatten())
+        for L in tr.plan.layers:
+            L.repack()

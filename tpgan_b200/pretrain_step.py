@@ -26,11 +26,13 @@ OPTIM = dict(learning_rate=5e-4, momentum=0.9, nesterov=True, weight_decay=5e-4)
 LR_MILESTONES, LR_GAMMA = (10, 20, 30), 0.1     # config.py:16-18, Pretrain.py:117-121 (MultiStepLR)
 
 
-class PretrainTrainer:
-    """step(images (B,3,H,W) in [-1,1], labels (B,8) = 4 ground-truth points (x,y), u (B,n) optional sub-sampling keys)."""
+class _FlatSGDTrainer:
+    """What the two pre-training trainers share: flat parameter / gradient / momentum buffers, the traced plan with
+    direct parameter gradients, the launch schedule (stage -> forward -> loss -> backward -> export -> [all-reduce] ->
+    SGD-Nesterov -> re-pack), CUDA-graph replay, MultiStepLR and the torch.optim-compatible optimizer view.  Subclasses
+    provide _trace_model(plan) (returns the output tensors whose gradients the loss writes), load_inputs, _stage, _loss."""
 
-    def __init__(self, model: MobileNetV2, B: int, image_hw=(128, 128), device="cuda", exact: bool = False,
-                 world_size: int = 1, group=None, use_graphs: bool = False):
+    def _setup(self, model, B: int, image_hw, device, exact: bool, world_size: int, group, use_graphs: bool):
         self.model, self.B, self.device = model, B, torch.device(device)
         self.hw = tuple(image_hw)
         self.world_size, self.group, self.use_graphs = world_size, group, use_graphs
@@ -47,19 +49,30 @@ class PretrainTrainer:
         self.plan = plan
         H, W = self.hw
         self.x = plan.new(B, H, W, 3, name="images", requires_grad=False)
-        self.loc, self.cls = model.trace(plan, self.x)
-        plan.seed_grad(self.loc)
-        plan.seed_grad(self.cls)
+        for t in self._trace_model(plan):
+            plan.seed_grad(t)
         plan.trace_backward()
-        self.n = self.loc.act.c // 2
-        assert self.cls.act.c == 5 * self.n
         self.set = LayerSet(plan.layers, self.device, plan.bias_jobs)
         self.set.repack()
         self.sums = torch.zeros(4, dtype=torch.float32, device=self.device)
-        self.labels = torch.zeros((B, self.n), dtype=torch.int32, device=self.device)
         self.inp: Optional[Dict[str, torch.Tensor]] = None
         self._sched: Dict[bool, object] = {}
         self.steps = 0
+
+
+class PretrainTrainer(_FlatSGDTrainer):
+    """step(images (B,3,H,W) in [-1,1], labels (B,8) = 4 ground-truth points (x,y), u (B,n) optional sub-sampling keys)."""
+
+    def __init__(self, model: MobileNetV2, B: int, image_hw=(128, 128), device="cuda", exact: bool = False,
+                 world_size: int = 1, group=None, use_graphs: bool = False):
+        self._setup(model, B, image_hw, device, exact, world_size, group, use_graphs)
+        self.n = self.loc.act.c // 2
+        assert self.cls.act.c == 5 * self.n
+        self.labels = torch.zeros((B, self.n), dtype=torch.int32, device=self.device)
+
+    def _trace_model(self, plan: Plan):
+        self.loc, self.cls = self.model.trace(plan, self.x)
+        return [self.loc, self.cls]
 
     # ---- inputs live in static device buffers so that every pointer of the schedule is fixed
     def load_inputs(self, images: torch.Tensor, labels: torch.Tensor, u: Optional[torch.Tensor]):
@@ -140,5 +153,42 @@ class PretrainTrainer:
     def sync_buffers(self):
         """num_batches_tracked of every BatchNorm2d (state_dict parity with nn.BatchNorm2d in train mode)."""
         for m in self.model.modules():
-            if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None:
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)) and m.num_batches_tracked is not None:
                 m.num_batches_tracked.fill_(self.steps)
+
+
+class ClassifierTrainer(PretrainTrainer):
+    """Pre-training of the feature extractor as an identity classifier (BASELINE config 5, "ResNet backbones"; what
+    FeatureExtract.py:5-41 builds: a backbone + Linear(., num_of_output_classes)): ResNet18-128 forward with batch-statistics
+    BatchNorm, softmax cross-entropy, backward, SGD-Nesterov - the same fused schedule as PretrainTrainer.
+    step(images (B,3,128,128) in [-1,1], labels (B,) int64)."""
+
+    def __init__(self, model, B: int, image_hw=(128, 128), device="cuda", exact: bool = False, world_size: int = 1,
+                 group=None, use_graphs: bool = False):
+        net = getattr(model, "base_model", model)      # FeatureExtractModel or the ResNet18 itself
+        self.net = net
+        self._setup(model, B, image_hw, device, exact, world_size, group, use_graphs)
+        self.num_classes = self.logits.act.c
+
+    def _trace_model(self, plan: Plan):
+        self.logits, self.fc0, self.pooled = self.net.trace_train(plan, self.x)
+        return [self.logits]
+
+    def load_inputs(self, images: torch.Tensor, labels: torch.Tensor, u=None):
+        if self.inp is None:
+            self.inp = dict(images=torch.empty((self.B, 3) + self.hw, dtype=torch.float32, device=self.device),
+                            labels=torch.empty((self.B,), dtype=torch.int64, device=self.device))
+        self.inp["images"].copy_(images, non_blocking=True)
+        self.inp["labels"].copy_(labels.reshape(self.B), non_blocking=True)
+
+    def _stage(self):
+        self.x.act.from_nchw(self.inp["images"], round_tf32=not self.plan.exact)
+
+    def _loss(self):
+        ops.softmax_ce(self.logits.act, self.inp["labels"], self.plan.grad_act(self.logits), 1.0 / self.B, self.sums[0:1])
+
+    def read_metrics(self) -> Dict[str, float]:
+        return dict(loss=float(self.sums[0].cpu()) / self.B)
+
+    def outputs(self):
+        return self.logits.act.buf.view(self.B, -1)[:, :self.num_classes].clone()
