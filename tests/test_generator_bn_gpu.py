@@ -1,0 +1,84 @@
+"""Generator(zdim, num_classes, use_batchnorm=True, ...) - the reference constructor's DEFAULT (D_and_G_model.py:351; config.py
+turns it off) - against golden vectors recorded from the live reference (tools/make_golden_bn.py; the reference needs the
+F1-F4 shim to construct this variant): conv / deconv (no bias) -> batch-statistics BatchNorm2d -> (Leaky)ReLU in every
+factory stack of the two pathways, 55 BatchNorm layers, outputs written straight into the concat buffers.
+
+fp32-exact mode pins it: outputs <= 1e-3 (training-mode BatchNorm over a batch of 2 amplifies round-off: 2 x 5x5 = 50 samples
+per channel in the local pathways' bottleneck), running statistics <= 1e-3, gradients: every BatchNorm affine gradient and
+the per-parameter norms <= 5e-2 overall.  TF32: outputs sanity-bounded (0.15)."""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "generator_bn_golden.pt")
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _functional(outs, seed=11):      # tools/make_golden_bn.py::functional
+    g = torch.Generator().manual_seed(seed)
+    total = 0.0
+    for o in (outs[0], outs[1], outs[3], outs[4], outs[5], outs[6]):
+        w = torch.randn(o.shape, generator=g)
+        total = total + (o * w.to(o.device)).sum() / o[0].numel()
+    return total
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_generator_with_batchnorm_vs_live_reference_goldens(exact):
+    import tpgan_b200.D_and_G_model as M
+    from oracle import step as ostep
+    gold = torch.load(GOLD, weights_only=False)
+    M.EXACT_MODE = exact
+    try:
+        torch.manual_seed(0)
+        G = M.Generator(64, 347, True, False)          # seeded init is bit-identical to the reference's (548 state_dict keys)
+        assert len(G.state_dict()) == 548
+        G.cuda().train()
+        b = {k: v.cuda() for k, v in ostep.make_batch(2, seed=3).items()}
+        outs = G(b["img"], b["left_eye"], b["right_eye"], b["nose"], b["mouth"], b["z"], False)
+        tol = 1e-3 if exact else 0.15
+        assert rel(outs[0], gold["fake"]) < tol and rel(outs[1], gold["logits"]) < tol, (rel(outs[0], gold["fake"]),
+                                                                                         rel(outs[1], gold["logits"]))
+        for o, w in zip((outs[3], outs[4], outs[5], outs[6]), gold["local"]):
+            assert rel(o, w) < tol
+        if not exact:
+            return
+        sd = G.state_dict()
+        for k, v in gold["running"].items():
+            assert rel(sd[k], v) < 1e-3, k
+        assert int(sd["global_pathway.conv0.0.1.num_batches_tracked"]) == 1
+        _functional(outs).backward()
+        num = den = 0.0
+        for k, p in G.named_parameters():
+            n_ref, s_ref = gold["grad_stats"][k]
+            assert p.grad is not None, k
+            num += (float(p.grad.norm()) - n_ref) ** 2
+            den += n_ref ** 2
+        assert math.sqrt(num / den) < 5e-2, math.sqrt(num / den)
+        pg = dict(G.named_parameters())
+        num = den = 0.0
+        for k, g in gold["bn_grads"].items():
+            num += float((pg[k].grad.double().cpu() - g.double()).pow(2).sum())
+            den += float(g.double().pow(2).sum())
+        assert math.sqrt(num / den) < 5e-2, math.sqrt(num / den)
+        G.eval()
+        with torch.no_grad():
+            oe = G(b["img"], b["left_eye"], b["right_eye"], b["nose"], b["mouth"], b["z"], False)
+        assert rel(oe[0], gold["eval_fake"]) < 2e-3 and rel(oe[1], gold["eval_logits"]) < 2e-3
+    finally:
+        M.EXACT_MODE = False
+
+
+def test_fused_trainer_rejects_batchnorm_models():
+    import tpgan_b200.D_and_G_model as M
+    from tpgan_b200.train_step import TPGANTrainer
+    G, D = M.Generator(64, 347, True, False).cuda(), M.Discriminator(False).cuda()
+    with pytest.raises(NotImplementedError, match="module API"):
+        TPGANTrainer(G, D, 1)

@@ -39,19 +39,22 @@ PART_NAMES = ("left_eye", "right_eye", "nose", "mouth")
 
 # ---------------------------------------------------------------------------------------------------- tracing helpers
 def _unpack_conv_seq(seq: nn.Sequential):
-    """conv()/deconv() factory output -> (reflection pad or None, conv module, fused activation slope or None)."""
-    pad_mod, conv_mod, slope = None, None, None
+    """conv()/deconv() factory output -> (reflection pad or None, conv module, fused activation slope or None, BatchNorm2d
+    or None).  With use_batchnorm=True the factories emit [pad] -> conv(bias=False) -> BatchNorm2d -> act
+    (ModificationLayer.py:125-156)."""
+    pad_mod, conv_mod, slope, bn_mod = None, None, None, None
     for m in seq:
         if isinstance(m, nn.ReflectionPad2d):
             pad_mod = m
         elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
             conv_mod = m
         elif isinstance(m, nn.BatchNorm2d):
-            raise NotImplementedError("use_batchnorm=True is not on the TP-GAN hot path (config.py:63,68 set it False)")
+            assert conv_mod is not None, "pre_activation stacks are not used by the G/D models"
+            bn_mod = m
         else:
             assert conv_mod is not None, "pre_activation stacks are not used by the G/D models"
             slope = _negative_slope(m)
-    return pad_mod, conv_mod, slope
+    return pad_mod, conv_mod, slope, bn_mod
 
 
 def _layer(conv_mod, name: str) -> ConvLayer:
@@ -70,9 +73,9 @@ def _layer(conv_mod, name: str) -> ConvLayer:
 def t_conv(plan: Plan, seqs: Sequence[nn.Sequential], xs: Sequence[T], outs=None, residuals=None, names=None,
            slope_override="same") -> List[T]:
     """Grouped conv()/deconv() stack: [reflect pad] -> conv (+bias, +residual) -> activation, one launch for all groups."""
-    layers, xin, slopes = [], [], []
+    layers, xin, slopes, bns = [], [], [], []
     for i, (seq, x) in enumerate(zip(seqs, xs)):
-        pad_mod, cm, slope = _unpack_conv_seq(seq)
+        pad_mod, cm, slope, bn = _unpack_conv_seq(seq)
         if pad_mod is not None:
             l, r, t, b = pad_mod.padding
             assert r == 0 and b == 0, "only left/top reflection padding is used (D_and_G_model.py:235)"
@@ -80,9 +83,19 @@ def t_conv(plan: Plan, seqs: Sequence[nn.Sequential], xs: Sequence[T], outs=None
         layers.append(_layer(cm, names[i] if names else ""))
         xin.append(x)
         slopes.append(slope)
-    assert all(s == slopes[0] for s in slopes)
+        bns.append(bn)
+    assert all(s == slopes[0] for s in slopes) and all((b is None) == (bns[0] is None) for b in bns)
     slope = slopes[0] if slope_override == "same" else slope_override
-    return plan.conv(layers, xin, slope, outs=outs, residuals=residuals)
+    if bns[0] is None:
+        return plan.conv(layers, xin, slope, outs=outs, residuals=residuals)
+    # use_batchnorm=True: one grouped conv launch (full fp32 out, no bias), then BatchNorm (+ residual) + activation per group,
+    # written straight into the concat slice where there is one
+    from .MobileNetV2 import BNLayer, _aux
+    hs = plan.conv(layers, xin, None, round_out=False)
+    res = list(residuals) if residuals is not None else [None] * len(hs)
+    return [plan.batchnorm(_aux(bn, BNLayer, (names[i] if names else "") + ".bn"), h, res=res[i], slope=slope,
+                           out=None if outs is None else outs[i])
+            for i, (bn, h) in enumerate(zip(bns, hs))]
 
 
 def t_res(plan: Plan, blocks: Sequence[ResidualBlock], xs: Sequence[T], outs=None, names=None) -> List[T]:
@@ -176,12 +189,17 @@ class TracedModule(nn.Module):
             if not x.is_cuda:
                 raise RuntimeError("tpgan_b200 modules run on CUDA tensors only (there is no CPU fallback); "
                                    "move the module and its inputs to a B200 device")
-        key = (tuple((tuple(x.shape), bool(x.requires_grad)) for x in tensors), static, torch.is_grad_enabled())
+        key = (tuple((tuple(x.shape), bool(x.requires_grad)) for x in tensors), static, torch.is_grad_enabled(),
+               bool(self.training))
         cache = self._cache()
         traced = cache.plans.get(key)
         if traced is None:
             traced = self._build(tensors, static, torch.is_grad_enabled())
             cache.plans[key] = traced
+        if self.training:   # nn.BatchNorm bookkeeping in train mode (the statistics themselves are updated by the kernels)
+            for m in self.modules():
+                if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None:
+                    m.num_batches_tracked += 1
         params = [p for p in self.parameters()]
         outs = _EngineFn.apply(self, traced, len(tensors), *tensors, *params)
         return outs
@@ -189,6 +207,7 @@ class TracedModule(nn.Module):
     def _build(self, tensors, static, grad_enabled) -> _Traced:
         dev = tensors[0].device
         plan = Plan(dev, training=grad_enabled, need_wgrad=grad_enabled, exact=EXACT_MODE)
+        plan.bn_training = bool(self.training)     # BatchNorm follows module.train() / .eval(), not the autograd mode
         ins = []
         for x in tensors:
             if x.dim() == 2:
@@ -414,8 +433,15 @@ class GlobalPathway(TracedModule):
         fc1 = plan.conv([fc1_layer], conv4, None)[0]                       # Linear(32768, 512) as an 8x8 valid conv
         fc2 = plan.maxout2(fc1, name="fc2")                               # MaxPool1d(2,2) "maxout"
         plan.copy(fc2, B["zin"].parts[0])
-        d8_flat = plan.conv([dec8_layer], [B["zin"]], 0.0)[0]              # ConvTranspose2d k8 on 1x1 = GEMM, ReLU
-        d8 = plan.alias(d8_flat, 8, 8, self.deconv_8.out_channels, name="deconv_8")
+        bn8 = next((m for m in self.deconv_8 if isinstance(m, nn.BatchNorm2d)), None)
+        if bn8 is None:
+            d8_flat = plan.conv([dec8_layer], [B["zin"]], 0.0)[0]          # ConvTranspose2d k8 on 1x1 = GEMM, ReLU
+            d8 = plan.alias(d8_flat, 8, 8, self.deconv_8.out_channels, name="deconv_8")
+        else:                                                              # use_batchnorm=True: GEMM -> BatchNorm2d(8x8 map) -> ReLU
+            from .MobileNetV2 import BNLayer, _aux
+            d8_flat = plan.conv([dec8_layer], [B["zin"]], None, round_out=False)[0]
+            d8 = plan.alias(d8_flat, 8, 8, self.deconv_8.out_channels, name="deconv_8.gemm")
+            d8 = plan.batchnorm(_aux(bn8, BNLayer, f"{pre}.deconv_8.bn"), d8, slope=0.0, name="deconv_8")
         plan.copy(d8, B["f8"].parts[0])
         d32 = t_conv(plan, [self.deconv_32], [d8], outs=[B["a32"].parts[0]], names=nm("deconv_32"))
         d64 = t_conv(plan, [self.deconv_64], d32, outs=[B["a64"].parts[0]], names=nm("deconv_64"))

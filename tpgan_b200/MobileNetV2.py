@@ -257,16 +257,12 @@ class MobileNetV2(TracedModule):
         return self.ssd_head.trace(plan, feats)
 
     def _trace(self, plan, x, static=()):
-        plan.training = bool(static[0]) if static else self.training   # batch statistics <=> module.train()
+        plan.bn_training = bool(static[0]) if static else self.training   # batch statistics <=> module.train()
         return self.trace(plan, x)
 
     def forward(self, x, use_dropout=False):
         # use_dropout is accepted and ignored, as in the reference (MobileNetV2.py:180: the flag is never read)
-        if self.training:
-            for m in self.modules():
-                if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None:
-                    m.num_batches_tracked += 1
-        loc, cls = self._traced_call([x], static=(self.training,))
+        loc, cls = self._traced_call([x], static=(self.training,))     # (bumps num_batches_tracked in train mode)
         n = x.shape[0]
         return loc.reshape(n, -1, 2), cls.reshape(n, -1, self.ssd_head.num_of_out_classes)
 

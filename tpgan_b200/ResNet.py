@@ -197,7 +197,7 @@ class ResNet18(TracedModule):
         return logits, fc0, pooled
 
     def _trace(self, plan, x, static=()):
-        plan.training = True
+        plan.training = plan.bn_training = True     # max-pool arg-max is recorded, BatchNorm uses batch statistics
         logits, fc0, _ = self.trace_train(plan, x)
         logits.flat = True
         if fc0 is not None:
@@ -210,9 +210,6 @@ class ResNet18(TracedModule):
         if self.training:
             if use_dropout and self.dropout.p > 0:
                 raise NotImplementedError("dropout > 0 between FC0 and FC is not built (ResNet.py:52 default 0.0)")
-            for m in self.modules():
-                if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)) and m.num_batches_tracked is not None:
-                    m.num_batches_tracked += 1
             self._traced_layers = None      # the folded eval-mode copies are stale once the weights train
             outs = self._traced_call([x], static=("train",))
             return (outs[0], outs[1]) if len(outs) > 1 else (outs[0], None)

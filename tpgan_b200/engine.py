@@ -373,6 +373,7 @@ class Plan:
         self.named: Dict[str, T] = {}         # layer name -> its output tensor (introspection / tests)
         self.aux: list = []                   # non-tensor-core parameter holders (BatchNorm, depthwise conv) of this plan
         self.direct_grads = False             # aux layers write straight into param.grad (flat buffers of a trainer)
+        self.bn_training: Optional[bool] = None   # BatchNorm mode when it differs from `training` (module.train() under no_grad)
 
     # ------------------------------------------------------------------ buffers
     def new(self, n, h, w, c, slope=LINEAR, name="", requires_grad=True) -> T:
@@ -750,19 +751,23 @@ class Plan:
 
     # ------------------------------------------------------------------ Pretrain path (MobileNetV2.py) ops
     def batchnorm(self, bn, x: T, res: Optional[T] = None, relu6: bool = False, round_out: bool = True,
-                  round_dx: bool = True, name: str = "", slope: Optional[float] = None) -> T:
+                  round_dx: bool = True, name: str = "", slope: Optional[float] = None, out: Optional[T] = None) -> T:
         """nn.BatchNorm2d (+nn.ReLU6, + the residual add of InvertedResidual.forward, MobileNetV2.py:107-120).  `bn` is a
         BNLayer (tpgan_b200/MobileNetV2.py).  Training plans use batch statistics and update the running ones."""
         n, h, w, c = x.shape
         assert c % 4 == 0 and x.act.c0 == 0 and x.act.buf.shape[3] == c, "BatchNorm needs a whole pixel-dense buffer"
-        out = self.new(n, h, w, c, name=name or bn.name)
+        if out is None:
+            out = self.new(n, h, w, c, name=name or bn.name)
+        else:   # write straight into a pre-allocated tensor (a channel slice of a concat buffer): pixel-dense, 16-byte lanes
+            assert (out.act.n, out.act.h, out.act.w, out.act.c) == (n, h, w, c) and out.act.c0 % 4 == 0, (out.shape, x.shape)
+            out.slope = LINEAR
         if slope is not None:      # (Leaky)ReLU after the BatchNorm (+ residual): forward in the kernel, backward through
             assert not relu6       # the engine's activation-mask machinery (sign of the stored output)
             out.slope = slope
         st = bn.state(self, c)
         if bn not in self.aux:
             self.aux.append(bn)
-        training = self.training
+        training = self.training if self.bn_training is None else self.bn_training
         rt = round_out and not self.exact
         self.use(x)
         if res is not None:

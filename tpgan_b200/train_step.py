@@ -268,7 +268,7 @@ class CriticPlan:
                 self.ops_.append(dict(kind="res", L1=L1, L2=L2, x=cur, h=hmid, y=y, s1=s1, s2=_negative_slope(m.activation)))
                 cur = y
             else:
-                _, cm, slope = _unpack_conv_seq(m)
+                _, cm, slope, _bn = _unpack_conv_seq(m)
                 L = self._mk(m, f"model.{i}", cur.c)
                 hw = (hw + 2 * L.pad - L.k) // L.stride + 1
                 y = new(M, hw, L.cout)
@@ -297,7 +297,7 @@ class CriticPlan:
         self._build()
 
     def _mk(self, seq, name, in_c) -> ConvLayer:
-        _, cm, _ = _unpack_conv_seq(seq)
+        _, cm, _, _bn = _unpack_conv_seq(seq)
         L = _layer(cm, name)
         L.setup(None, None, in_c, L.cout, self.device, exact=self.exact)
         self.layers.append(L)
@@ -515,6 +515,9 @@ class TPGANTrainer:
         """identity_net: optional frozen FeatureExtractModel / ResNet18 in eval() mode; adds the identity-preserving
         term weight_identity_preserving * L_ip to the generator loss."""
         self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
+        if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for net in (G, D) for m in net.modules()):
+            raise NotImplementedError("the fused G/D step is built for the config.py defaults (use_batchnorm False, config.py:63,"
+                                      "68); BatchNorm models train through the module API (forward / backward / optimizer)")
         self.use_dropout, self.exact = use_dropout, exact
         # "float": TrainDataset tensors (img, img_frontal, img64_frontal, img32_frontal as NCHW fp32 in [-1,1]);
         # "uint8": raw HWC bytes img_u8 / img_frontal_u8 (B,128,128,3) - ToTensor()*2-1 and the 64/32 targets are computed
