@@ -480,3 +480,48 @@ def test_full_size_forward_tf32_vs_emulated_oracle():
         with torch.no_grad():
             lg, cg = net(x.cuda())
         assert rel(lg, le) < tol and rel(cg, ce) < tol, (train, rel(lg, le), rel(cg, ce))
+
+
+def test_network_rejects_unsupported_aspect_ratio():
+    from tpgan_b200.MobileNetV2 import MobileNetV2
+    net = MobileNetV2().cuda().eval()
+    with pytest.raises(NotImplementedError, match="extent 1 in one dimension"):
+        net(torch.zeros(1, 3, 128, 64, device="cuda"))
+
+
+@pytest.mark.parametrize("hw,batch", [((64, 64), 3), ((256, 256), 1)])
+def test_network_other_image_sizes(hw, batch):
+    """The reference runs batch 1 'to handle images of different spatial size' (config.py:12): the traced network follows the
+    input size (plans are cached per shape).  fp32-exact mode against the oracle, forward and parameter gradients; the
+    number of predicted points follows MobileNetV2.num_points."""
+    import tpgan_b200.D_and_G_model as M
+    from oracle.pretrain_port import MobileNetV2Port
+    from tpgan_b200.MobileNetV2 import MobileNetV2
+    M.EXACT_MODE = True
+    try:
+        port, net = _nets(seed=9)
+        g = torch.Generator().manual_seed(1)
+        x = torch.rand((batch, 3) + hw, generator=g) * 2 - 1
+        port.eval(), net.eval()          # running statistics: a batch of 1 has no usable batch statistics at 1x1 maps
+        lw, cw = port(x)
+        lg, cg = net(x.cuda())
+        n = MobileNetV2.num_points(*hw)
+        assert lg.shape == (batch, n, 2) and cg.shape == (batch, n, 5) and lw.shape == lg.shape
+        assert rel(lg, lw) < 2e-4 and rel(cg, cw) < 2e-4, (rel(lg, lw), rel(cg, cw))
+        gen = torch.Generator().manual_seed(2)
+        dl, dc = torch.randn(lw.shape, generator=gen), torch.randn(cw.shape, generator=gen)
+        torch.autograd.backward([lw, cw], [dl, dc])
+        torch.autograd.backward([lg, cg], [dl.cuda(), dc.cuda()])
+        pg = dict(net.named_parameters())
+        num = den = 0.0
+        for k, p in port.named_parameters():
+            if p.grad is None:           # eval mode: BatchNorm affine parameters get no gradient from the eval-mode kernels
+                continue
+            if pg[k].grad is None:
+                assert "conv." in k or "conv1.1" in k or "conv2.1" in k, k
+                continue
+            num += float((pg[k].grad.double().cpu() - p.grad.double()).pow(2).sum())
+            den += float(p.grad.double().pow(2).sum())
+        assert math.sqrt(num / den) < 2e-2, math.sqrt(num / den)
+    finally:
+        M.EXACT_MODE = False

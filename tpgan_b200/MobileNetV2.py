@@ -126,6 +126,9 @@ def _layer_at(conv_mod: nn.Conv2d, name: str, x: T):
     """ConvLayer of a dense conv for input x.  A 3x3 / stride-2 / pad-1 conv applied to a 1x1 map (extra_layers 4 and 6,
     MobileNetV2.py:170-171) touches only its centre tap and yields a 1x1 map - the same arithmetic as stride 1, which is
     what the tensor-core kernel is given (its stride-2 parity planes need even extents)."""
+    if conv_mod.stride[0] == 2 and (x.act.h == 1) != (x.act.w == 1):
+        raise NotImplementedError(f"{name}: a stride-2 conv over a {x.act.h}x{x.act.w} map (extent 1 in one dimension only) is not "
+                                  "built; square power-of-two inputs (64, 128, 256) keep both extents equal down to 1x1")
     if conv_mod.stride[0] == 2 and x.act.h == 1 and x.act.w == 1:
         L = conv_mod.__dict__.get("_tc_layer_1x1")
         if L is None:
