@@ -417,7 +417,9 @@ def run_pretrain(a):
         return ms
 
     resident = lambda: tr.step(*devb, read_metrics=False)
-    e2e_step = lambda: tr.step(*host, read_metrics=True)     # pinned host batch in, loss read back, every step
+    hb = tuple(host)
+    # pinned host batch in (its copies are started on a copy stream during the previous step), loss read back, every step
+    e2e_step = lambda: tr.step(None, None, batch=hb, prefetch_next=hb, read_metrics=True)
     for _ in range(max(a.warmup, 3)):
         resident()
     sampler = ClockSampler(local)
@@ -429,6 +431,7 @@ def run_pretrain(a):
     if not a.no_graphs:
         launches = a.steps * list(tr._sched.values())[0].kernels_per_run
     clocks = sampler.stop() if rank == 0 else None
+    tr.prefetch(hb)
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, a.steps)

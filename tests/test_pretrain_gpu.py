@@ -525,3 +525,29 @@ def test_network_other_image_sizes(hw, batch):
         assert math.sqrt(num / den) < 2e-2, math.sqrt(num / den)
     finally:
         M.EXACT_MODE = False
+
+
+def test_prefetched_batches_give_the_same_steps():
+    """step(batch=..., prefetch_next=...) (host->device copies of the next batch on a copy stream) == step(images, labels, u).
+    Steps run without the optimizer so that they are independent: with updates, the summation-order noise of the atomics
+    (1e-6) is amplified into visibly different trajectories within two steps (see test_pretrain_step_vs_oracle)."""
+    from oracle import pretrain_port as P
+    from tpgan_b200.pretrain_step import PretrainTrainer
+    batches = [tuple(t.pin_memory() for t in P.make_batch(4, seed=70 + i)) for i in range(4)]
+    runs = []
+    for mode in ("direct", "prefetch"):
+        _, net = _nets(seed=11)
+        tr = PretrainTrainer(net, 4, use_graphs=True)
+        out = []
+        if mode == "prefetch":
+            tr.prefetch(batches[0])
+        for i, b in enumerate(batches):
+            if mode == "direct":
+                m = tr.step(*[t.cuda() for t in b], optimize=False)
+            else:
+                m = tr.step(None, None, batch=b, prefetch_next=batches[i + 1] if i + 1 < len(batches) else None, optimize=False)
+            out.append((m, tr.flat.grad.clone(), tr.labels.clone()))
+        runs.append(out)
+    for (ma, ga, la), (mb, gb, lb) in zip(*runs):
+        assert abs(ma["loss"] - mb["loss"]) <= 1e-5 * abs(ma["loss"]), (ma, mb)
+        assert torch.equal(la, lb) and rel(gb, ga) < 1e-4

@@ -91,16 +91,24 @@ def main(argv=None):
     history = []
     for epoch in range(a.epochs):
         t0, seen = time.time(), 0
-        for step, (images, labels) in enumerate(SyntheticLandmarks(a.batch, a.steps_per_epoch, seed=1000 * epoch + rank)):
-            m = trainer.step(images, labels)                                   # forward, loss, backward, SGD: one schedule
+        it = iter(SyntheticLandmarks(a.batch, a.steps_per_epoch, seed=1000 * epoch + rank))
+        cur, step = next(it, None), 0
+        if cur is not None:
+            trainer.prefetch(cur)
+        while cur is not None:
+            nxt = next(it, None)
+            # forward, loss, backward, SGD: one schedule; the next batch's host->device copies overlap it
+            m = trainer.step(None, None, batch=cur, prefetch_next=nxt)
             acc = float(decoder.decode(*trainer.outputs(), trainer.inp["labels"])[3].mean())   # Pretrain.py:165-168
             seen += a.batch * world
             history.append((m["loss"], acc))
-            if (step + 1) % a.log_every == 0 and rank == 0:
+            step += 1
+            if step % a.log_every == 0 and rank == 0:
                 vl, va = validate(model, loss_fn, decoder, SyntheticLandmarks(a.batch, a.val_steps, seed=777), device)
-                print(f"===== epoch: {epoch:2}, step: {step + 1:6} / {a.steps_per_epoch} =====\n train_loss: {m['loss']:6.4f}, "
+                print(f"===== epoch: {epoch:2}, step: {step:6} / {a.steps_per_epoch} =====\n train_loss: {m['loss']:6.4f}, "
                       f"train_accuracy: {acc:.4f}\nval_loss: {vl:6.4f}, val_accuracy {va:.4f}\n"
                       f"{seen / (time.time() - t0):.1f} imgs/s", flush=True)
+            cur = nxt
         if pretrain["use_learning_rate_scheduler"]:
             trainer.end_epoch()                                               # learning_rate_scheduler.step(), Pretrain.py:296
         if a.log_dir and rank == 0:

@@ -86,6 +86,39 @@ class PretrainTrainer(_FlatSGDTrainer):
             self.inp["u"].copy_(u, non_blocking=True)
         self._draw_u = u is None
 
+    # ---- the NEXT batch's host->device copies on a side stream while this step runs (pinned host tensors)
+    def prefetch(self, batch):
+        """batch = the tuple a later step() will be called with (the same object): staged into device buffers on a copy
+        stream now, picked up with device-to-device copies then."""
+        if getattr(self, "_pf_stream", None) is None:
+            self._pf_stream = torch.cuda.Stream(device=self.device)
+            self._pf_event = torch.cuda.Event()
+            self._pf_picked = None
+            self._pf_bufs = [None if t is None else torch.empty_like(t, device=self.device) for t in batch]
+        if self._pf_picked is not None:
+            self._pf_stream.wait_event(self._pf_picked)    # staging buffers are free once the last pick-up has run
+        with torch.cuda.stream(self._pf_stream):
+            for dst, src in zip(self._pf_bufs, batch):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            self._pf_event.record(self._pf_stream)
+        self._pf_batch = batch
+
+    def _take_prefetched(self, batch):
+        """If `batch` is the object handed to prefetch(), return its staged device copies (after waiting for the copy)."""
+        if getattr(self, "_pf_batch", None) is not batch or batch is None:
+            return batch
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._pf_event)
+        self._pf_batch = None
+        return tuple(self._pf_bufs)
+
+    def _mark_picked(self):
+        if getattr(self, "_pf_stream", None) is not None:
+            if self._pf_picked is None:
+                self._pf_picked = torch.cuda.Event()
+            self._pf_picked.record(torch.cuda.current_stream(self.device))
+
     def _stage(self):
         self.x.act.from_nchw(self.inp["images"], round_tf32=not self.plan.exact)
         if self._draw_u:
@@ -120,8 +153,16 @@ class PretrainTrainer(_FlatSGDTrainer):
         dist.all_reduce(self.flat.grad, group=self.group)
 
     def step(self, images: torch.Tensor, labels: torch.Tensor, u: Optional[torch.Tensor] = None, optimize: bool = True,
-             read_metrics: bool = True):
+             read_metrics: bool = True, batch=None, prefetch_next=None):
+        """batch: alternatively the (images, labels[, u]) tuple previously handed to prefetch(); prefetch_next: the tuple of
+        the NEXT step, whose host->device copies are started on the copy stream once this step's launches are enqueued."""
+        if batch is not None:
+            staged = self._take_prefetched(batch)
+            images, labels = staged[0], staged[1]
+            u = staged[2] if len(staged) > 2 else None
         self.load_inputs(images, labels, u)
+        if batch is not None:
+            self._mark_picked()
         if optimize not in self._sched:
             sch = self._schedule(optimize)
             self._sched[optimize] = GraphRunner(sch) if self.use_graphs else sch
@@ -132,6 +173,8 @@ class PretrainTrainer(_FlatSGDTrainer):
             for f in sch:
                 f()
         self.steps += 1
+        if prefetch_next is not None:
+            self.prefetch(prefetch_next)
         return self.read_metrics() if read_metrics else None
 
     def read_metrics(self) -> Dict[str, float]:
