@@ -1093,9 +1093,9 @@ int tpgan_multitask_loss(const float* loc, const float* cls, const float* truth,
 int tpgan_ssd_decode(const float* loc, const float* cls, int32_t batch, int32_t n, int64_t loc_stride, int64_t cls_stride,
                      int32_t num_classes, int32_t top_k, float confidence_threshold, float nms_distance, int32_t* count,
                      float* score, float* point, const float* truth, float* accuracy, void* stream) {
-  if (!loc || !cls || !count || !score || !point || batch < 1 || n < 1 || n > 4096 || num_classes < 1 || num_classes > 8 ||
+  if (!loc || !cls || !count || !score || !point || batch < 1 || n < 1 || n > 4000 || num_classes < 1 || num_classes > 8 ||
       top_k < 1 || top_k > 64 || loc_stride < 2ll * n || cls_stride < (long long)num_classes * n || (accuracy && !truth))
-    return set_error(TPGAN_ERR_INVALID, "ssd_decode: bad arguments (n <= 4096, classes <= 8, top_k <= 64)");
+    return set_error(TPGAN_ERR_INVALID, "ssd_decode: bad arguments (n <= 4000, classes <= 8, top_k <= 64)");
   const size_t bytes = (size_t)batch * num_classes * top_k * sizeof(float);
   cudaError_t e = cudaMemsetAsync(score, 0, bytes, ST);
   if (e == cudaSuccess) e = cudaMemsetAsync(point, 0, 2 * bytes, ST);
