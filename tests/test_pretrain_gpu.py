@@ -551,3 +551,61 @@ def test_prefetched_batches_give_the_same_steps():
     for (ma, ga, la), (mb, gb, lb) in zip(*runs):
         assert abs(ma["loss"] - mb["loss"]) <= 1e-5 * abs(ma["loss"]), (ma, mb)
         assert torch.equal(la, lb) and rel(gb, ga) < 1e-4
+
+
+def test_kernels_do_not_write_outside_their_outputs():
+    """(compute-sanitizer is closed on this pool.)  Every output of the Pretrain-path kernels sits between two guard slabs
+    filled with a sentinel; after the launches the guards are untouched.  Odd sizes on purpose (partial strips / groups)."""
+    from tpgan_b200 import ops
+    S = 1234.5
+
+    def guarded(n, h, w, c):
+        big = torch.full((n + 2, h, w, c), S, device="cuda")
+        return big, ops.Act(big[1:-1])
+
+    def intact(big):
+        return bool((big[0] == S).all()) and bool((big[-1] == S).all())
+
+    torch.manual_seed(0)
+    for C, H, W, s in ((24, 13, 11, 1), (96, 9, 7, 2), (960, 4, 4, 1)):
+        x = ops.Act(torch.randn(3, H, W, C, device="cuda"))
+        Ho, Wo = (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
+        w = torch.randn(C, 1, 3, 3, device="cuda")
+        by, y = guarded(3, Ho, Wo, C)
+        ops.dwconv3x3(x, y, w, s)
+        bx, dx = guarded(3, H, W, C)
+        ops.dwconv3x3_dgrad(ops.Act(torch.randn(3, Ho, Wo, C, device="cuda")), dx, w, s, False)
+        dwb = torch.full((C + 2, 1, 3, 3), S, device="cuda")
+        dwb[1:-1] = 0
+        ops.dwconv3x3_wgrad(x, ops.Act(torch.randn(3, Ho, Wo, C, device="cuda")), dwb[1:-1], s)
+        assert intact(by) and intact(bx) and bool((dwb[0] == S).all()) and bool((dwb[-1] == S).all()), (C, H, W, s)
+        # BatchNorm forward / backward
+        g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        sums = torch.zeros(2 * C + 3, dtype=torch.float64, device="cuda")
+        sums[-2:] = S
+        dsums = sums.clone()
+        coef = torch.full((4 * C + 8,), S, device="cuda")
+        bo, o = guarded(3, H, W, C)
+        ops.bn_forward(x, None, o, g, b, rm, rv, 0.1, 1e-5, True, True, False, sums[:2 * C + 1], coef[:4 * C])
+        bd, d = guarded(3, H, W, C)
+        dgb = torch.full((C + 8,), S, device="cuda")
+        ops.bn_backward(ops.Act(torch.randn(3, H, W, C, device="cuda")), x, d, coef[:4 * C], True, True, False, False,
+                        dsums[:2 * C + 1], dgb[:C], dgb[:C].clone())
+        assert intact(bo) and intact(bd) and bool((coef[4 * C:] == S).all()) and bool((dgb[C:] == S).all())
+        assert bool((sums[-2:] == S).all()) and bool((dsums[-2:] == S).all())
+    # loss / decoder outputs
+    B, n = 3, 77
+    loc, cls = torch.rand(B, n, 2, device="cuda") * 128, torch.randn(B, n, 5, device="cuda")
+    true, u = torch.rand(B, 8, device="cuda") * 128, torch.rand(B, n, device="cuda")
+    dl, dc = torch.full((B + 2, n, 2), S, device="cuda"), torch.full((B + 2, n, 5), S, device="cuda")
+    lab = torch.full((B + 2, n), 7, dtype=torch.int32, device="cuda")
+    sums3 = torch.full((5,), S, device="cuda")
+    sums3[:3] = 0
+    ops.multitask_loss(loc, cls, true, u, n, 2 * n, 5 * n, 7, 128.0, 128.0, 30.0, 0.1, 5.0, 1.0 / B, dl[1:-1], dc[1:-1],
+                       lab[1:-1], sums3[:3])
+    assert intact(dl) and intact(dc) and bool((lab[0] == 7).all()) and bool((lab[-1] == 7).all()) and bool((sums3[3:] == S).all())
+    cnt = torch.full((B + 2, 5), 9, dtype=torch.int32, device="cuda")
+    sc, pt = torch.full((B + 2, 5, 3), S, device="cuda"), torch.full((B + 2, 5, 3, 2), S, device="cuda")
+    ops.ssd_decode(loc, cls, n, 2 * n, 5 * n, 5, 3, 0.3, 10.0, cnt[1:-1], sc[1:-1], pt[1:-1])
+    assert intact(sc) and intact(pt) and bool((cnt[0] == 9).all()) and bool((cnt[-1] == 9).all())
