@@ -253,7 +253,7 @@ TPGAN_API int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const
                                int32_t act, float slope, int32_t round_tf32, double* sums, float* coef, void* stream);
 /* dz = dy * [0 < y < 6] (if relu6; for act 2 the caller masks dy by the sign of y first - tpgan_act_backward or the conv
  * dgrad epilogue); training: dx (+)= scale*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum dz*xhat,
- * dbeta = sum dz (overwritten; may be NULL); eval: dx (+)= scale*dz.  dsums = scratch of 2*C + 1 doubles, zeroed once by the
+ * dbeta = sum dz (overwritten; may be NULL); eval: dx (+)= scale*dz, dgamma / dbeta as in training mode when requested.  dsums = scratch of 2*C + 1 doubles, zeroed once by the
  * caller and left zeroed by every call. */
 TPGAN_API int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* coef, int32_t training, int32_t relu6,
                                 int32_t accumulate, int32_t round_tf32, double* dsums, float* dgamma, float* dbeta,

@@ -110,8 +110,7 @@ def test_batchnorm_kernels(C, M, relu6, residual):
         ops.bn_backward(_act(dy), xa, dx, coef, training, relu6, False, False, dsums, dg, db)
         tol = 5e-5 if n * h * w > 8 else 2e-3     # tiny batches: 1/sqrt(var) amplifies round-off in both implementations
         assert rel(dx.to_nchw(), xr.grad) < tol, training
-        if training:
-            assert rel(dg, bn.weight.grad) < tol and rel(db, bn.bias.grad) < tol
+        assert rel(dg, bn.weight.grad) < tol and rel(db, bn.bias.grad) < tol       # eval mode too (frozen statistics)
         assert float(sums.abs().sum()) == 0.0 and float(dsums.abs().sum()) == 0.0     # scratch left zeroed (incl. the ticket)
 
 
@@ -515,11 +514,7 @@ def test_network_other_image_sizes(hw, batch):
         pg = dict(net.named_parameters())
         num = den = 0.0
         for k, p in port.named_parameters():
-            if p.grad is None:           # eval mode: BatchNorm affine parameters get no gradient from the eval-mode kernels
-                continue
-            if pg[k].grad is None:
-                assert "conv." in k or "conv1.1" in k or "conv2.1" in k, k
-                continue
+            assert pg[k].grad is not None, k      # incl. the BatchNorm affine parameters (frozen statistics, trainable)
             num += float((pg[k].grad.double().cpu() - p.grad.double()).pow(2).sum())
             den += float(p.grad.double().pow(2).sum())
         assert math.sqrt(num / den) < 2e-2, math.sqrt(num / den)

@@ -582,24 +582,24 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, long long ldd,
                                                           const float* __restrict__ x, long long ldx, long long M, int C,
                                                           const float* __restrict__ coef, const double* __restrict__ dsums,
-                                                          int relu6, int training, float* __restrict__ dx, long long ldo,
-                                                          int accumulate, int round, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta) {
+                                                          int relu6, int training, int have_sums, float* __restrict__ dx,
+                                                          long long ldo, int accumulate, int round,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sm[];  // c1[C] = mean(dz), c2[C] = mean(dz*xhat)
   __shared__ int is_last;
   float* c1 = sm;
   float* c2 = sm + C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double a = training ? __ldcg(dsums + c) : 0.0, b = training ? __ldcg(dsums + C + c) : 0.0;
-    c1[c] = (float)(a / (double)M);
-    c2[c] = (float)(b / (double)M);
-    if (training && blockIdx.x == 0) {
+    const double a = have_sums ? __ldcg(dsums + c) : 0.0, b = have_sums ? __ldcg(dsums + C + c) : 0.0;
+    c1[c] = training ? (float)(a / (double)M) : 0.f;     // eval mode: statistics are constants, dx = scale * dz
+    c2[c] = training ? (float)(b / (double)M) : 0.f;
+    if (have_sums && blockIdx.x == 0) {
       if (dbeta) dbeta[c] = (float)a;
       if (dgamma) dgamma[c] = (float)b;
     }
   }
   __syncthreads();
-  if (training) {   // every block has consumed dsums once it takes a ticket: the last one leaves the scratch zeroed
+  if (have_sums) {   // every block has consumed dsums once it takes a ticket: the last one leaves the scratch zeroed
     unsigned int* ticket = reinterpret_cast<unsigned int*>(const_cast<double*>(dsums) + 2 * C);
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
@@ -1048,11 +1048,14 @@ int tpgan_bn_forward(tpgan_view x, tpgan_view res, tpgan_view y, const float* ga
 int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* coef, int32_t training, int32_t relu6,
                       int32_t accumulate, int32_t round_tf32, double* dsums, float* dgamma, float* dbeta, void* stream) {
   if (!dense(x) || !dense(dy) || !dense(dx) || x.c != dy.c || x.c != dx.c || x.n != dy.n || x.h != dy.h || x.w != dy.w ||
-      x.n != dx.n || x.h != dx.h || x.w != dx.w || !coef || (training && !dsums) || x.c * 8 > 48 * 1024)
+      x.n != dx.n || x.h != dx.h || x.w != dx.w || !coef || ((training || dgamma || dbeta) && !dsums) || x.c * 8 > 48 * 1024)
     return set_error(TPGAN_ERR_INVALID, "bn_backward: bad arguments");
   const long long M = (long long)x.n * x.h * x.w;
   const int C = x.c;
-  if (training) {
+  // the reduction feeds dx in training mode and the affine gradients in both modes (eval: BatchNorm frozen statistics with
+  // trainable gamma / beta, as nn.BatchNorm2d.eval() behaves under autograd)
+  const int have_sums = (training || dgamma || dbeta) ? 1 : 0;
+  if (have_sums) {
     const QMap m = qmap(C);
     static const int per_sm = env_int("TPGAN_BN_PER_SM", 5);
     dim3 grid((unsigned)grid_cap((M + m.rg * 8 - 1) / (m.rg * 8), per_sm), (unsigned)m.ny);
@@ -1062,7 +1065,8 @@ int tpgan_bn_backward(tpgan_view dy, tpgan_view x, tpgan_view dx, const float* c
   }
   const long long total = M * (C / 4);
   bn_bwd_apply_kernel<<<grid_cap((total + 255) / 256, 8), 256, (size_t)C * 8, ST>>>(
-      dy.ptr, dy.sw, x.ptr, x.sw, M, C, coef, dsums, relu6, training, dx.ptr, dx.sw, accumulate, round_tf32, dgamma, dbeta);
+      dy.ptr, dy.sw, x.ptr, x.sw, M, C, coef, dsums, relu6, training, have_sums, dx.ptr, dx.sw, accumulate, round_tf32, dgamma,
+      dbeta);
   TPG_CHECK_LAUNCH("bn_bwd_apply");
   return 0;
 }

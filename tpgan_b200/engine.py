@@ -790,7 +790,7 @@ class Plan:
                 return
             self._finalize(out)
             g = self.grad_act(out)
-            need_param = training and self.need_wgrad
+            need_param = self.need_wgrad       # eval mode too: frozen statistics, trainable gamma / beta
             dg, db = (bn.grad_targets(self) if need_param else (None, None))
             rdx = round_dx and not self.exact
             if res is not None:
