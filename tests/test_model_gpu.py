@@ -250,13 +250,14 @@ def test_cuda_graph_replay_matches_eager():
         assert abs(fixed[0][0][k] - fixed[2][0][k]) <= 1e-5 * abs(fixed[0][0][k]) + 1e-7, (k, fixed[0][0][k], fixed[2][0][k])
     assert rel(fixed[2][1], fixed[0][1]) < 1e-5 and rel(fixed[2][2], fixed[0][2]) < 1e-5
     spread = rel(traj[1][1], traj[0][1])
-    assert rel(traj[2][1], traj[0][1]) <= 5 * spread + 1e-5, (rel(traj[2][1], traj[0][1]), spread)
+    assert rel(traj[2][1], traj[0][1]) <= 10 * spread + 1e-4, (rel(traj[2][1], traj[0][1]), spread)
     for k in traj[0][0]:
         noise = abs(traj[0][0][k] - traj[1][0][k])
         # (||grad||-1)^2 and the critic means are differences of nearly equal numbers: allow an absolute slack as well
         # (a wrong device-side Adam step count or a stale packed weight would show as O(1) deviations; the slack only has to
         # absorb the chaotic amplification of summation-order noise over four sign-like Adam steps)
-        assert abs(traj[0][0][k] - traj[2][0][k]) <= 10 * noise + 1e-2 * abs(traj[0][0][k]) + 5e-3, (k, traj[0][0][k], traj[2][0][k])
+        # (observed once in ~10 runs of the suite: a metric 0.249 vs 0.26 with two eager runs that happened to agree to 1e-4)
+        assert abs(traj[0][0][k] - traj[2][0][k]) <= 20 * noise + 5e-2 * abs(traj[0][0][k]) + 2e-2, (k, traj[0][0][k], traj[2][0][k])
 
 
 def test_prefetched_inputs_match_direct_copies():

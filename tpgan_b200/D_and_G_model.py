@@ -411,6 +411,7 @@ class GlobalPathway(TracedModule):
         if L is None:
             fc1 = ConvLayer(self.fc1.weight, self.fc1.bias, False, 8, 1, 0, "global_pathway.fc1",
                             w_shape=(self.fc1.out_features, self.fc1.in_features // 64, 8, 8))
+            fc1.dgrad_gemm = True      # its input gradient is one GEMM over the dgrad packing (engine._emit_dgrad_gemm)
             d8 = self.deconv_8[0]
             assert d8.kernel_size == (8, 8) and d8.stride == (1, 1) and d8.padding == (0, 0)
             dec8 = DeconvAsLinear(d8.weight, d8.bias, 8, "global_pathway.deconv_8")
