@@ -315,6 +315,13 @@ TPGAN_API int64_t tpgan_launch_count(void);
 /* Which tensor-core kernel the calling thread's most recent tpgan_conv2d launched (profiling / bench attribution):
  * 0 = tapgemm_kernel, 1 = rowconv_kernel, 2 = rowstack_kernel. */
 TPGAN_API int tpgan_last_conv_kernel(void);
+/* Deterministic mode (process-wide; returns the previous setting).  By default the split reductions of
+ * tpgan_conv2d_wgrad and the multi-block bias sums combine partial results with fp32 atomics, so two runs of the same step
+ * agree only to summation order (torch.use_deterministic_algorithms is the reference-side analogue).  With on != 0 every
+ * weight-gradient CTA owns whole output tiles and tpgan_bias_grad uses one block per channel group: results are
+ * bit-identical from run to run (and between eager launches and CUDA-graph replays), at reduced speed. */
+TPGAN_API int tpgan_set_deterministic(int32_t on);
+TPGAN_API int tpgan_get_deterministic(void);
 
 #ifdef __cplusplus
 }

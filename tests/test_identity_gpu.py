@@ -203,7 +203,7 @@ def test_resnet_training_mode_vs_oracle(exact, use_bn):
         want_l, want_f, _ = ip.resnet18_128({k: v.detach() for k, v in sd.items()}, x, training=False)
         assert rel(le, want_l) < (1e-3 if exact else 1e-2) and rel(fe, want_f) < (1e-3 if exact else 1e-2)
     finally:
-        M.EXACT_MODE = False
+        M.EXACT_MODE = None
 
 
 def test_classifier_trainer_step_vs_oracle():

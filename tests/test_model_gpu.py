@@ -80,7 +80,7 @@ def test_forward_vs_golden_reference(exact, tol):
         assert rel(dl, gold["d_forward_b1"]) < tol
         assert torch.equal(outs[7].cpu(), gold["fuser_b1"]) or rel(outs[7], gold["fuser_b1"]) < 3e-4  # tf32-rounded inputs
     finally:
-        M.EXACT_MODE = False
+        M.EXACT_MODE = None
 
 
 @pytest.mark.parametrize("exact,tol_all,tol_each", [(True, 5e-4, 5e-3), (False, 3e-3, 1e-2)])
@@ -119,14 +119,50 @@ def test_generator_discriminator_gradients(exact, tol_all, tol_each):
             assert rel(p.grad, pd[k].grad) < tol_each, (k, rel(p.grad, pd[k].grad))
     finally:
         mp.MASK_HOOK = None
-        M.EXACT_MODE = False
+        M.EXACT_MODE = None
+
+
+def _oracle_step_grads(b, sg, sd, tr=None):
+    """Loss scalars and all gradients of the oracle step (fixed weights).  With `tr`, the oracle's activation backward is
+    evaluated on the CUDA path's stored sign pattern (MASK_HOOK); without, it is the plain fp32 oracle."""
+    from oracle import model_port as mp, step as ostep
+    B = b["img"].shape[0]
+    counter = {"i": -1}
+    ranges = [(2 * B, 3 * B), (0, B), (B, 2 * B), (0, B)]  # oracle call order: xhat, fake, real, (G phase) fake
+    try:
+        if tr is not None:
+            mp.MASK_HOOK = _mask_hook(tr.plan, tr.critic, ranges, counter)
+        pg = {k: v.clone().requires_grad_(True) for k, v in sg.items()}
+        pd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        Gc, Dc0 = ostep.port_callables(pg, pd)
+
+        def Dc(x):
+            counter["i"] += 1
+            return Dc0(x)
+        g_out = Gc(b)
+        ld, md = ostep.d_loss(Dc, g_out[0].detach(), b)
+        gd = torch.autograd.grad(ld, list(pd.values()))
+        lg, mg = ostep.g_loss(g_out, Dc(g_out[0]), b)
+        gg = torch.autograd.grad(lg, list(pg.values()))
+    finally:
+        mp.MASK_HOOK = None
+    return {k: float(v) for k, v in {**md, **mg}.items()}, gg, gd
+
+
+def _grad_errors(net, grads):
+    a = torch.cat([p.grad.flatten().cpu() for _, p in net.named_parameters()])
+    r = torch.cat([g.flatten() for g in grads])
+    each = {k: rel(p.grad, g) for (k, p), g in zip(net.named_parameters(), grads)}
+    return rel(a, r), each
 
 
 @pytest.mark.parametrize("exact", [True, False])
 def test_training_step_vs_oracle_step(exact):
     """Losses, crop boxes and every gradient of the fused step (incl. the gradient penalty's double backward) against
-    oracle/step.py, and the metrics against the golden record from the live reference modules."""
-    from oracle import model_port as mp, step as ostep
+    oracle/step.py, and the metrics against the golden record from the live reference modules.  Gradients are compared
+    twice: under the CUDA path's activation masks (sharp: the arithmetic format is the only difference) AND against the
+    plain oracle (un-masked; bounded by the sign flips that the forward deviation causes, see the module docstring)."""
+    from oracle import step as ostep
     from tpgan_b200 import _lib
     from tpgan_b200.train_step import TPGANTrainer
     gold = torch.load(GOLD, weights_only=False)
@@ -141,35 +177,47 @@ def test_training_step_vs_oracle_step(exact):
     tol_m = 3e-4 if exact else 1e-2
     for k, v in gold["step_b2_metrics"].items():
         assert abs(m[k] - v) <= tol_m * abs(v) + 1e-5, (k, m[k], v)
-    counter = {"i": -1}
-    ranges = [(2 * B, 3 * B), (0, B), (B, 2 * B), (0, B)]  # oracle call order: xhat, fake, real, (G phase) fake
-    try:
-        mp.MASK_HOOK = _mask_hook(tr.plan, tr.critic, ranges, counter)
-        pg = {k: v.clone().requires_grad_(True) for k, v in sg.items()}
-        pd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-        Gc, Dc0 = ostep.port_callables(pg, pd)
-
-        def Dc(x):
-            counter["i"] += 1
-            return Dc0(x)
-        g_out = Gc(b)
-        ld, _ = ostep.d_loss(Dc, g_out[0].detach(), b)
-        gd = torch.autograd.grad(ld, list(pd.values()))
-        lg, _ = ostep.g_loss(g_out, Dc(g_out[0]), b)
-        gg = torch.autograd.grad(lg, list(pg.values()))
-    finally:
-        mp.MASK_HOOK = None
+    _, gg, gd = _oracle_step_grads(b, sg, sd, tr)
     tol_all, tol_each = (5e-4, 1e-2) if exact else (3e-3, 3e-2)
-    a = torch.cat([p.grad.flatten().cpu() for _, p in G.named_parameters()])
-    r = torch.cat([g.flatten() for g in gg])
-    assert rel(a, r) < tol_all, rel(a, r)
-    for (k, p), g in zip(G.named_parameters(), gg):
-        assert rel(p.grad, g) < tol_each, (k, rel(p.grad, g))
-    a = torch.cat([p.grad.flatten().cpu() for _, p in D.named_parameters()])
-    r = torch.cat([g.flatten() for g in gd])
-    assert rel(a, r) < tol_all, rel(a, r)
-    for (k, p), g in zip(D.named_parameters(), gd):
-        assert rel(p.grad, g) < tol_each, (k, rel(p.grad, g))
+    for net, grads in ((G, gg), (D, gd)):
+        overall, each = _grad_errors(net, grads)
+        assert overall < tol_all, overall
+        assert max(each.values()) < tol_each, max(each.items(), key=lambda kv: kv[1])
+    # un-masked: measured 3e-2 (tf32) / 1e-2 (exact mode: even a 1e-5 forward deviation flips some LeakyReLU signs)
+    _, gg, gd = _oracle_step_grads(b, sg, sd, None)
+    for net, grads, bound in ((G, gg, 3e-2 if exact else 8e-2), (D, gd, 3e-2 if exact else 8e-2)):
+        overall, _ = _grad_errors(net, grads)
+        assert overall < bound, ("un-masked", overall)
+
+
+def test_training_step_batch32_vs_oracle():
+    """BASELINE config[1] itself: the full G+D step at batch 32 in the production tf32 mode against the fp32 oracle step
+    run on the host (same seeded weights and synthetic batch): all eleven loss scalars, crop boxes bit-exact, every
+    gradient under identical activation masks, and the un-masked gradient bound."""
+    from oracle import step as ostep
+    from tpgan_b200 import _lib
+    from tpgan_b200.train_step import TPGANTrainer
+    B = 32
+    G, D, sg, sd = _models(False)
+    b = ostep.make_batch(B)
+    tr = TPGANTrainer(G, D, B)
+    m = tr.step({k: v.cuda() for k, v in b.items()}, optimize=False)
+    torch.cuda.synchronize()
+    assert _lib.kernel_status() == 0
+    assert (tr.boxes.cpu().numpy() == ostep.crop_boxes(b["landmarks"].numpy())).all()
+    ref, gg, gd = _oracle_step_grads(b, sg, sd, tr)
+    for k, v in ref.items():
+        assert abs(m[k] - v) <= 1e-2 * abs(v) + 1e-4, (k, m[k], v)
+    for net, grads in ((G, gg), (D, gd)):
+        overall, each = _grad_errors(net, grads)
+        assert overall < 3e-3, overall
+        assert max(each.values()) < 3e-2, max(each.items(), key=lambda kv: kv[1])
+    ref_u, gg, gd = _oracle_step_grads(b, sg, sd, None)
+    for k, v in ref_u.items():
+        assert abs(m[k] - v) <= 1e-2 * abs(v) + 1e-4, (k, m[k], v)
+    for net, grads in ((G, gg), (D, gd)):
+        overall, _ = _grad_errors(net, grads)
+        assert overall < 8e-2, ("un-masked", overall)
 
 
 def test_optimizer_step_and_repack():
@@ -229,35 +277,42 @@ def test_full_size_batch32_properties():
 
 
 def test_cuda_graph_replay_matches_eager():
-    """The step captured into CUDA graphs (eager warm-up, capture, replays) reproduces the eagerly launched step: same
-    losses and gradients for a fixed-weights step, and an optimizer trajectory that stays within the run-to-run spread of
-    two eager runs (fp32 atomic-add order in wgrad/bias sums makes any two runs differ slightly; Adam's first updates are
-    sign-like and amplify that)."""
+    """The step captured into CUDA graphs (eager warm-up, capture, replays) IS the eagerly launched step.  In deterministic
+    mode (tpgan_set_deterministic: whole-tile weight-gradient CTAs, single-block bias sums - no racing fp32 atomics) every
+    gradient of a fixed-weights step and the parameters after four optimizer steps are BIT-IDENTICAL between eager launches
+    and graph replays; a wrong device-side Adam step count, a stale packed weight or a launch missing from a captured
+    segment cannot hide.  In the default (atomic split-K) mode the fixed-weights step agrees to summation order (1e-5)."""
     from oracle import step as ostep
+    from tpgan_b200 import _lib
     from tpgan_b200.train_step import TPGANTrainer
     B = 2
     b = {k: v.cuda() for k, v in ostep.make_batch(B).items()}
-    fixed, traj = [], []
-    for graphs in (False, False, True):
+
+    def run(graphs):
         G, D, _, _ = _models(False)
         tr = TPGANTrainer(G, D, B, use_graphs=graphs)
         ms = [tr.step(b, optimize=False) for _ in range(4)]      # warm-up, capture, two replays
-        fixed.append((ms[-1], tr.flat_g.grad.clone(), tr.flat_d.grad.clone()))
+        fixed = (ms[-1], tr.flat_g.grad.clone(), tr.flat_d.grad.clone())
         mt = [tr.step(b, optimize=True) for _ in range(4)]
         torch.cuda.synchronize()
-        traj.append((mt[-1], tr.flat_g.data.clone()))
-    for k in fixed[0][0]:
-        assert abs(fixed[0][0][k] - fixed[2][0][k]) <= 1e-5 * abs(fixed[0][0][k]) + 1e-7, (k, fixed[0][0][k], fixed[2][0][k])
-    assert rel(fixed[2][1], fixed[0][1]) < 1e-5 and rel(fixed[2][2], fixed[0][2]) < 1e-5
-    spread = rel(traj[1][1], traj[0][1])
-    assert rel(traj[2][1], traj[0][1]) <= 10 * spread + 1e-4, (rel(traj[2][1], traj[0][1]), spread)
-    for k in traj[0][0]:
-        noise = abs(traj[0][0][k] - traj[1][0][k])
-        # (||grad||-1)^2 and the critic means are differences of nearly equal numbers: allow an absolute slack as well
-        # (a wrong device-side Adam step count or a stale packed weight would show as O(1) deviations; the slack only has to
-        # absorb the chaotic amplification of summation-order noise over four sign-like Adam steps)
-        # (observed once in ~10 runs of the suite: a metric 0.249 vs 0.26 with two eager runs that happened to agree to 1e-4)
-        assert abs(traj[0][0][k] - traj[2][0][k]) <= 20 * noise + 5e-2 * abs(traj[0][0][k]) + 2e-2, (k, traj[0][0][k], traj[2][0][k])
+        return fixed, (mt[-1], tr.flat_g.data.clone(), tr.flat_d.data.clone())
+
+    prev = _lib.set_deterministic(True)
+    try:
+        (m_e, gg_e, gd_e), (t_e, pg_e, pd_e) = run(False)
+        (m_g, gg_g, gd_g), (t_g, pg_g, pd_g) = run(True)
+    finally:
+        _lib.set_deterministic(prev)
+    assert torch.equal(gg_e, gg_g) and torch.equal(gd_e, gd_g), (rel(gg_g, gg_e), rel(gd_g, gd_e))
+    assert torch.equal(pg_e, pg_g) and torch.equal(pd_e, pd_g), (rel(pg_g, pg_e), rel(pd_g, pd_e))
+    for k in m_e:   # the scalar loss sums are fp32 atomic adds over blocks: summation order only
+        assert abs(m_e[k] - m_g[k]) <= 1e-5 * abs(m_e[k]) + 1e-7, (k, m_e[k], m_g[k])
+        assert abs(t_e[k] - t_g[k]) <= 1e-5 * abs(t_e[k]) + 1e-7, (k, t_e[k], t_g[k])
+    # default mode: same comparison for the fixed-weights step, to summation order
+    (m_a, gg_a, gd_a), _ = run(True)
+    assert rel(gg_a, gg_e) < 1e-5 and rel(gd_a, gd_e) < 1e-5, (rel(gg_a, gg_e), rel(gd_a, gd_e))
+    for k in m_e:
+        assert abs(m_e[k] - m_a[k]) <= 1e-5 * abs(m_e[k]) + 1e-7, (k, m_e[k], m_a[k])
 
 
 def test_prefetched_inputs_match_direct_copies():

@@ -263,7 +263,7 @@ def test_network_forward_backward_vs_oracle(exact):
         overall = math.sqrt(num / den)
         assert overall < (2e-2 if exact else 0.6), (overall, worst)
     finally:
-        _set_exact(False)
+        _set_exact(None)
 
 
 def test_network_eval_mode_uses_running_statistics():
@@ -519,7 +519,7 @@ def test_network_other_image_sizes(hw, batch):
             den += float(p.grad.double().pow(2).sum())
         assert math.sqrt(num / den) < 2e-2, math.sqrt(num / den)
     finally:
-        M.EXACT_MODE = False
+        M.EXACT_MODE = None
 
 
 def test_prefetched_batches_give_the_same_steps():

@@ -31,7 +31,7 @@ from .ModificationLayer import ResidualBlock, conv, deconv, sequential, _negativ
 from .ops import Act
 from .UtilityMethods import elementwise_multiply_and_cast_to_int as EMaC2I
 
-EXACT_MODE = False  # tests only: trace new plans in the fp32-exact (3xTF32 split) verification mode of the engine
+EXACT_MODE = None   # tests only: force (True / False) the fp32-exact 3xTF32-split mode of newly traced plans; None = the module's own default
 
 PATCH_HW = ((40, 40), (40, 40), (32, 40), (32, 48))  # (h, w) of left eye, right eye, nose, mouth
 PART_NAMES = ("left_eye", "right_eye", "nose", "mouth")
@@ -206,7 +206,8 @@ class TracedModule(nn.Module):
 
     def _build(self, tensors, static, grad_enabled) -> _Traced:
         dev = tensors[0].device
-        plan = Plan(dev, training=grad_enabled, need_wgrad=grad_enabled, exact=EXACT_MODE)
+        exact = getattr(self, "_exact_default", False) if EXACT_MODE is None else bool(EXACT_MODE)
+        plan = Plan(dev, training=grad_enabled, need_wgrad=grad_enabled, exact=exact)
         plan.bn_training = bool(self.training)     # BatchNorm follows module.train() / .eval(), not the autograd mode
         ins = []
         for x in tensors:

@@ -87,6 +87,9 @@ def main(argv=None):
     torch.manual_seed(0)                       # identical replicas
     model = MobileNetV2().to(device)
     trainer = PretrainTrainer(model, a.batch, device=device, world_size=world, use_graphs=not a.no_graphs)
+    # replicas are built from the SAME seed above; the device-side draws (dropout mask, background sub-sampling keys) must
+    # differ per shard, as they do under DistributedDataParallel
+    torch.cuda.manual_seed(0x5EED + rank)
     loss_fn, decoder = MultiTaskLoss(), MultiTaskDecoder()
     history = []
     for epoch in range(a.epochs):

@@ -96,35 +96,68 @@ class ResNet18(TracedModule):
         return nn.Sequential(*layers)
 
     # ---- traced execution (eval mode, BN folded)
-    def _folded_layers(self, device):
-        """Builds (once per call - weights are frozen) the ConvLayers of the folded network."""
-        L = {}
-
-        def mk(name, seq, k, s, p, w_shape=None):
-            lin, w, b, relu = _fold(seq)
-            w4 = w if w.dim() == 4 else w.view(w.shape[0], w.shape[1], 1, 1)
-            L[name] = (ConvLayer(w4.to(device), b.to(device), False, k, s, p, name), relu)
-        mk("conv1", self.conv1, 7, 2, 3)
+    def _fold_specs(self):
+        """(name, conv()/linear() stack, kernel, stride, pad) of every folded layer, in forward order."""
+        specs = [("conv1", self.conv1, 7, 2, 3)]
         for si, sec in enumerate(self.sections):
             for bi, blk in enumerate(sec):
                 st = blk.conv_a[0].stride[0]
-                mk(f"sections.{si}.{bi}.conv_a", blk.conv_a, 3, st, 1)
-                mk(f"sections.{si}.{bi}.conv_b", blk.conv_b, 3, 1, 1)
+                specs.append((f"sections.{si}.{bi}.conv_a", blk.conv_a, 3, st, 1))
+                specs.append((f"sections.{si}.{bi}.conv_b", blk.conv_b, 3, 1, 1))
                 if len(blk.shortcut):
-                    mk(f"sections.{si}.{bi}.shortcut", blk.shortcut, 1, st, 0)
+                    specs.append((f"sections.{si}.{bi}.shortcut", blk.shortcut, 1, st, 0))
         if hasattr(self, "FC0"):
-            mk("FC0", self.FC0, 1, 1, 0)
-        mk("FC", self.FC, 1, 1, 0)
+            specs.append(("FC0", self.FC0, 1, 1, 0))
+        specs.append(("FC", self.FC, 1, 1, 0))
+        return specs
+
+    def _fold_fingerprint(self):
+        """Changes whenever a parameter / running statistic is written through torch (optimizer.step, load_state_dict,
+        train-mode forward) or a fused trainer reports raw-pointer writes (invalidate_folded())."""
+        ts = list(self.parameters()) + list(self.buffers())
+        return (self.__dict__.get("_fold_epoch", 0),) + tuple((t._version, t.data_ptr()) for t in ts)
+
+    def invalidate_folded(self):
+        """The fused trainers (ClassifierTrainer) update parameters and running statistics through raw device pointers,
+        which torch's version counters do not see: they call this after every step."""
+        self.__dict__["_fold_epoch"] = self.__dict__.get("_fold_epoch", 0) + 1
+
+    def _folded_layers(self, device):
+        """The BatchNorm-folded ConvLayers of the eval-mode network.  Built once; when the weights or running statistics
+        changed since (train -> eval cycles, load_state_dict) they are re-folded IN PLACE, so plans that hold the packed
+        operand pointers (IdentityPlan) see the new weights."""
+        fp = self._fold_fingerprint()
+        L = self.__dict__.get("_traced_layers")
+        if L is not None and self.__dict__.get("_fold_fp") == fp:
+            return L
+        fresh = L is None
+        if fresh:
+            L = {}
+        for name, seq, k, s, p in self._fold_specs():
+            lin, w, b, relu = _fold(seq)
+            w4 = w if w.dim() == 4 else w.view(w.shape[0], w.shape[1], 1, 1)
+            if fresh:
+                L[name] = (ConvLayer(w4.to(device), b.to(device), False, k, s, p, name), relu)
+            else:
+                layer = L[name][0]
+                layer.weight.copy_(w4)
+                layer.bias.copy_(b)
+                layer.repack()
+        self.__dict__["_traced_layers"] = L
+        self.__dict__["_fold_fp"] = fp
         return L
+
+    def refresh_folded(self):
+        """Re-fold if stale (cheap fingerprint check); trainers that hold an IdentityPlan call this before a step."""
+        if self.__dict__.get("_traced_layers") is not None:
+            dev = next(self.parameters()).device
+            self._folded_layers(dev)
 
     def trace(self, plan: Plan, x: T, with_logits: bool = True):
         """x: (N,128,128,3) NHWC -> (pooled 512 feature T, FC0 feature T or None, logits T or None)."""
         assert not self.training, "the traced identity network is eval-only (BatchNorm folded with running statistics)"
         # one set of folded tensor-core layers per module: several plans (fake / gt batches) share the packed weights
-        L = getattr(self, "_traced_layers", None)
-        if L is None:
-            L = self._folded_layers(x.act.buf.device)
-            self._traced_layers = L
+        L = self._folded_layers(x.act.buf.device)
 
         def cv(name, t, residual=None, relu=None):
             layer, r = L[name]
@@ -210,15 +243,24 @@ class ResNet18(TracedModule):
         if self.training:
             if use_dropout and self.dropout.p > 0:
                 raise NotImplementedError("dropout > 0 between FC0 and FC is not built (ResNet.py:52 default 0.0)")
-            self._traced_layers = None      # the folded eval-mode copies are stale once the weights train
+            self.invalidate_folded()        # the folded eval-mode copies are stale once the weights train
             outs = self._traced_call([x], static=("train",))
             return (outs[0], outs[1]) if len(outs) > 1 else (outs[0], None)
         if use_dropout and self.dropout.p > 0:
             raise NotImplementedError("dropout is a training-time option")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("ResNet18.eval()(x) returns plain tensors (no autograd graph): the identity loss and its "
+                               "input gradient run through TPGANTrainer(identity_net=...) / IdentityPlan; call under "
+                               "torch.no_grad() or detach the input")
         n = x.shape[0]
-        plan = Plan(x.device, training=False, need_wgrad=False)
-        t = plan.new(n, x.shape[2], x.shape[3], 3, name="in", requires_grad=False)
-        pooled, fc0, logits = self.trace(plan, t)
+        key = (n, x.shape[2], x.shape[3], str(x.device))
+        cache = self.__dict__.setdefault("_eval_plans", {})
+        if key not in cache:     # one plan per input shape: activations are allocated once, not per call
+            plan = Plan(x.device, training=False, need_wgrad=False)
+            t = plan.new(n, x.shape[2], x.shape[3], 3, name="in", requires_grad=False)
+            cache[key] = (plan, t) + tuple(self.trace(plan, t))
+        plan, t, pooled, fc0, logits = cache[key]
+        self.refresh_folded()
         t.act.from_nchw(x.detach().float(), round_tf32=True)
         plan.run_forward()
         out = logits.act.to_nchw().reshape(n, -1)

@@ -115,6 +115,8 @@ SYMBOLS = {
     "tpgan_kernel_status": (C.c_int, []),
     "tpgan_launch_count": (C.c_int64, []),
     "tpgan_last_conv_kernel": (C.c_int, []),
+    "tpgan_set_deterministic": (C.c_int, [_I32]),
+    "tpgan_get_deterministic": (C.c_int, []),
 }
 
 
@@ -149,6 +151,16 @@ def launch_count() -> int:
 def last_conv_kernel() -> str:
     """Which kernel the most recent conv2d call of this thread launched."""
     return ("tapgemm", "rowconv", "rowstack")[int(load().tpgan_last_conv_kernel())]
+
+
+def set_deterministic(on: bool) -> bool:
+    """Process-wide deterministic mode (see include/tpgan_b200.h); returns the previous setting.  Plans / job tables built
+    while it is on keep their deterministic geometry."""
+    return bool(load().tpgan_set_deterministic(int(bool(on))))
+
+
+def deterministic() -> bool:
+    return bool(load().tpgan_get_deterministic())
 
 
 def kernel_status() -> int:

@@ -51,6 +51,10 @@ struct DeviceState {
 };
 static DeviceState g_dev;
 static std::mutex g_mu;
+// Deterministic mode (tpgan_set_deterministic): split-K weight-gradient reductions and multi-block bias sums combine their
+// partial results with fp32 atomics, whose order varies from run to run.  With the flag set, a weight-gradient CTA owns
+// whole output tiles and a bias sum is one block per channel group: bit-identical results run to run, at a lower speed.
+std::atomic<int> g_deterministic{0};
 
 static int ensure_device() {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -81,6 +85,7 @@ static int ensure_device() {
 }
 
 int device_sm_count() { return g_dev.sm_count; }
+int* device_status_word() { return ensure_device() == 0 ? g_dev.status_dev : nullptr; }
 
 // ------------------------------------------------------------------------------------------------ TMA descriptors
 // 4D NHWC plane: dims {C, W, H, N}; step = parity-plane subsampling factor along H and W.
@@ -687,6 +692,7 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
       const double bytes = (double)G.Hp * G.Wp * G.Nimg * 4.0 * (ceil_div(G.m_valid, 4) * 4 + ceil_div(G.n_valid, 4) * 4);
       int nkb = (int)std::ceil(bytes / ((G.slab ? mb_slab : mb_plain) * 1048576.0));
       nkb = std::max(1, std::min(nkb, G.chunks));
+      if (g_deterministic.load(std::memory_order_relaxed)) nkb = 1;
       G.kb_chunks = ceil_div(G.chunks, nkb);
       G.nkb = ceil_div(G.chunks, G.kb_chunks);
     }
@@ -695,6 +701,7 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
   }
   if (work <= 0 || work > 0x7fffffffll) return set_error(TPGAN_ERR_INVALID, "wgrad: work list of %lld chunks unsupported", work);
   P.total_work = (int)work;
+  P.whole_tiles = g_deterministic.load(std::memory_order_relaxed) ? 1 : 0;
   P.nbuf = 2;
   for (int i = 0; i < P.ngroups; ++i) P.nbuf = std::min(P.nbuf, P.g[i].nbuf);
   P.a_stage_bytes = amax;
@@ -821,6 +828,11 @@ int tpgan_kernel_status(void) {
   return v;
 }
 int64_t tpgan_launch_count(void) { return (int64_t)g_launches.load(); }
+int tpgan_set_deterministic(int32_t on) {
+  const int prev = g_deterministic.exchange(on ? 1 : 0);
+  return prev;
+}
+int tpgan_get_deterministic(void) { return g_deterministic.load(); }
 int tpgan_last_conv_kernel(void) { return g_last_conv_kernel; }
 
 }  // extern "C"

@@ -8,6 +8,8 @@ namespace tpg {
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 int device_sm_count();
+extern std::atomic<int> g_deterministic;   // tpgan_set_deterministic
+int* device_status_word();   // device alias of the host-visible status word (tpgan_kernel_status), nullptr if unavailable
 
 #define TPG_CHECK_LAUNCH(name)                                                                        \
   do {                                                                                                \

@@ -158,6 +158,7 @@ struct WgradParams {
   int ring_bytes;                // stages * (a + b) + slack read (never written) by M = 128 MMAs over narrow P tensors
   int need_zero;                 // some group's pixel box leaves K rows unwritten: zero the ring first
   int nbuf;
+  int whole_tiles;               // deterministic mode: a CTA owns whole output tiles (no split reduction, no float atomics race)
   WgradGroup g[kMaxGroups];
 };
 struct WgradParams1 {
@@ -168,6 +169,7 @@ struct WgradParams1 {
   int ring_bytes;
   int need_zero;
   int nbuf;
+  int whole_tiles;
   WgradGroup g[1];
 };
 

@@ -809,7 +809,7 @@ __global__ void fill_kernel(V o, float v) {
 // dlogits = coeff * (softmax - onehot).  One warp per row.
 __global__ void softmax_ce_kernel(const float* __restrict__ x, long long row_stride, const long long* __restrict__ label,
                                   float* __restrict__ dx, long long drow_stride, int rows, int cols, float coeff,
-                                  float* __restrict__ loss_sum) {
+                                  float* __restrict__ loss_sum, int* __restrict__ status) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -820,7 +820,11 @@ __global__ void softmax_ce_kernel(const float* __restrict__ x, long long row_str
   float s = 0.f;
   for (int j = lane; j < cols; j += 32) s += expf(xr[j] - m);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const int lab = (int)label[row];
+  // a label outside [0, cols) would be an out-of-bounds read: clamp it and raise the host-visible status word
+  // (tpgan_kernel_status() != 0 -> the Python wrappers raise), code 0x7E
+  const long long lab64 = label[row];
+  const int lab = lab64 < 0 ? 0 : (lab64 >= cols ? cols - 1 : (int)lab64);
+  if (lab64 != lab && lane == 0 && status) atomicCAS(status, 0, 0x7E | (row << 8));
   const float lse = m + logf(s);
   if (lane == 0 && loss_sum) atomicAdd(loss_sum, lse - xr[lab]);
   if (dx) {
@@ -1195,11 +1199,13 @@ int tpgan_bias_grad(tpgan_view dy, float* db, int32_t accumulate, void* stream) 
   if (dense) {
     // channels beyond dy.c inside the last float4 are padding lanes of the same buffer (always readable)
     dim3 grid((unsigned)std::max(1ll, std::min((npix + 31) / 32, 8ll * 148)), (unsigned)((dy.c + 127) / 128));
+    if (tpg::g_deterministic.load(std::memory_order_relaxed)) grid.x = 1;   // one block per channel group: no atomics race
     bias_grad_dense_kernel<<<grid, 256, 0, ST>>>(dy.ptr, npix, dy.sw, dy.c, db);
     TPG_CHECK_LAUNCH("bias_grad");
     return 0;
   }
   dim3 grid((unsigned)std::max(1ll, std::min((npix + 63) / 64, 4ll * 148)), (unsigned)((dy.c + 31) / 32));
+  if (tpg::g_deterministic.load(std::memory_order_relaxed)) grid.x = 1;
   bias_grad_kernel<<<grid, 256, 0, ST>>>(dv(dy), db);
   TPG_CHECK_LAUNCH("bias_grad");
   return 0;
@@ -1374,7 +1380,8 @@ int tpgan_softmax_ce(const float* logits, int64_t row_stride, const int64_t* lab
   if (rows < 1 || cols < 1) return set_error(TPGAN_ERR_INVALID, "softmax_ce: empty");
   const int wpb = 4;
   softmax_ce_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, ST>>>(logits, row_stride, (const long long*)labels, dlogits,
-                                                                 drow_stride, rows, cols, coeff, loss_sum);
+                                                                 drow_stride, rows, cols, coeff, loss_sum,
+                                                                 tpg::device_status_word());
   TPG_CHECK_LAUNCH("softmax_ce");
   return 0;
 }

@@ -50,8 +50,13 @@ struct SegmentWalk {
       base = kb * G.kb_chunks;
       len = min(G.kb_chunks, G.chunks - base);
       const long long S = (long long)G.tiles * len;
-      pos = (int)((S * blockIdx.x) / gridDim.x);
-      end = (int)((S * (blockIdx.x + 1)) / gridDim.x);
+      if (P.whole_tiles) {   // deterministic mode: contiguous runs of WHOLE tiles, every dW element has one writer
+        pos = (int)(((long long)G.tiles * blockIdx.x) / gridDim.x) * len;
+        end = (int)(((long long)G.tiles * (blockIdx.x + 1)) / gridDim.x) * len;
+      } else {
+        pos = (int)((S * blockIdx.x) / gridDim.x);
+        end = (int)((S * (blockIdx.x + 1)) / gridDim.x);
+      }
     }
     const WgradGroup& G = P.g[gi];
     int tile = pos / len;

@@ -111,8 +111,10 @@ class ConvLayer:
         self.ready = False
 
     def setup(self, in_cmap: Optional[List[int]], out_cmap: Optional[List[int]], in_c: int, out_c: int, device,
-              need_dgrad: bool = True, exact: bool = False):
-        """Allocate packings for the internal channel layouts seen at trace time (idempotent; layouts must not change)."""
+              need_dgrad: bool = True, exact: bool = False, defer_pack: bool = False):
+        """Allocate packings for the internal channel layouts seen at trace time (idempotent; layouts must not change).
+        defer_pack: the caller re-packs all its layers with one multi-tensor launch (LayerSet.repack) right after tracing,
+        so the per-layer pack / transpose launches here would be redundant."""
         key = (tuple(in_cmap) if in_cmap else None, tuple(out_cmap) if out_cmap else None, in_c, out_c)
         if self.ready:
             assert key == self._key, f"{self.name}: channel layout changed between traces"
@@ -130,7 +132,7 @@ class ConvLayer:
         if exact:
             self._alloc_lo()
         nb = round_up(self.bias_len(), 4)
-        self._bias_buf = torch.zeros(2 * nb, dtype=torch.float32, device=device) if self.bias is not None else None
+        self._bias_buf = ops.zeros(2 * nb, torch.float32, device) if self.bias is not None else None
         self.bias_int = self._bias_buf[:nb] if self.bias is not None else None
         self.db_int = GradArena.get(device).alloc((nb,)) if self.bias is not None else None
         if out_cmap is not None:
@@ -138,7 +140,8 @@ class ConvLayer:
             self._b_valid = (oc >= 0).nonzero().flatten()
             self._b_ref = oc[self._b_valid]
         self.ready = True
-        self.repack()
+        if not defer_pack:
+            self.repack()
 
     def bias_len(self):
         return self.out_c
@@ -153,7 +156,7 @@ class ConvLayer:
 
     def _alloc_lo(self):
         """Residual packings w - tf32(w) for the fp32-exact verification mode (Plan(exact=True))."""
-        cp = lambda pk: None if pk is None else ops.Packed(torch.zeros_like(pk.data), pk.taps, pk.rows, pk.k, pk.rows_pad,
+        cp = lambda pk: None if pk is None else ops.Packed(ops.zeros(pk.data.shape, torch.float32, pk.data.device), pk.taps, pk.rows, pk.k, pk.rows_pad,
                                                           pk.k_pad)
         self.wf_lo, self.wd_lo = cp(self.wf), cp(self.wd)
 
@@ -201,7 +204,7 @@ class ConvLayer:
         return self.wd, self.wf, self.in_map, self.out_map, self.w_shape[1] * taps
 
     def multi_ok(self) -> bool:
-        if type(self) is not ConvLayer or not self.ready or self.wf_lo is not None:
+        if type(self) is not ConvLayer or not self.ready:
             return False
         if self.transposed and self.wd is None:
             return False
@@ -216,6 +219,11 @@ class ConvLayer:
             bp = ops.Packed(self._bias_buf, 1, 1, self.out_c, 1, nb)
             packs.append(ops.pack_job(self.bias.data, bp, 1, self.bias.numel(), None, self.out_map, 0))
         trans = [ops.transpose_job(tgt, other)] if other is not None else []
+        if self.wf_lo is not None:   # fp32-exact mode: the residual packings w - tf32(w), same geometry (flag 2)
+            tgt_lo, other_lo = (self.wf_lo, self.wd_lo) if not self.transposed else (self.wd_lo, self.wf_lo)
+            packs.append(ops.pack_job(self.weight.data, tgt_lo, self.k * self.k, row_len, rmap, kmap, 2))
+            if other_lo is not None:
+                trans.append(ops.transpose_job(tgt_lo, other_lo))
         return packs, trans
 
     def unpack_jobs(self, accumulate: bool = False):
@@ -225,7 +233,7 @@ class ConvLayer:
         src = self.dw
         if self.transposed:
             if getattr(self, "_dw_t", None) is None:
-                self._dw_t = ops.Packed(torch.zeros_like(self.wd.data), self.wd.taps, self.wd.rows, self.wd.k,
+                self._dw_t = ops.Packed(ops.zeros(self.wd.data.shape, torch.float32, self.wd.data.device), self.wd.taps, self.wd.rows, self.wd.k,
                                         self.wd.rows_pad, self.wd.k_pad)
             trans.append(ops.transpose_job(self.dw, self._dw_t))
             src = self._dw_t
@@ -266,7 +274,7 @@ class ConvLayer:
         if self.transposed and self.wd is not None:
             # deconv: transpose the [tap][Cout][Cin] gradient into the row-contiguous [tap][Cin][Cout] geometry first
             if getattr(self, "_dw_t", None) is None:
-                self._dw_t = ops.Packed(torch.zeros_like(self.wd.data), self.wd.taps, self.wd.rows, self.wd.k,
+                self._dw_t = ops.Packed(ops.zeros(self.wd.data.shape, torch.float32, self.wd.data.device), self.wd.taps, self.wd.rows, self.wd.k,
                                         self.wd.rows_pad, self.wd.k_pad)
             ops.transpose_packed(self.dw, self._dw_t)
             ops.unpack_weights(self._dw_t, self.weight.grad.view(self.w_shape), self.kind_dgrad, row_map=self.in_map,
@@ -308,18 +316,18 @@ class DeconvAsLinear(ConvLayer):
     def _alloc(self, device, need_dgrad):
         assert self.out_map is None and self.in_map is None and self.in_c % 32 == 0
         n, kdim = self.kk * self.co, self.in_c
-        mk = lambda: torch.zeros((2, n, kdim), dtype=torch.float32, device=device)
+        mk = lambda: ops.zeros((2, n, kdim), torch.float32, device)
         self.wf = ops.Packed(mk(), 1, n, kdim, n, kdim)
         self.dw = ops.Packed(GradArena.get(device).alloc((2, n, kdim)), 1, n, kdim, n, kdim)
         # views of the same storage in the [taps+1][Cout][Cin] geometry the (un)pack kernels use
         self._wf_taps = ops.Packed(self.wf.data, self.kk, self.co, kdim, self.co, kdim)
         self._dw_taps = ops.Packed(self.dw.data, self.kk, self.co, kdim, self.co, kdim)
-        self.wd = ops.Packed(torch.zeros((2, round_up(kdim, 16), n), dtype=torch.float32, device=device), 1, kdim, n,
+        self.wd = ops.Packed(ops.zeros((2, round_up(kdim, 16), n), torch.float32, device), 1, kdim, n,
                              round_up(kdim, 16), n)
         kk, co = self.kk, self.co
         idx = torch.arange(n, dtype=torch.int64)
         self._kmap_d = ((idx % co) * kk + idx // co).to(torch.int32).to(device)  # (tap, co) -> co*kk + tap
-        self.bias_full = torch.zeros(n, dtype=torch.float32, device=device)
+        self.bias_full = ops.zeros(n, torch.float32, device)
 
     def _alloc_lo(self):
         super()._alloc_lo()
@@ -355,8 +363,9 @@ class Plan:
     """Traced schedule for one network instance and batch size."""
 
     def __init__(self, device, training: bool = True, need_wgrad: bool = True, exact: bool = False,
-                 defer_bias: bool = False):
+                 defer_bias: bool = False, defer_pack: bool = False):
         self.device = device
+        self.defer_pack = defer_pack  # the owner re-packs every layer of this plan in one multi-tensor launch after tracing
         self.defer_bias = defer_bias  # record (layer, dY, ready index) instead of launching one bias-grad kernel per layer
         self.bias_jobs: list = []
         self.exact = exact  # fp32-exact verification mode: every tensor-core product is split hi/lo (3 launches)
@@ -390,7 +399,7 @@ class Plan:
         for c in widths:
             offs.append(o)
             o += round_up(c, 4)
-        buf = torch.zeros((n, h, w, o), dtype=torch.float32, device=self.device)
+        buf = ops.zeros((n, h, w, o), torch.float32, self.device)
         self.bytes += buf.numel() * 4
         padded = any(c % 4 for c in widths[:-1])
         total_c = o if padded else offs[-1] + widths[-1]
@@ -412,7 +421,7 @@ class Plan:
             buf = t.act.buf
             g = self.grad_bufs.get(id(buf))
             if g is None:
-                g = torch.zeros_like(buf)
+                g = ops.zeros(buf.shape, torch.float32, buf.device)
                 self.grad_bufs[id(buf)] = g
                 self.bytes += g.numel() * 4
             t.grad = Act(g, t.act.c0, t.act.c)
@@ -453,7 +462,7 @@ class Plan:
                 out_cmap = r.cmap
                 out.cmap, out.ref_c = r.cmap, r.ref_c
             out.slope = LINEAR if slope is None else slope
-            L.setup(x.cmap, out_cmap, x.act.c, out.act.c, self.device, exact=self.exact)
+            L.setup(x.cmap, out_cmap, x.act.c, out.act.c, self.device, exact=self.exact, defer_pack=self.defer_pack)
             if L not in self.layers:
                 self.layers.append(L)
             self.named[L.name] = out

@@ -31,6 +31,60 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+# ---------------------------------------------------------------------------------------------------------- zeroed memory
+class Arena:
+    """Bump allocator over a few large zero-initialised chunks.  A trainer allocates ~2000 buffers (activations, gradient
+    buffers, packed weights); as individual torch.zeros calls that is ~2000 fill launches before the first kernel of this
+    library runs.  Chunks are ordinary tensors and every allocation is a view of one, so lifetime is plain reference
+    counting: a chunk is freed when the last buffer carved out of it dies."""
+
+    def __init__(self, device, chunk_bytes: int = 256 << 20):
+        self.device, self.chunk_bytes = torch.device(device), chunk_bytes
+        self.chunk: Optional[torch.Tensor] = None
+        self.used = 0
+        self.total = 0
+
+    def alloc(self, shape, dtype=torch.float32) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = round_up(max(n, 1) * torch.empty((), dtype=dtype).element_size(), 256)   # keeps TMA / vector alignment
+        if self.chunk is None or self.used + nbytes > self.chunk.numel():
+            self.chunk = torch.zeros(max(self.chunk_bytes, nbytes), dtype=torch.uint8, device=self.device)
+            self.used = 0
+        o = self.used
+        self.used += nbytes
+        self.total += nbytes
+        return self.chunk[o:o + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+
+_ARENA: List[Arena] = []
+
+
+class use_arena:
+    """with use_arena(a): every ops.zeros() / Act.empty() on a's device inside is carved out of `a`."""
+
+    def __init__(self, arena: Arena):
+        self.arena = arena
+
+    def __enter__(self):
+        _ARENA.append(self.arena)
+        return self.arena
+
+    def __exit__(self, *exc):
+        _ARENA.pop()
+        return False
+
+
+def zeros(shape, dtype=torch.float32, device="cuda") -> torch.Tensor:
+    """Zero-initialised device tensor; inside a use_arena() block a view of the arena (no fill launch)."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    if _ARENA and _ARENA[-1].device == torch.device(device):
+        return _ARENA[-1].alloc(tuple(shape), dtype)
+    return torch.zeros(tuple(shape), dtype=dtype, device=device)
+
+
 class Act:
     """Channel slice [c0, c0+c) of an NHWC fp32 buffer `buf` of shape (N, H, W, Cs)."""
 
@@ -46,7 +100,8 @@ class Act:
     @staticmethod
     def empty(n: int, h: int, w: int, c: int, device="cuda", zero: bool = True) -> "Act":
         cs = round_up(c, 4)
-        buf = (torch.zeros if zero else torch.empty)((n, h, w, cs), dtype=torch.float32, device=device)
+        buf = zeros((n, h, w, cs), torch.float32, device) if (zero or _ARENA) else \
+            torch.empty((n, h, w, cs), dtype=torch.float32, device=device)
         return Act(buf, 0, c)
 
     @property
@@ -119,7 +174,7 @@ def alloc_packed(kind: int, w_shape: Sequence[int], rows_int: Optional[int] = No
     rows = rows if rows_int is None else rows_int
     k = k if k_int is None else k_int
     rows_pad, k_pad = round_up(rows, 16), round_up(k, 32)
-    data = torch.zeros((taps + 1, rows_pad, k_pad), dtype=torch.float32, device=device)
+    data = zeros((taps + 1, rows_pad, k_pad), torch.float32, device)
     return Packed(data, taps, rows, k, rows_pad, k_pad)
 
 
@@ -365,6 +420,8 @@ def bias_job(g: Act, db: torch.Tensor) -> "_lib.BiasJob":
     ppb = 8 * (32 // lanes)                      # pixels one 8-warp block takes per sweep
     # ~64 sweeps per block (8 loads of 16 B in flight per lane), at most two waves of blocks per tensor
     pix_blocks = max(1, min((npix + 64 * ppb - 1) // (64 * ppb), 296))
+    if _lib.deterministic():
+        pix_blocks = 1      # one block per channel group: a single atomic add per channel onto the cleared accumulator
     return _lib.BiasJob(v.ptr, db.data_ptr(), npix, v.sw, v.c, 0, pix_blocks, (v.c + 4 * lanes - 1) // (4 * lanes), lanes, 0)
 
 

@@ -42,7 +42,7 @@ class _FlatSGDTrainer:
         # what getOptimizer(model.parameters(), 'SGD')() would hold; save_optimizer(tr.optimizer, model, dir, epoch) works
         self.optimizer = FlatOptimizer(self.flat, model, "sgd", dict(lr=OPTIM["learning_rate"], momentum=OPTIM["momentum"],
                                                                      weight_decay=OPTIM["weight_decay"],
-                                                                     nesterov=OPTIM["nesterov"]))
+                                                                     nesterov=OPTIM["nesterov"]), lr_dev=self.lr_dev)
         self.epoch = 0
         plan = Plan(self.device, training=True, need_wgrad=True, exact=exact, defer_bias=True)
         plan.direct_grads = True
@@ -56,15 +56,17 @@ class _FlatSGDTrainer:
         self.set.repack()
         self.sums = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.inp: Optional[Dict[str, torch.Tensor]] = None
-        self._sched: Dict[bool, object] = {}
+        self._sched: Dict[tuple, object] = {}
         self.steps = 0
 
 
 class PretrainTrainer(_FlatSGDTrainer):
     """step(images (B,3,H,W) in [-1,1], labels (B,8) = 4 ground-truth points (x,y), u (B,n) optional sub-sampling keys)."""
 
-    def __init__(self, model: MobileNetV2, B: int, image_hw=(128, 128), device="cuda", exact: bool = False,
+    def __init__(self, model: MobileNetV2, B: int, image_hw=(128, 128), device="cuda", exact: bool = True,
                  world_size: int = 1, group=None, use_graphs: bool = False):
+        """exact=True (default): dense convolutions in the fp32-accurate 3xTF32 split mode - the production mode of this
+        network (see MobileNetV2's docstring: within 1e-3 of the fp32 reference); exact=False: single-pass TF32."""
         self._setup(model, B, image_hw, device, exact, world_size, group, use_graphs)
         self.n = self.loc.act.c // 2
         assert self.cls.act.c == 5 * self.n
@@ -163,16 +165,20 @@ class PretrainTrainer(_FlatSGDTrainer):
         self.load_inputs(images, labels, u)
         if batch is not None:
             self._mark_picked()
-        if optimize not in self._sched:
+        key = (optimize, bool(getattr(self, "_draw_u", False)))   # _stage branches on _draw_u; a captured graph freezes it
+        if key not in self._sched:
             sch = self._schedule(optimize)
-            self._sched[optimize] = GraphRunner(sch) if self.use_graphs else sch
-        sch = self._sched[optimize]
+            self._sched[key] = GraphRunner(sch) if self.use_graphs else sch
+        sch = self._sched[key]
         if self.use_graphs:
             sch.run()
         else:
             for f in sch:
                 f()
         self.steps += 1
+        inv = getattr(getattr(self, "net", None), "invalidate_folded", None)
+        if inv is not None:
+            inv()       # parameters / running statistics were written through raw pointers: eval-mode folded copies are stale
         if prefetch_next is not None:
             self.prefetch(prefetch_next)
         return self.read_metrics() if read_metrics else None
@@ -190,6 +196,12 @@ class PretrainTrainer(_FlatSGDTrainer):
     def end_epoch(self):
         """learning_rate_scheduler.step() (Pretrain.py:296): MultiStepLR(milestones, gamma)."""
         self.epoch += 1
+        k = sum(1 for m in LR_MILESTONES if self.epoch >= m)
+        self.lr_dev.fill_(OPTIM["learning_rate"] * (LR_GAMMA ** k))
+
+    def set_epoch(self, epoch: int):
+        """Resume: restore the MultiStepLR position (the scheduler's last_epoch) and the device-resident learning rate."""
+        self.epoch = int(epoch)
         k = sum(1 for m in LR_MILESTONES if self.epoch >= m)
         self.lr_dev.fill_(OPTIM["learning_rate"] * (LR_GAMMA ** k))
 

@@ -79,6 +79,9 @@ def main(argv=None):
     D = Discriminator(config.D["use_batchnorm"]).to(device)
     trainer = TPGANTrainer(G, D, a.batch, device=device, use_dropout=True, world_size=world, use_graphs=not a.no_graphs,
                            input_format="uint8")
+    # replicas are built from the SAME seed above; the device-side draws (dropout mask, background sub-sampling keys) must
+    # differ per shard, as they do under DistributedDataParallel
+    torch.cuda.manual_seed(0x5EED + rank)
     history = []
     for epoch in range(a.epochs):
         t0, seen, nxt = time.time(), 0, None

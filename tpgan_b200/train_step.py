@@ -60,10 +60,10 @@ class FlatParams:
             off += ops.round_up(named[n].numel(), 4)
         self.total = off
         dev = named[names[0]].device
-        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.data = ops.zeros(off, torch.float32, dev)
+        self.grad = ops.zeros(off, torch.float32, dev)
+        self.m = ops.zeros(off, torch.float32, dev)
+        self.v = ops.zeros(off, torch.float32, dev)
         self.step = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         for n in names:
@@ -87,9 +87,13 @@ class FlatOptimizer:
     {'optimizer', 'model', 'epoch'} file a torch.optim.SGD / Adam over `module.parameters()` would, and a file written
     by the reference's loop loads back with load_state_dict()."""
 
-    def __init__(self, flat: "FlatParams", module: torch.nn.Module, kind: str, hyper: Dict[str, float]):
+    def __init__(self, flat: "FlatParams", module: torch.nn.Module, kind: str, hyper: Dict[str, float],
+                 lr_dev: Optional[torch.Tensor] = None):
+        """lr_dev: the device-resident learning rate a trainer's scheduler decays (PretrainTrainer.end_epoch); when given,
+        state_dict() records the LIVE lr (and initial_lr, as torch's MultiStepLR does) and load_state_dict() restores it."""
         assert kind in ("sgd", "adam")
         self.flat, self.module, self.kind, self.hyper = flat, module, kind, dict(hyper)
+        self.lr_dev = lr_dev
 
     def _template_group(self) -> dict:
         p = [torch.nn.Parameter(torch.zeros(1))]
@@ -112,6 +116,9 @@ class FlatOptimizer:
                             "exp_avg_sq": self.flat.v[sl].view(p.shape).clone()}
         group = self._template_group()
         group["params"] = list(range(len(state)))
+        if self.lr_dev is not None:
+            group["initial_lr"] = group["lr"]
+            group["lr"] = float(self.lr_dev.item())
         return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: dict):
@@ -119,6 +126,8 @@ class FlatOptimizer:
         ids = sd["param_groups"][0]["params"]
         if len(sd["param_groups"]) != 1 or len(ids) != n:
             raise ValueError("optimizer state does not match the module's parameter list")
+        if self.lr_dev is not None and "lr" in sd["param_groups"][0]:
+            self.lr_dev.fill_(float(sd["param_groups"][0]["lr"]))
         for i, p, sl in self._slices():
             st = sd["state"].get(ids[i], sd["state"].get(str(ids[i])))
             if st is None:                       # torch omits parameters that never received a gradient
@@ -250,8 +259,9 @@ class CriticPlan:
     """Static schedule of the discriminator (reference D_and_G_model.py:409-435) for a batch of M images, with the native
     WGAN-GP machinery described in the module docstring."""
 
-    def __init__(self, D: Discriminator, M: int, B: int, device, exact: bool = False):
+    def __init__(self, D: Discriminator, M: int, B: int, device, exact: bool = False, defer_pack: bool = False):
         self.D, self.M, self.B, self.device, self.exact = D, M, B, device, exact
+        self.defer_pack = defer_pack
         self.h = Plan(device, exact=exact)  # launch emitters / keep-alive only
         new = lambda n, hw, c: Act.empty(n, hw, hw, c, device)
         self.x0 = new(M, 128, 3)
@@ -299,7 +309,7 @@ class CriticPlan:
     def _mk(self, seq, name, in_c) -> ConvLayer:
         _, cm, _, _bn = _unpack_conv_seq(seq)
         L = _layer(cm, name)
-        L.setup(None, None, in_c, L.cout, self.device, exact=self.exact)
+        L.setup(None, None, in_c, L.cout, self.device, exact=self.exact, defer_pack=self.defer_pack)
         self.layers.append(L)
         return L
 
@@ -529,8 +539,15 @@ class TPGANTrainer:
         self.lr = cfg.train["learning_rate"]
         self.world_size, self.group = world_size, group
         self.use_graphs = use_graphs
+        # every buffer of the trainer (activations, gradients, packed weights, flat parameter / optimizer state) is carved out
+        # of a few large zeroed chunks: one fill launch per 256 MB instead of one per buffer
+        self.arena = ops.Arena(self.device)
+        with ops.use_arena(self.arena):
+            self._init(G, D, B, exact, world_size, group, bucket_mb, identity_net)
+
+    def _init(self, G, D, B, exact, world_size, group, bucket_mb, identity_net):
         self._build_g()
-        self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact)
+        self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact, defer_pack=not exact)
         self.critic.build_g_phase(self.plan.grad_act(self.fake))
         order = self._ready_order()
         self.flat_g = FlatParams(G, order)
@@ -562,7 +579,7 @@ class TPGANTrainer:
     # ---- generator plan
     def _build_g(self):
         G, B, dev = self.G, self.B, self.device
-        plan = Plan(dev, exact=self.exact, defer_bias=True)
+        plan = Plan(dev, exact=self.exact, defer_bias=True, defer_pack=not self.exact)
         self.plan = plan
         gp = G.global_pathway
         bufs = gp.alloc_concats(plan, B)
@@ -728,6 +745,8 @@ class TPGANTrainer:
         stream as soon as this step's launches are enqueued (see prefetch())."""
         self.load_inputs(b)
         self.fixed_mask = self.inp_has_mask
+        if self.identity is not None:
+            self.identity.base.refresh_folded()   # re-fold the frozen network if its weights were replaced (load_state_dict)
         key = (optimize, self.fixed_mask)
         if key not in self._sched:
             sch = self._schedule(optimize)
