@@ -154,7 +154,7 @@ def run_b200(a):
         ident = FeatureExtractModel("resnet", config.G["num_classes"], residualBlock=BasicBlock,
                                     feature_layer_dim_before_FC=256).to(dev).eval()
     tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world, use_graphs=not a.no_graphs,
-                      identity_net=ident)
+                      identity_net=ident, dtype=a.dtype)
     host = ostep.make_batch(B, seed=1234 + rank)
     keys = ("img", "img_frontal", "img64_frontal", "img32_frontal", "landmarks", "z", "label", "gp_alpha")
     host = {k: host[k].contiguous().pin_memory() for k in keys}
@@ -247,11 +247,13 @@ def run_b200(a):
                     f.write(json.dumps({"ms": round(t, 4), "kind": kind, "tflops": round(fl / (t * 1e-3) / 1e12, 1),
                                         "gflop": round(fl / 1e9, 2), "label": label}) + "\n")
         peaks, which = _peaks()
-        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
-        names = {"tapgemm": "tapgemm_kernel (tcgen05 tf32 multi-tap implicit-GEMM conv fwd/dgrad/deconv/linear)",
-                 "rowconv": "rowconv_kernel (tcgen05 tf32 row-tile conv for the wide 128x128 stride-1 layers, fwd/dgrad)",
-                 "rowstack": "rowstack_kernel (tcgen05 tf32 N-stacked row-tile conv for the narrow 128x128 layers, fwd/dgrad)",
-                 "wgrad": "wgrad_kernel (tcgen05 tf32 weight-gradient GEMM over pixels)"}
+        bf16 = a.dtype == "bf16"
+        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / (1.0 if bf16 else 2.0)
+        dn = a.dtype
+        names = {"tapgemm": f"tapgemm_kernel (tcgen05 {dn} multi-tap implicit-GEMM conv fwd/dgrad/deconv/linear)",
+                 "rowconv": f"rowconv_kernel (tcgen05 {dn} row-tile conv for the wide 128x128 stride-1 layers, fwd/dgrad)",
+                 "rowstack": f"rowstack_kernel (tcgen05 {dn} N-stacked row-tile conv for the narrow 128x128 layers, fwd/dgrad)",
+                 "wgrad": f"wgrad_kernel (tcgen05 {dn} weight-gradient GEMM over pixels)"}
         step_ms = ms / a.steps
 
         def entry(kind):
@@ -262,7 +264,8 @@ def run_b200(a):
                     "algorithmic_gflop_per_step": fl / 1e9}
         dom = max(agg, key=lambda k: agg[k][1])
         roof = {"bound": "tensor", **entry(dom), "traffic": None,
-                "peak_source": f"0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json ({which}); tf32 = half the bf16 rate",
+                "peak_source": (f"bf16_tflops_sustained of MEASURED_PEAKS.json ({which})" if bf16 else
+                                f"0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json ({which}); tf32 = half the bf16 rate"),
                 "other_kernels": {k: entry(k) for k in agg if k != dom},
                 "all_conv_kernels": {"achieved": sum(v[0] for v in agg.values()) / (sum(v[1] for v in agg.values()) * 1e-3) / 1e12,
                                      "share_of_step": sum(v[1] for v in agg.values()) / step_ms}}
@@ -274,7 +277,7 @@ def run_b200(a):
         gb = B * world
         line = {"metric": METRIC, "value": gb * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
                 "config": {"workload": f"TP-GAN G+D training step (WGAN-GP critic + all G losses + Adam), batch {B}/GPU, "
                                        "128x128 synthetic faces + 4 landmark patches, dropout on" +
                                        (", + frozen ResNet18 identity-preserving loss" if a.identity else ""),
@@ -528,6 +531,8 @@ def main():
     ap.add_argument("--backbone", default="mobilenetv2", choices=["mobilenetv2", "resnet"],
                     help="pretrain workload: MobileNetV2-SSD landmark pre-training (Pretrain.py) or ResNet18 identity classifier")
     ap.add_argument("--identity", action="store_true", help="gan workload: add the frozen identity network's loss (configs[2], tf32)")
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
+                    help="gan workload: tensor-core operand type (tf32 = BASELINE configs[1]; bf16 = configs[2])")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     if a.workload == "pretrain":

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define TPGAN_ABI_VERSION 1
+#define TPGAN_ABI_VERSION 2
 #define TPGAN_API __attribute__((visibility("default")))
 
 enum tpgan_status {
@@ -44,6 +44,15 @@ enum tpgan_conv_kind {
   TPGAN_CONV_DGRAD = 1,   /* its input gradient         (aten::convolution_backward, input half) */
   TPGAN_DECONV_FWD = 2,   /* nn.ConvTranspose2d forward ModificationLayer.py:189 */
   TPGAN_DECONV_DGRAD = 3  /* its input gradient */
+};
+
+/* Operand type of the tensor-core kernels.  TF32: activations / packed weights are fp32 storage rounded to tf32
+ * (tcgen05.mma kind::tf32).  BF16: the A operand view (`in`; `x` and `dy` of a weight gradient) and the packed weights are
+ * bf16 storage - the view's ptr then addresses 2-byte elements and its strides count elements - multiplied with
+ * tcgen05.mma kind::f16, fp32 accumulation in TMEM either way.  BASELINE.json configs[2] ("bf16"). */
+enum tpgan_dtype {
+  TPGAN_DTYPE_TF32 = 0,
+  TPGAN_DTYPE_BF16 = 1
 };
 
 enum tpgan_epilogue {
@@ -71,6 +80,11 @@ typedef struct tpgan_conv_args {
   float slope;
   int32_t epilogue;
   int32_t round_tf32;     /* round the stored result to tf32 (round-to-nearest) */
+  int32_t dtype;          /* tpgan_dtype of `in` and `w_packed` ([kh*kw + 1][w_rows_pad][w_k_pad] bf16, w_k_pad % 64 == 0) */
+  tpgan_view out16;       /* BF16 only, optional (ptr NULL = unused): a bf16 copy of the result written by the same epilogue
+                             (operand storage for the tensor-core consumers of this tensor); ptr addresses 2-byte elements,
+                             8-byte aligned, strides in elements.  With out16 given, out.ptr may be NULL (no fp32 copy); out's
+                             n/h/w/c must describe the output either way.  bias / add1 / add2 / mask stay fp32. */
 } tpgan_conv_args;
 
 /* Runs 1..4 independent problems in ONE persistent launch (the four local pathways of
@@ -90,6 +104,7 @@ typedef struct tpgan_wgrad_args {
   int32_t w_rows_pad, w_k_pad;
   int32_t accumulate; /* 1: dW += (atomics); 0: the caller guarantees this is the only launch writing dW since it was
                          cleared, so tiles whose reduction is not split are written with plain vector stores */
+  int32_t dtype;      /* tpgan_dtype of x and dy (BF16: 2-byte elements, strides in elements); dw_packed is fp32 either way */
 } tpgan_wgrad_args;
 TPGAN_API int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* stream);
 
@@ -139,6 +154,18 @@ typedef struct tpgan_transpose_job { /* see tpgan_transpose_packed; blocks = tap
   float* dst;
   int32_t taps, rows, k, rows_src_pad, k_src_pad, rows_dst_pad, k_dst_pad, block_begin, tiles_k, tiles_r;
 } tpgan_transpose_job;
+typedef struct tpgan_cast_job {   /* packed fp32 [rows][k_pad] -> bf16 [rows][k_pad16]; blocks = ceil(rows * k_pad16 / 8192) */
+  const float* src;
+  uint16_t* dst;
+  int64_t rows;                   /* (taps + 1) * rows_pad */
+  int32_t k_pad, k_pad16;         /* k_pad16 % 64 == 0, >= k_pad; columns beyond k_pad are written as zero */
+  int32_t block_begin, pad_;
+} tpgan_cast_job;
+/* bf16 operand copies of the packed weights of all layers in one launch (after every optimizer step, BF16 mode). */
+TPGAN_API int tpgan_cast_packed_multi(const tpgan_cast_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream);
+/* dst16 (bf16 view of the same logical shape; ptr addresses 2-byte elements, strides in elements) = rne(src): the operand
+ * copy of an activation that was not written by a tensor-core epilogue (inputs, pooled / stitched tensors, loss gradients). */
+TPGAN_API int tpgan_cast_bf16(tpgan_view src, tpgan_view dst16, void* stream);
 TPGAN_API int tpgan_bias_grad_multi(const tpgan_bias_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream);
 TPGAN_API int tpgan_pack_multi(const tpgan_pack_job* jobs_dev, int32_t njobs, int32_t total_blocks, int32_t max_row_len,
                      int32_t unpack, void* stream);

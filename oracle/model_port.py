@@ -70,6 +70,34 @@ def _qw(w):
     return _RoundW.apply(w) if EMULATE_TF32 else w
 
 
+# ---- optional bf16 operand emulation ---------------------------------------------------------------------------------
+# The bf16 path (BASELINE configs[2]) keeps fp32 activations / gradients and hands the tensor cores bf16 COPIES of them: a
+# convolution reads bf16(x) and bf16(w), accumulates in fp32, and its backward reads bf16(dY) (dY = the masked total gradient
+# of its output) for both the input and the weight gradient; residual adds, gradient accumulation, masks, losses stay fp32.
+# With EMULATE_BF16 = True the port rounds exactly those operands, so that the bf16 path can be checked at the precision of
+# fp32 summation order instead of the format's 1e-2 (a stale or missing bf16 copy would hide inside 1e-2).  Rounding is
+# written with differentiable ops (value + detached correction) and a gradient hook, so it composes with autograd.grad(...,
+# create_graph=True); the gradient-penalty double backward is NOT claimed to be emulated exactly (the CUDA path evaluates it
+# as a tangent forward with its own rounding points).
+EMULATE_BF16 = False
+
+
+def _bf(x):
+    return x + (x.bfloat16().float() - x).detach()
+
+
+def _xin(x):
+    """A tensor-core operand (activation or weight)."""
+    return _bf(x) if EMULATE_BF16 else x
+
+
+def _gout(y):
+    """A conv / linear pre-activation output: its incoming gradient is read through a bf16 copy by dgrad and wgrad."""
+    if EMULATE_BF16 and y.requires_grad:
+        y.register_hook(_bf)
+    return y
+
+
 # ---- optional activation-mask injection ---------------------------------------------------------------------------------
 # (Leaky)ReLU makes gradients discontinuous in the forward values: an element whose pre-activation changes sign between
 # two implementations changes its gradient by ~100 %, so a forward deviation eps turns into a gradient deviation of order
@@ -110,14 +138,14 @@ def _conv(sd, key, x, stride=1, pad=0, slope=LEAKY):
         idx, p = 1, 0
     else:
         idx, p = 0, pad
-    y = F.conv2d(x, _qw(sd[f"{key}.{idx}.weight"]), sd[f"{key}.{idx}.bias"], stride=stride, padding=p)
+    y = _gout(F.conv2d(_xin(x), _xin(_qw(sd[f"{key}.{idx}.weight"])), sd[f"{key}.{idx}.bias"], stride=stride, padding=p))
     return _q(_act(y, slope, key))
 
 
 def _deconv(sd, key, x, stride, pad, out_pad):
     """deconv(): ConvTranspose2d(bias) -> ReLU (ModificationLayer.py:189-198)."""
-    return _q(_act(F.conv_transpose2d(x, _qw(sd[f"{key}.0.weight"]), sd[f"{key}.0.bias"], stride=stride, padding=pad,
-                                      output_padding=out_pad), 0.0, key))
+    return _q(_act(_gout(F.conv_transpose2d(_xin(x), _xin(_qw(sd[f"{key}.0.weight"])), sd[f"{key}.0.bias"], stride=stride,
+                                            padding=pad, output_padding=out_pad)), 0.0, key))
 
 
 def _res(sd, key, x, k=3, pad=None):
@@ -128,7 +156,7 @@ def _res(sd, key, x, k=3, pad=None):
         hp, idx, p = F.pad(h, tuple(pad), mode="reflect"), 1, 0
     else:
         hp, idx, p = h, 0, pad
-    y = F.conv2d(hp, _qw(sd[f"{key}.layers.1.{idx}.weight"]), sd[f"{key}.layers.1.{idx}.bias"], padding=p)
+    y = _gout(F.conv2d(_xin(hp), _xin(_qw(sd[f"{key}.layers.1.{idx}.weight"])), sd[f"{key}.layers.1.{idx}.bias"], padding=p))
     return _q(_act(y + 1.0 * x, LEAKY, f"{key}.layers.1"))
 
 
@@ -180,7 +208,7 @@ def global_pathway(sd, pre, I128, local_fake, local_feat, z):
     for i in range(1, 5):
         conv4 = _res(sd, p(f"conv4.{i}"), conv4, 3)
     B = I128.shape[0]
-    fc1 = _q(F.linear(conv4.reshape(B, -1), _qw(sd[p("fc1.weight")]), sd[p("fc1.bias")]))
+    fc1 = _q(_gout(F.linear(_xin(conv4.reshape(B, -1)), _xin(_qw(sd[p("fc1.weight")])), sd[p("fc1.bias")])))
     fc2 = F.max_pool1d(fc1.view(B, -1, 2), 2, 2).view(B, -1)
     deconv_8 = _deconv(sd, p("deconv_8"), torch.cat([fc2, z], 1).view(B, -1, 1, 1), 1, 0, 0)
     deconv_32 = _deconv(sd, p("deconv_32"), deconv_8, 4, 0, 1)
@@ -227,7 +255,7 @@ def generator(sd, I128, left_eye, right_eye, nose, mouth, z, dropout_mask=None):
     fused_in = local_fuser(parts_in)
     fake, enc = global_pathway(sd, "global_pathway", I128, fused_img, fused_feat, z)
     e = enc if dropout_mask is None else enc * dropout_mask
-    logits = _q(F.linear(e, _qw(sd["feature_predict.fc.weight"]), sd["feature_predict.fc.bias"]))
+    logits = _q(_gout(F.linear(_xin(e), _xin(_qw(sd["feature_predict.fc.weight"])), sd["feature_predict.fc.bias"])))
     return fake, logits, fused_img, imgs[0], imgs[1], imgs[2], imgs[3], fused_in
 
 

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtpgan_b200.so")
 
 CONV_FWD, CONV_DGRAD, DECONV_FWD, DECONV_DGRAD = 0, 1, 2, 3
 EPI_LINEAR, EPI_LEAKY, EPI_MASK = 0, 1, 2
+DTYPE_TF32, DTYPE_BF16 = 0, 1
 
 
 class View(C.Structure):
@@ -26,13 +27,19 @@ class ConvArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("in_", View), ("out", View), ("w_packed", C.c_void_p), ("w_rows_pad", C.c_int32),
                 ("w_k_pad", C.c_int32), ("bias", C.c_void_p), ("add1", View), ("add2", View), ("mask", View),
-                ("slopes", C.c_void_p), ("slope", C.c_float), ("epilogue", C.c_int32), ("round_tf32", C.c_int32)]
+                ("slopes", C.c_void_p), ("slope", C.c_float), ("epilogue", C.c_int32), ("round_tf32", C.c_int32),
+                ("dtype", C.c_int32), ("out16", View)]
 
 
 class WgradArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("x", View), ("dy", View), ("dw_packed", C.c_void_p), ("w_rows_pad", C.c_int32), ("w_k_pad", C.c_int32),
-                ("accumulate", C.c_int32)]
+                ("accumulate", C.c_int32), ("dtype", C.c_int32)]
+
+
+class CastJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int64), ("k_pad", C.c_int32), ("k_pad16", C.c_int32),
+                ("block_begin", C.c_int32), ("pad_", C.c_int32)]
 
 
 class BiasJob(C.Structure):
@@ -67,6 +74,8 @@ SYMBOLS = {
     "tpgan_unpack_weights": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _VP, _VP, _I32, _VP]),
     "tpgan_transpose_packed": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "tpgan_bias_grad_multi": (C.c_int, [_VP, _I32, _I32, _VP]),
+    "tpgan_cast_packed_multi": (C.c_int, [_VP, _I32, _I32, _VP]),
+    "tpgan_cast_bf16": (C.c_int, [View, View, _VP]),
     "tpgan_pack_multi": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _VP]),
     "tpgan_transpose_multi": (C.c_int, [_VP, _I32, _I32, _VP]),
     "tpgan_nchw_to_nhwc": (C.c_int, [_VP, View, _I32, _VP]),

@@ -21,12 +21,18 @@
 
 namespace tpg {
 
-template <class Params>
+template <class Params, bool BF16>
 __global__ void tapgemm_kernel(const __grid_constant__ Params P, int* status);
-template <class Params>
+template <class Params, bool BF16>
 __global__ void wgrad_kernel(const __grid_constant__ Params P, int* status);
+template <bool BF16>
 __global__ void rowconv_kernel(const __grid_constant__ RowConvParams P, int* status);
+template <bool BF16>
 __global__ void rowstack_kernel(const __grid_constant__ RowStackParams P, int* status);
+
+// Operand geometry by dtype: channels per 128-byte shared-memory row and elements per MMA K step (common.cuh: Opnd).
+static inline int chunk_ch(int bf16) { return bf16 ? 64 : 32; }
+static inline int mma_k(int bf16) { return bf16 ? 16 : 8; }
 
 // ------------------------------------------------------------------------------------------------ error state
 static thread_local char g_err[512] = "";
@@ -91,9 +97,11 @@ int* device_status_word() { return ensure_device() == 0 ? g_dev.status_dev : nul
 // 4D NHWC plane: dims {C, W, H, N}; step = parity-plane subsampling factor along H and W.
 static int encode_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int N, long long sw, long long sh,
                        long long sn, int bw, int bh, int bn, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
-                       int bc = 32) {
+                       int bc = 32, int bf16 = 0) {
+  // bf16: `base` addresses 2-byte elements (the caller passes the view's ptr); strides are in elements
+  const cuuint64_t eb = bf16 ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * eb, (cuuint64_t)sh * eb, (cuuint64_t)sn * eb};
   cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
@@ -101,8 +109,8 @@ static int encode_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, i
                      (const void*)base, sw, sh, sn);
   if (bw > 256 || bh > 256 || bn > 256 || bw < 1 || bh < 1 || bn < 1)
     return set_error(TPGAN_ERR_INVALID, "bad TMA box %d %d %d", bw, bh, bn);
-  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = g_dev.encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(TPGAN_ERR_CUDA, "cuTensorMapEncodeTiled(4D C=%d W=%d H=%d N=%d box %d,%d,%d) failed: %d", C, W, H, N,
@@ -111,14 +119,15 @@ static int encode_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, i
 }
 
 static int encode_weights(CUtensorMap* m, const float* base, int k_pad, int rows_pad, int taps, int block_n,
-                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int bc = 32) {
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int bc = 32, int bf16 = 0) {
+  const cuuint64_t eb = bf16 ? 2 : 4;
   cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)rows_pad, (cuuint64_t)taps};
-  cuuint64_t strides[2] = {(cuuint64_t)k_pad * 4, (cuuint64_t)k_pad * rows_pad * 4};
+  cuuint64_t strides[2] = {(cuuint64_t)k_pad * eb, (cuuint64_t)k_pad * rows_pad * eb};
   cuuint32_t box[3] = {(cuuint32_t)bc, (cuuint32_t)block_n, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   if ((uintptr_t)base & 15) return set_error(TPGAN_ERR_INVALID, "packed weights must be 16-byte aligned");
-  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = g_dev.encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(TPGAN_ERR_CUDA, "cuTensorMapEncodeTiled(weights k=%d rows=%d taps=%d bn=%d) failed: %d", k_pad,
@@ -131,19 +140,35 @@ static inline int pos_mod(int a, int b) { return a - floor_div(a, b) * b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 static DevView to_dev(const tpgan_view& v) { return DevView{v.ptr, v.sn, v.sh, v.sw}; }
+static DevView16 to_dev16(const tpgan_view& v) { return DevView16{reinterpret_cast<uint16_t*>(v.ptr), v.sn, v.sh, v.sw}; }
+// bf16 copy of the output: 8-byte stores of 4 channels need an 8-byte aligned view with strides that are multiples of 4
+static bool view16_ok(const tpgan_view& v) {
+  return v.ptr == nullptr || (((uintptr_t)v.ptr & 7) == 0 && v.sn % 4 == 0 && v.sh % 4 == 0 && v.sw % 4 == 0);
+}
+// dtype / output-view consistency shared by the three forward-type planners
+static int check_dtype(const tpgan_conv_args& a) {
+  if (a.dtype != TPGAN_DTYPE_TF32 && a.dtype != TPGAN_DTYPE_BF16) return set_error(TPGAN_ERR_INVALID, "bad dtype %d", a.dtype);
+  if (a.dtype == TPGAN_DTYPE_TF32 && a.out16.ptr) return set_error(TPGAN_ERR_INVALID, "out16 needs dtype BF16");
+  if (!a.out.ptr && !a.out16.ptr) return set_error(TPGAN_ERR_INVALID, "conv2d: no output view");
+  if (a.out16.ptr && (a.out16.n != a.out.n || a.out16.h != a.out.h || a.out16.w != a.out.w || a.out16.c != a.out.c))
+    return set_error(TPGAN_ERR_INVALID, "out16 geometry differs from out");
+  return 0;
+}
 static bool view_vec_ok(const tpgan_view& v) {
   return v.ptr == nullptr || (((uintptr_t)v.ptr & 15) == 0 && v.sn % 4 == 0 && v.sh % 4 == 0 && v.sw % 4 == 0);
 }
 
 // Parity planes of `t` for sampling stride s: plane (a,b) holds pixels (s*i + a, s*j + b).
 static int encode_planes(CUtensorMap* maps, const tpgan_view& t, int s, int bw, int bh, int bn,
-                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int bf16 = 0) {
   for (int a = 0; a < s; ++a)
     for (int b = 0; b < s; ++b) {
       int Hp = (t.h - a + s - 1) / s, Wp = (t.w - b + s - 1) / s;
       if (Hp <= 0 || Wp <= 0) return set_error(TPGAN_ERR_INVALID, "empty parity plane");
-      int rc = encode_nhwc(&maps[a * s + b], t.ptr + a * t.sh + b * t.sw, t.c, Wp, Hp, t.n, t.sw * s, t.sh * s, t.sn,
-                           bw, bh, bn, swz);
+      const long long off = a * t.sh + b * t.sw;   // elements
+      const float* base = bf16 ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(t.ptr) + off) : t.ptr + off;
+      int rc = encode_nhwc(&maps[a * s + b], base, t.c, Wp, Hp, t.n, t.sw * s, t.sh * s, t.sn,
+                           bw, bh, bn, swz, chunk_ch(bf16), bf16);
       if (rc) return rc;
     }
   return 0;
@@ -162,9 +187,14 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
   if (!gather && !phased) return set_error(TPGAN_ERR_INVALID, "bad kind %d", a.kind);
   const int Kc = a.in.c;
   const int taps = k * k;
-  if (a.w_k_pad % 32 || a.w_k_pad < Kc || a.w_rows_pad % 16 || a.w_rows_pad < a.out.c)
+  int rc0 = check_dtype(a);
+  if (rc0) return rc0;
+  const int bf16 = a.dtype == TPGAN_DTYPE_BF16;
+  const int CH = chunk_ch(bf16);
+  const int cout = a.out.c;   // out's geometry is always valid; only its ptr may be null (bf16 mode without an fp32 copy)
+  if (a.w_k_pad % CH || a.w_k_pad < Kc || a.w_rows_pad % 16 || a.w_rows_pad < cout)
     return set_error(TPGAN_ERR_INVALID, "packed weight dims (%d x %d) do not cover K=%d N=%d", a.w_rows_pad, a.w_k_pad, Kc,
-                     a.out.c);
+                     cout);
 
   G.Nimg = a.in.n;
   int ntap = 0;
@@ -233,16 +263,17 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
   G.n_tiles = ceil_div(a.w_rows_pad, 256) * n_split;
   G.block_n = ceil_div(ceil_div(a.w_rows_pad, G.n_tiles), 16) * 16;
   G.n_tiles = ceil_div(a.w_rows_pad, G.block_n);
-  G.kchunks = ceil_div(Kc, 32);
-  G.last_mmas = ceil_div(Kc - 32 * (G.kchunks - 1), 8);
+  G.kchunks = ceil_div(Kc, CH);
+  G.last_mmas = ceil_div(Kc - CH * (G.kchunks - 1), mma_k(bf16));
   G.tile_count = G.n_phases * G.m_tiles * G.n_tiles;
 
-  int rc = gather ? encode_planes(G.amap, a.in, s, G.bw, G.bh, G.bn) : encode_planes(G.amap, a.in, 1, G.bw, G.bh, G.bn);
+  int rc = encode_planes(G.amap, a.in, gather ? s : 1, G.bw, G.bh, G.bn, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
   if (rc) return rc;
-  rc = encode_weights(&G.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, taps + 1, G.block_n);
+  rc = encode_weights(&G.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, taps + 1, G.block_n, CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
   if (rc) return rc;
 
   G.out = to_dev(a.out);
+  G.out16 = to_dev16(a.out16);
   G.add1 = to_dev(a.add1);
   G.add2 = to_dev(a.add2);
   G.mask = to_dev(a.mask);
@@ -250,12 +281,12 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
   G.slopes = a.slopes;
   G.Hout = a.out.h;
   G.Wout = a.out.w;
-  G.cout_valid = a.out.c;
+  G.cout_valid = cout;
   G.epilogue = a.epilogue;
   G.slope = a.slope;
   G.round_tf32 = a.round_tf32;
   if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) return set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view");
-  G.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask);
+  G.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask) && view16_ok(a.out16);
   return 0;
 }
 
@@ -291,7 +322,7 @@ static int choose_n_split(const Params& P, const tpgan_conv_args* groups) {
 }
 
 template <class Params>
-static int launch_tapgemm(Params& P, cudaStream_t st) {
+static int launch_tapgemm(Params& P, cudaStream_t st, int bf16) {
   int bmax = 0;
   int tiles = 0;
   for (int i = 0; i < P.ngroups; ++i) {
@@ -310,8 +341,7 @@ static int launch_tapgemm(Params& P, cudaStream_t st) {
   if (const char* ev = getenv("TPGAN_STAGES")) P.stages = std::min(P.stages, std::max(2, atoi(ev)));
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "not enough shared memory for 2 stages");
   const int smem = P.stages * stage_bytes + 1024;
-  static std::once_flag once;
-  auto kern = tapgemm_kernel<Params>;
+  auto kern = bf16 ? tapgemm_kernel<Params, true> : tapgemm_kernel<Params, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int grid = std::min(tiles, g_dev.sm_count);
@@ -335,6 +365,9 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
   if (a.kh != a.kw || a.stride != 1 || 2 * p != k - 1 || k < 3 || k * k > kMaxTaps) return 0;
   if (a.in.w != 128 || a.out.w != 128 || a.in.h != a.out.h || a.in.n != a.out.n) return 0;
   if (a.w_rows_pad > 256) return 0;
+  if (check_dtype(a)) { *rc_out = TPGAN_ERR_INVALID; return 1; }
+  const int bf16 = a.dtype == TPGAN_DTYPE_BF16;
+  const int CH = chunk_ch(bf16);
   static thread_local RowConvParams P;
   memset(&P, 0, sizeof(P));
   P.H = a.out.h; P.W = 128; P.Nimg = a.in.n; P.k = k;
@@ -349,8 +382,8 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
   P.double_buf = (P.block_n * T <= 256) ? 1 : 0;
   P.row_tiles = ceil_div(P.H, T);
   P.total_tiles = P.Nimg * P.row_tiles * P.n_tiles;
-  P.kchunks = ceil_div(a.in.c, 32);
-  P.last_mmas = ceil_div(a.in.c - 32 * (P.kchunks - 1), 8);
+  P.kchunks = ceil_div(a.in.c, CH);
+  P.last_mmas = ceil_div(a.in.c - CH * (P.kchunks - 1), mma_k(bf16));
   const bool fwd = a.kind == TPGAN_CONV_FWD;
   P.dy0 = fwd ? -p : p - k + 1;
   P.dx0 = P.dy0;
@@ -369,20 +402,23 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
     P.b_slots = std::min(16, (budget - P.a_slots * P.slab_bytes) / P.b_bytes);
     if (P.b_slots < 2) return 0;
   }
-  int rc = encode_nhwc(&P.amap, a.in.ptr, a.in.c, a.in.w, a.in.h, a.in.n, a.in.sw, a.in.sh, a.in.sn, 128 + k - 1, 1, 1);
+  int rc = encode_nhwc(&P.amap, a.in.ptr, a.in.c, a.in.w, a.in.h, a.in.n, a.in.sw, a.in.sh, a.in.sn, 128 + k - 1, 1, 1,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
   if (rc) { *rc_out = rc; return 1; }
-  rc = encode_weights(&P.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, k * k + 1, P.block_n);
+  rc = encode_weights(&P.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, k * k + 1, P.block_n, CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
   if (rc) { *rc_out = rc; return 1; }
   P.out = to_dev(a.out); P.add1 = to_dev(a.add1); P.add2 = to_dev(a.add2); P.mask = to_dev(a.mask);
+  P.out16 = to_dev16(a.out16);
   P.bias = a.bias; P.slopes = a.slopes;
   P.cout_valid = a.out.c; P.epilogue = a.epilogue; P.slope = a.slope; P.round_tf32 = a.round_tf32;
   if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) { *rc_out = set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view"); return 1; }
-  P.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask);
+  P.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask) && view16_ok(a.out16);
   const int smem = P.a_slots * P.slab_bytes + P.b_slots * P.b_bytes + 1024;
-  cudaError_t e = cudaFuncSetAttribute(rowconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
+  auto kern = bf16 ? rowconv_kernel<true> : rowconv_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
   const int grid = std::min(P.total_tiles, g_dev.sm_count);
-  rowconv_kernel<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
+  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowconv launch: %s", cudaGetErrorString(e)); return 1; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -400,6 +436,9 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
   if (a.kh != a.kw || a.stride != 1 || 2 * p != k - 1 || k < 3 || k * k > kMaxTaps) return 0;
   if (a.in.w != 128 || a.out.w != 128 || a.in.h != a.out.h || a.in.n != a.out.n) return 0;
   if (a.w_rows_pad > 128) return 0;
+  if (check_dtype(a)) { *rc_out = TPGAN_ERR_INVALID; return 1; }
+  const int bf16 = a.dtype == TPGAN_DTYPE_BF16;
+  const int CH = chunk_ch(bf16) / 2;   // channels per 64-byte K chunk
   static thread_local RowStackParams P;
   memset(&P, 0, sizeof(P));
   P.H = a.out.h; P.W = 128; P.Nimg = a.in.n; P.k = k;
@@ -411,8 +450,8 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
   P.T = T;
   P.row_tiles = ceil_div(P.H, T);
   P.total_tiles = P.Nimg * P.row_tiles;
-  P.kchunks = ceil_div(a.in.c, 16);
-  P.last_mmas = ceil_div(a.in.c - 16 * (P.kchunks - 1), 8);
+  P.kchunks = ceil_div(a.in.c, CH);
+  P.last_mmas = ceil_div(a.in.c - CH * (P.kchunks - 1), mma_k(bf16));
   const bool fwd = a.kind == TPGAN_CONV_FWD;
   P.dy0 = fwd ? -p : p - k + 1;
   P.dx0 = P.dy0;
@@ -422,8 +461,9 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
   for (int s = 0; s < T + k - 1; ++s) {
     const int t_lo = std::max(0, s - k + 1), t_hi = std::min(T - 1, s);
     const int nn = (t_hi - t_lo + 1) * P.block_n;
-    // kind::tf32 instruction descriptor, M = 128, N = nn, K-major A and B (make_idesc_tf32 in common.cuh)
-    P.s_idesc[s] = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // instruction descriptor, M = 128, N = nn, K-major A and B, operand format 2 = tf32 / 1 = bf16 (Opnd::idesc in common.cuh)
+    const uint32_t fmt = bf16 ? 1u : 2u;
+    P.s_idesc[s] = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     P.s_boff[s] = (uint32_t)(k - 1 - (s - t_lo)) * (uint32_t)P.block_n * 4u;
     P.s_doff[s] = (uint32_t)(t_lo * P.block_n);
   }
@@ -441,20 +481,22 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
   P.a_slots = std::min(P.a_slots, nslab + 4);
   if (nslab > 16) return 0;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_64B;
-  int rc = encode_nhwc(&P.amap, a.in.ptr, a.in.c, a.in.w, a.in.h, a.in.n, a.in.sw, a.in.sh, a.in.sn, 128 + k - 1, 1, 1, swz, 16);
+  int rc = encode_nhwc(&P.amap, a.in.ptr, a.in.c, a.in.w, a.in.h, a.in.n, a.in.sw, a.in.sh, a.in.sn, 128 + k - 1, 1, 1, swz, CH, bf16);
   if (rc) { *rc_out = rc; return 1; }
-  rc = encode_weights(&P.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, k * k + 1, P.block_n, swz, 16);
+  rc = encode_weights(&P.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, k * k + 1, P.block_n, swz, CH, bf16);
   if (rc) { *rc_out = rc; return 1; }
   P.out = to_dev(a.out); P.add1 = to_dev(a.add1); P.add2 = to_dev(a.add2); P.mask = to_dev(a.mask);
+  P.out16 = to_dev16(a.out16);
   P.bias = a.bias; P.slopes = a.slopes;
   P.cout_valid = a.out.c; P.epilogue = a.epilogue; P.slope = a.slope; P.round_tf32 = a.round_tf32;
   if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) { *rc_out = set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view"); return 1; }
-  P.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask);
+  P.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask) && view16_ok(a.out16);
   const int smem = P.a_slots * P.slab_bytes + P.b_slots * P.wb_bytes + 1024;
-  cudaError_t e = cudaFuncSetAttribute(rowstack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
+  auto kern = bf16 ? rowstack_kernel<true> : rowstack_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
   const int grid = std::min(P.total_tiles, g_dev.sm_count);
-  rowstack_kernel<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
+  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowstack launch: %s", cudaGetErrorString(e)); return 1; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -484,31 +526,37 @@ static WgradChoice wgrad_option(const tpgan_wgrad_args& a, bool swap, bool slab)
   const tpgan_view& Pt = p_is_dy ? a.dy : a.x;
   const tpgan_view& Qt = p_is_dy ? a.x : a.dy;
   const int k = a.kh, ntaps = k * k;
+  const int bf16 = a.dtype == TPGAN_DTYPE_BF16;
+  const int CH = chunk_ch(bf16);        // channels per 128-byte operand chunk
+  const int MCH = 128 / CH;             // P chunks per M = 128 tile
+  const int NCH = 256 / CH;             // Q chunks per N = 256 MMA
   c.swap = swap;
   c.slab = slab;
   c.pc = Pt.c;
   c.qc = Qt.c;
   c.m_tiles = ceil_div(c.pc, 128);
-  c.nch_total = ceil_div(c.qc, 32);
+  c.nch_total = ceil_div(c.qc, CH);
   const long long npix = (long long)Pt.h * Pt.w * Pt.n;
   if (slab) {
     c.ncpt = c.nch_total;
     c.n_tiles = 1;
-    c.mpu = (c.m_tiles * c.ncpt * 2 <= 16) ? c.m_tiles : 1;   // (acc_chunks below may still shrink tpu)
-    static const int acc_chunks = getenv("TPGAN_WGRAD_SLAB_COLS") ? atoi(getenv("TPGAN_WGRAD_SLAB_COLS")) / 32 : 16;
-    const int tmax = std::min(std::min(k, 8), acc_chunks / std::max(1, c.mpu * c.ncpt));
-    if (c.ncpt > 8 || tmax < 2) { c.cost = 1e30; return c; }
+    static const int acc_cols = getenv("TPGAN_WGRAD_SLAB_COLS") ? atoi(getenv("TPGAN_WGRAD_SLAB_COLS")) : 512;
+    const int acc_chunks = acc_cols / CH;     // CH-column accumulator blocks in TMEM
+    c.mpu = (c.m_tiles * c.ncpt * 2 <= acc_chunks) ? c.m_tiles : 1;   // (acc_chunks below may still shrink tpu)
+    const int tmax = std::min(std::min(k, NCH), acc_chunks / std::max(1, c.mpu * c.ncpt));   // N = tpu * CH <= 256
+    if (c.ncpt > NCH || tmax < 2) { c.cost = 1e30; return c; }
     const int ngrp = ceil_div(k, tmax);
     c.tpu = ceil_div(k, ngrp);
     if (k * ngrp * c.tpu > kMaxTaps) { c.cost = 1e30; return c; }
-    c.block_n = c.tpu * 32;
-    c.a_ch = std::min(4 * c.mpu, ceil_div(c.pc, 32));
+    c.block_n = c.tpu * CH;
+    c.a_ch = std::min(MCH * c.mpu, ceil_div(c.pc, CH));
     c.b_ch = c.ncpt;
     double row = 0;   // MMA cycles per K step for the taps of one kernel row, one M tile, one Q chunk
     for (int g = 0, left = k; g < ngrp; ++g) {
       const int nt = std::min(c.tpu, left);
       left -= nt;
-      const double mma = std::max(16.0 * nt, 32.0 + 8.0 * nt) * c.mpu * c.ncpt;
+      const int nn = nt * CH;   // N of the slab MMA
+      const double mma = std::max(nn / 2.0, 32.0 + nn / 4.0) * c.mpu * c.ncpt;
       const double l2 = (c.a_ch + c.ncpt) * 1024.0 / kL2BytesPerClk;
       row += std::max(mma, l2) * ceil_div(c.m_tiles, c.mpu);
     }
@@ -519,22 +567,22 @@ static WgradChoice wgrad_option(const tpgan_wgrad_args& a, bool swap, bool slab)
     // narrow shifted tensor (one 32-channel chunk: the 3-channel image layers): several taps side by side in N, all
     // sharing the loads of P
     c.ncpt = c.nch_total;
-    c.tpu = std::min(ntaps, 8 / c.nch_total);
+    c.tpu = std::min(ntaps, NCH / c.nch_total);
     c.n_tiles = 1;
-    c.block_n = c.tpu * c.ncpt * 32;
+    c.block_n = c.tpu * c.ncpt * CH;
     c.mpu = 1;
-    c.a_ch = std::min(4, ceil_div(c.pc, 32));
+    c.a_ch = std::min(MCH, ceil_div(c.pc, CH));
     c.b_ch = c.tpu * c.ncpt;
   } else {
     c.tpu = 1;
-    c.n_tiles = ceil_div(c.nch_total, 8);
-    c.block_n = ceil_div(c.nch_total, c.n_tiles) * 32;
-    c.ncpt = c.block_n / 32;
+    c.n_tiles = ceil_div(c.nch_total, NCH);
+    c.block_n = ceil_div(c.nch_total, c.n_tiles) * CH;
+    c.ncpt = c.block_n / CH;
     // several M tiles per unit (one accumulator each), all sharing the loads of Q - when the reduction is long enough
     // (>= 32768 pixels) to amortise the then single-buffered epilogue
     static const long long mpu_min_pix = getenv("TPGAN_WGRAD_MPU_MINPIX") ? atoll(getenv("TPGAN_WGRAD_MPU_MINPIX")) : 32768;
     c.mpu = (no_pack || npix < mpu_min_pix) ? 1 : std::max(1, std::min(c.m_tiles, 512 / c.block_n));
-    c.a_ch = std::min(4 * c.mpu, ceil_div(c.pc, 32));
+    c.a_ch = std::min(MCH * c.mpu, ceil_div(c.pc, CH));
     c.b_ch = c.ncpt;
   }
   const double mma = std::max(c.block_n / 2.0, 32.0 + c.block_n / 4.0) * c.mpu;
@@ -570,6 +618,9 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   // deconv: P = x  (Cin),  Q = dy planes (Cout) -> dw[tap][co][ci], m=ci n=co (transposed write)
   const bool is_conv = (a.kind == TPGAN_CONV_FWD);
   if (!is_conv && a.kind != TPGAN_DECONV_FWD) return set_error(TPGAN_ERR_INVALID, "bad wgrad kind %d", a.kind);
+  if (a.dtype != TPGAN_DTYPE_TF32 && a.dtype != TPGAN_DTYPE_BF16) return set_error(TPGAN_ERR_INVALID, "bad dtype %d", a.dtype);
+  const int bf16 = a.dtype == TPGAN_DTYPE_BF16;
+  const int KR = mma_k(bf16);           // pixel rows per MMA K step
   const WgradChoice ch = choose_wgrad(a);
   const bool p_is_dy = is_conv && !ch.swap;
   const tpgan_view& Pt = p_is_dy ? a.dy : a.x;
@@ -590,7 +641,7 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   G.bw = (G.Wp <= box_px + box_px / 2) ? G.Wp : box_px;
   G.bh = ch.slab ? 1 : std::max(1, std::min(G.Hp, box_px / G.bw));
   G.bn = (!ch.slab && G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, box_px / (G.bw * G.bh))) : 1;
-  G.kp = ceil_div(G.bw * G.bh * G.bn, 8) * 8;
+  G.kp = ceil_div(G.bw * G.bh * G.bn, KR) * KR;
   G.tiles_w = ceil_div(G.Wp, G.bw);
   G.tiles_h = ceil_div(G.Hp, G.bh);
   G.chunks = G.tiles_w * G.tiles_h * ceil_div(G.Nimg, G.bn);
@@ -602,9 +653,10 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   G.mpu = ch.mpu;
   G.slab = ch.slab ? 1 : 0;
   G.mt_groups = ceil_div(G.m_tiles, G.mpu);
-  // MN-major tf32 operands need the 32B-atom flavour of the 128B swizzle
-  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.bw, G.bh, G.bn, swz);
+  // MN-major tf32 operands need the 32B-atom flavour of the 128B swizzle; bf16 uses the plain 128B swizzle
+  const CUtensorMapSwizzle swz = bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const int CH = chunk_ch(bf16);
+  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.bw, G.bh, G.bn, swz, CH, bf16);
   if (rc) return rc;
   if (ch.slab) {
     // taps: per kernel row, groups of tpu slots (unused slots: wtap 255), horizontal offset increasing inside a group
@@ -630,9 +682,9 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
         }
     G.ntaps = nt;
     G.tap_groups = k * ngrp;
-    G.nbuf = (G.mpu * G.ncpt * G.tpu * 32 <= 256) ? 2 : 1;
+    G.nbuf = (G.mpu * G.ncpt * G.tpu * CH <= 256) ? 2 : 1;
     G.q_chunk_bytes = ceil_div(G.kp + G.tpu - 1, 8) * 8 * 128;
-    rc = encode_nhwc(&G.qslab, Qt.ptr, Qt.c, Qt.w, Qt.h, Qt.n, Qt.sw, Qt.sh, Qt.sn, G.bw + G.tpu - 1, 1, 1, swz);
+    rc = encode_nhwc(&G.qslab, Qt.ptr, Qt.c, Qt.w, Qt.h, Qt.n, Qt.sw, Qt.sh, Qt.sn, G.bw + G.tpu - 1, 1, 1, swz, CH, bf16);
     if (rc) return rc;
     return 0;
   }
@@ -651,7 +703,7 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
       t.wtap = (uint8_t)(r * k + c);
       G.taps[nt++] = t;
     }
-  rc = encode_planes(G.qmap, Qt, s, G.bw, G.bh, G.bn, swz);
+  rc = encode_planes(G.qmap, Qt, s, G.bw, G.bh, G.bn, swz, bf16);
   if (rc) return rc;
   return 0;
 }
@@ -666,7 +718,7 @@ static int choose_wgrad_px(const tpgan_wgrad_args* groups, int ngroups) {
     for (int i = 0; i < ngroups; ++i) {
       const WgradChoice c = choose_wgrad(groups[i]);
       const int q_rows = c.slab ? ceil_div(px + c.tpu - 1, 8) * 8 : px;
-      worst = std::max(worst, c.a_ch * px * 128 + c.b_ch * q_rows * 128);
+      worst = std::max(worst, c.a_ch * px * 128 + c.b_ch * q_rows * 128);   // bytes: a chunk row is 128 B for either dtype
     }
     return worst;
   };
@@ -677,19 +729,20 @@ static int choose_wgrad_px(const tpgan_wgrad_args* groups, int ngroups) {
 }
 
 template <class Params>
-static int launch_wgrad(Params& P, cudaStream_t st) {
+static int launch_wgrad(Params& P, cudaStream_t st, int bf16) {
   int amax = 0, bmax = 0;
   long long work = 0;
+  const int CH = chunk_ch(bf16), MCH = 128 / CH, KR = mma_k(bf16);
   for (int i = 0; i < P.ngroups; ++i) {
     WgradGroup& G = P.g[i];
-    amax = std::max(amax, std::min(4 * G.mpu, ceil_div(G.m_valid, 32)) * G.kp * 128);
-    bmax = std::max(bmax, (G.slab ? G.ncpt : G.block_n / 32) * G.q_chunk_bytes);
+    amax = std::max(amax, std::min(MCH * G.mpu, ceil_div(G.m_valid, CH)) * G.kp * 128);
+    bmax = std::max(bmax, (G.slab ? G.ncpt : G.block_n / CH) * G.q_chunk_bytes);
     G.tiles = G.tap_groups * G.mt_groups * G.n_tiles;
     // K blocks: pixel ranges whose activations (P and Q) fit a slice of L2; every CTA works through block after block
     {
       static const double mb_plain = getenv("TPGAN_WGRAD_KB_MB") ? atof(getenv("TPGAN_WGRAD_KB_MB")) : 64.0;
       static const double mb_slab = getenv("TPGAN_WGRAD_KB_MB_SLAB") ? atof(getenv("TPGAN_WGRAD_KB_MB_SLAB")) : 1e6;   // slab units stream little from L2 and pay for every extra epilogue
-      const double bytes = (double)G.Hp * G.Wp * G.Nimg * 4.0 * (ceil_div(G.m_valid, 4) * 4 + ceil_div(G.n_valid, 4) * 4);
+      const double bytes = (double)G.Hp * G.Wp * G.Nimg * (bf16 ? 2.0 : 4.0) * (ceil_div(G.m_valid, 4) * 4 + ceil_div(G.n_valid, 4) * 4);
       int nkb = (int)std::ceil(bytes / ((G.slab ? mb_slab : mb_plain) * 1048576.0));
       nkb = std::max(1, std::min(nkb, G.chunks));
       if (g_deterministic.load(std::memory_order_relaxed)) nkb = 1;
@@ -710,17 +763,17 @@ static int launch_wgrad(Params& P, cudaStream_t st) {
   // an M = 128 MMA always reads four 32-channel P chunks; when fewer are loaded (P narrower than 128 channels) the read
   // runs into the following bytes (rows that are never stored), so the ring is followed by that much slack
   int slack = 0;
-  for (int i = 0; i < P.ngroups; ++i) slack = std::max(slack, 4 * P.g[i].mpu * P.g[i].kp * 128 - stage_bytes);
+  for (int i = 0; i < P.ngroups; ++i) slack = std::max(slack, MCH * P.g[i].mpu * P.g[i].kp * 128 - stage_bytes);
   slack = std::max(0, slack);
   const int budget = g_dev.max_smem - 1024 - 256 - slack;
   P.stages = std::min(kMaxStages, budget / stage_bytes);
   P.ring_bytes = P.stages * stage_bytes + slack;
   P.need_zero = 0;
   for (int i = 0; i < P.ngroups; ++i)
-    if ((P.g[i].bw * P.g[i].bh * P.g[i].bn) % 8) P.need_zero = 1;
+    if ((P.g[i].bw * P.g[i].bh * P.g[i].bn) % KR) P.need_zero = 1;
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "wgrad: not enough shared memory for 2 stages (%d B/stage)", stage_bytes);
   const int smem = P.ring_bytes + 1024;
-  auto kern = wgrad_kernel<Params>;
+  auto kern = bf16 ? wgrad_kernel<Params, true> : wgrad_kernel<Params, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   // balanced schedule: every CTA gets total_work / grid (+-1) chunks (see SegmentWalk in wgrad.cu)
@@ -745,6 +798,9 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
   int rc = ensure_device();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const int bf16 = groups[0].dtype == TPGAN_DTYPE_BF16;
+  for (int i = 1; i < ngroups; ++i)
+    if (groups[i].dtype != groups[0].dtype) return set_error(TPGAN_ERR_INVALID, "grouped problems must share one dtype");
   if (ngroups == 1) {
     int rrc = 0;
     g_last_conv_kernel = 2;
@@ -761,7 +817,7 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
       rc = plan_group(groups[0], P.g[0], f);
       if (rc) return rc;
     }
-    return launch_tapgemm(P, st);
+    return launch_tapgemm(P, st, bf16);
   }
   g_last_conv_kernel = 0;
   static thread_local TapGemmParams P;
@@ -776,7 +832,7 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
       rc = plan_group(groups[i], P.g[i], f);
       if (rc) return rc;
     }
-  return launch_tapgemm(P, st);
+  return launch_tapgemm(P, st, bf16);
 }
 
 int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* stream) {
@@ -784,12 +840,15 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
   int rc = ensure_device();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const int bf16 = groups[0].dtype == TPGAN_DTYPE_BF16;
+  for (int i = 1; i < ngroups; ++i)
+    if (groups[i].dtype != groups[0].dtype) return set_error(TPGAN_ERR_INVALID, "grouped problems must share one dtype");
   if (ngroups == 1) {
     static thread_local WgradParams1 P;
     P.ngroups = 1;
     rc = plan_wgrad(groups[0], P.g[0], choose_wgrad_px(groups, 1));
     if (rc) return rc;
-    return launch_wgrad(P, st);
+    return launch_wgrad(P, st, bf16);
   }
   static thread_local WgradParams P;
   P.ngroups = ngroups;
@@ -800,7 +859,7 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
     if (rc) return rc;
     const WgradGroup& G = P.g[i];
     // the zero-padded K rows of the smem ring stay zero only if every box fills its rows or all boxes are alike
-    if ((G.bw * G.bh * G.bn) % 8) uniform = false;
+    if ((G.bw * G.bh * G.bn) % mma_k(bf16)) uniform = false;
   }
   if (!uniform) {
     bool same = true;
@@ -816,7 +875,7 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
       return 0;
     }
   }
-  return launch_wgrad(P, st);
+  return launch_wgrad(P, st, bf16);
 }
 
 const char* tpgan_last_error(void) { return g_err; }

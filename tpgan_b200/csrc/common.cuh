@@ -185,6 +185,34 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// bf16 inputs (kind::f16), fp32 accumulate; K = 16 elements (32 bytes) per instruction.
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Operand-type traits of the tensor-core kernels.  Both operand types move through shared memory in 128-byte rows and
+// advance 32 bytes per MMA K step, so the kernels are identical in BYTES; what changes is the number of channels per row
+// (32 tf32 / 64 bf16), the elements per K step (8 / 16), the MMA kind and the instruction-descriptor format bits.
+template <bool BF16>
+struct Opnd {
+  static constexpr int kChunk = BF16 ? 64 : 32;   // channels per 128-byte shared-memory row
+  static constexpr int kMmaK = BF16 ? 16 : 8;     // elements per MMA K step
+  static __device__ __forceinline__ void mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    if constexpr (BF16) mma_bf16_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else mma_tf32_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
+  }
+  // instruction descriptor: fp32 accumulate (c_format 1), a/b format 2 = TF32 or 1 = BF16, major bits, N >> 3, M >> 4
+  static __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  }
+};
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
@@ -244,8 +272,21 @@ struct EpiArgs {
   int cout_valid, epilogue, round_tf32, vec_ok;
   float slope;
 };
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ uint16_t to_bf16(float x) {
+  uint16_t r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+// po: fp32 destination of the pixel (may be null), po16: bf16 copy of the same values (may be null; bf16 operand storage
+// for the tensor-core consumers of this tensor).  Both receive the value BEFORE any rounding of the other.
 __device__ __forceinline__ void epilogue_store16(const uint32_t (&r)[16], const EpiArgs& E, int col0, float* po,
-                                                 const float* p1, const float* p2, const float* pm) {
+                                                 const float* p1, const float* p2, const float* pm,
+                                                 uint16_t* po16 = nullptr) {
   const int nv16 = E.cout_valid - col0;
   if (nv16 <= 0) return;
   float v[16];
@@ -291,13 +332,28 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t (&r)[16], const 
         }
       }
     }
-    if (E.round_tf32) {
+    if (po16) {   // the view starts on a 4-channel boundary: 8-byte stores always, 16-byte when aligned
+      uint32_t h[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+      for (int j = 0; j < 8; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      uint16_t* d = po16 + col0;
+      if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(d + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(d + 4 * j) = make_uint2(h[2 * j], h[2 * j + 1]);
+      }
     }
+    if (po) {
+      if (E.round_tf32) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<float4*>(po + col0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(po + col0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
     return;
   }
   // ragged tail / unaligned views: element-wise
@@ -315,8 +371,9 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t (&r)[16], const 
         const float s = E.slopes ? __ldg(E.slopes + col) : E.slope;
         x = pm[col] > 0.f ? x : x * s;
       }
+      if (po16) po16[col] = to_bf16(x);
       if (E.round_tf32) x = round_tf32(x);
-      po[col] = x;
+      if (po) po[col] = x;
     }
   }
 }

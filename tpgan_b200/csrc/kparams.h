@@ -32,6 +32,11 @@ struct DevView {
   long long sn, sh, sw;
 };
 
+struct DevView16 {   // bf16 copy of an output view (operand storage for tensor-core consumers); ptr null = not written
+  uint16_t* ptr;
+  long long sn, sh, sw;
+};
+
 struct PhaseDesc {
   short tap_begin, tap_count;
   short oy, ox;  // output pixel = (y*out_sy + oy, x*out_sx + ox)
@@ -45,13 +50,14 @@ struct TapGemmGroup {
   int bw, bh, bn;                // pixels of one 128-row tile = bw*bh*bn (<= 128)
   int tiles_h, m_tiles;          // ceil(Hm/bh), tiles_h * ceil(Nimg/bn)
   int n_tiles, block_n;
-  int kchunks, last_mmas;        // K = C of the A operand, in 32-float chunks; MMAs (K=8) in the last chunk
+  int kchunks, last_mmas;        // K = C of the A operand, in 128-byte chunks (32 tf32 / 64 bf16 channels); MMAs in the last chunk
   int n_phases;
   int tile_begin, tile_count;    // this group's slice of the persistent tile list
   PhaseDesc phase[kMaxPhases];
   TapDesc taps[kMaxTaps];
   // epilogue
   DevView out, add1, add2, mask;
+  DevView16 out16;
   const float* bias;
   const float* slopes;
   int out_sy, out_sx, Hout, Wout;
@@ -92,6 +98,7 @@ struct RowConvParams {
   unsigned char wtap[kMaxTaps];   // weight tap slice for grid position r*k + j
   unsigned char dxoff[kMaxTaps];  // slab pixel-row offset (j) for grid position r*k + j
   DevView out, add1, add2, mask;
+  DevView16 out16;
   const float* bias;
   const float* slopes;
   int cout_valid, epilogue, round_tf32, vec_ok;
@@ -113,6 +120,7 @@ struct RowStackParams {
   // accumulator column t_lo * block_n
   uint32_t s_idesc[16], s_boff[16], s_doff[16];
   DevView out, add1, add2, mask;
+  DevView16 out16;
   const float* bias;
   const float* slopes;
   int cout_valid, epilogue, round_tf32, vec_ok;

@@ -865,6 +865,56 @@ __device__ __forceinline__ int find_job(const Job* jobs, int njobs, int block) {
   return lo;
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 operand copies
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// dst16 (bf16 view, same logical shape) = round-to-nearest-even(src).  One thread per (pixel, 4 channels): a 16-byte load
+// and an 8-byte store when both views allow it, element-wise otherwise.  Padding lanes inside the last quad (channels
+// >= c of a buffer whose channel stride is a multiple of 4) are copied too - they are zero in the source.
+__global__ void cast_bf16_kernel(V s, uint16_t* __restrict__ d, long long dsn, long long dsh, long long dsw, int vec) {
+  const int cq = (s.c + 3) >> 2;
+  const long long total = (long long)s.n * s.h * s.w * cq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cq);
+    long long r = i / cq;
+    const int x = (int)(r % s.w);
+    r /= s.w;
+    const int y = (int)(r % s.h);
+    const int n = (int)(r / s.h);
+    const float* sp = s.p + voff(s, n, y, x) + 4 * q;
+    uint16_t* dp = d + (long long)n * dsn + (long long)y * dsh + (long long)x * dsw + 4 * q;
+    if (vec) {
+      const float4 v = *reinterpret_cast<const float4*>(sp);
+      *reinterpret_cast<uint2*>(dp) = make_uint2(cvt_bf16x2(v.x, v.y), cvt_bf16x2(v.z, v.w));
+    } else {
+      for (int j = 0; j < 4 && 4 * q + j < s.c; ++j) {
+        uint16_t h;
+        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(sp[j]));
+        dp[j] = h;
+      }
+    }
+  }
+}
+// Packed fp32 weights [rows][k_pad] -> bf16 [rows][k_pad16] (k_pad16 >= k_pad, zero beyond), all layers in one launch.
+// A block converts 2048 quads (4 consecutive k of one row) of one job.
+__global__ void __launch_bounds__(256) cast_packed_multi_kernel(const tpgan_cast_job* __restrict__ jobs, int njobs) {
+  const int ji = find_job(jobs, njobs, (int)blockIdx.x);
+  const tpgan_cast_job J = jobs[ji];
+  const int kq = J.k_pad16 >> 2;
+  const long long total = J.rows * kq;
+  long long i = (long long)((int)blockIdx.x - J.block_begin) * 2048 + threadIdx.x;
+  for (int it = 0; it < 8 && i < total; ++it, i += 256) {
+    const long long r = i / kq;
+    const int kk = (int)(i - r * kq) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kk < J.k_pad) v = *reinterpret_cast<const float4*>(J.src + r * J.k_pad + kk);
+    *reinterpret_cast<uint2*>(J.dst + r * J.k_pad16 + kk) = make_uint2(cvt_bf16x2(v.x, v.y), cvt_bf16x2(v.z, v.w));
+  }
+}
+
 __global__ void __launch_bounds__(256) bias_grad_multi_kernel(const tpgan_bias_job* __restrict__ jobs, int njobs) {
   __shared__ float4 red[8][32];
   const int ji = find_job(jobs, njobs, (int)blockIdx.x);
@@ -1423,6 +1473,23 @@ int tpgan_transpose_packed(const float* src, float* dst, int32_t taps, int32_t r
   return 0;
 }
 
+int tpgan_cast_bf16(tpgan_view src, tpgan_view dst16, void* stream) {
+  if (!src.ptr || !dst16.ptr || !same_geom(src, dst16)) return set_error(TPGAN_ERR_INVALID, "cast_bf16: bad views");
+  const long long total = (long long)src.n * src.h * src.w * ((src.c + 3) / 4);
+  if (total <= 0) return 0;
+  const bool vec = view_vec4_ok(src) && (((uintptr_t)dst16.ptr & 7) == 0) && dst16.sn % 4 == 0 && dst16.sh % 4 == 0 &&
+                   dst16.sw % 4 == 0 && (src.sw >= ((src.c + 3) / 4) * 4) && (dst16.sw >= ((src.c + 3) / 4) * 4);
+  cast_bf16_kernel<<<grid_for(total, 256, 16), 256, 0, ST>>>(dv(src), reinterpret_cast<uint16_t*>(dst16.ptr), dst16.sn,
+                                                              dst16.sh, dst16.sw, vec ? 1 : 0);
+  TPG_CHECK_LAUNCH("cast_bf16");
+  return 0;
+}
+int tpgan_cast_packed_multi(const tpgan_cast_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream) {
+  if (!jobs_dev || njobs <= 0 || total_blocks <= 0) return set_error(TPGAN_ERR_INVALID, "cast_packed_multi: bad args");
+  cast_packed_multi_kernel<<<total_blocks, 256, 0, ST>>>(jobs_dev, njobs);
+  TPG_CHECK_LAUNCH("cast_packed_multi");
+  return 0;
+}
 int tpgan_bias_grad_multi(const tpgan_bias_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream) {
   if (!jobs_dev || njobs < 1 || total_blocks < 1) return set_error(TPGAN_ERR_INVALID, "bias_grad_multi: bad args");
   bias_grad_multi_kernel<<<total_blocks, 256, 0, ST>>>(jobs_dev, njobs);

@@ -23,7 +23,10 @@ namespace tpg {
 constexpr int kRcMaxSlots = 16;
 constexpr int kRowConvThreads = kConvThreads;   // warps 4..11 are the epilogue (two per TMEM lane quarter, alternating 16-column groups)
 
+template <bool BF16>
 __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __grid_constant__ RowConvParams P, int* status) {
+  using Op = Opnd<BF16>;
+  constexpr int CH = Op::kChunk;   // channels per 128-byte K chunk
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kRcMaxSlots];
   __shared__ __align__(8) uint64_t a_empty[kRcMaxSlots];
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
           auto load_slab = [&]() -> bool {
             if (!mbar_wait_a(ae0 + 8u * as_, aph ^ 1u, ac, 21)) return false;
             mbar_arrive_expect_tx_a(af0 + 8u * as_, slab_tx);
-            tma_load_4d_a(smem_a + (uint32_t)as_ * slab_bytes, &P.amap, af0 + 8u * as_, c * 32, P.dx0, y_in0 + next_slab, n);
+            tma_load_4d_a(smem_a + (uint32_t)as_ * slab_bytes, &P.amap, af0 + 8u * as_, c * CH, P.dx0, y_in0 + next_slab, n);
             ++next_slab;
             if (++as_ == AS) { as_ = 0; aph ^= 1u; }
             return true;
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
             for (int j = 0; j < k; ++j) {
               if (!mbar_wait_a(be0 + 8u * bs_, bph ^ 1u, ac, 22)) { ok = false; break; }
               mbar_arrive_expect_tx_a(bf0 + 8u * bs_, (uint32_t)P.block_n * 128u);
-              tma_load_3d_a(smem_b + (uint32_t)bs_ * b_bytes, &P.bmap, bf0 + 8u * bs_, c * 32, bn0, P.wtap[r * k + j]);
+              tma_load_3d_a(smem_b + (uint32_t)bs_ * b_bytes, &P.bmap, bf0 + 8u * bs_, c * CH, bn0, P.wtap[r * k + j]);
               if (++bs_ == BS) { bs_ = 0; bph ^= 1u; }
             }
             if (ok && next_slab < nslab) ok = load_slab();
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
       uint32_t tph = 0;
       bool ok = true;
       const uint32_t dhi = desc_hi(1024, 2);
-      const uint32_t idesc = make_idesc_tf32(128, P.block_n, 0, 0);
+      const uint32_t idesc = Op::idesc(128, P.block_n, 0, 0);
       const uint32_t a_lo0 = desc_lo(smem_a, 16), b_lo0 = desc_lo(smem_b, 16);
       const uint32_t slab16 = slab_bytes >> 4, b16 = b_bytes >> 4;
       for (int tile = blockIdx.x; ok && tile < P.total_tiles; tile += gridDim.x) {
@@ -149,13 +152,13 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
                 const uint32_t a_lo = a_lo0 + (uint32_t)slot * slab16 + a_off;
                 const uint32_t d = d0 + (uint32_t)(t * P.block_n);
                 if (nm == 4) {
-                  mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, first);
-                  mma_tf32_ss(d, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
-                  mma_tf32_ss(d, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
-                  mma_tf32_ss(d, desc_join(a_lo + 6, dhi), desc_join(b_lo + 6, dhi), idesc, 1);
+                  Op::mma(d, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, first);
+                  Op::mma(d, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
+                  Op::mma(d, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
+                  Op::mma(d, desc_join(a_lo + 6, dhi), desc_join(b_lo + 6, dhi), idesc, 1);
                 } else {
                   for (int q = 0; q < nm; ++q)
-                    mma_tf32_ss(d, desc_join(a_lo + 2 * q, dhi), desc_join(b_lo + 2 * q, dhi), idesc, q ? 1u : first);
+                    Op::mma(d, desc_join(a_lo + 2 * q, dhi), desc_join(b_lo + 2 * q, dhi), idesc, q ? 1u : first);
                 }
                 if (++slot == AS) slot = 0;
               }
@@ -199,12 +202,14 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
         const float* p1 = P.add1.ptr ? P.add1.ptr + (long long)n * P.add1.sn + (long long)y * P.add1.sh + (long long)x * P.add1.sw : nullptr;
         const float* p2 = P.add2.ptr ? P.add2.ptr + (long long)n * P.add2.sn + (long long)y * P.add2.sh + (long long)x * P.add2.sw : nullptr;
         const float* pm = P.mask.ptr ? P.mask.ptr + (long long)n * P.mask.sn + (long long)y * P.mask.sh + (long long)x * P.mask.sw : nullptr;
+        uint16_t* po16 = P.out16.ptr ? P.out16.ptr + (long long)n * P.out16.sn + (long long)y * P.out16.sh + (long long)x * P.out16.sw : nullptr;
+        if (!P.out.ptr) po = nullptr;
         const uint32_t t_addr = tmem_base + (uint32_t)(buf * 256 + t * P.block_n) + ((uint32_t)(q * 32) << 16);
         for (int c0 = ((warp - 4) >> 2) * 16; c0 < P.block_n; c0 += 16 * kEpiPerQuarter) {
           uint32_t r[16];
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
-          if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm);
+          if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm, po16);
         }
       }
       tc_fence_before();
@@ -218,5 +223,8 @@ __global__ void __launch_bounds__(kRowConvThreads, 1) rowconv_kernel(const __gri
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
+
+template __global__ void rowconv_kernel<false>(const __grid_constant__ RowConvParams, int*);
+template __global__ void rowconv_kernel<true>(const __grid_constant__ RowConvParams, int*);
 
 }  // namespace tpg

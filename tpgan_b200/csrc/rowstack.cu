@@ -23,7 +23,10 @@ namespace tpg {
 
 constexpr int kRsMaxSlots = 16;
 
+template <bool BF16>
 __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_constant__ RowStackParams P, int* status) {
+  using Op = Opnd<BF16>;
+  constexpr int CH = Op::kChunk / 2;   // channels per 64-byte K chunk (16 tf32 / 32 bf16)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kRsMaxSlots];
   __shared__ __align__(8) uint64_t a_empty[kRsMaxSlots];
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
         mbar_arrive_expect_tx_a(bf0 + 8u * bs_, box_bytes * (uint32_t)k);
         const uint32_t dst = smem_b + (uint32_t)bs_ * wb_bytes;
         for (int i = 0; i < k; ++i)   // stack order: vertical tap r = k-1 first
-          tma_load_3d_a(dst + (uint32_t)i * box_bytes, &P.bmap, bf0 + 8u * bs_, c * 16, bn0, P.wtap[(k - 1 - i) * k + j]);
+          tma_load_3d_a(dst + (uint32_t)i * box_bytes, &P.bmap, bf0 + 8u * bs_, c * CH, bn0, P.wtap[(k - 1 - i) * k + j]);
         if (++bs_ == BS) { bs_ = 0; bph ^= 1u; }
         return true;
       };
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
           for (int s = 0; ok && s < nslab; ++s) {
             if (!mbar_wait_a(ae0 + 8u * as_, aph ^ 1u, ac, 32)) { ok = false; break; }
             mbar_arrive_expect_tx_a(af0 + 8u * as_, slab_tx);
-            tma_load_4d_a(smem_a + (uint32_t)as_ * slab_bytes, &P.amap, af0 + 8u * as_, c * 16, P.dx0, y_in0 + s, n);
+            tma_load_4d_a(smem_a + (uint32_t)as_ * slab_bytes, &P.amap, af0 + 8u * as_, c * CH, P.dx0, y_in0 + s, n);
             if (++as_ == AS) { as_ = 0; aph ^= 1u; }
           }
           for (int j = 1; ok && j < k; ++j) ok = load_stack(c, j, 0);
@@ -147,18 +150,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
                 const int t_lo = max(0, s - k + 1);
                 const int t_acc_hi = fresh ? s - 1 : min(T - 1, s);
                 if (t_acc_hi >= t_lo) {
-                  const uint32_t idesc = make_idesc_tf32(128, (t_acc_hi - t_lo + 1) * N, 0, 0);
+                  const uint32_t idesc = Op::idesc(128, (t_acc_hi - t_lo + 1) * N, 0, 0);
                   const uint32_t bb = b_lo + P.s_boff[s];
                   const uint32_t d = d0 + P.s_doff[s];
-                  mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(bb, dhi), idesc, 1);
-                  if (two) mma_tf32_ss(d, desc_join(a_lo + 2, dhi), desc_join(bb + 2, dhi), idesc, 1);
+                  Op::mma(d, desc_join(a_lo, dhi), desc_join(bb, dhi), idesc, 1);
+                  if (two) Op::mma(d, desc_join(a_lo + 2, dhi), desc_join(bb + 2, dhi), idesc, 1);
                 }
                 if (fresh) {
-                  const uint32_t idesc = make_idesc_tf32(128, N, 0, 0);
+                  const uint32_t idesc = Op::idesc(128, N, 0, 0);
                   const uint32_t bb = b_lo + (uint32_t)(k - 1) * nrow16;   // vertical tap r = 0
                   const uint32_t d = d0 + (uint32_t)(s * N);
-                  mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(bb, dhi), idesc, 0);
-                  if (two) mma_tf32_ss(d, desc_join(a_lo + 2, dhi), desc_join(bb + 2, dhi), idesc, 1);
+                  Op::mma(d, desc_join(a_lo, dhi), desc_join(bb, dhi), idesc, 0);
+                  if (two) Op::mma(d, desc_join(a_lo + 2, dhi), desc_join(bb + 2, dhi), idesc, 1);
                 }
                 a_off += slab16;
                 if (a_off >= ring16) a_off -= ring16;
@@ -175,8 +178,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
                 const uint32_t idesc = P.s_idesc[s];
                 const uint32_t bb = b_lo + P.s_boff[s];
                 const uint32_t d = d0 + P.s_doff[s];
-                mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(bb, dhi), idesc, 1);
-                if (two) mma_tf32_ss(d, desc_join(a_lo + 2, dhi), desc_join(bb + 2, dhi), idesc, 1);
+                Op::mma(d, desc_join(a_lo, dhi), desc_join(bb, dhi), idesc, 1);
+                if (two) Op::mma(d, desc_join(a_lo + 2, dhi), desc_join(bb + 2, dhi), idesc, 1);
                 if (last) tc_commit_a(ae);                       // last use of this slab
                 a_off += slab16;
                 if (a_off >= ring16) a_off -= ring16;
@@ -218,12 +221,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
         const float* p1 = P.add1.ptr ? P.add1.ptr + (long long)n * P.add1.sn + (long long)y * P.add1.sh + (long long)x * P.add1.sw : nullptr;
         const float* p2 = P.add2.ptr ? P.add2.ptr + (long long)n * P.add2.sn + (long long)y * P.add2.sh + (long long)x * P.add2.sw : nullptr;
         const float* pm = P.mask.ptr ? P.mask.ptr + (long long)n * P.mask.sn + (long long)y * P.mask.sh + (long long)x * P.mask.sw : nullptr;
+        uint16_t* po16 = P.out16.ptr ? P.out16.ptr + (long long)n * P.out16.sn + (long long)y * P.out16.sh + (long long)x * P.out16.sw : nullptr;
+        if (!P.out.ptr) po = nullptr;
         const uint32_t t_addr = tmem_base + (uint32_t)(buf * 256 + t * N) + ((uint32_t)(q * 32) << 16);
         for (int c0 = ((warp - 4) >> 2) * 16; c0 < N; c0 += 16 * kEpiPerQuarter) {
           uint32_t r[16];
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
-          if (valid) epilogue_store16(r, E, c0, po, p1, p2, pm);
+          if (valid) epilogue_store16(r, E, c0, po, p1, p2, pm, po16);
         }
       }
       tc_fence_before();
@@ -237,5 +242,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
+
+template __global__ void rowstack_kernel<false>(const __grid_constant__ RowStackParams, int*);
+template __global__ void rowstack_kernel<true>(const __grid_constant__ RowStackParams, int*);
 
 }  // namespace tpg

@@ -51,8 +51,10 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
   return tc;
 }
 
-template <class Params>
+template <class Params, bool BF16>
 __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __grid_constant__ Params P, int* status) {
+  using Op = Opnd<BF16>;
+  constexpr int CH = Op::kChunk;   // channels per 128-byte K chunk
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -119,11 +121,11 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
             const uint32_t sb = sa + a_region;
             const bool two = (kst > 1) && (c + 1 < kchunks);
             mbar_arrive_expect_tx_a(fb, two ? 2u * chunk_tx : chunk_tx);
-            tma_load_4d_a(sa, am, fb, c * 32, ax, ay, tc.n0);
-            tma_load_3d_a(sb, bm, fb, c * 32, bn0, wt);
+            tma_load_4d_a(sa, am, fb, c * CH, ax, ay, tc.n0);
+            tma_load_3d_a(sb, bm, fb, c * CH, bn0, wt);
             if (two) {
-              tma_load_4d_a(sa + kAStageBytes, am, fb, c * 32 + 32, ax, ay, tc.n0);
-              tma_load_3d_a(sb + b_chunk, bm, fb, c * 32 + 32, bn0, wt);
+              tma_load_4d_a(sa + kAStageBytes, am, fb, c * CH + CH, ax, ay, tc.n0);
+              tma_load_3d_a(sb + b_chunk, bm, fb, c * CH + CH, bn0, wt);
             }
             sa += stage_bytes; fb += 8; eb += 8;
             if (++stage == S) { stage = 0; phase ^= 1u; sa = smem_base; fb = full0; eb = empty0; }
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
         const TapGemmGroup& G = P.g[tc.gi];
         if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 2)) break;
         tc_fence_after();
-        const uint32_t idesc = make_idesc_tf32(128, G.block_n, 0, 0);
+        const uint32_t idesc = Op::idesc(128, G.block_n, 0, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccCols);
         const int ntap = G.phase[tc.ph].tap_count;
         const int kchunks = G.kchunks;
@@ -162,16 +164,16 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
             tc_fence_after();
             const uint32_t b_lo = a_lo + areg16;
             if (c < last_c) {  // a full stage: kst * 4 MMAs
-              mma_tf32_ss(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
-              mma_tf32_ss(d_tmem, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
-              mma_tf32_ss(d_tmem, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
-              mma_tf32_ss(d_tmem, desc_join(a_lo + 6, dhi), desc_join(b_lo + 6, dhi), idesc, 1);
+              Op::mma(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
+              Op::mma(d_tmem, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
+              Op::mma(d_tmem, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
+              Op::mma(d_tmem, desc_join(a_lo + 6, dhi), desc_join(b_lo + 6, dhi), idesc, 1);
               if (kst > 1) {
                 const uint32_t a2 = a_lo + (kAStageBytes >> 4), b2 = b_lo + b16;
-                mma_tf32_ss(d_tmem, desc_join(a2, dhi), desc_join(b2, dhi), idesc, 1);
-                mma_tf32_ss(d_tmem, desc_join(a2 + 2, dhi), desc_join(b2 + 2, dhi), idesc, 1);
-                mma_tf32_ss(d_tmem, desc_join(a2 + 4, dhi), desc_join(b2 + 4, dhi), idesc, 1);
-                mma_tf32_ss(d_tmem, desc_join(a2 + 6, dhi), desc_join(b2 + 6, dhi), idesc, 1);
+                Op::mma(d_tmem, desc_join(a2, dhi), desc_join(b2, dhi), idesc, 1);
+                Op::mma(d_tmem, desc_join(a2 + 2, dhi), desc_join(b2 + 2, dhi), idesc, 1);
+                Op::mma(d_tmem, desc_join(a2 + 4, dhi), desc_join(b2 + 4, dhi), idesc, 1);
+                Op::mma(d_tmem, desc_join(a2 + 6, dhi), desc_join(b2 + 6, dhi), idesc, 1);
               }
             } else {
 #pragma unroll
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
                   const uint32_t off = (uint32_t)(m & 3) * 2u;
                   const uint32_t aj = a_lo + off + ((m >> 2) ? (kAStageBytes >> 4) : 0u);
                   const uint32_t bj = b_lo + off + ((m >> 2) ? b16 : 0u);
-                  mma_tf32_ss(d_tmem, desc_join(aj, dhi), desc_join(bj, dhi), idesc, m ? 1u : acc);
+                  Op::mma(d_tmem, desc_join(aj, dhi), desc_join(bj, dhi), idesc, m ? 1u : acc);
                 }
               }
             }
@@ -220,6 +222,8 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
       const float* p1 = G.add1.ptr ? G.add1.ptr + (long long)n * G.add1.sn + (long long)yo * G.add1.sh + (long long)xo * G.add1.sw : nullptr;
       const float* p2 = G.add2.ptr ? G.add2.ptr + (long long)n * G.add2.sn + (long long)yo * G.add2.sh + (long long)xo * G.add2.sw : nullptr;
       const float* pm = G.mask.ptr ? G.mask.ptr + (long long)n * G.mask.sn + (long long)yo * G.mask.sh + (long long)xo * G.mask.sw : nullptr;
+      uint16_t* po16 = G.out16.ptr ? G.out16.ptr + (long long)n * G.out16.sn + (long long)yo * G.out16.sh + (long long)xo * G.out16.sw : nullptr;
+      if (!G.out.ptr) po = nullptr;
       const uint32_t t_addr = tmem_base + (uint32_t)(as * kAccCols) + ((uint32_t)(q * 32) << 16);
       const int col_base = tc.nt * G.block_n;
       const EpiArgs E{G.bias, G.slopes, G.cout_valid, G.epilogue, G.round_tf32, G.vec_ok, G.slope};
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
         uint32_t r[16];
         tmem_ld16(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm);
+        if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm, po16);
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
@@ -243,7 +247,9 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
 }
 
 // explicit instantiations used by api.cu
-template __global__ void tapgemm_kernel<TapGemmParams>(const __grid_constant__ TapGemmParams, int*);
-template __global__ void tapgemm_kernel<TapGemmParams1>(const __grid_constant__ TapGemmParams1, int*);
+template __global__ void tapgemm_kernel<TapGemmParams, false>(const __grid_constant__ TapGemmParams, int*);
+template __global__ void tapgemm_kernel<TapGemmParams1, false>(const __grid_constant__ TapGemmParams1, int*);
+template __global__ void tapgemm_kernel<TapGemmParams, true>(const __grid_constant__ TapGemmParams, int*);
+template __global__ void tapgemm_kernel<TapGemmParams1, true>(const __grid_constant__ TapGemmParams1, int*);
 
 }  // namespace tpg

@@ -79,8 +79,13 @@ __device__ __forceinline__ int slab_group_ntap(const WgradGroup& G, int tap0) {
   return n;
 }
 
-template <class Params>
+template <class Params, bool BF16>
 __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_constant__ Params P, int* status) {
+  using Op = Opnd<BF16>;
+  constexpr int CH = Op::kChunk;        // channels per 128-byte row of an MN-major operand chunk (32 tf32 / 64 bf16)
+  constexpr int MCH = 128 / CH;         // chunks that make up the M = 128 rows of one accumulator
+  constexpr int KR = Op::kMmaK;         // pixel rows (GEMM K) per MMA
+  constexpr uint32_t KSTEP16 = (uint32_t)KR * 128u / 16u;   // descriptor advance per MMA (16-byte units)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -143,11 +148,11 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
         const CUtensorMap* pm = &G.pmap;
         const int mt0 = u.mg * G.mpu;
         const int pc0 = mt0 * 128;
-        const int mch = min(4 * G.mpu, (G.m_valid - pc0 + 31) / 32);        // P chunks of this unit (all its M tiles)
+        const int mch = min(MCH * G.mpu, (G.m_valid - pc0 + CH - 1) / CH);   // P chunks of this unit (all its M tiles)
         const int tap0 = u.tg * G.tpu;
         const int ntap = min(G.tpu, G.ntaps - tap0);
         const int qc0 = (G.tpu > 1 || G.slab) ? 0 : u.nt * G.block_n;
-        const int ncpt = (G.tpu > 1 || G.slab) ? G.ncpt : min(G.block_n / 32, (G.n_valid - qc0 + 31) / 32);
+        const int ncpt = (G.tpu > 1 || G.slab) ? G.ncpt : min(G.block_n / CH, (G.n_valid - qc0 + CH - 1) / CH);
         const uint32_t box_bytes = (uint32_t)(G.bw * G.bh * G.bn) * 128u;
         const bool slab = G.slab != 0;
         const uint32_t q_stride = (uint32_t)G.q_chunk_bytes;
@@ -168,19 +173,19 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
           if (!mbar_wait_a(eb, phase ^ 1u, ac, 11)) { ok = false; break; }
           uint32_t sb = sa + (uint32_t)P.a_stage_bytes;
           mbar_arrive_expect_tx_a(fb, tx);
-          for (int i = 0; i < mch; ++i) tma_load_4d_a(sa + (uint32_t)i * chunk_stride, pm, fb, pc0 + i * 32, x0, y0, n0);
+          for (int i = 0; i < mch; ++i) tma_load_4d_a(sa + (uint32_t)i * chunk_stride, pm, fb, pc0 + i * CH, x0, y0, n0);
           if (slab) {
             for (int i = 0; i < ncpt; ++i)
-              tma_load_4d_a(sb + (uint32_t)i * q_stride, &G.qslab, fb, i * 32, x0 + tdx0, y0 + tdy0, n0);
+              tma_load_4d_a(sb + (uint32_t)i * q_stride, &G.qslab, fb, i * CH, x0 + tdx0, y0 + tdy0, n0);
           } else if (single_tap) {
             for (int i = 0; i < ncpt; ++i)
-              tma_load_4d_a(sb + (uint32_t)i * chunk_stride, qm0, fb, qc0 + i * 32, x0 + tdx0, y0 + tdy0, n0);
+              tma_load_4d_a(sb + (uint32_t)i * chunk_stride, qm0, fb, qc0 + i * CH, x0 + tdx0, y0 + tdy0, n0);
           } else {
             for (int t = 0; t < ntap; ++t) {
               const TapDesc tap = taps[t];
               const CUtensorMap* qm = &G.qmap[tap.plane];
               for (int i = 0; i < ncpt; ++i) {
-                tma_load_4d_a(sb, qm, fb, qc0 + i * 32, x0 + tap.dx, y0 + tap.dy, n0);
+                tma_load_4d_a(sb, qm, fb, qc0 + i * CH, x0 + tap.dx, y0 + tap.dy, n0);
                 sb += chunk_stride;
               }
             }
@@ -199,7 +204,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
       int as = 0;
       uint32_t aphase = 0;
       bool ok = true;
-      const uint32_t dhi = desc_hi(512, 1);
+      // MN-major operands: tf32 = 32-byte-atom 128B swizzle (layout type 1, 4-row K atoms of 512 B); bf16 = plain 128B
+      // swizzle (layout type 2, 8-row K atoms of 1024 B)
+      const uint32_t dhi = BF16 ? desc_hi(1024, 2) : desc_hi(512, 1);
       const uint32_t stage16 = stage_bytes >> 4, areg16 = (uint32_t)P.a_stage_bytes >> 4;
       uint32_t fb = full0, eb = empty0, sbase16 = (smem_base & 0x3FFFFu) >> 4;
       const uint32_t sbase16_0 = sbase16;
@@ -209,19 +216,19 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
         const WgradGroup& G = P.g[u.gi];
         if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 12)) break;
         tc_fence_after();
-        const uint32_t idesc = make_idesc_tf32(128, G.block_n, 1, 1);
+        const uint32_t idesc = Op::idesc(128, G.block_n, 1, 1);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kWAccCols);
         const uint32_t chunk16 = ((uint32_t)G.kp * 128u) >> 4;
         const uint32_t lbo_field = (chunk16 & 0x3FFFu) << 16;
-        const int kgroups = G.kp / 8;
+        const int kgroups = G.kp / KR;
         const int nm = min(G.mpu, G.m_tiles - u.mg * G.mpu);   // M tiles (accumulators) of this unit
         const int c_begin = u.c_begin, c_end = u.c_end;
         // slab mode constants of this segment (hoisted: the issuing thread is the critical resource)
         const int s_ntap = G.slab ? slab_group_ntap(G, u.tg * G.tpu) : 0;
-        const uint32_t idesc_s = make_idesc_tf32(128, s_ntap * 32, 1, 1);
+        const uint32_t idesc_s = Op::idesc(128, s_ntap * CH, 1, 1);
         const uint32_t qchunk16 = (uint32_t)G.q_chunk_bytes >> 4;
         const int s_ncpt = G.ncpt;
-        const uint32_t s_dstep = (uint32_t)(G.tpu * 32);
+        const uint32_t s_dstep = (uint32_t)(G.tpu * CH);
         const bool is_slab = G.slab != 0;
         uint32_t acc = 0;
         for (int c = c_begin; c < c_end; ++c) {
@@ -234,34 +241,34 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
             const uint32_t bs_lo = (sbase16 + areg16) | (8u << 16);
             uint32_t d = d_tmem;
             for (int mi = 0; mi < nm; ++mi) {
-              const uint32_t a_lo = (sbase16 + (uint32_t)mi * 4u * chunk16) | lbo_field;
+              const uint32_t a_lo = (sbase16 + (uint32_t)mi * (uint32_t)MCH * chunk16) | lbo_field;
               uint32_t bi_lo = bs_lo;
               for (int i = 0; i < s_ncpt; ++i) {
-                mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(bi_lo, dhi), idesc_s, acc);
+                Op::mma(d, desc_join(a_lo, dhi), desc_join(bi_lo, dhi), idesc_s, acc);
                 for (int k = 1; k < kgroups; ++k)
-                  mma_tf32_ss(d, desc_join(a_lo + 64 * k, dhi), desc_join(bi_lo + 64 * k, dhi), idesc_s, 1);
+                  Op::mma(d, desc_join(a_lo + KSTEP16 * k, dhi), desc_join(bi_lo + KSTEP16 * k, dhi), idesc_s, 1);
                 d += s_dstep;
                 bi_lo += qchunk16;
               }
             }
           } else if (nm == 1 && kgroups == 8) {
             const uint32_t a_lo = sbase16 | lbo_field;
-            mma_tf32_ss(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
+            Op::mma(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
 #pragma unroll
             for (int k = 1; k < 8; ++k)
-              mma_tf32_ss(d_tmem, desc_join(a_lo + 64 * k, dhi), desc_join(b_lo + 64 * k, dhi), idesc, 1);
+              Op::mma(d_tmem, desc_join(a_lo + KSTEP16 * k, dhi), desc_join(b_lo + KSTEP16 * k, dhi), idesc, 1);
           } else
           for (int mi = 0; mi < nm; ++mi) {
-            const uint32_t a_lo = (sbase16 + (uint32_t)mi * 4u * chunk16) | lbo_field;
+            const uint32_t a_lo = (sbase16 + (uint32_t)mi * (uint32_t)MCH * chunk16) | lbo_field;
             const uint32_t d = d_tmem + (uint32_t)(mi * G.block_n);
             if (kgroups == 4) {
-              mma_tf32_ss(d, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
-              mma_tf32_ss(d, desc_join(a_lo + 64, dhi), desc_join(b_lo + 64, dhi), idesc, 1);
-              mma_tf32_ss(d, desc_join(a_lo + 128, dhi), desc_join(b_lo + 128, dhi), idesc, 1);
-              mma_tf32_ss(d, desc_join(a_lo + 192, dhi), desc_join(b_lo + 192, dhi), idesc, 1);
+              Op::mma(d, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
+              Op::mma(d, desc_join(a_lo + KSTEP16, dhi), desc_join(b_lo + KSTEP16, dhi), idesc, 1);
+              Op::mma(d, desc_join(a_lo + 2 * KSTEP16, dhi), desc_join(b_lo + 2 * KSTEP16, dhi), idesc, 1);
+              Op::mma(d, desc_join(a_lo + 3 * KSTEP16, dhi), desc_join(b_lo + 3 * KSTEP16, dhi), idesc, 1);
             } else {
               for (int k = 0; k < kgroups; ++k)
-                mma_tf32_ss(d, desc_join(a_lo + 64 * k, dhi), desc_join(b_lo + 64 * k, dhi), idesc, k ? 1u : acc);
+                Op::mma(d, desc_join(a_lo + KSTEP16 * k, dhi), desc_join(b_lo + KSTEP16 * k, dhi), idesc, k ? 1u : acc);
             }
           }
           acc = 1;
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
       const bool single = (u.c_begin == 0) && (u.c_end == G.chunks) && (G.accumulate == 0);
       const int nm = min(G.mpu, G.m_tiles - u.mg * G.mpu);
       const int tap0 = u.tg * G.tpu;
-      const int cols_per_tap = (G.tpu > 1) ? G.ncpt * 32 : G.block_n;
+      const int cols_per_tap = (G.tpu > 1) ? G.ncpt * CH : G.block_n;
       // 16 accumulator columns of row m -> dw (columns n0 .. n0+15 of tap `tap`)
       auto store16 = [&](const uint32_t (&r)[16], const TapDesc tap, int m, int n0) {
         float* dw = G.dw + (size_t)tap.wtap * G.rows_pad * G.k_pad;
@@ -332,18 +339,20 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
         for (int mi = 0; mi < nm; ++mi) {
           const int m = (u.mg * G.mpu + mi) * 128 + row;
           const bool mvalid = m < G.m_valid;
-          // 16-column blocks (chunk i, tap t, half h) of this M tile, round-robin over the warps of the quarter
-          const int nblk = G.ncpt * ntap * 2;
+          // 16-column blocks (chunk i, tap t, part h of the chunk's CH columns) of this M tile, round-robin over the warps
+          // of the quarter
+          constexpr int HP = CH / 16;
+          const int nblk = G.ncpt * ntap * HP;
           for (int blk = (warp - 4) >> 2; blk < nblk; blk += kEpiPerQuarter) {
-            const int h = blk & 1;
-            const int t = (blk >> 1) % ntap;
-            const int i = (blk >> 1) / ntap;
-            const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + ((mi * G.ncpt + i) * G.tpu + t) * 32 + h * 16) +
+            const int h = blk % HP;
+            const int t = (blk / HP) % ntap;
+            const int i = (blk / HP) / ntap;
+            const uint32_t t_addr = tmem_base + (uint32_t)(as * kWAccCols + ((mi * G.ncpt + i) * G.tpu + t) * CH + h * 16) +
                                     ((uint32_t)(q * 32) << 16);
             uint32_t r[16];
             tmem_ld16(t_addr, r);
             tmem_ld_wait();
-            if (mvalid && i * 32 + h * 16 < G.n_valid) store16(r, G.taps[tap0 + t], m, i * 32 + h * 16);
+            if (mvalid && i * CH + h * 16 < G.n_valid) store16(r, G.taps[tap0 + t], m, i * CH + h * 16);
           }
         }
       } else
@@ -373,7 +382,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
   if (warp == 2) tmem_dealloc(tmem_base, kWTmemCols);
 }
 
-template __global__ void wgrad_kernel<WgradParams>(const __grid_constant__ WgradParams, int*);
-template __global__ void wgrad_kernel<WgradParams1>(const __grid_constant__ WgradParams1, int*);
+template __global__ void wgrad_kernel<WgradParams, false>(const __grid_constant__ WgradParams, int*);
+template __global__ void wgrad_kernel<WgradParams1, false>(const __grid_constant__ WgradParams1, int*);
+template __global__ void wgrad_kernel<WgradParams, true>(const __grid_constant__ WgradParams, int*);
+template __global__ void wgrad_kernel<WgradParams1, true>(const __grid_constant__ WgradParams1, int*);
 
 }  // namespace tpg

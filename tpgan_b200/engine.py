@@ -47,6 +47,10 @@ class T:
         self.grad_written = False
         self.masked = False
         self.deferred: List[Act] = []            # residual-branch addends waiting for a conv contribution
+        # bf16 operand mode: is the bf16 twin of the activation / of its gradient up to date?  (tensor-core epilogues write
+        # both copies; any other writer leaves the twin stale and the next tensor-core consumer inserts a cast)
+        self.s16 = False
+        self.g16 = False
 
     def leaves(self) -> List["T"]:
         return self.parts if self.parts is not None else [self]
@@ -111,17 +115,21 @@ class ConvLayer:
         self.ready = False
 
     def setup(self, in_cmap: Optional[List[int]], out_cmap: Optional[List[int]], in_c: int, out_c: int, device,
-              need_dgrad: bool = True, exact: bool = False, defer_pack: bool = False):
+              need_dgrad: bool = True, exact: bool = False, defer_pack: bool = False, bf16: bool = False):
         """Allocate packings for the internal channel layouts seen at trace time (idempotent; layouts must not change).
         defer_pack: the caller re-packs all its layers with one multi-tensor launch (LayerSet.repack) right after tracing,
         so the per-layer pack / transpose launches here would be redundant."""
         key = (tuple(in_cmap) if in_cmap else None, tuple(out_cmap) if out_cmap else None, in_c, out_c)
         if self.ready:
             assert key == self._key, f"{self.name}: channel layout changed between traces"
+            assert bf16 == self.bf16, f"{self.name}: a layer serves either tf32 or bf16 plans"
             if exact and self.wf_lo is None:
                 self._alloc_lo()
                 self.repack()
             return
+        assert not (bf16 and exact), "the fp32-exact split mode is a tf32 verification mode"
+        self.bf16 = bf16
+        self.wf16 = self.wd16 = None
         self.wf_lo = self.wd_lo = None
         self._want_lo = exact
         self._key = key
@@ -129,6 +137,9 @@ class ConvLayer:
         self.in_map, self.out_map = mk(in_cmap), mk(out_cmap)
         self.in_c, self.out_c = in_c, out_c  # internal widths (incl. padding lanes when a map is given)
         self._alloc(device, need_dgrad)
+        if bf16:    # bf16 operand copies of the packings (fp32 packings stay: they are the transpose / cast source)
+            self.wf16 = ops.alloc_packed16(self.wf)
+            self.wd16 = ops.alloc_packed16(self.wd) if self.wd is not None else None
         if exact:
             self._alloc_lo()
         nb = round_up(self.bias_len(), 4)
@@ -164,21 +175,36 @@ class ConvLayer:
         return self.weight.data.view(self.w_shape)
 
     def repack(self):
-        """Reference-layout fp32 master weights -> tf32-rounded K-major packings (after every optimizer step)."""
+        """Reference-layout fp32 master weights -> K-major packings (after every optimizer step): tf32-rounded fp32 for the
+        tf32 kernels; un-rounded fp32 + their bf16 copies for the bf16 kernels."""
         if not self.ready:
             return
+        self._repack32()
+        if self.bf16:
+            ops.cast_packed(self.wf, self.wf16)
+            if self.wd is not None:
+                ops.cast_packed(self.wd, self.wd16)
+
+    def cast_jobs(self):
+        """Multi-tensor form of the bf16 copies (LayerSet)."""
+        if not self.bf16:
+            return []
+        return [ops.cast_job(self.wf, self.wf16)] + ([ops.cast_job(self.wd, self.wd16)] if self.wd is not None else [])
+
+    def _repack32(self):
         w = self._w()
+        rt = not self.bf16      # bf16 mode: keep fp32 bits here, round once when casting
         # the packing whose rows follow the reference's leading dimension is a row-contiguous (fast) pack; the other one
         # is its per-tap transpose
         if not self.transposed:
-            ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map)
+            ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map, round_tf32=rt)
             if self.wd is not None:
                 ops.transpose_packed(self.wf, self.wd)
         elif self.wd is not None:
-            ops.pack_weights(w, self.kind_dgrad, self.wd, row_map=self.in_map, k_map=self.out_map)
+            ops.pack_weights(w, self.kind_dgrad, self.wd, row_map=self.in_map, k_map=self.out_map, round_tf32=rt)
             ops.transpose_packed(self.wd, self.wf)
         else:
-            ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map)
+            ops.pack_weights(w, self.kind_fwd, self.wf, row_map=self.out_map, k_map=self.in_map, round_tf32=rt)
         if self.wf_lo is not None:
             ops.pack_weights(w, self.kind_fwd, self.wf_lo, row_map=self.out_map, k_map=self.in_map, round_tf32=2)
             if self.wd_lo is not None:
@@ -213,7 +239,7 @@ class ConvLayer:
     def pack_jobs(self):
         """([pack jobs], [transpose jobs]) re-creating wf / wd / bias_int from the reference-layout parameters."""
         tgt, other, rmap, kmap, row_len = self._row_geometry()
-        packs = [ops.pack_job(self.weight.data, tgt, self.k * self.k, row_len, rmap, kmap, 1)]
+        packs = [ops.pack_job(self.weight.data, tgt, self.k * self.k, row_len, rmap, kmap, 0 if self.bf16 else 1)]
         if self.bias is not None:
             nb = self.bias_int.numel()
             bp = ops.Packed(self._bias_buf, 1, 1, self.out_c, 1, nb)
@@ -333,15 +359,14 @@ class DeconvAsLinear(ConvLayer):
         super()._alloc_lo()
         self._wf_lo_taps = ops.Packed(self.wf_lo.data, self.kk, self.co, self.in_c, self.co, self.in_c)
 
-    def repack(self):
-        if not self.ready:
-            return
+    def _repack32(self):
         w = self.weight.data
-        ops.pack_weights(w, DECONV_FWD, self._wf_taps)
+        rt = 0 if self.bf16 else 1
+        ops.pack_weights(w, DECONV_FWD, self._wf_taps, round_tf32=rt)
         lib = ops._lib.load()
         n = self.kk * self.co
         ops._lib.check(lib.tpgan_pack_weights(w.data_ptr(), self.wd.data.data_ptr(), 1, self.in_c, n, self.wd.rows_pad, n,
-                                              n, 1, None, self._kmap_d.data_ptr(), 1, ops._stream()), "pack deconv_8 dgrad")
+                                              n, 1, None, self._kmap_d.data_ptr(), rt, ops._stream()), "pack deconv_8 dgrad")
         if self.wf_lo is not None:
             ops.pack_weights(w, DECONV_FWD, self._wf_lo_taps, round_tf32=2)
             ops._lib.check(lib.tpgan_pack_weights(w.data_ptr(), self.wd_lo.data.data_ptr(), 1, self.in_c, n,
@@ -363,8 +388,13 @@ class Plan:
     """Traced schedule for one network instance and batch size."""
 
     def __init__(self, device, training: bool = True, need_wgrad: bool = True, exact: bool = False,
-                 defer_bias: bool = False, defer_pack: bool = False):
+                 defer_bias: bool = False, defer_pack: bool = False, bf16: bool = False):
         self.device = device
+        # bf16 operand mode (BASELINE configs[2]): tensor-core operands are the bf16 twins of the activations / activation
+        # gradients (ops.Arena(shadow=True)), written by the conv epilogues next to the fp32 copies that the pointwise
+        # kernels, the masks and the residual / gradient accumulations keep using; fp32 accumulate, fp32 master weights
+        self.bf16 = bf16
+        assert not (bf16 and exact)
         self.defer_pack = defer_pack  # the owner re-packs every layer of this plan in one multi-tensor launch after tracing
         self.defer_bias = defer_bias  # record (layer, dY, ready index) instead of launching one bias-grad kernel per layer
         self.bias_jobs: list = []
@@ -390,8 +420,11 @@ class Plan:
         self.bytes += a.buf.numel() * 4
         return T(a, slope, name, requires_grad)
 
-    def wrap(self, act: Act, slope=LINEAR, name="", requires_grad=True) -> T:
-        return T(act, slope, name, requires_grad)
+    def wrap(self, act: Act, slope=LINEAR, name="", requires_grad=True, s16: bool = False) -> T:
+        """s16: the bf16 twin of `act` is already current (it was written by a tensor-core epilogue of another plan)."""
+        t = T(act, slope, name, requires_grad)
+        t.s16 = s16
+        return t
 
     def concat(self, n, h, w, widths: Sequence[int], name="") -> T:
         """Concat buffer: parts are written in place by their producers (replaces torch.cat, D_and_G_model.py:100...)."""
@@ -399,7 +432,7 @@ class Plan:
         for c in widths:
             offs.append(o)
             o += round_up(c, 4)
-        buf = ops.zeros((n, h, w, o), torch.float32, self.device)
+        buf = ops.zeros((n, h, w, round_up(o, 8) if self.bf16 else o), torch.float32, self.device)
         self.bytes += buf.numel() * 4
         padded = any(c % 4 for c in widths[:-1])
         total_c = o if padded else offs[-1] + widths[-1]
@@ -462,7 +495,8 @@ class Plan:
                 out_cmap = r.cmap
                 out.cmap, out.ref_c = r.cmap, r.ref_c
             out.slope = LINEAR if slope is None else slope
-            L.setup(x.cmap, out_cmap, x.act.c, out.act.c, self.device, exact=self.exact, defer_pack=self.defer_pack)
+            L.setup(x.cmap, out_cmap, x.act.c, out.act.c, self.device, exact=self.exact, defer_pack=self.defer_pack,
+                    bf16=self.bf16)
             if L not in self.layers:
                 self.layers.append(L)
             self.named[L.name] = out
@@ -474,9 +508,34 @@ class Plan:
             if r is not None:
                 self.use(r)
             outs_l.append(out)
+            self._ensure16(x, self.fwd)
         self._emit_conv(args, self.fwd)
+        for out in outs_l:
+            for p in out.leaves():
+                p.s16 = self.bf16
         self.tape.append(lambda: self._bwd_conv(layers, list(xs), outs_l, res))
         return outs_l
+
+    # ------------------------------------------------------------------ bf16 twins
+    def _ensure16(self, t: T, lst):
+        """Make the bf16 twin of activation t current before a tensor-core consumer reads it."""
+        if not self.bf16:
+            return
+        for p in t.leaves():
+            if not p.s16:
+                a = p.act
+                lst.append(_tag(lambda a=a: ops.cast_bf16(a), "cast16", 6.0 * a.n * a.h * a.w * a.c, p.name))
+                p.s16 = True
+
+    def _ensure_g16(self, t: T):
+        """The same for the gradient of t (read by dgrad and wgrad launches as their dY operand)."""
+        if not self.bf16:
+            return
+        for p in t.leaves():
+            if not p.g16:
+                g = self.grad_act(p)
+                self.bwd.append(_tag(lambda g=g: ops.cast_bf16(g), "cast16", 6.0 * g.n * g.h * g.w * g.c, p.name + ".grad"))
+                p.g16 = True
 
     @staticmethod
     def _flops(L, x: Act, out: Act, dgrad: bool) -> float:
@@ -490,13 +549,16 @@ class Plan:
         def mk(sp, x, out, pack, **kw):
             L = sp["L"]
             return ops.conv_args(L.kind_dgrad if sp["dgrad"] else L.kind_fwd, x, out, pack, L.k, L.stride, L.pad,
-                                 round_tf32=(not self.exact) and sp.get("round", True), **kw)
+                                 round_tf32=(not self.exact) and sp.get("round", True), bf16=self.bf16,
+                                 out16=sp.get("out16", True), **kw)
         full = lambda sp: dict(bias=sp.get("bias"), add1=sp.get("add1"), add2=sp.get("add2"), mask=sp.get("mask"),
                                slopes=sp.get("slopes"), slope=sp.get("slope", 0.0), epilogue=sp.get("epilogue", EPI_LINEAR))
         if not self.exact:
-            run = self._conv_launch([mk(sp, sp["x"], sp["out"], sp["L"].wd if sp["dgrad"] else sp["L"].wf, **full(sp))
-                                     for sp in specs], fl, ",".join(sp["L"].name for sp in specs) +
-                                    (":dgrad" if specs[0]["dgrad"] else ":fwd"))
+            # tf32: fp32 activations + tf32-rounded packings; bf16: the bf16 twins of the activations + bf16 packings
+            wpack = (lambda sp: sp["L"].wd16 if sp["dgrad"] else sp["L"].wf16) if self.bf16 else \
+                (lambda sp: sp["L"].wd if sp["dgrad"] else sp["L"].wf)
+            run = self._conv_launch([mk(sp, sp["x"], sp["out"], wpack(sp), **full(sp)) for sp in specs], fl,
+                                    ",".join(sp["L"].name for sp in specs) + (":dgrad" if specs[0]["dgrad"] else ":fwd"))
             sp0, L0 = specs[0], specs[0]["L"]
             pk = L0.wd if sp0["dgrad"] else L0.wf
             if (len(specs) == 1 and not L0.transposed and L0.stride == 1 and 2 * L0.pad == L0.k - 1 and L0.k >= 3
@@ -537,7 +599,7 @@ class Plan:
         """specs: (L, x Act, dy Act) of one grouped weight-gradient launch.  accumulate=False: the launch is the only
         writer of each layer's (cleared) dW this step."""
         acc = accumulate or self.exact
-        mk = lambda L, x, dy: ops.wgrad_args(L.kind_fwd, x, dy, L.dw, L.k, L.stride, L.pad, acc)
+        mk = lambda L, x, dy: ops.wgrad_args(L.kind_fwd, x, dy, L.dw, L.k, L.stride, L.pad, acc, bf16=self.bf16)
         if not self.exact:
             fl = sum(self._flops(L, x, dy, False) for L, x, dy in specs)
             lst.append(self._wgrad_launch([mk(L, x, dy) for L, x, dy in specs], fl, ",".join(L.name for L, _, _ in specs) + ":wgrad"))
@@ -633,6 +695,7 @@ class Plan:
         assert src.act.c0 == 0 and src.act.c == buf.shape[3] and buf.shape[1] * buf.shape[2] * buf.shape[3] == h * w * c
         nbuf = buf.view(n, h, w, c)
         out = T(Act(nbuf, 0, c), LINEAR, name or src.name + ".alias")
+        out.s16 = src.s16           # same storage, same twin
         self.use(src)
         self.keep.append(nbuf)
 
@@ -643,6 +706,7 @@ class Plan:
             assert not src.grad_written, "alias source must have a single consumer"
             src.grad = Act(self.grad_act(out).buf.view(buf.shape), 0, src.act.c)
             src.grad_written = True
+            src.g16 = out.g16
             src.pending -= 1
         # the two T's must share one gradient buffer: allocate it through the alias and view it back
         self.tape.append(bwd)
@@ -679,6 +743,7 @@ class Plan:
             for p in parts:
                 for l in p.leaves():
                     l.grad_written = True
+                    l.g16 = False
                     l.pending -= 1
         self.tape.append(bwd)
         return out
@@ -875,6 +940,7 @@ class Plan:
         self.grad_act(t)
         for p in t.leaves():
             p.grad_written = True
+            p.g16 = False
 
     def trace_backward(self):
         for fn in reversed(self.tape):
@@ -902,6 +968,7 @@ class Plan:
                 self.bwd.append(lambda add=add, dst=dst, acc=acc: ops.view_copy(add, dst, acc))
                 for p in holder.leaves():
                     p.grad_written = True
+                    p.g16 = False
 
     def _zero_unwritten(self, t: T):
         for p in t.leaves():
@@ -909,6 +976,7 @@ class Plan:
                 g = self.grad_act(p)
                 self.bwd.append(lambda g=g: g.buf[..., g.c0:g.c0 + g.c].zero_())
                 p.grad_written = True
+                p.g16 = False
 
     def _finalize(self, t: T):
         """Make t.grad hold d(loss)/d(pre-activation): flush deferred addends, apply the activation mask if nobody fused
@@ -919,6 +987,7 @@ class Plan:
                 g = self.grad_act(p)
                 self.bwd.append(lambda g=g, p=p: ops.act_backward(g, p.act, g, slope=p.slope))
                 p.masked = True
+                p.g16 = False
 
     def _contribute(self, x: T, emit: Callable[[Act, bool], None]):
         """Generic (non-conv) gradient contribution to x: emit(dst, accumulate)."""
@@ -936,6 +1005,7 @@ class Plan:
         self.bwd.append(run)
         for p in leaves:
             p.grad_written = True
+            p.g16 = False
             p.pending -= 1
 
     def _bwd_conv(self, layers, xs: List[T], outs: List[T], res: List[Optional[T]]):
@@ -950,6 +1020,7 @@ class Plan:
             return
         for i in live:
             self._finalize(outs[i])
+            self._ensure_g16(outs[i])     # dY is read by the wgrad and dgrad launches below through its bf16 twin
         # weight / bias gradients
         if self.need_wgrad:
             self._emit_wgrad([(layers[i], xs[i].act, self.grad_act(outs[i])) for i in live], self.bwd, accumulate=False)
@@ -1017,14 +1088,17 @@ class Plan:
                         vec[o:o + p.act.c] = s
                     slope_vec = vec.to(self.device)
                     self.keep.append(slope_vec)
+            conv_written = True
             if getattr(L, "dgrad_gemm", False) and not self.exact:
                 self._emit_dgrad_gemm(L, self.grad_act(outs[i]), dst, adds, mask, slope_vec, slope_val, epi)
+                conv_written = False    # finished by view copies: the bf16 twin of dst is stale
             else:
                 dargs.append(dict(L=L, dgrad=True, x=self.grad_act(outs[i]), out=dst,
                                   add1=adds[0] if len(adds) > 0 else None, add2=adds[1] if len(adds) > 1 else None,
                                   mask=mask, slopes=slope_vec, slope=slope_val, epilogue=epi))
             for p in leaves:
                 p.grad_written = True
+                p.g16 = self.bf16 and conv_written
         if dargs:
             self._emit_conv(dargs, self.bwd)
 
@@ -1040,9 +1114,11 @@ class Plan:
         n = dy.n
         tmp = Act.empty(n, 1, 1, taps * cin, self.device)
         tmp8 = Act(tmp.buf.view(n, L.k, L.k, cin))
+        if self.bf16:
+            wd = L.wd16
         pk = ops.Packed(wd.data, 1, taps * cin, wd.k, taps * cin, wd.k_pad)
         self.keep.append((tmp, tmp8, pk))
-        arg = ops.conv_args(CONV_FWD, dy, tmp, pk, 1, 1, 0, round_tf32=False)
+        arg = ops.conv_args(CONV_FWD, dy, tmp, pk, 1, 1, 0, round_tf32=False, bf16=self.bf16, out16=False)
         fl = 2.0 * n * taps * cin * L.cout
         run = self._conv_launch([arg], fl, L.name + ":dgrad")
         self.bwd.append(run)

@@ -12,8 +12,8 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (CONV_DGRAD, CONV_FWD, DECONV_DGRAD, DECONV_FWD, EPI_LEAKY, EPI_LINEAR, EPI_MASK, NULL_VIEW, ConvArgs,
-                   View, WgradArgs)
+from ._lib import (CONV_DGRAD, CONV_FWD, DECONV_DGRAD, DECONV_FWD, DTYPE_BF16, DTYPE_TF32, EPI_LEAKY, EPI_LINEAR, EPI_MASK,
+                   NULL_VIEW, ConvArgs, View, WgradArgs)
 
 
 def _stream() -> int:
@@ -23,7 +23,7 @@ def _stream() -> int:
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None:
         return None
-    assert t.is_cuda and t.dtype in (torch.float32, torch.int32, torch.uint8), (t.device, t.dtype)
+    assert t.is_cuda and t.dtype in (torch.float32, torch.int32, torch.uint8, torch.bfloat16), (t.device, t.dtype)
     return t.data_ptr()
 
 
@@ -38,11 +38,18 @@ class Arena:
     library runs.  Chunks are ordinary tensors and every allocation is a view of one, so lifetime is plain reference
     counting: a chunk is freed when the last buffer carved out of it dies."""
 
-    def __init__(self, device, chunk_bytes: int = 256 << 20):
-        self.device, self.chunk_bytes = torch.device(device), chunk_bytes
+    def __init__(self, device, chunk_bytes: int = 256 << 20, shadow: bool = False):
+        """shadow=True (bf16 operand mode): every chunk has a bf16 twin of half its size; the twin of an fp32 buffer sits at
+        the SAME ELEMENT OFFSET in it, so any view of the buffer (channel slice, batch slice, reshape) finds its bf16 operand
+        copy by pointer arithmetic with unchanged element strides (Act.view16)."""
+        self.device, self.chunk_bytes, self.shadow = torch.device(device), chunk_bytes, shadow
         self.chunk: Optional[torch.Tensor] = None
         self.used = 0
         self.total = 0
+        self.twins: list = []     # (fp32 chunk base pointer, bytes, bf16 twin, chunk) of every shadowed chunk
+        if shadow:
+            import weakref
+            _SHADOWS.append(weakref.ref(self))
 
     def alloc(self, shape, dtype=torch.float32) -> torch.Tensor:
         n = 1
@@ -52,6 +59,9 @@ class Arena:
         if self.chunk is None or self.used + nbytes > self.chunk.numel():
             self.chunk = torch.zeros(max(self.chunk_bytes, nbytes), dtype=torch.uint8, device=self.device)
             self.used = 0
+            if self.shadow:
+                twin = torch.zeros(self.chunk.numel() // 2, dtype=torch.uint8, device=self.device)
+                self.twins.append((self.chunk.data_ptr(), self.chunk.numel(), twin, self.chunk))
         o = self.used
         self.used += nbytes
         self.total += nbytes
@@ -59,6 +69,28 @@ class Arena:
 
 
 _ARENA: List[Arena] = []
+_SHADOWS: list = []     # weak references to the shadowed arenas alive (a bf16 trainer owns one)
+
+
+def _find_twin(ptr: int):
+    dead = False
+    for ref in _SHADOWS:
+        a = ref()
+        if a is None:
+            dead = True
+            continue
+        for base, nbytes, twin, _ in a.twins:
+            if base <= ptr < base + nbytes:
+                return base, twin
+    if dead:
+        _SHADOWS[:] = [r for r in _SHADOWS if r() is not None]
+    raise RuntimeError("tpgan_b200: buffer has no bf16 twin (allocate it inside use_arena(Arena(shadow=True)))")
+
+
+def shadow_ptr(ptr: int) -> int:
+    """Address of the bf16 twin of the fp32 element at device address `ptr` (must lie in a shadowed arena chunk)."""
+    base, twin = _find_twin(ptr)
+    return twin.data_ptr() + (ptr - base) // 2
 
 
 class use_arena:
@@ -99,7 +131,9 @@ class Act:
 
     @staticmethod
     def empty(n: int, h: int, w: int, c: int, device="cuda", zero: bool = True) -> "Act":
-        cs = round_up(c, 4)
+        # channel stride: 16-byte pixels for fp32 (TMA rows); in a shadowed (bf16) arena 8 channels, so that the bf16 twin's
+        # pixel stride is a multiple of 16 bytes as well
+        cs = round_up(c, 8 if (_ARENA and _ARENA[-1].shadow) else 4)
         buf = zeros((n, h, w, cs), torch.float32, device) if (zero or _ARENA) else \
             torch.empty((n, h, w, cs), dtype=torch.float32, device=device)
         return Act(buf, 0, c)
@@ -122,6 +156,18 @@ class Act:
     def view(self) -> View:
         n, h, w, cs = self.buf.shape
         return View(self.buf.data_ptr() + 4 * self.c0, h * w * cs, w * cs, cs, n, h, w, self.c)
+
+    def view16(self) -> View:
+        """The bf16 twin of this view (same element strides; ptr addresses 2-byte elements)."""
+        n, h, w, cs = self.buf.shape
+        return View(shadow_ptr(self.buf.data_ptr() + 4 * self.c0), h * w * cs, w * cs, cs, n, h, w, self.c)
+
+    def twin(self) -> torch.Tensor:
+        """The bf16 twin as a torch tensor of this view's logical shape (N, H, W, c) - tests / debugging."""
+        n, h, w, cs = self.buf.shape
+        p = self.buf.data_ptr() + 4 * self.c0
+        base, tw = _find_twin(p)
+        return torch.as_strided(tw.view(torch.bfloat16), (n, h, w, self.c), (h * w * cs, w * cs, cs, 1), (p - base) // 4)
 
     def like(self, zero: bool = True) -> "Act":
         return Act.empty(self.n, self.h, self.w, self.c, self.buf.device, zero)
@@ -218,9 +264,20 @@ def transpose_packed(src: Packed, dst: Packed) -> None:
 def conv_args(kind: int, x: Act, out: Act, w: Packed, k: int, stride: int, pad: int, bias: Optional[torch.Tensor] = None,
               add1: Optional[Act] = None, add2: Optional[Act] = None, mask: Optional[Act] = None,
               slopes: Optional[torch.Tensor] = None, slope: float = 0.0, epilogue: int = EPI_LINEAR,
-              round_tf32: bool = True) -> ConvArgs:
-    return ConvArgs(kind, k, k, stride, pad, x.view(), out.view(), w.data.data_ptr(), w.rows_pad, w.k_pad, _ptr(bias),
-                    _v(add1), _v(add2), _v(mask), _ptr(slopes), float(slope), epilogue, int(round_tf32))
+              round_tf32: bool = True, bf16: bool = False, out16: bool = True, out32: bool = True) -> ConvArgs:
+    """bf16=True: x is read through its bf16 twin, `w` is a bf16 packing (Packed.data of dtype bfloat16), the result is
+    written to out (fp32, unless out32=False) and to out's bf16 twin (unless out16=False)."""
+    if not bf16:
+        return ConvArgs(kind, k, k, stride, pad, x.view(), out.view(), w.data.data_ptr(), w.rows_pad, w.k_pad, _ptr(bias),
+                        _v(add1), _v(add2), _v(mask), _ptr(slopes), float(slope), epilogue, int(round_tf32), DTYPE_TF32,
+                        NULL_VIEW)
+    assert w.data.dtype == torch.bfloat16 and (out16 or out32)
+    ov = out.view()
+    if not out32:
+        ov.ptr = None
+    return ConvArgs(kind, k, k, stride, pad, x.view16(), ov, w.data.data_ptr(), w.rows_pad, w.k_pad, _ptr(bias),
+                    _v(add1), _v(add2), _v(mask), _ptr(slopes), float(slope), epilogue, 0, DTYPE_BF16,
+                    out.view16() if out16 else NULL_VIEW)
 
 
 def conv2d_grouped(args: List[ConvArgs]) -> None:
@@ -232,9 +289,34 @@ def conv2d(*a, **kw) -> None:
     conv2d_grouped([conv_args(*a, **kw)])
 
 
-def wgrad_args(kind: int, x: Act, dy: Act, dw: Packed, k: int, stride: int, pad: int, accumulate: bool = True) -> WgradArgs:
+def wgrad_args(kind: int, x: Act, dy: Act, dw: Packed, k: int, stride: int, pad: int, accumulate: bool = True,
+               bf16: bool = False) -> WgradArgs:
+    if bf16:    # operands = the bf16 twins of x and dy; dw stays the fp32 forward-packed accumulator
+        return WgradArgs(kind, k, k, stride, pad, x.view16(), dy.view16(), dw.data.data_ptr(), dw.rows_pad, dw.k_pad,
+                         int(accumulate), DTYPE_BF16)
     return WgradArgs(kind, k, k, stride, pad, x.view(), dy.view(), dw.data.data_ptr(), dw.rows_pad, dw.k_pad,
-                     int(accumulate))
+                     int(accumulate), DTYPE_TF32)
+
+
+def cast_bf16(a: Act) -> None:
+    """bf16 twin of `a` <- rne(a): operand copy of a tensor that no tensor-core epilogue wrote."""
+    _lib.check(_lib.load().tpgan_cast_bf16(a.view(), a.view16(), _stream()), "cast_bf16")
+
+
+def alloc_packed16(pk: Packed) -> Packed:
+    """bf16 operand copy of a packing: [taps+1][rows_pad][k_pad16], k_pad16 = k_pad rounded up to 64."""
+    k16 = round_up(pk.k_pad, 64)
+    data = zeros((pk.data.shape[0], pk.rows_pad, k16), torch.bfloat16, pk.data.device)
+    return Packed(data, pk.taps, pk.rows, pk.k, pk.rows_pad, k16)
+
+
+def cast_job(src: Packed, dst: Packed) -> "_lib.CastJob":
+    assert dst.data.dtype == torch.bfloat16 and src.rows_pad == dst.rows_pad and src.data.shape[0] == dst.data.shape[0]
+    return _lib.CastJob(src.data.data_ptr(), dst.data.data_ptr(), src.data.shape[0] * src.rows_pad, src.k_pad, dst.k_pad, 0, 0)
+
+
+def cast_packed(src: Packed, dst: Packed) -> None:
+    JobTable("cast", [cast_job(src, dst)], src.data.device).run()
 
 
 def wgrad_grouped(args: List[WgradArgs]) -> None:
@@ -388,6 +470,8 @@ class JobTable:
             j.block_begin = self.blocks
             if kind == "bias":
                 self.blocks += j.pix_blocks * j.cgroups
+            elif kind == "cast":
+                self.blocks += (j.rows * j.k_pad16 // 4 + 2047) // 2048
             elif kind == "pack":
                 self.blocks += j.rows if unpack else j.rows_pad
                 # shared-memory floats of one staged row: [k][tap] with an odd tap stride (pack_multi_kernel)
@@ -403,6 +487,8 @@ class JobTable:
         lib = _lib.load()
         if self.kind == "bias":
             _lib.check(lib.tpgan_bias_grad_multi(self.table.data_ptr(), self.n, self.blocks, _stream()), "bias_grad_multi")
+        elif self.kind == "cast":
+            _lib.check(lib.tpgan_cast_packed_multi(self.table.data_ptr(), self.n, self.blocks, _stream()), "cast_packed_multi")
         elif self.kind == "pack":
             _lib.check(lib.tpgan_pack_multi(self.table.data_ptr(), self.n, self.blocks, self.max_row, int(self.unpack),
                                             _stream()), "pack_multi")

@@ -38,11 +38,13 @@ class _FlatSGDTrainer:
         self.world_size, self.group, self.use_graphs = world_size, group, use_graphs
         model.train()
         self.flat = FlatParams(model)                      # params + .grad as views of flat buffers (m = momentum buffer)
-        self.lr_dev = torch.full((1,), OPTIM["learning_rate"], dtype=torch.float32, device=self.device)
+        self.lr = float(OPTIM["learning_rate"])            # live learning rate: host copy + the device word the SGD kernel reads
+        self.lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=self.device)
         # what getOptimizer(model.parameters(), 'SGD')() would hold; save_optimizer(tr.optimizer, model, dir, epoch) works
         self.optimizer = FlatOptimizer(self.flat, model, "sgd", dict(lr=OPTIM["learning_rate"], momentum=OPTIM["momentum"],
                                                                      weight_decay=OPTIM["weight_decay"],
-                                                                     nesterov=OPTIM["nesterov"]), lr_dev=self.lr_dev)
+                                                                     nesterov=OPTIM["nesterov"]),
+                                       lr_get=lambda: self.lr, lr_set=self._set_lr)
         self.epoch = 0
         plan = Plan(self.device, training=True, need_wgrad=True, exact=exact, defer_bias=True)
         plan.direct_grads = True
@@ -195,15 +197,17 @@ class PretrainTrainer(_FlatSGDTrainer):
 
     def end_epoch(self):
         """learning_rate_scheduler.step() (Pretrain.py:296): MultiStepLR(milestones, gamma)."""
-        self.epoch += 1
-        k = sum(1 for m in LR_MILESTONES if self.epoch >= m)
-        self.lr_dev.fill_(OPTIM["learning_rate"] * (LR_GAMMA ** k))
+        self.set_epoch(self.epoch + 1)
 
     def set_epoch(self, epoch: int):
         """Resume: restore the MultiStepLR position (the scheduler's last_epoch) and the device-resident learning rate."""
         self.epoch = int(epoch)
         k = sum(1 for m in LR_MILESTONES if self.epoch >= m)
-        self.lr_dev.fill_(OPTIM["learning_rate"] * (LR_GAMMA ** k))
+        self._set_lr(OPTIM["learning_rate"] * (LR_GAMMA ** k))
+
+    def _set_lr(self, lr: float):
+        self.lr = float(lr)
+        self.lr_dev.fill_(self.lr)
 
     def sync_buffers(self):
         """num_batches_tracked of every BatchNorm2d (state_dict parity with nn.BatchNorm2d in train mode)."""

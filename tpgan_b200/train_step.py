@@ -88,12 +88,13 @@ class FlatOptimizer:
     by the reference's loop loads back with load_state_dict()."""
 
     def __init__(self, flat: "FlatParams", module: torch.nn.Module, kind: str, hyper: Dict[str, float],
-                 lr_dev: Optional[torch.Tensor] = None):
-        """lr_dev: the device-resident learning rate a trainer's scheduler decays (PretrainTrainer.end_epoch); when given,
-        state_dict() records the LIVE lr (and initial_lr, as torch's MultiStepLR does) and load_state_dict() restores it."""
+                 lr_get: Optional[Callable[[], float]] = None, lr_set: Optional[Callable[[float], None]] = None):
+        """lr_get / lr_set: accessors of the LIVE learning rate a trainer's scheduler decays (PretrainTrainer.end_epoch keeps
+        it on the host and in device memory); when given, state_dict() records it (and initial_lr, as torch's MultiStepLR
+        does) and load_state_dict() restores it."""
         assert kind in ("sgd", "adam")
         self.flat, self.module, self.kind, self.hyper = flat, module, kind, dict(hyper)
-        self.lr_dev = lr_dev
+        self.lr_get, self.lr_set = lr_get, lr_set
 
     def _template_group(self) -> dict:
         p = [torch.nn.Parameter(torch.zeros(1))]
@@ -116,9 +117,9 @@ class FlatOptimizer:
                             "exp_avg_sq": self.flat.v[sl].view(p.shape).clone()}
         group = self._template_group()
         group["params"] = list(range(len(state)))
-        if self.lr_dev is not None:
+        if self.lr_get is not None:
             group["initial_lr"] = group["lr"]
-            group["lr"] = float(self.lr_dev.item())
+            group["lr"] = float(self.lr_get())
         return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: dict):
@@ -126,8 +127,8 @@ class FlatOptimizer:
         ids = sd["param_groups"][0]["params"]
         if len(sd["param_groups"]) != 1 or len(ids) != n:
             raise ValueError("optimizer state does not match the module's parameter list")
-        if self.lr_dev is not None and "lr" in sd["param_groups"][0]:
-            self.lr_dev.fill_(float(sd["param_groups"][0]["lr"]))
+        if self.lr_set is not None and "lr" in sd["param_groups"][0]:
+            self.lr_set(float(sd["param_groups"][0]["lr"]))
         for i, p, sl in self._slices():
             st = sd["state"].get(ids[i], sd["state"].get(str(ids[i])))
             if st is None:                       # torch omits parameters that never received a gradient
@@ -159,6 +160,8 @@ class LayerSet:
             c, d = L.unpack_jobs(False)
             utr += c
             unp += d
+        casts = [j for L in self.multi for j in L.cast_jobs()]
+        self.cast_tab = ops.JobTable("cast", casts, device)      # bf16 operand copies of the packings (bf16 mode only)
         self.pack_tab = ops.JobTable("pack", packs, device)
         self.ptrans_tab = ops.JobTable("transpose", ptr, device)
         self.utrans_tab = ops.JobTable("transpose", utr, device)
@@ -169,6 +172,7 @@ class LayerSet:
     def repack(self):
         self.pack_tab.run()
         self.ptrans_tab.run()
+        self.cast_tab.run()
         for L in self.single:
             L.repack()
 
@@ -259,10 +263,12 @@ class CriticPlan:
     """Static schedule of the discriminator (reference D_and_G_model.py:409-435) for a batch of M images, with the native
     WGAN-GP machinery described in the module docstring."""
 
-    def __init__(self, D: Discriminator, M: int, B: int, device, exact: bool = False, defer_pack: bool = False):
+    def __init__(self, D: Discriminator, M: int, B: int, device, exact: bool = False, defer_pack: bool = False,
+                 bf16: bool = False):
         self.D, self.M, self.B, self.device, self.exact = D, M, B, device, exact
         self.defer_pack = defer_pack
-        self.h = Plan(device, exact=exact)  # launch emitters / keep-alive only
+        self.bf16 = bf16
+        self.h = Plan(device, exact=exact, bf16=bf16)  # launch emitters / keep-alive only
         new = lambda n, hw, c: Act.empty(n, hw, hw, c, device)
         self.x0 = new(M, 128, 3)
         self.ops_: List[dict] = []
@@ -309,7 +315,7 @@ class CriticPlan:
     def _mk(self, seq, name, in_c) -> ConvLayer:
         _, cm, _, _bn = _unpack_conv_seq(seq)
         L = _layer(cm, name)
-        L.setup(None, None, in_c, L.cout, self.device, exact=self.exact, defer_pack=self.defer_pack)
+        L.setup(None, None, in_c, L.cout, self.device, exact=self.exact, defer_pack=self.defer_pack, bf16=self.bf16)
         self.layers.append(L)
         return L
 
@@ -451,13 +457,21 @@ class CriticPlan:
         mid = [lambda: self.gp_sum.zero_(), lambda: ops.sample_sqnorm(gx, self.sq),
                lambda: ops.gp_coeff(self.sq, self.coeff, gp_weight * 2.0 / B, self.gp_sum),
                lambda: ops.sample_scale(gx, self.coeff, self.V_(self.x0))]
+        if self.bf16:   # bf16 twins of the tensors the convs read that pointwise kernels wrote: x0 (the caller filled it),
+            # the seeded logit deltas, the tangent seed; every other operand is written by a conv epilogue together with its twin
+            x0, v0 = self.x0, self.V_(self.x0)
+            pre += [lambda: ops.cast_bf16(x0), lambda: ops.cast_bf16(gl)]
+            mid += [lambda: ops.cast_bf16(v0)]
         return pre + self.fwd_all + self.bwd_d + mid + self.tangent
 
     def g_phase_list(self, adv_weight: float) -> List[Callable]:
         """D(fake) with the current weights, then d(-adv_weight * mean D(fake))/d fake accumulated into dfake."""
         B = self.B
         seed = -adv_weight / (B * self.logits.h * self.logits.w)
-        return [lambda: ops.fill(self.g_logits_g, seed)] + self.fwd_fake + self.bwd_g
+        pre = [lambda: ops.fill(self.g_logits_g, seed)]
+        if self.bf16:   # x0[:B] still holds the fake images and their twins from the D phase
+            pre.append(lambda: ops.cast_bf16(self.g_logits_g))
+        return pre + self.fwd_fake + self.bwd_g
 
     def d_phase(self, gp_weight: float):
         self._run(self.d_phase_list(gp_weight))
@@ -474,19 +488,19 @@ class IdentityPlan:
     of the fake branch accumulated into d fake.  No weight gradients: the network is frozen."""
 
     def __init__(self, net, B: int, fake: Act, dfake: Act, frontal: Act, weight: float, sums: torch.Tensor, device,
-                 exact: bool = False):
+                 exact: bool = False, bf16: bool = False):
         from .FeatureExtract import FeatureExtractModel
         base = net.base_model if isinstance(net, FeatureExtractModel) else net
         assert not base.training, "the identity network must be in eval() mode (frozen, BatchNorm folded)"
         self.base = base
         # fake branch: forward + input gradient
-        pf = Plan(device, training=True, need_wgrad=False, exact=exact)
-        xin = pf.wrap(fake, name="fake", requires_grad=True)
+        pf = Plan(device, training=True, need_wgrad=False, exact=exact, bf16=bf16)
+        xin = pf.wrap(fake, name="fake", requires_grad=True, s16=bf16)   # fake's twin: written by G's last conv epilogue
         xin.grad = dfake
         xin.grad_written = True           # image / adversarial terms are already in d fake: accumulate
         pooled, fc0, _ = base.trace(pf, xin, with_logits=False)
         # gt branch: forward only
-        pg = Plan(device, training=False, need_wgrad=False, exact=exact)
+        pg = Plan(device, training=False, need_wgrad=False, exact=exact, bf16=bf16)
         gin = pg.wrap(frontal, name="frontal", requires_grad=False)
         pooled_gt, fc0_gt, _ = base.trace(pg, gin, with_logits=False)
         feats = [(pooled, pooled_gt)] + ([(fc0, fc0_gt)] if fc0 is not None else [])
@@ -521,9 +535,15 @@ class TPGANTrainer:
 
     def __init__(self, G: Generator, D: Discriminator, B: int, device="cuda", use_dropout: bool = False,
                  exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0, use_graphs: bool = False,
-                 identity_net=None, input_format: str = "float"):
+                 identity_net=None, input_format: str = "float", dtype: str = "tf32"):
         """identity_net: optional frozen FeatureExtractModel / ResNet18 in eval() mode; adds the identity-preserving
-        term weight_identity_preserving * L_ip to the generator loss."""
+        term weight_identity_preserving * L_ip to the generator loss.
+        dtype: "tf32" (BASELINE configs[1]) or "bf16" (configs[2]): bf16 tensor-core operands (activations, activation
+        gradients and weights rounded to bf16 where a convolution reads them), fp32 accumulation, fp32 master weights,
+        fp32 residual / gradient accumulation and losses."""
+        assert dtype in ("tf32", "bf16")
+        self.dtype, self.bf16 = dtype, dtype == "bf16"
+        assert not (self.bf16 and exact), "exact is the tf32 verification mode"
         self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
         if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for net in (G, D) for m in net.modules()):
             raise NotImplementedError("the fused G/D step is built for the config.py defaults (use_batchnorm False, config.py:63,"
@@ -541,13 +561,13 @@ class TPGANTrainer:
         self.use_graphs = use_graphs
         # every buffer of the trainer (activations, gradients, packed weights, flat parameter / optimizer state) is carved out
         # of a few large zeroed chunks: one fill launch per 256 MB instead of one per buffer
-        self.arena = ops.Arena(self.device)
+        self.arena = ops.Arena(self.device, shadow=self.bf16)
         with ops.use_arena(self.arena):
             self._init(G, D, B, exact, world_size, group, bucket_mb, identity_net)
 
     def _init(self, G, D, B, exact, world_size, group, bucket_mb, identity_net):
         self._build_g()
-        self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact, defer_pack=not exact)
+        self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact, defer_pack=not exact, bf16=self.bf16)
         self.critic.build_g_phase(self.plan.grad_act(self.fake))
         order = self._ready_order()
         self.flat_g = FlatParams(G, order)
@@ -566,7 +586,8 @@ class TPGANTrainer:
         self.identity = None
         if identity_net is not None:
             self.identity = IdentityPlan(identity_net, B, self.fake.act, self.plan.grad_act(self.fake), self.frontal,
-                                         float(self.w["weight_identity_preserving"]), self.sums[13:15], self.device, exact=exact)
+                                         float(self.w["weight_identity_preserving"]), self.sums[13:15], self.device, exact=exact,
+                                         bf16=self.bf16)
         self._d_logits = torch.zeros_like(self.critic.logits.buf[:2 * B])
         self.inp: Optional[Dict[str, torch.Tensor]] = None
         self._pf_stream = self._pf_event = self._pf_bufs = self._pf_batch = self._pf_picked = None
@@ -579,7 +600,7 @@ class TPGANTrainer:
     # ---- generator plan
     def _build_g(self):
         G, B, dev = self.G, self.B, self.device
-        plan = Plan(dev, exact=self.exact, defer_bias=True, defer_pack=not self.exact)
+        plan = Plan(dev, exact=self.exact, defer_bias=True, defer_pack=not self.exact, bf16=self.bf16)
         self.plan = plan
         gp = G.global_pathway
         bufs = gp.alloc_concats(plan, B)
@@ -657,7 +678,7 @@ class TPGANTrainer:
     def _stage(self):
         """Static input buffers -> NHWC staging + landmark crops (all kernel launches, no host dependence)."""
         B, b = self.B, self.inp
-        rt = not self.exact
+        rt = not self.exact and not self.bf16      # bf16 mode rounds once, when the twin is written
         img = self.bufs["a128"].parts[2].act
         if self.input_format == "uint8":
             ops.u8_to_nhwc(b["img_u8"], img, rt)
