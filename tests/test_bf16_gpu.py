@@ -27,7 +27,24 @@ def _record(name, data):
             f.write(json.dumps({"test": name, **data}) + "\n")
 
 
+def _twins_current(acts):
+    """Every bf16 twin that a tensor-core launch read equals the bf16 rounding of its fp32 copy (a stale twin, a missing
+    cast or a twin written from a different value than the fp32 copy would break the equality)."""
+    bad = []
+    for a in acts:
+        ref = a.buf[..., a.c0:a.c0 + a.c].bfloat16()
+        if not torch.equal(a.twin(), ref):
+            bad.append((tuple(a.buf.shape), a.c0, a.c, rel(a.twin().float(), ref.float())))
+    return bad
+
+
 def test_step_bf16_vs_oracle():
+    """The bf16 step against the fp32 oracle step (B = 2): loss scalars at the north-star's bf16 tolerance (1e-2), all
+    gradients under identical activation masks, the un-masked bound - and the deviation the FORMAT itself causes, measured by
+    running the oracle with the same operand rounding (EMULATE_BF16): the CUDA path may not deviate from fp32 by more than
+    1.5x that.  (A bf16-emulating oracle cannot be matched more sharply than that: rounding to bf16 turns a summation-order
+    difference d into a difference sqrt(d * ulp) per layer, so two correct implementations decorrelate to the ulp level within
+    ~5 layers.  What IS sharp: tests/test_conv_bf16_gpu.py per kernel, and the twin-consistency check below.)"""
     from oracle import model_port as mp, step as ostep
     from tpgan_b200 import _lib
     from tpgan_b200.train_step import TPGANTrainer
@@ -39,42 +56,45 @@ def test_step_bf16_vs_oracle():
     torch.cuda.synchronize()
     assert _lib.kernel_status() == 0
     assert (tr.boxes.cpu().numpy() == ostep.crop_boxes(b["landmarks"].numpy())).all()
+    # ---- plumbing: every operand copy the tensor cores read is the rounding of the current fp32 value
+    reads = tr.plan.twin_reads + tr.critic.h.twin_reads
+    assert len(reads) > 300
+    assert _twins_current(reads) == []
+    crit = tr.critic
+    assert _twins_current([crit.x0, crit.G_(crit.logits), crit.V_(crit.x0), crit.g_logits_g] +
+                          [op["y"] for op in crit.ops_] + [crit.G_(op["y"]) for op in crit.ops_[:-1]]) == []
     rec = {"metrics": m}
-    # ---- forward: the generator's image against the golden record of the live reference (fp32)
-    gold = torch.load(GOLD, weights_only=False)
-    # ---- (1) same-rounding oracle, identical masks: sharp
-    mp.EMULATE_BF16 = True
-    try:
-        ref_e, gg, gd = _oracle_step_grads(b, sg, sd, tr)
-    finally:
-        mp.EMULATE_BF16 = False
-    rec["metrics_emulated"] = ref_e
-    eg, each_g = _grad_errors(G, gg)
-    ed, each_d = _grad_errors(D, gd)
-    rec.update(emul_g_overall=eg, emul_g_worst=max(each_g.items(), key=lambda kv: kv[1]), emul_d_overall=ed,
-               emul_d_worst=max(each_d.items(), key=lambda kv: kv[1]))
-    # ---- (2) plain fp32 oracle, identical masks, and un-masked
+    # ---- fp32 oracle, identical masks
     ref, gg, gd = _oracle_step_grads(b, sg, sd, tr)
     fg, feach_g = _grad_errors(G, gg)
     fd, feach_d = _grad_errors(D, gd)
     rec.update(metrics_fp32=ref, fp32_g_overall=fg, fp32_g_worst=max(feach_g.items(), key=lambda kv: kv[1]), fp32_d_overall=fd,
                fp32_d_worst=max(feach_d.items(), key=lambda kv: kv[1]))
-    _, gg, gd = _oracle_step_grads(b, sg, sd, None)
-    ug, _ = _grad_errors(G, gg)
-    ud, _ = _grad_errors(D, gd)
+    # ---- the format's own deviation: the oracle with bf16 operands against the fp32 oracle (same masks)
+    mp.EMULATE_BF16 = True
+    try:
+        ref_e, gg_e, gd_e = _oracle_step_grads(b, sg, sd, tr)
+    finally:
+        mp.EMULATE_BF16 = False
+    cat = lambda gs: torch.cat([g.flatten() for g in gs])
+    fmt_g, fmt_d = rel(cat(gg_e), cat(gg)), rel(cat(gd_e), cat(gd))
+    rec.update(metrics_emulated=ref_e, format_g_overall=fmt_g, format_d_overall=fmt_d)
+    _, gg_u, gd_u = _oracle_step_grads(b, sg, sd, None)
+    ug, _ = _grad_errors(G, gg_u)
+    ud, _ = _grad_errors(D, gd_u)
     rec.update(unmasked_g_overall=ug, unmasked_d_overall=ud)
     _record("step_b2", rec)
-    for k, v in ref_e.items():     # same rounding points: the loss scalars agree far below the format's precision
-        assert abs(m[k] - v) <= 2e-3 * abs(v) + 1e-4, ("emulated", k, m[k], v)
-    for k, v in ref.items():       # against fp32: the north-star's bf16 tolerance
+    for k, v in ref.items():       # the north-star's bf16 tolerance
         assert abs(m[k] - v) <= 1e-2 * abs(v) + 1e-3, ("fp32", k, m[k], v)
-    assert eg < 1e-2 and ed < 3e-2, (eg, ed)                  # G: sharp; D: the penalty's tangent pass rounds elsewhere
-    assert fg < 3e-2 and fd < 5e-2, (fg, fd)
-    assert ug < 0.3 and ud < 0.3, (ug, ud)
+    assert fg < 1e-2 and fd < 1e-2, (fg, fd)                         # all gradients, masks identical: measured 6.6e-3 / 2.5e-3
+    assert fg < 1.5 * fmt_g + 1e-3 and fd < 1.5 * fmt_d + 1e-3, (fg, fmt_g, fd, fmt_d)
+    assert max(feach_g.values()) < 0.1 and max(feach_d.values()) < 3e-2   # per tensor (smallest local-pathway biases: 5.8e-2)
+    assert ug < 6e-2 and ud < 8e-2, (ug, ud)                         # un-masked: sign flips of the forward deviation (3e-2 / 4e-2)
 
 
 def test_forward_bf16_tensors():
-    """Stored activations of the bf16 step against the fp32 oracle: the generator image and the critic logits."""
+    """Stored activations of the bf16 step against the fp32 oracle: the generator image and the identity logits within the
+    north-star's 1e-2, and within 1.5x of what the format itself costs the oracle."""
     from oracle import model_port as mp, step as ostep
     from tpgan_b200.train_step import TPGANTrainer
     B = 2
@@ -89,20 +109,18 @@ def test_forward_bf16_tensors():
         mp.EMULATE_BF16 = emu
         try:
             with torch.no_grad():
-                o = mp.generator(sg, *[b[k] for k in NAMES])
-                dl = mp.discriminator(sd, o[0])
+                outs[emu] = mp.generator(sg, *[b[k] for k in NAMES])
         finally:
             mp.EMULATE_BF16 = False
-        outs[emu] = (o, dl)
-    e_fp32, e_emu = rel(fake, outs[False][0][0]), rel(fake, outs[True][0][0])
+    e_fp32, fmt = rel(fake, outs[False][0]), rel(outs[True][0], outs[False][0])
     logits = tr.logits.act.to_nchw().reshape(B, -1).cpu()
-    l_fp32, l_emu = rel(logits, outs[False][0][1]), rel(logits, outs[True][0][1])
+    l_fp32, lfmt = rel(logits, outs[False][1]), rel(outs[True][1], outs[False][1])
     twin = tr.fake.act.twin().float().permute(0, 3, 1, 2).cpu()
-    _record("forward_b2", dict(fake_vs_fp32=e_fp32, fake_vs_emulated=e_emu, logits_vs_fp32=l_fp32, logits_vs_emulated=l_emu,
+    _record("forward_b2", dict(fake_vs_fp32=e_fp32, format_fake=fmt, logits_vs_fp32=l_fp32, format_logits=lfmt,
                                twin_vs_fp32copy=rel(twin, fake)))
-    assert e_emu < 2e-3 and l_emu < 2e-3, (e_emu, l_emu)       # same rounding points: sign-flip / summation-order level
-    assert e_fp32 < 2e-2 and l_fp32 < 2e-2, (e_fp32, l_fp32)   # the format: ~60 stacked convolutions x 2^-9
-    assert rel(twin, fake) < 4e-3                              # the bf16 copy is the rounded fp32 copy
+    assert e_fp32 < 1e-2 and l_fp32 < 1e-2, (e_fp32, l_fp32)            # measured 6.7e-3 / 5.8e-3
+    assert e_fp32 < 1.5 * fmt and l_fp32 < 1.5 * lfmt + 1e-3, (e_fp32, fmt, l_fp32, lfmt)
+    assert torch.equal(tr.fake.act.twin(), tr.fake.act.buf[..., :3].bfloat16())
 
 
 def test_bf16_training_trajectory_and_graphs():
@@ -132,3 +150,31 @@ def test_bf16_training_trajectory_and_graphs():
     assert all(v == v and abs(v) < 1e4 for m in me for v in m.values()), me
     assert me[-1]["g_total"] < me[0]["g_total"]        # the same batch four times: the generator loss goes down
     _record("trajectory", dict(first=me[0], last=me[-1]))
+
+
+def test_identity_step_bf16():
+    """BASELINE configs[2] as stated: the G+D step with the frozen identity network's loss, bf16 operands (the identity
+    network's folded convolutions included): every generator-side metric against the fp32 oracle step at 1e-2, and the
+    twins the identity plans read are current."""
+    from oracle import step as ostep
+    from test_identity_gpu import _net
+    from tpgan_b200.train_step import TPGANTrainer
+    G, D, sg, sd = _models(False)
+    pg = {k: v.clone().requires_grad_(True) for k, v in sg.items()}
+    pd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    net, isd = _net(seed=7)
+    B = 2
+    b = ostep.make_batch(B)
+    tr = TPGANTrainer(G, D, B, identity_net=net.cuda(), dtype="bf16")
+    m = tr.step({k: v.cuda() for k, v in b.items()}, optimize=False)
+    torch.cuda.synchronize()
+    assert _twins_current(tr.identity.pf.twin_reads + tr.identity.pg.twin_reads) == []
+    Gc, Dc = ostep.port_callables(pg, pd)
+    og = torch.optim.Adam(list(pg.values()), lr=ostep.LEARNING_RATE)
+    od = torch.optim.Adam(list(pd.values()), lr=ostep.LEARNING_RATE)
+    ref = ostep.train_step(Gc, Dc, list(pg.values()), list(pd.values()), og, od, b, step_optim=False, identity_sd=isd)
+    _record("identity_b2", dict(metrics=m, oracle=ref))
+    for k in ("pixel", "local", "symmetry", "tv", "ce", "ip", "g_total"):
+        assert abs(m[k] - ref[k]) <= 1e-2 * abs(ref[k]) + 1e-4, (k, m[k], ref[k])
+    m2 = tr.step({k: v.cuda() for k, v in b.items()}, optimize=True)       # and the optimizer path runs
+    assert all(v == v for v in m2.values())

@@ -249,3 +249,45 @@ def test_classifier_trainer_step_vs_oracle():
             tr.flat.m[o:o + p.numel()].copy_(opt.state[p]["momentum_buffer"].flatten())
         for L in tr.plan.layers:
             L.repack()
+
+
+def test_eval_forward_follows_weight_updates():
+    """the eval-mode network caches its BatchNorm-folded tensor-core layers.  A weight update between two eval
+    forwards (optimizer step through torch, a train-mode forward that moves the running statistics, load_state_dict) must
+    show up in the second one - the cache is keyed on parameter / buffer versions and re-folds in place."""
+    from oracle import identity_port as ip
+    net, _ = _net(seed=11)
+    net = net.cuda()
+    base = net.base_model
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((3, 3, 128, 128), generator=g) * 2 - 1
+    xc = x.cuda()
+    with torch.no_grad():
+        f1, _ = base(xc)
+    # (1) an optimizer-style in-place update of every parameter
+    with torch.no_grad():
+        for p in base.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g).cuda() * p.abs().mean())
+        f2, z2 = base(xc)
+    sd = {k: v.detach().cpu().clone() for k, v in base.state_dict().items()}
+    want, want0, _ = ip.resnet18_128(sd, x, training=False)
+    assert rel(f2, want) < 1e-2 and rel(z2, want0) < 1e-2, (rel(f2, want), rel(z2, want0))
+    assert rel(f2, f1) > 1e-2            # the update is visible at all
+    # (2) a train-mode forward moves the running statistics through raw device pointers
+    base.train()
+    base(xc)
+    base.eval()
+    with torch.no_grad():
+        f3, _ = base(xc)
+    sd = {k: v.detach().cpu().clone() for k, v in base.state_dict().items()}
+    want3, _, _ = ip.resnet18_128(sd, x, training=False)
+    assert rel(f3, want3) < 1e-2 and rel(f3, f2) > 1e-3, (rel(f3, want3), rel(f3, f2))
+    # (3) load_state_dict back to the state after (1)
+    sd1 = {k: v.clone() for k, v in base.state_dict().items()}
+    base.load_state_dict({k: (v * 0.9 if v.is_floating_point() else v) for k, v in sd1.items()})
+    with torch.no_grad():
+        f4, _ = base(xc)
+    want4, _, _ = ip.resnet18_128({k: v.detach().cpu() for k, v in base.state_dict().items()}, x, training=False)
+    assert rel(f4, want4) < 1e-2, rel(f4, want4)
+    with pytest.raises(RuntimeError, match="no autograd graph"):
+        base(xc.clone().requires_grad_(True))

@@ -395,6 +395,8 @@ class Plan:
         # kernels, the masks and the residual / gradient accumulations keep using; fp32 accumulate, fp32 master weights
         self.bf16 = bf16
         assert not (bf16 and exact)
+        self.twin_reads: List[Act] = []   # every view a tensor-core launch of this plan reads through its bf16 twin (tests:
+                                          # after a step each twin must equal the bf16 rounding of its fp32 copy)
         self.defer_pack = defer_pack  # the owner re-packs every layer of this plan in one multi-tensor launch after tracing
         self.defer_bias = defer_bias  # record (layer, dY, ready index) instead of launching one bias-grad kernel per layer
         self.bias_jobs: list = []
@@ -522,6 +524,7 @@ class Plan:
         if not self.bf16:
             return
         for p in t.leaves():
+            self.twin_reads.append(p.act)
             if not p.s16:
                 a = p.act
                 lst.append(_tag(lambda a=a: ops.cast_bf16(a), "cast16", 6.0 * a.n * a.h * a.w * a.c, p.name))
@@ -532,6 +535,7 @@ class Plan:
         if not self.bf16:
             return
         for p in t.leaves():
+            self.twin_reads.append(self.grad_act(p))
             if not p.g16:
                 g = self.grad_act(p)
                 self.bwd.append(_tag(lambda g=g: ops.cast_bf16(g), "cast16", 6.0 * g.n * g.h * g.w * g.c, p.name + ".grad"))

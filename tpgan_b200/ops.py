@@ -108,11 +108,21 @@ class use_arena:
         return False
 
 
+def _same_device(a: torch.device, b: torch.device) -> bool:
+    """torch.device("cuda") and torch.device("cuda", i) name the same device when i is the current one."""
+    if a.type != b.type:
+        return False
+    if a.type != "cuda" or a.index == b.index:
+        return True
+    cur = torch.cuda.current_device()
+    return (cur if a.index is None else a.index) == (cur if b.index is None else b.index)
+
+
 def zeros(shape, dtype=torch.float32, device="cuda") -> torch.Tensor:
     """Zero-initialised device tensor; inside a use_arena() block a view of the arena (no fill launch)."""
     if isinstance(shape, int):
         shape = (shape,)
-    if _ARENA and _ARENA[-1].device == torch.device(device):
+    if _ARENA and _same_device(_ARENA[-1].device, torch.device(device)):
         return _ARENA[-1].alloc(tuple(shape), dtype)
     return torch.zeros(tuple(shape), dtype=dtype, device=device)
 
@@ -315,8 +325,17 @@ def cast_job(src: Packed, dst: Packed) -> "_lib.CastJob":
     return _lib.CastJob(src.data.data_ptr(), dst.data.data_ptr(), src.data.shape[0] * src.rows_pad, src.k_pad, dst.k_pad, 0, 0)
 
 
+_CAST_TABLES: dict = {}
+
+
 def cast_packed(src: Packed, dst: Packed) -> None:
-    JobTable("cast", [cast_job(src, dst)], src.data.device).run()
+    """dst (bf16 packing) <- src (fp32 packing).  The one-job table is built once per (src, dst) pair: building it copies
+    host memory to the device, which must not happen while a CUDA graph is being captured."""
+    key = (src.data.data_ptr(), dst.data.data_ptr())
+    tab = _CAST_TABLES.get(key)
+    if tab is None:
+        tab = _CAST_TABLES[key] = (JobTable("cast", [cast_job(src, dst)], src.data.device), src, dst)
+    tab[0].run()
 
 
 def wgrad_grouped(args: List[WgradArgs]) -> None:
