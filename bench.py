@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 METRIC = "tpgan_g_d_train_step_images_per_sec"
 UNIT = "images/s"
 PER_GPU_BATCH = 32
+CPU_BATCH = 4          # BASELINE.json configs[0]: the reference's own CPU-runnable case
 
 
 def _peaks():
@@ -114,12 +115,14 @@ def run_reference(a):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    batch = 2
-    sec, threads = cpu_port_step_time(batch, a.steps, a.warmup)
+    batch = CPU_BATCH      # BASELINE.json configs[0] / BASELINE.md section 4: batch 4, >= 1 warm-up step, >= 3 timed steps
+    steps, warmup = max(a.steps, 3), max(a.warmup, 1)
+    sec, threads = cpu_port_step_time(batch, steps, warmup)
     val = batch / sec
-    sample = f"oracle fp32 PyTorch port of the reference G+D + oracle step, batch {batch} per step, {a.steps} steps"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    sample = (f"oracle fp32 PyTorch port of the reference G+D + oracle step, batch {batch} per step, {steps} timed steps after "
+              f"{warmup} warm-up")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "TP-GAN G+D training step (WGAN-GP critic + all G losses + Adam), 128x128, "
                                    f"bounded CPU sample batch {batch}", "per_step_batch": batch},
@@ -128,36 +131,42 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def run_b200(a):
+def _ncu_summary(dtype: str, batch: int):
+    """Per-kernel DRAM traffic and tensor-pipe activity from the committed ncu pass of this same workload
+    (profiles/ncu_kernel_summary_r2.json, produced by tools/ncu_summary.py from `ncu --metrics gpu__time_duration.sum,
+    dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active...` over one eager step)."""
+    p = os.path.join(ROOT, "profiles", "ncu_kernel_summary_r2.json")
+    if not os.path.exists(p):
+        return {}
+    d = json.load(open(p))
+    return d.get(f"{dtype}_b{batch}", {})
+
+
+def gan_line(a, B, dtype, identity, steps, warmup, world, rank, dev, want_roofline=True, want_cpu=True, per_layer=""):
+    """Build a trainer, time `steps` resident steps and `steps` end-to-end steps, optionally the per-kernel roofline.
+    Returns the JSON line (rank 0) or None."""
+    import gc
+
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from oracle import step as ostep  # synthetic batch generator only (inputs, not compute)
-    from tpgan_b200 import D_and_G_model as M, _lib, config
-    from tpgan_b200.train_step import TPGANTrainer
-    B = a.batch
+    from tpgan_b200 import D_and_G_model as M, _lib, config, synthetic
+    from tpgan_b200.train_step import Eager, TPGANTrainer
+    local = dev.index
     torch.manual_seed(0)
     G = M.Generator(config.G["zdim"], config.G["num_classes"], config.G["use_batchnorm"], config.G["use_residual_block"])
     D = M.Discriminator(config.D["use_batchnorm"])
     G.to(dev)
     D.to(dev)
     ident = None
-    if a.identity:   # BASELINE configs[2]: frozen FeatureExtract (ResNet18-128) identity-preserving loss (tf32 here; bf16 is not built)
+    if identity:   # BASELINE configs[2]: frozen FeatureExtract (ResNet18-128) identity-preserving loss
         from tpgan_b200.FeatureExtract import FeatureExtractModel
         from tpgan_b200.ResNet import BasicBlock
         ident = FeatureExtractModel("resnet", config.G["num_classes"], residualBlock=BasicBlock,
                                     feature_layer_dim_before_FC=256).to(dev).eval()
     tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world, use_graphs=not a.no_graphs,
-                      identity_net=ident, dtype=a.dtype)
-    host = ostep.make_batch(B, seed=1234 + rank)
-    keys = ("img", "img_frontal", "img64_frontal", "img32_frontal", "landmarks", "z", "label", "gp_alpha")
-    host = {k: host[k].contiguous().pin_memory() for k in keys}
+                      identity_net=ident, dtype=dtype)
+    host = synthetic.make_batch(B, seed=1234 + rank)
+    host = {k: host[k].contiguous().pin_memory() for k in synthetic.KEYS}
     devb = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -166,11 +175,11 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         e1.record()
         barrier()
@@ -192,46 +201,53 @@ def run_b200(a):
         d2h_bytes[0] = 16 * 4 + 3 * B * 16 * 4 * 4 + 4
         return m
 
-    for _ in range(max(a.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    ms = timed(resident, a.steps)
+    ms = timed(resident, steps)
     launches = _lib.launch_count() - l0
     if not a.no_graphs:   # replayed graphs do not go through the library's host entry points: count the captured kernels
         runner = list(tr._sched.values())[0]
-        launches = a.steps * runner.kernels_per_run
+        launches = steps * runner.kernels_per_run
     clocks = sampler.stop() if rank == 0 else None
     tr.prefetch(host)
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, a.steps)
+    ms_e2e = timed(e2e_step, steps)
     assert _lib.kernel_status() == 0, "a kernel aborted a barrier wait"
+    # replicas must stay identical under data parallelism: spread of a parameter checksum over the ranks
+    spread = None
+    if world > 1:
+        cs = torch.stack([tr.flat_g.data.double().sum(), tr.flat_d.data.double().sum()])
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        st = torch.stack(allcs)
+        spread = float(((st.max(0).values - st.min(0).values) / st.mean(0).abs().clamp_min(1e-30)).max())
 
-    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): per-launch CUDA events over one more step
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): per-launch CUDA events over one more (eager) step of
+    # the WHOLE schedule - generator plan, critic (D phase, gradient penalty tangent pass, G phase), identity network
     roof = None
     cpu = None
-    if rank == 0:
+    if rank == 0 and want_roofline:
         ev = []
         torch.cuda.synchronize()
-
-        def instrument(lst):
-            for f in lst:
-                if getattr(f, "kind", None) in ("tapgemm", "rowconv", "wgrad"):
-                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s.record()
-                    f()
-                    e.record()
-                    # conv launches: ask the library which kernel it actually routed the call to
-                    kind = f.kind if f.kind == "wgrad" else _lib.last_conv_kernel()
-                    ev.append((kind, f.flops, s, e, f.label))
-                else:
-                    f()
-        tr.stage_inputs(devb)
-        instrument(tr.plan.fwd)
-        instrument(tr.plan.bwd)
+        tr.load_inputs(devb)
+        for f in tr._schedule(True):
+            if isinstance(f, Eager):
+                continue                 # collectives: the other ranks are not here
+            if getattr(f, "kind", None) in ("tapgemm", "rowconv", "wgrad"):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                f()
+                e.record()
+                # conv launches: ask the library which kernel it actually routed the call to
+                kind = f.kind if f.kind == "wgrad" else _lib.last_conv_kernel()
+                ev.append((kind, f.flops, s, e, f.label))
+            else:
+                f()
         torch.cuda.synchronize()
         agg = {}
         for kind, fl, s, e, label in ev:
@@ -240,54 +256,115 @@ def run_b200(a):
             g[0] += fl
             g[1] += t
             g[2] += 1
-        if a.per_layer:
+        if per_layer:
             rows = sorted(((s.elapsed_time(e), kind, fl, label) for kind, fl, s, e, label in ev), reverse=True)
-            with open(a.per_layer, "w") as f:
+            with open(per_layer, "w") as f:
                 for t, kind, fl, label in rows:
                     f.write(json.dumps({"ms": round(t, 4), "kind": kind, "tflops": round(fl / (t * 1e-3) / 1e12, 1),
                                         "gflop": round(fl / 1e9, 2), "label": label}) + "\n")
         peaks, which = _peaks()
-        bf16 = a.dtype == "bf16"
-        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / (1.0 if bf16 else 2.0)
-        dn = a.dtype
-        names = {"tapgemm": f"tapgemm_kernel (tcgen05 {dn} multi-tap implicit-GEMM conv fwd/dgrad/deconv/linear)",
-                 "rowconv": f"rowconv_kernel (tcgen05 {dn} row-tile conv for the wide 128x128 stride-1 layers, fwd/dgrad)",
-                 "rowstack": f"rowstack_kernel (tcgen05 {dn} N-stacked row-tile conv for the narrow 128x128 layers, fwd/dgrad)",
-                 "wgrad": f"wgrad_kernel (tcgen05 {dn} weight-gradient GEMM over pixels)"}
-        step_ms = ms / a.steps
+        bf16 = dtype == "bf16"
+        div = 1.0 if bf16 else 2.0
+        peak_sus = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / div
+        peak_burst = peaks["bf16_tflops"] / div
+        names = {"tapgemm": f"tapgemm_kernel (tcgen05 {dtype} multi-tap implicit-GEMM conv fwd/dgrad/deconv/linear)",
+                 "rowconv": f"rowconv_kernel (tcgen05 {dtype} row-tile conv for the wide 128x128 stride-1 layers, fwd/dgrad)",
+                 "rowstack": f"rowstack_kernel (tcgen05 {dtype} N-stacked row-tile conv for the narrow 128x128 layers, fwd/dgrad)",
+                 "wgrad": f"wgrad_kernel (tcgen05 {dtype} weight-gradient GEMM over pixels)"}
+        step_ms = ms / steps
+        ncu = _ncu_summary(dtype, B)
 
         def entry(kind):
             fl, t, n = agg[kind]
             ach = fl / (t * 1e-3) / 1e12
-            return {"kernel": names[kind], "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                    "launches": n, "avg_launch_ms": t / n, "share_of_step": t / step_ms,
-                    "algorithmic_gflop_per_step": fl / 1e9}
+            d = {"kernel": names[kind], "achieved": ach, "peak": peak_sus, "unit": "TFLOP/s", "frac": ach / peak_sus,
+                 "frac_of_burst_peak": ach / peak_burst, "launches": n, "avg_launch_ms": t / n, "share_of_step": t / step_ms,
+                 "algorithmic_gflop_per_step": fl / 1e9}
+            k = ncu.get(kind + "_kernel")
+            if k:     # from the committed ncu pass of this workload (per launch, like `achieved`)
+                d.update(traffic=k["dram_bytes_per_launch"], tensor_pipe_pct=k["tensor_pipe_pct"],
+                         ncu_share_of_step=k["share_of_step"])
+            return d
         dom = max(agg, key=lambda k: agg[k][1])
-        roof = {"bound": "tensor", **entry(dom), "traffic": None,
-                "peak_source": (f"bf16_tflops_sustained of MEASURED_PEAKS.json ({which})" if bf16 else
-                                f"0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json ({which}); tf32 = half the bf16 rate"),
+        tot_fl, tot_t = sum(v[0] for v in agg.values()), sum(v[1] for v in agg.values())
+        roof = {"bound": "tensor", "traffic": None, **entry(dom),
+                "traffic_source": ("profiles/ncu_kernel_summary_r2.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                   "averaged over the kernel's launches of one step") if ncu else None,
+                "peak_source": (f"bf16_tflops_sustained of MEASURED_PEAKS.json ({which}); frac_of_burst_peak uses bf16_tflops" if bf16
+                                else f"0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json ({which}); tf32 = half the bf16 rate "
+                                     "(assumed, not measured); frac_of_burst_peak uses 0.5 x bf16_tflops"),
+                "scope": "every tensor-core launch of the step: generator plan, critic D / GP-tangent / G phases" +
+                         (", identity network" if identity else ""),
                 "other_kernels": {k: entry(k) for k in agg if k != dom},
-                "all_conv_kernels": {"achieved": sum(v[0] for v in agg.values()) / (sum(v[1] for v in agg.values()) * 1e-3) / 1e12,
-                                     "share_of_step": sum(v[1] for v in agg.values()) / step_ms}}
-        if not a.no_cpu:
-            sec, threads = cpu_port_step_time(2, 1, 0)
-            cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "one oracle-port G+D training step (fp32 PyTorch, CPU) at batch 2"}
+                "all_conv_kernels": {"achieved": tot_fl / (tot_t * 1e-3) / 1e12, "frac": tot_fl / (tot_t * 1e-3) / 1e12 / peak_sus,
+                                     "share_of_step": tot_t / step_ms, "algorithmic_gflop_per_step": tot_fl / 1e9},
+                "whole_step": {"achieved": tot_fl / (step_ms * 1e-3) / 1e12, "frac": tot_fl / (step_ms * 1e-3) / 1e12 / peak_sus}}
+    if rank == 0 and want_cpu and not a.no_cpu:
+        sec, threads = cpu_port_step_time(CPU_BATCH, 3, 1)
+        cpu = {"value": CPU_BATCH / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"three oracle-port G+D training steps (fp32 PyTorch, CPU) at batch {CPU_BATCH} after one warm-up step"}
+    line = None
     if rank == 0:
         gb = B * world
-        line = {"metric": METRIC, "value": gb * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        line = {"metric": METRIC, "value": gb * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": max(warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True,
+                "scaling": "strong" if a.global_batch else "weak",
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": f"TP-GAN G+D training step (WGAN-GP critic + all G losses + Adam), batch {B}/GPU, "
                                        "128x128 synthetic faces + 4 landmark patches, dropout on" +
-                                       (", + frozen ResNet18 identity-preserving loss" if a.identity else ""),
+                                       (", + frozen ResNet18 identity-preserving loss" if identity else ""),
                            "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
-                           "l2": "activations per step (~8 GB) exceed the 126 MB L2; no explicit flush",
+                           "l2": f"activations per step (~{0.27 * B:.0f} GB) exceed the 126 MB L2; no explicit flush",
                            "cuda_graphs": not a.no_graphs},
                 "clocks": clocks,
-                "e2e": {"value": gb * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "h2d": "pinned host batch, copied on a side stream during the previous step",
-                        "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": ms_e2e / a.steps},
+                "e2e": {"value": gb * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "h2d": "pinned host batch, copied on a side stream during the previous step",
+                        "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": ms_e2e / steps},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        if spread is not None:
+            line["replica_checksum_spread"] = spread
+    del tr, G, D, ident, devb
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.batch
+    if a.global_batch:
+        assert a.global_batch % world == 0, "--global-batch must be a multiple of the number of GPUs"
+        B = a.global_batch // world
+    line = gan_line(a, B, a.dtype, a.identity, a.steps, a.warmup, world, rank, dev, per_layer=a.per_layer)
+    if rank == 0 and world == 1 and not a.no_secondary and not a.identity and a.dtype == "tf32" and not a.global_batch:
+        # the other single-GPU configurations BASELINE.json names, measured in the same run (short: 5 timed steps each)
+        sec = []
+        try:
+            l2 = gan_line(a, 64, "bf16", True, 5, 3, 1, 0, dev, want_roofline=False, want_cpu=False)
+            sec.append({"config": "BASELINE configs[2]: G+D step + frozen ResNet18 identity loss, bf16 operands, batch 64, 1 GPU",
+                        **{k: l2[k] for k in ("value", "unit", "ms_per_step", "dtype", "steps", "e2e", "gpu_launches", "clocks")}})
+            l3 = gan_line(a, 32, "bf16", False, 5, 3, 1, 0, dev, want_roofline=True, want_cpu=False)
+            sec.append({"config": "the headline workload (configs[1], batch 32) with bf16 operands",
+                        **{k: l3[k] for k in ("value", "unit", "ms_per_step", "dtype", "steps", "e2e", "gpu_launches")},
+                        "roofline": {k: l3["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "share_of_step",
+                                                                    "all_conv_kernels", "whole_step")}})
+            for backbone in ("mobilenetv2", "resnet"):
+                ns = argparse.Namespace(**{**vars(a), "batch": 32, "steps": 10, "warmup": 3, "no_cpu": True, "backbone": backbone})
+                lp = pretrain_line(ns, 1, 0, dev, want_roofline=False)
+                sec.append({"config": f"BASELINE configs[4] per GPU: Pretrain step, {backbone} backbone, batch 32, 1 GPU",
+                            **{k: lp[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "steps", "e2e", "gpu_launches")}})
+        except Exception as ex:     # a secondary measurement must never take the headline down with it
+            sec.append({"error": f"{type(ex).__name__}: {ex}"})
+        line["secondary"] = sec
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -378,14 +455,37 @@ def run_pretrain(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from oracle import pretrain_port as P   # synthetic batch generator only (inputs, not compute)
+    line = pretrain_line(a, world, rank, dev)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _pretrain_batch(B: int, seed: int):
+    """Synthetic Pretrain batch: faces U(-1,1), 4 ground-truth points = landmark means + U(-3,3) px jitter,
+    per-point sub-sampling keys.  Same draw order as the oracle's generator (product code: no oracle import)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand((B, 3, 128, 128), generator=g) * 2 - 1
+    # eyes, nose, mouth centre (mean of the two mouth corners) of D_and_G_model.py:120-128
+    means = torch.tensor([[39.4799, 40.2799], [85.9613, 38.7062], [63.6415, 63.6473], [64.7803, 89.3250]])
+    true = (means[None] + (torch.rand((B, 4, 2), generator=g) * 6 - 3)).reshape(B, 8)
+    u = torch.rand((B, 394), generator=g)
+    return x, true, u
+
+
+def pretrain_line(a, world, rank, dev, want_roofline=True):
+    import torch
+    import torch.distributed as dist
+    local = dev.index
     from tpgan_b200 import _lib
     from tpgan_b200.MobileNetV2 import MobileNetV2
     from tpgan_b200.pretrain_step import ClassifierTrainer, PretrainTrainer
     B = a.batch
     resnet = a.backbone == "resnet"
     torch.manual_seed(0)
-    x, true, u = P.make_batch(B, seed=1234 + rank)
+    x, true, u = _pretrain_batch(B, seed=1234 + rank)
     if resnet:
         from tpgan_b200.FeatureExtract import FeatureExtractModel
         from tpgan_b200.ResNet import BasicBlock
@@ -440,7 +540,7 @@ def run_pretrain(a):
     ms_e2e = timed(e2e_step, a.steps)
     assert _lib.kernel_status() == 0, "a kernel aborted a barrier wait"
     roof = cpu = None
-    if rank == 0:
+    if rank == 0 and want_roofline:
         ev = []
         tr.load_inputs(*devb)
         tr._stage()
@@ -498,7 +598,9 @@ def run_pretrain(a):
         gb = B * world
         line = {"metric": PRETRAIN_METRIC_RESNET if resnet else PRETRAIN_METRIC, "value": gb * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if resnet else "tf32x3 (fp32-accurate three-pass operand split, the MobileNetV2 production mode)",
+                "data": "synthetic",
                 "config": {"workload": (f"feature-extractor pre-training step: ResNet18-128 forward/backward (training BatchNorm) + "
                                         f"softmax cross-entropy (347 identities) + SGD-Nesterov, batch {B}/GPU, 128x128 synthetic faces"
                                         if resnet else
@@ -511,9 +613,11 @@ def run_pretrain(a):
                 "e2e": {"value": gb * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / a.steps},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del tr, net, devb
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -527,6 +631,11 @@ def main():
                     help="gan = G+D training step (BASELINE configs[1], the headline); pretrain = Pretrain.py MobileNetV2 "
                          "step (configs[4])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="gan workload, 1 GPU: skip the short measurements of BASELINE configs[2] / [4] appended to the line")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="gan workload: fixed GLOBAL batch split over the GPUs (BASELINE configs[3]: 256 at 2/4/8 GPUs = "
+                         "128/64/32 per GPU; strong scaling) instead of a fixed per-GPU batch")
     ap.add_argument("--per-layer", default="", help="write the per-launch conv/wgrad timing table (JSON lines) here")
     ap.add_argument("--backbone", default="mobilenetv2", choices=["mobilenetv2", "resnet"],
                     help="pretrain workload: MobileNetV2-SSD landmark pre-training (Pretrain.py) or ResNet18 identity classifier")
