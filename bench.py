@@ -163,8 +163,11 @@ def gan_line(a, B, dtype, identity, steps, warmup, world, rank, dev, want_roofli
         from tpgan_b200.ResNet import BasicBlock
         ident = FeatureExtractModel("resnet", config.G["num_classes"], residualBlock=BasicBlock,
                                     feature_layer_dim_before_FC=256).to(dev).eval()
+    if a.sm_reserve:
+        _lib.set_sm_reserve(a.sm_reserve)
     tr = TPGANTrainer(G, D, B, device=dev, use_dropout=True, world_size=world, use_graphs=not a.no_graphs,
-                      identity_net=ident, dtype=dtype)
+                      identity_net=ident, dtype=dtype, overlap_allreduce=a.dp_mode == "overlap",
+                      graph_collectives=a.graph_collectives, bucket_mb=a.bucket_mb)
     host = synthetic.make_batch(B, seed=1234 + rank)
     host = {k: host[k].contiguous().pin_memory() for k in synthetic.KEYS}
     devb = {k: v.to(dev) for k, v in host.items()}
@@ -315,7 +318,9 @@ def gan_line(a, B, dtype, identity, steps, warmup, world, rank, dev, want_roofli
                                        (", + frozen ResNet18 identity-preserving loss" if identity else ""),
                            "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
                            "l2": f"activations per step (~{0.27 * B:.0f} GB) exceed the 126 MB L2; no explicit flush",
-                           "cuda_graphs": not a.no_graphs},
+                           "cuda_graphs": not a.no_graphs,
+                           **({"dp_mode": a.dp_mode, "graph_collectives": a.graph_collectives, "sm_reserve": a.sm_reserve,
+                               "bucket_mb": a.bucket_mb} if world > 1 else {})},
                 "clocks": clocks,
                 "e2e": {"value": gb * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "h2d": "pinned host batch, copied on a side stream during the previous step",
@@ -591,6 +596,8 @@ def pretrain_line(a, world, rank, dev, want_roofline=True):
                 "timing": "per-launch CUDA events in eager mode with an L2 flush (256 MB memset) before each launch",
                 "peak_source": f"MEASURED_PEAKS.json ({which})",
                 "other_kernels": {names.get(k, k): entry(k) for k in agg if k != dom}}
+    line = None
+    if rank == 0:
         if not a.no_cpu:
             sec, threads = (cpu_classifier_step_time if resnet else cpu_pretrain_step_time)(B, 2, 1)
             cpu = {"value": B / sec, "unit": UNIT, "cores": threads, "kind": "port",
@@ -642,6 +649,11 @@ def main():
     ap.add_argument("--identity", action="store_true", help="gan workload: add the frozen identity network's loss (configs[2], tf32)")
     ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
                     help="gan workload: tensor-core operand type (tf32 = BASELINE configs[1]; bf16 = configs[2])")
+    ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "serial"],
+                    help="N > 1: bucketed all-reduce overlapped with backward, or one all-reduce after backward")
+    ap.add_argument("--graph-collectives", action="store_true", help="N > 1: capture the NCCL calls into the step's CUDA graph")
+    ap.add_argument("--sm-reserve", type=int, default=0, help="SMs the persistent kernels leave free (for the NCCL kernels)")
+    ap.add_argument("--bucket-mb", type=float, default=32.0, help="N > 1, overlap mode: all-reduce bucket size")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     if a.workload == "pretrain":

@@ -349,6 +349,10 @@ TPGAN_API int tpgan_last_conv_kernel(void);
  * bit-identical from run to run (and between eager launches and CUDA-graph replays), at reduced speed. */
 TPGAN_API int tpgan_set_deterministic(int32_t on);
 TPGAN_API int tpgan_get_deterministic(void);
+/* SMs the persistent tensor-core kernels (one CTA per SM, static tile partition) leave free for concurrent work on other
+ * streams - the NCCL all-reduce overlapped with backward (0..64, process-wide; returns the previous value).  Applies to
+ * launches issued (or captured into a CUDA graph) after the call. */
+TPGAN_API int tpgan_set_sm_reserve(int32_t sms);
 
 #ifdef __cplusplus
 }

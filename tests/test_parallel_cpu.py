@@ -44,7 +44,7 @@ def _worker(rank, world, port, ret):
     loss = mp.discriminator(pd, x).mean()          # local mean
     grads = torch.autograd.grad(loss, list(pd.values()))
     flat = torch.cat([g.flatten() for g in grads])
-    allreduce_sum(flat).wait()
+    allreduce_sum(flat)      # stream / call-ordered (async_op=False): complete on return for gloo
     flat *= 1.0 / world                            # the optimizer's grad_scale
     if rank == 0:
         full = mp.discriminator(pd, b["img"]).mean()

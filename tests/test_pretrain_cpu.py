@@ -199,7 +199,7 @@ def _dp_worker(rank, world, port, ret):
         return torch.cat([p.grad.flatten() for p in net.parameters()])
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     flat = shard_grad(rank)
-    allreduce_sum(flat).wait()
+    allreduce_sum(flat)      # call-ordered (async_op=False): complete on return for gloo
     flat *= 1.0 / world                                      # PretrainTrainer's grad_scale of the SGD kernel
     if rank == 0:
         want = torch.zeros_like(flat)

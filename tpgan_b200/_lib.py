@@ -126,6 +126,7 @@ SYMBOLS = {
     "tpgan_last_conv_kernel": (C.c_int, []),
     "tpgan_set_deterministic": (C.c_int, [_I32]),
     "tpgan_get_deterministic": (C.c_int, []),
+    "tpgan_set_sm_reserve": (C.c_int, [_I32]),
 }
 
 
@@ -166,6 +167,11 @@ def set_deterministic(on: bool) -> bool:
     """Process-wide deterministic mode (see include/tpgan_b200.h); returns the previous setting.  Plans / job tables built
     while it is on keep their deterministic geometry."""
     return bool(load().tpgan_set_deterministic(int(bool(on))))
+
+
+def set_sm_reserve(sms: int) -> int:
+    """SMs the persistent tensor-core kernels leave free for concurrent kernels (NCCL); returns the previous value."""
+    return int(load().tpgan_set_sm_reserve(int(sms)))
 
 
 def deterministic() -> bool:

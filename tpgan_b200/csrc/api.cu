@@ -61,6 +61,12 @@ static std::mutex g_mu;
 // partial results with fp32 atomics, whose order varies from run to run.  With the flag set, a weight-gradient CTA owns
 // whole output tiles and a bias sum is one block per channel group: bit-identical results run to run, at a lower speed.
 std::atomic<int> g_deterministic{0};
+// SMs left free by the persistent tensor-core kernels (tpgan_set_sm_reserve).  These kernels run one CTA per SM with a
+// static tile partition; when a concurrent kernel on another stream (an NCCL collective overlapped with backward) holds k
+// SMs, k CTAs of the next launch cannot start until an SM frees up and the launch can take up to twice as long.  With a
+// reserve >= the collective's CTA count both run side by side at (sm_count - k) / sm_count of the tensor throughput.
+std::atomic<int> g_sm_reserve{0};
+static inline int persistent_sms() { return std::max(1, g_dev.sm_count - g_sm_reserve.load(std::memory_order_relaxed)); }
 
 static int ensure_device() {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -315,7 +321,7 @@ static int choose_n_split(const Params& P, const tpgan_conv_args* groups) {
       worst_tile = std::max(worst_tile, per_tile);
     }
     if (!ok) break;
-    const double cost = std::ceil(tiles / g_dev.sm_count) * worst_tile;
+    const double cost = std::ceil(tiles / persistent_sms()) * worst_tile;
     if (f == 1 || cost < best_cost * 0.9) { best_cost = cost; best = f; }
   }
   return best;
@@ -344,7 +350,7 @@ static int launch_tapgemm(Params& P, cudaStream_t st, int bf16) {
   auto kern = bf16 ? tapgemm_kernel<Params, true> : tapgemm_kernel<Params, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  int grid = std::min(tiles, g_dev.sm_count);
+  int grid = std::min(tiles, persistent_sms());
   if (const char* ev = getenv("TPGAN_GRID")) grid = std::min(grid, std::max(1, atoi(ev)));
   kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
@@ -417,7 +423,7 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
   auto kern = bf16 ? rowconv_kernel<true> : rowconv_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-  const int grid = std::min(P.total_tiles, g_dev.sm_count);
+  const int grid = std::min(P.total_tiles, persistent_sms());
   kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowconv launch: %s", cudaGetErrorString(e)); return 1; }
@@ -495,7 +501,7 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
   auto kern = bf16 ? rowstack_kernel<true> : rowstack_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-  const int grid = std::min(P.total_tiles, g_dev.sm_count);
+  const int grid = std::min(P.total_tiles, persistent_sms());
   kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowstack launch: %s", cudaGetErrorString(e)); return 1; }
@@ -777,7 +783,7 @@ static int launch_wgrad(Params& P, cudaStream_t st, int bf16) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   // balanced schedule: every CTA gets total_work / grid (+-1) chunks (see SegmentWalk in wgrad.cu)
-  const int grid = (int)std::min<long long>(work, g_dev.sm_count);
+  const int grid = (int)std::min<long long>(work, persistent_sms());
   kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
@@ -892,6 +898,10 @@ int tpgan_set_deterministic(int32_t on) {
   return prev;
 }
 int tpgan_get_deterministic(void) { return g_deterministic.load(); }
+int tpgan_set_sm_reserve(int32_t sms) {
+  const int prev = g_sm_reserve.exchange(std::max(0, std::min((int)sms, 64)));
+  return prev;
+}
 int tpgan_last_conv_kernel(void) { return g_last_conv_kernel; }
 
 }  // extern "C"

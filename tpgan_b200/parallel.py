@@ -31,8 +31,10 @@ def plan_buckets(sizes: Sequence[int], ready: Sequence[int], bucket_elems: int) 
 
 
 def allreduce_sum(t: torch.Tensor, group=None):
+    """Sum all-reduce enqueued on the CURRENT stream (no host blocking: with NCCL, async_op=False only orders the stream
+    after the collective).  Stream-ordered and event-free on the host side, so it can be captured into a CUDA graph."""
     import torch.distributed as dist
-    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=False)
 
 
 class BucketReducer:
@@ -87,14 +89,11 @@ class BucketReducer:
                 ev.record()
                 self.comm.wait_event(ev)
                 with torch.cuda.stream(self.comm):
-                    self.works.append(allreduce_sum(flat.grad[off:off + cnt], self.group))
+                    allreduce_sum(flat.grad[off:off + cnt], self.group)
             idx = self.ready[i1 - 1]
             prev = hk.get(idx)
             hk[idx] = fn if prev is None else (lambda a=prev, b=fn: (a(), b()))
         return hk
 
     def finish(self):
-        for w in self.works:
-            w.wait()
-        self.works = []
-        torch.cuda.current_stream().wait_stream(self.comm)
+        torch.cuda.current_stream().wait_stream(self.comm)     # join: every bucket's all-reduce precedes the optimizer

@@ -186,7 +186,7 @@ class LayerSet:
 
 # ---------------------------------------------------------------------------------------------------------- CUDA graphs
 class Eager:
-    """Marks a schedule entry that must run eagerly (collectives, host-visible side effects)."""
+    """Marks a schedule entry that must run eagerly (host-visible side effects)."""
 
     def __init__(self, fn):
         self.fn = fn
@@ -195,15 +195,21 @@ class Eager:
         self.fn()
 
 
+class Collective(Eager):
+    """A stream-ordered NCCL collective (possibly forked onto a communication stream with events).  Runs eagerly between
+    graph segments by default; with GraphRunner(capture_collectives=True) it is captured INTO the graph like any other
+    launch (torch's NCCL process group is capturable), so a data-parallel step is a single graph replay."""
+
+
 class GraphRunner:
     """Replays a schedule (list of callables) as CUDA graphs: every maximal run of capturable entries becomes one graph,
     `Eager` entries run between them.  All device pointers in a schedule are static (pre-allocated plans)."""
 
-    def __init__(self, schedule: Sequence[Callable]):
+    def __init__(self, schedule: Sequence[Callable], capture_collectives: bool = False):
         self.segments: list = []
         run: List[Callable] = []
         for f in schedule:
-            if isinstance(f, Eager):
+            if isinstance(f, Eager) and not (capture_collectives and isinstance(f, Collective)):
                 if run:
                     self.segments.append(run)
                     run = []
@@ -535,7 +541,8 @@ class TPGANTrainer:
 
     def __init__(self, G: Generator, D: Discriminator, B: int, device="cuda", use_dropout: bool = False,
                  exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0, use_graphs: bool = False,
-                 identity_net=None, input_format: str = "float", dtype: str = "tf32"):
+                 identity_net=None, input_format: str = "float", dtype: str = "tf32", overlap_allreduce: bool = True,
+                 graph_collectives: bool = False, force_reducer: bool = False):
         """identity_net: optional frozen FeatureExtractModel / ResNet18 in eval() mode; adds the identity-preserving
         term weight_identity_preserving * L_ip to the generator loss.
         dtype: "tf32" (BASELINE configs[1]) or "bf16" (configs[2]): bf16 tensor-core operands (activations, activation
@@ -543,6 +550,10 @@ class TPGANTrainer:
         fp32 residual / gradient accumulation and losses."""
         assert dtype in ("tf32", "bf16")
         self.dtype, self.bf16 = dtype, dtype == "bf16"
+        # data parallelism: overlap_allreduce = bucketed all-reduce of G's gradients on a side stream during backward (else
+        # one all-reduce after backward); graph_collectives = capture the NCCL calls into the step's CUDA graph (one replay
+        # per step instead of one graph segment per bucket); force_reducer = build the bucket reducer on a 1-rank group (tests)
+        self.overlap_allreduce, self.graph_collectives, self.force_reducer = overlap_allreduce, graph_collectives, force_reducer
         assert not (self.bf16 and exact), "exact is the tf32 verification mode"
         self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
         if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for net in (G, D) for m in net.modules()):
@@ -579,7 +590,7 @@ class TPGANTrainer:
         self.g_set.repack()
         self.d_set.repack()
         self.reducer = None
-        if world_size > 1:
+        if (world_size > 1 and self.overlap_allreduce) or self.force_reducer:
             from .parallel import BucketReducer
             self.reducer = BucketReducer(self, bucket_mb, group)
         self.sums = torch.zeros(16, dtype=torch.float32, device=self.device)  # 0..7 image terms, 8..11 local parts, 12 ce, 13..14 identity
@@ -721,8 +732,8 @@ class TPGANTrainer:
         sch.append(self.d_set.export)
         d_logits = self._d_logits
         sch.append(lambda: ops.view_copy(_sl(crit.logits, 0, 2 * B), Act(d_logits, 0, 1)))
-        if self.world_size > 1:
-            sch.append(Eager(lambda: self._allreduce(self.flat_d.grad)))
+        if self.world_size > 1 or self.force_reducer:
+            sch.append(Collective(lambda: self._allreduce(self.flat_d.grad)))
         if optimize:
             sch.append(lambda: self.flat_d.adam(self.lr, 1.0 / self.world_size))
             sch.append(self.d_set.repack)
@@ -749,11 +760,13 @@ class TPGANTrainer:
             for i, f in enumerate(self.plan.bwd):
                 sch.append(f)
                 if (i + 1) in hooks:
-                    sch.append(Eager(hooks[i + 1]))
-            sch.append(Eager(self.reducer.finish))
+                    sch.append(Collective(hooks[i + 1]))
+            sch.append(Collective(self.reducer.finish))
         else:
             sch += self.plan.bwd
             sch.append(self.g_set.export)
+            if self.world_size > 1:     # one all-reduce of the whole flat gradient after backward
+                sch.append(Collective(lambda: self._allreduce(self.flat_g.grad)))
         if optimize:
             sch.append(lambda: self.flat_g.adam(self.lr, 1.0 / self.world_size))
             sch.append(self.g_set.repack)
@@ -771,7 +784,7 @@ class TPGANTrainer:
         key = (optimize, self.fixed_mask)
         if key not in self._sched:
             sch = self._schedule(optimize)
-            self._sched[key] = GraphRunner(sch) if self.use_graphs else sch
+            self._sched[key] = GraphRunner(sch, capture_collectives=self.graph_collectives) if self.use_graphs else sch
         sch = self._sched[key]
         if self.use_graphs:
             sch.run()
