@@ -236,6 +236,12 @@ TPGAN_API int tpgan_adam_step(float* p, const float* g, float* m, float* v, int6
  * corrections), so the launch can be captured in a CUDA graph and replayed. */
 TPGAN_API int tpgan_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, int32_t* step_dev, float grad_scale, void* stream);
+/* The same update over a SLICE of the flat buffers; increment != 0 advances the device-resident step count first (exactly one
+ * call per optimizer step must do so).  Data-parallel runs update bucket after bucket, each as soon as its all-reduce has
+ * finished, so the NCCL transfer of bucket i+1 overlaps the HBM-bound update + re-pack of bucket i. */
+TPGAN_API int tpgan_adam_slice_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                                   float eps, float weight_decay, int32_t* step_dev, float grad_scale, int32_t increment,
+                                   void* stream);
 
 /* Per-sample gradient-penalty helpers: norms[n] = ||g[n]||_2 ; u = coeff[n] * g. */
 TPGAN_API int tpgan_sample_sqnorm(tpgan_view g, float* sqnorm, void* stream);

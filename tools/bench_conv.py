@@ -57,12 +57,16 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--kinds", default="fwd,dgrad,wgrad")
     ap.add_argument("--out", default="")
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"])
     a = ap.parse_args()
+    bf16 = a.dtype == "bf16"
+    arena = ops.Arena("cuda", shadow=bf16)
+    ops._ARENA.append(arena)      # every buffer below comes from the (shadowed, in bf16 mode) arena
     peaks = {}
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peaks = json.load(open(p))
-    tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2
+    tf32_peak = peaks.get("bf16_tflops", 1590.0) / (1 if bf16 else 2)
     flush = torch.zeros(64 * 1024 * 1024, device="cuda")  # 256 MB
     B = a.batch
     rows = []
@@ -92,21 +96,33 @@ def main():
         dx = ops.Act.empty(B, H, H, cin)
         w = torch.empty(wshape, device="cuda").uniform_(-0.05, 0.05, generator=g)
         bias = torch.zeros(ops.round_up(cout, 4), device="cuda")
-        wf = ops.pack_weights(w, kf)
-        wd = ops.pack_weights(w, kd)
+        wf = ops.pack_weights(w, kf, round_tf32=not bf16)
+        wd = ops.pack_weights(w, kd, round_tf32=not bf16)
+        if bf16:
+            wf16, wd16 = ops.alloc_packed16(wf), ops.alloc_packed16(wd)
+            ops.cast_packed(wf, wf16)
+            ops.cast_packed(wd, wd16)
+            ops.cast_bf16(x)
+            ops.cast_bf16(dy)
+            wf, wd = wf16, wd16
         dw = ops.alloc_packed(kf, wshape)
+        o32 = os.environ.get("BENCH_NO_FP32_OUT") is None
         fns = {
-            "fwd": lambda: ops.conv2d(kf, x, y, wf, k, s, pad, bias=bias, slope=0.01, epilogue=ops.EPI_LEAKY),
-            "dgrad": lambda: ops.conv2d(kd, dy, dx, wd, k, s, pad, mask=x, slope=0.01, epilogue=ops.EPI_MASK),
-            "wgrad": lambda: ops.wgrad(kf, x, dy, dw, k, s, pad),
+            "fwd": lambda: ops.conv2d(kf, x, y, wf, k, s, pad, bias=bias, slope=0.01, epilogue=ops.EPI_LEAKY,
+                                      **(dict(bf16=True, out32=o32) if bf16 else {})),
+            "dgrad": lambda: ops.conv2d(kd, dy, dx, wd, k, s, pad, mask=x, slope=0.01, epilogue=ops.EPI_MASK,
+                                        **(dict(bf16=True, out32=o32) if bf16 else {})),
+            "wgrad": lambda: ops.wgrad(kf, x, dy, dw, k, s, pad, bf16=bf16),
         }
         for kind in a.kinds.split(","):
             ms = timeit(fns[kind], a.iters, flush)
             tf = 2 * macs / ms / 1e9
-            row = dict(shape=name, kind=kind, batch=B, ms=round(ms, 4), tflops=round(tf, 1), frac_tf32_peak=round(tf / tf32_peak, 3))
+            row = dict(shape=name, kind=kind, dtype=a.dtype, batch=B, ms=round(ms, 4), tflops=round(tf, 1), frac_peak=round(tf / tf32_peak, 3))
             rows.append(row)
             print(json.dumps(row), flush=True)
         del x, y, dy, dx, w, wf, wd, dw
+        arena.chunk = None          # start a fresh chunk per shape: the previous one is freed with its last view
+        arena.twins.clear()
         torch.cuda.empty_cache()
     from tpgan_b200 import _lib
     assert _lib.kernel_status() == 0

@@ -98,6 +98,7 @@ SYMBOLS = {
     "tpgan_maxout2_backward": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
     "tpgan_adam_step": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _F, _I32, _F, _VP]),
     "tpgan_adam_step_dev": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _F, _VP, _F, _VP]),
+    "tpgan_adam_slice_dev": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _F, _F, _F, _F, _F, _VP, _F, _I32, _VP]),
     "tpgan_sample_sqnorm": (C.c_int, [View, _VP, _VP]),
     "tpgan_sample_scale": (C.c_int, [View, _VP, View, _VP]),
     "tpgan_gp_coeff": (C.c_int, [_VP, _VP, _I32, _F, _VP, _VP]),

@@ -1445,11 +1445,23 @@ int tpgan_split_tf32(tpgan_view src, tpgan_view hi, tpgan_view lo, void* stream)
   return 0;
 }
 
+static int adam_dev_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int32_t* step_dev, float grad_scale, int increment, void* stream);
 int tpgan_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                         float weight_decay, int32_t* step_dev, float grad_scale, void* stream) {
+  return adam_dev_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale, 1, stream);
+}
+int tpgan_adam_slice_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int32_t* step_dev, float grad_scale, int32_t increment, void* stream) {
+  return adam_dev_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale, increment, stream);
+}
+static int adam_dev_launch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int32_t* step_dev, float grad_scale, int increment, void* stream) {
   if (!p || !g || !m || !v || !step_dev || n <= 0) return set_error(TPGAN_ERR_INVALID, "adam_step_dev: bad args");
-  counter_inc_kernel<<<1, 1, 0, ST>>>(step_dev);
-  TPG_CHECK_LAUNCH("counter_inc");
+  if (increment) {
+    counter_inc_kernel<<<1, 1, 0, ST>>>(step_dev);
+    TPG_CHECK_LAUNCH("counter_inc");
+  }
   const bool vec = (n % 4 == 0) && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   if (vec)
     adam_dev_vec4_kernel<<<grid_for(n / 4, 256, 16), 256, 0, ST>>>(

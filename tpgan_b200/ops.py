@@ -437,6 +437,15 @@ def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev: tor
                "adam_step_dev")
 
 
+def adam_slice_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev: torch.Tensor, grad_scale=1.0,
+                   increment: bool = False) -> None:
+    """Adam over a slice of the flat buffers (see tpgan_adam_slice_dev): the step count is advanced by the first slice only."""
+    assert step_dev.dtype == torch.int32 and step_dev.is_cuda and p.numel() == g.numel()
+    _lib.check(_lib.load().tpgan_adam_slice_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1,
+                                                beta2, eps, weight_decay, step_dev.data_ptr(), grad_scale, int(increment),
+                                                _stream()), "adam_slice_dev")
+
+
 def sample_sqnorm(g: Act, out: torch.Tensor) -> None:
     _lib.check(_lib.load().tpgan_sample_sqnorm(g.view(), out.data_ptr(), _stream()), "sample_sqnorm")
 
