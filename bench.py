@@ -238,6 +238,10 @@ def gan_line(a, B, dtype, identity, steps, warmup, world, rank, dev, want_roofli
         ev = []
         torch.cuda.synchronize()
         tr.load_inputs(devb)
+        # eager launches cost the host ~10-20 us each (planning + tensor-map encoding), more than the small kernels run: keep
+        # the device queue full (the host enqueues the whole step behind a ~30 ms spin) so that the events bracket kernel
+        # execution, not the GPU waiting for the next launch
+        torch.cuda._sleep(int(0.03 * 1.9e9))
         for f in tr._schedule(True):
             if isinstance(f, Eager):
                 continue                 # collectives: the other ranks are not here
@@ -273,6 +277,7 @@ def gan_line(a, B, dtype, identity, steps, warmup, world, rank, dev, want_roofli
         names = {"tapgemm": f"tapgemm_kernel (tcgen05 {dtype} multi-tap implicit-GEMM conv fwd/dgrad/deconv/linear)",
                  "rowconv": f"rowconv_kernel (tcgen05 {dtype} row-tile conv for the wide 128x128 stride-1 layers, fwd/dgrad)",
                  "rowstack": f"rowstack_kernel (tcgen05 {dtype} N-stacked row-tile conv for the narrow 128x128 layers, fwd/dgrad)",
+                 "flatconv": f"flatconv_kernel (tcgen05 {dtype} flat-slab conv for the small-map stride-1 layers, fwd/dgrad)",
                  "wgrad": f"wgrad_kernel (tcgen05 {dtype} weight-gradient GEMM over pixels)"}
         step_ms = ms / steps
         ncu = _ncu_summary(dtype, B)

@@ -272,6 +272,145 @@ def test_grouped_local_pathway_shapes():
         assert rel(o.to_nchw(), r) < TOL
 
 
+FLAT_CASES = [
+    # n, cin, cout, h, w, k  (stride 1, "same" padding): the flat-slab kernel (csrc/flatconv.cu) in forced mode
+    (5, 64, 64, 40, 40, 3),      # local conv0.x: T = 2 row units
+    (5, 128, 128, 20, 20, 3),    # local conv1.x
+    (5, 128, 128, 16, 24, 3),    # mouth patch at half resolution
+    (6, 256, 256, 10, 10, 3),    # local conv2.x: one image per unit
+    (7, 256, 256, 8, 10, 3),     # nose patch at quarter resolution
+    (8, 96, 64, 8, 8, 3),        # whole-image units: four images per three-tile unit
+    (7, 96, 64, 8, 8, 3),        # ... with a ragged last unit
+    (3, 75, 40, 24, 24, 5),      # 5x5 taps, partial last K chunk, ragged channel count
+    (2, 320, 512, 12, 12, 3),    # two N tiles
+    (5, 3, 64, 40, 40, 3),       # one partial K chunk
+    (2, 64, 3, 33, 17, 3),       # ragged map, 3 output channels
+    (2, 64, 64, 64, 64, 5),      # global-pathway conv1.x: four-tile units, 25 taps, two slab slots
+    (2, 80, 80, 64, 64, 5),
+    (2, 128, 128, 32, 32, 3),    # global-pathway conv2.x
+    (32, 64, 64, 40, 40, 3),     # production batch: several units per CTA (ring / accumulator phases wrap)
+    (32, 64, 64, 64, 64, 5),
+    (32, 80, 80, 64, 64, 5),
+    (32, 128, 128, 32, 32, 3),
+]
+
+
+@pytest.mark.parametrize("case", FLAT_CASES)
+def test_flatconv_fwd_dgrad(case, monkeypatch):
+    from tpgan_b200 import ops, _lib
+    monkeypatch.setenv("TPGAN_FLATCONV", "2")
+    n, cin, cout, h, w, k = case
+    p = (k - 1) // 2
+    x = _mk(n, cin, h, w, 1)
+    wt = _mk(cout, cin, k, k, 2) * (1.0 / (cin * k * k) ** 0.5)
+    b = _mk(1, cout, 1, 1, 3).flatten()
+    res = _mk(n, cout, h, w, 4)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=p) + res, 0.01)
+    out = ops.Act.empty(n, h, w, cout)
+    pw = ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True)
+    ops.conv2d(ops.CONV_FWD, _act(x, ops), out, pw, k, 1, p, bias=b.cuda(), add1=_act(res, ops), slope=0.01,
+               epilogue=ops.EPI_LEAKY, round_tf32=True)
+    assert _lib.last_conv_kernel() == "flatconv"
+    torch.cuda.synchronize()
+    assert _lib.kernel_status() == 0
+    assert rel(out.to_nchw(), ref) < TOL
+    dy, a1, msrc = _mk(n, cout, h, w, 5), _mk(n, cin, h, w, 6), _mk(n, cin, h, w, 7)
+    g = torch.nn.grad.conv2d_input((n, cin, h, w), wt, dy, padding=p) + a1
+    refm = torch.where(msrc > 0, g, g * 0.01)
+    dx = ops.Act.empty(n, h, w, cin)
+    pwd = ops.pack_weights(wt.cuda(), ops.CONV_DGRAD, round_tf32=True)
+    ops.conv2d(ops.CONV_DGRAD, _act(dy, ops), dx, pwd, k, 1, p, add1=_act(a1, ops), mask=_act(msrc, ops), slope=0.01,
+               epilogue=ops.EPI_MASK, round_tf32=True)
+    assert _lib.last_conv_kernel() == "flatconv"
+    torch.cuda.synchronize()
+    assert _lib.kernel_status() == 0
+    assert rel(dx.to_nchw(), refm) < TOL
+
+
+@pytest.mark.parametrize("div,cin,cout", [(1, 64, 64), (2, 128, 128), (4, 256, 256)])
+def test_flatconv_grouped_matches_tapgemm(div, cin, cout, monkeypatch):
+    """The four local-pathway patches of one layer in one flat-slab launch: same results (to tf32 accumulation order) as the
+    multi-tap GEMM kernel and as ATen."""
+    from tpgan_b200 import ops, _lib
+    shapes = [(40 // div, 40 // div), (40 // div, 40 // div), (32 // div, 40 // div), (32 // div, 48 // div)]
+    n = 5
+    args, refs, keep = [], [], []
+    for i, (h, w) in enumerate(shapes):
+        x = _mk(n, cin, h, w, 10 + i)
+        wt = _mk(cout, cin, 3, 3, 20 + i) * (1.0 / (cin * 9) ** 0.5)
+        b = _mk(1, cout, 1, 1, 30 + i).flatten()
+        refs.append(F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.01))
+        xa, bc, pw = _act(x, ops), b.cuda(), ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True)
+        keep += [xa, bc, pw]
+        args.append((xa, pw, bc, h, w))
+    outs = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("TPGAN_FLATCONV", mode)
+        o = [ops.Act.empty(n, h, w, cout) for (_, _, _, h, w) in args]
+        l0 = _lib.launch_count()
+        ops.conv2d_grouped([ops.conv_args(ops.CONV_FWD, xa, oo, pw, 3, 1, 1, bias=bc, slope=0.01, epilogue=ops.EPI_LEAKY,
+                                          round_tf32=True) for (xa, pw, bc, _, _), oo in zip(args, o)])
+        assert _lib.launch_count() - l0 == 1
+        assert _lib.last_conv_kernel() == ("flatconv" if mode == "2" else "tapgemm")
+        torch.cuda.synchronize()
+        assert _lib.kernel_status() == 0
+        outs[mode] = o
+    for a, b_, r in zip(outs["0"], outs["2"], refs):
+        assert rel(b_.to_nchw(), r) < TOL
+        assert rel(b_.to_nchw(), a.to_nchw()) < 2e-4
+
+
+GROUPED_WGRAD_CASES = [
+    # (cin, cout, k, stride, pad, kind, patch sizes of the four pathways at this depth) - D_and_G_model.py:390-393 patches
+    # 40x40 / 40x40 / 32x40 / 32x48 after 0..3 stride-2 convs.  10x10 and 5x5 boxes do not fill their last 8-pixel K step while
+    # the nose / mouth boxes do: the launch mixes box shapes and must re-zero the unwritten K rows every stage.
+    (64, 64, 3, 1, 1, "conv", [(40, 40), (40, 40), (32, 40), (32, 48)]),
+    (128, 128, 3, 1, 1, "conv", [(20, 20), (20, 20), (16, 20), (16, 24)]),
+    (256, 256, 3, 1, 1, "conv", [(10, 10), (10, 10), (8, 10), (8, 12)]),
+    (512, 512, 3, 1, 1, "conv", [(5, 5), (5, 5), (4, 5), (4, 6)]),
+    (256, 512, 3, 2, 1, "conv", [(10, 10), (10, 10), (8, 10), (8, 12)]),
+    (512, 256, 3, 2, 1, "deconv", [(5, 5), (5, 5), (4, 5), (4, 6)]),
+]
+
+
+@pytest.mark.parametrize("case", GROUPED_WGRAD_CASES)
+def test_grouped_local_pathway_wgrad(case):
+    """The four pathways' weight gradients of one layer in ONE launch (mixed pixel-box shapes included), each equal to ATen's."""
+    from tpgan_b200 import ops, _lib
+    cin, cout, k, s, p, kind, shapes = case
+    n = 5
+    args, refs, dws, keep = [], [], [], []
+    for i, (h, w) in enumerate(shapes):
+        x = _mk(n, cin, h, w, 40 + i)
+        if kind == "conv":
+            ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+            dy = _mk(n, cout, ho, wo, 50 + i)
+            refs.append(torch.nn.grad.conv2d_weight(x, (cout, cin, k, k), dy, stride=s, padding=p))
+            wshape, akind = (cout, cin, k, k), ops.CONV_FWD
+        else:
+            ho, wo = (h - 1) * s - 2 * p + k + 1, (w - 1) * s - 2 * p + k + 1
+            dy = _mk(n, cout, ho, wo, 50 + i)
+            wt = torch.zeros(cin, cout, k, k, requires_grad=True)
+            F.conv_transpose2d(x, wt, stride=s, padding=p, output_padding=1).backward(dy)
+            refs.append(wt.grad)
+            wshape, akind = (cin, cout, k, k), ops.DECONV_FWD
+        xa, dya = _act(x, ops), _act(dy, ops)
+        dw = ops.alloc_packed(akind, wshape)
+        keep += [xa, dya]
+        dws.append((dw, wshape, akind))
+        args.append(ops.wgrad_args(akind, xa, dya, dw, k, s, p, accumulate=False))
+    l0 = _lib.launch_count()
+    ops.wgrad_grouped(args)
+    assert _lib.launch_count() - l0 == 1, "grouped weight gradients must be one launch"
+    for (dw, wshape, akind), ref in zip(dws, refs):
+        got = torch.zeros(wshape, device="cuda")
+        ops.unpack_weights(dw, got, akind)
+        torch.cuda.synchronize()
+        err = rel(got, ref)
+        assert err < TOL, err
+    assert _lib.kernel_status() == 0
+
+
 # ---- full-size (BASELINE config 1, batch 32) size-independent property: the three kernels of a layer are adjoint.
 #   <conv(x, w), dy> = <x, dgrad(dy, w)> = <w, wgrad(x, dy)>
 # With tf32-representable x, w, dy every product is exact in the tensor cores, so the three inner products differ only

@@ -105,6 +105,26 @@ def test_image_losses_values_and_gradient():
     assert float(bad) < 1e-3 and float((g - r).norm() / r.norm()) < 2e-2
 
 
+def test_image_losses_tiled_matches_generic(monkeypatch):
+    """The shared-memory tiled kernel (the one the step's float4 layout takes) against the per-element kernel: gradients
+    bit-identical, sums to fp32 addition order."""
+    from tpgan_b200 import ops
+    B = 5
+    fake, gt = _rand(B, 3, 128, 128, seed=11), _rand(B, 3, 128, 128, seed=12)
+    t64, t32 = F.avg_pool2d(gt, 2), F.avg_pool2d(gt, 4)
+    coeffs = [1e-6 * (i + 1) for i in range(8)]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TPGAN_IMAGE_LOSSES_GENERIC", mode)
+        df = ops.Act.empty(B, 128, 128, 3)
+        sums = torch.zeros(8, device="cuda")
+        ops.image_losses(_act(fake), _act(gt), _act(t64), _act(t32), df, coeffs, sums)
+        torch.cuda.synchronize()
+        res[mode] = (df.to_nchw().cpu(), sums.cpu())
+    assert torch.equal(res["0"][0], res["1"][0])
+    assert torch.allclose(res["0"][1], res["1"][1], rtol=1e-5)
+
+
 def test_l1_ce_maxout_lerp_mul():
     from tpgan_b200 import ops
     a, b = _rand(4, 3, 32, 48, seed=1), _rand(4, 3, 32, 48, seed=2)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--div", type=int, default=1)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--kinds", default="fwd,dgrad,wgrad")
+    ap.add_argument("--chain", type=int, default=0, help="also time N back-to-back launches replayed as one CUDA graph (warm caches)")
     a = ap.parse_args()
     shapes = [(40 // a.div, 40 // a.div), (40 // a.div, 40 // a.div), (32 // a.div, 40 // a.div), (32 // a.div, 48 // a.div)]
     B, k, p = a.batch, a.k, (a.k - 1) // 2
@@ -43,11 +44,53 @@ def main():
         macs += B * h * w * a.cin * a.cout * k * k
     fns = {"fwd": lambda: ops.conv2d_grouped(fa), "dgrad": lambda: ops.conv2d_grouped(da), "wgrad": lambda: ops.wgrad_grouped(wa)}
     flush = torch.zeros(64 * 1024 * 1024, device="cuda")
+
+    def graph_ms(fn, reps=8):
+        # device-side time of one launch: (flush + launch) x reps replayed as a CUDA graph minus the flushes alone - the eager
+        # event timing below includes the host's planning of a 4-group launch (tens of microseconds), the step does not
+        def cap(body):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    flush.add_(1.0)
+                    body()
+            return g
+        gs = [cap(fn), cap(lambda: None)]
+        out = []
+        for g in gs:
+            g.replay()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            out.append(min(ts))
+        return (out[0] - out[1]) / reps
+
     for kind in a.kinds.split(","):
         fn = fns[kind]
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
+        gms = graph_ms(fn)
+        cms = None
+        if a.chain:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(a.chain):
+                    fn()
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            e1.synchronize()
+            cms = e0.elapsed_time(e1) / a.chain
         ts = []
         for _ in range(a.iters):
             flush.add_(1.0)
@@ -59,8 +102,9 @@ def main():
             ts.append(e0.elapsed_time(e1))
         ts.sort()
         ms = ts[len(ts) // 2]
-        print(json.dumps(dict(kind=kind, cin=a.cin, cout=a.cout, k=k, div=a.div, ms=round(ms, 4),
-                              tflops=round(2 * macs / ms / 1e9, 1))), flush=True)
+        print(json.dumps(dict(kind=kind, cin=a.cin, cout=a.cout, k=k, div=a.div, kernel=_lib.last_conv_kernel() if kind != "wgrad" else "wgrad",
+                              ms=round(ms, 4), tflops=round(2 * macs / ms / 1e9, 1), graph_ms=round(gms, 4),
+                              graph_tflops=round(2 * macs / gms / 1e9, 1), chain_ms=None if cms is None else round(cms, 4))), flush=True)
     assert _lib.kernel_status() == 0
 
 

@@ -161,7 +161,7 @@ def launch_count() -> int:
 
 def last_conv_kernel() -> str:
     """Which kernel the most recent conv2d call of this thread launched."""
-    return ("tapgemm", "rowconv", "rowstack")[int(load().tpgan_last_conv_kernel())]
+    return ("tapgemm", "rowconv", "rowstack", "flatconv")[int(load().tpgan_last_conv_kernel())]
 
 
 def set_deterministic(on: bool) -> bool:

@@ -26,6 +26,8 @@ __global__ void tapgemm_kernel(const __grid_constant__ Params P, int* status);
 template <class Params, bool BF16>
 __global__ void wgrad_kernel(const __grid_constant__ Params P, int* status);
 template <bool BF16>
+__global__ void flatconv_kernel(const __grid_constant__ FlatConvParams P, int* status);
+template <bool BF16>
 __global__ void rowconv_kernel(const __grid_constant__ RowConvParams P, int* status);
 template <bool BF16>
 __global__ void rowstack_kernel(const __grid_constant__ RowStackParams P, int* status);
@@ -67,6 +69,34 @@ std::atomic<int> g_deterministic{0};
 // reserve >= the collective's CTA count both run side by side at (sm_count - k) / sm_count of the tensor throughput.
 std::atomic<int> g_sm_reserve{0};
 static inline int persistent_sms() { return std::max(1, g_dev.sm_count - g_sm_reserve.load(std::memory_order_relaxed)); }
+
+// Tensor-core kernels are launched as programmatic dependents of the kernel before them in the stream (captured into CUDA
+// graphs as programmatic edges): their CTAs become resident as the previous grid's CTAs exit and run the prologue early;
+// griddepcontrol.wait in the kernel orders every global-memory access after the previous grid's completion.
+// TPGAN_PDL=0 falls back to plain stream serialisation (for A/B measurements).
+std::atomic<int> g_pdl{-1};
+template <class Kern, class Params>
+static cudaError_t launch_tc(Kern kern, int grid, int smem, cudaStream_t st, const Params& P) {
+  int pdl = g_pdl.load(std::memory_order_relaxed);
+  if (pdl < 0) {
+    const char* ev = getenv("TPGAN_PDL");
+    pdl = (ev && atoi(ev) == 0) ? 0 : 1;
+    g_pdl.store(pdl, std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)kConvThreads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1u : 0u;
+  int* status = g_dev.status_dev;
+  void* args[2] = {const_cast<Params*>(&P), &status};
+  return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), args);
+}
 
 static int ensure_device() {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -352,8 +382,7 @@ static int launch_tapgemm(Params& P, cudaStream_t st, int bf16) {
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int grid = std::min(tiles, persistent_sms());
   if (const char* ev = getenv("TPGAN_GRID")) grid = std::min(grid, std::max(1, atoi(ev)));
-  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
-  e = cudaGetLastError();
+  e = launch_tc(kern, grid, smem, st, P);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -424,8 +453,7 @@ static int try_rowconv(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
   const int grid = std::min(P.total_tiles, persistent_sms());
-  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
-  e = cudaGetLastError();
+  e = launch_tc(kern, grid, smem, st, P);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowconv launch: %s", cudaGetErrorString(e)); return 1; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 1;
@@ -502,9 +530,145 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
   const int grid = std::min(P.total_tiles, persistent_sms());
-  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
-  e = cudaGetLastError();
+  e = launch_tc(kern, grid, smem, st, P);
   if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "rowstack launch: %s", cudaGetErrorString(e)); return 1; }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ flat-slab conv
+// Eligible: Conv2d forward / input gradient, stride 1, "same" padding, k >= 3, maps up to 64 pixels wide - every group of the
+// launch.  Opt-in (TPGAN_FLATCONV=1) where tapgemm is bound by L2 -> SM operand traffic: at most 128 (padded)
+// output channels, i.e. the 64- and 128-channel layers of the local pathways; TPGAN_FLATCONV=2 takes every eligible
+// launch, 0 none.  Returns 1 when launched (or failed with *rc_out set), 0 when not eligible.
+struct FlatChoice {
+  int T, ur, bn;
+  double eff;   // real pixels / M rows computed
+};
+static FlatChoice choose_flat(int H, int W, int N, int k, int block_n) {
+  // every (T, unit shape) candidate; the winner is the LARGEST T (most weight reuse) within 3 % of the best efficiency
+  FlatChoice cand[8];
+  int nc = 0;
+  const int Wp = W + k - 1;
+  const int Tmax = std::min(4, 256 / block_n);
+  for (int T = 1; T <= Tmax; ++T) {
+    const int rows = T * 128;
+    FlatChoice c{T, 0, 0, 0.0};
+    const int ur = std::min(H, rows / Wp);
+    if (ur >= 1 && ur + k - 1 <= 256) c = FlatChoice{T, ur, 1, (double)H * W / ((double)ceil_div(H, ur) * rows)};
+    const int ipitch = (H + k - 1) * Wp;
+    if (H * Wp <= rows && H + k - 1 <= 256) {
+      const int bn = std::min(N, 1 + (rows - H * Wp) / ipitch);
+      const double eff = (double)N * H * W / ((double)ceil_div(N, bn) * rows);
+      if (bn >= 2 && eff > c.eff) c = FlatChoice{T, H, bn, eff};
+    }
+    if (c.ur > 0) cand[nc++] = c;
+  }
+  FlatChoice best{0, 0, 0, 0.0};
+  double top = 0.0;
+  for (int i = 0; i < nc; ++i) top = std::max(top, cand[i].eff);
+  for (int i = 0; i < nc; ++i)
+    if (cand[i].eff >= 0.97 * top) best = cand[i];
+  return best;
+}
+
+static int try_flatconv(const tpgan_conv_args* groups, int ngroups, cudaStream_t st, int* rc_out) {
+  *rc_out = 0;
+  const char* mode_ev = getenv("TPGAN_FLATCONV");   // read per call: tests switch it between launches
+  const int mode = mode_ev ? atoi(mode_ev) : 0;
+  if (mode == 0) return 0;
+  const tpgan_conv_args& a0 = groups[0];
+  if (const char* only = getenv("TPGAN_FLAT_ONLY")) {   // debugging aid: restrict the kernel to one class of launches
+    if ((!strcmp(only, "fwd") && a0.kind != TPGAN_CONV_FWD) || (!strcmp(only, "dgrad") && a0.kind != TPGAN_CONV_DGRAD) ||
+        (!strcmp(only, "single") && ngroups != 1) || (!strcmp(only, "grouped") && ngroups == 1))
+      return 0;
+  }
+  const int k = a0.kh, p = a0.pad;
+  if (a0.kind != TPGAN_CONV_FWD && a0.kind != TPGAN_CONV_DGRAD) return 0;
+  if (a0.kh != a0.kw || a0.stride != 1 || 2 * p != k - 1 || k < 3 || k * k > kMaxTaps) return 0;
+  const int bf16 = a0.dtype == TPGAN_DTYPE_BF16;
+  const int CH = chunk_ch(bf16);
+  FlatChoice ch[kMaxGroups];
+  int block_n[kMaxGroups], n_tiles[kMaxGroups];
+  for (int i = 0; i < ngroups; ++i) {
+    const tpgan_conv_args& a = groups[i];
+    if (a.kind != a0.kind || a.kh != k || a.kw != k || a.stride != 1 || a.pad != p || a.dtype != a0.dtype) return 0;
+    if (a.in.w != a.out.w || a.in.h != a.out.h || a.in.n != a.out.n) return 0;
+    if (a.in.w > 64 || a.in.w < 8 || a.in.w + k - 1 > 128) return 0;
+    n_tiles[i] = ceil_div(a.w_rows_pad, 256);
+    block_n[i] = ceil_div(ceil_div(a.w_rows_pad, n_tiles[i]), 16) * 16;
+    n_tiles[i] = ceil_div(a.w_rows_pad, block_n[i]);
+    if (mode == 1 && block_n[i] > 128) return 0;
+    ch[i] = choose_flat(a.in.h, a.in.w, a.in.n, k, block_n[i]);
+    if (ch[i].T < 1 || ch[i].eff < (mode == 1 ? 0.6 : 0.3)) return 0;
+  }
+  static thread_local FlatConvParams P;
+  memset(&P, 0, sizeof(P));
+  P.ngroups = ngroups;
+  P.k = k;
+  const bool fwd = a0.kind == TPGAN_CONV_FWD;
+  P.dy0 = fwd ? -p : p - k + 1;
+  P.dx0 = P.dy0;
+  for (int r = 0; r < k; ++r)
+    for (int j = 0; j < k; ++j)
+      P.wtap[r * k + j] = (unsigned char)(fwd ? (r * k + j) : ((k - 1 - r) * k + (k - 1 - j)));
+  int tiles = 0, slab_rows = 0, bmax = 0;
+  for (int i = 0; i < ngroups; ++i) {
+    const tpgan_conv_args& a = groups[i];
+    FlatGroup& G = P.g[i];
+    int rc = check_dtype(a);
+    if (rc) { *rc_out = rc; return 1; }
+    if (a.w_k_pad % CH || a.w_k_pad < a.in.c || a.w_rows_pad % 16 || a.w_rows_pad < a.out.c) {
+      *rc_out = set_error(TPGAN_ERR_INVALID, "packed weight dims (%d x %d) do not cover K=%d N=%d", a.w_rows_pad, a.w_k_pad, a.in.c, a.out.c);
+      return 1;
+    }
+    if (a.epilogue == TPGAN_EPI_MASK && a.mask.ptr == nullptr) { *rc_out = set_error(TPGAN_ERR_INVALID, "EPI_MASK needs a mask view"); return 1; }
+    G.H = a.out.h; G.W = a.out.w; G.Nimg = a.in.n;
+    G.Wp = G.W + k - 1;
+    G.T = ch[i].T; G.ur = ch[i].ur; G.bn = ch[i].bn;
+    G.R = G.ur + k - 1;
+    G.ipitch = G.R * G.Wp;
+    G.units_h = ceil_div(G.H, G.ur);
+    G.n_tiles = n_tiles[i];
+    G.block_n = block_n[i];
+    G.kchunks = ceil_div(a.in.c, CH);
+    G.last_mmas = ceil_div(a.in.c - CH * (G.kchunks - 1), mma_k(bf16));
+    G.tile_begin = tiles;
+    G.tile_count = G.units_h * ceil_div(G.Nimg, G.bn) * G.n_tiles;
+    tiles += G.tile_count;
+    G.slab_tx = G.bn * G.R * G.Wp * 128;
+    // rows an M = 128 MMA of the last tile / last tap may read (garbage rows beyond the box only reach rows never stored)
+    slab_rows = std::max(slab_rows, std::max(G.bn * G.R * G.Wp, G.T * 128 + (k - 1) * G.Wp + (k - 1)));
+    bmax = std::max(bmax, G.block_n * 128);
+    rc = encode_nhwc(&G.amap, a.in.ptr, a.in.c, a.in.w, a.in.h, a.in.n, a.in.sw, a.in.sh, a.in.sn, G.Wp, G.R, G.bn,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
+    if (rc) { *rc_out = rc; return 1; }
+    rc = encode_weights(&G.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, k * k + 1, G.block_n, CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
+    if (rc) { *rc_out = rc; return 1; }
+    G.out = to_dev(a.out); G.add1 = to_dev(a.add1); G.add2 = to_dev(a.add2); G.mask = to_dev(a.mask);
+    G.out16 = to_dev16(a.out16);
+    G.bias = a.bias; G.slopes = a.slopes;
+    G.cout_valid = a.out.c; G.epilogue = a.epilogue; G.slope = a.slope; G.round_tf32 = a.round_tf32;
+    G.vec_ok = view_vec_ok(a.out) && view_vec_ok(a.add1) && view_vec_ok(a.add2) && view_vec_ok(a.mask) && view16_ok(a.out16);
+  }
+  P.total_tiles = tiles;
+  P.slab_bytes = ceil_div(slab_rows * 128, 1024) * 1024;
+  P.b_bytes = bmax;
+  const int budget = g_dev.max_smem - 1024 - 1024;   // alignment slack + this kernel's static shared memory
+  P.a_slots = 3;
+  P.b_slots = std::min(16, (budget - P.a_slots * P.slab_bytes) / P.b_bytes);
+  if (P.b_slots < 4) {
+    P.a_slots = 2;
+    P.b_slots = std::min(16, (budget - P.a_slots * P.slab_bytes) / P.b_bytes);
+    if (P.b_slots < 3) return 0;
+  }
+  const int smem = P.a_slots * P.slab_bytes + P.b_slots * P.b_bytes + 1024;
+  auto kern = bf16 ? flatconv_kernel<true> : flatconv_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
+  if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+  const int grid = std::min(P.total_tiles, persistent_sms());
+  e = launch_tc(kern, grid, smem, st, P);
+  if (e != cudaSuccess) { *rc_out = set_error(TPGAN_ERR_CUDA, "flatconv launch: %s", cudaGetErrorString(e)); return 1; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 1;
 }
@@ -544,29 +708,58 @@ static WgradChoice wgrad_option(const tpgan_wgrad_args& a, bool swap, bool slab)
   c.nch_total = ceil_div(c.qc, CH);
   const long long npix = (long long)Pt.h * Pt.w * Pt.n;
   if (slab) {
-    c.ncpt = c.nch_total;
-    c.n_tiles = 1;
     static const int acc_cols = getenv("TPGAN_WGRAD_SLAB_COLS") ? atoi(getenv("TPGAN_WGRAD_SLAB_COLS")) : 512;
     const int acc_chunks = acc_cols / CH;     // CH-column accumulator blocks in TMEM
-    c.mpu = (c.m_tiles * c.ncpt * 2 <= acc_chunks) ? c.m_tiles : 1;   // (acc_chunks below may still shrink tpu)
-    const int tmax = std::min(std::min(k, NCH), acc_chunks / std::max(1, c.mpu * c.ncpt));   // N = tpu * CH <= 256
-    if (c.ncpt > NCH || tmax < 2) { c.cost = 1e30; return c; }
-    const int ngrp = ceil_div(k, tmax);
-    c.tpu = ceil_div(k, ngrp);
-    if (k * ngrp * c.tpu > kMaxTaps) { c.cost = 1e30; return c; }
-    c.block_n = c.tpu * CH;
-    c.a_ch = std::min(MCH * c.mpu, ceil_div(c.pc, CH));
-    c.b_ch = c.ncpt;
-    double row = 0;   // MMA cycles per K step for the taps of one kernel row, one M tile, one Q chunk
-    for (int g = 0, left = k; g < ngrp; ++g) {
-      const int nt = std::min(c.tpu, left);
-      left -= nt;
-      const int nn = nt * CH;   // N of the slab MMA
-      const double mma = std::max(nn / 2.0, 32.0 + nn / 4.0) * c.mpu * c.ncpt;
-      const double l2 = (c.a_ch + c.ncpt) * 1024.0 / kL2BytesPerClk;
-      row += std::max(mma, l2) * ceil_div(c.m_tiles, c.mpu);
-    }
-    c.cost = row * k;
+    c.cost = 1e30;
+    // wide Q tensors are cut into N tiles of ncpt chunks (each re-loads P) so that a whole kernel row of taps still fits TMEM
+    const int budget = g_dev.max_smem - 1024 - 256;
+    for (int nt = 1; nt <= 4; nt *= 2)
+      for (int share_m = 1; share_m >= 0; --share_m) {
+        WgradChoice o = c;
+        o.n_tiles = nt;
+        o.ncpt = ceil_div(c.nch_total, nt);
+        if (o.ncpt * nt != c.nch_total && nt > 1) continue;
+        o.mpu = (share_m && c.m_tiles * o.ncpt * 2 <= acc_chunks) ? c.m_tiles : 1;   // (acc_chunks below may still shrink tpu)
+        if (!share_m && c.m_tiles == 1) continue;
+        const int tmax = std::min(std::min(k, NCH), acc_chunks / std::max(1, o.mpu * o.ncpt));   // N = tpu * CH <= 256
+        if (o.ncpt > NCH || tmax < 2) continue;
+        const int ngrp = ceil_div(k, tmax);
+        o.tpu = ceil_div(k, ngrp);
+        if (k * ngrp * o.tpu > kMaxTaps) continue;
+        o.block_n = o.tpu * CH;
+        o.a_ch = std::min(MCH * o.mpu, ceil_div(c.pc, CH));
+        o.b_ch = o.ncpt;
+        double row = 0;   // MMA cycles per K step for the taps of one kernel row, one M tile, one Q chunk
+        for (int g = 0, left = k; g < ngrp; ++g) {
+          const int ntp = std::min(o.tpu, left);
+          left -= ntp;
+          const int nn = ntp * CH;   // N of the slab MMA
+          const double mma = std::max(nn / 2.0, 32.0 + nn / 4.0) * o.mpu * o.ncpt;
+          const double l2 = (o.a_ch + o.ncpt) * 1024.0 / kL2BytesPerClk;
+          row += std::max(mma, l2) * ceil_div(c.m_tiles, o.mpu);
+        }
+        // K rows spent per real pixel: narrow maps are boxed as whole rows with the padded pitch W + tpu - 1 (plan_wgrad),
+        // and every box is rounded up to the MMA K step
+        int px = 16;
+        for (int cand : {128, 64, 32}) {
+          const int sb = (o.a_ch * cand + o.b_ch * ceil_div(cand + o.tpu - 1, 8) * 8) * 128;
+          if (budget / sb >= (cand == 32 ? 3 : 4)) { px = cand; break; }
+        }
+        const int KR = mma_k(bf16);
+        const int pbw = Pt.w + o.tpu - 1;
+        double keff;
+        if (Pt.w <= px + px / 2 && px / pbw >= 2) {
+          const int bh = std::min(Pt.h, px / pbw);
+          const int bn = (bh == Pt.h) ? std::max(1, std::min(Pt.n, px / (pbw * bh))) : 1;
+          const int kp = ceil_div(pbw * bh * bn, KR) * KR;
+          keff = (double)Pt.h * Pt.w * bn / ((double)ceil_div(Pt.h, bh) * kp);
+        } else {
+          const int bw = (Pt.w <= px + px / 2) ? Pt.w : px;
+          keff = (double)Pt.w / ((double)ceil_div(Pt.w, bw) * ceil_div(bw, KR) * KR);
+        }
+        o.cost = row * k * nt / std::max(keff, 0.05);
+        if (o.cost < c.cost) { const bool sw = c.swap; c = o; c.swap = sw; c.slab = true; }
+      }
     return c;
   }
   if (c.nch_total <= tap_pack_max && ntaps > 1 && !no_pack) {
@@ -603,7 +796,8 @@ static WgradChoice choose_wgrad(const tpgan_wgrad_args& a) {
   const bool is_conv = (a.kind == TPGAN_CONV_FWD);
   const tpgan_view& Pt = is_conv ? a.dy : a.x;
   // slab mode needs unit-stride taps along W and row-segment boxes worth a pipeline stage
-  if (slab_mode && a.stride == 1 && a.kh >= 2 && Pt.w >= 32) {
+  static const int slab_min_w = getenv("TPGAN_WGRAD_SLAB_MINW") ? atoi(getenv("TPGAN_WGRAD_SLAB_MINW")) : 32;   // narrower maps: slab units lose to plain multi-row boxes (measured)
+  if (slab_mode && a.stride == 1 && a.kh >= 2 && Pt.w >= slab_min_w) {
     for (int sw = 0; sw < (is_conv ? 2 : 1); ++sw) {
       WgradChoice c = wgrad_option(a, sw != 0, true);
       if (c.cost < best.cost * 0.95) best = c;
@@ -643,11 +837,20 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   G.Hp = Pt.h;
   G.Wp = Pt.w;
   G.Nimg = Pt.n;
-  // pixel boxes of ~box_px pixels (slab mode: one row segment)
+  // pixel boxes of ~box_px pixels.  Slab mode: one row segment - or, on maps narrow enough for two or more whole rows per
+  // box, rows enumerated with the PADDED pitch W + tpu - 1 (the pad columns are out-of-bounds zeros of P): tap t of every
+  // pixel is still the Q slab read t rows further down, and a stage carries ~box_px pixels instead of one short row
   G.bw = (G.Wp <= box_px + box_px / 2) ? G.Wp : box_px;
+  int pbw = G.bw;                       // width of the P (and, multi-row, Q) box
   G.bh = ch.slab ? 1 : std::max(1, std::min(G.Hp, box_px / G.bw));
-  G.bn = (!ch.slab && G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, box_px / (G.bw * G.bh))) : 1;
-  G.kp = ceil_div(G.bw * G.bh * G.bn, KR) * KR;
+  if (ch.slab && G.bw == G.Wp && box_px / (G.Wp + ch.tpu - 1) >= 2) {
+    pbw = G.Wp + ch.tpu - 1;
+    G.bh = std::min(G.Hp, box_px / pbw);
+  }
+  const bool multirow = ch.slab && pbw != G.bw;
+  G.bn = ((!ch.slab || multirow) && G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, box_px / (pbw * G.bh))) : 1;
+  G.p_rows = pbw * G.bh * G.bn;
+  G.kp = ceil_div(G.p_rows, KR) * KR;
   G.tiles_w = ceil_div(G.Wp, G.bw);
   G.tiles_h = ceil_div(G.Hp, G.bh);
   G.chunks = G.tiles_w * G.tiles_h * ceil_div(G.Nimg, G.bn);
@@ -662,8 +865,12 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   // MN-major tf32 operands need the 32B-atom flavour of the 128B swizzle; bf16 uses the plain 128B swizzle
   const CUtensorMapSwizzle swz = bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   const int CH = chunk_ch(bf16);
-  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.bw, G.bh, G.bn, swz, CH, bf16);
+  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, pbw, G.bh, G.bn, swz, CH, bf16);
   if (rc) return rc;
+  if (G.kp > G.p_rows) {
+    rc = encode_nhwc(&G.pzero, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.kp - G.p_rows, 1, 1, swz, CH, bf16);
+    if (rc) return rc;
+  }
   if (ch.slab) {
     // taps: per kernel row, groups of tpu slots (unused slots: wtap 255), horizontal offset increasing inside a group
     const int ngrp = ceil_div(k, G.tpu);
@@ -690,7 +897,12 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
     G.tap_groups = k * ngrp;
     G.nbuf = (G.mpu * G.ncpt * G.tpu * CH <= 256) ? 2 : 1;
     G.q_chunk_bytes = ceil_div(G.kp + G.tpu - 1, 8) * 8 * 128;
-    rc = encode_nhwc(&G.qslab, Qt.ptr, Qt.c, Qt.w, Qt.h, Qt.n, Qt.sw, Qt.sh, Qt.sn, G.bw + G.tpu - 1, 1, 1, swz, CH, bf16);
+    // multi-row: the Q box has the P box's shape (rows past it, read by the last taps of the pad columns, stay zero: the
+    // ring is cleared once per launch); single row: one segment + halo
+    G.q_rows = multirow ? G.p_rows : G.bw + G.tpu - 1;
+    G.zero_ring = multirow ? 1 : 0;
+    rc = encode_nhwc(&G.qslab, Qt.ptr, Qt.c, Qt.w, Qt.h, Qt.n, Qt.sw, Qt.sh, Qt.sn, multirow ? pbw : G.bw + G.tpu - 1,
+                     multirow ? G.bh : 1, multirow ? G.bn : 1, swz, CH, bf16);
     if (rc) return rc;
     return 0;
   }
@@ -730,6 +942,15 @@ static int choose_wgrad_px(const tpgan_wgrad_args* groups, int ngroups) {
   };
   for (int px : {128, 64})
     if (budget / stage_bytes(px) >= 4) return px;
+  // small maps (multi-row boxes): three stages of 64 pixels beat more stages of 32 - the per-stage cost (a dozen TMA
+  // requests of 2-4 KB and a barrier round trip per 3-4 K steps) dominates those launches (measured on the grouped
+  // 128->128 3x3 layer at 20x20: 81 -> 50 us)
+  bool small_maps = true;
+  for (int i = 0; i < ngroups; ++i) {
+    const bool is_conv = groups[i].kind == TPGAN_CONV_FWD;
+    small_maps = small_maps && (is_conv ? groups[i].dy.w : groups[i].x.w) <= 64;
+  }
+  if (small_maps && budget / stage_bytes(64) >= 3) return 64;
   if (budget / stage_bytes(32) >= 3) return 32;
   return 16;
 }
@@ -776,16 +997,24 @@ static int launch_wgrad(Params& P, cudaStream_t st, int bf16) {
   P.ring_bytes = P.stages * stage_bytes + slack;
   P.need_zero = 0;
   for (int i = 0; i < P.ngroups; ++i)
-    if ((P.g[i].bw * P.g[i].bh * P.g[i].bn) % KR) P.need_zero = 1;
+    if ((P.g[i].p_rows % KR) || P.g[i].zero_ring) P.need_zero = 1;
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "wgrad: not enough shared memory for 2 stages (%d B/stage)", stage_bytes);
   const int smem = P.ring_bytes + 1024;
+  static const bool debug = getenv("TPGAN_WGRAD_DEBUG") != nullptr;
+  if (debug)
+    for (int i = 0; i < P.ngroups; ++i) {
+      const WgradGroup& G = P.g[i];
+      fprintf(stderr, "wgrad[%d/%d] P %dx%dx%d m_valid %d n_valid %d slab %d transpose %d mpu %d tpu %d ncpt %d n_tiles %d block_n %d box %dx%dx%d p_rows %d kp %d "
+              "chunks %d tiles %d nkb %d stages %d stage_bytes %d nbuf %d zero_tail %d need_zero %d\n", i, P.ngroups, G.Nimg, G.Hp, G.Wp, G.m_valid,
+              G.n_valid, G.slab, G.transpose_out, G.mpu, G.tpu, G.ncpt, G.n_tiles, G.block_n, G.bw, G.bh, G.bn, G.p_rows, G.kp, G.chunks, G.tiles,
+              G.nkb, P.stages, stage_bytes, P.nbuf, P.zero_tail, P.need_zero);
+    }
   auto kern = bf16 ? wgrad_kernel<Params, true> : wgrad_kernel<Params, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   // balanced schedule: every CTA gets total_work / grid (+-1) chunks (see SegmentWalk in wgrad.cu)
   const int grid = (int)std::min<long long>(work, persistent_sms());
-  kern<<<grid, kConvThreads, smem, st>>>(P, g_dev.status_dev);
-  e = cudaGetLastError();
+  e = launch_tc(kern, grid, smem, st, P);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -813,6 +1042,8 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     if (try_rowstack(groups[0], st, &rrc)) return rrc;
     g_last_conv_kernel = 1;
     if (try_rowconv(groups[0], st, &rrc)) return rrc;
+    g_last_conv_kernel = 3;
+    if (try_flatconv(groups, 1, st, &rrc)) return rrc;
     g_last_conv_kernel = 0;
     static thread_local TapGemmParams1 P;
     P.ngroups = 1;
@@ -824,6 +1055,11 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
       if (rc) return rc;
     }
     return launch_tapgemm(P, st, bf16);
+  }
+  {
+    int rrc = 0;
+    g_last_conv_kernel = 3;
+    if (try_flatconv(groups, ngroups, st, &rrc)) return rrc;
   }
   g_last_conv_kernel = 0;
   static thread_local TapGemmParams P;
@@ -852,6 +1088,7 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
   if (ngroups == 1) {
     static thread_local WgradParams1 P;
     P.ngroups = 1;
+    P.zero_tail = 0;
     rc = plan_wgrad(groups[0], P.g[0], choose_wgrad_px(groups, 1));
     if (rc) return rc;
     return launch_wgrad(P, st, bf16);
@@ -864,22 +1101,18 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
     rc = plan_wgrad(groups[i], P.g[i], px);
     if (rc) return rc;
     const WgradGroup& G = P.g[i];
-    // the zero-padded K rows of the smem ring stay zero only if every box fills its rows or all boxes are alike
-    if ((G.bw * G.bh * G.bn) % mma_k(bf16)) uniform = false;
+    if (G.p_rows % mma_k(bf16)) uniform = false;
   }
+  // the zero-padded K rows of the smem ring stay zero by themselves only if every box fills its rows or all boxes are
+  // alike; otherwise each stage re-zeroes them (WgradGroup::pzero)
+  P.zero_tail = 0;
   if (!uniform) {
     bool same = true;
     for (int i = 1; i < ngroups; ++i)
-      same = same && P.g[i].bw == P.g[0].bw && P.g[i].bh == P.g[0].bh && P.g[i].bn == P.g[0].bn &&
+      same = same && P.g[i].bw == P.g[0].bw && P.g[i].bh == P.g[0].bh && P.g[i].bn == P.g[0].bn && P.g[i].p_rows == P.g[0].p_rows &&
              P.g[i].block_n == P.g[0].block_n && P.g[i].mpu == P.g[0].mpu && P.g[i].tpu == P.g[0].tpu &&
              P.g[i].slab == P.g[0].slab;
-    if (!same) {
-      for (int i = 0; i < ngroups; ++i) {
-        rc = tpgan_conv2d_wgrad(groups + i, 1, stream);
-        if (rc) return rc;
-      }
-      return 0;
-    }
+    if (!same) P.zero_tail = 1;
   }
   return launch_wgrad(P, st, bf16);
 }

@@ -24,6 +24,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The tensor-core kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may
+// become resident (on SMs this grid's CTAs have already left) and run their prologue - barrier init, TMEM allocation -
+// while this grid is still finishing.  pdl_wait() returns once every prerequisite grid has COMPLETED and its memory
+// operations are visible; nothing before it may touch global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -127,14 +127,51 @@ struct RowStackParams {
   float slope;
 };
 
+// ---------------------------------------------------------------- flat-slab convolution (small maps, stride 1, "same" padding)
+// A unit = T consecutive 128-row M tiles over the PADDED-PITCH pixel enumeration of `ur` output rows (or `bn` whole images):
+// flat row m <-> image m / ipitch, row (m % ipitch) / Wp, column (m % ipitch) % Wp, with Wp = W + k - 1.  One TMA box
+// {chunk, Wp, R, bn} (R = ur + k - 1, zero padding = out-of-bounds fill) lands in shared memory in exactly that enumeration,
+// so tap (r, j) of EVERY pixel is the same slab read r * Wp + j rows further down: the k*k taps share one activation load,
+// and the T tiles of the unit share every weight tile.
+struct FlatGroup {
+  CUtensorMap amap;              // 4D {C, W, H, N}, box {chunk, Wp, R, bn}, 128B swizzle
+  CUtensorMap bmap;              // 3D {k_pad, rows_pad, taps+1}, box {chunk, block_n, 1}
+  int H, W, Nimg;
+  int Wp, R, bn, ur, ipitch;     // ipitch = R * Wp flat rows per image of a unit
+  int T;                         // 128-row tiles per unit (T * block_n <= 256 TMEM columns, double-buffered)
+  int units_h;                   // ceil(H / ur); units = units_h * ceil(Nimg / bn)
+  int n_tiles, block_n;
+  int kchunks, last_mmas;
+  int tile_begin, tile_count;    // units * n_tiles
+  int slab_tx;                   // bn * R * Wp * 128 bytes per slab load
+  DevView out, add1, add2, mask;
+  DevView16 out16;
+  const float* bias;
+  const float* slopes;
+  int cout_valid, epilogue, round_tf32, vec_ok;
+  float slope;
+};
+
+struct FlatConvParams {
+  int ngroups, total_tiles;
+  int k, dy0, dx0;               // shared by the groups of a launch (same layer type)
+  int a_slots, b_slots, slab_bytes, b_bytes;
+  unsigned char wtap[kMaxTaps];  // weight tap slice for grid position r*k + j
+  FlatGroup g[kMaxGroups];
+};
+
 // ---------------------------------------------------------------- weight-gradient GEMM
 // D[m = channel of P][n = channel of Q] (per tap) = sum over pixels P[pix, m] * Qtap[pix, n]
 struct WgradGroup {
   CUtensorMap pmap;              // unshifted tensor, 4D {C, W, H, N}, box {32, bw, bh, bn}
   CUtensorMap qmap[kMaxPlanes];  // shifted tensor planes, same box
   CUtensorMap qslab;             // slab mode: box {32, bw + tpu - 1, 1, 1} of the shifted tensor (one row segment + halo)
+  CUtensorMap pzero;             // box {32, kp - bw*bh*bn, 1, 1} of the unshifted tensor, only ever fetched fully out of bounds:
+                                 // zero-fills the K rows a pixel box leaves unwritten (launches that mix box shapes)
   int Hp, Wp, Nimg;
   int bw, bh, bn, kp;            // kp = K rows per stage (pixels rounded up to 8)
+  int p_rows, q_rows;            // pixel rows one P box / one Q slab box writes (multi-row slab boxes include the pad columns)
+  int zero_ring;                 // the kernel must clear the ring before the first load (rows no box ever writes are read)
   int tiles_w, tiles_h, chunks;  // pixel boxes: tiles_w * tiles_h * ceil(Nimg/bn)
   int m_tiles, n_tiles, block_n; // M tile = 128 P-channels, N tile = block_n columns
   // A unit covers `mpu` consecutive M tiles (one accumulator each; they share every Q load) and `tpu` consecutive taps
@@ -167,6 +204,7 @@ struct WgradParams {
   int need_zero;                 // some group's pixel box leaves K rows unwritten: zero the ring first
   int nbuf;
   int whole_tiles;               // deterministic mode: a CTA owns whole output tiles (no split reduction, no float atomics race)
+  int zero_tail;                 // groups with different box shapes share the ring: every stage zero-fills the unwritten K rows of P
   WgradGroup g[kMaxGroups];
 };
 struct WgradParams1 {
@@ -178,6 +216,7 @@ struct WgradParams1 {
   int need_zero;
   int nbuf;
   int whole_tiles;
+  int zero_tail;
   WgradGroup g[1];
 };
 

@@ -343,7 +343,8 @@ struct CropOut {
   V v[4];
 };
 // one warp per (image, part, patch row): lanes sweep (x, c) contiguously
-__global__ void patch_crop_kernel(V img, const float* __restrict__ lm, CropOut out, int* __restrict__ boxes, float fill) {
+// vec: every view stores a pixel as one aligned float4 (c <= 4, channel stride 4): a lane moves a whole pixel per access
+__global__ void patch_crop_kernel(V img, const float* __restrict__ lm, CropOut out, int* __restrict__ boxes, float fill, int vec) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int pw[4] = {40, 40, 40, 48}, phh[4] = {40, 40, 32, 32};
@@ -375,6 +376,16 @@ __global__ void patch_crop_kernel(V img, const float* __restrict__ lm, CropOut o
     const V& o = out.v[part];
     const int sy = upper + rr;
     const int C = o.c;
+    if (vec) {
+      const bool row_in = sy >= 0 && sy < img.h;
+      for (int x = lane; x < pw[part]; x += 32) {
+        const int sx = left + x;
+        float4 v = make_float4(fill, fill, fill, C > 3 ? fill : 0.f);
+        if (row_in && sx >= 0 && sx < img.w) v = *reinterpret_cast<const float4*>(img.p + voff(img, n, sy, sx));
+        *reinterpret_cast<float4*>(o.p + voff(o, n, rr, x)) = v;
+      }
+      continue;
+    }
     for (int e = lane; e < pw[part] * C; e += 32) {
       int x = e / C, c = e % C;
       int sx = left + x;
@@ -591,6 +602,122 @@ __global__ void image_losses_kernel(V f, V g128, V g64, V g32, V df, LossW W, fl
     float s = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[threadIdx.x][i];
     atomicAdd(sums + threadIdx.x, s);
+  }
+}
+
+// Tiled variant for the layout the step uses (c <= 4 with a channel stride of 4 floats, W <= 256, W % 4 == 0): one block per
+// (image, band of 4 rows).  The band and one halo row above / below are staged in shared memory with one coalesced 16-byte
+// load per pixel, the 2x2 / 4x4 block means of the band (a band is aligned to both grids) are computed once, and every
+// term of the pixel - mirror column, vertical / horizontal neighbours, block means and their mirrors - is read from shared
+// memory: each global byte is read once (the halo rows twice) and the gradient leaves as one 16-byte store per pixel.
+// The per-element arithmetic and its order are those of image_losses_kernel (identical gradients, sums to fp32 addition order).
+__global__ void __launch_bounds__(128) image_losses_tiled_kernel(V f, V g128, V g64, V g32, V df, LossW W, float* __restrict__ sums) {
+  extern __shared__ float4 tl_smem[];
+  const int Wd = f.w, H = f.h;
+  float4* tile = tl_smem;                 // [6][Wd]   rows y0-1 .. y0+4
+  float4* m2 = tile + 6 * Wd;             // [2][Wd/2] 2x2 means of the band
+  float4* m4 = m2 + Wd;                   // [Wd/4]    4x4 means of the band
+  const int bands = H / 4;
+  const int n = blockIdx.x / bands, y0 = (blockIdx.x % bands) * 4;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 6 * Wd; i += blockDim.x) {
+    const int row = i / Wd, x = i - row * Wd, y = y0 - 1 + row;
+    tile[i] = (y >= 0 && y < H) ? *reinterpret_cast<const float4*>(f.p + voff(f, n, y, x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  auto ld = [&](const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); };
+  for (int i = tid; i < Wd; i += blockDim.x) {          // 2 x (Wd/2) block means, (dy, dx) summation order of block_mean
+    const int by = i / (Wd / 2), bx = i - by * (Wd / 2);
+    float a[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float t = 0.f;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) t += ld(tile[(1 + by * 2 + dy) * Wd + bx * 2 + dx], c);
+      a[c] = t / 4.f;
+    }
+    m2[i] = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  for (int i = tid; i < Wd / 4; i += blockDim.x) {
+    float a[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float t = 0.f;
+      for (int dy = 0; dy < 4; ++dy)
+        for (int dx = 0; dx < 4; ++dx) t += ld(tile[(1 + dy) * Wd + i * 4 + dx], c);
+      a[c] = t / 16.f;
+    }
+    m4[i] = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  __syncthreads();
+  float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = tid; i < 4 * Wd; i += blockDim.x) {
+    const int ry = i / Wd, x = i - ry * Wd, y = y0 + ry, mx = Wd - 1 - x;
+    const float4 v4 = tile[(1 + ry) * Wd + x], mir = tile[(1 + ry) * Wd + mx];
+    const float4 up = tile[ry * Wd + x], dn = tile[(2 + ry) * Wd + x];
+    const float4 lf = tile[(1 + ry) * Wd + (x > 0 ? x - 1 : x)], rt = tile[(1 + ry) * Wd + (x + 1 < Wd ? x + 1 : x)];
+    const float4 t128 = *reinterpret_cast<const float4*>(g128.p + voff(g128, n, y, x));
+    const float4 t64 = *reinterpret_cast<const float4*>(g64.p + voff(g64, n, y >> 1, x >> 1));
+    const float4 t32 = *reinterpret_cast<const float4*>(g32.p + voff(g32, n, y >> 2, x >> 2));
+    const float4 a2 = m2[(ry >> 1) * (Wd / 2) + (x >> 1)], a2m = m2[(ry >> 1) * (Wd / 2) + (Wd / 2 - 1 - (x >> 1))];
+    const float4 a4 = m4[x >> 2], a4m = m4[Wd / 4 - 1 - (x >> 2)];
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= f.c) continue;
+      const float v = ld(v4, c);
+      float grad = 0.f;
+      float d = v - ld(t128, c);
+      part[0] += fabsf(d);
+      grad += W.w[0] * sgn(d);
+      float ds = v - ld(mir, c);
+      part[3] += fabsf(ds);
+      grad += 2.f * W.w[3] * sgn(ds);
+      {
+        const float dd = ld(a2, c) - ld(t64, c), dsm = ld(a2, c) - ld(a2m, c);
+        if (((y & 1) == 0) && ((x & 1) == 0)) { part[1] += fabsf(dd); part[4] += fabsf(dsm); }
+        const float inv = 1.f / 4.f;
+        grad += W.w[1] * inv * sgn(dd) + 2.f * W.w[4] * inv * sgn(dsm);
+      }
+      {
+        const float dd = ld(a4, c) - ld(t32, c), dsm = ld(a4, c) - ld(a4m, c);
+        if (((y & 3) == 0) && ((x & 3) == 0)) { part[2] += fabsf(dd); part[5] += fabsf(dsm); }
+        const float inv = 1.f / 16.f;
+        grad += W.w[2] * inv * sgn(dd) + 2.f * W.w[5] * inv * sgn(dsm);
+      }
+      if (y + 1 < H) {
+        const float t = ld(dn, c) - v;
+        part[6] += fabsf(t);
+        grad -= W.w[6] * sgn(t);
+      }
+      if (y > 0) grad += W.w[6] * sgn(v - ld(up, c));
+      if (x + 1 < Wd) {
+        const float t = ld(rt, c) - v;
+        part[7] += fabsf(t);
+        grad -= W.w[7] * sgn(t);
+      }
+      if (x > 0) grad += W.w[7] * sgn(v - ld(lf, c));
+      g[c] = grad;
+    }
+    float* o = df.p + voff(df, n, y, x);
+    if (df.c >= 4 || f.c >= 4) *reinterpret_cast<float4*>(o) = make_float4(g[0], g[1], g[2], g[3]);
+    else {   // 3-channel views: the fourth lane is the layout's zero padding
+      *reinterpret_cast<float4*>(o) = make_float4(g[0], g[1], g[2], 0.f);
+    }
+  }
+  __shared__ float red[8][4];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float sacc = part[k];
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+    if (lane == 0) red[k][wp] = sacc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float sacc = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sacc += red[threadIdx.x][i];
+    atomicAdd(sums + threadIdx.x, sacc);
   }
 }
 
@@ -1292,7 +1419,12 @@ int tpgan_patch_crop(tpgan_view img, const float* landmarks, tpgan_view left_eye
   if (!landmarks) return set_error(TPGAN_ERR_INVALID, "patch_crop: landmarks NULL");
   long long rows = (long long)img.n * 144;
   int grid = (int)std::max(1ll, std::min((rows + 7) / 8, 8ll * 148));
-  patch_crop_kernel<<<grid, 256, 0, ST>>>(dv(img), landmarks, co, boxes, fill);
+  auto px4 = [](const tpgan_view& v) {
+    return v.sw == 4 && v.c <= 4 && (((uintptr_t)v.ptr) & 15) == 0 && v.sh % 4 == 0 && v.sn % 4 == 0;
+  };
+  int vec = px4(img) ? 1 : 0;
+  for (int i = 0; i < 4; ++i) vec = vec && px4(*o[i]);
+  patch_crop_kernel<<<grid, 256, 0, ST>>>(dv(img), landmarks, co, boxes, fill, vec);
   TPG_CHECK_LAUNCH("patch_crop");
   return 0;
 }
@@ -1349,6 +1481,18 @@ int tpgan_image_losses(tpgan_view fake, tpgan_view t128, tpgan_view t64, tpgan_v
   LossW W;
   for (int i = 0; i < 8; ++i) W.w[i] = w[i];
   long long total = (long long)fake.n * fake.h * fake.w * fake.c;
+  auto vec4 = [](const tpgan_view& v) {   // a pixel is one aligned float4 whose lanes beyond c are layout padding
+    return v.sw == 4 && v.c <= 4 && (((uintptr_t)v.ptr) & 15) == 0 && v.sh % 4 == 0 && v.sn % 4 == 0;
+  };
+  const char* gen_ev = getenv("TPGAN_IMAGE_LOSSES_GENERIC");   // per call: the parity test compares the two kernels
+  if (!(gen_ev && atoi(gen_ev)) && vec4(fake) && vec4(t128) && vec4(t64) && vec4(t32) && vec4(dfake) && fake.w <= 256 && t64.w * 2 == fake.w &&
+      t32.w * 4 == fake.w && t64.c == fake.c && t32.c == fake.c) {
+    const int threads = 128;   // small blocks: ~8 bands in flight per SM hide the load -> sync -> load latency chain
+    const size_t smem = (size_t)(6 * fake.w + fake.w + fake.w / 4) * sizeof(float4);
+    image_losses_tiled_kernel<<<fake.n * (fake.h / 4), threads, smem, ST>>>(dv(fake), dv(t128), dv(t64), dv(t32), dv(dfake), W, sums);
+    TPG_CHECK_LAUNCH("image_losses_tiled");
+    return 0;
+  }
   image_losses_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dv(fake), dv(t128), dv(t64), dv(t32), dv(dfake), W, sums);
   TPG_CHECK_LAUNCH("image_losses");
   return 0;

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_flag;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) rowstack_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above touched only shared / tensor memory; global memory from here on
   const uint32_t tmem_base = tmem_base_s;
   AbortCtl ac{&abort_flag, status};
 

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_flag;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = P.stages;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above touched only shared / tensor memory; global memory from here on
   const uint32_t tmem_base = tmem_base_s;
   AbortCtl ac{&abort_flag, status};
 

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_flag;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = P.stages;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above touched only shared / tensor memory; global memory from here on
   const uint32_t tmem_base = tmem_base_s;
   AbortCtl ac{&abort_flag, status};
   const int nbuf = P.nbuf;   // accumulator buffers (uniform over the groups of a launch)
@@ -151,13 +153,16 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
         const int mch = min(MCH * G.mpu, (G.m_valid - pc0 + CH - 1) / CH);   // P chunks of this unit (all its M tiles)
         const int tap0 = u.tg * G.tpu;
         const int ntap = min(G.tpu, G.ntaps - tap0);
-        const int qc0 = (G.tpu > 1 || G.slab) ? 0 : u.nt * G.block_n;
+        const int qc0 = G.slab ? u.nt * G.ncpt * CH : (G.tpu > 1 ? 0 : u.nt * G.block_n);
         const int ncpt = (G.tpu > 1 || G.slab) ? G.ncpt : min(G.block_n / CH, (G.n_valid - qc0 + CH - 1) / CH);
-        const uint32_t box_bytes = (uint32_t)(G.bw * G.bh * G.bn) * 128u;
+        const uint32_t box_bytes = (uint32_t)G.p_rows * 128u;
         const bool slab = G.slab != 0;
         const uint32_t q_stride = (uint32_t)G.q_chunk_bytes;
-        const uint32_t tx = slab ? box_bytes * (uint32_t)mch + (uint32_t)(G.bw + G.tpu - 1) * 128u * (uint32_t)G.ncpt
-                                 : box_bytes * (uint32_t)(mch + ntap * ncpt);
+        // K rows the pixel box leaves unwritten: in a launch that mixes box shapes they would hold another group's pixels,
+        // so every stage overwrites them (P side only: 0 * finite = 0) with a box fetched fully out of bounds
+        const uint32_t tail_bytes = P.zero_tail ? (uint32_t)G.kp * 128u - box_bytes : 0u;
+        const uint32_t tx = (slab ? box_bytes * (uint32_t)mch + (uint32_t)G.q_rows * 128u * (uint32_t)G.ncpt
+                                  : box_bytes * (uint32_t)(mch + ntap * ncpt)) + tail_bytes * (uint32_t)mch;
         const uint32_t chunk_stride = (uint32_t)G.kp * 128u;
         const int c_begin = u.c_begin, c_end = u.c_end;
         const int tiles_w = G.tiles_w, tiles_h = G.tiles_h, bw = G.bw, bh = G.bh, bn = G.bn;
@@ -174,9 +179,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
           uint32_t sb = sa + (uint32_t)P.a_stage_bytes;
           mbar_arrive_expect_tx_a(fb, tx);
           for (int i = 0; i < mch; ++i) tma_load_4d_a(sa + (uint32_t)i * chunk_stride, pm, fb, pc0 + i * CH, x0, y0, n0);
+          if (tail_bytes)
+            for (int i = 0; i < mch; ++i)
+              tma_load_4d_a(sa + (uint32_t)i * chunk_stride + box_bytes, &G.pzero, fb, pc0 + i * CH, G.Wp, 0, 0);
           if (slab) {
             for (int i = 0; i < ncpt; ++i)
-              tma_load_4d_a(sb + (uint32_t)i * q_stride, &G.qslab, fb, i * CH, x0 + tdx0, y0 + tdy0, n0);
+              tma_load_4d_a(sb + (uint32_t)i * q_stride, &G.qslab, fb, qc0 + i * CH, x0 + tdx0, y0 + tdy0, n0);
           } else if (single_tap) {
             for (int i = 0; i < ncpt; ++i)
               tma_load_4d_a(sb + (uint32_t)i * chunk_stride, qm0, fb, qc0 + i * CH, x0 + tdx0, y0 + tdy0, n0);
@@ -352,7 +360,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
             uint32_t r[16];
             tmem_ld16(t_addr, r);
             tmem_ld_wait();
-            if (mvalid && i * CH + h * 16 < G.n_valid) store16(r, G.taps[tap0 + t], m, i * CH + h * 16);
+            const int n0 = (u.nt * G.ncpt + i) * CH + h * 16;
+            if (mvalid && n0 < G.n_valid) store16(r, G.taps[tap0 + t], m, n0);
           }
         }
       } else
