@@ -206,6 +206,14 @@ def gan_line(a, B, dtype, identity, steps, warmup, world, rank, dev, want_roofli
 
     for _ in range(max(warmup, 3)):
         resident()
+    if getattr(a, "profile_step", False):
+        # ncu --profile-from-start off: exactly ONE step between cudaProfilerStart/Stop (use with --no-graphs so that every
+        # kernel is its own launch); numbers printed by a run under ncu are never bench values
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -660,6 +668,8 @@ def main():
     ap.add_argument("--sm-reserve", type=int, default=0, help="SMs the persistent kernels leave free (for the NCCL kernels)")
     ap.add_argument("--bucket-mb", type=float, default=32.0, help="N > 1, overlap mode: all-reduce bucket size")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket one extra step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     a = ap.parse_args()
     if a.workload == "pretrain":
         (run_pretrain_reference if a.impl == "reference" else run_pretrain)(a)

@@ -131,6 +131,37 @@ def _act(y, slope, name):
     return F.leaky_relu(y, slope)
 
 
+# The two selection sites of the generator - the maxout after fc1 and the LocalFuser's max over the four padded patches -
+# are discontinuous in the same way: a near-tie that resolves differently routes a whole gradient element elsewhere.  With
+# MASK_HOOK installed, MASK_HOOK("<fc1 key>#maxout") may return the CUDA path's stored fc1 output and
+# MASK_HOOK("local_fuser#<site>") its stored arg-max map; the port's *backward* then follows those selections (forward
+# values stay the port's own), exactly like the activation masks above.
+class _MaxoutWithSel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pairs, sel_src):          # (B, F, 2)
+        ctx.save_for_backward(sel_src[..., 0] >= sel_src[..., 1])   # first of an equal pair wins (maxout2_backward_kernel)
+        return pairs.max(dim=2).values
+
+    @staticmethod
+    def backward(ctx, g):
+        (first,) = ctx.saved_tensors
+        z = torch.zeros_like(g)
+        return torch.stack([torch.where(first, g, z), torch.where(first, z, g)], dim=2), None
+
+
+class _FuseWithSel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, stacked, idx):            # (4, B, C, 128, 128), (B, C, 128, 128) int64
+        ctx.save_for_backward(idx)
+        return stacked.max(dim=0).values
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        out = torch.zeros((4,) + tuple(g.shape), dtype=g.dtype)
+        return out.scatter_(0, idx.unsqueeze(0), g.unsqueeze(0)), None
+
+
 def _conv(sd, key, x, stride=1, pad=0, slope=LEAKY):
     """conv(): [ReflectionPad2d(4-list)] -> Conv2d(bias) -> activation (ModificationLayer.py:83-119)."""
     if isinstance(pad, (list, tuple)):
@@ -187,12 +218,16 @@ FUSE_RECTS = ((39 - 20 - 1, 40 - 20 - 1, 40, 40), (86 - 20 - 1, 39 - 20 - 1, 40,
               (65 - 24 - 1, 89 - 16 - 1, 48, 32))
 
 
-def local_fuser(parts, return_index=False):
-    """max over the four zero-padded maps (D_and_G_model.py:154-159)."""
+def local_fuser(parts, return_index=False, site=None):
+    """max over the four zero-padded maps (D_and_G_model.py:154-159).  site: name of the call for selection injection."""
     padded = []
     for t, (left, top, w, h) in zip(parts, FUSE_RECTS):
         assert t.shape[2] == h and t.shape[3] == w
         padded.append(F.pad(t, (left, 128 - left - w, top, 128 - top - h)))
+    if MASK_HOOK is not None and site is not None and not return_index:
+        sel = MASK_HOOK("local_fuser#" + site)
+        if sel is not None:
+            return _FuseWithSel.apply(torch.stack(padded, 0), sel)
     val, idx = torch.max(torch.stack(padded, 0), 0)
     return (val, idx) if return_index else val
 
@@ -209,7 +244,11 @@ def global_pathway(sd, pre, I128, local_fake, local_feat, z):
         conv4 = _res(sd, p(f"conv4.{i}"), conv4, 3)
     B = I128.shape[0]
     fc1 = _q(_gout(F.linear(_xin(conv4.reshape(B, -1)), _xin(_qw(sd[p("fc1.weight")])), sd[p("fc1.bias")])))
-    fc2 = F.max_pool1d(fc1.view(B, -1, 2), 2, 2).view(B, -1)
+    sel = MASK_HOOK(p("fc1") + "#maxout") if MASK_HOOK is not None else None
+    if sel is not None:
+        fc2 = _MaxoutWithSel.apply(fc1.view(B, -1, 2), sel.reshape(B, -1, 2))
+    else:
+        fc2 = F.max_pool1d(fc1.view(B, -1, 2), 2, 2).view(B, -1)
     deconv_8 = _deconv(sd, p("deconv_8"), torch.cat([fc2, z], 1).view(B, -1, 1, 1), 1, 0, 0)
     deconv_32 = _deconv(sd, p("deconv_32"), deconv_8, 4, 0, 1)
     deconv_64 = _deconv(sd, p("deconv_64"), deconv_32, 2, 1, 1)
@@ -250,9 +289,9 @@ def generator(sd, I128, left_eye, right_eye, nose, mouth, z, dropout_mask=None):
         im, ft = local_pathway(sd, f"local_pathway_{n}", t)
         imgs.append(im)
         feats.append(ft)
-    fused_feat = local_fuser(feats)
-    fused_img = local_fuser(imgs)
-    fused_in = local_fuser(parts_in)
+    fused_feat = local_fuser(feats, site="feature")
+    fused_img = local_fuser(imgs, site="fake_image")
+    fused_in = local_fuser(parts_in, site="origin")
     fake, enc = global_pathway(sd, "global_pathway", I128, fused_img, fused_feat, z)
     e = enc if dropout_mask is None else enc * dropout_mask
     logits = _q(_gout(F.linear(_xin(e), _xin(_qw(sd["feature_predict.fc.weight"])), sd["feature_predict.fc.bias"])))

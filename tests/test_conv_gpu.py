@@ -360,6 +360,32 @@ def test_flatconv_grouped_matches_tapgemm(div, cin, cout, monkeypatch):
         assert rel(b_.to_nchw(), a.to_nchw()) < 2e-4
 
 
+@pytest.mark.parametrize("case", [(32, 512, 512, 8, 8, 8), (32, 8192, 256, 1, 1, 1), (5, 4096, 48, 1, 1, 1), (3, 64, 1000, 4, 4, 4)])
+def test_linear_split_k(case):
+    """Linear layers as GEMM-like launches (rows = images): fc1 is an 8x8 'conv' of 64 taps on the 8x8x512 map
+    (D_and_G_model.py:289), the identity network's FC a one-tap product over 8192 features.  Few tiles and a long reduction:
+    the library splits the taps / the K chunks over the SMs; the CTA arriving last adds the parked partial sums in a fixed
+    order and runs the fused epilogue (api.cu, tapgemm.cu)."""
+    from tpgan_b200 import ops, _lib
+    n, cin, cout, h, w, k = case
+    x = _mk(n, cin, h, w, 1)
+    wt = _mk(cout, cin, k, k, 2) * (1.0 / (cin * k * k) ** 0.5)
+    b = _mk(1, cout, 1, 1, 3).flatten()
+    ref = F.leaky_relu(F.conv2d(x, wt, b), 0.01)
+    pw = ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True)
+    xa, bc = _act(x, ops), b.cuda()
+    outs = []
+    for _ in range(3):          # repeated launches: the arrival counters reset themselves, the result is bit-reproducible
+        out = ops.Act.empty(n, 1, 1, cout)
+        out.buf.fill_(7.0)
+        ops.conv2d(ops.CONV_FWD, xa, out, pw, k, 1, 0, bias=bc, slope=0.01, epilogue=ops.EPI_LEAKY, round_tf32=True)
+        outs.append(out.to_nchw())
+    torch.cuda.synchronize()
+    assert _lib.kernel_status() == 0
+    assert rel(outs[0], ref) < TOL
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 GROUPED_WGRAD_CASES = [
     # (cin, cout, k, stride, pad, kind, patch sizes of the four pathways at this depth) - D_and_G_model.py:390-393 patches
     # 40x40 / 40x40 / 32x40 / 32x48 after 0..3 stride-2 convs.  10x10 and 5x5 boxes do not fill their last 8-pixel K step while

@@ -41,6 +41,12 @@ def _mask_hook(plan, crit=None, ranges=None, counter=None):
     from tpgan_b200.train_step import _sl
 
     def hook(name):
+        if name.startswith("local_fuser#"):        # stored arg-max of the stitch (uint8, NHWC) -> (B, C, 128, 128) int64
+            am = getattr(plan, "fuse_argmax", {}).get(name.split("#", 1)[1])
+            return None if am is None else am.permute(0, 3, 1, 2).contiguous().long().cpu()
+        if name.endswith("#maxout"):               # stored fc1 output: the pair element the maxout backward follows
+            t = plan.named.get(name[:-len("#maxout")])
+            return None if t is None else t.act.to_nchw().cpu().flatten(1)
         if crit is not None and name.startswith("model."):
             n0, n1 = ranges[counter["i"]]
             for op in crit.ops_:
@@ -208,9 +214,13 @@ def test_training_step_batch32_vs_oracle():
     ref, gg, gd = _oracle_step_grads(b, sg, sd, tr)
     for k, v in ref.items():
         assert abs(m[k] - v) <= 1e-2 * abs(v) + 1e-4, (k, m[k], v)
+    # masked = the CUDA path's activation signs, maxout winners and LocalFuser arg-max injected into the oracle's backward
+    # (oracle/model_port.py): measured 1.35e-3 (G) / 4.7e-4 (D), and the same to 2 % whichever conv kernel computed the
+    # forward (multi-tap GEMM or flat-slab: 1.35e-3 / 1.33e-3).  Before the selection sites were injected the bound had to
+    # be 3e-3 and a one-ulp change of a few forward values moved the G figure between 2.2e-3 and 8e-3.
     for net, grads in ((G, gg), (D, gd)):
         overall, each = _grad_errors(net, grads)
-        assert overall < 3e-3, overall
+        assert overall < 2e-3, overall
         assert max(each.values()) < 3e-2, max(each.items(), key=lambda kv: kv[1])
     ref_u, gg, gd = _oracle_step_grads(b, sg, sd, None)
     for k, v in ref_u.items():

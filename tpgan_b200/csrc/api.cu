@@ -56,6 +56,8 @@ struct DeviceState {
   int* status_dev = nullptr;   // device alias of the mapped host status word
   int* status_host = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  void* split_ws = nullptr;    // split-K workspace ring (see kSplitSlots); null = split-K unavailable
+  int* split_cnt = nullptr;
 };
 static DeviceState g_dev;
 static std::mutex g_mu;
@@ -68,6 +70,14 @@ std::atomic<int> g_deterministic{0};
 // SMs, k CTAs of the next launch cannot start until an SM frees up and the launch can take up to twice as long.  With a
 // reserve >= the collective's CTA count both run side by side at (sm_count - k) / sm_count of the tensor throughput.
 std::atomic<int> g_sm_reserve{0};
+// Split-K workspace: a ring of slots (partial accumulators + per-tile arrival counters, self-resetting).  Consecutive
+// launches take consecutive slots; a slot is reused only after kSplitSlots further split launches, i.e. never while an
+// earlier user can still be in flight unless that many whole-GPU launches overlap across streams.
+constexpr int kSplitSlots = 8;
+constexpr size_t kSplitSlotBytes = 4u << 20;
+constexpr int kSplitCounters = 256;
+std::atomic<unsigned> g_split_seq{0};
+
 static inline int persistent_sms() { return std::max(1, g_dev.sm_count - g_sm_reserve.load(std::memory_order_relaxed)); }
 
 // Tensor-core kernels are launched as programmatic dependents of the kernel before them in the stream (captured into CUDA
@@ -122,6 +132,16 @@ static int ensure_device() {
   *g_dev.status_host = 0;
   e = cudaHostGetDevicePointer((void**)&g_dev.status_dev, g_dev.status_host, 0);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e));
+  {   // split-K workspace ring + zeroed arrival counters (the kernels leave every counter at zero again)
+    const size_t ws_bytes = (size_t)kSplitSlots * kSplitSlotBytes, cnt_bytes = (size_t)kSplitSlots * kSplitCounters * sizeof(int);
+    void* p = nullptr;
+    if (cudaMalloc(&p, ws_bytes + cnt_bytes) == cudaSuccess && cudaMemset((char*)p + ws_bytes, 0, cnt_bytes) == cudaSuccess) {
+      g_dev.split_ws = p;
+      g_dev.split_cnt = reinterpret_cast<int*>((char*)p + ws_bytes);
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
   g_dev.ready = true;
   return 0;
 }
@@ -302,6 +322,9 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
   G.kchunks = ceil_div(Kc, CH);
   G.last_mmas = ceil_div(Kc - CH * (G.kchunks - 1), mma_k(bf16));
   G.tile_count = G.n_phases * G.m_tiles * G.n_tiles;
+  G.ksplit = 1;
+  G.kc_per = G.kchunks;
+  G.kt_per = 0;
 
   int rc = encode_planes(G.amap, a.in, gather ? s : 1, G.bw, G.bh, G.bn, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
   if (rc) return rc;
@@ -538,9 +561,9 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
 
 // ------------------------------------------------------------------------------------------------ flat-slab conv
 // Eligible: Conv2d forward / input gradient, stride 1, "same" padding, k >= 3, maps up to 64 pixels wide - every group of the
-// launch.  Opt-in (TPGAN_FLATCONV=1) where tapgemm is bound by L2 -> SM operand traffic: at most 128 (padded)
-// output channels, i.e. the 64- and 128-channel layers of the local pathways; TPGAN_FLATCONV=2 takes every eligible
-// launch, 0 none.  Returns 1 when launched (or failed with *rc_out set), 0 when not eligible.
+// launch.  Taken by default (TPGAN_FLATCONV unset or 1) where it measures faster than tapgemm: at most 128 (padded) output
+// channels, or maps up to 12 wide (the 64 / 128 / 256-channel layers of the local pathways, the 64..128-channel encoder
+// layers of the global pathway at 64x64 and 32x32); TPGAN_FLATCONV=2 takes every eligible launch, 0 none.  Returns 1 when launched (or failed with *rc_out set), 0 when not eligible.
 struct FlatChoice {
   int T, ur, bn;
   double eff;   // real pixels / M rows computed
@@ -575,7 +598,7 @@ static FlatChoice choose_flat(int H, int W, int N, int k, int block_n) {
 static int try_flatconv(const tpgan_conv_args* groups, int ngroups, cudaStream_t st, int* rc_out) {
   *rc_out = 0;
   const char* mode_ev = getenv("TPGAN_FLATCONV");   // read per call: tests switch it between launches
-  const int mode = mode_ev ? atoi(mode_ev) : 0;
+  const int mode = mode_ev ? atoi(mode_ev) : 1;
   if (mode == 0) return 0;
   const tpgan_conv_args& a0 = groups[0];
   if (const char* only = getenv("TPGAN_FLAT_ONLY")) {   // debugging aid: restrict the kernel to one class of launches
@@ -598,7 +621,7 @@ static int try_flatconv(const tpgan_conv_args* groups, int ngroups, cudaStream_t
     n_tiles[i] = ceil_div(a.w_rows_pad, 256);
     block_n[i] = ceil_div(ceil_div(a.w_rows_pad, n_tiles[i]), 16) * 16;
     n_tiles[i] = ceil_div(a.w_rows_pad, block_n[i]);
-    if (mode == 1 && block_n[i] > 128) return 0;
+    if (mode == 1 && block_n[i] > 128 && a.in.w > 12) return 0;
     ch[i] = choose_flat(a.in.h, a.in.w, a.in.n, k, block_n[i]);
     if (ch[i].T < 1 || ch[i].eff < (mode == 1 ? 0.6 : 0.3)) return 0;
   }
@@ -655,13 +678,11 @@ static int try_flatconv(const tpgan_conv_args* groups, int ngroups, cudaStream_t
   P.slab_bytes = ceil_div(slab_rows * 128, 1024) * 1024;
   P.b_bytes = bmax;
   const int budget = g_dev.max_smem - 1024 - 1024;   // alignment slack + this kernel's static shared memory
-  P.a_slots = 3;
+  // two slab slots (the one in use + the next, requested a whole K chunk ahead by its own producer warp); the rest of the
+  // shared memory is the weight ring - the stream whose bytes in flight set the pace
+  P.a_slots = 2;
   P.b_slots = std::min(16, (budget - P.a_slots * P.slab_bytes) / P.b_bytes);
-  if (P.b_slots < 4) {
-    P.a_slots = 2;
-    P.b_slots = std::min(16, (budget - P.a_slots * P.slab_bytes) / P.b_bytes);
-    if (P.b_slots < 3) return 0;
-  }
+  if (P.b_slots < 3) return 0;
   const int smem = P.a_slots * P.slab_bytes + P.b_slots * P.b_bytes + 1024;
   auto kern = bf16 ? flatconv_kernel<true> : flatconv_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 1024);
@@ -1053,6 +1074,38 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     if (f > 1) {
       rc = plan_group(groups[0], P.g[0], f);
       if (rc) return rc;
+    }
+    // Split-K for GEMM-like launches (the Linear layers: rows = images) whose few tiles stream a long reduction - fc1, an
+    // 8x8 "conv" of 64 taps on the 8x8x512 map, reads 67 MB of weights on 16 CTAs otherwise.  The reduction is cut into
+    // ranges of whole taps (or of K chunks of a single tap); partial accumulators go to a workspace slot and the CTA
+    // arriving last at the tile's counter adds them in range order and runs the normal epilogue: deterministic, any epilogue.
+    {
+      const tpgan_conv_args& a = groups[0];
+      TapGemmGroup& G = P.g[0];
+      static const bool no_splitk = getenv("TPGAN_NO_SPLITK") != nullptr;
+      if (!no_splitk && g_dev.split_ws && a.stride == 1 && a.pad == 0 && a.kind == TPGAN_CONV_FWD && a.out.h == 1 && a.out.w == 1 &&
+          G.n_phases == 1 && G.tile_count * 4 <= persistent_sms() && G.tile_count <= kSplitCounters) {
+        const int ntap = G.phase[0].tap_count;
+        const int want = persistent_sms() / G.tile_count;
+        int ksplit = 1, kt_per = 0, kc_per = G.kchunks;
+        if ((long long)ntap * G.kchunks >= 256) {
+          if (ntap >= 2 * want) {
+            kt_per = ceil_div(ntap, want);
+            ksplit = ceil_div(ntap, kt_per);
+          } else if (ntap == 1 && G.kchunks >= 64) {
+            const int ks = std::min(want, G.kchunks / 16);
+            kc_per = ceil_div(ceil_div(G.kchunks, ks), 2) * 2;   // even: a stage carries up to two chunks
+            ksplit = ceil_div(G.kchunks, kc_per);
+          }
+        }
+        if (ksplit > 1 && (size_t)G.tile_count * ksplit * 128 * G.block_n * sizeof(float) <= kSplitSlotBytes) {
+          const unsigned slot = g_split_seq.fetch_add(1, std::memory_order_relaxed) % kSplitSlots;
+          G.split_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_dev.split_ws) + (size_t)slot * kSplitSlotBytes);
+          G.split_cnt = g_dev.split_cnt + slot * kSplitCounters;
+          G.ksplit = ksplit; G.kt_per = kt_per; G.kc_per = kc_per;
+          G.tile_count *= ksplit;
+        }
+      }
     }
     return launch_tapgemm(P, st, bf16);
   }

@@ -10,7 +10,7 @@
 // tiles of a unit share every weight tile (one accumulator each).  M rows that fall into the halo columns / rows compute
 // garbage that is never stored (78-89 % of the rows are real pixels on the local-pathway shapes).
 //
-//   warp 0: TMA producer (slab ring + weight ring)   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4..: epilogue
+//   warp 0: weight-tile TMA producer   warp 3: slab TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4..: epilogue
 #include "common.cuh"
 #include "kparams.h"
 
@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) flatconv_kernel(const __grid_
   const uint32_t bf0 = smem_u32(&b_full[0]), be0 = smem_u32(&b_empty[0]);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer: weight tiles
     if (elect_one()) {
-      int as_ = 0, bs_ = 0;
-      uint32_t aph = 0, bph = 0;
+      int bs_ = 0;
+      uint32_t bph = 0;
       bool ok = true;
       for (int tile = blockIdx.x; ok && tile < P.total_tiles; tile += gridDim.x) {
         const FlatGroup& G = P.g[flat_group_of(P, tile)];
@@ -102,16 +102,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) flatconv_kernel(const __grid_
         const int bn0 = u.nt * G.block_n;
         const uint32_t b_tx = (uint32_t)G.block_n * 128u;
         for (int c = 0; ok && c < G.kchunks; ++c) {
-          if (!mbar_wait_a(ae0 + 8u * as_, aph ^ 1u, ac, 31)) { ok = false; break; }
-          mbar_arrive_expect_tx_a(af0 + 8u * as_, (uint32_t)G.slab_tx);
-          tma_load_4d_a(smem_a + (uint32_t)as_ * slab_bytes, &G.amap, af0 + 8u * as_, c * CH, P.dx0, u.y0 + P.dy0, u.n0);
-          if (++as_ == AS) { as_ = 0; aph ^= 1u; }
           for (int t = 0; t < ntaps; ++t) {
             if (!mbar_wait_a(be0 + 8u * bs_, bph ^ 1u, ac, 32)) { ok = false; break; }
             mbar_arrive_expect_tx_a(bf0 + 8u * bs_, b_tx);
             tma_load_3d_a(smem_b + (uint32_t)bs_ * b_bytes, &G.bmap, bf0 + 8u * bs_, c * CH, bn0, P.wtap[t]);
             if (++bs_ == BS) { bs_ = 0; bph ^= 1u; }
           }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer: activation slabs.  Its own warp, so
+    // that the slab of the next K chunk (or of the next unit) is requested as soon as a slab slot frees up instead of
+    // behind the k*k weight tiles of the current chunk - the slab is the long-latency load of this kernel
+    if (elect_one()) {
+      int as_ = 0;
+      uint32_t aph = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; ok && tile < P.total_tiles; tile += gridDim.x) {
+        const FlatGroup& G = P.g[flat_group_of(P, tile)];
+        const FlatUnit u = flat_unit(G, tile - G.tile_begin);
+        for (int c = 0; c < G.kchunks; ++c) {
+          if (!mbar_wait_a(ae0 + 8u * as_, aph ^ 1u, ac, 31)) { ok = false; break; }
+          mbar_arrive_expect_tx_a(af0 + 8u * as_, (uint32_t)G.slab_tx);
+          tma_load_4d_a(smem_a + (uint32_t)as_ * slab_bytes, &G.amap, af0 + 8u * as_, c * CH, P.dx0, u.y0 + P.dy0, u.n0);
+          if (++as_ == AS) { as_ = 0; aph ^= 1u; }
         }
       }
     }

@@ -51,6 +51,11 @@ struct TapGemmGroup {
   int tiles_h, m_tiles;          // ceil(Hm/bh), tiles_h * ceil(Nimg/bn)
   int n_tiles, block_n;
   int kchunks, last_mmas;        // K = C of the A operand, in 128-byte chunks (32 tf32 / 64 bf16 channels); MMAs in the last chunk
+  int ksplit, kc_per, kt_per;    // split-K (GEMM-like launches with few tiles and a long reduction: the Linear layers): a tile
+                                 // is cut into ksplit ranges of kt_per taps (kt_per > 0) or of kc_per chunks of its single tap.
+  float* split_ws;               // Partial accumulators [tile][range][128 rows][block_n] in a library workspace; the CTA that
+  int* split_cnt;                // arrives last at the tile's counter adds them IN RANGE ORDER (deterministic, no float
+                                 // atomics), runs the normal fused epilogue and resets the counter
   int n_phases;
   int tile_begin, tile_count;    // this group's slice of the persistent tile list
   PhaseDesc phase[kMaxPhases];

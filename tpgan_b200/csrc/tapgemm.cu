@@ -27,6 +27,8 @@ constexpr int kTapGemmThreads = kConvThreads;
 
 struct TileCoord {
   int gi, ph, h0, n0, nt;
+  int t0, t1, c0, c1;   // taps t0 .. t1 and K chunks c0 .. c1 of this tile (everything unless the group is split)
+  int ks, base;         // split-K: range index, un-split tile index inside the group
 };
 
 template <class Params>
@@ -40,6 +42,10 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
   const TapGemmGroup& G = P.g[gi];
   int local = tile - G.tile_begin;
   tc.gi = gi;
+  const int ks = local % G.ksplit;
+  local /= G.ksplit;
+  tc.ks = ks;
+  tc.base = local;
   tc.nt = local % G.n_tiles;
   int rest = local / G.n_tiles;
   int mt = rest % G.m_tiles;
@@ -48,6 +54,12 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
   int nb = mt / G.tiles_h;
   tc.h0 = hb * G.bh;
   tc.n0 = nb * G.bn;
+  const int ntap = G.phase[tc.ph].tap_count;
+  tc.t0 = 0; tc.t1 = ntap; tc.c0 = 0; tc.c1 = G.kchunks;
+  if (G.ksplit > 1) {
+    if (G.kt_per > 0) { tc.t0 = ks * G.kt_per; tc.t1 = min(ntap, tc.t0 + G.kt_per); }
+    else { tc.c0 = ks * G.kc_per; tc.c1 = min(G.kchunks, tc.c0 + G.kc_per); }
+  }
   return tc;
 }
 
@@ -62,6 +74,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_flag;
+  __shared__ int split_last;
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -114,14 +127,14 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
         const int bn0 = tc.nt * G.block_n;
         const TapDesc* taps = &G.taps[ph.tap_begin];
         const CUtensorMap* bm = &G.bmap;
-        for (int t = 0; ok && t < ph.tap_count; ++t) {
+        for (int t = tc.t0; ok && t < tc.t1; ++t) {
           const TapDesc tap = taps[t];
           const CUtensorMap* am = &G.amap[tap.plane];
           const int ax = tap.dx, ay = tc.h0 + tap.dy, wt = tap.wtap;
-          for (int c = 0; c < kchunks; c += kst) {
+          for (int c = tc.c0; c < tc.c1; c += kst) {
             if (!mbar_wait_a(eb, phase ^ 1u, ac, 1)) { ok = false; break; }
             const uint32_t sb = sa + a_region;
-            const bool two = (kst > 1) && (c + 1 < kchunks);
+            const bool two = (kst > 1) && (c + 1 < tc.c1);
             mbar_arrive_expect_tx_a(fb, two ? 2u * chunk_tx : chunk_tx);
             tma_load_4d_a(sa, am, fb, c * CH, ax, ay, tc.n0);
             tma_load_3d_a(sb, bm, fb, c * CH, bn0, wt);
@@ -156,16 +169,17 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccCols);
         const int ntap = G.phase[tc.ph].tap_count;
         const int kchunks = G.kchunks;
-        // MMAs in the last stage of every tap: full chunks before the last one + the partial last chunk
-        const int last_c = ((kchunks - 1) / kst) * kst;
-        const int n_last = (kchunks - 1 - last_c) * 4 + G.last_mmas;
+        // a stage carries kst chunks except the last one of the K range; the last chunk of the whole K may be partial
+        const int c0 = tc.c0, c1 = tc.c1;
         uint32_t acc = 0;
-        for (int t = 0; ok && t < ntap; ++t) {
-          for (int c = 0; c < kchunks; c += kst) {
+        for (int t = tc.t0; ok && t < tc.t1; ++t) {
+          for (int c = c0; c < c1; c += kst) {
             if (!mbar_wait_a(fb, phase, ac, 3)) { ok = false; break; }
             tc_fence_after();
             const uint32_t b_lo = a_lo + areg16;
-            if (c < last_c) {  // a full stage: kst * 4 MMAs
+            const int nch = min(kst, c1 - c);
+            const int n_mma = (nch - 1) * 4 + ((c + nch == kchunks) ? G.last_mmas : 4);
+            if (n_mma == 4 * kst) {  // a full stage: kst * 4 MMAs
               Op::mma(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
               Op::mma(d_tmem, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
               Op::mma(d_tmem, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
@@ -180,7 +194,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
             } else {
 #pragma unroll
               for (int m = 0; m < 8; ++m) {
-                if (m < n_last) {
+                if (m < n_mma) {
                   const uint32_t off = (uint32_t)(m & 3) * 2u;
                   const uint32_t aj = a_lo + off + ((m >> 2) ? (kAStageBytes >> 4) : 0u);
                   const uint32_t bj = b_lo + off + ((m >> 2) ? b16 : 0u);
@@ -229,6 +243,54 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
       const uint32_t t_addr = tmem_base + (uint32_t)(as * kAccCols) + ((uint32_t)(q * 32) << 16);
       const int col_base = tc.nt * G.block_n;
       const EpiArgs E{G.bias, G.slopes, G.cout_valid, G.epilogue, G.round_tf32, G.vec_ok, G.slope};
+      if (G.ksplit > 1) {
+        // ---- split-K: park the partial accumulator, then the last of the tile's ksplit CTAs finishes the tile
+        float* ws = G.split_ws + ((size_t)(tc.base * G.ksplit + tc.ks) * 128 + row) * G.block_n;
+        for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 16 * kEpiPerQuarter) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(ws + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);      // the accumulator is free: the next tile's MMAs overlap the fix-up
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"r"(kTapGemmThreads - 128) : "memory");
+        if (threadIdx.x == 128) {
+          const int prev = atomicAdd(G.split_cnt + tc.base, 1);
+          split_last = (prev == G.ksplit - 1) ? 1 : 0;
+          if (split_last) G.split_cnt[tc.base] = 0;   // ready for the next launch that uses this workspace slot
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(kTapGemmThreads - 128) : "memory");
+        if (split_last) {
+          __threadfence();
+          const float* w0 = G.split_ws + ((size_t)(tc.base * G.ksplit) * 128 + row) * G.block_n;
+          const size_t rstride = (size_t)128 * G.block_n;
+          for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 16 * kEpiPerQuarter) {
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            for (int k2 = 0; k2 < G.ksplit; ++k2) {      // fixed order: bit-reproducible whatever the arrival order
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(w0 + k2 * rstride + c0 + j));
+                acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+              }
+            }
+            uint32_t r[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(acc[j]);
+            if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm, po16);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(kTapGemmThreads - 128) : "memory");   // split_last is rewritten by the next tile
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+        continue;
+      }
       for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 16 * kEpiPerQuarter) {
         uint32_t r[16];
         tmem_ld16(t_addr + (uint32_t)c0, r);

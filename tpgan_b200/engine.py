@@ -22,6 +22,13 @@ from .ops import Act, CONV_DGRAD, CONV_FWD, DECONV_DGRAD, DECONV_FWD, EPI_LEAKY,
 LINEAR = 1.0  # "slope" of a tensor with no activation (nothing to mask in backward)
 
 
+def dw_free(fn):
+    """Mark a backward launch that neither reads nor writes packed weight gradients: the graph capture may leave the
+    weight-gradient branch (train_step.GraphRunner, side stream) running across it."""
+    fn.dw_free = True
+    return fn
+
+
 def _tag(fn, kind: str, nbytes: float, label: str = ""):
     """Attach (kind, algorithmic HBM bytes, label) to a recorded launch; bench.py groups per-launch timings by kind."""
     fn.kind, fn.bytes, fn.label = kind, nbytes, label
@@ -978,7 +985,7 @@ class Plan:
         for p in t.leaves():
             if not p.grad_written:
                 g = self.grad_act(p)
-                self.bwd.append(lambda g=g: g.buf[..., g.c0:g.c0 + g.c].zero_())
+                self.bwd.append(dw_free(lambda g=g: g.buf[..., g.c0:g.c0 + g.c].zero_()))
                 p.grad_written = True
                 p.g16 = False
 
@@ -989,7 +996,7 @@ class Plan:
         for p in t.leaves():
             if p.slope != LINEAR and not p.masked and p.grad_written:
                 g = self.grad_act(p)
-                self.bwd.append(lambda g=g, p=p: ops.act_backward(g, p.act, g, slope=p.slope))
+                self.bwd.append(dw_free(lambda g=g, p=p: ops.act_backward(g, p.act, g, slope=p.slope)))
                 p.masked = True
                 p.g16 = False
 
@@ -1003,7 +1010,7 @@ class Plan:
             self._zero_unwritten(x)
         acc = any(written)
         dst = self.grad_act(x)
-        run = lambda: emit(dst, acc)
+        run = dw_free(lambda: emit(dst, acc))   # writes an activation gradient
         if hasattr(emit, "kind"):   # tagged launches (kind, algorithmic HBM bytes) keep their tag for bench.py
             _tag(run, emit.kind, emit.bytes + (4.0 * dst.n * dst.h * dst.w * dst.c if acc else 0.0), emit.label)
         self.bwd.append(run)

@@ -29,7 +29,7 @@ import torch
 from . import config as cfg
 from . import ops
 from .D_and_G_model import PART_NAMES, PATCH_HW, Discriminator, Generator, _layer, _unpack_conv_seq
-from .engine import LINEAR, ConvLayer, GradArena, Plan, T
+from .engine import LINEAR, ConvLayer, GradArena, Plan, T, dw_free
 from .ModificationLayer import ResidualBlock, _negative_slope
 from .ops import Act, EPI_LEAKY, EPI_LINEAR, EPI_MASK
 
@@ -221,6 +221,10 @@ class GraphRunner:
         self.graphs: Optional[list] = None
         self.warm = False
         self.kernels_per_run = 0
+        import os
+        # weight gradients on a parallel graph branch (see _capture_two_streams); TPGAN_SIDE_WGRAD=0 captures one stream
+        self.side_wgrad = os.environ.get("TPGAN_SIDE_WGRAD", "1") != "0"
+        self._side = torch.cuda.Stream() if self.side_wgrad else None
 
     def run_eager(self):
         for seg in self.segments:
@@ -242,12 +246,45 @@ class GraphRunner:
                 continue
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                for f in seg:
-                    f()
+                if self.side_wgrad:
+                    self._capture_two_streams(seg)
+                else:
+                    for f in seg:
+                        f()
             g.replay()          # capture does not execute: run the segment once so later segments see its results
             self.graphs.append(g)
         self.kernels_per_run = _lib.launch_count() - l0   # kernels of this library recorded into the graphs
         torch.cuda.synchronize()
+
+    def _capture_two_streams(self, seg):
+        """Weight-gradient launches go to a side stream (a parallel branch of the captured graph): wgrad of layer l needs only
+        dy_l - final before the launch is reached - and the stored forward activation, and nothing later in the backward pass
+        writes either, so it may overlap the input-gradient chain that continues on the main stream; its dW is read by the
+        export / optimizer launches only.  The main stream joins the branch before every launch that is not itself a
+        convolution (anything that might read dW) and at the end of the segment."""
+        main = torch.cuda.current_stream()
+        side = self._side
+        pending = False
+        for f in seg:
+            kind = getattr(f, "kind", None)
+            if kind == "wgrad":
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    f()
+                pending = True
+                continue
+            if pending and kind not in ("tapgemm", "rowconv", "cast16") and not getattr(f, "dw_free", False):
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
+                pending = False
+            f()
+        if pending:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     def run(self):
         if not self.warm:       # first call: plain launches (CUDA lazily loads kernels on first use, which capture forbids)
@@ -368,7 +405,7 @@ class CriticPlan:
             if w1 > w0:
                 self.h._emit_wgrad([(L, _sl(x, w0, w1), dy_full)], lst)
                 if L.db_int is not None:
-                    lst.append(lambda d=dy_full, L=L: ops.bias_grad(d, L.db_int, True))
+                    lst.append(dw_free(lambda d=dy_full, L=L: ops.bias_grad(d, L.db_int, True)))
 
         def dyw(a):  # delta of activation `a` restricted to the weight-gradient images
             if a is self.logits:
@@ -460,14 +497,14 @@ class CriticPlan:
         gx = self.g_x
         pre = [lambda: ops.fill(_sl(gl, 0, B), c), lambda: ops.fill(_sl(gl, B, 2 * B), -c),
                lambda: ops.fill(_sl(gl, 2 * B, 3 * B), 1.0), self.zero_grad]
-        mid = [lambda: self.gp_sum.zero_(), lambda: ops.sample_sqnorm(gx, self.sq),
-               lambda: ops.gp_coeff(self.sq, self.coeff, gp_weight * 2.0 / B, self.gp_sum),
-               lambda: ops.sample_scale(gx, self.coeff, self.V_(self.x0))]
+        mid = [dw_free(lambda: self.gp_sum.zero_()), dw_free(lambda: ops.sample_sqnorm(gx, self.sq)),
+               dw_free(lambda: ops.gp_coeff(self.sq, self.coeff, gp_weight * 2.0 / B, self.gp_sum)),
+               dw_free(lambda: ops.sample_scale(gx, self.coeff, self.V_(self.x0)))]
         if self.bf16:   # bf16 twins of the tensors the convs read that pointwise kernels wrote: x0 (the caller filled it),
             # the seeded logit deltas, the tangent seed; every other operand is written by a conv epilogue together with its twin
             x0, v0 = self.x0, self.V_(self.x0)
             pre += [lambda: ops.cast_bf16(x0), lambda: ops.cast_bf16(gl)]
-            mid += [lambda: ops.cast_bf16(v0)]
+            mid += [dw_free(lambda: ops.cast_bf16(v0))]
         return pre + self.fwd_all + self.bwd_d + mid + self.tangent
 
     def g_phase_list(self, adv_weight: float) -> List[Callable]:
