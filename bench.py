@@ -666,7 +666,7 @@ def main():
                     help="N > 1: bucketed all-reduce overlapped with backward, or one all-reduce after backward")
     ap.add_argument("--graph-collectives", action="store_true", help="N > 1: capture the NCCL calls into the step's CUDA graph")
     ap.add_argument("--sm-reserve", type=int, default=0, help="SMs the persistent kernels leave free (for the NCCL kernels)")
-    ap.add_argument("--bucket-mb", type=float, default=32.0, help="N > 1, overlap mode: all-reduce bucket size")
+    ap.add_argument("--bucket-mb", type=float, default=128.0, help="N > 1, overlap mode: all-reduce bucket size")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket one extra step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")

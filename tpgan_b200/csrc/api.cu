@@ -316,7 +316,7 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
   G.bn = (G.bh == G.Hm) ? std::max(1, std::min(G.Nimg, 128 / (G.bw * G.bh))) : 1;
   G.tiles_h = ceil_div(G.Hm, G.bh);
   G.m_tiles = G.tiles_h * ceil_div(G.Nimg, G.bn);
-  G.n_tiles = ceil_div(a.w_rows_pad, 256) * n_split;
+  G.n_tiles = n_split < 0 ? -n_split : ceil_div(a.w_rows_pad, 256) * n_split;   // n_split < 0: explicit tile count
   G.block_n = ceil_div(ceil_div(a.w_rows_pad, G.n_tiles), 16) * 16;
   G.n_tiles = ceil_div(a.w_rows_pad, G.block_n);
   G.kchunks = ceil_div(Kc, CH);
@@ -353,6 +353,8 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
 // (K steps x cycles of one M=128 MMA at that N + a fixed per-tile cost).  Returns the factor by which to multiply n_tiles.
 template <class Params>
 static int choose_n_split(const Params& P, const tpgan_conv_args* groups) {
+  // Returns the number of N tiles per 256 output channels... see choose_n_tiles below (kept: the factor form used by the
+  // grouped launches, powers of two)
   static const bool off = getenv("TPGAN_NO_NSPLIT") != nullptr;
   if (off) return 1;
   double best_cost = 0;
@@ -378,6 +380,34 @@ static int choose_n_split(const Params& P, const tpgan_conv_args* groups) {
     if (f == 1 || cost < best_cost * 0.9) { best_cost = cost; best = f; }
   }
   return best;
+}
+
+// Single launches: any number of N tiles (not only powers of two times the 256-column minimum).  Modelled makespan =
+// waves of tiles x (K steps x cycles per K step + a fixed per-tile cost); a K step costs the MMA (N/2 clocks) or the
+// operand bytes it needs at what a CTA's ~190 KB in flight sustain (~72 B/clk), whichever is larger - the model that
+// reproduces the measured tensor-pipe utilisation of these launches.  The point of the
+// finer search is wave quantisation: enhance_features_16 (768 channels, 64 M tiles) runs 192 tiles of 256 columns on 148
+// SMs, i.e. two waves for 1.3; 256 tiles of 192 columns fill both.  Returns 0 to keep the default tiling.
+static int choose_n_tiles(const TapGemmGroup& G, const tpgan_conv_args& a) {
+  static const bool off = getenv("TPGAN_NO_NSPLIT") != nullptr;
+  if (off) return 0;
+  const int base = ceil_div(a.w_rows_pad, 256);
+  int taps = 0;
+  for (int ph = 0; ph < G.n_phases; ++ph) taps += G.phase[ph].tap_count;
+  const double ksteps = (double)taps / G.n_phases * G.kchunks * 4;
+  double best_cost = 0;
+  int best = 0;
+  for (int nt = base; nt <= base * 8; ++nt) {
+    const int bn = ceil_div(ceil_div(a.w_rows_pad, nt), 16) * 16;
+    if (nt > base && bn < 32) break;
+    if (ceil_div(a.w_rows_pad, bn) != nt) continue;   // this count collapses to a smaller one after rounding to 16 columns
+    const double per_kstep = std::max(bn / 2.0, (4096.0 + 32.0 * bn) / 72.0);
+    const double per_tile = ksteps * per_kstep + 4000.0;
+    const double tiles = (double)G.n_phases * G.m_tiles * nt;
+    const double cost = std::ceil(tiles / persistent_sms()) * per_tile;
+    if (best == 0 || cost < best_cost * 0.95) { best_cost = cost; best = nt; }
+  }
+  return best == base ? 0 : best;
 }
 
 template <class Params>
@@ -561,9 +591,10 @@ static int try_rowstack(const tpgan_conv_args& a, cudaStream_t st, int* rc_out) 
 
 // ------------------------------------------------------------------------------------------------ flat-slab conv
 // Eligible: Conv2d forward / input gradient, stride 1, "same" padding, k >= 3, maps up to 64 pixels wide - every group of the
-// launch.  Taken by default (TPGAN_FLATCONV unset or 1) where it measures faster than tapgemm: at most 128 (padded) output
-// channels, or maps up to 12 wide (the 64 / 128 / 256-channel layers of the local pathways, the 64..128-channel encoder
-// layers of the global pathway at 64x64 and 32x32); TPGAN_FLATCONV=2 takes every eligible launch, 0 none.  Returns 1 when launched (or failed with *rc_out set), 0 when not eligible.
+// launch.  Opt-in: TPGAN_FLATCONV=1 takes the launches where it measures faster than tapgemm in isolation (13-20 %: at most
+// 128 (padded) output channels, or maps up to 12 wide - the 64 / 128 / 256-channel layers of the local pathways, the
+// 64..128-channel encoder layers of the global pathway at 64x64 and 32x32), =2 every eligible launch.  Off by default: on
+// the whole (power-capped) step the A/B difference is below the run-to-run noise (44.05 vs 44.02, 43.70 vs 43.69 ms).  Returns 1 when launched (or failed with *rc_out set), 0 when not eligible.
 struct FlatChoice {
   int T, ur, bn;
   double eff;   // real pixels / M rows computed
@@ -598,7 +629,7 @@ static FlatChoice choose_flat(int H, int W, int N, int k, int block_n) {
 static int try_flatconv(const tpgan_conv_args* groups, int ngroups, cudaStream_t st, int* rc_out) {
   *rc_out = 0;
   const char* mode_ev = getenv("TPGAN_FLATCONV");   // read per call: tests switch it between launches
-  const int mode = mode_ev ? atoi(mode_ev) : 1;
+  const int mode = mode_ev ? atoi(mode_ev) : 0;
   if (mode == 0) return 0;
   const tpgan_conv_args& a0 = groups[0];
   if (const char* only = getenv("TPGAN_FLAT_ONLY")) {   // debugging aid: restrict the kernel to one class of launches
@@ -1070,9 +1101,9 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     P.ngroups = 1;
     rc = plan_group(groups[0], P.g[0]);
     if (rc) return rc;
-    const int f = choose_n_split(P, groups);
-    if (f > 1) {
-      rc = plan_group(groups[0], P.g[0], f);
+    const int nt = choose_n_tiles(P.g[0], groups[0]);
+    if (nt > 0) {
+      rc = plan_group(groups[0], P.g[0], -nt);
       if (rc) return rc;
     }
     // Split-K for GEMM-like launches (the Linear layers: rows = images) whose few tiles stream a long reduction - fc1, an

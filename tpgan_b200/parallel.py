@@ -40,7 +40,7 @@ def allreduce_sum(t: torch.Tensor, group=None):
 class BucketReducer:
     """Bucketed, backward-overlapped gradient all-reduce over the generator's flat gradient buffer."""
 
-    def __init__(self, trainer, bucket_mb: float = 32.0, group=None):
+    def __init__(self, trainer, bucket_mb: float = 128.0, group=None):
         from .ops import round_up
         self.tr, self.group = trainer, group
         plan, flat = trainer.plan, trainer.flat_g
@@ -72,7 +72,9 @@ class BucketReducer:
         self.sets = [LayerSet(layers[i0:i1], trainer.device, plan.bias_jobs) for (i0, i1, _, _) in self.buckets]
         self.ready = ready
         self.tail = (acc, flat.total - acc)  # parameters outside the traced layers (none for G): reduced with the last bucket
-        self.comm = torch.cuda.Stream()
+        import os
+        # a high-priority stream: NCCL's CTAs are placed as soon as an SM frees up instead of behind the queued persistent grids
+        self.comm = torch.cuda.Stream(priority=int(os.environ.get("TPGAN_COMM_PRIORITY", "0")))
         self.works: list = []
 
     def hooks(self) -> Dict[int, Callable[[], None]]:

@@ -225,6 +225,9 @@ class GraphRunner:
         # weight gradients on a parallel graph branch (see _capture_two_streams); TPGAN_SIDE_WGRAD=0 captures one stream
         self.side_wgrad = os.environ.get("TPGAN_SIDE_WGRAD", "1") != "0"
         self._side = torch.cuda.Stream() if self.side_wgrad else None
+        # data parallel: SMs left to NCCL by the launches right behind an overlapped all-reduce (see capture())
+        self.reserve_sms = int(os.environ.get("TPGAN_DP_RESERVE", "0"))
+        self.reserve_launches = int(os.environ.get("TPGAN_DP_RESERVE_LAUNCHES", "3"))
 
     def run_eager(self):
         for seg in self.segments:
@@ -239,11 +242,20 @@ class GraphRunner:
         torch.cuda.synchronize()
         self.graphs = []
         l0 = _lib.launch_count()
+        after_collective = False
         for seg in self.segments:
             if isinstance(seg, Eager):
                 seg()
                 self.graphs.append(seg)
+                after_collective = isinstance(seg, Collective)
                 continue
+            # A segment that starts right behind an overlapped all-reduce: its first launches are captured with a few SMs left
+            # free, so that NCCL's CTAs run NEXT to the persistent kernels instead of delaying the CTAs that would have
+            # taken those SMs (a statically partitioned launch is as slow as its last CTA).  Only those launches pay.
+            window = self.reserve_launches if (after_collective and self.reserve_sms > 0) else 0
+            if window:
+                seg = self._with_reserve(seg, window)
+            after_collective = False
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 if self.side_wgrad:
@@ -255,6 +267,29 @@ class GraphRunner:
             self.graphs.append(g)
         self.kernels_per_run = _lib.launch_count() - l0   # kernels of this library recorded into the graphs
         torch.cuda.synchronize()
+
+    def _with_reserve(self, seg, window: int):
+        """seg with tpgan_set_sm_reserve(reserve_sms) around its first `window` tensor-core launches (host-side planning
+        state: it shapes the grid of the launches recorded while it is set, so it must be set at CAPTURE time)."""
+        from . import _lib
+        out, seen, on = [], 0, False
+        for f in seg:
+            is_tc = getattr(f, "kind", None) in ("tapgemm", "rowconv", "wgrad")
+            if is_tc and seen < window:
+                def wrapped(f=f):
+                    prev = _lib.set_sm_reserve(self.reserve_sms)
+                    try:
+                        f()
+                    finally:
+                        _lib.set_sm_reserve(prev)
+                for attr in ("kind", "flops", "label", "dw_free"):
+                    if hasattr(f, attr):
+                        setattr(wrapped, attr, getattr(f, attr))
+                out.append(wrapped)
+                seen += 1
+            else:
+                out.append(f)
+        return out
 
     def _capture_two_streams(self, seg):
         """Weight-gradient launches go to a side stream (a parallel branch of the captured graph): wgrad of layer l needs only
@@ -577,7 +612,7 @@ class TPGANTrainer:
     (DataAndDataset.py:10-56)."""
 
     def __init__(self, G: Generator, D: Discriminator, B: int, device="cuda", use_dropout: bool = False,
-                 exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 32.0, use_graphs: bool = False,
+                 exact: bool = False, world_size: int = 1, group=None, bucket_mb: float = 128.0, use_graphs: bool = False,
                  identity_net=None, input_format: str = "float", dtype: str = "tf32", overlap_allreduce: bool = True,
                  graph_collectives: bool = False, force_reducer: bool = False):
         """identity_net: optional frozen FeatureExtractModel / ResNet18 in eval() mode; adds the identity-preserving
