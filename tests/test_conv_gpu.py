@@ -386,6 +386,30 @@ def test_linear_split_k(case):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("case", [(2, 3, 64, 128, 128, 7, 1, 3), (3, 3, 64, 128, 128, 3, 2, 1), (4, 3, 48, 40, 56, 5, 1, 2), (2, 4, 64, 33, 47, 3, 1, 1)])
+def test_wgrad_im2col_rgb_slice(case):
+    """Weight gradients of the RGB input layers (generator conv0.0: 3->64 k7, critic layer 0: 3->64 k3 stride 2) take the
+    im2col-by-TMA path: a zero-padded float4 copy of the input read through tensor maps with overlapping 8-pixel windows.
+    Here the input is a channel SLICE of a wider concat buffer (as I128 is in the generator: D_and_G_model.py:312)."""
+    from tpgan_b200 import ops
+    n, cin, cout, h, w, k, s, p = case
+    x = _mk(n, cin, h, w, 1)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    dy = _mk(n, cout, ho, wo, 5)
+    ref = torch.nn.grad.conv2d_weight(x, (cout, cin, k, k), dy, stride=s, padding=p)
+    wide = ops.Act.empty(n, h, w, 76)
+    wide.buf.uniform_(-1, 1)
+    xa = wide.slice(72, cin) if cin <= 4 else None
+    xa.from_nchw(x.cuda(), round_tf32=True)
+    dw = ops.alloc_packed(ops.CONV_FWD, (cout, cin, k, k))
+    for _ in range(2):     # the second launch takes the next slot of the padded-copy ring and accumulates
+        ops.wgrad(ops.CONV_FWD, xa, _act(dy, ops), dw, k, s, p)
+    got = torch.zeros((cout, cin, k, k), device="cuda")
+    ops.unpack_weights(dw, got, ops.CONV_FWD)
+    torch.cuda.synchronize()
+    assert rel(got, 2 * ref) < TOL
+
+
 GROUPED_WGRAD_CASES = [
     # (cin, cout, k, stride, pad, kind, patch sizes of the four pathways at this depth) - D_and_G_model.py:390-393 patches
     # 40x40 / 40x40 / 32x40 / 32x48 after 0..3 stride-2 convs.  10x10 and 5x5 boxes do not fill their last 8-pixel K step while

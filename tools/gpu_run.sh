@@ -1,15 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu --no-secondary"
-show() { python -c "
-import json,sys
-for l in open('$1'):
+python -m pytest tests -x -q -m gpu > gpurun_out/r3c_pytest_all.log 2>&1; echo "pytest all rc=$?"; tail -3 gpurun_out/r3c_pytest_all.log
+python bench.py --no-cpu --no-secondary --per-layer gpurun_out/r3c_per_layer.jsonl > gpurun_out/r3c_bench.json 2>/dev/null
+python - <<EOF
+import json
+for l in open('gpurun_out/r3c_bench.json'):
     if l.startswith('{'):
-        d=json.loads(l); print('$2', round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), d.get('replica_checksum_spread'))
-"; }
-CUDA_VISIBLE_DEVICES=0 python bench.py --no-cpu --no-secondary > gpurun_out/r2x_n1.json 2>/dev/null; show gpurun_out/r2x_n1.json n1
-i=0
-for v in "0 32" "-1 96" "0 96" "-1 64" "-1 160" "-1 96" "0 32"; do
-  set -- $v; i=$((i+1))
-  TPGAN_COMM_PRIORITY=$1 $T --bucket-mb $2 > gpurun_out/r2x_$i.json 2>gpurun_out/r2x_$i.err; show gpurun_out/r2x_$i.json "dp2 prio=$1 bucket=$2"
-done
+        d=json.loads(l); print(round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), d['clocks']['sm_mhz'], round(d['roofline']['frac'],3))
+for l in open('gpurun_out/r3c_per_layer.jsonl'):
+    r=json.loads(l)
+    if r['kind']=='wgrad' and r['tflops']<60 and r['ms']>0.025: print(r['ms'], r['tflops'], r['label'][:70])
+EOF

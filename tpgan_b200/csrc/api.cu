@@ -58,6 +58,7 @@ struct DeviceState {
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   void* split_ws = nullptr;    // split-K workspace ring (see kSplitSlots); null = split-K unavailable
   int* split_cnt = nullptr;
+  void* im2col_ws = nullptr;   // padded-input ring of the im2col-by-TMA weight gradients; null = that mode is off
 };
 static DeviceState g_dev;
 static std::mutex g_mu;
@@ -77,6 +78,11 @@ constexpr int kSplitSlots = 8;
 constexpr size_t kSplitSlotBytes = 4u << 20;
 constexpr int kSplitCounters = 256;
 std::atomic<unsigned> g_split_seq{0};
+// Zero-padded float4-per-pixel copies of <= 4-channel conv inputs for the im2col-by-TMA weight gradients (same ring
+// discipline: written and read by consecutive launches of one stream, reused kIm2colSlots launches later).
+constexpr int kIm2colSlots = 4;
+constexpr size_t kIm2colSlotBytes = 32u << 20;
+std::atomic<unsigned> g_im2col_seq{0};
 
 static inline int persistent_sms() { return std::max(1, g_dev.sm_count - g_sm_reserve.load(std::memory_order_relaxed)); }
 
@@ -141,6 +147,9 @@ static int ensure_device() {
     } else {
       (void)cudaGetLastError();
     }
+    void* q = nullptr;
+    if (cudaMalloc(&q, (size_t)kIm2colSlots * kIm2colSlotBytes) == cudaSuccess) g_dev.im2col_ws = q;
+    else (void)cudaGetLastError();
   }
   g_dev.ready = true;
   return 0;
@@ -728,6 +737,7 @@ static int try_flatconv(const tpgan_conv_args* groups, int ngroups, cudaStream_t
 // ------------------------------------------------------------------------------------------------ wgrad planning
 // How one weight-gradient problem is mapped onto the kernel (see WgradGroup in kparams.h).
 struct WgradChoice {
+  bool im2col;    // <= 4 input channels: horizontal taps folded into the 32-lane chunk (see WgradGroup::im2col_k)
   bool swap;      // stride-1 conv only: P = x (M = Cin), Q = dy shifted by -tap (N = Cout), dw written transposed
   bool slab;      // taps of one kernel row share one Q slab (N = taps * 32 per MMA)
   int pc, qc;     // channels of P and Q
@@ -842,8 +852,41 @@ static WgradChoice wgrad_option(const tpgan_wgrad_args& a, bool swap, bool slab)
   return c;
 }
 
+// im2col-by-TMA weight gradients: Conv2d with at most 4 input channels stored as one aligned float4 per pixel (the RGB
+// layers: generator conv0.0, local conv0.0, critic layer 0), stride 1 or 2, tf32.  Instead of k*k taps that each use 3 of
+// the 32 K lanes of a chunk, the k horizontal taps x 4 channels of a kernel row ARE the chunk.
+static thread_local int g_wgrad_ngroups = 1;   // set by tpgan_conv2d_wgrad around planning
+static bool wgrad_im2col_ok(const tpgan_wgrad_args& a) {
+  static const bool off = getenv("TPGAN_NO_IM2COL") != nullptr;
+  if (off || !g_dev.im2col_ws) return false;
+  // single launches only: in the grouped local-pathway launch (four 40x40-ish patches) the four padded copies cost more
+  // than the better lane use saves (measured 0.045 -> 0.056 ms)
+  if (g_wgrad_ngroups != 1) return false;
+  if (a.kind != TPGAN_CONV_FWD || a.dtype != TPGAN_DTYPE_TF32) return false;
+  if (a.x.c > 4) return false;
+  if (a.kh != a.kw || a.kh < 2 || a.kh > 8 || (a.stride != 1 && a.stride != 2)) return false;
+  const size_t bytes = (size_t)a.x.n * (a.x.h + 2 * a.pad) * (a.x.w + 2 * a.pad + 8) * 16;
+  return bytes <= kIm2colSlotBytes;
+}
+
 static WgradChoice choose_wgrad(const tpgan_wgrad_args& a) {
   static const int slab_mode = getenv("TPGAN_WGRAD_SLAB") ? atoi(getenv("TPGAN_WGRAD_SLAB")) : 1;
+  if (wgrad_im2col_ok(a)) {
+    WgradChoice c{};
+    c.im2col = true;
+    c.pc = a.dy.c;
+    c.qc = 32;
+    c.m_tiles = ceil_div(c.pc, 128);
+    c.nch_total = c.ncpt = 1;
+    c.n_tiles = 1;
+    c.tpu = a.kh;
+    c.block_n = c.tpu * 32;
+    c.mpu = 1;
+    c.a_ch = std::min(4, ceil_div(c.pc, 32));
+    c.b_ch = c.tpu;
+    c.cost = 0;
+    return c;
+  }
   WgradChoice best = wgrad_option(a, false, false);
   const bool is_conv = (a.kind == TPGAN_CONV_FWD);
   const tpgan_view& Pt = is_conv ? a.dy : a.x;
@@ -858,7 +901,84 @@ static WgradChoice choose_wgrad(const tpgan_wgrad_args& a) {
   return best;
 }
 
-static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
+// xp[n][y + p][x + p][0..3] = x[n][y][x][0..C) (C <= 4; x may be a channel slice of a wider buffer), zero elsewhere; xp is
+// dense [N][Hq][Wq] with one float4 per pixel.
+__global__ void pad_copy4_kernel(const float* __restrict__ x, long long sn, long long sh, long long sw, int C, int N, int H,
+                                 int W, int p, int Hq, int Wq, float4* __restrict__ xp) {
+  const long long total = (long long)N * Hq * Wq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(i % Wq);
+    const long long r = i / Wq;
+    const int yq = (int)(r % Hq), n = (int)(r / Hq);
+    const int xs = xq - p, ys = yq - p;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (xs >= 0 && xs < W && ys >= 0 && ys < H) {
+      const float* src = x + n * sn + ys * sh + xs * sw;
+      for (int c = 0; c < C; ++c) v[c] = src[c];
+    }
+    xp[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+static int plan_wgrad_im2col(const tpgan_wgrad_args& a, WgradGroup& G, int box_px, cudaStream_t st) {
+  const int k = a.kh, s = a.stride, p = a.pad;
+  const int Hq = a.x.h + 2 * p, Wq = a.x.w + 2 * p + 8;
+  const unsigned slot = g_im2col_seq.fetch_add(1, std::memory_order_relaxed) % kIm2colSlots;
+  float* xp = reinterpret_cast<float*>(reinterpret_cast<char*>(g_dev.im2col_ws) + (size_t)slot * kIm2colSlotBytes);
+  {
+    const long long total = (long long)a.x.n * Hq * Wq;
+    const int grid = (int)std::max(1ll, std::min((total + 255) / 256, (long long)g_dev.sm_count * 8));
+    pad_copy4_kernel<<<grid, 256, 0, st>>>(a.x.ptr, a.x.sn, a.x.sh, a.x.sw, a.x.c, a.x.n, a.x.h, a.x.w, p, Hq, Wq,
+                                           reinterpret_cast<float4*>(xp));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "pad_copy4 launch: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  const tpgan_view& Pt = a.dy;
+  G.transpose_out = 0;
+  G.m_valid = Pt.c;
+  G.n_valid = 32;
+  G.im2col_k = k;
+  G.im2col_cin = a.x.c;
+  G.Hp = Pt.h; G.Wp = Pt.w; G.Nimg = Pt.n;
+  G.bw = (G.Wp <= box_px + box_px / 2) ? G.Wp : box_px;
+  G.bh = std::max(1, std::min(G.Hp, box_px / G.bw));
+  G.bn = (G.bh == G.Hp && G.bw == G.Wp) ? std::max(1, std::min(G.Nimg, box_px / (G.bw * G.bh))) : 1;
+  G.p_rows = G.bw * G.bh * G.bn;
+  G.kp = ceil_div(G.p_rows, 8) * 8;
+  G.tiles_w = ceil_div(G.Wp, G.bw);
+  G.tiles_h = ceil_div(G.Hp, G.bh);
+  G.chunks = G.tiles_w * G.tiles_h * ceil_div(G.Nimg, G.bn);
+  G.m_tiles = ceil_div(Pt.c, 128);
+  G.ncpt = 1; G.tpu = k; G.n_tiles = 1; G.block_n = k * 32; G.mpu = 1; G.slab = 0;
+  G.mt_groups = G.m_tiles;
+  G.ntaps = k; G.tap_groups = 1;
+  G.nbuf = (G.block_n <= 256) ? 2 : 1;
+  G.q_chunk_bytes = G.kp * 128;
+  G.q_rows = G.p_rows;
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  int rc = encode_nhwc(&G.pmap, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.bw, G.bh, G.bn, swz, 32, 0);
+  if (rc) return rc;
+  if (G.kp > G.p_rows) {
+    rc = encode_nhwc(&G.pzero, Pt.ptr, Pt.c, Pt.w, Pt.h, Pt.n, Pt.sw, Pt.sh, Pt.sn, G.kp - G.p_rows, 1, 1, swz, 32, 0);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < k; ++r) {
+    // vertical tap r: 32 "channels" = the 8-pixel window starting at padded pixel (stride*y + r, stride*x); the pixel
+    // stride of the map (16 B x stride) is smaller than its inner extent (128 B) - overlapping windows, by design
+    rc = encode_nhwc(&G.qmap[r], xp + (size_t)r * Wq * 4, 32, Pt.w, Pt.h, Pt.n, 4ll * s, 4ll * s * Wq, 4ll * Hq * Wq, G.bw, G.bh, G.bn,
+                     swz, 32, 0);
+    if (rc) return rc;
+    TapDesc t;
+    t.plane = (int8_t)r;
+    t.dy = t.dx = 0;
+    t.wtap = (uint8_t)r;
+    G.taps[r] = t;
+  }
+  return 0;
+}
+
+static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px, cudaStream_t st = nullptr) {
   memset(&G, 0, sizeof(G));
   const int k = a.kh;
   if (a.kh != a.kw || k < 1 || k > 8) return set_error(TPGAN_ERR_INVALID, "kernel %dx%d unsupported", a.kh, a.kw);
@@ -886,6 +1006,7 @@ static int plan_wgrad(const tpgan_wgrad_args& a, WgradGroup& G, int box_px) {
   G.k_pad = a.w_k_pad;
   G.dw = a.dw_packed;
   G.accumulate = a.accumulate;
+  if (ch.im2col) return plan_wgrad_im2col(a, G, box_px, st);
   G.Hp = Pt.h;
   G.Wp = Pt.w;
   G.Nimg = Pt.n;
@@ -1020,7 +1141,12 @@ static int launch_wgrad(Params& P, cudaStream_t st, int bf16) {
     // K blocks: pixel ranges whose activations (P and Q) fit a slice of L2; every CTA works through block after block
     {
       static const double mb_plain = getenv("TPGAN_WGRAD_KB_MB") ? atof(getenv("TPGAN_WGRAD_KB_MB")) : 64.0;
-      static const double mb_slab = getenv("TPGAN_WGRAD_KB_MB_SLAB") ? atof(getenv("TPGAN_WGRAD_KB_MB_SLAB")) : 1e6;   // slab units stream little from L2 and pay for every extra epilogue
+      // slab units stream little from L2 and pay for every extra epilogue: one K block - unless the activations would be
+      // streamed from HBM a dozen times (75->75 k7: 7 kernel rows x 2 tap groups = 14 passes over 0.32 GB = 3.8 GB of DRAM
+      // reads at 51 % of the DRAM peak, ncu_full_r2_wgrad_add128): then 64 MB blocks keep a block's pixels in L2 for all
+      // its tiles (measured 0.910 -> 0.845 ms; the 64-channel and swapped 206->64 layers, 7-10 passes, lose with blocks)
+      static const double mb_slab_env = getenv("TPGAN_WGRAD_KB_MB_SLAB") ? atof(getenv("TPGAN_WGRAD_KB_MB_SLAB")) : 0.0;
+      const double mb_slab = mb_slab_env > 0 ? mb_slab_env : (G.tiles >= 12 ? 64.0 : 1e6);
       const double bytes = (double)G.Hp * G.Wp * G.Nimg * (bf16 ? 2.0 : 4.0) * (ceil_div(G.m_valid, 4) * 4 + ceil_div(G.n_valid, 4) * 4);
       int nkb = (int)std::ceil(bytes / ((G.slab ? mb_slab : mb_plain) * 1048576.0));
       nkb = std::max(1, std::min(nkb, G.chunks));
@@ -1169,11 +1295,12 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
   const int bf16 = groups[0].dtype == TPGAN_DTYPE_BF16;
   for (int i = 1; i < ngroups; ++i)
     if (groups[i].dtype != groups[0].dtype) return set_error(TPGAN_ERR_INVALID, "grouped problems must share one dtype");
+  g_wgrad_ngroups = ngroups;
   if (ngroups == 1) {
     static thread_local WgradParams1 P;
     P.ngroups = 1;
     P.zero_tail = 0;
-    rc = plan_wgrad(groups[0], P.g[0], choose_wgrad_px(groups, 1));
+    rc = plan_wgrad(groups[0], P.g[0], choose_wgrad_px(groups, 1), st);
     if (rc) return rc;
     return launch_wgrad(P, st, bf16);
   }
@@ -1182,7 +1309,7 @@ int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* st
   bool uniform = true;
   const int px = choose_wgrad_px(groups, ngroups);
   for (int i = 0; i < ngroups; ++i) {
-    rc = plan_wgrad(groups[i], P.g[i], px);
+    rc = plan_wgrad(groups[i], P.g[i], px, st);
     if (rc) return rc;
     const WgradGroup& G = P.g[i];
     if (G.p_rows % mma_k(bf16)) uniform = false;

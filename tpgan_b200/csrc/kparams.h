@@ -198,6 +198,12 @@ struct WgradGroup {
   int transpose_out;             // 0: dw[tap][m][n]   1: dw[tap][n][m]
   int m_valid, n_valid;          // bounds in the dw tensor (rows_pad/k_pad by orientation)
   int accumulate;                // 1: dW += (always atomics); 0: dW = (plain stores when the K range is not split)
+  // im2col-by-TMA mode (inputs of <= 4 channels, e.g. the RGB layers): Q is a zero-padded copy of x seen through tensor maps
+  // whose pixel stride (16 B x stride) is smaller than their 128-byte inner extent - row p of the operand is the window of 8
+  // consecutive pixels x 4 channels that starts at input pixel stride*p, i.e. ALL horizontal taps of a kernel row in one
+  // 32-lane chunk.  The taps of a unit are the k VERTICAL taps (one map each, plane = r); accumulator column
+  // r*32 + j*4 + c is dW[tap (r, j)][m][c].  im2col_k = k (0 = off).
+  int im2col_k, im2col_cin;
 };
 
 struct WgradParams {

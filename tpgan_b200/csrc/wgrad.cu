@@ -309,6 +309,18 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_co
       const int cols_per_tap = (G.tpu > 1) ? G.ncpt * CH : G.block_n;
       // 16 accumulator columns of row m -> dw (columns n0 .. n0+15 of tap `tap`)
       auto store16 = [&](const uint32_t (&r)[16], const TapDesc tap, int m, int n0) {
+        if (G.im2col_k) {        // column n of vertical tap r = (horizontal tap n / 4, input channel n % 4)
+          const int kk = G.im2col_k, rr = tap.wtap;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j, jt = n >> 2, c = n & 3;
+            if (jt < kk && c < G.im2col_cin) {
+              float* d = G.dw + ((size_t)(rr * kk + jt) * G.rows_pad + m) * G.k_pad + c;
+              if (single) *d = __uint_as_float(r[j]); else atomicAdd(d, __uint_as_float(r[j]));
+            }
+          }
+          return;
+        }
         float* dw = G.dw + (size_t)tap.wtap * G.rows_pad * G.k_pad;
         if (G.transpose_out) {   // dw[n][m]: lanes hold consecutive m -> every red is a coalesced 128 B row segment
 #pragma unroll
