@@ -315,7 +315,7 @@ def gan_line(a, B, dtype, identity, steps, warmup, world, rank, dev, want_roofli
                 "all_conv_kernels": {"achieved": tot_fl / (tot_t * 1e-3) / 1e12, "frac": tot_fl / (tot_t * 1e-3) / 1e12 / peak_sus,
                                      "share_of_step": tot_t / step_ms, "algorithmic_gflop_per_step": tot_fl / 1e9},
                 "whole_step": {"achieved": tot_fl / (step_ms * 1e-3) / 1e12, "frac": tot_fl / (step_ms * 1e-3) / 1e12 / peak_sus}}
-    if rank == 0 and want_cpu and not a.no_cpu:
+    if rank == 0 and world == 1 and want_cpu and not a.no_cpu:   # N = 1 only: with N ranks the host cores are shared
         sec, threads = cpu_port_step_time(CPU_BATCH, 3, 1)
         cpu = {"value": CPU_BATCH / sec, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"three oracle-port G+D training steps (fp32 PyTorch, CPU) at batch {CPU_BATCH} after one warm-up step"}
@@ -611,7 +611,7 @@ def pretrain_line(a, world, rank, dev, want_roofline=True):
                 "other_kernels": {names.get(k, k): entry(k) for k in agg if k != dom}}
     line = None
     if rank == 0:
-        if not a.no_cpu:
+        if not a.no_cpu and world == 1:
             sec, threads = (cpu_classifier_step_time if resnet else cpu_pretrain_step_time)(B, 2, 1)
             cpu = {"value": B / sec, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"two oracle-port {'ResNet18 classifier' if resnet else 'Pretrain'} steps (fp32 PyTorch, CPU) at batch {B} after one warm-up"}
