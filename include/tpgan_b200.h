@@ -4,7 +4,8 @@
  * This is the drop-in boundary.  The reference (PandaKenWei/TP-GAN) has no FFI: its hot path is a set of
  * ATen calls made from ModificationLayer.py / D_and_G_model.py.  Each entry point below names the reference
  * call site(s) it replaces.  All pointers are raw device pointers owned by the caller (PyTorch's allocator
- * in the shipped host code); the library never allocates or frees device memory on the data path.
+ * in the shipped host code); the library never allocates or frees device memory on the data path (it owns one fixed
+ * scratch allocation made on first use, see tpgan_conv2d).
  * All tensors are fp32, channels-last ("NHWC") views with unit channel stride.  Tensor-core math is TF32
  * (tcgen05.mma kind::tf32, fp32 accumulation in TMEM).
  *
@@ -88,7 +89,14 @@ typedef struct tpgan_conv_args {
 } tpgan_conv_args;
 
 /* Runs 1..4 independent problems in ONE persistent launch (the four local pathways of
- * D_and_G_model.py:390-393 are one grouped launch per layer). */
+ * D_and_G_model.py:390-393 are one grouped launch per layer).
+ * Library-owned scratch: two kinds of launch use a small ring of device workspace slots that the library allocates once
+ * (first call) - Linear-like launches whose reduction is split over the SMs (partial accumulators + per-tile arrival
+ * counters; the result is deterministic), and, in tpgan_conv2d_wgrad, weight gradients of <= 4-channel inputs (a
+ * zero-padded copy of the input).  A slot is written and read by launches that follow each other in `stream` and is
+ * reused 4-8 such launches later; callers that issue these launches concurrently on SEVERAL streams of one process must
+ * serialise them.  All launches are issued as programmatic dependents of the preceding kernel in `stream` and order
+ * their global-memory accesses themselves (griddepcontrol.wait); no caller-visible change. */
 TPGAN_API int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream);
 
 /* Weight gradient, accumulated (+=, fp32 atomics) into the forward-packed layout:
