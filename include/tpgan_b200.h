@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TPGAN_ABI_VERSION 2
+#define TPGAN_ABI_VERSION 3
 #define TPGAN_API __attribute__((visibility("default")))
 
 enum tpgan_status {
@@ -86,6 +86,11 @@ typedef struct tpgan_conv_args {
                              (operand storage for the tensor-core consumers of this tensor); ptr addresses 2-byte elements,
                              8-byte aligned, strides in elements.  With out16 given, out.ptr may be NULL (no fp32 copy); out's
                              n/h/w/c must describe the output either way.  bias / add1 / add2 / mask stay fp32. */
+  /* fp32-accurate "3xTF32" product in ONE launch (ABI v3; TF32 only, kh*kw*3 <= 64): `in` / `w_packed` hold the tf32-rounded
+   * high parts, in_lo / w_lo_packed the residuals (tpgan_split_tf32, tpgan_pack_weights with round_tf32 = 2); the launch
+   * accumulates in_hi*w_lo + in_lo*w_hi + in_hi*w_hi in the same TMEM accumulator.  in_lo.ptr NULL = plain product. */
+  tpgan_view in_lo;
+  const float* w_lo_packed;
 } tpgan_conv_args;
 
 /* Runs 1..4 independent problems in ONE persistent launch (the four local pathways of

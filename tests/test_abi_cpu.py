@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
 def test_abi_version_and_error_string():
     from tpgan_b200 import _lib
     lib = _lib.load()
-    assert lib.tpgan_abi_version() == 2     # v2: dtype + out16 in the conv / wgrad argument structs (bf16 operands)
+    assert lib.tpgan_abi_version() == 3     # v2: dtype + out16 (bf16 operands); v3: in_lo / w_lo_packed (one-launch 3xTF32)
     assert isinstance(lib.tpgan_last_error(), bytes)
     assert lib.tpgan_launch_count() >= 0
 

@@ -28,7 +28,7 @@ class ConvArgs(C.Structure):
                 ("in_", View), ("out", View), ("w_packed", C.c_void_p), ("w_rows_pad", C.c_int32),
                 ("w_k_pad", C.c_int32), ("bias", C.c_void_p), ("add1", View), ("add2", View), ("mask", View),
                 ("slopes", C.c_void_p), ("slope", C.c_float), ("epilogue", C.c_int32), ("round_tf32", C.c_int32),
-                ("dtype", C.c_int32), ("out16", View)]
+                ("dtype", C.c_int32), ("out16", View), ("in_lo", View), ("w_lo_packed", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):

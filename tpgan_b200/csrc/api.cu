@@ -319,6 +319,33 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
         ph.tap_count = (short)(ntap - ph.tap_begin);
       }
   }
+  // One-launch 3xTF32: every phase's tap list three times - (in_hi, w_lo), (in_lo, w_hi), (in_hi, w_hi); the in_lo planes
+  // follow the in_hi planes in amap[], bit 7 of wtap selects the residual weight packing.
+  const bool exact3 = a.in_lo.ptr != nullptr;
+  const int nplanes = gather ? s * s : 1;
+  if (exact3) {
+    if (bf16 || !a.w_lo_packed) return set_error(TPGAN_ERR_INVALID, "in_lo needs TF32 operands and w_lo_packed");
+    if (ntap * 3 > kMaxTaps || nplanes * 2 > kMaxPlanes || taps + 1 > 0x7f)
+      return set_error(TPGAN_ERR_INVALID, "3xTF32 in one launch: %d taps x 3 exceed the tap table", ntap);
+    if (a.in_lo.n != a.in.n || a.in_lo.h != a.in.h || a.in_lo.w != a.in.w || a.in_lo.c != a.in.c)
+      return set_error(TPGAN_ERR_INVALID, "in_lo geometry differs from in");
+    TapDesc old[kMaxTaps];
+    memcpy(old, G.taps, sizeof(old));
+    int nt3 = 0;
+    for (int ph = 0; ph < G.n_phases; ++ph) {
+      const int b0 = G.phase[ph].tap_begin, cnt = G.phase[ph].tap_count;
+      G.phase[ph].tap_begin = (short)nt3;
+      for (int v = 0; v < 3; ++v)
+        for (int t = 0; t < cnt; ++t) {
+          TapDesc d = old[b0 + t];
+          if (v == 1) d.plane = (int8_t)(d.plane + nplanes);
+          if (v == 0) d.wtap = (uint8_t)(d.wtap | 0x80);
+          G.taps[nt3++] = d;
+        }
+      G.phase[ph].tap_count = (short)(3 * cnt);
+    }
+    ntap = nt3;
+  }
   if (G.Wm > 128) return set_error(TPGAN_ERR_INVALID, "tile-space width %d > 128 unsupported", G.Wm);
   G.bw = G.Wm;
   G.bh = std::min(G.Hm, 128 / G.bw);
@@ -339,6 +366,12 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
   if (rc) return rc;
   rc = encode_weights(&G.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, taps + 1, G.block_n, CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
   if (rc) return rc;
+  if (exact3) {
+    rc = encode_planes(G.amap + nplanes, a.in_lo, gather ? s : 1, G.bw, G.bh, G.bn, CU_TENSOR_MAP_SWIZZLE_128B, 0);
+    if (rc) return rc;
+    rc = encode_weights(&G.bmap_lo, a.w_lo_packed, a.w_k_pad, a.w_rows_pad, taps + 1, G.block_n, CU_TENSOR_MAP_SWIZZLE_128B, CH, 0);
+    if (rc) return rc;
+  }
 
   G.out = to_dev(a.out);
   G.out16 = to_dev16(a.out16);
@@ -1216,12 +1249,14 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     if (groups[i].dtype != groups[0].dtype) return set_error(TPGAN_ERR_INVALID, "grouped problems must share one dtype");
   if (ngroups == 1) {
     int rrc = 0;
-    g_last_conv_kernel = 2;
-    if (try_rowstack(groups[0], st, &rrc)) return rrc;
-    g_last_conv_kernel = 1;
-    if (try_rowconv(groups[0], st, &rrc)) return rrc;
-    g_last_conv_kernel = 3;
-    if (try_flatconv(groups, 1, st, &rrc)) return rrc;
+    if (!groups[0].in_lo.ptr) {      // the three-term product is a tap-list feature of tapgemm
+      g_last_conv_kernel = 2;
+      if (try_rowstack(groups[0], st, &rrc)) return rrc;
+      g_last_conv_kernel = 1;
+      if (try_rowconv(groups[0], st, &rrc)) return rrc;
+      g_last_conv_kernel = 3;
+      if (try_flatconv(groups, 1, st, &rrc)) return rrc;
+    }
     g_last_conv_kernel = 0;
     static thread_local TapGemmParams1 P;
     P.ngroups = 1;
@@ -1268,8 +1303,10 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
   }
   {
     int rrc = 0;
+    bool any_lo = false;
+    for (int i = 0; i < ngroups; ++i) any_lo = any_lo || groups[i].in_lo.ptr != nullptr;
     g_last_conv_kernel = 3;
-    if (try_flatconv(groups, ngroups, st, &rrc)) return rrc;
+    if (!any_lo && try_flatconv(groups, ngroups, st, &rrc)) return rrc;
   }
   g_last_conv_kernel = 0;
   static thread_local TapGemmParams P;

@@ -46,6 +46,7 @@ struct PhaseDesc {
 struct TapGemmGroup {
   CUtensorMap amap[kMaxPlanes];  // 4D {C, W, H, N} fp32, box {32, bw, bh, bn}, 128B swizzle
   CUtensorMap bmap;              // 3D {k_pad, rows_pad, taps+1}, box {32, block_n, 1}
+  CUtensorMap bmap_lo;           // one-launch 3xTF32: the residual packing (taps whose wtap has bit 7 set read it)
   int Hm, Wm, Nimg;              // tile space (pixels enumerated by the M dimension)
   int bw, bh, bn;                // pixels of one 128-row tile = bw*bh*bn (<= 128)
   int tiles_h, m_tiles;          // ceil(Hm/bh), tiles_h * ceil(Nimg/bn)

@@ -126,11 +126,11 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
         const int kchunks = G.kchunks;
         const int bn0 = tc.nt * G.block_n;
         const TapDesc* taps = &G.taps[ph.tap_begin];
-        const CUtensorMap* bm = &G.bmap;
         for (int t = tc.t0; ok && t < tc.t1; ++t) {
           const TapDesc tap = taps[t];
           const CUtensorMap* am = &G.amap[tap.plane];
-          const int ax = tap.dx, ay = tc.h0 + tap.dy, wt = tap.wtap;
+          const CUtensorMap* bm = (tap.wtap & 0x80) ? &G.bmap_lo : &G.bmap;   // bit 7: the residual weight packing
+          const int ax = tap.dx, ay = tc.h0 + tap.dy, wt = tap.wtap & 0x7f;
           for (int c = tc.c0; c < tc.c1; c += kst) {
             if (!mbar_wait_a(eb, phase ^ 1u, ac, 1)) { ok = false; break; }
             const uint32_t sb = sa + a_region;

@@ -554,14 +554,36 @@ class Plan:
         pix_src = (out if L.transposed else x) if dgrad else (x if L.transposed else out)
         return 2.0 * pix_src.n * pix_src.h * pix_src.w * L.cin * L.cout * L.k * L.k
 
+    def _split(self, x: Act, lst):
+        """fp32-exact mode: tf32 high part and residual of `x`, emitted into `lst`.  The input-gradient and weight-gradient
+        launches of a layer are emitted back to back and both read the same (final) output gradient: the second request
+        for the same tensor in the same list reuses the first split instead of launching it again."""
+        key = (x.buf.data_ptr(), x.c0, x.c, tuple(x.buf.shape), id(lst))
+        recent = getattr(self, "_recent_splits", [])
+        for k, pos, xh, xl in recent:
+            if k == key and pos >= len(lst) - 4:     # emitted a launch or two ago: nothing in between writes the tensor
+                return xh, xl
+        # a layer input split for the forward launch is still valid when its weight gradient is traced: forward
+        # activations are never written again within a step (the weight gradient itself relies on that)
+        fwd_splits = self.__dict__.setdefault("_fwd_splits", {})
+        if lst is self.bwd and key[:4] in fwd_splits:
+            return fwd_splits[key[:4]]
+        xh, xl = Act.empty(x.n, x.h, x.w, x.c, self.device), Act.empty(x.n, x.h, x.w, x.c, self.device)
+        self.keep.append((xh, xl))
+        lst.append(dw_free(lambda x=x, xh=xh, xl=xl: ops.split_tf32(x, xh, xl)))
+        self._recent_splits = (recent + [(key, len(lst), xh, xl)])[-2:]
+        if lst is self.fwd:
+            fwd_splits[key[:4]] = (xh, xl)
+        return xh, xl
+
     def _emit_conv(self, specs, lst):
         """specs: dicts {L, dgrad, x, out, bias, add1, add2, mask, slopes, slope, epilogue} of one grouped launch."""
         fl = sum(self._flops(sp["L"], sp["x"], sp["out"], sp["dgrad"]) for sp in specs)
-        def mk(sp, x, out, pack, **kw):
+        def mk(sp, x, out, pack, x_lo=None, w_lo=None, **kw):
             L = sp["L"]
             return ops.conv_args(L.kind_dgrad if sp["dgrad"] else L.kind_fwd, x, out, pack, L.k, L.stride, L.pad,
                                  round_tf32=(not self.exact) and sp.get("round", True), bf16=self.bf16,
-                                 out16=sp.get("out16", True), **kw)
+                                 out16=sp.get("out16", True), x_lo=x_lo, w_lo=w_lo, **kw)
         full = lambda sp: dict(bias=sp.get("bias"), add1=sp.get("add1"), add2=sp.get("add2"), mask=sp.get("mask"),
                                slopes=sp.get("slopes"), slope=sp.get("slope", 0.0), epilogue=sp.get("epilogue", EPI_LINEAR))
         if not self.exact:
@@ -575,6 +597,23 @@ class Plan:
             if (len(specs) == 1 and not L0.transposed and L0.stride == 1 and 2 * L0.pad == L0.k - 1 and L0.k >= 3
                     and sp0["x"].w == 128 and sp0["out"].w == 128 and pk.rows_pad <= 256):
                 run.kind = "rowconv"   # the library routes these to rowconv_kernel (api.cu: try_rowconv)
+            lst.append(run)
+            return
+        # fp32-exact mode.  Kernels up to 4x4 (every MobileNetV2 layer): the three-term product a_h*w_l + a_l*w_h + a_h*w_h
+        # is ONE launch - the tap list of the launch three times over the hi / lo operand copies (tpgan_conv_args.in_lo) -
+        # after one launch that splits the activation.  Larger kernels (3 x k*k taps exceed the tap table): three chained
+        # launches through a scratch tensor, as before.
+        def fits(L):   # taps of the launch (hole phases of a stride > kernel deconv add one zero tap each), three times
+            holes = L.stride ** 2 if (L.transposed and L.stride > L.k) else 0
+            return 3 * (L.k ** 2 + holes) <= 64
+        if all(fits(sp["L"]) for sp in specs):
+            args = []
+            for sp in specs:
+                L, x, out = sp["L"], sp["x"], sp["out"]
+                hi_pack, lo_pack = (L.wd, L.wd_lo) if sp["dgrad"] else (L.wf, L.wf_lo)
+                xh, xl = self._split(x, lst)
+                args.append(mk(sp, xh, out, hi_pack, x_lo=xl, w_lo=lo_pack, **full(sp)))
+            run = self._conv_launch(args, fl, ",".join(sp["L"].name for sp in specs) + (":dgrad" if specs[0]["dgrad"] else ":fwd"))
             lst.append(run)
             return
         a1, a2, a3 = [], [], []
@@ -617,13 +656,17 @@ class Plan:
             return
         g1, g2, g3 = [], [], []
         for L, x, dy in specs:
-            e = lambda a: Act.empty(a.n, a.h, a.w, a.c, self.device)
-            xh, xl, dh, dl = e(x), e(x), e(dy), e(dy)
-            self.keep.append((xh, xl, dh, dl))
-            lst.append(lambda x=x, xh=xh, xl=xl, dy=dy, dh=dh, dl=dl: (ops.split_tf32(x, xh, xl), ops.split_tf32(dy, dh, dl)))
+            dh, dl = self._split(dy, lst)
+            xh, xl = self._split(x, lst)
             g1.append(mk(L, xh, dh))
             g2.append(mk(L, xl, dh))
             g3.append(mk(L, xh, dl))
+        if len(specs) == 1:
+            # the three products of one layer accumulate into the same dW: ONE grouped launch of three problems (fp32
+            # reds into the cleared dW; a grouped launch takes up to four independent problems)
+            lst.append(self._wgrad_launch(g1 + g2 + g3, sum(self._flops(L, x, dy, False) for L, x, dy in specs),
+                                          specs[0][0].name + ":wgrad"))
+            return
         for g in (g1, g2, g3):
             lst.append(self._wgrad_launch(g))
 

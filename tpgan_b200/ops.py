@@ -274,20 +274,23 @@ def transpose_packed(src: Packed, dst: Packed) -> None:
 def conv_args(kind: int, x: Act, out: Act, w: Packed, k: int, stride: int, pad: int, bias: Optional[torch.Tensor] = None,
               add1: Optional[Act] = None, add2: Optional[Act] = None, mask: Optional[Act] = None,
               slopes: Optional[torch.Tensor] = None, slope: float = 0.0, epilogue: int = EPI_LINEAR,
-              round_tf32: bool = True, bf16: bool = False, out16: bool = True, out32: bool = True) -> ConvArgs:
+              round_tf32: bool = True, bf16: bool = False, out16: bool = True, out32: bool = True,
+              x_lo: Optional[Act] = None, w_lo: Optional[Packed] = None) -> ConvArgs:
     """bf16=True: x is read through its bf16 twin, `w` is a bf16 packing (Packed.data of dtype bfloat16), the result is
-    written to out (fp32, unless out32=False) and to out's bf16 twin (unless out16=False)."""
+    written to out (fp32, unless out32=False) and to out's bf16 twin (unless out16=False).
+    x_lo / w_lo (tf32 only): residual parts of the operands - the launch computes the fp32-accurate three-term product."""
     if not bf16:
+        assert (x_lo is None) == (w_lo is None)
         return ConvArgs(kind, k, k, stride, pad, x.view(), out.view(), w.data.data_ptr(), w.rows_pad, w.k_pad, _ptr(bias),
                         _v(add1), _v(add2), _v(mask), _ptr(slopes), float(slope), epilogue, int(round_tf32), DTYPE_TF32,
-                        NULL_VIEW)
+                        NULL_VIEW, _v(x_lo), None if w_lo is None else w_lo.data.data_ptr())
     assert w.data.dtype == torch.bfloat16 and (out16 or out32)
     ov = out.view()
     if not out32:
         ov.ptr = None
     return ConvArgs(kind, k, k, stride, pad, x.view16(), ov, w.data.data_ptr(), w.rows_pad, w.k_pad, _ptr(bias),
                     _v(add1), _v(add2), _v(mask), _ptr(slopes), float(slope), epilogue, 0, DTYPE_BF16,
-                    out.view16() if out16 else NULL_VIEW)
+                    out.view16() if out16 else NULL_VIEW, NULL_VIEW, None)
 
 
 def conv2d_grouped(args: List[ConvArgs]) -> None:

@@ -302,7 +302,7 @@ class GraphRunner:
         pending = False
         for f in seg:
             kind = getattr(f, "kind", None)
-            if kind == "wgrad":
+            if kind in ("wgrad", "dw_wgrad"):      # dense and depthwise weight gradients
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
@@ -310,7 +310,7 @@ class GraphRunner:
                     f()
                 pending = True
                 continue
-            if pending and kind not in ("tapgemm", "rowconv", "cast16") and not getattr(f, "dw_free", False):
+            if pending and kind not in ("tapgemm", "rowconv", "cast16", "dw_dgrad", "dw_fwd") and not getattr(f, "dw_free", False):
                 ev = torch.cuda.Event()
                 ev.record(side)
                 main.wait_event(ev)
