@@ -361,6 +361,10 @@ TPGAN_API int64_t tpgan_launch_count(void);
 /* Which tensor-core kernel the calling thread's most recent tpgan_conv2d launched (profiling / bench attribution):
  * 0 = tapgemm_kernel, 1 = rowconv_kernel, 2 = rowstack_kernel. */
 TPGAN_API int tpgan_last_conv_kernel(void);
+/* 1 when that launch ran tapgemm_kernel over CTA pairs (clusters of 2 CTAs, tcgen05 cta_group::2: one M = 256 MMA per two
+ * consecutive 128-pixel tiles, each CTA staging half of the weight tile); 0 otherwise.  TPGAN_PAIR=0 in the environment turns
+ * pairing off (A/B measurements). */
+TPGAN_API int tpgan_last_conv_pair(void);
 /* Deterministic mode (process-wide; returns the previous setting).  By default the split reductions of
  * tpgan_conv2d_wgrad and the multi-block bias sums combine partial results with fp32 atomics, so two runs of the same step
  * agree only to summation order (torch.use_deterministic_algorithms is the reference-side analogue).  With on != 0 every

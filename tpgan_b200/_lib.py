@@ -125,6 +125,7 @@ SYMBOLS = {
     "tpgan_kernel_status": (C.c_int, []),
     "tpgan_launch_count": (C.c_int64, []),
     "tpgan_last_conv_kernel": (C.c_int, []),
+    "tpgan_last_conv_pair": (C.c_int, []),
     "tpgan_set_deterministic": (C.c_int, [_I32]),
     "tpgan_get_deterministic": (C.c_int, []),
     "tpgan_set_sm_reserve": (C.c_int, [_I32]),
@@ -157,6 +158,11 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(load().tpgan_launch_count())
+
+
+def last_conv_pair() -> bool:
+    """True when the calling thread's most recent conv launch ran over CTA pairs (cta_group::2)."""
+    return bool(load().tpgan_last_conv_pair())
 
 
 def last_conv_kernel() -> str:

@@ -21,7 +21,7 @@
 
 namespace tpg {
 
-template <class Params, bool BF16>
+template <class Params, bool BF16, bool PAIR>
 __global__ void tapgemm_kernel(const __grid_constant__ Params P, int* status);
 template <class Params, bool BF16>
 __global__ void wgrad_kernel(const __grid_constant__ Params P, int* status);
@@ -92,7 +92,7 @@ static inline int persistent_sms() { return std::max(1, g_dev.sm_count - g_sm_re
 // TPGAN_PDL=0 falls back to plain stream serialisation (for A/B measurements).
 std::atomic<int> g_pdl{-1};
 template <class Kern, class Params>
-static cudaError_t launch_tc(Kern kern, int grid, int smem, cudaStream_t st, const Params& P) {
+static cudaError_t launch_tc(Kern kern, int grid, int smem, cudaStream_t st, const Params& P, int cluster = 1) {
   int pdl = g_pdl.load(std::memory_order_relaxed);
   if (pdl < 0) {
     const char* ev = getenv("TPGAN_PDL");
@@ -104,11 +104,22 @@ static cudaError_t launch_tc(Kern kern, int grid, int smem, cudaStream_t st, con
   cfg.blockDim = dim3((unsigned)kConvThreads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster > 1) {   // CTA pairs (tcgen05 cta_group::2): grid is a multiple of the cluster size
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1u : 0u;
+  cfg.numAttrs = na;
   int* status = g_dev.status_dev;
   void* args[2] = {const_cast<Params*>(&P), &status};
   return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), args);
@@ -240,6 +251,16 @@ static int encode_planes(CUtensorMap* maps, const tpgan_view& t, int s, int bw, 
 }
 
 // ------------------------------------------------------------------------------------------------ conv planning
+// CTA-pair launches (tapgemm_kernel<.., PAIR = true>): set around plan_group / launch_tapgemm by tpgan_conv2d.  The plan of a
+// paired group differs in two places: the weight box is half an N tile (each CTA of the pair stages block_n / 2 rows) and the
+// tile list counts PAIRS of consecutive M tiles.
+static thread_local bool t_pair = false;
+static thread_local int g_last_conv_pair = 0;
+static int pair_mode() {   // TPGAN_PAIR: 0 = never, 1 = whenever eligible (default)
+  static const int mode = [] { const char* ev = getenv("TPGAN_PAIR"); return ev ? atoi(ev) : 1; }();
+  return mode;
+}
+
 static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1) {
   memset(&G, 0, sizeof(G));
   const int k = a.kh;
@@ -357,19 +378,20 @@ static int plan_group(const tpgan_conv_args& a, TapGemmGroup& G, int n_split = 1
   G.n_tiles = ceil_div(a.w_rows_pad, G.block_n);
   G.kchunks = ceil_div(Kc, CH);
   G.last_mmas = ceil_div(Kc - CH * (G.kchunks - 1), mma_k(bf16));
-  G.tile_count = G.n_phases * G.m_tiles * G.n_tiles;
+  G.tile_count = G.n_phases * (t_pair ? ceil_div(G.m_tiles, 2) : G.m_tiles) * G.n_tiles;
   G.ksplit = 1;
   G.kc_per = G.kchunks;
   G.kt_per = 0;
 
   int rc = encode_planes(G.amap, a.in, gather ? s : 1, G.bw, G.bh, G.bn, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
   if (rc) return rc;
-  rc = encode_weights(&G.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, taps + 1, G.block_n, CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
+  const int wbox = t_pair ? G.block_n / 2 : G.block_n;
+  rc = encode_weights(&G.bmap, a.w_packed, a.w_k_pad, a.w_rows_pad, taps + 1, wbox, CU_TENSOR_MAP_SWIZZLE_128B, CH, bf16);
   if (rc) return rc;
   if (exact3) {
     rc = encode_planes(G.amap + nplanes, a.in_lo, gather ? s : 1, G.bw, G.bh, G.bn, CU_TENSOR_MAP_SWIZZLE_128B, 0);
     if (rc) return rc;
-    rc = encode_weights(&G.bmap_lo, a.w_lo_packed, a.w_k_pad, a.w_rows_pad, taps + 1, G.block_n, CU_TENSOR_MAP_SWIZZLE_128B, CH, 0);
+    rc = encode_weights(&G.bmap_lo, a.w_lo_packed, a.w_k_pad, a.w_rows_pad, taps + 1, wbox, CU_TENSOR_MAP_SWIZZLE_128B, CH, 0);
     if (rc) return rc;
   }
 
@@ -459,7 +481,7 @@ static int launch_tapgemm(Params& P, cudaStream_t st, int bf16) {
   for (int i = 0; i < P.ngroups; ++i) {
     P.g[i].tile_begin = tiles;
     tiles += P.g[i].tile_count;
-    bmax = std::max(bmax, P.g[i].block_n * 128);
+    bmax = std::max(bmax, P.g[i].block_n * (t_pair ? 64 : 128));
   }
   P.total_tiles = tiles;
   P.b_stage_bytes = bmax;
@@ -472,12 +494,14 @@ static int launch_tapgemm(Params& P, cudaStream_t st, int bf16) {
   if (const char* ev = getenv("TPGAN_STAGES")) P.stages = std::min(P.stages, std::max(2, atoi(ev)));
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "not enough shared memory for 2 stages");
   const int smem = P.stages * stage_bytes + 1024;
-  auto kern = bf16 ? tapgemm_kernel<Params, true> : tapgemm_kernel<Params, false>;
+  auto kern = t_pair ? (bf16 ? tapgemm_kernel<Params, true, true> : tapgemm_kernel<Params, false, true>)
+                     : (bf16 ? tapgemm_kernel<Params, true, false> : tapgemm_kernel<Params, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_dev.max_smem - 256);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  int grid = std::min(tiles, persistent_sms());
-  if (const char* ev = getenv("TPGAN_GRID")) grid = std::min(grid, std::max(1, atoi(ev)));
-  e = launch_tc(kern, grid, smem, st, P);
+  int grid = t_pair ? 2 * std::min(tiles, std::max(1, persistent_sms() / 2)) : std::min(tiles, persistent_sms());
+  if (const char* ev = getenv("TPGAN_GRID")) grid = std::min(grid, std::max(t_pair ? 2 : 1, atoi(ev) & (t_pair ? ~1 : ~0)));
+  g_last_conv_pair = t_pair ? 1 : 0;
+  e = launch_tc(kern, grid, smem, st, P, t_pair ? 2 : 1);
   if (e != cudaSuccess) return set_error(TPGAN_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -1260,6 +1284,7 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
     g_last_conv_kernel = 0;
     static thread_local TapGemmParams1 P;
     P.ngroups = 1;
+    t_pair = false;
     rc = plan_group(groups[0], P.g[0]);
     if (rc) return rc;
     const int nt = choose_n_tiles(P.g[0], groups[0]);
@@ -1299,6 +1324,13 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
         }
       }
     }
+    if (pair_mode() && P.g[0].ksplit == 1 && P.g[0].m_tiles >= 2) {   // same tiling, over CTA pairs
+      t_pair = true;
+      rc = plan_group(groups[0], P.g[0], -P.g[0].n_tiles);
+      if (!rc) rc = launch_tapgemm(P, st, bf16);
+      t_pair = false;
+      return rc;
+    }
     return launch_tapgemm(P, st, bf16);
   }
   {
@@ -1311,17 +1343,21 @@ int tpgan_conv2d(const tpgan_conv_args* groups, int32_t ngroups, void* stream) {
   g_last_conv_kernel = 0;
   static thread_local TapGemmParams P;
   P.ngroups = ngroups;
+  t_pair = false;
   for (int i = 0; i < ngroups; ++i) {
     rc = plan_group(groups[i], P.g[i]);
     if (rc) return rc;
   }
   const int f = choose_n_split(P, groups);
-  if (f > 1)
-    for (int i = 0; i < ngroups; ++i) {
-      rc = plan_group(groups[i], P.g[i], f);
-      if (rc) return rc;
-    }
-  return launch_tapgemm(P, st, bf16);
+  bool pair = pair_mode() != 0;
+  for (int i = 0; i < ngroups; ++i) pair = pair && P.g[i].m_tiles >= 2;
+  if (f > 1 || pair) {
+    t_pair = pair;
+    for (int i = 0; i < ngroups && !rc; ++i) rc = plan_group(groups[i], P.g[i], f);
+  }
+  if (!rc) rc = launch_tapgemm(P, st, bf16);
+  t_pair = false;
+  return rc;
 }
 
 int tpgan_conv2d_wgrad(const tpgan_wgrad_args* groups, int32_t ngroups, void* stream) {
@@ -1384,5 +1420,6 @@ int tpgan_set_sm_reserve(int32_t sms) {
   return prev;
 }
 int tpgan_last_conv_kernel(void) { return g_last_conv_kernel; }
+int tpgan_last_conv_pair(void) { return g_last_conv_pair; }
 
 }  // extern "C"

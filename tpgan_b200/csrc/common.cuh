@@ -145,6 +145,95 @@ __device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma of M = 256: each CTA holds its 128 rows of A and of the
+// accumulator and HALF of B (N/2 rows) - the tensor cores exchange the B halves, so a CTA's shared memory receives and
+// serves half the weight bytes per MMA.  Protocol (the one CUTLASS's 2-SM kernels use):
+//   * both CTAs issue their own TMA loads, but every load signals the LEADER's (cluster rank 0) full barrier: the barrier
+//     operand of cp.async.bulk.tensor.cta_group::2 is the local barrier's address with the cluster-rank bit cleared;
+//   * the leader's elected thread issues the MMAs and commits with .multicast::cluster to the barrier at the same offset
+//     in BOTH CTAs (stage-empty and accumulator-full);
+//   * the epilogue warps of both CTAs release an accumulator by arriving on the LEADER's barrier (mapa + remote arrive).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address -> the same offset in cluster rank 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// one arrival on the barrier at this offset in both CTAs of the pair once every MMA issued so far has retired
+__device__ __forceinline__ void tc_commit2_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrival on the barrier at this offset in cluster rank `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+// wait whose acquire covers arrivals made by the peer CTA
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+static __device__ __noinline__ bool mbar_wait_cluster_a(uint32_t bar, uint32_t parity, volatile int* smem_flag, int* status, int code) {
+  if (mbar_try_wait_cluster_a(bar, parity)) return true;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster_a(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      if (*smem_flag) return false;
+      if (clock64() - t0 > (1ll << 31)) {
+        *smem_flag = 1;
+        if (status) {
+          atomicCAS(status, 0, code | (int(blockIdx.x) << 8));
+          __threadfence_system();
+        }
+        return false;
+      }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- TMA (cp.async.bulk.tensor)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -214,6 +303,25 @@ struct Opnd {
                                              uint32_t accumulate) {
     if constexpr (BF16) mma_bf16_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
     else mma_tf32_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
+  }
+  // M = 256 over a CTA pair (issued by the leader CTA only)
+  static __device__ __forceinline__ void mma2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    if constexpr (BF16) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+          : "memory");
+    }
   }
   // instruction descriptor: fp32 accumulate (c_format 1), a/b format 2 = TF32 or 1 = BF16, major bits, N >> 3, M >> 4
   static __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn_major, int b_mn_major) {

@@ -13,6 +13,11 @@
 //
 // Serves: Conv2d fwd + dgrad, ConvTranspose2d fwd + dgrad (ModificationLayer.py:101,189 of the reference), and the
 // Linear layers (as 1x1 problems).  Up to four independent problems share one launch (grouped local pathways).
+//
+// PAIR = true: the same kernel over CTA pairs (clusters of 2, tcgen05 cta_group::2, common.cuh).  A pair works on two
+// consecutive M tiles of one (phase, N tile): every MMA is M = 256 x N = block_n, each CTA stages its own 128 activation
+// rows and HALF of the weight tile (block_n / 2 rows), so per MMA a CTA's shared memory takes in and serves half the weight
+// bytes - the shared-memory port is what bounds this kernel for N <= 208.
 #include "common.cuh"
 #include "kparams.h"
 
@@ -31,8 +36,8 @@ struct TileCoord {
   int ks, base;         // split-K: range index, un-split tile index inside the group
 };
 
-template <class Params>
-__device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
+template <class Params, bool PAIR = false>
+__device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile, int rank = 0) {
   TileCoord tc;
   int gi = 0;
   constexpr int kG = (int)(sizeof(P.g) / sizeof(P.g[0]));
@@ -48,8 +53,15 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
   tc.base = local;
   tc.nt = local % G.n_tiles;
   int rest = local / G.n_tiles;
-  int mt = rest % G.m_tiles;
-  tc.ph = rest / G.m_tiles;
+  int mt;
+  if constexpr (PAIR) {   // `tile` counts pairs of M tiles (split-K launches are never paired); an odd count leaves the
+    const int m_pairs = (G.m_tiles + 1) >> 1;   // last pair's second CTA a tile past the end (loads zero-fill, no stores)
+    mt = 2 * (rest % m_pairs) + rank;
+    tc.ph = rest / m_pairs;
+  } else {
+    mt = rest % G.m_tiles;
+    tc.ph = rest / G.m_tiles;
+  }
   int hb = mt % G.tiles_h;
   int nb = mt / G.tiles_h;
   tc.h0 = hb * G.bh;
@@ -63,9 +75,13 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int tile) {
   return tc;
 }
 
-template <class Params, bool BF16>
+template <class Params, bool BF16, bool PAIR>
 __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __grid_constant__ Params P, int* status) {
   using Op = Opnd<BF16>;
+  // PAIR: cluster rank (0 = leader: issues the MMAs, owns the full / accumulator-empty barriers), pair index, pair count
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int CH = Op::kChunk;   // channels per 128-byte K chunk
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -89,17 +105,24 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kTapGemmThreads - 128);
+      // pairs: one arrival per epilogue warp of BOTH CTAs, on the leader's barrier
+      mbar_init(&tempty_bar[i], PAIR ? 2 * (kTapGemmThreads - 128) / 32 : kTapGemmThreads - 128);
     }
     abort_flag = 0;
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_base_s, kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc2(&tmem_base_s, kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&tmem_base_s, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   pdl_wait();   // everything above touched only shared / tensor memory; global memory from here on
   const uint32_t tmem_base = tmem_base_s;
@@ -118,13 +141,15 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
       uint32_t phase = 0;
       uint32_t sa = smem_base, fb = full0, eb = empty0;
       bool ok = true;
-      for (int tile = blockIdx.x; ok && tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
+      for (int tile = tile0; ok && tile < P.total_tiles; tile += tstep) {
+        const TileCoord tc = decode_tile<Params, PAIR>(P, tile, rank);
         const TapGemmGroup& G = P.g[tc.gi];
-        const uint32_t chunk_tx = (uint32_t)(G.bw * G.bh * G.bn + G.block_n) * 128u;
+        // pairs: the leader's barrier expects the bytes of both CTAs (2 x (A box + half a weight box))
+        const uint32_t chunk_tx = PAIR ? (uint32_t)(2 * G.bw * G.bh * G.bn + G.block_n) * 128u
+                                       : (uint32_t)(G.bw * G.bh * G.bn + G.block_n) * 128u;
         const PhaseDesc ph = G.phase[tc.ph];
         const int kchunks = G.kchunks;
-        const int bn0 = tc.nt * G.block_n;
+        const int bn0 = tc.nt * G.block_n + (PAIR ? rank * (G.block_n >> 1) : 0);
         const TapDesc* taps = &G.taps[ph.tap_begin];
         for (int t = tc.t0; ok && t < tc.t1; ++t) {
           const TapDesc tap = taps[t];
@@ -135,21 +160,39 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
             if (!mbar_wait_a(eb, phase ^ 1u, ac, 1)) { ok = false; break; }
             const uint32_t sb = sa + a_region;
             const bool two = (kst > 1) && (c + 1 < tc.c1);
-            mbar_arrive_expect_tx_a(fb, two ? 2u * chunk_tx : chunk_tx);
-            tma_load_4d_a(sa, am, fb, c * CH, ax, ay, tc.n0);
-            tma_load_3d_a(sb, bm, fb, c * CH, bn0, wt);
-            if (two) {
-              tma_load_4d_a(sa + kAStageBytes, am, fb, c * CH + CH, ax, ay, tc.n0);
-              tma_load_3d_a(sb + b_chunk, bm, fb, c * CH + CH, bn0, wt);
+            if constexpr (PAIR) {
+              if (rank == 0) mbar_arrive_expect_tx_a(fb, two ? 2u * chunk_tx : chunk_tx);
+              tma_load_4d_pair(sa, am, fb, c * CH, ax, ay, tc.n0);
+              tma_load_3d_pair(sb, bm, fb, c * CH, bn0, wt);
+              if (two) {
+                tma_load_4d_pair(sa + kAStageBytes, am, fb, c * CH + CH, ax, ay, tc.n0);
+                tma_load_3d_pair(sb + b_chunk, bm, fb, c * CH + CH, bn0, wt);
+              }
+            } else {
+              mbar_arrive_expect_tx_a(fb, two ? 2u * chunk_tx : chunk_tx);
+              tma_load_4d_a(sa, am, fb, c * CH, ax, ay, tc.n0);
+              tma_load_3d_a(sb, bm, fb, c * CH, bn0, wt);
+              if (two) {
+                tma_load_4d_a(sa + kAStageBytes, am, fb, c * CH + CH, ax, ay, tc.n0);
+                tma_load_3d_a(sb + b_chunk, bm, fb, c * CH + CH, bn0, wt);
+              }
             }
             sa += stage_bytes; fb += 8; eb += 8;
             if (++stage == S) { stage = 0; phase ^= 1u; sa = smem_base; fb = full0; eb = empty0; }
           }
         }
       }
+      if constexpr (PAIR) {
+        // tail: every multicast stage-release of the leader has landed on this CTA's barriers before it may exit
+        for (int i = 0; ok && i < S; ++i) {
+          if (!mbar_wait_a(eb, phase ^ 1u, ac, 1)) break;
+          eb += 8;
+          if (++stage == S) { stage = 0; phase ^= 1u; eb = empty0; }
+        }
+      }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one elected lane)
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane; pairs: the leader's)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -160,12 +203,20 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
       const uint32_t a_lo0 = desc_lo(smem_base, 16);
       const uint32_t stage16 = stage_bytes >> 4, areg16 = a_region >> 4, b16 = b_chunk >> 4;
       uint32_t a_lo = a_lo0, fb = full0, eb = empty0;
-      for (int tile = blockIdx.x; ok && tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc_) {
+        if constexpr (PAIR) Op::mma2(d, a, b, id, acc_);
+        else Op::mma(d, a, b, id, acc_);
+      };
+      for (int tile = tile0; ok && tile < P.total_tiles; tile += tstep) {
+        const TileCoord tc = decode_tile<Params, PAIR>(P, tile, 0);
         const TapGemmGroup& G = P.g[tc.gi];
-        if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 2)) break;
+        if constexpr (PAIR) {
+          if (!mbar_wait_cluster_a(smem_u32(&tempty_bar[as]), aphase ^ 1u, ac.smem_flag, ac.status, 2)) break;
+        } else {
+          if (!mbar_wait(&tempty_bar[as], aphase ^ 1u, ac, 2)) break;
+        }
         tc_fence_after();
-        const uint32_t idesc = Op::idesc(128, G.block_n, 0, 0);
+        const uint32_t idesc = Op::idesc(PAIR ? 256 : 128, G.block_n, 0, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccCols);
         const int ntap = G.phase[tc.ph].tap_count;
         const int kchunks = G.kchunks;
@@ -180,16 +231,16 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
             const int nch = min(kst, c1 - c);
             const int n_mma = (nch - 1) * 4 + ((c + nch == kchunks) ? G.last_mmas : 4);
             if (n_mma == 4 * kst) {  // a full stage: kst * 4 MMAs
-              Op::mma(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
-              Op::mma(d_tmem, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
-              Op::mma(d_tmem, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
-              Op::mma(d_tmem, desc_join(a_lo + 6, dhi), desc_join(b_lo + 6, dhi), idesc, 1);
+              mma(d_tmem, desc_join(a_lo, dhi), desc_join(b_lo, dhi), idesc, acc);
+              mma(d_tmem, desc_join(a_lo + 2, dhi), desc_join(b_lo + 2, dhi), idesc, 1);
+              mma(d_tmem, desc_join(a_lo + 4, dhi), desc_join(b_lo + 4, dhi), idesc, 1);
+              mma(d_tmem, desc_join(a_lo + 6, dhi), desc_join(b_lo + 6, dhi), idesc, 1);
               if (kst > 1) {
                 const uint32_t a2 = a_lo + (kAStageBytes >> 4), b2 = b_lo + b16;
-                Op::mma(d_tmem, desc_join(a2, dhi), desc_join(b2, dhi), idesc, 1);
-                Op::mma(d_tmem, desc_join(a2 + 2, dhi), desc_join(b2 + 2, dhi), idesc, 1);
-                Op::mma(d_tmem, desc_join(a2 + 4, dhi), desc_join(b2 + 4, dhi), idesc, 1);
-                Op::mma(d_tmem, desc_join(a2 + 6, dhi), desc_join(b2 + 6, dhi), idesc, 1);
+                mma(d_tmem, desc_join(a2, dhi), desc_join(b2, dhi), idesc, 1);
+                mma(d_tmem, desc_join(a2 + 2, dhi), desc_join(b2 + 2, dhi), idesc, 1);
+                mma(d_tmem, desc_join(a2 + 4, dhi), desc_join(b2 + 4, dhi), idesc, 1);
+                mma(d_tmem, desc_join(a2 + 6, dhi), desc_join(b2 + 6, dhi), idesc, 1);
               }
             } else {
 #pragma unroll
@@ -198,18 +249,20 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
                   const uint32_t off = (uint32_t)(m & 3) * 2u;
                   const uint32_t aj = a_lo + off + ((m >> 2) ? (kAStageBytes >> 4) : 0u);
                   const uint32_t bj = b_lo + off + ((m >> 2) ? b16 : 0u);
-                  Op::mma(d_tmem, desc_join(aj, dhi), desc_join(bj, dhi), idesc, m ? 1u : acc);
+                  mma(d_tmem, desc_join(aj, dhi), desc_join(bj, dhi), idesc, m ? 1u : acc);
                 }
               }
             }
             acc = 1;
-            tc_commit_a(eb);
+            if constexpr (PAIR) tc_commit2_a(eb);
+            else tc_commit_a(eb);
             a_lo += stage16; fb += 8; eb += 8;
             if (++stage == S) { stage = 0; phase ^= 1u; a_lo = a_lo0; fb = full0; eb = empty0; }
           }
         }
         if (!ok) break;
-        tc_commit(&tfull_bar[as]);
+        if constexpr (PAIR) tc_commit2_a(smem_u32(&tfull_bar[as]));
+        else tc_commit(&tfull_bar[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -220,8 +273,8 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
     const int row = q * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      TileCoord tc = decode_tile(P, tile);
+    for (int tile = tile0; tile < P.total_tiles; tile += tstep) {
+      TileCoord tc = decode_tile<Params, PAIR>(P, tile, rank);
       const TapGemmGroup& G = P.g[tc.gi];
       if (!mbar_wait(&tfull_bar[as], aphase, ac, 4)) break;
       tc_fence_after();
@@ -243,7 +296,7 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
       const uint32_t t_addr = tmem_base + (uint32_t)(as * kAccCols) + ((uint32_t)(q * 32) << 16);
       const int col_base = tc.nt * G.block_n;
       const EpiArgs E{G.bias, G.slopes, G.cout_valid, G.epilogue, G.round_tf32, G.vec_ok, G.slope};
-      if (G.ksplit > 1) {
+      if (!PAIR && G.ksplit > 1) {
         // ---- split-K: park the partial accumulator, then the last of the tile's ksplit CTAs finishes the tile
         float* ws = G.split_ws + ((size_t)(tc.base * G.ksplit + tc.ks) * 128 + row) * G.block_n;
         for (int c0 = ((warp - 4) >> 2) * 16; c0 < G.block_n; c0 += 16 * kEpiPerQuarter) {
@@ -298,7 +351,12 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
         if (valid) epilogue_store16(r, E, col_base + c0, po, p1, p2, pm, po16);
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if constexpr (PAIR) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(smem_u32(&tempty_bar[as]), 0);
+      } else {
+        mbar_arrive(&tempty_bar[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -306,14 +364,22 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // neither CTA leaves (or frees tensor memory) while the other may still signal it
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // explicit instantiations used by api.cu
-template __global__ void tapgemm_kernel<TapGemmParams, false>(const __grid_constant__ TapGemmParams, int*);
-template __global__ void tapgemm_kernel<TapGemmParams1, false>(const __grid_constant__ TapGemmParams1, int*);
-template __global__ void tapgemm_kernel<TapGemmParams, true>(const __grid_constant__ TapGemmParams, int*);
-template __global__ void tapgemm_kernel<TapGemmParams1, true>(const __grid_constant__ TapGemmParams1, int*);
+template __global__ void tapgemm_kernel<TapGemmParams, false, false>(const __grid_constant__ TapGemmParams, int*);
+template __global__ void tapgemm_kernel<TapGemmParams1, false, false>(const __grid_constant__ TapGemmParams1, int*);
+template __global__ void tapgemm_kernel<TapGemmParams, true, false>(const __grid_constant__ TapGemmParams, int*);
+template __global__ void tapgemm_kernel<TapGemmParams1, true, false>(const __grid_constant__ TapGemmParams1, int*);
+template __global__ void tapgemm_kernel<TapGemmParams, false, true>(const __grid_constant__ TapGemmParams, int*);
+template __global__ void tapgemm_kernel<TapGemmParams1, false, true>(const __grid_constant__ TapGemmParams1, int*);
+template __global__ void tapgemm_kernel<TapGemmParams, true, true>(const __grid_constant__ TapGemmParams, int*);
+template __global__ void tapgemm_kernel<TapGemmParams1, true, true>(const __grid_constant__ TapGemmParams1, int*);
 
 }  // namespace tpg
