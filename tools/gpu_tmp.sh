@@ -1,14 +1,24 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r4b_pytest_all.log 2>&1; echo "pytest all rc=$?"; tail -3 gpurun_out/r4b_pytest_all.log
-for pm in 0 1; do
-TPGAN_PAIR=$pm timeout 600 python bench.py --no-cpu --no-secondary --dtype bf16 > gpurun_out/r4b_bf16_pair$pm.json 2> gpurun_out/r4b_bf16_pair$pm.err; echo "bench bf16 pair=$pm rc=$?"
-TPGAN_PAIR=$pm timeout 600 python bench.py --no-cpu --workload pretrain > gpurun_out/r4b_pretrain_pair$pm.json 2> gpurun_out/r4b_pretrain_pair$pm.err; echo "bench pretrain pair=$pm rc=$?"
-done
-python - <<PY
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r4b_*_pair*.json')):
-    for l in open(f):
-        if l.startswith('{'):
-            d=json.loads(l); print(f, round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), d['gpu_launches'])
-PY
+run() {  # label, env...
+  label=$1; shift
+  echo "=== $label"
+  for sh in enh64 enh32 enh16 add64 conv1_64 up128 up32 conv4rb; do env "$@" python tools/bench_conv.py --only $sh --kinds fwd,dgrad | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print('  %-22s %-5s %.4f ms %6.1f TF' % (d['shape'], d['kind'], d['ms'], d['tflops']))"; done
+  env TPGAN_FLATCONV=0 "$@" python tools/bench_local.py --cin 128 --cout 128 --div 2 --kinds fwd | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print('  local128 fwd %.4f ms graph %.4f' % (d['ms'], d['graph_ms']))"
+  env "$@" python bench.py --no-cpu --no-secondary 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('  bench', round(d['value'],1), round(d['ms_per_step'],3), d['clocks']['sm_mhz'])"
+}
+run default X=1
+run kst1 TPGAN_KST=1
+run kst1_s12 TPGAN_KST=1 TPGAN_TAP_MAXSTAGES=12
+run kst2_s12 TPGAN_TAP_MAXSTAGES=12
+run default_again X=1

@@ -461,14 +461,18 @@ static int choose_n_tiles(const TapGemmGroup& G, const tpgan_conv_args& a) {
   const double ksteps = (double)taps / G.n_phases * G.kchunks * 4;
   double best_cost = 0;
   int best = 0;
+  // CTA pairs (TPGAN_PAIR_MODEL=1): the schedulable unit is a pair of M tiles on a pair of SMs, and a CTA stages half the
+  // weight bytes per K step
+  static const bool pair_model = getenv("TPGAN_PAIR_MODEL") != nullptr && atoi(getenv("TPGAN_PAIR_MODEL")) != 0;
+  const bool pm = pair_model && pair_mode() && G.m_tiles >= 2;
   for (int nt = base; nt <= base * 8; ++nt) {
     const int bn = ceil_div(ceil_div(a.w_rows_pad, nt), 16) * 16;
     if (nt > base && bn < 32) break;
     if (ceil_div(a.w_rows_pad, bn) != nt) continue;   // this count collapses to a smaller one after rounding to 16 columns
-    const double per_kstep = std::max(bn / 2.0, (4096.0 + 32.0 * bn) / 72.0);
+    const double per_kstep = std::max(bn / 2.0, (4096.0 + (pm ? 16.0 : 32.0) * bn) / 72.0);
     const double per_tile = ksteps * per_kstep + 4000.0;
-    const double tiles = (double)G.n_phases * G.m_tiles * nt;
-    const double cost = std::ceil(tiles / persistent_sms()) * per_tile;
+    const double tiles = (double)G.n_phases * (pm ? ceil_div(G.m_tiles, 2) : G.m_tiles) * nt;
+    const double cost = std::ceil(tiles / (pm ? std::max(1, persistent_sms() / 2) : persistent_sms())) * per_tile;
     if (best == 0 || cost < best_cost * 0.95) { best_cost = cost; best = nt; }
   }
   return best == base ? 0 : best;
@@ -488,9 +492,18 @@ static int launch_tapgemm(Params& P, cudaStream_t st, int bf16) {
   const int budget = g_dev.max_smem - 1024 - 256;
   // two 32-float K chunks per stage when at least 3 such stages fit (halves the per-stage barrier/issue overhead)
   P.kst = (budget / (2 * (16384 + bmax)) >= 3) ? 2 : 1;
+  if (t_pair && P.kst == 2 && budget / (2 * (16384 + bmax)) == 3) {
+    // Paired launches of the wide layers: three two-chunk stages whose last stage per tap is half empty (odd chunk count -
+    // 208 channels = 6.5 chunks) leave too little in flight; seven single-chunk stages measure 11 % faster there
+    // (208->208 k3 @64x64: 583 -> 651 TFLOP/s), while an even chunk count (512 channels) is faster with the big stages.
+    bool odd = false;
+    for (int i = 0; i < P.ngroups; ++i) odd = odd || (P.g[i].kchunks & 1);
+    if (odd) P.kst = 1;
+  }
   if (const char* ev = getenv("TPGAN_KST")) P.kst = std::max(1, std::min(2, atoi(ev)));
   const int stage_bytes = P.kst * (16384 + bmax);
-  P.stages = std::min(kMaxStages, budget / stage_bytes);
+  static const int max_stages = [] { const char* ev = getenv("TPGAN_TAP_MAXSTAGES"); return ev ? std::max(2, std::min(kTapMaxStages, atoi(ev))) : kMaxStages; }();
+  P.stages = std::min(max_stages, budget / stage_bytes);
   if (const char* ev = getenv("TPGAN_STAGES")) P.stages = std::min(P.stages, std::max(2, atoi(ev)));
   if (P.stages < 2) return set_error(TPGAN_ERR_INVALID, "not enough shared memory for 2 stages");
   const int smem = P.stages * stage_bytes + 1024;
@@ -1228,7 +1241,8 @@ static int launch_wgrad(Params& P, cudaStream_t st, int bf16) {
   for (int i = 0; i < P.ngroups; ++i) slack = std::max(slack, MCH * P.g[i].mpu * P.g[i].kp * 128 - stage_bytes);
   slack = std::max(0, slack);
   const int budget = g_dev.max_smem - 1024 - 256 - slack;
-  P.stages = std::min(kMaxStages, budget / stage_bytes);
+  static const int max_stages = [] { const char* ev = getenv("TPGAN_TAP_MAXSTAGES"); return ev ? std::max(2, std::min(kTapMaxStages, atoi(ev))) : kMaxStages; }();
+  P.stages = std::min(max_stages, budget / stage_bytes);
   P.ring_bytes = P.stages * stage_bytes + slack;
   P.need_zero = 0;
   for (int i = 0; i < P.ngroups; ++i)

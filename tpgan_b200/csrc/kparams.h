@@ -12,6 +12,7 @@ constexpr int kMaxPhases = 16;  // stride-4 deconv: 4x4 output phases
 constexpr int kMaxPlanes = 16;  // stride-4 gather: 4x4 input parity planes
 constexpr int kMaxGroups = 4;   // the four local pathways
 constexpr int kMaxStages = 8;
+constexpr int kTapMaxStages = 12;  // tapgemm: single-chunk stages of a paired launch are 20-30 KB
 // Epilogue warps per TMEM lane quarter in the three tensor-core kernels (warps 4 .. 4 + 4*kEpiPerQuarter - 1); the warps
 // of a quarter take the 16-column groups of an accumulator round-robin.  The epilogue is latency-bound on its global
 // loads/stores, so more warps = more of them in flight.

@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(kTapGemmThreads, 1) tapgemm_kernel(const __gri
   const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int CH = Op::kChunk;   // channels per 128-byte K chunk
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t full_bar[kTapMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kTapMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
