@@ -57,6 +57,11 @@ CONV_CASES = [
     (1, 64, 64, 4, 200, 3, 1, 1),
     (2, 40, 24, 6, 36, 4, 1, 2),
     (2, 160, 32, 5, 64, 5, 1, 2),
+    # CTA-pair launches (tapgemm over clusters of 2) with an ODD number of 128-pixel tiles: the last pair's second CTA runs a
+    # tile past the end (zero-filled loads, no stores)
+    (5, 64, 64, 8, 8, 3, 1, 1),
+    (3, 32, 48, 24, 24, 3, 1, 1),
+    (3, 96, 208, 24, 24, 3, 2, 1),
 ]
 
 # every distinct dense-conv shape of MobileNetV2-SSD at 128x128 (Pretrain path, MobileNetV2.py:28-44,103-171): the stem,
@@ -98,6 +103,27 @@ def test_conv_fwd(case):
     assert _lib.kernel_status() == 0
     err = rel(out.to_nchw(), ref)
     assert err < TOL, err
+
+
+def test_conv_runs_over_cta_pairs():
+    """Launches with two or more 128-pixel tiles run tapgemm over CTA pairs (cta_group::2) unless TPGAN_PAIR=0; a single-tile
+    launch and the split-K Linear layers stay on single CTAs.  Results are the same arithmetic either way (test_conv_fwd)."""
+    import os
+    from tpgan_b200 import _lib, ops
+    def run(n, cin, cout, h, k, p):
+        x = _mk(n, cin, h, h, 1)
+        wt = _mk(cout, cin, k, k, 2) * (1.0 / (cin * k * k) ** 0.5)
+        ref = F.conv2d(x, wt, None, padding=p)
+        out = ops.Act.empty(n, ref.shape[2], ref.shape[3], cout)
+        ops.conv2d(ops.CONV_FWD, _act(x, ops), out, ops.pack_weights(wt.cuda(), ops.CONV_FWD, round_tf32=True), k, 1, p,
+                   round_tf32=True)
+        torch.cuda.synchronize()
+        assert _lib.kernel_status() == 0
+        assert rel(out.to_nchw(), ref) < TOL
+        return _lib.last_conv_kernel(), _lib.last_conv_pair()
+    want = os.environ.get("TPGAN_PAIR", "1") != "0"
+    assert run(5, 64, 64, 8, 3, 1) == ("tapgemm", want)        # 3 tiles: one full pair + one half-empty pair
+    assert run(2, 64, 64, 8, 3, 1) == ("tapgemm", False)       # one tile
 
 
 @pytest.mark.parametrize("case", FWD_CASES)
