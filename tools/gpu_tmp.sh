@@ -1,24 +1,16 @@
 #!/bin/bash
 mkdir -p gpurun_out
-run() {  # label, env...
-  label=$1; shift
-  echo "=== $label"
-  for sh in enh64 enh32 enh16 add64 conv1_64 up128 up32 conv4rb; do env "$@" python tools/bench_conv.py --only $sh --kinds fwd,dgrad | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print('  %-22s %-5s %.4f ms %6.1f TF' % (d['shape'], d['kind'], d['ms'], d['tflops']))"; done
-  env TPGAN_FLATCONV=0 "$@" python tools/bench_local.py --cin 128 --cout 128 --div 2 --kinds fwd | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print('  local128 fwd %.4f ms graph %.4f' % (d['ms'], d['graph_ms']))"
-  env "$@" python bench.py --no-cpu --no-secondary 2>/dev/null | python -c "
-import sys,json
-for l in sys.stdin:
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r4e_pytest_all.log 2>&1; echo "pytest all rc=$?"; tail -3 gpurun_out/r4e_pytest_all.log
+for i in 1 2; do
+timeout 600 python bench.py --no-cpu --no-secondary > gpurun_out/r4e_bench$i.json 2> gpurun_out/r4e_bench$i.err; echo "bench rc=$?"
+python - <<PY
+import json
+for l in open('gpurun_out/r4e_bench$i.json'):
     if l.startswith('{'):
-        d=json.loads(l); print('  bench', round(d['value'],1), round(d['ms_per_step'],3), d['clocks']['sm_mhz'])"
-}
-run default X=1
-run kst1 TPGAN_KST=1
-run kst1_s12 TPGAN_KST=1 TPGAN_TAP_MAXSTAGES=12
-run kst2_s12 TPGAN_TAP_MAXSTAGES=12
-run default_again X=1
+        d=json.loads(l); print(round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), d['gpu_launches'], d['clocks'])
+PY
+done
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed
+ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/r4e_launches_tf32.csv \
+      python bench.py --steps 1 --warmup 3 --no-graphs --no-cpu --no-secondary --profile-step > gpurun_out/r4e_ncu.log 2>&1
+python tools/ncu_summary.py gpurun_out/r4e_launches_tf32.csv tf32_b32 | head -14
