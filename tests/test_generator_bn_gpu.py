@@ -76,9 +76,83 @@ def test_generator_with_batchnorm_vs_live_reference_goldens(exact):
         M.EXACT_MODE = None
 
 
-def test_fused_trainer_rejects_batchnorm_models():
+def test_fused_trainer_rejects_batchnorm_critic():
     import tpgan_b200.D_and_G_model as M
     from tpgan_b200.train_step import TPGANTrainer
-    G, D = M.Generator(64, 347, True, False).cuda(), M.Discriminator(False).cuda()
+    G, D = M.Generator(64, 347, False, False).cuda(), M.Discriminator(True).cuda()
     with pytest.raises(NotImplementedError, match="module API"):
         TPGANTrainer(G, D, 1)
+
+
+STEP_GOLD = os.path.join(os.path.dirname(__file__), "golden", "step_bn_golden.pt")
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_step_with_batchnorm_generator_vs_live_reference_goldens(exact):
+    """TPGANTrainer over Generator(use_batchnorm=True) + the config's BatchNorm-free Discriminator: one fused step at fixed
+    weights against the oracle step run on the LIVE reference modules (tools/make_golden_bn_step.py): the 11 loss scalars,
+    every BatchNorm affine gradient, per-parameter gradient norms of both networks, the running statistics after the step's
+    single generator forward.  Exact (3xTF32) mode pins it; tf32 is sanity-bounded (training-mode BatchNorm over a batch of
+    2 amplifies the operand rounding, see the module docstring)."""
+    import tpgan_b200.D_and_G_model as M
+    from oracle import step as ostep
+    from tpgan_b200 import _lib
+    from tpgan_b200.train_step import TPGANTrainer
+    gold = torch.load(STEP_GOLD, weights_only=False)
+    torch.manual_seed(0)
+    G = M.Generator(64, 347, True, False)
+    D = M.Discriminator(False)
+    G.cuda()
+    D.cuda()
+    B = 2
+    b = ostep.make_batch(B, seed=3)
+    tr = TPGANTrainer(G, D, B, exact=exact)
+    m = tr.step({k: v.cuda() for k, v in b.items()}, optimize=False)
+    torch.cuda.synchronize()
+    assert _lib.kernel_status() == 0
+    tol_m = 2e-3 if exact else 0.2
+    for k, v in gold["metrics"].items():
+        assert abs(m[k] - v) <= tol_m * abs(v) + 1e-4, (k, m[k], v)
+    if not exact:
+        return
+    tr.sync_buffers()
+    sd = G.state_dict()
+    for k, v in gold["running"].items():
+        assert rel(sd[k], v) < 1e-3, k
+    assert int(sd["global_pathway.conv0.0.1.num_batches_tracked"]) == gold["num_batches_tracked"] == 1
+    for net, stats in ((G, gold["g_grad_stats"]), (D, gold["d_grad_stats"])):
+        num = den = 0.0
+        for k, p in net.named_parameters():
+            n_ref, _ = stats[k]
+            assert p.grad is not None, k
+            num += (float(p.grad.norm()) - n_ref) ** 2
+            den += n_ref ** 2
+        assert math.sqrt(num / den) < 5e-2, math.sqrt(num / den)
+    pg = dict(G.named_parameters())
+    num = den = 0.0
+    for k, g in gold["bn_grads"].items():
+        num += float((pg[k].grad.double().cpu() - g.double()).pow(2).sum())
+        den += float(g.double().pow(2).sum())
+    assert math.sqrt(num / den) < 5e-2, math.sqrt(num / den)
+
+
+def test_fused_step_with_batchnorm_generator_trains_and_replays_as_graph():
+    """Three optimizer steps of the BatchNorm generator through CUDA graphs: finite losses, parameters and running statistics
+    move, the affine parameters of a BatchNorm layer receive Adam updates, num_batches_tracked follows the step count."""
+    import tpgan_b200.D_and_G_model as M
+    from oracle import step as ostep
+    from tpgan_b200.train_step import TPGANTrainer
+    torch.manual_seed(0)
+    G, D = M.Generator(64, 347, True, False).cuda(), M.Discriminator(False).cuda()
+    B = 2
+    tr = TPGANTrainer(G, D, B, use_graphs=True)
+    bn = G.global_pathway.conv0[0][1]
+    w0, rm0 = bn.weight.detach().clone(), bn.running_mean.clone()
+    for i in range(3):
+        b = {k: v.cuda() for k, v in ostep.make_batch(B, seed=20 + i).items()}
+        m = tr.step(b)
+        assert all(math.isfinite(v) for v in m.values()), m
+    tr.sync_buffers()
+    assert int(bn.num_batches_tracked) == 3
+    assert not torch.equal(bn.weight.detach(), w0) and not torch.equal(bn.running_mean, rm0)
+    assert torch.isfinite(tr.flat_g.data).all()

@@ -1,6 +1,6 @@
 """Developer tool: trace the TP-GAN trainer (tf32 or bf16) on the CPU with a stub library (every C-ABI call returns 0,
 nothing is computed) to catch host-side tracing bugs without a GPU.  Not part of the product or the tests.
-usage: python tools/dry_trace_gan.py [batch] [tf32|bf16] [identity]"""
+usage: python tools/dry_trace_gan.py [batch] [tf32|bf16] [identity] [bn] [exact]"""
 import os
 import sys
 
@@ -35,14 +35,14 @@ from tpgan_b200.train_step import TPGANTrainer
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dtype = sys.argv[2] if len(sys.argv) > 2 else "tf32"
 torch.manual_seed(0)
-G = M.Generator(config.G["zdim"], config.G["num_classes"], config.G["use_batchnorm"], config.G["use_residual_block"])
+G = M.Generator(config.G["zdim"], config.G["num_classes"], ("bn" in sys.argv) or config.G["use_batchnorm"], config.G["use_residual_block"])
 D = M.Discriminator(config.D["use_batchnorm"])
 ident = None
 if "identity" in sys.argv:
     from tpgan_b200.FeatureExtract import FeatureExtractModel
     from tpgan_b200.ResNet import BasicBlock
     ident = FeatureExtractModel("resnet", config.G["num_classes"], residualBlock=BasicBlock, feature_layer_dim_before_FC=256).eval()
-tr = TPGANTrainer(G, D, B, device="cpu", use_dropout=True, dtype=dtype, identity_net=ident)
+tr = TPGANTrainer(G, D, B, device="cpu", use_dropout=True, dtype=dtype, identity_net=ident, exact="exact" in sys.argv)
 print("plan: fwd", len(tr.plan.fwd), "bwd", len(tr.plan.bwd), "layers", len(tr.plan.layers), "arena MB", tr.arena.total / 2**20)
 b = dict(img=torch.rand(B, 3, 128, 128), img_frontal=torch.rand(B, 3, 128, 128), img64_frontal=torch.rand(B, 3, 64, 64),
          img32_frontal=torch.rand(B, 3, 32, 32), landmarks=torch.rand(B, 5, 2) * 100, z=torch.rand(B, 64),

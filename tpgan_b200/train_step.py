@@ -628,9 +628,21 @@ class TPGANTrainer:
         self.overlap_allreduce, self.graph_collectives, self.force_reducer = overlap_allreduce, graph_collectives, force_reducer
         assert not (self.bf16 and exact), "exact is the tf32 verification mode"
         self.G, self.D, self.B, self.device = G, D, B, torch.device(device)
-        if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for net in (G, D) for m in net.modules()):
-            raise NotImplementedError("the fused G/D step is built for the config.py defaults (use_batchnorm False, config.py:63,"
-                                      "68); BatchNorm models train through the module API (forward / backward / optimizer)")
+        has_bn = lambda net: any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in net.modules())
+        if has_bn(D):
+            raise NotImplementedError("the fused step is built for a BatchNorm-free critic (config.py:68; the gradient penalty's "
+                                      "double backward through batch statistics is not built); a Discriminator(use_batchnorm="
+                                      "True) trains through the module API (forward / backward / optimizer)")
+        # Generator(use_batchnorm=True) - the reference constructor's default (D_and_G_model.py:351; config.py:63 turns it
+        # off): conv / deconv (no bias) -> batch-statistics BatchNorm2d -> (Leaky)ReLU in every factory stack.  The BatchNorm
+        # kernels write their affine gradients straight into the flat gradient buffer and update the running statistics in
+        # place; one generator forward per step = one statistics update per step, as in the oracle step.
+        self.g_bn = has_bn(G)
+        if self.g_bn:
+            assert not self.bf16, "BatchNorm generators run in tf32 (or the exact verification mode)"
+            G.train()
+            self.overlap_allreduce = self.force_reducer = False   # one all-reduce after backward (no bucket order for BatchNorm)
+        self.steps = 0
         self.use_dropout, self.exact = use_dropout, exact
         # "float": TrainDataset tensors (img, img_frontal, img64_frontal, img32_frontal as NCHW fp32 in [-1,1]);
         # "uint8": raw HWC bytes img_u8 / img_frontal_u8 (B,128,128,3) - ToTensor()*2-1 and the 64/32 targets are computed
@@ -649,11 +661,13 @@ class TPGANTrainer:
             self._init(G, D, B, exact, world_size, group, bucket_mb, identity_net)
 
     def _init(self, G, D, B, exact, world_size, group, bucket_mb, identity_net):
+        if self.g_bn:
+            self.flat_g = FlatParams(G)    # before tracing: the BatchNorm backward launches capture their .grad targets
         self._build_g()
         self.critic = CriticPlan(D, 3 * B, B, self.device, exact=exact, defer_pack=not exact, bf16=self.bf16)
         self.critic.build_g_phase(self.plan.grad_act(self.fake))
-        order = self._ready_order()
-        self.flat_g = FlatParams(G, order)
+        if not self.g_bn:
+            self.flat_g = FlatParams(G, self._ready_order())
         self.flat_d = FlatParams(D)
         adam = dict(lr=self.lr)      # torch.optim.Adam defaults otherwise, as FlatParams.adam
         self.optimizer_g, self.optimizer_d = FlatOptimizer(self.flat_g, G, "adam", adam), FlatOptimizer(self.flat_d, D, "adam", adam)
@@ -684,6 +698,7 @@ class TPGANTrainer:
     def _build_g(self):
         G, B, dev = self.G, self.B, self.device
         plan = Plan(dev, exact=self.exact, defer_bias=True, defer_pack=not self.exact, bf16=self.bf16)
+        plan.direct_grads = self.g_bn
         self.plan = plan
         gp = G.global_pathway
         bufs = gp.alloc_concats(plan, B)
@@ -863,9 +878,18 @@ class TPGANTrainer:
         else:
             for f in sch:
                 f()
+        if optimize or self.g_bn:
+            self.steps += 1      # generator forwards in training mode (BatchNorm statistics updates), see sync_buffers()
         if prefetch_next is not None:
             self.prefetch(prefetch_next)
         return self.read_metrics() if read_metrics else None
+
+    def sync_buffers(self):
+        """num_batches_tracked of the generator's BatchNorm layers (state_dict parity with nn.BatchNorm2d in train mode; the
+        running statistics themselves are updated in place by the forward kernels)."""
+        for m in self.G.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None:
+                m.num_batches_tracked.fill_(self.steps)
 
     def _allreduce(self, t: torch.Tensor):
         import torch.distributed as dist
