@@ -1241,8 +1241,7 @@ static int launch_wgrad(Params& P, cudaStream_t st, int bf16) {
   for (int i = 0; i < P.ngroups; ++i) slack = std::max(slack, MCH * P.g[i].mpu * P.g[i].kp * 128 - stage_bytes);
   slack = std::max(0, slack);
   const int budget = g_dev.max_smem - 1024 - 256 - slack;
-  static const int max_stages = [] { const char* ev = getenv("TPGAN_TAP_MAXSTAGES"); return ev ? std::max(2, std::min(kTapMaxStages, atoi(ev))) : kMaxStages; }();
-  P.stages = std::min(max_stages, budget / stage_bytes);
+  P.stages = std::min(kMaxStages, budget / stage_bytes);
   P.ring_bytes = P.stages * stage_bytes + slack;
   P.need_zero = 0;
   for (int i = 0; i < P.ngroups; ++i)
