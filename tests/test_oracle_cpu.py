@@ -199,3 +199,25 @@ def test_identity_modules_mirror_reference_interface():
         FeatureExtractModel("vgg")
     with pytest.raises(RuntimeError):
         net.eval()(torch.zeros(1, 3, 128, 128))   # CPU tensor: the product path has no CPU fallback
+
+
+@needs_ref
+def test_batchnorm_step_golden_is_the_live_reference():
+    """tests/golden/step_bn_golden.pt (the fused BatchNorm-generator step's fixture, tools/make_golden_bn_step.py) regenerated
+    in process from the live reference: Generator(use_batchnorm=True) + BatchNorm-free Discriminator, one oracle step."""
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "step_bn_golden.pt"), weights_only=False)
+    ns = reference.load()
+    torch.manual_seed(0)
+    G, D = ns.DG.Generator(64, 347, True, False), ns.DG.Discriminator(False)
+    G.train()
+    b = ostep.make_batch(2, seed=3)
+    m = ostep.train_step(lambda bb: G(bb["img"], bb["left_eye"], bb["right_eye"], bb["nose"], bb["mouth"], bb["z"], False), D,
+                         list(G.parameters()), list(D.parameters()), torch.optim.Adam(G.parameters(), lr=1e-4),
+                         torch.optim.Adam(D.parameters(), lr=1e-4), b, step_optim=False)
+    for k, v in gold["metrics"].items():
+        assert abs(m[k] - v) <= 1e-5 * abs(v) + 1e-6, (k, m[k], v)
+    sd = G.state_dict()
+    for k, v in gold["running"].items():
+        assert torch.allclose(sd[k], v, rtol=1e-5, atol=1e-7), k
+    for k, g in gold["bn_grads"].items():
+        assert torch.allclose(dict(G.named_parameters())[k].grad, g, rtol=1e-4, atol=1e-6), k
