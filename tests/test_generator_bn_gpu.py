@@ -136,16 +136,23 @@ def test_fused_step_with_batchnorm_generator_vs_live_reference_goldens(exact):
     assert math.sqrt(num / den) < 5e-2, math.sqrt(num / den)
 
 
-def test_fused_step_with_batchnorm_generator_trains_and_replays_as_graph():
-    """Three optimizer steps of the BatchNorm generator through CUDA graphs: finite losses, parameters and running statistics
-    move, the affine parameters of a BatchNorm layer receive Adam updates, num_batches_tracked follows the step count."""
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+def test_fused_step_with_batchnorm_generator_trains_and_replays_as_graph(dtype):
+    """Three optimizer steps of the BatchNorm generator through CUDA graphs (tf32 and bf16 operands - the BatchNorm kernels
+    read and write the fp32 copies, the engine re-casts their outputs for the tensor-core consumers): the first step's losses
+    within the format's sanity bound of the live-reference golden, finite losses, parameters and running statistics move, the
+    affine parameters of a BatchNorm layer receive Adam updates, num_batches_tracked follows the step count."""
     import tpgan_b200.D_and_G_model as M
     from oracle import step as ostep
     from tpgan_b200.train_step import TPGANTrainer
+    gold = torch.load(STEP_GOLD, weights_only=False)
     torch.manual_seed(0)
     G, D = M.Generator(64, 347, True, False).cuda(), M.Discriminator(False).cuda()
     B = 2
-    tr = TPGANTrainer(G, D, B, use_graphs=True)
+    tr = TPGANTrainer(G, D, B, use_graphs=True, dtype=dtype)
+    m0 = tr.step({k: v.cuda() for k, v in ostep.make_batch(B, seed=3).items()})
+    for k in ("pixel", "local", "symmetry", "tv", "ce", "g_total"):     # the terms that do not hinge on the critic's sign
+        assert abs(m0[k] - gold["metrics"][k]) <= 0.25 * abs(gold["metrics"][k]) + 1e-3, (k, m0[k], gold["metrics"][k])
     bn = G.global_pathway.conv0[0][1]
     w0, rm0 = bn.weight.detach().clone(), bn.running_mean.clone()
     for i in range(3):
@@ -153,6 +160,6 @@ def test_fused_step_with_batchnorm_generator_trains_and_replays_as_graph():
         m = tr.step(b)
         assert all(math.isfinite(v) for v in m.values()), m
     tr.sync_buffers()
-    assert int(bn.num_batches_tracked) == 3
+    assert int(bn.num_batches_tracked) == 4
     assert not torch.equal(bn.weight.detach(), w0) and not torch.equal(bn.running_mean, rm0)
     assert torch.isfinite(tr.flat_g.data).all()

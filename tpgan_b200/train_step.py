@@ -639,7 +639,6 @@ class TPGANTrainer:
         # place; one generator forward per step = one statistics update per step, as in the oracle step.
         self.g_bn = has_bn(G)
         if self.g_bn:
-            assert not self.bf16, "BatchNorm generators run in tf32 (or the exact verification mode)"
             G.train()
             self.overlap_allreduce = self.force_reducer = False   # one all-reduce after backward (no bucket order for BatchNorm)
         self.steps = 0
