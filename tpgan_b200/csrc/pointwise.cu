@@ -1100,7 +1100,6 @@ __global__ void __launch_bounds__(kPackThreads) pack_multi_kernel(const tpgan_pa
   extern __shared__ float srow[];
   const int ji = find_job(jobs, njobs, (int)blockIdx.x);
   const tpgan_pack_job J = jobs[ji];
-  {
   const int r = (int)blockIdx.x - J.block_begin;
   const int taps = J.taps;
   const int tstride = taps | 1;
@@ -1171,7 +1170,6 @@ __global__ void __launch_bounds__(kPackThreads) pack_multi_kernel(const tpgan_pa
         dst[i] = J.flag ? (dst[i] + v) : v;
       }
     }
-  }
   }
 }
 
